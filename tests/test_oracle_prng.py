@@ -1,0 +1,50 @@
+"""Known-answer tests pinning the oracle's PRNG restatement."""
+import numpy as np
+
+from oracle import prng
+
+
+def test_threefry2x32_random123_kats():
+    kats = [((0, 0, 0, 0), (0x6B200159, 0x99BA4EFE)),
+            ((0xFFFFFFFF,) * 4, (0x1CB996FC, 0xBB002BE7)),
+            ((0x13198A2E, 0x03707344, 0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for args, want in kats:
+        got = prng.threefry2x32(*args)
+        assert (int(got[0]), int(got[1])) == want
+
+
+def test_jax_split_and_fold_in_known_values():
+    """jax.random.split(key(0)) / fold_in(key(0), 1) with jax_threefry_partitionable=True."""
+    s = prng.split(prng.key(0))
+    assert s.tolist() == [[1797259609, 2579123966], [928981903, 3453687069]]
+    assert prng.fold_in(prng.key(0), 1).tolist() == [928981903, 3453687069]
+
+
+def test_uniform_and_normal_ranges_and_moments():
+    u = prng.uniform(prng.key(7), (1 << 16,))
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+    x = prng.normal(prng.key(42), (1 << 17,))
+    assert np.isfinite(x).all() and abs(x.mean()) < 1e-2 and abs(x.std() - 1) < 1e-2
+
+
+def test_erfinv_matches_float64():
+    from scipy.special import erfinv
+    u = np.linspace(-0.999999, 0.999999, 20001).astype(np.float32)
+    ref = erfinv(u.astype(np.float64))
+    assert np.max(np.abs(prng.erfinv_f32(u) - ref) / np.maximum(1, np.abs(ref))) < 1e-5
+
+
+def test_randint_range_and_permutation_is_a_permutation():
+    r = prng.randint(prng.key(1), (4096,), 0, 32)
+    assert r.min() == 0 and r.max() == 31
+    assert prng.permutation_rounds(1024) == 1 and prng.permutation_rounds(4096) == 2
+    for n in (1, 7, 256, 4096):
+        p = prng.permutation(prng.key(n), n)
+        assert sorted(p.tolist()) == list(range(n))
+
+
+def test_rngs_stream_counts():
+    r = prng.Rngs(0)
+    a, b = r(), r()
+    assert r.count == 2 and a.tolist() == prng.fold_in(prng.key(0), 0).tolist()
+    assert b.tolist() == prng.fold_in(prng.key(0), 1).tolist()

@@ -1,0 +1,223 @@
+/*
+ * b200ppo.h — C ABI of the B200-native PPO hot path (sm_100a).
+ *
+ * Drop-in boundary for the hot path of emiwar/nnx-ppo (reference v0.2.1).  The reference is pure
+ * Python/JAX and has no FFI seam of its own; each entry point below replaces the *computation* of
+ * the reference function cited next to it, and is what an XLA-FFI / ctypes binding for that
+ * function binds (see INTEGRATION.md for the reference-side stubs).
+ *
+ * Conventions (all entry points):
+ *   - plain C types only; every pointer marked "dev" is a device pointer owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; launchers never allocate, free or synchronise,
+ *     so they can be captured into a CUDA graph;
+ *   - return 0 on success, a negative B200PPO_E* code on invalid arguments, or a positive
+ *     cudaError_t value if a launch failed (b200ppo_error_string decodes all three);
+ *   - re-entrant: no global mutable state except one-time cudaFuncSetAttribute opt-ins.
+ *
+ * Layouts: everything is float32 row-major unless noted; rollout tensors are time-major
+ * [T][B][...] with B = number of envs on this rank; masks are uint8 (0/1); indices are int32.
+ */
+#ifndef B200PPO_H_
+#define B200PPO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PPO_MAX_LAYERS 8
+
+#define B200PPO_ACT_NONE 0
+#define B200PPO_ACT_RELU 1
+#define B200PPO_ACT_SWISH 2
+#define B200PPO_ACT_TANH 3
+
+#define B200PPO_EINVAL (-1)   /* bad shape / null pointer / unsupported plan            */
+#define B200PPO_ELIMIT (-2)   /* size exceeds a compiled-in limit       */
+#define B200PPO_EALIGN (-3)   /* pointer or offset not aligned as documented            */
+
+/* One stack of Dense layers (reference: networks/feedforward.py:13-51, factories.py:14-45):
+ * layer l computes z = h W_l + b_l with W_l [dims[l]][dims[l+1]] row-major at w_off[l] and b_l at
+ * b_off[l] (float offsets into the parameter arena, multiples of 4); hidden layers apply `act`,
+ * the last layer is linear. */
+typedef struct b200ppo_chain {
+  int32_t n_layers;
+  int32_t act;
+  int32_t dims[B200PPO_MAX_LAYERS + 1];
+  int32_t pad_;
+  int64_t w_off[B200PPO_MAX_LAYERS];
+  int64_t b_off[B200PPO_MAX_LAYERS];
+} b200ppo_chain;
+
+/* The network "plan": what make_mlp_actor_critic builds (reference: networks/factories.py:72-146):
+ * Normalizer? -> PPOAdapter(action = actor MLP + NormalTanhSampler, value = critic MLP). */
+typedef struct b200ppo_plan {
+  int32_t obs_dim;
+  int32_t act_dim;
+  int32_t normalize;        /* 1 if a Normalizer precedes the adapter                      */
+  int32_t pad_;
+  float entropy_weight;     /* NormalTanhSampler args, sampling_layers.py:69-80            */
+  float min_std;
+  float std_scale;
+  float pad2_;
+  int64_t n_params;         /* arena length in floats (including alignment padding)       */
+  b200ppo_chain actor;      /* out = 2 * act_dim                                           */
+  b200ppo_chain critic;     /* out = 1                                                     */
+} b200ppo_plan;
+
+/* Hyper-parameters of one minibatch update (reference: PPOConfig, algorithms/config.py:11-30). */
+typedef struct b200ppo_hparams {
+  float gamma;              /* discounting_factor */
+  float lambda_;            /* gae_lambda         */
+  float clip_range;
+  float critic_loss_weight;
+  float learning_rate;
+  float adam_b1, adam_b2, adam_eps;
+  float weight_decay;       /* < 0: plain adam; >= 0: adamw with this decay               */
+  float grad_clip;          /* <= 0: no clip_by_global_norm                               */
+  int32_t normalize_advantages;
+  int32_t world_size;       /* data-parallel ranks sharing this update (means are global) */
+} b200ppo_hparams;
+
+/* Device buffers of one minibatch update.  ws is a scratch arena of
+ * b200ppo_update_workspace_bytes() bytes, 256-byte aligned. */
+typedef struct b200ppo_update_bufs {
+  /* rollout buffer, time-major over the B envs of this rank */
+  const float* obs;            /* dev [T][B][O]  raw observations (Normalizer rollout_extras)    */
+  const float* raw_action;     /* dev [T][B][A]  sampler rollout_extras                           */
+  const float* loglik_old;     /* dev [T][B]                                                       */
+  const float* reward;         /* dev [T][B]                                                       */
+  const uint8_t* done;         /* dev [T][B]                                                       */
+  const uint8_t* truncated;    /* dev [T][B]                                                       */
+  const float* next_obs_last;  /* dev [B][O]     next_obs[-1] (ppo.py:433)                         */
+  const int32_t* inds;         /* dev [mb]       env indices of this minibatch (ppo.py:297)        */
+  /* normalizer (read-only during updates) */
+  const float* norm_mean;      /* dev [O]                                                          */
+  const float* norm_std;       /* dev [O]  from b200ppo_norm_prepare                               */
+  /* parameters and optimizer state (updated in place) */
+  float* params;               /* dev [P]                                                          */
+  float* adam_mu;              /* dev [P]                                                          */
+  float* adam_nu;              /* dev [P]                                                          */
+  /* counters: [0..1] sampler stream key, [2] sampler count base, [3] adam count base */
+  const uint32_t* rng_state;   /* dev uint32[4]                                                    */
+  float* metrics_out;          /* dev [4]: actor loss, critic loss, regularisation loss, grad norm */
+  void* ws;                    /* dev scratch                                                      */
+} b200ppo_update_bufs;
+
+/* -------- library -------------------------------------------------------------------------- */
+int b200ppo_version(void);
+const char* b200ppo_error_string(int code);
+int b200ppo_num_sms(void);
+
+/* -------- K7: threefry device functions, exposed for parity tests -------------------------- *
+ * jax.random.bits / normal / randint over a flat shape (n,) from a key held by value.          */
+int b200ppo_random_bits(void* stream, uint32_t k0, uint32_t k1, int64_t n, uint32_t* out /*dev*/);
+int b200ppo_random_normal(void* stream, uint32_t k0, uint32_t k1, int64_t n, float* out /*dev*/);
+
+/* -------- K6: minibatch permutation indices (ppo.py:287-294) ------------------------------- *
+ * out[e][:] = jax.random.permutation(fold_in(new_key, e), n) for e < n_epochs, bit-exact.      *
+ * new_key: dev uint32[2].  scratch: dev, b200ppo_permutation_scratch_bytes(n, n_epochs) bytes. */
+int64_t b200ppo_permutation_scratch_bytes(int32_t n, int32_t n_epochs);
+int b200ppo_permutation(void* stream, const uint32_t* new_key /*dev*/, int32_t n, int32_t n_epochs,
+                        int32_t* out /*dev [n_epochs][n]*/, void* scratch /*dev*/);
+
+/* -------- K2: generalised advantage estimation (ppo.py:351-394) ---------------------------- */
+int b200ppo_gae(void* stream, const float* rewards /*dev [T][B]*/,
+                const float* values_excl_last /*dev [T][B]*/, const float* last_value /*dev [B]*/,
+                const uint8_t* done /*dev [T][B]*/, const uint8_t* truncation /*dev [T][B]*/,
+                int32_t T, int32_t B, float lambda_, float gamma, float* advantages /*dev [T][B]*/);
+
+/* -------- K5: Normalizer (normalizer.py:63-136) -------------------------------------------- *
+ * norm_prepare : std[o] = counter > 0 ? sqrt(max(M2/counter, 1e-6)) : 10                        *
+ * norm_batch_stats: batch mean / M2 of x[n_rows][O] -> batch_stats[2*O] (two-pass, fp32)        *
+ * norm_merge   : Chan-merge `world` batch statistics (rank order) into (mean, M2, counter)      */
+int b200ppo_norm_prepare(void* stream, const float* M2 /*dev [O]*/, const float* counter /*dev [1]*/,
+                         int32_t O, float* std_out /*dev [O]*/);
+int64_t b200ppo_norm_scratch_bytes(int32_t O);
+int b200ppo_norm_batch_stats(void* stream, const float* x /*dev [n_rows][O]*/, int64_t n_rows,
+                             int32_t O, float* batch_stats /*dev [2*O]*/, void* scratch /*dev*/);
+int b200ppo_norm_merge(void* stream, const float* batch_stats /*dev [world][2*O]*/,
+                       int32_t world, float n_per_rank, int32_t O, float* mean /*dev [O]*/,
+                       float* M2 /*dev [O]*/, float* counter /*dev [1]*/);
+
+/* -------- K1: policy step (rollout.py:18; sampling_layers.py:82-113; adapter.py:75-117) ----- *
+ * One network call on B rows: normalize -> actor -> NormalTanhSampler -> critic.                *
+ * mode 0: sample (rollout_extras=None); 1: replay raw_action_in; |2: deterministic (mean).      *
+ * count_offset is added to rng_state[2]; the call consumes 2 counts (1 if deterministic).       */
+int64_t b200ppo_policy_workspace_bytes(const b200ppo_plan* plan, int32_t B);
+int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const float* params /*dev*/,
+                        const float* norm_mean /*dev*/, const float* norm_std /*dev*/,
+                        const float* obs /*dev [B][O]*/, int32_t B, int32_t mode,
+                        const uint32_t* rng_state /*dev*/, uint32_t count_offset,
+                        const float* raw_action_in /*dev [B][A] or NULL*/,
+                        float* raw_action /*dev [B][A]*/, float* action /*dev [B][A]*/,
+                        float* loglik /*dev [B]*/, float* value /*dev [B]*/,
+                        float* reg_loss /*dev [B] or NULL*/, void* ws /*dev*/);
+
+/* -------- K1 (persistent): fused T-step rollout on the synthetic env (rollout.py:11-73) ---- *
+ * env state (in/out): obs [B][O], step_counter int32 [B], term_state uint32 [B].                *
+ * iter_keys: dev uint32[4] = reset_key, new_key (ppo.py:271).  Advances nothing on its own;     *
+ * consumes sampler counts rng_state[2] + 2t, +2t+1 for t < T.                                   */
+typedef struct b200ppo_synth_env {
+  int32_t obs_dim, act_dim, max_len, term_thresh16;
+  const float* Wo;             /* dev [O][O] */
+  const float* Wa;             /* dev [A][O] */
+} b200ppo_synth_env;
+
+int b200ppo_synth_reset(void* stream, const b200ppo_synth_env* env, const uint32_t* keys /*dev [B][2]*/,
+                        int32_t B, float* obs, int32_t* step_counter, uint32_t* term_state);
+int b200ppo_synth_init_keys(void* stream, uint32_t k0, uint32_t k1, int32_t B, uint32_t* keys_out);
+int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                          const float* params /*dev*/, const float* norm_mean, const float* norm_std,
+                          const uint32_t* rng_state /*dev*/, const uint32_t* iter_keys /*dev*/,
+                          int32_t T, int32_t B,
+                          float* env_obs /*dev [B][O] in/out*/, int32_t* env_counter /*dev [B]*/,
+                          uint32_t* env_term /*dev [B]*/,
+                          float* obs /*dev [T][B][O]*/, float* raw_action /*dev [T][B][A]*/,
+                          float* action /*dev [T][B][A]*/, float* loglik /*dev [T][B]*/,
+                          float* reward /*dev [T][B]*/, uint8_t* done /*dev [T][B]*/,
+                          uint8_t* truncated /*dev [T][B]*/, float* next_obs_last /*dev [B][O]*/);
+
+/* -------- K3 + K4: one minibatch update (ppo.py:296-317 update_step, 397-531 ppo_loss) ------ *
+ * Stages (bit mask, launched in this order):                                                    *
+ *   FWD   critic+actor forward over the gathered minibatch (+ bootstrap rows)                   *
+ *   GAE   per-env reverse scan from the fresh values, advantage moment sums -> adv_sums          *
+ *   LOSS  clipped surrogate / value / entropy terms and their gradients w.r.t. network outputs  *
+ *   BWD   backward through both MLPs (dX chain, then dW split over row ranges)                  *
+ *   RED   reduce dW partials to the flat gradient (b200ppo_update_grad_ptr) + its squared norm  *
+ *   ADAM  optax adam / adamw (+ clip_by_global_norm) from the flat gradient                     *
+ * A data-parallel caller all-reduces adv_sums after GAE and the flat gradient after RED.        *
+ * update_index selects the sampler count offset (2*(T+1) per update after the 2*T of the        *
+ * rollout) and the adam step (rng_state[3] + update_index + 1).                                 */
+#define B200PPO_STAGE_FWD 1
+#define B200PPO_STAGE_GAE 2
+#define B200PPO_STAGE_LOSS 4
+#define B200PPO_STAGE_BWD 8
+#define B200PPO_STAGE_RED 16
+#define B200PPO_STAGE_ADAM 32
+#define B200PPO_STAGE_ALL 63
+
+int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb);
+int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,
+                   const b200ppo_update_bufs* bufs, int32_t T, int32_t B, int32_t mb,
+                   uint32_t rng_count_offset, int32_t update_index, int32_t stages);
+/* Pointers into the workspace that a data-parallel caller reduces across ranks. */
+double* b200ppo_update_adv_sums_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws);
+float* b200ppo_update_grad_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws);
+/* Debug / parity views into the workspace (after the corresponding stage has run). */
+float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws,
+                                int32_t which /*0 adv, 1 values, 2 actor out, 3 d_y, 4 d_v*/);
+
+/* End-of-iteration bookkeeping: rng_state[2] += rng_advance; rng_state[3] += adam_advance. */
+int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rng_advance,
+                          uint32_t adam_advance);
+
+/* -------- measurement helper: register-resident FFMA loop (fp32 CUDA-core peak) ------------ */
+int b200ppo_ffma_peak(void* stream, int32_t iters, float* sink /*dev [blocks*threads]*/,
+                      int32_t blocks, int32_t threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PPO_H_ */

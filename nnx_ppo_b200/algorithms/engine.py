@@ -1,0 +1,241 @@
+"""Device engine for one PPO iteration (the body of the reference's jitted ``ppo_step``,
+ppo.py:254-348) as a fixed launch sequence over preallocated HBM buffers:
+
+    norm_prepare -> fused T-step rollout -> permutation indices -> E*M x update
+    (FWD, GAE, LOSS, BWD, RED, ADAM) -> Normalizer batch statistics + merge -> counters
+
+The sequence is captured once into a CUDA graph and replayed per iteration (the reference relies
+on XLA's jit for the same purpose).  Per-iteration inputs (the two PRNG keys of ppo.py:271) are
+copied from pinned host memory into a 16-byte device block that the kernels read, so the graph
+never needs re-capturing.  With world_size > 1 every rank runs the same sequence on its own env
+shard and two NCCL all-reduces per update (advantage moment sums, flat gradient) plus one
+all-gather per iteration (Normalizer batch statistics) keep the ranks in lock step.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .. import _lib
+from ..networks.plan import CompiledNet
+
+
+class AdamOptimizer:
+    """State of ``nnx.Optimizer(networks, optax.chain([clip?], adam|adamw))`` — ppo.py:555-569.
+    ``mu`` / ``nu`` are flat device arenas parallel to the parameter arena."""
+
+    def __init__(self, net: CompiledNet, learning_rate: float = 1e-4,
+                 gradient_clipping: Optional[float] = None, weight_decay=None,
+                 b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        import torch
+        self.net = net
+        self.learning_rate = float(learning_rate)
+        self.gradient_clipping = gradient_clipping
+        self.weight_decay = weight_decay
+        self.b1, self.b2, self.eps = b1, b2, eps
+        self.mu = torch.zeros(net.n_params, dtype=torch.float32, device=net.device)
+        self.nu = torch.zeros(net.n_params, dtype=torch.float32, device=net.device)
+        self.step = 0   # host mirror of counters[3]
+
+    @property
+    def wd_value(self) -> float:
+        if self.weight_decay is None:
+            return -1.0
+        if isinstance(self.weight_decay, bool):
+            return 1e-4 if self.weight_decay else -1.0   # optax.adamw default decay
+        return float(self.weight_decay)
+
+
+class PPOEngine:
+    def __init__(self, net: CompiledNet, env, opt: AdamOptimizer, n_envs: int, rollout_length: int,
+                 n_epochs: int, n_minibatches: int, gae_lambda: float, discounting_factor: float,
+                 clip_range: float, normalize_advantages: bool, critic_loss_weight: float,
+                 world_size: int = 1, group=None, use_graph: Optional[bool] = None):
+        import torch
+        if not getattr(env, "fused_rollout", False):
+            raise NotImplementedError("PPOEngine needs a device env with a fused rollout kernel")
+        if n_envs % n_minibatches:
+            raise ValueError("n_envs must be divisible by n_minibatches (ppo.py:285-290 reshape)")
+        self.lib = _lib.load()
+        self.net, self.env, self.opt = net, env, opt
+        self.B, self.T, self.E, self.M = n_envs, rollout_length, n_epochs, n_minibatches
+        self.mb = n_envs // n_minibatches
+        self.world, self.group = int(world_size), group
+        dev = net.device
+        self.dev = dev
+        O, A, T, B = net.plan.obs_dim, net.plan.act_dim, self.T, self.B
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.obs = torch.zeros(T, B, O, **f32)
+        self.raw_action = torch.zeros(T, B, A, **f32)
+        self.action = torch.zeros(T, B, A, **f32)
+        self.loglik = torch.zeros(T, B, **f32)
+        self.reward = torch.zeros(T, B, **f32)
+        self.done = torch.zeros(T, B, dtype=torch.uint8, device=dev)
+        self.trunc = torch.zeros(T, B, dtype=torch.uint8, device=dev)
+        self.next_obs_last = torch.zeros(B, O, **f32)
+        self.inds = torch.zeros(self.E, B, dtype=torch.int32, device=dev)
+        self.perm_scratch = torch.zeros(int(self.lib.b200ppo_permutation_scratch_bytes(B, self.E)) // 4 + 64,
+                                        dtype=torch.int32, device=dev)
+        ws_bytes = int(self.lib.b200ppo_update_workspace_bytes(net.plan, T, self.mb))
+        if ws_bytes <= 0:
+            raise _lib.B200PPOError("update_workspace_bytes rejected the plan")
+        # zero-initialised: tickets and the alignment padding of the gradient arena rely on it
+        self.ws = torch.zeros(ws_bytes // 4, **f32)
+        self.n_updates = self.E * self.M
+        self.metrics = torch.zeros(self.n_updates, 4, **f32)
+        self.metrics_host = torch.zeros(self.n_updates, 4, dtype=torch.float32).pin_memory()
+        self.iter_keys = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.iter_keys_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.norm_scratch = torch.zeros(int(self.lib.b200ppo_norm_scratch_bytes(O)) // 4 + 64, **f32)
+        self.batch_stats = torch.zeros(2 * O, **f32)
+        self.batch_stats_all = torch.zeros(self.world, 2 * O, **f32)
+        wsp = self.ws.data_ptr()
+        adv_p = self.lib.b200ppo_update_adv_sums_ptr(net.plan, T, self.mb, wsp)
+        grad_p = self.lib.b200ppo_update_grad_ptr(net.plan, T, self.mb, wsp)
+        ao, go = (adv_p - wsp) // 4, (grad_p - wsp) // 4
+        self.adv_sums = self.ws[ao:ao + 4].view(torch.float64)
+        self.grad = self.ws[go:go + net.n_params]
+        self.hp = _lib.HParams()
+        self.hp.gamma, self.hp.lambda_ = float(discounting_factor), float(gae_lambda)
+        self.hp.clip_range, self.hp.critic_loss_weight = float(clip_range), float(critic_loss_weight)
+        self.hp.learning_rate = opt.learning_rate
+        self.hp.adam_b1, self.hp.adam_b2, self.hp.adam_eps = opt.b1, opt.b2, opt.eps
+        self.hp.weight_decay = opt.wd_value
+        self.hp.grad_clip = float(opt.gradient_clipping) if opt.gradient_clipping is not None else -1.0
+        self.hp.normalize_advantages = 1 if normalize_advantages else 0
+        self.hp.world_size = self.world
+        self.bufs = []
+        for u in range(self.n_updates):
+            b = _lib.UpdateBufs()
+            b.obs, b.raw_action, b.loglik_old = self.obs.data_ptr(), self.raw_action.data_ptr(), self.loglik.data_ptr()
+            b.reward, b.done, b.truncated = self.reward.data_ptr(), self.done.data_ptr(), self.trunc.data_ptr()
+            b.next_obs_last = self.next_obs_last.data_ptr()
+            b.inds = self.inds.data_ptr() + 4 * u * self.mb        # [E*M][mb] view of [E][B]
+            b.norm_mean, b.norm_std = net.norm_ptrs()
+            b.params, b.adam_mu, b.adam_nu = net.arena.data_ptr(), opt.mu.data_ptr(), opt.nu.data_ptr()
+            b.rng_state = net.counters.data_ptr()
+            b.metrics_out = self.metrics.data_ptr() + 16 * u
+            b.ws = wsp
+            self.bufs.append(b)
+        self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
+        if use_graph is None:
+            use_graph = os.environ.get("B200PPO_GRAPH", "1") != "0"
+        self.use_graph = use_graph
+        self.graph = None
+        self.iters_run = 0
+        self.kernel_launches_per_iter = 0
+        self._env_state = None
+
+    # ------------------------------------------------------------------------------------
+    def _allreduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
+
+    def _enqueue(self, env_state) -> int:
+        """Enqueue one whole iteration on the current stream.  Returns the number of kernel
+        launches issued by this library (NCCL kernels not counted)."""
+        n = self._enqueue_rollout(env_state)
+        n += self._enqueue_updates(2 * self.T, self.rng_per_iter)
+        return n
+
+    def _enqueue_rollout(self, env_state) -> int:
+        lib, net, T, B = self.lib, self.net, self.T, self.B
+        s = _lib.current_stream()
+        n = 0
+        if net.normalizer is not None:
+            net.normalizer.prepare(s); n += 1
+        mean_p, std_p = net.norm_ptrs()
+        es = self.env.c_struct(self.dev)
+        _lib.check(lib.b200ppo_rollout_synth(
+            s, net.plan, es, net.arena.data_ptr(), mean_p, std_p, net.counters.data_ptr(),
+            self.iter_keys.data_ptr(), T, B, env_state.obs.data_ptr(), env_state.step_counter.data_ptr(),
+            env_state.term_state.data_ptr(), self.obs.data_ptr(), self.raw_action.data_ptr(),
+            self.action.data_ptr(), self.loglik.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+            self.trunc.data_ptr(), self.next_obs_last.data_ptr()), "rollout_synth"); n += 1
+        return n
+
+    def _enqueue_updates(self, rng_offset0: int, rng_advance: int) -> int:
+        """Permutation indices, the E*M minibatch updates, Normalizer statistics, counters.
+        ``rng_offset0`` = sampler counts already consumed since counters[2] was last advanced."""
+        lib, net, T, B = self.lib, self.net, self.T, self.B
+        s = _lib.current_stream()
+        n = 0
+        _lib.check(lib.b200ppo_permutation(s, self.iter_keys.data_ptr() + 8, B, self.E, self.inds.data_ptr(),
+                                           self.perm_scratch.data_ptr()), "permutation"); n += 1
+        clip_launch = 1 if self.hp.grad_clip > 0 else 0
+        for u in range(self.n_updates):
+            off = rng_offset0 + u * 2 * (T + 1)
+            args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
+            if self.world == 1:
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL), "update")
+            else:
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE), "update/fwd")
+                if self.hp.normalize_advantages:
+                    self._allreduce(self.adv_sums)
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")
+                self._allreduce(self.grad)
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ADAM), "update/adam")
+            n += 7 + clip_launch
+        if self.world > 1:
+            self._allreduce(self.metrics)
+        if net.normalizer is not None:
+            nz = net.normalizer
+            _lib.check(lib.b200ppo_norm_batch_stats(s, self.obs.data_ptr(), T * B, nz.size,
+                                                    self.batch_stats.data_ptr(), self.norm_scratch.data_ptr()),
+                       "norm_batch_stats"); n += 2
+            src = self.batch_stats
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.batch_stats_all, self.batch_stats, group=self.group)
+                src = self.batch_stats_all
+            _lib.check(lib.b200ppo_norm_merge(s, src.data_ptr(), self.world, float(T * B), nz.size,
+                                              nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),
+                                              nz.counter._dev.data_ptr()), "norm_merge"); n += 1
+        _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), rng_advance, self.n_updates),
+                   "iter_finalize"); n += 1
+        return n
+
+    def step(self, env_state, reset_key, new_key, fetch_metrics: bool = True):
+        """Run one iteration.  ``reset_key, new_key = split(rng_key)`` (ppo.py:271) come from the
+        host; everything else stays on the device.  Asynchronous unless ``fetch_metrics``."""
+        import torch
+        k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
+        self.iter_keys_host.numpy()[:] = k
+        self.iter_keys.copy_(self.iter_keys_host, non_blocking=True)
+        if self._env_state is not None and env_state is not self._env_state and self.graph is not None:
+            # a different env-state object: the captured graph points at the old tensors
+            self._env_state.obs.copy_(env_state.obs)
+            self._env_state.step_counter.copy_(env_state.step_counter)
+            self._env_state.term_state.copy_(env_state.term_state)
+            env_state = self._env_state
+        if self.iters_run == 0:
+            self.net.adam_step = self.opt.step
+            self.net.sync_counters_to_device()
+        if not self.use_graph or self.iters_run == 0:
+            self.kernel_launches_per_iter = self._enqueue(env_state)
+        else:
+            if self.graph is None:
+                self._env_state = env_state
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue(env_state)
+                self.graph = g
+            self.graph.replay()
+        self.iters_run += 1
+        self.net.advance_rng(self.rng_per_iter)
+        self.opt.step += self.n_updates
+        self.net.adam_step = self.opt.step
+        if fetch_metrics:
+            self.metrics_host.copy_(self.metrics, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return self.metrics_host.numpy().copy()
+        return None
+
+    def h2d_bytes_per_step(self) -> int:
+        return 16
+
+    def d2h_bytes_per_step(self) -> int:
+        return self.n_updates * 16

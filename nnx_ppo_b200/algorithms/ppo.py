@@ -1,0 +1,224 @@
+"""PPO driver — same public API as nnx_ppo/algorithms/ppo.py (``train_ppo`` :41, ``ppo_step``
+:254, ``gae`` :351, ``new_training_state`` :534, ``default_config`` :29, ``_should_run`` :34),
+with the jitted device program replaced by the CUDA engine (algorithms/engine.py).
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from collections.abc import Callable
+from typing import Any, Optional
+
+import numpy as np
+
+from .. import _lib, prng
+from ..networks.plan import compile_network
+from ..networks.types import StatefulModule
+from . import rollout
+from .config import EvalConfig, PPOConfig, TrainConfig, TrainResult, VideoConfig, VideoData  # noqa: F401
+from .engine import AdamOptimizer, PPOEngine
+from .types import LoggingLevel, RLEnv, TrainingState
+
+
+def default_config() -> TrainConfig:
+    return TrainConfig()
+
+
+def _should_run(steps: int, last_step: int, every_steps: int) -> bool:
+    if every_steps <= 0:
+        return False
+    return (steps // every_steps) > (last_step // every_steps)
+
+
+def _dist_info():
+    """(world_size, process_group) when torch.distributed is initialised, else (1, None)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), None
+    except Exception:
+        pass
+    return 1, None
+
+
+def new_training_state(env: RLEnv, networks: StatefulModule, n_envs: int, seed: int,
+                       learning_rate: float = 1e-4, gradient_clipping: Optional[float] = None,
+                       weight_decay: Optional[float] = None) -> TrainingState:
+    """ppo.py:534-572.  Under torch.distributed every rank is an independent replica of this
+    function on its own env shard: rank r folds r into the seed-derived keys (rank 0 is
+    bit-identical to a single-process run)."""
+    net = compile_network(networks)
+    key = prng.key(seed)
+    key, training_key = prng.split(key)                                  # ppo.py:544-545
+    world, _ = _dist_info()
+    if world > 1:
+        import torch.distributed as dist
+        r = dist.get_rank()
+        if r > 0:
+            key, training_key = prng.fold_in(key, r), prng.fold_in(training_key, r)
+    if getattr(env, "fused_rollout", False):
+        env_states = env.reset_from_split(key, n_envs, net.device)       # ppo.py:548-549
+    else:
+        env_states = rollout.reset_envs(env, key, n_envs, net.device)
+    network_states = networks.initialize_state(n_envs)                   # ppo.py:552
+    optimizer = AdamOptimizer(net, learning_rate, gradient_clipping, weight_decay)
+    return TrainingState(networks, network_states, env_states, optimizer, training_key,
+                         np.float32(0.0))
+
+
+def _engine_for(env, training_state: TrainingState, n_envs, rollout_length, gae_lambda,
+                discounting_factor, clip_range, normalize_advantages, n_epochs, n_minibatches,
+                critic_loss_weight) -> PPOEngine:
+    net = compile_network(training_state.networks)
+    opt: AdamOptimizer = training_state.optimizer
+    world, group = _dist_info()
+    key = (id(env), id(opt), n_envs, rollout_length, float(gae_lambda), float(discounting_factor),
+           float(clip_range), bool(normalize_advantages), n_epochs, n_minibatches,
+           float(critic_loss_weight), opt.learning_rate, opt.gradient_clipping, opt.wd_value, world)
+    eng = net.engines.get(key)
+    if eng is None:
+        eng = PPOEngine(net, env, opt, n_envs, rollout_length, n_epochs, n_minibatches, gae_lambda,
+                        discounting_factor, clip_range, normalize_advantages, critic_loss_weight,
+                        world_size=world, group=group)
+        net.engines[key] = eng
+    return eng
+
+
+def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_length: int,
+             gae_lambda, discounting_factor, clip_range, normalize_advantages: bool,
+             combine_advantages: bool, n_epochs: int, n_minibatches: int,
+             critic_loss_weight=1.0, logging_level: LoggingLevel = LoggingLevel.LOSSES,
+             logging_percentiles: Optional[tuple[int, ...]] = None
+             ) -> tuple[TrainingState, dict[str, Any]]:
+    """One PPO iteration (ppo.py:254-348).  The input state is consumed: env state, parameters,
+    optimizer moments and Normalizer statistics are updated in place on the device."""
+    if combine_advantages:
+        raise NotImplementedError("combine_advantages needs dict rewards; single scalar reward only")
+    if not getattr(env, "fused_rollout", False):
+        return rollout.ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda,
+                                        discounting_factor, clip_range, normalize_advantages,
+                                        n_epochs, n_minibatches, critic_loss_weight, logging_level,
+                                        logging_percentiles)
+    eng = _engine_for(env, training_state, n_envs, rollout_length, gae_lambda, discounting_factor,
+                      clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight)
+    reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
+    per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
+    total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
+    metrics = _loss_metrics(per_update, logging_level, logging_percentiles)
+    metrics["total_steps"] = total_steps                                 # ppo.py:333
+    new_state = training_state.replace(rng_key=new_key, steps_taken=total_steps)
+    return new_state, metrics
+
+
+def _loss_metrics(per_update: np.ndarray, logging_level, percentiles) -> dict[str, Any]:
+    """metrics.py:17-100 for the ``losses/*`` keys (mean / std or percentiles over the updates)."""
+    m: dict[str, Any] = {}
+    if LoggingLevel.LOSSES in logging_level:
+        for i, name in enumerate(("losses/actor", "losses/critic", "losses/regularization")):
+            x = per_update[:, i]
+            if percentiles:
+                for pl, p in zip(percentiles, np.percentile(x, percentiles)):
+                    m[f"{name}/p{int(pl)}"] = np.float32(p)
+            else:
+                m[f"{name}/mean"] = x.mean(dtype=np.float32)
+                m[f"{name}/std"] = x.std(dtype=np.float32)
+    return m
+
+
+def gae(rewards, values_excl_last, last_value, done, truncation, lambda_, gamma):
+    """ppo.py:351-394 on CUDA tensors: [T, B] float32 rewards / values, [B] last_value,
+    [T, B] bool done / truncation -> [T, B] advantages (K2, csrc/misc.cu)."""
+    import torch
+    lib = _lib.load()
+    T, B = rewards.shape
+    r = rewards.contiguous().float()
+    v = values_excl_last.contiguous().float()
+    lv = last_value.contiguous().float()
+    d = done.to(torch.uint8).contiguous()
+    tr = truncation.to(torch.uint8).contiguous()
+    _lib.require_cuda(r, v, lv, d, tr)
+    out = torch.empty_like(r)
+    _lib.check(lib.b200ppo_gae(_lib.current_stream(), _lib.ptr(r), _lib.ptr(v), _lib.ptr(lv), _lib.ptr(d),
+                               _lib.ptr(tr), T, B, float(lambda_), float(gamma), _lib.ptr(out)), "gae")
+    return out
+
+
+def train_ppo(env: RLEnv, networks: StatefulModule, config: Optional[TrainConfig] = None, *,
+              total_steps: Optional[int] = None, seed: Optional[int] = None,
+              log_fn: Optional[Callable[[dict[str, Any], int], None]] = None,
+              video_fn: Optional[Callable[[VideoData], None]] = None,
+              checkpoint_fn: Optional[Callable[[TrainingState, int], None]] = None,
+              eval_env: Optional[RLEnv] = None,
+              initial_state: Optional[TrainingState] = None) -> TrainResult:
+    """Train a PPO agent — host loop of ppo.py:41-251 (same cadence rules for eval / checkpoint /
+    logging; video rendering is out of scope and ignored)."""
+    if config is None:
+        config = default_config()
+    if total_steps is not None:
+        config = dataclasses.replace(config, ppo=dataclasses.replace(config.ppo, total_steps=total_steps))
+    if seed is not None:
+        config = dataclasses.replace(config, seed=seed)
+    if eval_env is None:
+        eval_env = env
+    if initial_state is None:
+        training_state = new_training_state(env, networks, config.ppo.n_envs, config.seed,
+                                            config.ppo.learning_rate, config.ppo.gradient_clipping,
+                                            config.ppo.weight_decay)
+    else:
+        training_state = initial_state
+
+    eval_history: list[dict[str, Any]] = []
+    last_eval_step = -config.eval.every_steps
+    last_checkpoint_step = -config.checkpoint_every_steps
+    metrics: dict[str, Any] = {}
+    n_iterations = 0
+    measure_throughput = LoggingLevel.THROUGHPUT in config.ppo.logging_level
+
+    def run_eval(steps: int) -> dict[str, Any]:
+        networks.eval()
+        t0 = time.perf_counter() if measure_throughput else None
+        em = rollout.eval_rollout(eval_env, networks, config.eval.n_envs, config.eval.max_episode_length,
+                                  prng.key(config.seed), config.eval.logging_percentiles)
+        if measure_throughput:
+            em["throughput/eval_sps"] = (config.eval.n_envs * config.eval.max_episode_length
+                                         / (time.perf_counter() - t0))
+        networks.train()
+        return dict(em)
+
+    steps = int(training_state.steps_taken)
+    if config.eval.enabled:
+        em = run_eval(steps)
+        metrics.update(em)
+        eval_history.append({"step": steps, **em})
+        last_eval_step = steps
+    if checkpoint_fn is not None and _should_run(steps, last_checkpoint_step, config.checkpoint_every_steps):
+        checkpoint_fn(training_state, steps)
+        last_checkpoint_step = steps
+    if log_fn is not None and metrics:
+        log_fn(metrics, steps)
+
+    while int(training_state.steps_taken) < config.ppo.total_steps:
+        t0 = time.perf_counter() if measure_throughput else None
+        training_state, metrics = ppo_step(
+            env, training_state, config.ppo.n_envs, config.ppo.rollout_length, config.ppo.gae_lambda,
+            config.ppo.discounting_factor, config.ppo.clip_range, config.ppo.normalize_advantages,
+            config.ppo.combine_advantages, config.ppo.n_epochs, config.ppo.n_minibatches,
+            config.ppo.critic_loss_weight, config.ppo.logging_level, config.ppo.logging_percentiles)
+        n_iterations += 1
+        steps = int(training_state.steps_taken)          # ppo_step already synchronised on the metrics
+        if measure_throughput:
+            metrics["throughput/train_sps"] = (config.ppo.n_envs * config.ppo.rollout_length
+                                               / (time.perf_counter() - t0))
+        if config.eval.enabled and _should_run(steps, last_eval_step, config.eval.every_steps):
+            em = run_eval(steps)
+            metrics.update(em)
+            eval_history.append({"step": steps, **em})
+            last_eval_step = steps
+        if checkpoint_fn is not None and _should_run(steps, last_checkpoint_step, config.checkpoint_every_steps):
+            checkpoint_fn(training_state, steps)
+            last_checkpoint_step = steps
+        if log_fn is not None:
+            log_fn(metrics, steps)
+
+    return TrainResult(training_state=training_state, final_metrics=metrics, eval_history=eval_history,
+                       total_steps=int(training_state.steps_taken), total_iterations=n_iterations)

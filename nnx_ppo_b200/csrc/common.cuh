@@ -1,0 +1,159 @@
+// Shared device helpers for the B200 PPO kernels: threefry2x32 + JAX random transforms,
+// activation / sampler math, small reductions.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200ppo.h"
+
+#define B200PPO_LAUNCH_CHECK()                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return static_cast<int>(e__);        \
+  } while (0)
+
+namespace b200ppo {
+
+// ------------------------------------------------------------------------------------------
+// threefry2x32 (20 rounds) — jax/_src/prng.py; reference call sites ppo.py:271,288-289,
+// rollout.py:57-59, sampling_layers.py:96,144.  Bit-exact integer work.
+// ------------------------------------------------------------------------------------------
+struct Key {
+  uint32_t a, b;
+};
+
+__host__ __device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) {
+  return (x << r) | (x >> (32 - r));
+}
+
+__host__ __device__ __forceinline__ Key threefry2x32(Key k, uint32_t x0, uint32_t x1) {
+  const uint32_t ks0 = k.a, ks1 = k.b, ks2 = k.a ^ k.b ^ 0x1BD11BDAu;
+  x0 += ks0;
+  x1 += ks1;
+#define TF_ROUND(r) \
+  x0 += x1;         \
+  x1 = rotl32(x1, r); \
+  x1 ^= x0;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += ks1; x1 += ks2 + 1u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += ks2; x1 += ks0 + 2u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += ks0; x1 += ks1 + 3u;
+  TF_ROUND(17) TF_ROUND(29) TF_ROUND(16) TF_ROUND(24)
+  x0 += ks1; x1 += ks2 + 4u;
+  TF_ROUND(13) TF_ROUND(15) TF_ROUND(26) TF_ROUND(6)
+  x0 += ks2; x1 += ks0 + 5u;
+#undef TF_ROUND
+  return Key{x0, x1};
+}
+
+// jax.random.fold_in(key, d) and element j of jax.random.split(key, n) (partitionable layout).
+__host__ __device__ __forceinline__ Key fold_in(Key k, uint32_t d) { return threefry2x32(k, 0u, d); }
+__host__ __device__ __forceinline__ Key split_at(Key k, uint32_t j) { return threefry2x32(k, 0u, j); }
+// element j of jax.random.bits(key, shape, uint32) (partitionable layout, j < 2^32).
+__host__ __device__ __forceinline__ uint32_t random_bits_at(Key k, uint32_t j) {
+  Key o = threefry2x32(k, 0u, j);
+  return o.a ^ o.b;
+}
+
+// XLA float32 erf_inv (Giles' polynomial on w = -log1p(-x^2)).
+__device__ __forceinline__ float erfinv_giles(float x) {
+  float w = -log1pf(-__fmul_rn(x, x));
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = __fadd_rn(3.43273939e-07f, __fmul_rn(p, w));
+    p = __fadd_rn(-3.5233877e-06f, __fmul_rn(p, w));
+    p = __fadd_rn(-4.39150654e-06f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00021858087f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00125372503f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00417768164f, __fmul_rn(p, w));
+    p = __fadd_rn(0.246640727f, __fmul_rn(p, w));
+    p = __fadd_rn(1.50140941f, __fmul_rn(p, w));
+  } else {
+    w = sqrtf(w) - 3.0f;
+    p = -0.000200214257f;
+    p = __fadd_rn(0.000100950558f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00134934322f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.00367342844f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00573950773f, __fmul_rn(p, w));
+    p = __fadd_rn(-0.0076224613f, __fmul_rn(p, w));
+    p = __fadd_rn(0.00943887047f, __fmul_rn(p, w));
+    p = __fadd_rn(1.00167406f, __fmul_rn(p, w));
+    p = __fadd_rn(2.83297682f, __fmul_rn(p, w));
+  }
+  return __fmul_rn(p, x);
+}
+
+// jax.random.normal from 32 random bits: sqrt(2) * erfinv(uniform(nextafter(-1, 0), 1)).
+__device__ __forceinline__ float bits_to_normal(uint32_t bits) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0) in float32
+  float f = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  float u = __fadd_rn(__fmul_rn(f, __fsub_rn(1.0f, lo)), lo);
+  u = fmaxf(lo, u);
+  return __fmul_rn(1.41421356f, erfinv_giles(u));
+}
+
+// jax.random.randint(key, (), 0, span) for int32 (jax/_src/random.py _randint).
+__device__ __forceinline__ int32_t randint_scalar(Key k, uint32_t span) {
+  Key k1 = split_at(k, 0u), k2 = split_at(k, 1u);
+  uint32_t hi = random_bits_at(k1, 0u), lo = random_bits_at(k2, 0u);
+  if (span == 0u) span = 1u;
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  uint32_t off = (hi % span) * mult + (lo % span);
+  return static_cast<int32_t>(off % span);
+}
+
+// ------------------------------------------------------------------------------------------
+// activation / sampler math (feedforward.py:48-50; sampling_layers.py:88-147)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e = expf(-fabsf(x));
+  return x >= 0.0f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+}
+__device__ __forceinline__ float softplus_f(float x) {
+  return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  switch (act) {
+    case B200PPO_ACT_RELU: return fmaxf(z, 0.0f);
+    case B200PPO_ACT_TANH: return tanhf(z);
+    case B200PPO_ACT_SWISH: return z * sigmoid_f(z);
+    default: return z;
+  }
+}
+__device__ __forceinline__ float act_grad(float z, int act) {
+  switch (act) {
+    case B200PPO_ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
+    case B200PPO_ACT_TANH: { float h = tanhf(z); return 1.0f - h * h; }
+    case B200PPO_ACT_SWISH: { float s = sigmoid_f(z); return s * (1.0f + z * (1.0f - s)); }
+    default: return 1.0f;
+  }
+}
+
+#define B200PPO_LOG2 0.69314718f
+#define B200PPO_HALF_LOG_2PI 0.91893853f
+
+// log|d tanh(z)/dz| in the Brax-stable form (sampling_layers.py:131).
+__device__ __forceinline__ float log_det_jac(float z) {
+  return 2.0f * (B200PPO_LOG2 - z - softplus_f(-2.0f * z));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
+
+}  // namespace b200ppo

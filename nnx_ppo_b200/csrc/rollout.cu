@@ -1,0 +1,544 @@
+// K1: policy step and the persistent fused rollout on the synthetic env.  sm_100a.
+//
+// Reference computation replaced: rollout.single_transition / unroll_env (rollout.py:11-73) with
+// the network of make_mlp_actor_critic (factories.py:72-146): Normalizer.__call__
+// (normalizer.py:63-96) -> actor Dense stack (feedforward.py:48-50) -> NormalTanhSampler
+// (sampling_layers.py:82-147) and critic Dense stack -> value squeeze (adapter.py:98).
+//
+// Design: every env is an independent unit, so one CTA owns a tile of TE envs for ALL T steps
+// (no grid-wide synchronisation, one launch per rollout).  Actor + env weights are staged once
+// in shared memory and re-used for T steps; activations ping-pong between two smem tiles;
+// each thread computes a 2-env x 4-column register tile per layer.
+#include "common.cuh"
+
+using namespace b200ppo;
+
+namespace {
+
+constexpr int TE = 32;          // envs per CTA
+constexpr int NT = 256;         // threads per CTA
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+// out[e][n] = act( sum_k in[e][k] * W[k][n] + bias[n] )  for e < TE, n < N.
+// `in`/`out` are shared-memory tiles; W/bias may live in shared or global memory.
+__device__ __forceinline__ void dense_tile(const float* __restrict__ in, int ldin, int K,
+                                           const float* __restrict__ W, const float* __restrict__ bias,
+                                           int N, float* __restrict__ out, int ldout, int act) {
+  const int ng = (N + 3) >> 2;
+  const int total = (TE / 2) * ng;
+  const bool vec = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int item = threadIdx.x; item < total; item += NT) {
+    const int eg = item / ng, nq = item - eg * ng;
+    const int e0 = eg * 2, n0 = nq * 4;
+    float acc[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float b = (bias != nullptr && n0 + j < N) ? bias[n0 + j] : 0.0f;
+      acc[0][j] = b;
+      acc[1][j] = b;
+    }
+    const float* x0 = in + e0 * ldin;
+    const float* x1 = x0 + ldin;
+    if (vec) {
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(k) * N + n0);
+        const float a0 = x0[k], a1 = x1[k];
+        acc[0][0] = fmaf(a0, w.x, acc[0][0]); acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+        acc[0][2] = fmaf(a0, w.z, acc[0][2]); acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, w.x, acc[1][0]); acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+        acc[1][2] = fmaf(a1, w.z, acc[1][2]); acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        const float a0 = x0[k], a1 = x1[k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float w = (n0 + j < N) ? W[static_cast<size_t>(k) * N + n0 + j] : 0.0f;
+          acc[0][j] = fmaf(a0, w, acc[0][j]);
+          acc[1][j] = fmaf(a1, w, acc[1][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + j < N) {
+        out[e0 * ldout + n0 + j] = act_fwd(acc[0][j], act);
+        out[(e0 + 1) * ldout + n0 + j] = act_fwd(acc[1][j], act);
+      }
+    }
+  }
+}
+
+// Runs one Dense chain on a smem tile; returns the buffer holding the last layer's output.
+__device__ __forceinline__ float* run_chain(const b200ppo_chain& ch, const float* __restrict__ P,
+                                            float* bufA, float* bufB, int ld) {
+  float* cur = bufA;
+  float* nxt = bufB;
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const int act = (l + 1 < ch.n_layers) ? ch.act : B200PPO_ACT_NONE;
+    dense_tile(cur, ld, ch.dims[l], P + ch.w_off[l], P + ch.b_off[l], ch.dims[l + 1], nxt, ld, act);
+    __syncthreads();
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  return cur;
+}
+
+struct SamplerOut {
+  float raw, action, llterm, regterm;
+};
+
+// NormalTanhSampler for one (row, action-dim) element — sampling_layers.py:88-147.
+__device__ __forceinline__ SamplerOut sampler_elem(float mu, float rho, float min_std, float std_scale,
+                                                   float entropy_weight, int mode, float raw_in,
+                                                   Key k_sample, Key k_ent, uint32_t j, bool want_reg) {
+  SamplerOut o;
+  const float sigma = (softplus_f(rho) + min_std) * std_scale;
+  float z;
+  if (mode & 1) {
+    z = raw_in;                                   // LOSS_REPLAY: stored raw action
+  } else if (mode & 2) {
+    z = mu;                                       // deterministic
+  } else {
+    const float eps = bits_to_normal(random_bits_at(k_sample, j));
+    z = __fadd_rn(mu, __fmul_rn(sigma, eps));
+  }
+  o.raw = z;
+  o.action = tanhf(z);
+  const float q = (z - mu) / sigma;
+  o.llterm = -0.5f * q * q - (B200PPO_HALF_LOG_2PI + logf(sigma)) - log_det_jac(z);
+  o.regterm = 0.0f;
+  if (want_reg) {
+    const float eps2 = bits_to_normal(random_bits_at(k_ent, j));
+    const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
+    o.regterm = -entropy_weight * (0.5f + B200PPO_HALF_LOG_2PI + logf(sigma) + log_det_jac(zp));
+  }
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// reset of the synthetic env for one env (see oracle/env.py for the definition)
+// ------------------------------------------------------------------------------------------
+struct ResetScalars {
+  Key k_base;
+  int32_t counter;
+  uint32_t term;
+};
+__device__ __forceinline__ ResetScalars synth_reset_scalars(Key key, int max_len) {
+  ResetScalars r;
+  r.k_base = split_at(key, 0u);
+  const Key k_cnt = split_at(key, 1u);
+  r.counter = randint_scalar(k_cnt, static_cast<uint32_t>(max_len / 2));
+  r.term = k_cnt.a ^ k_cnt.b;
+  return r;
+}
+
+__global__ void synth_init_keys_kernel(Key k, int B, uint32_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    const Key o = split_at(k, static_cast<uint32_t>(i));
+    keys[2 * i] = o.a;
+    keys[2 * i + 1] = o.b;
+  }
+}
+
+__global__ void synth_reset_kernel(const uint32_t* __restrict__ keys, int B, int O, int max_len,
+                                   float* __restrict__ obs, int32_t* __restrict__ counter,
+                                   uint32_t* __restrict__ term) {
+  const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * O) return;
+  const int e = static_cast<int>(idx / O), o = static_cast<int>(idx - static_cast<int64_t>(e) * O);
+  const Key key{keys[2 * e], keys[2 * e + 1]};
+  const Key kb = split_at(key, 0u);
+  obs[idx] = bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o)));
+  if (o == 0) {
+    const ResetScalars r = synth_reset_scalars(key, max_len);
+    counter[e] = r.counter;
+    term[e] = r.term;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// persistent fused rollout
+// ------------------------------------------------------------------------------------------
+struct RolloutArgs {
+  b200ppo_plan plan;
+  int O, A, max_len, term_thresh16;
+  const float* Wenv;          // [(O + A)][O]: rows 0..O-1 = Wo, rows O.. = Wa  (global)
+  const float* params;
+  const float* mean;
+  const float* std;
+  const uint32_t* rng_state;
+  const uint32_t* iter_keys;
+  int T, B;
+  float* env_obs; int32_t* env_counter; uint32_t* env_term;
+  float* obs; float* raw_action; float* action; float* loglik; float* reward;
+  uint8_t* done; uint8_t* trunc; float* next_obs_last;
+  int stage_actor;            // actor parameters staged in smem
+  int stage_env;              // env weights staged in smem
+  int actor_span;             // floats of the arena covered by the actor chain (starts at 0)
+  int ld;                     // row stride of the activation tiles
+};
+
+__global__ void __launch_bounds__(NT, 1) rollout_synth_kernel(const RolloutArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.O, A = a.A, ld = a.ld;
+  const int env0 = blockIdx.x * TE;
+  float* sp = smem;
+  float* bufA = sp; sp += TE * ld;
+  float* bufB = sp; sp += TE * ld;
+  float* obs_s = sp; sp += TE * O;
+  float* act_s = sp; sp += TE * A;
+  float* raw_s = sp; sp += TE * A;
+  float* llt_s = sp; sp += TE * A;
+  float* mean_s = sp; sp += O;
+  float* std_s = sp; sp += O;
+  float* rew_s = sp; sp += TE;
+  int32_t* cnt_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  uint32_t* term_s = reinterpret_cast<uint32_t*>(sp); sp += TE;
+  uint32_t* kb_s = reinterpret_cast<uint32_t*>(sp); sp += 2 * TE;
+  int32_t* done_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  sp = smem + ((sp - smem + 3) & ~3);
+  const float* P = a.params;
+  if (a.stage_actor) {
+    float* ps = sp; sp += (a.actor_span + 3) & ~3;
+    for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
+    P = ps;
+  }
+  const float* Wenv = a.Wenv;
+  if (a.stage_env) {
+    float* ws = sp; sp += (O + A) * O;
+    for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
+    Wenv = ws;
+  }
+  for (int i = threadIdx.x; i < O; i += NT) {
+    mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
+    std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
+  }
+  for (int i = threadIdx.x; i < TE * O; i += NT) {
+    const int e = i / O;
+    obs_s[i] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0) * O + i] : 0.0f;
+  }
+  if (threadIdx.x < TE) {
+    const bool ok = env0 + threadIdx.x < a.B;
+    cnt_s[threadIdx.x] = ok ? a.env_counter[env0 + threadIdx.x] : 0;
+    term_s[threadIdx.x] = ok ? a.env_term[env0 + threadIdx.x] : 0u;
+  }
+  const Key stream_key{a.rng_state[0], a.rng_state[1]};
+  const uint32_t count0 = a.rng_state[2];
+  const Key reset_key{a.iter_keys[0], a.iter_keys[1]};
+  __syncthreads();
+
+  for (int t = 0; t < a.T; ++t) {
+    // (1) record the raw observation, normalise into bufA  (rollout.py:23; normalizer.py:78-80)
+    const size_t row0 = static_cast<size_t>(t) * a.B + env0;
+    for (int i = threadIdx.x; i < TE * O; i += NT) {
+      const int e = i / O, o = i - e * O;
+      const float x = obs_s[i];
+      if (env0 + e < a.B) a.obs[row0 * O + i] = x;
+      bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
+    }
+    __syncthreads();
+    // (2) actor MLP
+    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld);
+    // (3) sampler: one fresh normal draw per (env, action dim); count = count0 + 2t
+    //     (the entropy draw at count0 + 2t + 1 does not influence the rollout and is skipped)
+    const Key k_sample = fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
+    for (int i = threadIdx.x; i < TE * A; i += NT) {
+      const int e = i / A, d = i - e * A;
+      const uint32_t j = static_cast<uint32_t>(env0 + e) * static_cast<uint32_t>(A) + d;
+      const SamplerOut s = sampler_elem(y[e * ld + d], y[e * ld + A + d], a.plan.min_std,
+                                        a.plan.std_scale, a.plan.entropy_weight, 0, 0.0f, k_sample,
+                                        k_sample, j, false);
+      raw_s[i] = s.raw;
+      act_s[i] = s.action;
+      llt_s[i] = s.llterm;
+    }
+    __syncthreads();
+    // (4) env step input = [obs, action]  ->  obs' = tanh([obs, action] @ [Wo; Wa])
+    float* xin = (y == bufA) ? bufB : bufA;
+    float* xout = (y == bufA) ? bufA : bufB;   // y is dead after the sampler
+    for (int i = threadIdx.x; i < TE * (O + A); i += NT) {
+      const int e = i / (O + A), c = i - e * (O + A);
+      xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
+    }
+    __syncthreads();
+    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH);
+    __syncthreads();
+    // (5) reward = -mean(obs'^2): one warp per env
+    for (int e = threadIdx.x >> 5; e < TE; e += NT / 32) {
+      float s = 0.0f;
+      for (int o = threadIdx.x & 31; o < O; o += 32) { const float v = xout[e * ld + o]; s = fmaf(v, v, s); }
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) rew_s[e] = -(s / static_cast<float>(O));
+    }
+    __syncthreads();
+    // (6) episode bookkeeping (integer-exact), transition record, reset scalars
+    if (threadIdx.x < TE) {
+      const int e = threadIdx.x;
+      const int ge = env0 + e;
+      float ll = 0.0f;
+      for (int d = 0; d < A; ++d) ll += llt_s[e * A + d];
+      const int32_t c = cnt_s[e] + 1;
+      const uint32_t ts = term_s[e] * 1664525u + 1013904223u;
+      const bool terminated = (ts >> 16) < static_cast<uint32_t>(a.term_thresh16);
+      const bool truncated = c >= a.max_len;
+      const bool dn = terminated || truncated;
+      if (ge < a.B) {
+        a.loglik[row0 + e] = ll;
+        a.reward[row0 + e] = rew_s[e];
+        a.done[row0 + e] = dn ? 1 : 0;
+        a.trunc[row0 + e] = truncated ? 1 : 0;
+      }
+      done_s[e] = dn ? 1 : 0;
+      if (dn) {
+        // rng_keys_for_env_reset[t][env] = split(reset_key, (T, B))[t, env]  (rollout.py:57-59)
+        const Key k = split_at(reset_key, static_cast<uint32_t>(t) * static_cast<uint32_t>(a.B) +
+                                              static_cast<uint32_t>(ge));
+        const ResetScalars r = synth_reset_scalars(k, a.max_len);
+        cnt_s[e] = r.counter;
+        term_s[e] = r.term;
+        kb_s[2 * e] = r.k_base.a;
+        kb_s[2 * e + 1] = r.k_base.b;
+      } else {
+        cnt_s[e] = c;
+        term_s[e] = ts;
+      }
+    }
+    for (int i = threadIdx.x; i < TE * A; i += NT) {
+      const int e = i / A;
+      if (env0 + e < a.B) {
+        a.raw_action[row0 * A + i] = raw_s[i];
+        a.action[row0 * A + i] = act_s[i];
+      }
+    }
+    __syncthreads();
+    // (7) next_obs[-1] is the pre-reset observation (rollout.py:30); then tree_where(done, reset, next)
+    for (int i = threadIdx.x; i < TE * O; i += NT) {
+      const int e = i / O, o = i - e * O;
+      const float v = xout[e * ld + o];
+      if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0) * O + i] = v;
+      obs_s[i] = done_s[e] ? bits_to_normal(random_bits_at(Key{kb_s[2 * e], kb_s[2 * e + 1]},
+                                                            static_cast<uint32_t>(o)))
+                           : v;
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < TE * O; i += NT) {
+    const int e = i / O;
+    if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0) * O + i] = obs_s[i];
+  }
+  if (threadIdx.x < TE && env0 + threadIdx.x < a.B) {
+    a.env_counter[env0 + threadIdx.x] = cnt_s[threadIdx.x];
+    a.env_term[env0 + threadIdx.x] = term_s[threadIdx.x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic single policy step on B rows (used for host/torch envs, replay checks and eval)
+// ------------------------------------------------------------------------------------------
+struct PolicyArgs {
+  b200ppo_plan plan;
+  const float* params; const float* mean; const float* std; const float* obs;
+  int B, mode, ld;
+  const uint32_t* rng_state; uint32_t count_offset;
+  const float* raw_in;
+  float* raw; float* action; float* loglik; float* value; float* reg;
+};
+
+__global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.plan.obs_dim, A = a.plan.act_dim, ld = a.ld;
+  const int row0 = blockIdx.x * TE;
+  float* bufA = smem;
+  float* bufB = bufA + TE * ld;
+  float* x_s = bufB + TE * ld;          // normalised obs, kept for the critic
+  float* llt_s = x_s + TE * ld;
+  float* reg_s = llt_s + TE * A;
+  for (int i = threadIdx.x; i < TE * O; i += NT) {
+    const int e = i / O, o = i - e * O;
+    float x = (row0 + e < a.B) ? a.obs[static_cast<size_t>(row0) * O + i] : 0.0f;
+    if (a.plan.normalize) x = __fdiv_rn(x - a.mean[o], a.std[o]);
+    x_s[e * ld + o] = x;
+    bufA[e * ld + o] = x;
+  }
+  __syncthreads();
+  const float* y = run_chain(a.plan.actor, a.params, bufA, bufB, ld);
+  const Key stream_key{a.rng_state[0], a.rng_state[1]};
+  uint32_t c = a.rng_state[2] + a.count_offset;
+  const bool deterministic = (a.mode & 2) != 0;
+  // sampling_layers.py:93-96: the sample key is only drawn when not deterministic
+  Key k_sample = stream_key;
+  if (!deterministic) { k_sample = fold_in(stream_key, c); c += 1u; }
+  const Key k_ent = fold_in(stream_key, c);
+  const bool want_reg = a.reg != nullptr;
+  for (int i = threadIdx.x; i < TE * A; i += NT) {
+    const int e = i / A, d = i - e * A;
+    const int row = row0 + e;
+    if (row < a.B) {
+      const uint32_t j = static_cast<uint32_t>(row) * static_cast<uint32_t>(A) + d;
+      const float rin = (a.mode & 1) ? a.raw_in[static_cast<size_t>(row) * A + d] : 0.0f;
+      const SamplerOut s = sampler_elem(y[e * ld + d], y[e * ld + A + d], a.plan.min_std,
+                                        a.plan.std_scale, a.plan.entropy_weight, a.mode, rin, k_sample,
+                                        k_ent, j, want_reg);
+      a.raw[static_cast<size_t>(row) * A + d] = s.raw;
+      a.action[static_cast<size_t>(row) * A + d] = s.action;
+      llt_s[i] = s.llterm;
+      reg_s[i] = s.regterm;
+    } else {
+      llt_s[i] = 0.0f;
+      reg_s[i] = 0.0f;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TE && row0 + threadIdx.x < a.B) {
+    float ll = 0.0f, rg = 0.0f;
+    for (int d = 0; d < A; ++d) { ll += llt_s[threadIdx.x * A + d]; rg += reg_s[threadIdx.x * A + d]; }
+    a.loglik[row0 + threadIdx.x] = ll;
+    if (want_reg) a.reg[row0 + threadIdx.x] = rg;
+  }
+  __syncthreads();
+  // critic on the same normalised input (adapter.py:87-88)
+  float* ca = (y == bufA) ? bufB : bufA;
+  for (int i = threadIdx.x; i < TE * O; i += NT) {
+    const int e = i / O, o = i - e * O;
+    ca[e * ld + o] = x_s[e * ld + o];
+  }
+  __syncthreads();
+  float* cb = (ca == bufA) ? bufB : bufA;
+  const float* v = run_chain(a.plan.critic, a.params, ca, cb, ld);
+  if (threadIdx.x < TE && row0 + threadIdx.x < a.B) a.value[row0 + threadIdx.x] = v[threadIdx.x * ld];
+}
+
+int max_dim(const b200ppo_chain& c) {
+  int m = 0;
+  for (int l = 0; l <= c.n_layers; ++l) m = c.dims[l] > m ? c.dims[l] : m;
+  return m;
+}
+
+int check_plan(const b200ppo_plan* p) {
+  if (!p) return B200PPO_EINVAL;
+  if (p->obs_dim <= 0 || p->act_dim <= 0) return B200PPO_EINVAL;
+  const b200ppo_chain* cs[2] = {&p->actor, &p->critic};
+  for (const b200ppo_chain* c : cs) {
+    if (c->n_layers < 1 || c->n_layers > B200PPO_MAX_LAYERS) return B200PPO_EINVAL;
+    if (c->dims[0] != p->obs_dim) return B200PPO_EINVAL;
+    for (int l = 0; l < c->n_layers; ++l) {
+      if (c->dims[l + 1] <= 0) return B200PPO_EINVAL;
+      if ((c->w_off[l] & 3) || (c->b_off[l] & 3)) return B200PPO_EALIGN;
+      if (c->w_off[l] < 0 || c->w_off[l] + static_cast<int64_t>(c->dims[l]) * c->dims[l + 1] > p->n_params)
+        return B200PPO_EINVAL;
+      if (c->b_off[l] < 0 || c->b_off[l] + c->dims[l + 1] > p->n_params) return B200PPO_EINVAL;
+    }
+  }
+  if (p->actor.dims[p->actor.n_layers] != 2 * p->act_dim) return B200PPO_EINVAL;
+  if (p->critic.dims[p->critic.n_layers] != 1) return B200PPO_EINVAL;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int b200ppo_synth_init_keys(void* stream, uint32_t k0, uint32_t k1, int32_t B, uint32_t* keys_out) {
+  if (B <= 0 || !keys_out) return B200PPO_EINVAL;
+  synth_init_keys_kernel<<<cdiv(B, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(Key{k0, k1}, B, keys_out);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_synth_reset(void* stream, const b200ppo_synth_env* env, const uint32_t* keys,
+                                   int32_t B, float* obs, int32_t* step_counter, uint32_t* term_state) {
+  if (!env || B <= 0 || !keys || !obs || !step_counter || !term_state || env->obs_dim <= 0) return B200PPO_EINVAL;
+  const int64_t n = static_cast<int64_t>(B) * env->obs_dim;
+  synth_reset_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      keys, B, env->obs_dim, env->max_len, obs, step_counter, term_state);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                                     const float* params, const float* norm_mean, const float* norm_std,
+                                     const uint32_t* rng_state, const uint32_t* iter_keys, int32_t T,
+                                     int32_t B, float* env_obs, int32_t* env_counter, uint32_t* env_term,
+                                     float* obs, float* raw_action, float* action, float* loglik,
+                                     float* reward, uint8_t* done, uint8_t* truncated,
+                                     float* next_obs_last) {
+  int rc = check_plan(plan);
+  if (rc) return rc;
+  if (!env || !params || !rng_state || !iter_keys || !env_obs || !env_counter || !env_term || !obs ||
+      !raw_action || !action || !loglik || !reward || !done || !truncated || !next_obs_last)
+    return B200PPO_EINVAL;
+  if (plan->normalize && (!norm_mean || !norm_std)) return B200PPO_EINVAL;
+  if (T <= 0 || B <= 0) return B200PPO_EINVAL;
+  if (env->obs_dim != plan->obs_dim || env->act_dim != plan->act_dim || !env->Wo || !env->Wa) return B200PPO_EINVAL;
+  const int O = plan->obs_dim, A = plan->act_dim;
+  // Wo [O][O] and Wa [A][O] must be one contiguous [(O + A)][O] block (Wa right after Wo).
+  if (env->Wa != env->Wo + static_cast<size_t>(O) * O) return B200PPO_EINVAL;
+  RolloutArgs a;
+  a.plan = *plan;
+  a.O = O; a.A = A; a.max_len = env->max_len; a.term_thresh16 = env->term_thresh16;
+  a.Wenv = env->Wo; a.params = params; a.mean = norm_mean; a.std = norm_std;
+  a.rng_state = rng_state; a.iter_keys = iter_keys; a.T = T; a.B = B;
+  a.env_obs = env_obs; a.env_counter = env_counter; a.env_term = env_term;
+  a.obs = obs; a.raw_action = raw_action; a.action = action; a.loglik = loglik; a.reward = reward;
+  a.done = done; a.trunc = truncated; a.next_obs_last = next_obs_last;
+  int md = max_dim(plan->actor);
+  if (O + A > md) md = O + A;
+  a.ld = md + 1;  // odd stride: the two rows a thread reads land in different banks
+  // actor parameters occupy the arena prefix [0, actor_span)
+  int64_t span = 0;
+  for (int l = 0; l < plan->actor.n_layers; ++l) {
+    int64_t we = plan->actor.w_off[l] + static_cast<int64_t>(plan->actor.dims[l]) * plan->actor.dims[l + 1];
+    int64_t be = plan->actor.b_off[l] + plan->actor.dims[l + 1];
+    span = we > span ? we : span;
+    span = be > span ? be : span;
+  }
+  int64_t base_bytes = 4ll * (2ll * TE * a.ld + static_cast<int64_t>(TE) * O + 3ll * TE * A + 2ll * O + 6ll * TE + 8);
+  if (base_bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
+  int64_t bytes = base_bytes;
+  a.actor_span = static_cast<int>(span);
+  a.stage_actor = 0;
+  a.stage_env = 0;
+  if (bytes + 4 * ((span + 3) & ~3ll) <= SMEM_LIMIT) { a.stage_actor = 1; bytes += 4 * ((span + 3) & ~3ll); }
+  const int64_t envw = 4ll * (O + A) * O;
+  if (bytes + envw <= SMEM_LIMIT) { a.stage_env = 1; bytes += envw; }
+  cudaError_t e = cudaFuncSetAttribute(rollout_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  rollout_synth_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t b200ppo_policy_workspace_bytes(const b200ppo_plan* plan, int32_t B) {
+  (void)plan; (void)B;
+  return 256;  // the policy step keeps everything in shared memory
+}
+
+extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const float* params,
+                                   const float* norm_mean, const float* norm_std, const float* obs,
+                                   int32_t B, int32_t mode, const uint32_t* rng_state,
+                                   uint32_t count_offset, const float* raw_action_in, float* raw_action,
+                                   float* action, float* loglik, float* value, float* reg_loss, void* ws) {
+  (void)ws;
+  int rc = check_plan(plan);
+  if (rc) return rc;
+  if (B < 0) return B200PPO_EINVAL;
+  if (B == 0) return 0;
+  if (!params || !obs || !rng_state || !raw_action || !action || !loglik || !value) return B200PPO_EINVAL;
+  if (plan->normalize && (!norm_mean || !norm_std)) return B200PPO_EINVAL;
+  if ((mode & 1) && !raw_action_in) return B200PPO_EINVAL;
+  PolicyArgs a;
+  a.plan = *plan; a.params = params; a.mean = norm_mean; a.std = norm_std; a.obs = obs;
+  a.B = B; a.mode = mode; a.rng_state = rng_state; a.count_offset = count_offset; a.raw_in = raw_action_in;
+  a.raw = raw_action; a.action = action; a.loglik = loglik; a.value = value; a.reg = reg_loss;
+  int md = max_dim(plan->actor);
+  const int mc = max_dim(plan->critic);
+  md = mc > md ? mc : md;
+  a.ld = md + 1;
+  const int64_t bytes = 4ll * (3ll * TE * a.ld + 2ll * TE * plan->act_dim);
+  if (bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
+  cudaError_t e = cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  policy_step_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,838 @@
+// K3 + K4: one PPO minibatch update — ppo.py:296-317 (update_step), 397-531 (ppo_loss),
+// 555-569 (optax adam / adamw / clip_by_global_norm).  sm_100a.
+//
+// Reference structure replaced: nnx.grad(ppo_loss) = a T-step forward scan of tiny per-step
+// GEMMs, a reverse GAE scan and the transposed scan.  For the stateless MLP plan the time scan is
+// mathematically a flat batch, so one update is six launches over the R = T*mb
+// gathered rows (+ mb bootstrap rows for V_{T}):
+//   FWD  row-tile kernel: gather + normalise obs, both Dense stacks, pre-activations -> workspace
+//   GAE  thread-per-env reverse scan on the fresh values + fp64 advantage moment sums
+//   LOSS per-row sampler math, clipped surrogate / value / entropy terms, d loss / d outputs
+//   BWD  row-tile dX chain (dY W^T ⊙ act'), then dW = H^T dY as split-row tiles
+//   RED  fixed-order reduction of the dW partials -> flat gradient
+//   ADAM fused optax update
+// All GEMMs share one register-tiled fp32 FFMA routine (TM=128 rows resident in shared memory,
+// 8x4 accumulators per thread, B operand streamed in double-buffered 16-deep chunks).
+#include "common.cuh"
+
+using namespace b200ppo;
+
+namespace {
+
+constexpr int TM = 128;        // rows per CTA tile
+constexpr int TN = 64;         // output columns per chunk
+constexpr int TK = 16;         // reduction depth of one staged B chunk
+constexpr int KB = 256;        // resident reduction length of the A tile
+constexpr int LDA = TM + 4;
+constexpr int LDB = TN + 4;
+constexpr int NTH = 256;
+constexpr int GEMM_SMEM = (KB * LDA + 2 * TK * LDB) * 4;
+
+constexpr int DW_T = 64;       // dW output tile (k x n)
+constexpr int DW_R = 32;       // rows per staged chunk
+constexpr int DW_LD = DW_T + 4;
+constexpr int DW_SMEM = 4 * DW_R * DW_LD * 4;
+
+constexpr int MAXL = B200PPO_MAX_LAYERS;
+constexpr int MAX_PART_BLOCKS = 1024;   // GAE / grad-norm partial blocks
+constexpr int MAX_LOSS_BLOCKS = 4096;   // loss partial blocks (R <= 524288 rows per update)
+constexpr int DBL_GAE_PART = 8;
+constexpr int DBL_LOSS_PART = DBL_GAE_PART + 2 * MAX_PART_BLOCKS;
+constexpr int DBL_GN_PART = DBL_LOSS_PART + 3 * MAX_LOSS_BLOCKS;
+constexpr int DBL_TOTAL = DBL_GN_PART + MAX_PART_BLOCKS;
+
+struct Layout {
+  int R, Rv, S, n_tiles, rows_per_split;
+  size_t xhat, adv, gpart, grad;
+  size_t za[MAXL], zc[MAXL], da[MAXL], dc[MAXL];
+  size_t dbl;        // doubles: [0..1] adv_sums, [2..3] gnorm2/unused, then partial arrays
+  size_t tickets;    // 8 uint32 tickets
+  size_t total_floats;
+};
+
+inline size_t align64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
+
+int dw_tiles(const b200ppo_chain& c) {
+  int n = 0;
+  for (int l = 0; l < c.n_layers; ++l) n += cdiv(c.dims[l], DW_T) * cdiv(c.dims[l + 1], DW_T);
+  return n;
+}
+
+Layout make_layout(const b200ppo_plan& p, int T, int mb) {
+  Layout L;
+  L.R = T * mb;
+  L.Rv = (T + 1) * mb;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = align64(o + n); return r; };
+  L.tickets = take(64);
+  L.dbl = take(2 * static_cast<size_t>(DBL_TOTAL));
+  L.xhat = take(static_cast<size_t>(L.Rv) * p.obs_dim);
+  L.adv = take(L.R);
+  for (int l = 0; l < p.actor.n_layers; ++l) {
+    L.za[l] = take(static_cast<size_t>(L.R) * p.actor.dims[l + 1]);
+    L.da[l] = take(static_cast<size_t>(L.R) * p.actor.dims[l + 1]);
+  }
+  for (int l = 0; l < p.critic.n_layers; ++l) {
+    L.zc[l] = take(static_cast<size_t>(L.Rv) * p.critic.dims[l + 1]);
+    L.dc[l] = take(static_cast<size_t>(L.R) * p.critic.dims[l + 1]);
+  }
+  L.n_tiles = dw_tiles(p.actor) + dw_tiles(p.critic);
+  const int sms = b200ppo_num_sms();
+  int S = (2 * sms) / (L.n_tiles > 0 ? L.n_tiles : 1);
+  if (S < 1) S = 1;
+  if (S > 32) S = 32;
+  int rps = cdiv(cdiv(L.R, S), DW_R) * DW_R;
+  if (rps < DW_R) rps = DW_R;
+  S = cdiv(L.R, rps);
+  L.S = S;
+  L.rows_per_split = rps;
+  L.gpart = take(static_cast<size_t>(S) * p.n_params);
+  L.grad = take(p.n_params);
+  L.total_floats = o;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// the shared GEMM routine:  C[TM x N] = act_in(A)[rows x K] * B[K x N]
+//   A: global row-major, row r at A + r*lda (rows >= nrows read as zero), act_in applied on load
+//   B: TRANS_B ? Bm[n*ldb + k] : Bm[k*ldb + n]
+//   epi(row_base, col_base, acc[8][4]) once per thread per 64-column chunk
+// ------------------------------------------------------------------------------------------
+template <bool TRANS_B, class Epi>
+__device__ __forceinline__ void gemm_rowtile(float* __restrict__ As, float* __restrict__ Bs,
+                                             const float* __restrict__ A, int lda, int row0, int nrows,
+                                             int act_in, const float* __restrict__ Bm, int ldb, int K,
+                                             int N, Epi epi) {
+  const int tid = threadIdx.x;
+  const int tn = tid & 15, tm = tid >> 4;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nkb = (K + KB - 1) / KB;
+  for (int n0 = 0; n0 < N; n0 += TN) {
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int k0 = kb * KB;
+      const int kc = (K - k0) < KB ? (K - k0) : KB;
+      const int kc_pad = (kc + TK - 1) / TK * TK;
+      if (nkb > 1 || n0 == 0) {
+        __syncthreads();
+        // transposed, conflict-free staging: a warp moves 4 rows x 8 k per step
+        const int nkg = kc_pad >> 3;
+        const int units = (TM / 4) * nkg;
+#pragma unroll 4
+        for (int u = warp; u < units; u += NTH / 32) {
+          const int rg = u / nkg, kg = u - rg * nkg;
+          const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+          float v = 0.0f;
+          if (row0 + r < nrows && k < kc) v = act_fwd(A[static_cast<size_t>(row0 + r) * lda + k0 + k], act_in);
+          As[k * LDA + r] = v;
+        }
+        __syncthreads();
+      }
+      const int nch = kc_pad / TK;
+      float breg[4];
+      auto load_b = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int kk, nn;
+          if (TRANS_B) { kk = tid & 15; nn = (tid >> 4) + 16 * i; }
+          else { nn = tid & 63; kk = (tid >> 6) + 4 * i; }
+          const int k = k0 + c * TK + kk, n = n0 + nn;
+          float v = 0.0f;
+          if (k < K && n < N) v = TRANS_B ? Bm[static_cast<size_t>(n) * ldb + k] : Bm[static_cast<size_t>(k) * ldb + n];
+          breg[i] = v;
+        }
+      };
+      auto store_b = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int kk, nn;
+          if (TRANS_B) { kk = tid & 15; nn = (tid >> 4) + 16 * i; }
+          else { nn = tid & 63; kk = (tid >> 6) + 4 * i; }
+          Bs[buf * TK * LDB + kk * LDB + nn] = breg[i];
+        }
+      };
+      load_b(0);
+      store_b(0);
+      __syncthreads();
+      for (int c = 0; c < nch; ++c) {
+        if (c + 1 < nch) load_b(c + 1);
+        const float* ap = As + (c * TK) * LDA + tm * 8;
+        const float* bp = Bs + (c & 1) * TK * LDB + tn * 4;
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+          const float4 a0 = *reinterpret_cast<const float4*>(ap + kk * LDA);
+          const float4 a1 = *reinterpret_cast<const float4*>(ap + kk * LDA + 4);
+          const float4 b = *reinterpret_cast<const float4*>(bp + kk * LDB);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (c + 1 < nch) store_b((c + 1) & 1);
+        __syncthreads();
+      }
+    }
+    epi(row0 + tm * 8, n0 + tn * 4, acc);
+  }
+}
+
+// Thin-output variant (N < 16, K <= KB): one thread per (row, column).
+template <class Store>
+__device__ __forceinline__ void gemm_thin(float* __restrict__ As, const float* __restrict__ A, int lda,
+                                          int row0, int nrows, int act_in, const float* __restrict__ W,
+                                          int K, int N, Store store) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  const int kc_pad = (K + 7) & ~7;
+  const int nkg = kc_pad >> 3;
+  const int units = (TM / 4) * nkg;
+#pragma unroll 4
+  for (int u = warp; u < units; u += NTH / 32) {
+    const int rg = u / nkg, kg = u - rg * nkg;
+    const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+    float v = 0.0f;
+    if (row0 + r < nrows && k < K) v = act_fwd(A[static_cast<size_t>(row0 + r) * lda + k], act_in);
+    As[k * LDA + r] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TM * N; idx += NTH) {
+    const int n = idx / TM, m = idx - n * TM;
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s = fmaf(As[k * LDA + m], __ldg(W + static_cast<size_t>(k) * N + n), s);
+    store(row0 + m, n, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FWD
+// ------------------------------------------------------------------------------------------
+struct FwdArgs {
+  b200ppo_plan plan;
+  Layout L;
+  const float* obs; const float* next_obs_last; const int32_t* inds;
+  const float* mean; const float* std; const float* params;
+  float* ws;
+  int T, B, mb;
+};
+
+__device__ __forceinline__ void chain_forward_tile(const b200ppo_chain& ch, const float* __restrict__ P,
+                                                   float* ws, const size_t* zoff, size_t xhat_off, int O,
+                                                   int row0, int nrows, float* As, float* Bs) {
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const int K = ch.dims[l], N = ch.dims[l + 1];
+    const float* A = l == 0 ? ws + xhat_off : ws + zoff[l - 1];
+    const int act_in = l == 0 ? B200PPO_ACT_NONE : ch.act;
+    const float* W = P + ch.w_off[l];
+    const float* bias = P + ch.b_off[l];
+    float* Z = ws + zoff[l];
+    if (N < 16 && K <= KB) {
+      gemm_thin(As, A, K, row0, nrows, act_in, W, K, N, [&](int r, int n, float s) {
+        if (r < nrows) Z[static_cast<size_t>(r) * N + n] = s + __ldg(bias + n);
+      });
+    } else {
+      gemm_rowtile<false>(As, Bs, A, K, row0, nrows, act_in, W, N, K, N,
+                          [&](int rb, int cb, float (&acc)[8][4]) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                              const int r = rb + i;
+                              if (r < nrows) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                  if (cb + j < N) Z[static_cast<size_t>(r) * N + cb + j] = acc[i][j] + __ldg(bias + cb + j);
+                              }
+                            }
+                          });
+    }
+    __syncthreads();  // this tile's z_l is complete before it is re-read as the next layer's input
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) upd_fwd_kernel(const FwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = smem + KB * LDA;
+  const int O = a.plan.obs_dim;
+  const int row0 = blockIdx.x * TM;
+  const int R = a.L.R, Rv = a.L.Rv;
+  float* xhat = a.ws + a.L.xhat;
+  // gather + normalise this tile's observations (ppo.py:297 gather; normalizer.py:78-80)
+  for (int idx = threadIdx.x; idx < TM * O; idx += NTH) {
+    const int m = idx / O, k = idx - m * O;
+    const int r = row0 + m;
+    if (r < Rv) {
+      const float* src;
+      if (r < R) {
+        const int t = r / a.mb, j = r - t * a.mb;
+        src = a.obs + (static_cast<size_t>(t) * a.B + a.inds[j]) * O;
+      } else {
+        src = a.next_obs_last + static_cast<size_t>(a.inds[r - R]) * O;
+      }
+      float x = src[k];
+      if (a.plan.normalize) x = __fdiv_rn(x - __ldg(a.mean + k), __ldg(a.std + k));
+      xhat[static_cast<size_t>(r) * O + k] = x;
+    }
+  }
+  __syncthreads();
+  chain_forward_tile(a.plan.critic, a.params, a.ws, a.L.zc, a.L.xhat, O, row0, Rv, As, Bs);
+  if (row0 < R) chain_forward_tile(a.plan.actor, a.params, a.ws, a.L.za, a.L.xhat, O, row0, R, As, Bs);
+}
+
+// ------------------------------------------------------------------------------------------
+// GAE on the fresh values (ppo.py:447-455) + advantage moment sums for ppo.py:477-480
+// ------------------------------------------------------------------------------------------
+struct GaeArgs {
+  Layout L;
+  const float* reward; const uint8_t* done; const uint8_t* trunc; const int32_t* inds;
+  float* ws; size_t v_off;
+  int T, B, mb;
+  float gamma, lambda_;
+};
+
+__global__ void __launch_bounds__(128) upd_gae_kernel(const GaeArgs a) {
+  __shared__ double red[2][4];
+  __shared__ bool is_last;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* v = a.ws + a.v_off;
+  float* adv = a.ws + a.L.adv;
+  double s1 = 0.0, s2 = 0.0;
+  if (j < a.mb) {
+    const int e = a.inds[j];
+    float next_adv = 0.0f;
+    float next_val = v[static_cast<size_t>(a.L.R) + j];
+#pragma unroll 4
+    for (int t = a.T - 1; t >= 0; --t) {
+      const size_t gi = static_cast<size_t>(t) * a.B + e;
+      const size_t ri = static_cast<size_t>(t) * a.mb + j;
+      const float r = a.reward[gi], val = v[ri];
+      const bool d = a.done[gi] != 0, tr = a.trunc[gi] != 0;
+      const float nv = d ? 0.0f : next_val;
+      float ad = __fsub_rn(__fadd_rn(r, __fmul_rn(a.gamma, nv)), val);
+      ad = tr ? 0.0f : ad;
+      const float nd = d ? 0.0f : 1.0f;
+      next_adv = __fadd_rn(ad, __fmul_rn(__fmul_rn(__fmul_rn(nd, a.gamma), a.lambda_), next_adv));
+      adv[ri] = next_adv;
+      next_val = val;
+      s1 += next_adv;
+      s2 += static_cast<double>(next_adv) * next_adv;
+    }
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  double* dbl = reinterpret_cast<double*>(a.ws + a.L.dbl);
+  double* part = dbl + DBL_GAE_PART;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    part[2 * blockIdx.x + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    __threadfence();
+    const unsigned int tk = atomicAdd(&ticket[0], 1u);
+    is_last = tk == gridDim.x - 1;
+    if (is_last) {
+      ticket[0] = 0u;
+      __threadfence();
+      double t1 = 0.0, t2 = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) {
+        t1 += __ldcg(&part[2 * b]);
+        t2 += __ldcg(&part[2 * b + 1]);
+      }
+      dbl[0] = t1;   // adv_sums: a data-parallel caller all-reduces these two doubles
+      dbl[1] = t2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// LOSS: per-row sampler math, loss terms and d loss / d (actor output, value) — SURVEY App. A
+// ------------------------------------------------------------------------------------------
+struct LossArgs {
+  b200ppo_plan plan;
+  Layout L;
+  const float* raw_action; const float* loglik_old; const int32_t* inds;
+  const uint32_t* rng_state;
+  float* ws; float* metrics_out;
+  size_t y_off, v_off, dy_off, dv_off;
+  int T, B, mb;
+  uint32_t count_offset;
+  float clip, critic_w;
+  int normalize_adv;
+  double n_global;
+};
+
+__global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
+  __shared__ double red[3][4];
+  const int A = a.plan.act_dim;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
+  const double ng = a.n_global;
+  const float inv_n = static_cast<float>(1.0 / ng);
+  float a_mean = 0.0f, a_den = 1.0f;
+  if (a.normalize_adv) {
+    const double m = dbl[0] / ng;
+    double var = dbl[1] / ng - m * m;
+    var = var > 0.0 ? var : 0.0;
+    a_mean = static_cast<float>(m);
+    a_den = static_cast<float>(sqrt(var)) + 1e-8f;
+  }
+  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
+  if (r < a.L.R) {
+    const int t = r / a.mb, j = r - t * a.mb;
+    const size_t grow = static_cast<size_t>(t) * a.B + a.inds[j];
+    const float* y = a.ws + a.y_off + static_cast<size_t>(r) * 2 * A;
+    float* dy = a.ws + a.dy_off + static_cast<size_t>(r) * 2 * A;
+    const float* z_in = a.raw_action + grow * A;
+    // entropy noise: second draw of replay step t, count = base + 2t + 1, shape (mb, A)
+    const Key stream_key{a.rng_state[0], a.rng_state[1]};
+    const Key k_ent = fold_in(stream_key, a.rng_state[2] + a.count_offset + 2u * static_cast<uint32_t>(t) + 1u);
+    float ll = 0.0f, ent = 0.0f;
+    for (int d = 0; d < A; ++d) {
+      const float mu = y[d], rho = y[A + d], z = z_in[d];
+      const float sigma = (softplus_f(rho) + a.plan.min_std) * a.plan.std_scale;
+      const float q = (z - mu) / sigma;
+      const float ls = logf(sigma);
+      ll += -0.5f * q * q - (B200PPO_HALF_LOG_2PI + ls) - log_det_jac(z);
+      const float eps2 = bits_to_normal(random_bits_at(k_ent, static_cast<uint32_t>(j) * A + d));
+      const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
+      ent += 0.5f + B200PPO_HALF_LOG_2PI + ls + log_det_jac(zp);
+    }
+    const float adv = a.ws[a.L.adv + r];
+    const float v = a.ws[a.v_off + r];
+    const float target = __fadd_rn(v, adv);                    // ppo.py:456-458
+    const float diff = __fsub_rn(v, target);
+    const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
+    const float ratio = expf(ll - a.loglik_old[grow]);
+    const float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
+    const float c1 = __fmul_rn(ratio, an);
+    const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
+    l_actor = -static_cast<double>(fminf(c1, c2));
+    l_critic = 0.5 * static_cast<double>(diff) * diff;
+    l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
+    // JAX tie rules: minimum and clip split the cotangent 0.5 / 0.5 on exact ties
+    const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
+    const float w2 = 1.0f - w1;
+    const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
+    const float g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    const float we = a.plan.entropy_weight * inv_n;
+    for (int d = 0; d < A; ++d) {
+      const float mu = y[d], rho = y[A + d], z = z_in[d];
+      const float sigma = (softplus_f(rho) + a.plan.min_std) * a.plan.std_scale;
+      const float eps2 = bits_to_normal(random_bits_at(k_ent, static_cast<uint32_t>(j) * A + d));
+      const float th = tanhf(__fadd_rn(mu, __fmul_rn(sigma, eps2)));
+      const float dm = z - mu;
+      const float is = 1.0f / sigma;
+      const float d_mu = g_ll * dm * is * is + we * 2.0f * th;
+      const float d_sig = g_ll * (dm * dm * is * is * is - is) - we * (is - 2.0f * th * eps2);
+      dy[d] = d_mu;
+      dy[A + d] = d_sig * sigmoid_f(rho) * a.plan.std_scale;
+    }
+    a.ws[a.dv_off + r] = a.critic_w * diff * inv_n;
+  }
+  l_actor = warp_sum_d(l_actor);
+  l_critic = warp_sum_d(l_critic);
+  l_reg = warp_sum_d(l_reg);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = l_actor;
+    red[1][threadIdx.x >> 5] = l_critic;
+    red[2][threadIdx.x >> 5] = l_reg;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* part = const_cast<double*>(dbl) + DBL_LOSS_PART;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
+    for (int q = 0; q < 3; ++q) part[3 * blockIdx.x + q] = red[q][0] + red[q][1] + red[q][2] + red[q][3];
+    __threadfence();
+    const unsigned int tk = atomicAdd(&ticket[1], 1u);
+    if (tk == gridDim.x - 1) {
+      ticket[1] = 0u;
+      __threadfence();
+      double s[3] = {0.0, 0.0, 0.0};
+      for (unsigned int b = 0; b < gridDim.x; ++b)
+        for (int q = 0; q < 3; ++q) s[q] += __ldcg(&part[3 * b + q]);
+      for (int q = 0; q < 3; ++q) a.metrics_out[q] = static_cast<float>(s[q] / ng);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BWD dX chain:  dpre_{l-1} = (dpre_l W_l^T) ⊙ act'(z_{l-1})
+// ------------------------------------------------------------------------------------------
+struct BwdArgs {
+  b200ppo_plan plan;
+  Layout L;
+  const float* params;
+  float* ws;
+};
+
+__device__ __forceinline__ void chain_backward_tile(const b200ppo_chain& ch, const float* __restrict__ P,
+                                                    float* ws, const size_t* zoff, const size_t* doff,
+                                                    int row0, int nrows, float* As, float* Bs) {
+  for (int l = ch.n_layers - 1; l >= 1; --l) {
+    const int Kl = ch.dims[l], Nl = ch.dims[l + 1];
+    const float* dY = ws + doff[l];
+    const float* W = P + ch.w_off[l];
+    const float* zprev = ws + zoff[l - 1];
+    float* dprev = ws + doff[l - 1];
+    const int act = ch.act;
+    gemm_rowtile<true>(As, Bs, dY, Nl, row0, nrows, B200PPO_ACT_NONE, W, Nl, Nl, Kl,
+                       [&](int rb, int cb, float (&acc)[8][4]) {
+#pragma unroll
+                         for (int i = 0; i < 8; ++i) {
+                           const int r = rb + i;
+                           if (r < nrows) {
+#pragma unroll
+                             for (int j = 0; j < 4; ++j)
+                               if (cb + j < Kl) {
+                                 const size_t o = static_cast<size_t>(r) * Kl + cb + j;
+                                 dprev[o] = acc[i][j] * act_grad(zprev[o], act);
+                               }
+                           }
+                         }
+                       });
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(NTH, 1) upd_bwd_dx_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = smem + KB * LDA;
+  const int row0 = blockIdx.x * TM;
+  chain_backward_tile(a.plan.critic, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, As, Bs);
+  chain_backward_tile(a.plan.actor, a.params, a.ws, a.L.za, a.L.da, row0, a.L.R, As, Bs);
+}
+
+// ------------------------------------------------------------------------------------------
+// BWD dW:  dW_l = act(z_{l-1})^T dpre_l,  db_l = colsum(dpre_l); 64x64 output tiles, rows split
+// into S ranges whose partial results land in gpart[s][P] (reduced in a fixed order by RED).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;                       // [2][DW_R][DW_LD]
+  float* Bs = smem + 2 * DW_R * DW_LD;    // [2][DW_R][DW_LD]
+  // decode blockIdx.x -> (chain, layer, k tile, n tile)
+  int item = blockIdx.x;
+  const b200ppo_chain* ch = &a.plan.actor;
+  const size_t* zoff = a.L.za;
+  const size_t* doff = a.L.da;
+  int layer = -1, kt = 0, nt = 0;
+  for (int c = 0; c < 2 && layer < 0; ++c) {
+    ch = c == 0 ? &a.plan.actor : &a.plan.critic;
+    zoff = c == 0 ? a.L.za : a.L.zc;
+    doff = c == 0 ? a.L.da : a.L.dc;
+    for (int l = 0; l < ch->n_layers; ++l) {
+      const int nk = (ch->dims[l] + DW_T - 1) / DW_T, nn = (ch->dims[l + 1] + DW_T - 1) / DW_T;
+      if (item < nk * nn) { layer = l; kt = item / nn; nt = item - kt * nn; break; }
+      item -= nk * nn;
+    }
+  }
+  if (layer < 0) return;
+  const int K = ch->dims[layer], N = ch->dims[layer + 1];
+  const int k0 = kt * DW_T, n0 = nt * DW_T;
+  const float* H = layer == 0 ? a.ws + a.L.xhat : a.ws + zoff[layer - 1];
+  const int act_in = layer == 0 ? B200PPO_ACT_NONE : ch->act;
+  const float* D = a.ws + doff[layer];
+  const int s = blockIdx.y;
+  const int r_begin = s * a.L.rows_per_split;
+  int r_end = r_begin + a.L.rows_per_split;
+  if (r_end > a.L.R) r_end = a.L.R;
+  const int tid = threadIdx.x;
+  const int tk = tid >> 4, tn = tid & 15;
+  const int lc = tid & 63, lr = tid >> 6;   // loader: column, row (4 rows per pass, 8 passes)
+  float acc[4][4];
+  float bacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float ra[8], rb[8];
+  auto load = [&](int rc) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = rc + lr + 4 * i;
+      float va = 0.0f, vb = 0.0f;
+      if (r < r_end) {
+        if (k0 + lc < K) va = act_fwd(H[static_cast<size_t>(r) * K + k0 + lc], act_in);
+        if (n0 + lc < N) vb = D[static_cast<size_t>(r) * N + n0 + lc];
+      }
+      ra[i] = va;
+      rb[i] = vb;
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      As[(buf * DW_R + lr + 4 * i) * DW_LD + lc] = ra[i];
+      Bs[(buf * DW_R + lr + 4 * i) * DW_LD + lc] = rb[i];
+    }
+  };
+  const int nch = (r_end - r_begin + DW_R - 1) / DW_R;
+  if (nch > 0) {
+    load(r_begin);
+    store(0);
+  }
+  __syncthreads();
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) load(r_begin + (c + 1) * DW_R);
+    const float* ap = As + (c & 1) * DW_R * DW_LD + tk * 4;
+    const float* bp = Bs + (c & 1) * DW_R * DW_LD + tn * 4;
+#pragma unroll
+    for (int rr = 0; rr < DW_R; ++rr) {
+      const float4 av = *reinterpret_cast<const float4*>(ap + rr * DW_LD);
+      const float4 bv = *reinterpret_cast<const float4*>(bp + rr * DW_LD);
+      const float a4[4] = {av.x, av.y, av.z, av.w};
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      if (tk == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bacc[j] += b4[j];
+      }
+    }
+    if (c + 1 < nch) store((c + 1) & 1);
+    __syncthreads();
+  }
+  float* gp = a.ws + a.L.gpart + static_cast<size_t>(s) * a.plan.n_params;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + tk * 4 + i;
+    if (k < K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tn * 4 + j;
+        if (n < N) gp[ch->w_off[layer] + static_cast<size_t>(k) * N + n] = acc[i][j];
+      }
+    }
+  }
+  if (kt == 0 && tk == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn * 4 + j;
+      if (n < N) gp[ch->b_off[layer] + n] = bacc[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// RED / grad-norm / ADAM
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ gpart, int S, int64_t P,
+                                                      float* __restrict__ grad) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= P) return;
+  float g = 0.0f;
+  for (int s = 0; s < S; ++s) g += gpart[static_cast<size_t>(s) * P + i];
+  grad[i] = g;
+}
+
+__global__ void __launch_bounds__(256) upd_gnorm_kernel(const float* __restrict__ grad, int64_t P,
+                                                        double* __restrict__ part, double* __restrict__ out,
+                                                        unsigned int* __restrict__ ticket) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double g = grad[i];
+    s += g * g;
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    part[blockIdx.x] = t;
+    __threadfence();
+    const unsigned int tk = atomicAdd(ticket, 1u);
+    if (tk == gridDim.x - 1) {
+      *ticket = 0u;
+      __threadfence();
+      double tot = 0.0;
+      for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(&part[b]);
+      *out = tot;
+    }
+  }
+}
+
+struct AdamArgs {
+  const float* grad; float* params; float* mu; float* nu;
+  const uint32_t* rng_state; const double* gnorm2; float* metrics_out;
+  int64_t P;
+  int update_index;
+  float lr, b1, b2, eps, wd, clip;
+};
+
+// optax.adam / adamw (scale_by_adam -> [add_decayed_weights] -> scale(-lr)), optionally preceded by
+// clip_by_global_norm — ppo.py:555-569.
+__global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  float gn = 0.0f;
+  if (a.clip > 0.0f) {
+    gn = sqrtf(static_cast<float>(*a.gnorm2));
+    if (i == 0) a.metrics_out[3] = gn;
+  }
+  if (i >= a.P) return;
+  float g = a.grad[i];
+  if (a.clip > 0.0f && !(gn < a.clip)) g = __fmul_rn(__fdiv_rn(g, gn), a.clip);
+  const float t = static_cast<float>(a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u);
+  const float m = __fadd_rn(__fmul_rn(1.0f - a.b1, g), __fmul_rn(a.b1, a.mu[i]));
+  const float v = __fadd_rn(__fmul_rn(1.0f - a.b2, __fmul_rn(g, g)), __fmul_rn(a.b2, a.nu[i]));
+  a.mu[i] = m;
+  a.nu[i] = v;
+  const float bc1 = 1.0f - powf(a.b1, t), bc2 = 1.0f - powf(a.b2, t);
+  const float mh = __fdiv_rn(m, bc1), vh = __fdiv_rn(v, bc2);
+  float u = __fdiv_rn(mh, __fadd_rn(sqrtf(vh), a.eps));
+  const float p = a.params[i];
+  if (a.wd >= 0.0f) u = __fadd_rn(u, __fmul_rn(a.wd, p));
+  a.params[i] = __fadd_rn(p, __fmul_rn(-a.lr, u));
+}
+
+int check_plan_u(const b200ppo_plan* p) {
+  if (!p || p->obs_dim <= 0 || p->act_dim <= 0 || p->n_params <= 0) return B200PPO_EINVAL;
+  const b200ppo_chain* cs[2] = {&p->actor, &p->critic};
+  for (const b200ppo_chain* c : cs) {
+    if (c->n_layers < 1 || c->n_layers > MAXL || c->dims[0] != p->obs_dim) return B200PPO_EINVAL;
+    for (int l = 0; l < c->n_layers; ++l) {
+      if (c->dims[l + 1] <= 0) return B200PPO_EINVAL;
+      if ((c->w_off[l] & 3) || (c->b_off[l] & 3)) return B200PPO_EALIGN;
+      if (c->w_off[l] < 0 || c->w_off[l] + static_cast<int64_t>(c->dims[l]) * c->dims[l + 1] > p->n_params) return B200PPO_EINVAL;
+      if (c->b_off[l] < 0 || c->b_off[l] + c->dims[l + 1] > p->n_params) return B200PPO_EINVAL;
+    }
+  }
+  if (p->actor.dims[p->actor.n_layers] != 2 * p->act_dim || p->critic.dims[p->critic.n_layers] != 1) return B200PPO_EINVAL;
+  return 0;
+}
+
+bool g_attr_done = false;
+int set_attrs() {
+  if (g_attr_done) return 0;
+  cudaError_t e;
+  e = cudaFuncSetAttribute(upd_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  g_attr_done = true;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb) {
+  if (check_plan_u(plan) || T <= 0 || mb <= 0) return B200PPO_EINVAL;
+  return static_cast<int64_t>(make_layout(*plan, T, mb).total_floats) * 4;
+}
+
+extern "C" double* b200ppo_update_adv_sums_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws) {
+  if (check_plan_u(plan) || !ws) return nullptr;
+  return reinterpret_cast<double*>(static_cast<float*>(ws) + make_layout(*plan, T, mb).dbl);
+}
+extern "C" float* b200ppo_update_grad_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws) {
+  if (check_plan_u(plan) || !ws) return nullptr;
+  return static_cast<float*>(ws) + make_layout(*plan, T, mb).grad;
+}
+extern "C" float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws, int32_t which) {
+  if (check_plan_u(plan) || !ws) return nullptr;
+  const Layout L = make_layout(*plan, T, mb);
+  float* w = static_cast<float*>(ws);
+  switch (which) {
+    case 0: return w + L.adv;
+    case 1: return w + L.zc[plan->critic.n_layers - 1];
+    case 2: return w + L.za[plan->actor.n_layers - 1];
+    case 3: return w + L.da[plan->actor.n_layers - 1];
+    case 4: return w + L.dc[plan->critic.n_layers - 1];
+    default: return nullptr;
+  }
+}
+
+extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,
+                              const b200ppo_update_bufs* b, int32_t T, int32_t B, int32_t mb,
+                              uint32_t rng_count_offset, int32_t update_index, int32_t stages) {
+  int rc = check_plan_u(plan);
+  if (rc) return rc;
+  if (!hp || !b || T <= 0 || B <= 0 || mb <= 0 || mb > B || update_index < 0) return B200PPO_EINVAL;
+  if (!b->obs || !b->raw_action || !b->loglik_old || !b->reward || !b->done || !b->truncated ||
+      !b->next_obs_last || !b->inds || !b->params || !b->adam_mu || !b->adam_nu || !b->rng_state ||
+      !b->metrics_out || !b->ws)
+    return B200PPO_EINVAL;
+  if (plan->normalize && (!b->norm_mean || !b->norm_std)) return B200PPO_EINVAL;
+  if (reinterpret_cast<uintptr_t>(b->ws) & 255) return B200PPO_EALIGN;
+  if (hp->world_size < 1) return B200PPO_EINVAL;
+  rc = set_attrs();
+  if (rc) return rc;
+  const Layout L = make_layout(*plan, T, mb);
+  if (cdiv(mb, 128) > MAX_PART_BLOCKS || cdiv(L.R, 128) > MAX_LOSS_BLOCKS) return B200PPO_ELIMIT;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* ws = static_cast<float*>(b->ws);
+  const size_t v_off = L.zc[plan->critic.n_layers - 1];
+  const size_t y_off = L.za[plan->actor.n_layers - 1];
+  const size_t dv_off = L.dc[plan->critic.n_layers - 1];
+  const size_t dy_off = L.da[plan->actor.n_layers - 1];
+  double* dbl = reinterpret_cast<double*>(ws + L.dbl);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + L.tickets);
+
+  if (stages & B200PPO_STAGE_FWD) {
+    FwdArgs a;
+    a.plan = *plan; a.L = L; a.obs = b->obs; a.next_obs_last = b->next_obs_last; a.inds = b->inds;
+    a.mean = b->norm_mean; a.std = b->norm_std; a.params = b->params; a.ws = ws;
+    a.T = T; a.B = B; a.mb = mb;
+    upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  if (stages & B200PPO_STAGE_GAE) {
+    GaeArgs a;
+    a.L = L; a.reward = b->reward; a.done = b->done; a.trunc = b->truncated; a.inds = b->inds;
+    a.ws = ws; a.v_off = v_off; a.T = T; a.B = B; a.mb = mb; a.gamma = hp->gamma; a.lambda_ = hp->lambda_;
+    upd_gae_kernel<<<cdiv(mb, 128), 128, 0, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  if (stages & B200PPO_STAGE_LOSS) {
+    LossArgs a;
+    a.plan = *plan; a.L = L; a.raw_action = b->raw_action; a.loglik_old = b->loglik_old; a.inds = b->inds;
+    a.rng_state = b->rng_state; a.ws = ws; a.metrics_out = b->metrics_out;
+    a.y_off = y_off; a.v_off = v_off; a.dy_off = dy_off; a.dv_off = dv_off;
+    a.T = T; a.B = B; a.mb = mb; a.count_offset = rng_count_offset;
+    a.clip = hp->clip_range; a.critic_w = hp->critic_loss_weight; a.normalize_adv = hp->normalize_advantages;
+    a.n_global = static_cast<double>(L.R) * hp->world_size;
+    upd_loss_kernel<<<cdiv(L.R, 128), 128, 0, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  if (stages & B200PPO_STAGE_BWD) {
+    BwdArgs a;
+    a.plan = *plan; a.L = L; a.params = b->params; a.ws = ws;
+    upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+    upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  if (stages & B200PPO_STAGE_RED) {
+    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, L.S, plan->n_params, ws + L.grad);
+    B200PPO_LAUNCH_CHECK();
+  }
+  if (stages & B200PPO_STAGE_ADAM) {
+    if (hp->grad_clip > 0.0f) {
+      int nb = cdiv(plan->n_params, 256 * 8);
+      if (nb > MAX_PART_BLOCKS) nb = MAX_PART_BLOCKS;
+      upd_gnorm_kernel<<<nb, 256, 0, s>>>(ws + L.grad, plan->n_params, dbl + DBL_GN_PART, dbl + 2, tickets + 2);
+      B200PPO_LAUNCH_CHECK();
+    }
+    AdamArgs a;
+    a.grad = ws + L.grad; a.params = b->params; a.mu = b->adam_mu; a.nu = b->adam_nu;
+    a.rng_state = b->rng_state; a.gnorm2 = dbl + 2; a.metrics_out = b->metrics_out;
+    a.P = plan->n_params; a.update_index = update_index;
+    a.lr = hp->learning_rate; a.b1 = hp->adam_b1; a.b2 = hp->adam_b2; a.eps = hp->adam_eps;
+    a.wd = hp->weight_decay; a.clip = hp->grad_clip;
+    upd_adam_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  return 0;
+}

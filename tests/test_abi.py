@@ -1,0 +1,110 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports exactly what include/b200ppo.h
+declares; host-side key arithmetic and config mirror the reference (no compute calls here)."""
+import ctypes
+import dataclasses
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nnx_ppo_b200 import _lib, prng
+from nnx_ppo_b200.algorithms import config, ppo
+from nnx_ppo_b200.algorithms.types import LoggingLevel
+from nnx_ppo_b200.networks import factories
+from nnx_ppo_b200.networks.normalizer import Normalizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from nnx_ppo_b200 import build
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "b200ppo.h")).read()
+    declared = set(re.findall(r"\b(b200ppo_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.b200ppo_version() == 100
+    assert b"invalid" in lib.b200ppo_error_string(-1)
+
+
+def test_struct_sizes_match_header_layout():
+    assert ctypes.sizeof(_lib.Chain) == 4 + 4 + 9 * 4 + 4 + 8 * 8 + 8 * 8
+    assert ctypes.sizeof(_lib.Plan) == 16 + 16 + 8 + 2 * ctypes.sizeof(_lib.Chain)
+    assert ctypes.sizeof(_lib.HParams) == 48
+    assert ctypes.sizeof(_lib.UpdateBufs) == 16 * 8
+    assert ctypes.sizeof(_lib.SynthEnv) == 32
+
+
+def test_argument_validation_without_gpu(lib):
+    """Error behaviour of the ABI: bad arguments are rejected before any launch."""
+    assert lib.b200ppo_gae(None, None, None, None, None, None, 4, 4, 0.9, 0.9, None) == -1
+    assert lib.b200ppo_gae(None, None, None, None, None, None, 0, 4, 0.9, 0.9, None) == 0   # empty
+    assert lib.b200ppo_permutation(None, None, 0, 4, None, None) == 0                        # empty
+    assert lib.b200ppo_permutation(None, None, 8, 4, None, None) == -1
+    assert lib.b200ppo_random_bits(None, 0, 0, -1, None) == -1
+    plan = _lib.Plan()
+    assert lib.b200ppo_update_workspace_bytes(plan, 4, 4) < 0
+
+
+def test_host_prng_matches_jax_known_values():
+    assert prng.split(prng.key(0)) == [(1797259609, 2579123966), (928981903, 3453687069)]
+    assert prng.fold_in(prng.key(0), 1) == (928981903, 3453687069)
+    r = prng.Rngs(0)
+    assert r() == prng.fold_in(prng.key(0), 0) and r.count == 1
+
+
+def test_config_fields_mirror_reference_defaults():
+    """algorithms/config.py:11-68 — names and defaults are API."""
+    p = config.PPOConfig()
+    assert dataclasses.asdict(p) | {"logging_level": None} == {
+        "n_envs": 256, "rollout_length": 20, "total_steps": 512_000, "gae_lambda": 0.95,
+        "discounting_factor": 0.99, "clip_range": 0.2, "learning_rate": 1e-4,
+        "normalize_advantages": True, "combine_advantages": False, "n_epochs": 4,
+        "n_minibatches": 4, "critic_loss_weight": 1.0, "gradient_clipping": None,
+        "weight_decay": None, "logging_level": None, "logging_percentiles": None}
+    assert p.logging_level == LoggingLevel.LOSSES
+    t = config.TrainConfig()
+    assert t.seed == 17 and t.checkpoint_every_steps == 500_000
+    assert config.EvalConfig().logging_percentiles == (0, 25, 50, 75, 100)
+    assert ppo._should_run(50_000, 0, 50_000) and not ppo._should_run(49_999, 0, 50_000)
+    assert not ppo._should_run(10, 0, 0)
+
+
+def test_factory_topology_and_init_match_oracle():
+    """factories.py:72-146: Sequential([Normalizer, PPOAdapter]); key-draw order of the init."""
+    from oracle import nets as onets
+    nets = factories.make_mlp_actor_critic(24, 5, [64, 64], [32], prng.Rngs(42), activation="tanh")
+    assert isinstance(nets.layers[0], Normalizer)
+    o = onets.make_mlp_actor_critic(24, 5, [64, 64], [32], seed=42, activation="tanh")
+    actor = nets.layers[1].action.layers
+    for l, (W, b) in zip(actor[:-1], zip(o.actor.W, o.actor.b)):
+        assert np.array_equal(l.linear.kernel.numpy(), W) and np.array_equal(l.linear.bias.numpy(), b)
+    assert actor[-1].rng.count == o.rng_count == 2 * 5
+    bare = factories.make_mlp_actor_critic(4, 1, [8], [8], prng.Rngs(0), normalize_obs=False)
+    assert type(bare).__name__ == "PPOAdapter"
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nnx_ppo_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has CUDA")
+    from nnx_ppo_b200.envs import SyntheticEnv
+    nets = factories.make_mlp_actor_critic(8, 2, [16], [16], prng.Rngs(0))
+    with pytest.raises(_lib.B200PPOError):
+        ppo.new_training_state(SyntheticEnv(8, 2), nets, 16, 0)

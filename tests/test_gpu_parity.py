@@ -1,0 +1,454 @@
+"""GPU parity tests: every CUDA kernel of the hot path, called through the C ABI, against the CPU
+oracle on identical seeded inputs.  Integer / mask / index results must be bit-exact; float
+results must agree to the float32 tolerances written next to each assert.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from nnx_ppo_b200 import _lib, prng as hprng                                     # noqa: E402
+from nnx_ppo_b200 import Rngs                                                      # noqa: E402
+from nnx_ppo_b200.algorithms import ppo, rollout                                   # noqa: E402
+from nnx_ppo_b200.algorithms.config import PPOConfig, TrainConfig, EvalConfig      # noqa: E402
+from nnx_ppo_b200.algorithms.engine import PPOEngine, AdamOptimizer                # noqa: E402
+from nnx_ppo_b200.envs import SyntheticEnv                                         # noqa: E402
+from nnx_ppo_b200.networks.factories import make_mlp_actor_critic                  # noqa: E402
+from nnx_ppo_b200.networks.normalizer import Normalizer                            # noqa: E402
+from nnx_ppo_b200.networks.plan import compile_network                             # noqa: E402
+from oracle import env as oenv, nets as onets, ppo as oppo, prng as oprng          # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_device):
+    from nnx_ppo_b200 import build
+    build.build()
+    _lib.load()
+    return cuda_device
+
+
+def u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# ------------------------------------------------------------------------------------------
+# K7 threefry
+# ------------------------------------------------------------------------------------------
+def test_random_bits_bit_exact(dev):
+    lib = _lib.load()
+    for seed, n in ((0, 1), (7, 1000), (123456789, 100003)):
+        k = oprng.key(seed)
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(lib.b200ppo_random_bits(_lib.current_stream(), int(k[0]), int(k[1]), n, out.data_ptr()))
+        assert np.array_equal(u32(out), oprng.random_bits(k, (n,)))
+    assert lib.b200ppo_random_bits(_lib.current_stream(), 0, 0, 0, 0) == 0       # empty input
+
+
+def test_random_normal_matches_oracle(dev):
+    lib = _lib.load()
+    k = oprng.fold_in(oprng.key(42), 5)
+    n = 1 << 18
+    out = torch.empty(n, device=dev)
+    _lib.check(lib.b200ppo_random_normal(_lib.current_stream(), int(k[0]), int(k[1]), n, out.data_ptr()))
+    ref = oprng.normal(k, (n,))
+    got = out.cpu().numpy()
+    # same bits, same polynomial; only log1p / sqrt rounding differs (float32 tolerance 2e-6 rel)
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------
+# K6 permutation indices — bit exact, incl. n = 1, non powers of two and the global-scratch path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,epochs", [(1, 2), (7, 3), (256, 4), (1024, 4), (4096, 4), (5000, 2),
+                                       (20000, 2)])
+def test_permutation_bit_exact(dev, n, epochs):
+    lib = _lib.load()
+    new_key = oprng.fold_in(oprng.key(17), n)
+    kd = torch.from_numpy(new_key.view(np.int32).copy()).to(dev)
+    out = torch.zeros(epochs, n, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(int(lib.b200ppo_permutation_scratch_bytes(n, epochs)) // 4 + 2,
+                          dtype=torch.int32, device=dev)
+    _lib.check(lib.b200ppo_permutation(_lib.current_stream(), kd.data_ptr(), n, epochs, out.data_ptr(),
+                                       scratch.data_ptr()))
+    got = out.cpu().numpy()
+    for e in range(epochs):
+        ref = oprng.permutation(oprng.fold_in(new_key, e), n)
+        assert np.array_equal(got[e], ref)
+        assert np.array_equal(np.sort(got[e]), np.arange(n))
+
+
+def test_minibatch_indices_match_oracle(dev):
+    lib = _lib.load()
+    new_key = oprng.key(99)
+    ref = oppo.minibatch_indices(new_key, 512, 4, 8)
+    kd = torch.from_numpy(new_key.view(np.int32).copy()).to(dev)
+    out = torch.zeros(4, 512, dtype=torch.int32, device=dev)
+    scratch = torch.zeros(int(lib.b200ppo_permutation_scratch_bytes(512, 4)) // 4 + 2, dtype=torch.int32, device=dev)
+    _lib.check(lib.b200ppo_permutation(_lib.current_stream(), kd.data_ptr(), 512, 4, out.data_ptr(), scratch.data_ptr()))
+    assert np.array_equal(out.cpu().numpy().reshape(32, 64), ref)
+
+
+# ------------------------------------------------------------------------------------------
+# K2 GAE
+# ------------------------------------------------------------------------------------------
+def test_gae_reference_known_answer(dev):
+    """The reference's own test_gae (ppo_test.py:229-264): max |diff| < 1e-6 vs its float64 loop."""
+    g = np.load(os.path.join(GOLDEN, "gae_kat.npz"))
+    T, B = 100, 512
+    done = np.unpackbits(g["done_bits"])[: T * B].reshape(T, B).astype(bool)
+    trunc = np.unpackbits(g["trunc_bits"])[: T * B].reshape(T, B).astype(bool)
+    r = torch.from_numpy(g["rewards_f32"]).to(dev)
+    v = torch.from_numpy(g["values_f32"]).to(dev)
+    adv = ppo.gae(r, v[:-1], v[-1], torch.from_numpy(done).to(dev), torch.from_numpy(trunc).to(dev), 0.95, 0.8)
+    got = adv.cpu().numpy()
+    assert np.abs(got - g["adv_f64"]).max() < 1e-6
+    ref32 = oppo.gae(g["rewards_f32"], g["values_f32"][:-1], g["values_f32"][-1], done, trunc, 0.95, 0.8)
+    assert np.array_equal(got, ref32)          # same op order, no FMA contraction -> bit exact
+
+
+def test_gae_edge_cases(dev):
+    # all-done, all-truncated, T = 1, ragged B (not a multiple of the block size)
+    rs = np.random.default_rng(0)
+    for T, B in ((1, 1), (1, 130), (5, 33), (64, 1000)):
+        r = rs.standard_normal((T, B)).astype(np.float32)
+        v = rs.standard_normal((T + 1, B)).astype(np.float32)
+        for pd in (0.0, 0.3, 1.0):
+            done = rs.random((T, B)) < pd
+            trunc = done & (rs.random((T, B)) < 0.5)
+            ref = oppo.gae(r, v[:-1], v[-1], done, trunc, 0.9, 0.97)
+            got = ppo.gae(torch.from_numpy(r).to(dev), torch.from_numpy(v[:-1]).to(dev),
+                          torch.from_numpy(v[-1]).to(dev), torch.from_numpy(done).to(dev),
+                          torch.from_numpy(trunc).to(dev), 0.9, 0.97).cpu().numpy()
+            assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------
+# K5 Normalizer
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("O,T,B", [(8, 5, 16), (5, 30, 1024), (64, 32, 4096), (300, 3, 77)])
+def test_normalizer_statistics(dev, O, T, B):
+    """normalizer_test.py:42-65 / factories_test.py:76-119: moments within 1e-5; counter == T*B;
+    a second merge equals the oracle's Chan merge."""
+    g = np.random.default_rng(O)
+    data = (g.standard_normal(O) * 3 + g.standard_normal((T, B, O)) * (1 + g.random(O))).astype(np.float32)
+    nz = Normalizer(O)
+    nz.update_statistics(torch.from_numpy(data).to(dev))
+    onet = onets.make_mlp_actor_critic(O, 1, [4], [4], seed=0)
+    onet.update_statistics(data)
+    assert float(nz.counter.numpy()[0]) == T * B == float(onet.counter)
+    mean, M2 = nz.mean.numpy(), nz.M2.numpy()
+    assert np.abs(mean - data.mean(axis=(0, 1))).max() < 1e-5
+    assert np.abs(np.sqrt(M2 / (T * B)) - data.std(axis=(0, 1))).max() < 1e-5
+    assert np.allclose(mean, onet.mean, rtol=1e-5, atol=1e-6) and np.allclose(M2, onet.M2, rtol=2e-5)
+    data2 = (1.5 + 0.5 * g.standard_normal((T, B, O))).astype(np.float32)
+    nz.update_statistics(torch.from_numpy(data2).to(dev))
+    onet.update_statistics(data2)
+    assert float(nz.counter.numpy()[0]) == 2 * T * B
+    assert np.allclose(nz.mean.numpy(), onet.mean, rtol=1e-5, atol=1e-6)
+    assert np.allclose(nz.M2.numpy(), onet.M2, rtol=3e-5)
+    nz.prepare()
+    torch.cuda.synchronize()
+    assert np.allclose(nz._std.cpu().numpy(), onet.norm_std(), rtol=2e-5)
+
+
+def test_normalizer_default_std_is_ten(dev):
+    """normalizer_test.py:33-40: before any update the forward divides by 10."""
+    nets = make_mlp_actor_critic(4, 2, [8], [8], Rngs(0))
+    net = compile_network(nets)
+    net.normalizer.prepare()
+    torch.cuda.synchronize()
+    assert np.array_equal(net.normalizer._std.cpu().numpy(), np.full(4, 10.0, np.float32))
+
+
+# ------------------------------------------------------------------------------------------
+# K1 policy step (sample / replay / deterministic)
+# ------------------------------------------------------------------------------------------
+def _pair(obs_dim, act_dim, ah, ch, seed, act="relu", **kw):
+    nets = make_mlp_actor_critic(obs_dim, act_dim, ah, ch, Rngs(seed), activation=act, **kw)
+    onet = onets.make_mlp_actor_critic(obs_dim, act_dim, ah, ch, seed=seed, activation=act, **kw)
+    return nets, onet
+
+
+@pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=300, act="relu"),
+                                  dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=33, act="tanh"),
+                                  dict(O=24, A=5, ah=[48, 40], ch=[72], B=64, act="swish")])
+def test_policy_step_matches_oracle(dev, cfg):
+    nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 3, cfg["act"])
+    g = np.random.default_rng(1)
+    # give the normalizer non-trivial statistics on both sides
+    hist = (2 + 3 * g.standard_normal((4, 50, cfg["O"]))).astype(np.float32)
+    nets.layers[0].update_statistics(torch.from_numpy(hist).to(dev))
+    onet.update_statistics(hist)
+    obs = (2 + 3 * g.standard_normal((cfg["B"], cfg["O"]))).astype(np.float32)
+    state = nets.initialize_state(cfg["B"])
+    out = nets(state, torch.from_numpy(obs).to(dev))
+    ref = onets.policy_forward(onet, obs)
+    po = out.output
+    tol = dict(rtol=2e-5, atol=2e-5)       # float32: summation order + libm differences
+    assert np.allclose(out.rollout_extras[1]["action"][-1].cpu().numpy(), ref["raw_action"], **tol)
+    assert np.allclose(po.actions.cpu().numpy(), ref["action"], **tol)
+    assert np.allclose(po.loglikelihoods.cpu().numpy(), ref["loglik"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(po.value_estimates.cpu().numpy(), ref["value"], **tol)
+    assert np.allclose(out.regularization_loss.cpu().numpy(), ref["reg"], rtol=1e-4, atol=1e-5)
+    assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+    # replay (adapter_test.py:61-75): same weights + stored extras -> same actions and log-probs
+    out2 = nets(state, torch.from_numpy(obs).to(dev), out.rollout_extras)
+    assert torch.equal(out2.output.actions, po.actions)
+    assert torch.allclose(out2.output.loglikelihoods, po.loglikelihoods, rtol=0, atol=0)
+    onets.policy_forward(onet, obs, raw_action=ref["raw_action"])
+    # deterministic (eval mode): action = tanh(mean); one RNG count per call
+    nets.eval()
+    c0 = nets.layers[1].action.layers[-1].rng.count
+    out3 = nets(state, torch.from_numpy(obs).to(dev))
+    nets.train()
+    ref3 = onets.policy_forward(onet, obs, deterministic=True)
+    assert np.allclose(out3.output.actions.cpu().numpy(), np.tanh(ref3["mu"]), **tol)
+    assert nets.layers[1].action.layers[-1].rng.count == c0 + 1
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic env reset + fused rollout
+# ------------------------------------------------------------------------------------------
+def _oracle_state(oe, onet, B, seed):
+    return oppo.new_training_state(oe, onet, B, seed)
+
+
+def test_env_reset_matches_oracle(dev):
+    env = SyntheticEnv(64, 8, max_len=64)
+    oe = oenv.SyntheticEnv(64, 8, max_len=64)
+    k = hprng.split(hprng.key(5))[0]
+    st = env.reset_from_split(k, 1000, dev)
+    keys = oprng.split(np.array(k, np.uint32), 1000)
+    ref = oe.reset(keys)
+    ref_fast = oe.reset_fast(keys)
+    assert np.array_equal(ref.step_counter, ref_fast.step_counter)
+    assert np.array_equal(st.step_counter.cpu().numpy(), ref.step_counter)            # bit exact
+    assert np.array_equal(u32(st.term_state), ref.term_state)                          # bit exact
+    assert np.allclose(st.obs.cpu().numpy(), ref.obs, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=200, T=40, max_len=24, thr=1500),
+                                  dict(O=5, A=1, ah=[32, 32], ch=[32], B=64, T=30, max_len=16, thr=3000),
+                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=31, T=9, max_len=8, thr=0)])
+def test_fused_rollout_matches_oracle(dev, cfg):
+    nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 11)
+    env = SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
+    oe = oenv.SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
+    ts = ppo.new_training_state(env, nets, cfg["B"], 17)
+    ots = _oracle_state(oe, onet, cfg["B"], 17)
+    assert tuple(int(x) for x in ots.rng_key) == tuple(ts.rng_key)
+    reset_key, _ = hprng.split(ts.rng_key)
+    _, env2, tr = rollout.unroll_env(env, ts.env_states, nets, ts.network_states, cfg["T"], reset_key)
+    oenv2, oro = oppo.unroll_env(oe, ots.env_state, onet, cfg["T"], np.array(reset_key, np.uint32))
+    # reset masks and episode bookkeeping: bit exact
+    assert np.array_equal(tr.done.cpu().numpy(), oro.done)
+    assert np.array_equal(tr.truncated.cpu().numpy(), oro.truncated)
+    assert np.array_equal(env2.step_counter.cpu().numpy(), oenv2.step_counter)
+    assert np.array_equal(u32(env2.term_state), oenv2.term_state)
+    assert oro.done.sum() > 0 and (cfg["thr"] == 0 or (oro.done & ~oro.truncated).sum() > 0)
+    assert oro.truncated.sum() > 0
+    # floats: float32 tolerance (errors accumulate over T steps of the env recurrence)
+    tol = dict(rtol=2e-4, atol=2e-4)
+    assert np.allclose(tr.obs.cpu().numpy(), oro.obs, **tol)
+    assert np.allclose(tr.rollout_extras[1]["action"][-1].cpu().numpy(), oro.raw_action, **tol)
+    assert np.allclose(tr.network_output.actions.cpu().numpy(), oro.action, **tol)
+    assert np.allclose(tr.network_output.loglikelihoods.cpu().numpy(), oro.loglik, rtol=1e-3, atol=1e-3)
+    assert np.allclose(tr.network_output.value_estimates.cpu().numpy(), oro.value, **tol)
+    assert np.allclose(tr.rewards.cpu().numpy(), oro.reward, **tol)
+    assert np.allclose(tr.next_obs.cpu().numpy(), oro.next_obs_last, **tol)
+    assert np.allclose(env2.obs.cpu().numpy(), oenv2.obs, **tol)
+    assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+
+
+# ------------------------------------------------------------------------------------------
+# K3/K4 one minibatch update against the oracle's loss + analytic gradients + Adam
+# ------------------------------------------------------------------------------------------
+def _dbg(eng, which, n):
+    p = eng.lib.b200ppo_update_debug_ptr(eng.net.plan, eng.T, eng.mb, eng.ws.data_ptr(), which)
+    off = (p - eng.ws.data_ptr()) // 4
+    return eng.ws[off:off + n].cpu().numpy()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, M=2, act="relu", clip=None, wd=None),
+    dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=96, T=30, M=2, act="tanh", clip=0.5, wd=None),
+    dict(O=24, A=5, ah=[48, 40], ch=[72], B=70, T=7, M=2, act="swish", clip=None, wd=1e-3),
+    dict(O=300, A=3, ah=[32], ch=[20, 20], B=40, T=5, M=1, act="relu", clip=None, wd=None)])
+def test_single_update_matches_oracle(dev, cfg):
+    O, A, B, T, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["M"]
+    nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
+    env = SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
+    oe = oenv.SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
+    ts = ppo.new_training_state(env, nets, B, 3, learning_rate=1e-3, gradient_clipping=cfg["clip"],
+                                weight_decay=cfg["wd"])
+    ots = _oracle_state(oe, onet, B, 3)
+    net = compile_network(nets)
+    # non-trivial normalizer statistics on both sides
+    g = np.random.default_rng(2)
+    hist = (g.standard_normal((3, 40, O))).astype(np.float32)
+    net.normalizer.update_statistics(torch.from_numpy(hist).to(dev))
+    onet.update_statistics(hist)
+    eng = PPOEngine(net, env, ts.optimizer, B, T, 1, M, 0.95, 0.99, 0.2, True, 1.0, use_graph=False)
+    reset_key, new_key = hprng.split(ts.rng_key)
+    k = np.array([*reset_key, *new_key], np.uint32).view(np.int32)
+    eng.iter_keys.copy_(torch.from_numpy(k.copy()))
+    net.sync_counters_to_device()
+    eng._enqueue_rollout(ts.env_states)
+    lib = eng.lib
+    _lib.check(lib.b200ppo_permutation(_lib.current_stream(), eng.iter_keys.data_ptr() + 8, B, 1,
+                                       eng.inds.data_ptr(), eng.perm_scratch.data_ptr()))
+    # oracle: same rollout, same indices
+    _, oro = oppo.unroll_env(oe, ots.env_state, onet, T, np.array(reset_key, np.uint32))
+    oinds = oppo.minibatch_indices(np.array(new_key, np.uint32), B, 1, M)
+    assert np.array_equal(eng.inds.cpu().numpy().reshape(M, B // M), oinds)
+    # make a good fraction of samples clip: perturb the stored old log-probs on both sides
+    noise = (0.3 * g.standard_normal((T, B))).astype(np.float32)
+    eng.loglik += torch.from_numpy(noise).to(dev)
+    # use the GPU rollout as THE rollout on both sides so this test isolates the update kernels
+    oro.obs[:] = eng.obs.cpu().numpy(); oro.raw_action[:] = eng.raw_action.cpu().numpy()
+    oro.loglik[:] = eng.loglik.cpu().numpy(); oro.reward[:] = eng.reward.cpu().numpy()
+    oro.next_obs_last[:] = eng.next_obs_last.cpu().numpy()
+    mb = B // M
+    base = onet.rng_count
+    total, m, grads = oppo.ppo_loss_and_grads(onet, oro, oinds[0], base)
+    _lib.check(lib.b200ppo_update(_lib.current_stream(), net.plan, eng.hp, eng.bufs[0], T, B, mb, 2 * T, 0,
+                                  _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED))
+    torch.cuda.synchronize()
+    R = T * mb
+    tol = dict(rtol=1e-4, atol=1e-5)
+    assert np.allclose(_dbg(eng, 1, R + mb)[:R].reshape(T, mb), m["values"], **tol)
+    assert np.allclose(_dbg(eng, 1, R + mb)[R:], m["v_last"], **tol)
+    assert np.allclose(_dbg(eng, 0, R).reshape(T, mb), m["adv"], rtol=1e-4, atol=1e-4)       # advantages
+    sums = eng.adv_sums.cpu().numpy()
+    assert abs(sums[0] / R - m["adv_mean"]) < 1e-5 and abs(np.sqrt(sums[1] / R - (sums[0] / R) ** 2) - m["adv_std"]) < 1e-4
+    met = eng.metrics[0].cpu().numpy()
+    assert abs(met[0] - m["losses/actor"]) < 1e-5 and abs(met[1] - m["losses/critic"]) < 1e-4 * max(1, abs(m["losses/critic"]))
+    assert abs(met[2] - m["losses/regularization"]) < 1e-5
+    dy = _dbg(eng, 3, R * 2 * A).reshape(R, 2 * A)
+    assert np.abs(dy - m["d_y"]).max() < 1e-4 * max(np.abs(m["d_y"]).max(), 1e-6) + 1e-9
+    dv = _dbg(eng, 4, R)
+    assert np.abs(dv - m["d_v"]).max() < 1e-4 * np.abs(m["d_v"]).max() + 1e-10
+    got_g = net.params_logical(eng.grad)
+    gs = np.abs(grads).max()
+    assert np.abs(got_g - grads).max() < 2e-4 * gs, (np.abs(got_g - grads).max(), gs)
+    # K4: optax update from the SAME gradient on both sides
+    p_before = net.params_logical()
+    ost = oppo.AdamState(np.zeros_like(p_before), np.zeros_like(p_before), 0)
+    p_ref = oppo.adam_update(p_before, got_g, ost, lr=1e-3, gradient_clipping=cfg["clip"], weight_decay=cfg["wd"])
+    _lib.check(lib.b200ppo_update(_lib.current_stream(), net.plan, eng.hp, eng.bufs[0], T, B, mb, 2 * T, 0,
+                                  _lib.STAGE_ADAM))
+    torch.cuda.synchronize()
+    p_after = net.params_logical()
+    assert np.abs(p_after - p_ref).max() < 2e-7, np.abs(p_after - p_ref).max()
+    assert np.abs(net.params_logical(ts.optimizer.mu) - ost.mu).max() < 1e-7 * max(1.0, gs)
+    if cfg["clip"] is not None:
+        assert abs(eng.metrics[0, 3].item() - np.sqrt((got_g.astype(np.float64) ** 2).sum())) < 1e-4 * max(1, gs)
+
+
+# ------------------------------------------------------------------------------------------
+# full iterations through the public API (eager first iteration, captured graph afterwards)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, E=2, M=4, iters=3),
+    dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=128, T=30, E=4, M=4, iters=2)])
+def test_ppo_step_matches_oracle_over_iterations(dev, cfg):
+    O, A, B, T, E, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["E"], cfg["M"]
+    nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
+    env = SyntheticEnv(O, A, max_len=48, term_thresh16=700)
+    oe = oenv.SyntheticEnv(O, A, max_len=48, term_thresh16=700)
+    ts = ppo.new_training_state(env, nets, B, 17)
+    ots = _oracle_state(oe, onet, B, 17)
+    net = compile_network(nets)
+    for it in range(cfg["iters"]):
+        ts, metrics = ppo.ppo_step(env, ts, B, T, 0.95, 0.99, 0.2, True, False, E, M)
+        tr = {}
+        ots, om = oppo.ppo_step(oe, ots, B, T, n_epochs=E, n_minibatches=M, trace=tr)
+        eng = next(iter(net.engines.values()))
+        # bit exact: minibatch permutation indices, reset masks, episode bookkeeping, counters
+        assert np.array_equal(eng.inds.cpu().numpy().reshape(E * M, B // M), tr["indices"])
+        assert np.array_equal(eng.done.cpu().numpy().astype(bool), tr["rollout"].done)
+        assert np.array_equal(eng.trunc.cpu().numpy().astype(bool), tr["rollout"].truncated)
+        assert np.array_equal(ts.env_states.step_counter.cpu().numpy(), ots.env_state.step_counter)
+        assert np.array_equal(u32(ts.env_states.term_state), ots.env_state.term_state)
+        assert tuple(ts.rng_key) == tuple(int(x) for x in ots.rng_key)
+        assert float(ts.steps_taken) == float(ots.steps_taken) == (it + 1) * T * B
+        assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+        cnt = u32(net.counters)
+        assert cnt[2] == onet.rng_count and cnt[3] == (it + 1) * E * M == ots.opt.count
+        assert float(net.normalizer.counter.numpy()[0]) == (it + 1) * T * B            # ppo_test.py:344-349
+        # float32 tolerance
+        for k in ("losses/actor/mean", "losses/critic/mean", "losses/regularization/mean"):
+            assert abs(metrics[k] - om[k]) < 2e-4 * max(1.0, abs(om[k])), (k, metrics[k], om[k])
+        p, po = net.params_logical(), onet.flat_params()
+        # Adam moves each parameter by at most lr per update; rounding differences in tiny
+        # gradients can flip individual steps, so compare against a few-steps budget
+        assert np.abs(p - po).max() < 1e-4 * 4, np.abs(p - po).max()
+        assert np.mean(np.abs(p - po)) < 2e-6
+        assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-5)
+        assert np.allclose(net.normalizer.M2.numpy(), onet.M2, rtol=1e-3)
+        assert np.allclose(ts.env_states.obs.cpu().numpy(), ots.env_state.obs, rtol=1e-3, atol=1e-3)
+    assert eng.graph is not None            # iterations >= 2 ran from the captured CUDA graph
+
+
+def test_train_ppo_api(dev):
+    """ppo_test.py:213-227 / 307-349 style: total steps, counter, finite metrics, log cadence."""
+    env = SyntheticEnv(16, 4, max_len=32)
+    nets = make_mlp_actor_critic(16, 4, [32, 32], [32, 32], Rngs(1))
+    logged = []
+    ckpts = []
+    cfgt = TrainConfig(ppo=PPOConfig(n_envs=64, rollout_length=10, total_steps=64 * 10 * 5, n_minibatches=4),
+                       eval=EvalConfig(enabled=False), checkpoint_every_steps=64 * 10 * 2)
+    res = ppo.train_ppo(env, nets, cfgt, seed=3, log_fn=lambda m, s: logged.append((s, dict(m))),
+                        checkpoint_fn=lambda st, s: ckpts.append(s))
+    assert res.total_steps == 64 * 10 * 5 and res.total_iterations == 5
+    assert [s for s, _ in logged] == [640 * i for i in range(1, 6)]
+    assert ckpts == [0, 1280, 2560]
+    assert all(np.isfinite(v) for _, m in logged for v in m.values())
+    assert float(nets.layers[0].counter.numpy()[0]) == 3200
+    p = compile_network(nets).params_logical()
+    assert np.isfinite(p).all()
+    with pytest.raises(ValueError):
+        ppo.new_training_state(env, nets, 30, 0) and ppo.ppo_step(env, ppo.new_training_state(env, nets, 30, 0),
+                                                                  30, 4, .95, .99, .2, True, False, 1, 4)
+
+
+def test_eval_rollout_bookkeeping(dev):
+    """rollout.py:97-148 on a batched torch env: sticky done, lifespan and reward accumulation."""
+    import dataclasses
+
+    @dataclasses.dataclass
+    class S:
+        obs: torch.Tensor
+        reward: torch.Tensor
+        done: torch.Tensor
+        info: dict
+        metrics: dict
+        t: torch.Tensor
+
+    class CountEnv:
+        observation_size, action_size = 3, 2
+
+        def reset(self, keys):
+            B = keys.shape[0]
+            life = (keys[:, 0].abs() % 5 + 2).float()
+            return S(torch.zeros(B, 3, device=keys.device), torch.zeros(B, device=keys.device),
+                     torch.zeros(B, device=keys.device), {"life": life}, {}, torch.zeros(B, device=keys.device))
+
+        def step(self, s, a):
+            t = s.t + 1
+            return S(s.obs, torch.ones_like(t), (t >= s.info["life"]).float(), s.info, {}, t)
+
+    env = CountEnv()
+    nets = make_mlp_actor_critic(3, 2, [8], [8], Rngs(0))
+    m = rollout.eval_rollout(env, nets, 32, 12, hprng.key(4), None)
+    keys = rollout.split_keys_device(hprng.key(4), 32, dev)
+    life = (keys[:, 0].abs() % 5 + 2).float()
+    # lifespan counts the steps before the first done; reward also counts the terminal step
+    assert abs(m["lifespan_mean"] - float((life - 1).mean())) < 1e-6
+    assert abs(m["episode_reward/mean"] - float(life.mean())) < 1e-6

@@ -244,7 +244,7 @@ def run_own(args):
                 "clocks": clock_info,
                 "final_metrics": {k: float(v) for k, v in metrics.items()}}
     # ---- roofline of the dominant kernel + cpu baseline: N = 1 only ----
-    if world == 1:
+    if world == 1 and not args.quick:
         # FFMA peak probe (fp32 CUDA-core ceiling; not in MEASURED_PEAKS.json)
         blocks, threads, iters = 148 * 8, 256, 20000
         sink = torch.zeros(blocks * threads, device="cuda")
@@ -302,6 +302,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-envs", type=int, default=512)
+    ap.add_argument("--quick", action="store_true", help="skip the roofline stage timing and the CPU baseline (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

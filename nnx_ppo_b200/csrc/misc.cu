@@ -165,18 +165,32 @@ gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
   if (b >= B) return;
   float next_adv = 0.0f;
   float next_val = last_value[b];
-#pragma unroll 4
-  for (int t = T - 1; t >= 0; --t) {
-    const size_t i = static_cast<size_t>(t) * B + b;
-    const float r = rewards[i], v = values[i];
-    const bool d = done[i] != 0, tr = trunc[i] != 0;
-    const float nv = d ? 0.0f : next_val;
-    float a = __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, nv)), v);
-    a = tr ? 0.0f : a;
-    const float nd = d ? 0.0f : 1.0f;
-    next_adv = __fadd_rn(a, __fmul_rn(__fmul_rn(__fmul_rn(nd, gamma), lambda_), next_adv));
-    adv[i] = next_adv;
-    next_val = v;
+  constexpr int CH = 8;   // loads of a chunk are independent of the recurrence: issue them first
+  for (int t0 = T - 1; t0 >= 0; t0 -= CH) {
+    float rr[CH], vv[CH];
+    uint8_t dd[CH], tt[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int t = t0 - i;
+      if (t >= 0) {
+        const size_t gi = static_cast<size_t>(t) * B + b;
+        rr[i] = rewards[gi]; vv[i] = values[gi]; dd[i] = done[gi]; tt[i] = trunc[gi];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int t = t0 - i;
+      if (t >= 0) {
+        const bool d = dd[i] != 0, tr = tt[i] != 0;
+        const float nv = d ? 0.0f : next_val;
+        float a = __fsub_rn(__fadd_rn(rr[i], __fmul_rn(gamma, nv)), vv[i]);
+        a = tr ? 0.0f : a;
+        const float nd = d ? 0.0f : 1.0f;
+        next_adv = __fadd_rn(a, __fmul_rn(__fmul_rn(__fmul_rn(nd, gamma), lambda_), next_adv));
+        adv[static_cast<size_t>(t) * B + b] = next_adv;
+        next_val = vv[i];
+      }
+    }
   }
 }
 

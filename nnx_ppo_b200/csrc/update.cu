@@ -122,13 +122,26 @@ __device__ __forceinline__ void gemm_rowtile(float* __restrict__ As, float* __re
         // transposed, conflict-free staging: a warp moves 4 rows x 8 k per step
         const int nkg = kc_pad >> 3;
         const int units = (TM / 4) * nkg;
-#pragma unroll 4
-        for (int u = warp; u < units; u += NTH / 32) {
-          const int rg = u / nkg, kg = u - rg * nkg;
-          const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
-          float v = 0.0f;
-          if (row0 + r < nrows && k < kc) v = act_fwd(A[static_cast<size_t>(row0 + r) * lda + k0 + k], act_in);
-          As[k * LDA + r] = v;
+        // all AB loads of a batch are issued before the first one is consumed (memory-level
+        // parallelism); the activation is applied at the shared-memory store
+        constexpr int AB = 16;
+        for (int u0 = warp; u0 < units; u0 += (NTH / 32) * AB) {
+          float v[AB];
+#pragma unroll
+          for (int j = 0; j < AB; ++j) {
+            const int u = u0 + j * (NTH / 32);
+            const int rg = u / nkg, kg = u - rg * nkg;
+            const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+            v[j] = 0.0f;
+            if (u < units && row0 + r < nrows && k < kc) v[j] = A[static_cast<size_t>(row0 + r) * lda + k0 + k];
+          }
+#pragma unroll
+          for (int j = 0; j < AB; ++j) {
+            const int u = u0 + j * (NTH / 32);
+            const int rg = u / nkg, kg = u - rg * nkg;
+            const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+            if (u < units) As[k * LDA + r] = act_fwd(v[j], act_in);
+          }
         }
         __syncthreads();
       }
@@ -192,13 +205,24 @@ __device__ __forceinline__ void gemm_thin(float* __restrict__ As, const float* _
   const int kc_pad = (K + 7) & ~7;
   const int nkg = kc_pad >> 3;
   const int units = (TM / 4) * nkg;
-#pragma unroll 4
-  for (int u = warp; u < units; u += NTH / 32) {
-    const int rg = u / nkg, kg = u - rg * nkg;
-    const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
-    float v = 0.0f;
-    if (row0 + r < nrows && k < K) v = act_fwd(A[static_cast<size_t>(row0 + r) * lda + k], act_in);
-    As[k * LDA + r] = v;
+  constexpr int AB = 16;
+  for (int u0 = warp; u0 < units; u0 += (NTH / 32) * AB) {
+    float v[AB];
+#pragma unroll
+    for (int j = 0; j < AB; ++j) {
+      const int u = u0 + j * (NTH / 32);
+      const int rg = u / nkg, kg = u - rg * nkg;
+      const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+      v[j] = 0.0f;
+      if (u < units && row0 + r < nrows && k < K) v[j] = A[static_cast<size_t>(row0 + r) * lda + k];
+    }
+#pragma unroll
+    for (int j = 0; j < AB; ++j) {
+      const int u = u0 + j * (NTH / 32);
+      const int rg = u / nkg, kg = u - rg * nkg;
+      const int r = rg * 4 + (lane >> 3), k = kg * 8 + (lane & 7);
+      if (u < units) As[k * LDA + r] = act_fwd(v[j], act_in);
+    }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < TM * N; idx += NTH) {
@@ -262,20 +286,39 @@ __global__ void __launch_bounds__(NTH, 1) upd_fwd_kernel(const FwdArgs a) {
   const int R = a.L.R, Rv = a.L.Rv;
   float* xhat = a.ws + a.L.xhat;
   // gather + normalise this tile's observations (ppo.py:297 gather; normalizer.py:78-80)
-  for (int idx = threadIdx.x; idx < TM * O; idx += NTH) {
-    const int m = idx / O, k = idx - m * O;
+  // per-row source pointers once per tile, then batched coalesced copies
+  const float** rowsrc = reinterpret_cast<const float**>(Bs);
+  for (int m = threadIdx.x; m < TM; m += NTH) {
     const int r = row0 + m;
-    if (r < Rv) {
-      const float* src;
-      if (r < R) {
-        const int t = r / a.mb, j = r - t * a.mb;
-        src = a.obs + (static_cast<size_t>(t) * a.B + a.inds[j]) * O;
-      } else {
-        src = a.next_obs_last + static_cast<size_t>(a.inds[r - R]) * O;
+    const float* src = nullptr;
+    if (r < R) {
+      const int t = r / a.mb, j = r - t * a.mb;
+      src = a.obs + (static_cast<size_t>(t) * a.B + a.inds[j]) * O;
+    } else if (r < Rv) {
+      src = a.next_obs_last + static_cast<size_t>(a.inds[r - R]) * O;
+    }
+    rowsrc[m] = src;
+  }
+  __syncthreads();
+  constexpr int XB = 8;
+  for (int i0 = threadIdx.x; i0 < TM * O; i0 += NTH * XB) {
+    float xv[XB];
+#pragma unroll
+    for (int j = 0; j < XB; ++j) {
+      const int idx = i0 + j * NTH;
+      const int m = idx / O, k = idx - m * O;
+      xv[j] = 0.0f;
+      if (idx < TM * O && rowsrc[m] != nullptr) xv[j] = rowsrc[m][k];
+    }
+#pragma unroll
+    for (int j = 0; j < XB; ++j) {
+      const int idx = i0 + j * NTH;
+      const int m = idx / O, k = idx - m * O;
+      if (idx < TM * O && rowsrc[m] != nullptr) {
+        float x = xv[j];
+        if (a.plan.normalize) x = __fdiv_rn(x - __ldg(a.mean + k), __ldg(a.std + k));
+        xhat[static_cast<size_t>(row0 + m) * O + k] = x;
       }
-      float x = src[k];
-      if (a.plan.normalize) x = __fdiv_rn(x - __ldg(a.mean + k), __ldg(a.std + k));
-      xhat[static_cast<size_t>(r) * O + k] = x;
     }
   }
   __syncthreads();
@@ -294,34 +337,53 @@ struct GaeArgs {
   float gamma, lambda_;
 };
 
-__global__ void __launch_bounds__(128) upd_gae_kernel(const GaeArgs a) {
+constexpr int GAE_THREADS = 64;
+constexpr int GAE_CHUNK = 8;
+
+__global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
   __shared__ double red[2][4];
   __shared__ bool is_last;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const float* v = a.ws + a.v_off;
   float* adv = a.ws + a.L.adv;
   double s1 = 0.0, s2 = 0.0;
+  if (threadIdx.x < 4) { red[0][threadIdx.x] = 0.0; red[1][threadIdx.x] = 0.0; }
   if (j < a.mb) {
     const int e = a.inds[j];
     float next_adv = 0.0f;
     float next_val = v[static_cast<size_t>(a.L.R) + j];
-#pragma unroll 4
-    for (int t = a.T - 1; t >= 0; --t) {
-      const size_t gi = static_cast<size_t>(t) * a.B + e;
-      const size_t ri = static_cast<size_t>(t) * a.mb + j;
-      const float r = a.reward[gi], val = v[ri];
-      const bool d = a.done[gi] != 0, tr = a.trunc[gi] != 0;
-      const float nv = d ? 0.0f : next_val;
-      float ad = __fsub_rn(__fadd_rn(r, __fmul_rn(a.gamma, nv)), val);
-      ad = tr ? 0.0f : ad;
-      const float nd = d ? 0.0f : 1.0f;
-      next_adv = __fadd_rn(ad, __fmul_rn(__fmul_rn(__fmul_rn(nd, a.gamma), a.lambda_), next_adv));
-      adv[ri] = next_adv;
-      next_val = val;
-      s1 += next_adv;
-      s2 += static_cast<double>(next_adv) * next_adv;
+    // loads of a chunk of time steps are independent of the recurrence: issue them all first
+    for (int t0 = a.T - 1; t0 >= 0; t0 -= GAE_CHUNK) {
+      float rr[GAE_CHUNK], vv[GAE_CHUNK];
+      uint8_t dd[GAE_CHUNK], tt[GAE_CHUNK];
+#pragma unroll
+      for (int i = 0; i < GAE_CHUNK; ++i) {
+        const int t = t0 - i;
+        if (t >= 0) {
+          const size_t gi = static_cast<size_t>(t) * a.B + e;
+          rr[i] = a.reward[gi]; dd[i] = a.done[gi]; tt[i] = a.trunc[gi];
+          vv[i] = v[static_cast<size_t>(t) * a.mb + j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < GAE_CHUNK; ++i) {
+        const int t = t0 - i;
+        if (t >= 0) {
+          const bool d = dd[i] != 0, tr = tt[i] != 0;
+          const float nv = d ? 0.0f : next_val;
+          float ad = __fsub_rn(__fadd_rn(rr[i], __fmul_rn(a.gamma, nv)), vv[i]);
+          ad = tr ? 0.0f : ad;
+          const float nd = d ? 0.0f : 1.0f;
+          next_adv = __fadd_rn(ad, __fmul_rn(__fmul_rn(__fmul_rn(nd, a.gamma), a.lambda_), next_adv));
+          adv[static_cast<size_t>(t) * a.mb + j] = next_adv;
+          next_val = vv[i];
+          s1 += next_adv;
+          s2 += static_cast<double>(next_adv) * next_adv;
+        }
+      }
     }
   }
+  __syncthreads();
   s1 = warp_sum_d(s1);
   s2 = warp_sum_d(s2);
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
@@ -558,7 +620,7 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
       const int r = rc + lr + 4 * i;
       float va = 0.0f, vb = 0.0f;
       if (r < r_end) {
-        if (k0 + lc < K) va = act_fwd(H[static_cast<size_t>(r) * K + k0 + lc], act_in);
+        if (k0 + lc < K) va = H[static_cast<size_t>(r) * K + k0 + lc];
         if (n0 + lc < N) vb = D[static_cast<size_t>(r) * N + n0 + lc];
       }
       ra[i] = va;
@@ -568,7 +630,7 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
   auto store = [&](int buf) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      As[(buf * DW_R + lr + 4 * i) * DW_LD + lc] = ra[i];
+      As[(buf * DW_R + lr + 4 * i) * DW_LD + lc] = act_fwd(ra[i], act_in);
       Bs[(buf * DW_R + lr + 4 * i) * DW_LD + lc] = rb[i];
     }
   };
@@ -770,7 +832,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   rc = set_attrs();
   if (rc) return rc;
   const Layout L = make_layout(*plan, T, mb);
-  if (cdiv(mb, 128) > MAX_PART_BLOCKS || cdiv(L.R, 128) > MAX_LOSS_BLOCKS) return B200PPO_ELIMIT;
+  if (cdiv(mb, GAE_THREADS) > MAX_PART_BLOCKS || cdiv(L.R, 128) > MAX_LOSS_BLOCKS) return B200PPO_ELIMIT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(b->ws);
   const size_t v_off = L.zc[plan->critic.n_layers - 1];
@@ -792,7 +854,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     GaeArgs a;
     a.L = L; a.reward = b->reward; a.done = b->done; a.trunc = b->truncated; a.inds = b->inds;
     a.ws = ws; a.v_off = v_off; a.T = T; a.B = B; a.mb = mb; a.gamma = hp->gamma; a.lambda_ = hp->lambda_;
-    upd_gae_kernel<<<cdiv(mb, 128), 128, 0, s>>>(a);
+    upd_gae_kernel<<<cdiv(mb, GAE_THREADS), GAE_THREADS, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_LOSS) {

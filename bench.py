@@ -291,8 +291,14 @@ def run_own(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear down without running NCCL communicator destructors: destroying a communicator whose
+        # kernels are still referenced by a captured CUDA graph hung the process at exit on B200
+        # (driver 580.159, NCCL 2.28.9).  Everything is flushed and synchronised, so exit hard.
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

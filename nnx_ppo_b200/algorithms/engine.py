@@ -19,7 +19,7 @@ from typing import Optional
 
 import numpy as np
 
-from .. import _lib
+from .. import _lib, parallel
 from ..networks.plan import CompiledNet
 
 
@@ -131,8 +131,7 @@ class PPOEngine:
 
     # ------------------------------------------------------------------------------------
     def _allreduce(self, t):
-        import torch.distributed as dist
-        dist.all_reduce(t, group=self.group)
+        parallel.all_reduce_sum(t, self.group)
 
     def _enqueue(self, env_state) -> int:
         """Enqueue one whole iteration on the current stream.  Returns the number of kernel
@@ -188,8 +187,7 @@ class PPOEngine:
                        "norm_batch_stats"); n += 2
             src = self.batch_stats
             if self.world > 1:
-                import torch.distributed as dist
-                dist.all_gather_into_tensor(self.batch_stats_all, self.batch_stats, group=self.group)
+                parallel.all_gather_into(self.batch_stats_all.view(-1), self.batch_stats, self.group)
                 src = self.batch_stats_all
             _lib.check(lib.b200ppo_norm_merge(s, src.data_ptr(), self.world, float(T * B), nz.size,
                                               nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),

@@ -11,7 +11,7 @@ from typing import Any, Optional
 
 import numpy as np
 
-from .. import _lib, prng
+from .. import _lib, parallel, prng
 from ..networks.plan import compile_network
 from ..networks.types import StatefulModule
 from . import rollout
@@ -32,13 +32,7 @@ def _should_run(steps: int, last_step: int, every_steps: int) -> bool:
 
 def _dist_info():
     """(world_size, process_group) when torch.distributed is initialised, else (1, None)."""
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist.get_world_size(), None
-    except Exception:
-        pass
-    return 1, None
+    return parallel.dist_info()[0], None
 
 
 def new_training_state(env: RLEnv, networks: StatefulModule, n_envs: int, seed: int,
@@ -48,14 +42,7 @@ def new_training_state(env: RLEnv, networks: StatefulModule, n_envs: int, seed: 
     function on its own env shard: rank r folds r into the seed-derived keys (rank 0 is
     bit-identical to a single-process run)."""
     net = compile_network(networks)
-    key = prng.key(seed)
-    key, training_key = prng.split(key)                                  # ppo.py:544-545
-    world, _ = _dist_info()
-    if world > 1:
-        import torch.distributed as dist
-        r = dist.get_rank()
-        if r > 0:
-            key, training_key = prng.fold_in(key, r), prng.fold_in(training_key, r)
+    key, training_key = parallel.rank_keys(seed, parallel.dist_info()[1])   # ppo.py:544-545
     if getattr(env, "fused_rollout", False):
         env_states = env.reset_from_split(key, n_envs, net.device)       # ppo.py:548-549
     else:

@@ -213,6 +213,12 @@ float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb,
 int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rng_advance,
                           uint32_t adam_advance);
 
+/* -------- tensor-core bring-up / parity hook: C[M][N] = A[M][K] * B[K][N] with tcgen05.mma ---- *
+ * kind::tf32, fp32 accumulation in TMEM; split = 0: plain TF32 operands, 1: error-compensated   *
+ * 3xTF32 (hi/lo operand split).  N multiple of 16 in [16, 256].                                 */
+int b200ppo_tc_gemm_test(void* stream, const float* A /*dev*/, const float* B /*dev*/, float* C /*dev*/,
+                         int32_t M, int32_t N, int32_t K, int32_t split);
+
 /* -------- measurement helper: register-resident FFMA loop (fp32 CUDA-core peak) ------------ */
 int b200ppo_ffma_peak(void* stream, int32_t iters, float* sink /*dev [blocks*threads]*/,
                       int32_t blocks, int32_t threads);

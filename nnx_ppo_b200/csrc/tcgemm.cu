@@ -1,0 +1,151 @@
+// Standalone tcgen05 GEMM (C = A B, fp32 in / fp32 out, 1xTF32 or error-compensated 3xTF32):
+// the bring-up and parity harness of the tensor-core building blocks in tc.cuh.
+#include "common.cuh"
+#include "tc.cuh"
+
+using namespace b200ppo;
+
+namespace {
+
+constexpr int TCM = 128;     // rows per CTA (UMMA M)
+constexpr int TCK = 32;      // k per stage (4 MMAs of K = 8)
+constexpr int TCT = 256;     // threads
+
+// stage layout (bytes): A_hi | A_lo | B_hi | B_lo, each KC/4 planes
+__host__ __device__ constexpr uint32_t stage_bytes(int n) {
+  return 2u * (TCK / 4) * tc::plane_bytes(TCM) + 2u * (TCK / 4) * tc::plane_bytes(n);
+}
+
+__global__ void __launch_bounds__(TCT, 1)
+tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                    int M, int N, int K, int split, int tmem_cols) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar_empty[2];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TCM;
+  const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(N);
+  const uint32_t sbytes = stage_bytes(N);
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 32) {
+    tc::mbar_init(&bar_empty[0], 1);
+    tc::mbar_init(&bar_empty[1], 1);
+    tc::mbar_init(&bar_done, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = tc::make_idesc_tf32(TCM, N);
+
+  const int nst = (K + TCK - 1) / TCK;
+  uint32_t phase[2] = {0u, 0u};
+  for (int s = 0; s < nst; ++s) {
+    const int buf = s & 1;
+    uint8_t* st = smem + buf * sbytes;
+    uint8_t* a_hi = st;
+    uint8_t* a_lo = a_hi + (TCK / 4) * pa;
+    uint8_t* b_hi = a_lo + (TCK / 4) * pa;
+    uint8_t* b_lo = b_hi + (TCK / 4) * pb;
+    if (s >= 2) {                       // the MMAs that read this buffer two stages ago are done
+      tc::mbar_wait(&bar_empty[buf], phase[buf]);
+      phase[buf] ^= 1u;
+    }
+    const int k0 = s * TCK;
+    // ---- stage A: rows x 8 planes; lane -> (plane q = idx & 7, row = idx >> 3): 128 B per row ----
+    for (int idx = tid; idx < TCM * (TCK / 4); idx += TCT) {
+      const int q = idx & 7, r = idx >> 3;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + 4 * q;
+      if (row0 + r < M) {
+        const float* src = A + static_cast<size_t>(row0 + r) * K + k;
+        if (k + 3 < K && (K & 3) == 0) x = *reinterpret_cast<const float4*>(src);
+        else {
+          if (k + 0 < K) x.x = src[0];
+          if (k + 1 < K) x.y = src[1];
+          if (k + 2 < K) x.z = src[2];
+          if (k + 3 < K) x.w = src[3];
+        }
+      }
+      float4 hi, lo;
+      tc::split4(x, hi, lo);
+      *reinterpret_cast<float4*>(a_hi + q * pa + r * 16) = hi;
+      *reinterpret_cast<float4*>(a_lo + q * pa + r * 16) = lo;
+    }
+    // ---- stage B: B_op(n, k) = B[k][n]; lane -> consecutive n (coalesced), 4 k's per thread ----
+    for (int idx = tid; idx < N * (TCK / 4); idx += TCT) {
+      const int n = idx % N, q = idx / N;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int k = k0 + 4 * q;
+      if (k + 0 < K) x.x = B[static_cast<size_t>(k + 0) * N + n];
+      if (k + 1 < K) x.y = B[static_cast<size_t>(k + 1) * N + n];
+      if (k + 2 < K) x.z = B[static_cast<size_t>(k + 2) * N + n];
+      if (k + 3 < K) x.w = B[static_cast<size_t>(k + 3) * N + n];
+      float4 hi, lo;
+      tc::split4(x, hi, lo);
+      *reinterpret_cast<float4*>(b_hi + q * pb + n * 16) = hi;
+      *reinterpret_cast<float4*>(b_lo + q * pb + n * 16) = lo;
+    }
+    tc::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < TCK / 8; ++j) {
+        const uint64_t ah = tc::make_desc(tc::smem_u32(a_hi + 2 * j * pa), pa, 128);
+        const uint64_t al = tc::make_desc(tc::smem_u32(a_lo + 2 * j * pa), pa, 128);
+        const uint64_t bh = tc::make_desc(tc::smem_u32(b_hi + 2 * j * pb), pb, 128);
+        const uint64_t bl = tc::make_desc(tc::smem_u32(b_lo + 2 * j * pb), pb, 128);
+        const uint32_t acc0 = (s > 0 || j > 0) ? 1u : 0u;
+        if (split) {
+          // small terms first, then the dominant product
+          tc::mma_tf32(tmem_base, al, bh, idesc, acc0);
+          tc::mma_tf32(tmem_base, ah, bl, idesc, 1u);
+          tc::mma_tf32(tmem_base, ah, bh, idesc, 1u);
+        } else {
+          tc::mma_tf32(tmem_base, ah, bh, idesc, acc0);
+        }
+      }
+      tc::commit(&bar_empty[buf]);
+      if (s == nst - 1) tc::commit(&bar_done);
+    }
+  }
+  // ---- epilogue: TMEM -> registers -> global ----
+  tc::mbar_wait(&bar_done, 0u);
+  tc::tc_fence_after();
+  const int sub = warp & 3;                 // TMEM sub-partition this warp may read
+  const int row = row0 + sub * 32 + lane;
+  for (int c = (warp >> 2) * 16; c < N; c += 32) {
+    float v[16];
+    tc::tmem_ld16(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
+    if (row < M) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c + i < N) C[static_cast<size_t>(row) * N + c + i] = v[i];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// Test hook: C[M][N] = A[M][K] * B[K][N] on the tensor cores.  N multiple of 16, 16 <= N <= 256.
+extern "C" int b200ppo_tc_gemm_test(void* stream, const float* A, const float* B, float* C, int32_t M,
+                                    int32_t N, int32_t K, int32_t split) {
+  if (!A || !B || !C || M <= 0 || K <= 0) return B200PPO_EINVAL;
+  if (N < 16 || N > 256 || (N & 15)) return B200PPO_EINVAL;
+  int cols = 32;
+  while (cols < N) cols <<= 1;
+  const size_t smem = 2 * static_cast<size_t>(stage_bytes(N));
+  cudaError_t e = cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_gemm_test_kernel<<<cdiv(M, TCM), TCT, smem, static_cast<cudaStream_t>(stream)>>>(A, B, C, M, N, K, split, cols);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}

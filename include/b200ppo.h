@@ -202,6 +202,13 @@ int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int3
 int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,
                    const b200ppo_update_bufs* bufs, int32_t T, int32_t B, int32_t mb,
                    uint32_t rng_count_offset, int32_t update_index, int32_t stages);
+/* GEMM engine of the update: 0 = fp32 FFMA on CUDA cores, 1 = tcgen05 3xTF32 (default; error-   *
+ * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
+ * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
+int b200ppo_set_gemm_mode(int mode);
+/* Number of kernels b200ppo_update launches for the given stage mask (for launch accounting).   */
+int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
+                                int32_t mb, int32_t stages);
 /* Pointers into the workspace that a data-parallel caller reduces across ranks. */
 double* b200ppo_update_adv_sums_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws);
 float* b200ppo_update_grad_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws);

@@ -164,7 +164,7 @@ class PPOEngine:
         n = 0
         _lib.check(lib.b200ppo_permutation(s, self.iter_keys.data_ptr() + 8, B, self.E, self.inds.data_ptr(),
                                            self.perm_scratch.data_ptr()), "permutation"); n += 1
-        clip_launch = 1 if self.hp.grad_clip > 0 else 0
+        per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, _lib.STAGE_ALL))
         for u in range(self.n_updates):
             off = rng_offset0 + u * 2 * (T + 1)
             args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
@@ -177,7 +177,7 @@ class PPOEngine:
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")
                 self._allreduce(self.grad)
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ADAM), "update/adam")
-            n += 7 + clip_launch
+            n += per_update
         if self.world > 1:
             self._allreduce(self.metrics)
         if net.normalizer is not None:

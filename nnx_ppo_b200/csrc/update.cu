@@ -14,6 +14,10 @@
 // All GEMMs share one register-tiled fp32 FFMA routine (TM=128 rows resident in shared memory,
 // 8x4 accumulators per thread, B operand streamed in double-buffered 16-deep chunks).
 #include "common.cuh"
+#include "tc.cuh"
+
+#include <cstdlib>
+#include <cstring>
 
 using namespace b200ppo;
 
@@ -41,8 +45,16 @@ constexpr int DBL_LOSS_PART = DBL_GAE_PART + 2 * MAX_PART_BLOCKS;
 constexpr int DBL_GN_PART = DBL_LOSS_PART + 3 * MAX_LOSS_BLOCKS;
 constexpr int DBL_TOTAL = DBL_GN_PART + MAX_PART_BLOCKS;
 
+// pre-split (hi / lo tf32) weight operands of one layer for the tensor-core path
+struct TcLayer {
+  size_t wf_hi, wf_lo, wb_hi, wb_lo;   // float offsets into the workspace
+  int kpad, npad, nred_pad, kout_pad;  // K -> 32, N -> 16 (fwd operand); N -> 32, K -> 16 (dX operand)
+};
+
 struct Layout {
   int R, Rv, S, n_tiles, rows_per_split;
+  int tc_ok, tc_tiles, tc_S, tc_rows_per_split;
+  TcLayer tca[MAXL], tcc[MAXL];
   size_t xhat, adv, gpart, grad;
   size_t za[MAXL], zc[MAXL], da[MAXL], dc[MAXL];
   size_t dbl;        // doubles: [0..1] adv_sums, [2..3] gnorm2/unused, then partial arrays
@@ -86,7 +98,36 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
   S = cdiv(L.R, rps);
   L.S = S;
   L.rows_per_split = rps;
-  L.gpart = take(static_cast<size_t>(S) * p.n_params);
+  // tensor-core path: D rows tiled by 128, one row-range split per CTA, <= 1 CTA per SM
+  L.tc_ok = 1;
+  L.tc_tiles = 0;
+  for (int c = 0; c < 2; ++c) {
+    const b200ppo_chain& ch = c == 0 ? p.actor : p.critic;
+    TcLayer* tl = c == 0 ? L.tca : L.tcc;
+    for (int l = 0; l < ch.n_layers; ++l) {
+      const int K = ch.dims[l], N = ch.dims[l + 1];
+      if (N > 256) L.tc_ok = 0;
+      tl[l].kpad = (K + 31) & ~31;
+      tl[l].npad = (N + 15) & ~15;
+      tl[l].nred_pad = (N + 31) & ~31;
+      tl[l].kout_pad = (K + 15) & ~15;
+      // planes of (rows + 1) float4 (padded plane stride, identical to the smem stage layout)
+      tl[l].wf_hi = take(static_cast<size_t>(tl[l].kpad) * (tl[l].npad + 1));
+      tl[l].wf_lo = take(static_cast<size_t>(tl[l].kpad) * (tl[l].npad + 1));
+      tl[l].wb_hi = take(static_cast<size_t>(tl[l].nred_pad) * (tl[l].kout_pad + 1));
+      tl[l].wb_lo = take(static_cast<size_t>(tl[l].nred_pad) * (tl[l].kout_pad + 1));
+      L.tc_tiles += cdiv(K, 128);
+    }
+  }
+  int tS = sms / (L.tc_tiles > 0 ? L.tc_tiles : 1);
+  if (tS < 1) tS = 1;
+  if (tS > 64) tS = 64;
+  int trps = cdiv(cdiv(L.R, tS), 32) * 32;
+  if (trps < 32) trps = 32;
+  L.tc_S = cdiv(L.R, trps);
+  L.tc_rows_per_split = trps;
+  const int smax = L.tc_S > S ? L.tc_S : S;
+  L.gpart = take(static_cast<size_t>(smax) * p.n_params);
   L.grad = take(p.n_params);
   L.total_floats = o;
   return L;
@@ -683,6 +724,8 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
   }
 }
 
+#include "update_tc.cuh"
+
 // ------------------------------------------------------------------------------------------
 // RED / grad-norm / ADAM
 // ------------------------------------------------------------------------------------------
@@ -783,11 +826,51 @@ int set_attrs() {
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(upd_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM);
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_bwd_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
   g_attr_done = true;
   return 0;
 }
 
+// GEMM engine: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (default, fp32-level accuracy),
+// 2 = tcgen05 1xTF32 (JAX-GPU default matmul precision; NOT fp32 parity).  B200PPO_GEMM=ffma|tf32x3|tf32
+int g_gemm_mode = -1;
+int gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char* e = std::getenv("B200PPO_GEMM");
+    g_gemm_mode = 1;
+    if (e && !std::strcmp(e, "ffma")) g_gemm_mode = 0;
+    if (e && !std::strcmp(e, "tf32")) g_gemm_mode = 2;
+  }
+  return g_gemm_mode;
+}
+
 }  // namespace
+
+extern "C" int b200ppo_set_gemm_mode(int mode) {
+  const int prev = gemm_mode();
+  if (mode >= 0 && mode <= 2) g_gemm_mode = mode;
+  return prev;
+}
+
+extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
+                                           int32_t mb, int32_t stages) {
+  if (check_plan_u(plan) || !hp || T <= 0 || mb <= 0) return B200PPO_EINVAL;
+  const Layout L = make_layout(*plan, T, mb);
+  const bool use_tc = gemm_mode() != 0 && L.tc_ok;
+  int n = 0;
+  if (stages & B200PPO_STAGE_FWD) n += use_tc ? 2 : 1;
+  if (stages & B200PPO_STAGE_GAE) n += 1;
+  if (stages & B200PPO_STAGE_LOSS) n += 1;
+  if (stages & B200PPO_STAGE_BWD) n += 2;
+  if (stages & B200PPO_STAGE_RED) n += 1;
+  if (stages & B200PPO_STAGE_ADAM) n += hp->grad_clip > 0.0f ? 2 : 1;
+  return n;
+}
 
 extern "C" int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb) {
   if (check_plan_u(plan) || T <= 0 || mb <= 0) return B200PPO_EINVAL;
@@ -832,6 +915,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   rc = set_attrs();
   if (rc) return rc;
   const Layout L = make_layout(*plan, T, mb);
+  const bool use_tc = gemm_mode() != 0 && L.tc_ok;
+  const int tc_split = gemm_mode() == 1 ? 1 : 0;
   if (cdiv(mb, GAE_THREADS) > MAX_PART_BLOCKS || cdiv(L.R, 128) > MAX_LOSS_BLOCKS) return B200PPO_ELIMIT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(b->ws);
@@ -847,7 +932,15 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.plan = *plan; a.L = L; a.obs = b->obs; a.next_obs_last = b->next_obs_last; a.inds = b->inds;
     a.mean = b->norm_mean; a.std = b->norm_std; a.params = b->params; a.ws = ws;
     a.T = T; a.B = B; a.mb = mb;
-    upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
+    if (use_tc) {
+      PrepArgs pa;
+      pa.plan = *plan; pa.L = L; pa.params = b->params; pa.ws = ws;
+      upd_prep_w_kernel<<<dim3(16, 2 * MAXL, 2), 256, 0, s>>>(pa);
+      B200PPO_LAUNCH_CHECK();
+      upd_fwd_tc_kernel<<<cdiv(L.Rv, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
+    } else {
+      upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
+    }
     B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_GAE) {
@@ -871,13 +964,20 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   if (stages & B200PPO_STAGE_BWD) {
     BwdArgs a;
     a.plan = *plan; a.L = L; a.params = b->params; a.ws = ws;
-    upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
-    upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
+    if (use_tc) {
+      upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
+      B200PPO_LAUNCH_CHECK();
+      upd_bwd_dw_tc_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, TC_SMEM, s>>>(a, tc_split);
+      B200PPO_LAUNCH_CHECK();
+    } else {
+      upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
+      B200PPO_LAUNCH_CHECK();
+      upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
+      B200PPO_LAUNCH_CHECK();
+    }
   }
   if (stages & B200PPO_STAGE_RED) {
-    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, L.S, plan->n_params, ws + L.grad);
+    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, use_tc ? L.tc_S : L.S, plan->n_params, ws + L.grad);
     B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_ADAM) {

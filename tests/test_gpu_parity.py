@@ -287,7 +287,17 @@ def _dbg(eng, which, n):
     dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=96, T=30, M=2, act="tanh", clip=0.5, wd=None),
     dict(O=24, A=5, ah=[48, 40], ch=[72], B=70, T=7, M=2, act="swish", clip=None, wd=1e-3),
     dict(O=300, A=3, ah=[32], ch=[20, 20], B=40, T=5, M=1, act="relu", clip=None, wd=None)])
-def test_single_update_matches_oracle(dev, cfg):
+@pytest.mark.parametrize("gemm", [0, 1, 2])
+def test_single_update_matches_oracle(dev, cfg, gemm):
+    """gemm = 0: fp32 FFMA kernels, 1: tcgen05 3xTF32 (default), 2: tcgen05 plain TF32 (loose)."""
+    _lib.load().b200ppo_set_gemm_mode(gemm)
+    try:
+        _single_update(dev, cfg, 300.0 if gemm == 2 else 1.0)
+    finally:
+        _lib.load().b200ppo_set_gemm_mode(1)
+
+
+def _single_update(dev, cfg, loose):
     O, A, B, T, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["M"]
     nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
     env = SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
@@ -328,22 +338,28 @@ def test_single_update_matches_oracle(dev, cfg):
                                   _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED))
     torch.cuda.synchronize()
     R = T * mb
-    tol = dict(rtol=1e-4, atol=1e-5)
+    tol = dict(rtol=1e-4 * loose, atol=1e-5 * loose)
     assert np.allclose(_dbg(eng, 1, R + mb)[:R].reshape(T, mb), m["values"], **tol)
     assert np.allclose(_dbg(eng, 1, R + mb)[R:], m["v_last"], **tol)
-    assert np.allclose(_dbg(eng, 0, R).reshape(T, mb), m["adv"], rtol=1e-4, atol=1e-4)       # advantages
+    assert np.allclose(_dbg(eng, 0, R).reshape(T, mb), m["adv"], rtol=1e-4 * loose, atol=1e-4 * loose)   # advantages
     sums = eng.adv_sums.cpu().numpy()
-    assert abs(sums[0] / R - m["adv_mean"]) < 1e-5 and abs(np.sqrt(sums[1] / R - (sums[0] / R) ** 2) - m["adv_std"]) < 1e-4
+    assert abs(sums[0] / R - m["adv_mean"]) < 1e-5 * loose and abs(np.sqrt(sums[1] / R - (sums[0] / R) ** 2) - m["adv_std"]) < 1e-4 * loose
     met = eng.metrics[0].cpu().numpy()
-    assert abs(met[0] - m["losses/actor"]) < 1e-5 and abs(met[1] - m["losses/critic"]) < 1e-4 * max(1, abs(m["losses/critic"]))
-    assert abs(met[2] - m["losses/regularization"]) < 1e-5
+    assert abs(met[0] - m["losses/actor"]) < 1e-5 * loose and abs(met[1] - m["losses/critic"]) < 1e-4 * loose * max(1, abs(m["losses/critic"]))
+    assert abs(met[2] - m["losses/regularization"]) < 1e-5 * loose
+    if loose > 1.0:
+        # plain TF32 is not fp32 parity (clip decisions can flip): only require a sane gradient
+        got_g = net.params_logical(eng.grad)
+        assert np.isfinite(got_g).all()
+        assert np.linalg.norm(got_g - grads) < 0.2 * np.linalg.norm(grads)
+        return
     dy = _dbg(eng, 3, R * 2 * A).reshape(R, 2 * A)
-    assert np.abs(dy - m["d_y"]).max() < 1e-4 * max(np.abs(m["d_y"]).max(), 1e-6) + 1e-9
+    assert np.abs(dy - m["d_y"]).max() < 1e-4 * loose * max(np.abs(m["d_y"]).max(), 1e-6) + 1e-9
     dv = _dbg(eng, 4, R)
-    assert np.abs(dv - m["d_v"]).max() < 1e-4 * np.abs(m["d_v"]).max() + 1e-10
+    assert np.abs(dv - m["d_v"]).max() < 1e-4 * loose * np.abs(m["d_v"]).max() + 1e-10
     got_g = net.params_logical(eng.grad)
     gs = np.abs(grads).max()
-    assert np.abs(got_g - grads).max() < 2e-4 * gs, (np.abs(got_g - grads).max(), gs)
+    assert np.abs(got_g - grads).max() < 2e-4 * loose * gs, (np.abs(got_g - grads).max(), gs)
     # K4: optax update from the SAME gradient on both sides
     p_before = net.params_logical()
     ost = oppo.AdamState(np.zeros_like(p_before), np.zeros_like(p_before), 0)
@@ -365,6 +381,19 @@ def test_single_update_matches_oracle(dev, cfg):
     dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, E=2, M=4, iters=3),
     dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=128, T=30, E=4, M=4, iters=2)])
 def test_ppo_step_matches_oracle_over_iterations(dev, cfg):
+    _iterations(dev, cfg)
+
+
+def test_ppo_step_matches_oracle_ffma_engine(dev):
+    """Same check with the fp32 CUDA-core GEMM kernels (B200PPO_GEMM=ffma)."""
+    _lib.load().b200ppo_set_gemm_mode(0)
+    try:
+        _iterations(dev, dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, E=2, M=4, iters=2))
+    finally:
+        _lib.load().b200ppo_set_gemm_mode(1)
+
+
+def _iterations(dev, cfg):
     O, A, B, T, E, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["E"], cfg["M"]
     nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
     env = SyntheticEnv(O, A, max_len=48, term_thresh16=700)

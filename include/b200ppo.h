@@ -226,6 +226,10 @@ int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rn
 int b200ppo_tc_gemm_test(void* stream, const float* A /*dev*/, const float* B /*dev*/, float* C /*dev*/,
                          int32_t M, int32_t N, int32_t K, int32_t split);
 
+/* Same with both operands MN-major: C[M][N] = At[K][M]^T * B[K][N] (K % 32 == 0, M % 4 == 0).   */
+int b200ppo_tc_gemm_tn_test(void* stream, const float* At /*dev*/, const float* B /*dev*/, float* C /*dev*/,
+                            int32_t M, int32_t N, int32_t K, int32_t split);
+
 /* -------- measurement helper: register-resident FFMA loop (fp32 CUDA-core peak) ------------ */
 int b200ppo_ffma_peak(void* stream, int32_t iters, float* sink /*dev [blocks*threads]*/,
                       int32_t blocks, int32_t threads);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "b200ppo_update_debug_ptr": (_vp, [_PP, _i32, _i32, _vp, _i32]),
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
+    "b200ppo_tc_gemm_tn_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
     "b200ppo_ffma_peak": (C.c_int, [_vp, _i32, _vp, _i32, _i32]),
 }
 

@@ -78,6 +78,15 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// same, both operands MN-major (the M / N index is the contiguous one in shared memory)
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major, no swizzle: a 128-byte core matrix holds 8 k-rows x 4 consecutive mn; mn chunks are
+// MN_SBO bytes apart (128 + 16 pad: conflict-free staging), groups of 8 k are LBO bytes apart.
+constexpr uint32_t MN_SBO = 144u;
+__host__ __device__ constexpr uint32_t mn_lbo(int rows) { return static_cast<uint32_t>(rows / 4) * MN_SBO; }
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

@@ -563,6 +563,132 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   }
 }
 
+// Same computation with one thread per (row, action dim) when A divides 32: the per-element
+// threefry / erfinv / transcendental chains of the A dims run in parallel and the two row sums
+// (log-lik, entropy) are butterfly reductions over the A adjacent lanes.  ncu: the thread-per-row
+// version ran 4 warps per SM on long dependent chains (27 us per launch).
+__global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
+  __shared__ double red[3][8];
+  __shared__ float stats_s[2];
+  const int A = a.plan.act_dim;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gid / A, d = gid - r * A;
+  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
+  const double ng = a.n_global;
+  const float inv_n = static_cast<float>(1.0 / ng);
+  if (threadIdx.x == 0) {                       // fp64 moment math once per block (fp64 is slow)
+    float am = 0.0f, ad = 1.0f;
+    if (a.normalize_adv) {
+      const double m = dbl[0] / ng;
+      double var = dbl[1] / ng - m * m;
+      var = var > 0.0 ? var : 0.0;
+      am = static_cast<float>(m);
+      ad = static_cast<float>(sqrt(var)) + 1e-8f;
+    }
+    stats_s[0] = am;
+    stats_s[1] = ad;
+  }
+  __syncthreads();
+  const float a_mean = stats_s[0], a_den = stats_s[1];
+  const bool valid = r < a.L.R;
+  float llt = 0.0f, entt = 0.0f, mu = 0.f, rho = 0.f, z = 0.f, sigma = 1.f, eps2 = 0.f, th = 0.f;
+  size_t grow = 0;
+  int t = 0, j = 0;
+  if (valid) {
+    t = r / a.mb; j = r - t * a.mb;
+    grow = static_cast<size_t>(t) * a.B + a.inds[j];
+    const float* y = a.ws + a.y_off + static_cast<size_t>(r) * 2 * A;
+    mu = y[d]; rho = y[A + d]; z = a.raw_action[grow * A + d];
+    const Key stream_key{a.rng_state[0], a.rng_state[1]};
+    const Key k_ent = fold_in(stream_key, a.rng_state[2] + a.count_offset + 2u * static_cast<uint32_t>(t) + 1u);
+    sigma = (softplus_f(rho) + a.plan.min_std) * a.plan.std_scale;
+    const float q = (z - mu) / sigma;
+    const float ls = logf(sigma);
+    llt = -0.5f * q * q - (B200PPO_HALF_LOG_2PI + ls) - log_det_jac(z);
+    eps2 = bits_to_normal(random_bits_at(k_ent, static_cast<uint32_t>(j) * A + d));
+    const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
+    entt = 0.5f + B200PPO_HALF_LOG_2PI + ls + log_det_jac(zp);
+    th = tanhf(zp);
+  }
+  float ll = llt, ent = entt;
+  for (int o = 1; o < A; o <<= 1) {
+    ll += __shfl_xor_sync(0xffffffffu, ll, o);
+    ent += __shfl_xor_sync(0xffffffffu, ent, o);
+  }
+  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
+  if (valid) {
+    const float adv = a.ws[a.L.adv + r];
+    const float v = a.ws[a.v_off + r];
+    const float target = __fadd_rn(v, adv);
+    const float diff = __fsub_rn(v, target);
+    const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
+    const float ratio = expf(ll - a.loglik_old[grow]);
+    const float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
+    const float c1 = __fmul_rn(ratio, an);
+    const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
+    const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
+    const float w2 = 1.0f - w1;
+    const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
+    const float g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    const float we = a.plan.entropy_weight * inv_n;
+    const float dm = z - mu;
+    const float is = 1.0f / sigma;
+    const float d_mu = g_ll * dm * is * is + we * 2.0f * th;
+    const float d_sig = g_ll * (dm * dm * is * is * is - is) - we * (is - 2.0f * th * eps2);
+    float* dy = a.ws + a.dy_off + static_cast<size_t>(r) * 2 * A;
+    dy[d] = d_mu;
+    dy[A + d] = d_sig * sigmoid_f(rho) * a.plan.std_scale;
+    if (d == 0) {
+      a.ws[a.dv_off + r] = a.critic_w * diff * inv_n;
+      l_actor = -static_cast<double>(fminf(c1, c2));
+      l_critic = 0.5 * static_cast<double>(diff) * diff;
+      l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
+    }
+  }
+  l_actor = warp_sum_d(l_actor);
+  l_critic = warp_sum_d(l_critic);
+  l_reg = warp_sum_d(l_reg);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = l_actor;
+    red[1][threadIdx.x >> 5] = l_critic;
+    red[2][threadIdx.x >> 5] = l_reg;
+  }
+  __syncthreads();
+  __shared__ bool is_last_s;
+  double* part = const_cast<double*>(dbl) + DBL_LOSS_PART;
+  if (threadIdx.x == 0) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
+    for (int q = 0; q < 3; ++q) {
+      double sacc = 0.0;
+      for (int w = 0; w < 8; ++w) sacc += red[q][w];
+      part[3 * blockIdx.x + q] = sacc;
+    }
+    __threadfence();
+    const unsigned int tk = atomicAdd(&ticket[1], 1u);
+    is_last_s = tk == gridDim.x - 1;
+    if (is_last_s) ticket[1] = 0u;
+  }
+  __syncthreads();
+  if (is_last_s) {
+    // the last block sums the per-block partials with all its threads (strided loads in flight
+    // together, then a fixed-order tree): deterministic, and not a serial latency chain
+    __threadfence();
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+      for (int q = 0; q < 3; ++q) acc[q] += __ldcg(&part[3 * b + q]);
+    for (int q = 0; q < 3; ++q) acc[q] = warp_sum_d(acc[q]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+      for (int q = 0; q < 3; ++q) red[q][threadIdx.x >> 5] = acc[q];
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+      a.metrics_out[threadIdx.x] = static_cast<float>(t / ng);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // BWD dX chain:  dpre_{l-1} = (dpre_l W_l^T) ⊙ act'(z_{l-1})
 // ------------------------------------------------------------------------------------------
@@ -768,6 +894,7 @@ __global__ void __launch_bounds__(256) upd_gnorm_kernel(const float* __restrict_
 }
 
 struct AdamArgs {
+  const float* gpart; int S; float* grad_out;   // S > 0: fused fixed-order reduction of the dW partials
   const float* grad; float* params; float* mu; float* nu;
   const uint32_t* rng_state; const double* gnorm2; float* metrics_out;
   int64_t P;
@@ -785,7 +912,14 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
     if (i == 0) a.metrics_out[3] = gn;
   }
   if (i >= a.P) return;
-  float g = a.grad[i];
+  float g;
+  if (a.S > 0) {
+    g = 0.0f;
+    for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
+    a.grad_out[i] = g;
+  } else {
+    g = a.grad[i];
+  }
   if (a.clip > 0.0f && !(gn < a.clip)) g = __fmul_rn(__fdiv_rn(g, gn), a.clip);
   const float t = static_cast<float>(a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u);
   const float m = __fadd_rn(__fmul_rn(1.0f - a.b1, g), __fmul_rn(a.b1, a.mu[i]));
@@ -867,7 +1001,8 @@ extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200p
   if (stages & B200PPO_STAGE_GAE) n += 1;
   if (stages & B200PPO_STAGE_LOSS) n += 1;
   if (stages & B200PPO_STAGE_BWD) n += 2;
-  if (stages & B200PPO_STAGE_RED) n += 1;
+  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f);
+  if ((stages & B200PPO_STAGE_RED) && !fuse_red) n += 1;
   if (stages & B200PPO_STAGE_ADAM) n += hp->grad_clip > 0.0f ? 2 : 1;
   return n;
 }
@@ -958,7 +1093,10 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.T = T; a.B = B; a.mb = mb; a.count_offset = rng_count_offset;
     a.clip = hp->clip_range; a.critic_w = hp->critic_loss_weight; a.normalize_adv = hp->normalize_advantages;
     a.n_global = static_cast<double>(L.R) * hp->world_size;
-    upd_loss_kernel<<<cdiv(L.R, 128), 128, 0, s>>>(a);
+    const int A = plan->act_dim;
+    const bool par = A <= 32 && (A & (A - 1)) == 0 && cdiv(static_cast<int64_t>(L.R) * A, 256) <= MAX_LOSS_BLOCKS;
+    if (par) upd_loss_par_kernel<<<cdiv(static_cast<int64_t>(L.R) * A, 256), 256, 0, s>>>(a);
+    else upd_loss_kernel<<<cdiv(L.R, 128), 128, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_BWD) {
@@ -976,7 +1114,9 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
       B200PPO_LAUNCH_CHECK();
     }
   }
-  if (stages & B200PPO_STAGE_RED) {
+  // reduce + adam fuse into one launch when both stages are requested and no global norm is needed
+  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f);
+  if ((stages & B200PPO_STAGE_RED) && !fuse_red) {
     upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, use_tc ? L.tc_S : L.S, plan->n_params, ws + L.grad);
     B200PPO_LAUNCH_CHECK();
   }
@@ -988,6 +1128,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
       B200PPO_LAUNCH_CHECK();
     }
     AdamArgs a;
+    a.gpart = ws + L.gpart; a.S = fuse_red ? (use_tc ? L.tc_S : L.S) : 0; a.grad_out = ws + L.grad;
     a.grad = ws + L.grad; a.params = b->params; a.mu = b->adam_mu; a.nu = b->adam_nu;
     a.rng_state = b->rng_state; a.gnorm2 = dbl + 2; a.metrics_out = b->metrics_out;
     a.P = plan->n_params; a.update_index = update_index;

@@ -139,8 +139,12 @@ __device__ __forceinline__ float4 act4(float4 x, int act) {
 template <class Epi>
 __device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restrict__ A, int lda, int row0,
                                                 int nrows, int K, int act, const float* __restrict__ Bhi,
-                                                const float* __restrict__ Blo, int npad, int split, Epi epi) {
+                                                const float* __restrict__ Blo, int npad, int split,
+                                                const float* __restrict__ colvec, int ncol, float* colvec_s,
+                                                Epi epi) {
   const int tid = threadIdx.x;
+  // per-column epilogue vector (bias) staged in shared memory: visible after the first stage barrier
+  if (colvec != nullptr && tid < npad) colvec_s[tid] = tid < ncol ? __ldg(colvec + tid) : 0.0f;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = (K + TCK - 1) / TCK;
   const uint32_t bbytes = (TCK / 4) * pb;
@@ -159,8 +163,9 @@ __device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restri
     kq[i] = 4 * q;
   }
   const bool vec = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-  float4 areg[TC_APT];
-  auto load_a = [&](int s) {
+  // A is prefetched TWO stages ahead in registers (global-load latency >> one stage of MMAs)
+  float4 areg[2][TC_APT];
+  auto load_a = [&](int s, float4 (&dst)[TC_APT]) {
     const int k0 = s * TCK;
 #pragma unroll
     for (int i = 0; i < TC_APT; ++i) {
@@ -177,7 +182,7 @@ __device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restri
           if (k + 3 < K) x.w = src[3];
         }
       }
-      areg[i] = x;
+      dst[i] = x;
     }
   };
   auto issue_b = [&](int s, int buf) {        // one thread
@@ -189,16 +194,20 @@ __device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restri
   };
   tc_wait_free(cx, 0);
   if (tid == 0) issue_b(0, 0);
-  load_a(0);
+  load_a(0, areg[0]);
+  if (nst > 1) load_a(1, areg[1]);
   for (int s = 0; s < nst; ++s) {
     const int buf = s & 1;
     const TcStage st = tc_stage(cx, buf);
 #pragma unroll
     for (int i = 0; i < TC_APT; ++i) {
       float4 hi, lo;
-      tc::split4(act4(areg[i], act), hi, lo);
+      tc::split4(act4(buf ? areg[1][i] : areg[0][i], act), hi, lo);
       *reinterpret_cast<float4*>(st.a_hi + soff[i]) = hi;
       if (split) *reinterpret_cast<float4*>(st.a_lo + soff[i]) = lo;
+    }
+    if (s + 2 < nst) {                          // refill the register set just consumed
+      if (buf) load_a(s + 2, areg[1]); else load_a(s + 2, areg[0]);
     }
     tc::fence_proxy_async();
     __syncthreads();
@@ -211,7 +220,6 @@ __device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restri
     if (s + 1 < nst) {
       tc_wait_free(cx, buf ^ 1);
       if (tid == 0) issue_b(s + 1, buf ^ 1);
-      load_a(s + 1);
     }
   }
   tc_epilogue(cx, npad, epi);
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,
                                                  const float* __restrict__ P, float* ws, const size_t* zoff,
-                                                 size_t xhat_off, int row0, int nrows, int split) {
+                                                 size_t xhat_off, int row0, int nrows, int split, float* bias_s) {
   for (int l = 0; l < ch.n_layers; ++l) {
     const int K = ch.dims[l], N = ch.dims[l + 1];
     const float* A = l == 0 ? ws + xhat_off : ws + zoff[l - 1];
@@ -274,7 +282,7 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
     const float* bias = P + ch.b_off[l];
     float* Z = ws + zoff[l];
     tc_gemm_rowtile(cx, A, K, row0, nrows, K, act_in, ws + tl[l].wf_hi, ws + tl[l].wf_lo, tl[l].npad, split,
-                    [&](int r, int c, const float (&v)[16]) {
+                    bias, N, bias_s, [&](int r, int c, const float (&v)[16]) {
                       const int row = row0 + r;
                       if (row < nrows) {
                         float* dst = Z + static_cast<size_t>(row) * N + c;
@@ -282,14 +290,14 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
 #pragma unroll
                           for (int i = 0; i < 16; i += 4)
                             if (c + i < N) {
-                              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c + i));
+                              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
                               *reinterpret_cast<float4*>(dst + i) =
                                   make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
                             }
                         } else {
 #pragma unroll
                           for (int i = 0; i < 16; ++i)
-                            if (c + i < N) dst[i] = v[i] + __ldg(bias + c + i);
+                            if (c + i < N) dst[i] = v[i] + bias_s[c + i];
                         }
                       }
                     });
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   __shared__ const float* rowsrc[TCM];
+  __shared__ __align__(16) float bias_s[TC_MAXN];
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
   const int O = a.plan.obs_dim;
@@ -341,8 +350,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
     }
   }
   __syncthreads();
-  tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split);
-  if (row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split);
+  tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, bias_s);
+  if (row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, bias_s);
   tc_ctx_fini(cx);
 }
 
@@ -359,7 +368,7 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
     float* dprev = ws + doff[l - 1];
     const int act = ch.act;
     tc_gemm_rowtile(cx, dY, Nl, row0, nrows, Nl, B200PPO_ACT_NONE, ws + tl[l].wb_hi, ws + tl[l].wb_lo,
-                    tl[l].kout_pad, split, [&](int r, int c, const float (&v)[16]) {
+                    tl[l].kout_pad, split, nullptr, 0, nullptr, [&](int r, int c, const float (&v)[16]) {
                       const int row = row0 + r;
                       if (row < nrows) {
                         const size_t o = static_cast<size_t>(row) * Kl + c;

@@ -206,6 +206,10 @@ int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
+/* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *
+ * kernel -> out_host; returns -(1000 + count).                                                   */
+int b200ppo_debug_timestamps(long long* out_host, int32_t max_n);
+int b200ppo_debug_select(int skip_dw);   /* 1: the dW kernel does not overwrite the stamps (keeps dX's) */
 /* Number of kernels b200ppo_update launches for the given stage mask (for launch accounting).   */
 int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
                                 int32_t mb, int32_t stages);
@@ -226,9 +230,10 @@ int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rn
 int b200ppo_tc_gemm_test(void* stream, const float* A /*dev*/, const float* B /*dev*/, float* C /*dev*/,
                          int32_t M, int32_t N, int32_t K, int32_t split);
 
-/* Same with both operands MN-major: C[M][N] = At[K][M]^T * B[K][N] (K % 32 == 0, M % 4 == 0).   */
-int b200ppo_tc_gemm_tn_test(void* stream, const float* At /*dev*/, const float* B /*dev*/, float* C /*dev*/,
-                            int32_t M, int32_t N, int32_t K, int32_t split);
+/* Microbenchmark (profiling aid): cycles for `iters` dependent tcgen05.mma (M=128, N, K=8), for  *
+ * `iters` serialized bulk copies of `bytes`, and for the MMAs over `nacc` accumulators.           */
+int b200ppo_tc_microbench(void* stream, const float* src /*dev*/, long long* out /*dev [4]*/, int32_t N,
+                          int32_t iters, int32_t bytes, int32_t nacc, int32_t blocks);
 
 /* -------- measurement helper: register-resident FFMA loop (fp32 CUDA-core peak) ------------ */
 int b200ppo_ffma_peak(void* stream, int32_t iters, float* sink /*dev [blocks*threads]*/,

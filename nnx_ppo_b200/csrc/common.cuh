@@ -118,21 +118,25 @@ __device__ __forceinline__ float sigmoid_f(float x) {
 __device__ __forceinline__ float softplus_f(float x) {
   return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
 }
+// relu / identity stay inline; the transcendental activations are out-of-line so that heavily
+// unrolled GEMM prologues / epilogues do not carry 16 copies of tanhf / expf (instruction cache)
+static __device__ __noinline__ float act_fwd_slow(float z, int act) {
+  return act == B200PPO_ACT_TANH ? tanhf(z) : z * sigmoid_f(z);
+}
+static __device__ __noinline__ float act_grad_slow(float z, int act) {
+  if (act == B200PPO_ACT_TANH) { const float h = tanhf(z); return 1.0f - h * h; }
+  const float s = sigmoid_f(z);
+  return s * (1.0f + z * (1.0f - s));
+}
 __device__ __forceinline__ float act_fwd(float z, int act) {
-  switch (act) {
-    case B200PPO_ACT_RELU: return fmaxf(z, 0.0f);
-    case B200PPO_ACT_TANH: return tanhf(z);
-    case B200PPO_ACT_SWISH: return z * sigmoid_f(z);
-    default: return z;
-  }
+  if (act == B200PPO_ACT_RELU) return fmaxf(z, 0.0f);
+  if (act == B200PPO_ACT_NONE) return z;
+  return act_fwd_slow(z, act);
 }
 __device__ __forceinline__ float act_grad(float z, int act) {
-  switch (act) {
-    case B200PPO_ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
-    case B200PPO_ACT_TANH: { float h = tanhf(z); return 1.0f - h * h; }
-    case B200PPO_ACT_SWISH: { float s = sigmoid_f(z); return s * (1.0f + z * (1.0f - s)); }
-    default: return 1.0f;
-  }
+  if (act == B200PPO_ACT_RELU) return z > 0.0f ? 1.0f : 0.0f;
+  if (act == B200PPO_ACT_NONE) return 1.0f;
+  return act_grad_slow(z, act);
 }
 
 #define B200PPO_LOG2 0.69314718f

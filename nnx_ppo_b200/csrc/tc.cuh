@@ -38,6 +38,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive without release semantics (does not wait for the thread's outstanding loads)
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
@@ -77,15 +84,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
-
-// same, both operands MN-major (the M / N index is the contiguous one in shared memory)
-__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
-  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
-}
-// MN-major, no swizzle: a 128-byte core matrix holds 8 k-rows x 4 consecutive mn; mn chunks are
-// MN_SBO bytes apart (128 + 16 pad: conflict-free staging), groups of 8 k are LBO bytes apart.
-constexpr uint32_t MN_SBO = 144u;
-__host__ __device__ constexpr uint32_t mn_lbo(int rows) { return static_cast<uint32_t>(rows / 4) * MN_SBO; }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

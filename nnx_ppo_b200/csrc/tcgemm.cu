@@ -132,123 +132,79 @@ tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// C[M x N] = At^T B with At [K][M] and B [K][N] (both MN-major operands: straight float4 copies,
-// no transposition while staging).  One CTA per 128 rows of C; K multiple of 32, M multiple of 4.
-__global__ void __launch_bounds__(TCT, 1)
-tc_gemm_tn_test_kernel(const float* __restrict__ At, const float* __restrict__ B, float* __restrict__ C,
-                       int M, int N, int K, int split_in, int tmem_cols) {
-  int split = split_in;
+// Microbenchmark: (a) `iters` dependent tcgen05.mma (M=128, N, K=8) on resident smem operands,
+// (b) `iters` bulk copies of `bytes` into smem, each waited for.  out[0] = cycles of (a), out[1] = (b),
+// out[2] = (a) with `nacc` independent accumulators round-robin.
+__global__ void __launch_bounds__(128, 1)
+tc_microbench_kernel(const float* __restrict__ src, long long* __restrict__ out, int N, int iters, int bytes,
+                     int nacc) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar_empty[2];
-  __shared__ uint64_t bar_done;
+  __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TCM;
-  const int variant = split >> 4;          // bring-up: bit0 swap LBO/SBO in the descriptor, bit1 unpadded chunks
-  split &= 15;
-  const uint32_t csb = (variant & 2) ? 128u : tc::MN_SBO;
-  const uint32_t lbo_a = (TCM / 4) * csb, lbo_b = (N / 4) * csb;
-  const uint32_t a_bytes = (TCK / 8) * lbo_a, b_bytes = (TCK / 8) * lbo_b;
-  const uint32_t sbytes = 2 * a_bytes + 2 * b_bytes;
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, tmem_cols);
-  if (tid == 32) {
-    tc::mbar_init(&bar_empty[0], 1);
-    tc::mbar_init(&bar_empty[1], 1);
-    tc::mbar_init(&bar_done, 1);
-    tc::mbar_init_fence();
-  }
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) { tc::mbar_init(&bar, 1); tc::mbar_init(&bar2, 1); tc::mbar_init_fence(); }
+  for (int i = tid; i < 65536 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t idesc = tc::make_idesc_tf32_mn(TCM, N);
-  const int nst = K / TCK;
-  uint32_t phase[2] = {0u, 0u};
-  for (int s = 0; s < nst; ++s) {
-    const int buf = s & 1;
-    uint8_t* a_hi = smem + buf * sbytes;
-    uint8_t* a_lo = a_hi + a_bytes;
-    uint8_t* b_hi = a_lo + a_bytes;
-    uint8_t* b_lo = b_hi + b_bytes;
-    if (s >= 2) { tc::mbar_wait(&bar_empty[buf], phase[buf]); phase[buf] ^= 1u; }
-    const int k0 = s * TCK;
-    for (int idx = tid; idx < TCK * (TCM / 4); idx += TCT) {
-      const int c = idx & 31, kr = idx >> 5;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m0 + 4 * c + 3 < M) x = *reinterpret_cast<const float4*>(At + static_cast<size_t>(k0 + kr) * M + m0 + 4 * c);
-      float4 hi, lo;
-      tc::split4(x, hi, lo);
-      const uint32_t o = (kr >> 3) * lbo_a + c * csb + (kr & 7) * 16;
-      *reinterpret_cast<float4*>(a_hi + o) = hi;
-      *reinterpret_cast<float4*>(a_lo + o) = lo;
+  if (tid == 0) {
+    const uint32_t pa = tc::plane_bytes(128), pb = tc::plane_bytes(N);
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    const uint64_t ad = tc::make_desc(tc::smem_u32(smem), pa, 128);
+    const uint64_t bd = tc::make_desc(tc::smem_u32(smem + 8192), pb, 128);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) tc::mma_tf32(tmem_base, ad, bd, idesc, 1u);
+    tc::commit(&bar);
+    tc::mbar_wait(&bar, 0u);
+    long long t1 = clock64();
+    out[0] = t1 - t0;
+    t0 = clock64();
+    for (int i = 0; i < iters; ++i) tc::mma_tf32(tmem_base + static_cast<uint32_t>((i % nacc) * N), ad, bd, idesc, 1u);
+    tc::commit(&bar);
+    tc::mbar_wait(&bar, 1u);
+    t1 = clock64();
+    out[2] = t1 - t0;
+    t0 = clock64();
+    uint32_t par = 0;
+    for (int i = 0; i < iters; ++i) {
+      tc::mbar_arrive_expect_tx(&bar2, bytes);
+      tc::bulk_g2s(smem + 65536, src, bytes, &bar2);
+      tc::mbar_wait(&bar2, par);
+      par ^= 1u;
     }
-    const int nc = N / 4;
-    for (int idx = tid; idx < TCK * nc; idx += TCT) {
-      const int c = idx % nc, kr = idx / nc;
-      const float4 x = *reinterpret_cast<const float4*>(B + static_cast<size_t>(k0 + kr) * N + 4 * c);
-      float4 hi, lo;
-      tc::split4(x, hi, lo);
-      const uint32_t o = (kr >> 3) * lbo_b + c * csb + (kr & 7) * 16;
-      *reinterpret_cast<float4*>(b_hi + o) = hi;
-      *reinterpret_cast<float4*>(b_lo + o) = lo;
+    t1 = clock64();
+    out[1] = t1 - t0;
+    // 4 copies in flight
+    t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+      tc::mbar_arrive_expect_tx(&bar2, 4 * (bytes / 4));
+      for (int j = 0; j < 4; ++j) tc::bulk_g2s(smem + 65536 + j * (bytes / 4), src + j * (bytes / 16), bytes / 4, &bar2);
+      tc::mbar_wait(&bar2, par);
+      par ^= 1u;
     }
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc::tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < TCK / 8; ++j) {
-        const uint32_t la = (variant & 1) ? csb : lbo_a, sa = (variant & 1) ? lbo_a : csb;
-        const uint32_t lb = (variant & 1) ? csb : lbo_b, sb = (variant & 1) ? lbo_b : csb;
-        const uint64_t ah = tc::make_desc(tc::smem_u32(a_hi + j * lbo_a), la, sa);
-        const uint64_t al = tc::make_desc(tc::smem_u32(a_lo + j * lbo_a), la, sa);
-        const uint64_t bh = tc::make_desc(tc::smem_u32(b_hi + j * lbo_b), lb, sb);
-        const uint64_t bl = tc::make_desc(tc::smem_u32(b_lo + j * lbo_b), lb, sb);
-        const uint32_t acc0 = (s > 0 || j > 0) ? 1u : 0u;
-        if (split) {
-          tc::mma_tf32(tmem_base, al, bh, idesc, acc0);
-          tc::mma_tf32(tmem_base, ah, bl, idesc, 1u);
-          tc::mma_tf32(tmem_base, ah, bh, idesc, 1u);
-        } else {
-          tc::mma_tf32(tmem_base, ah, bh, idesc, acc0);
-        }
-      }
-      tc::commit(&bar_empty[buf]);
-      if (s == nst - 1) tc::commit(&bar_done);
-    }
-  }
-  tc::mbar_wait(&bar_done, 0u);
-  tc::tc_fence_after();
-  const int sub = warp & 3;
-  const int row = m0 + sub * 32 + lane;
-  for (int c = (warp >> 2) * 16; c < N; c += 32) {
-    float v[16];
-    tc::tmem_ld16(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
-    if (row < M) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (c + i < N) C[static_cast<size_t>(row) * N + c + i] = v[i];
-    }
+    t1 = clock64();
+    out[3] = t1 - t0;
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
 
-// Test hook (MN-major operands): C[M][N] = At[K][M]^T * B[K][N]; K % 32 == 0, M % 4 == 0.
-extern "C" int b200ppo_tc_gemm_tn_test(void* stream, const float* At, const float* B, float* C, int32_t M,
-                                       int32_t N, int32_t K, int32_t split) {
-  if (!At || !B || !C || M <= 0 || K <= 0 || (K % TCK) || (M & 3)) return B200PPO_EINVAL;
-  if (N < 16 || N > 256 || (N & 15)) return B200PPO_EINVAL;
-  int cols = 32;
-  while (cols < N) cols <<= 1;
-  const size_t smem = 2 * (2 * static_cast<size_t>((TCK / 8) * tc::mn_lbo(TCM)) + 2 * static_cast<size_t>((TCK / 8) * tc::mn_lbo(N)));
-  cudaError_t e = cudaFuncSetAttribute(tc_gemm_tn_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+extern "C" int b200ppo_tc_microbench(void* stream, const float* src, long long* out, int32_t N, int32_t iters,
+                                     int32_t bytes, int32_t nacc, int32_t blocks) {
+  if (!src || !out || N < 16 || N > 256 || (N & 15) || bytes <= 0 || (bytes & 63) || bytes > 131072 || nacc < 1 ||
+      nacc * N > 512 || blocks < 1)
+    return B200PPO_EINVAL;
+  const size_t smem = 65536 + 131072;
+  cudaError_t e = cudaFuncSetAttribute(tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  tc_gemm_tn_test_kernel<<<cdiv(M, TCM), TCT, smem, static_cast<cudaStream_t>(stream)>>>(At, B, C, M, N, K, split, cols);
+  tc_microbench_kernel<<<blocks, 128, smem, static_cast<cudaStream_t>(stream)>>>(src, out, N, iters, bytes, nacc);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

@@ -985,6 +985,30 @@ int gemm_mode() {
 
 }  // namespace
 
+// profiling aid: phase timestamps (clock64) of CTA 0 of the most recent tensor-core update kernel
+extern "C" int b200ppo_debug_timestamps(long long* out_host, int32_t max_n) {
+  if (!out_host || max_n <= 0) return B200PPO_EINVAL;
+  int n = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&n, g_tc_nstamp, sizeof(int));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (n > 128) n = 128;
+  if (n > max_n) n = max_n;
+  if (n > 0) {
+    e = cudaMemcpyFromSymbol(out_host, g_tc_stamp, sizeof(long long) * n);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  if (n + 4 <= max_n) {     // dW probe accumulators appended after the stamps
+    e = cudaMemcpyFromSymbol(out_host + n, g_tc_acc, sizeof(long long) * 4);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return -1000 - n;   // encodes the count: n = -(rc + 1000)
+}
+
+extern "C" int b200ppo_debug_select(int skip_dw) {
+  cudaError_t e = cudaMemcpyToSymbol(g_tc_stamp_skip_dw, &skip_dw, sizeof(int));
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
 extern "C" int b200ppo_set_gemm_mode(int mode) {
   const int prev = gemm_mode();
   if (mode >= 0 && mode <= 2) g_gemm_mode = mode;

@@ -6,48 +6,64 @@
 // x = hi + lo (both tf32): D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32), measured at 2-4x the
 // error of a cuBLAS fp32 GEMM (tests/test_gpu_tensorcore.py).  Weights are split once per update
 // by upd_prep_w_kernel and reach shared memory with cp.async.bulk; activations / gradients are
-// split while they are staged, one stage ahead in registers.
+// split while they are staged.
 //
-// Pipeline per GEMM (all 512 threads in lock step, 2 shared-memory stages of 32 k):
-//   store A(s) regs -> fence.proxy.async -> __syncthreads -> one thread waits for B(s) and issues
-//   4 k-steps x 3 MMAs + tcgen05.commit -> wait(other stage free) -> issue B(s+1) bulk copy and
-//   A(s+1) loads (both in flight while the MMAs run) -> ... -> wait(done) -> tcgen05.ld epilogue.
-// ncu (profiles/r1_ncu_summary_tc.md): the first version of these kernels was bound by staging
-// INSTRUCTIONS (31 per element), hence the hoisted per-thread pointers, the fixed 8-plane stages
-// and the bounds-check-free fast paths below.
+// Warp-specialised pipeline over a 4-deep shared-memory ring of 16-k stages (no __syncthreads in
+// the main loop; all hand-offs are mbarriers):
+//   warps 0-15  producers: global -> registers (3 stages ahead) -> hi/lo split -> st.shared ->
+//               fence.proxy.async -> arrive(full_a[stage]); later the tcgen05.ld epilogue
+//   warp 16     one thread waits full_a/full_b, issues 2 k-steps x 3 MMAs, tcgen05.commit ->
+//               empty[stage]
+//   warp 17     one thread streams the pre-split weight planes with cp.async.bulk -> full_b[stage]
+// Measured on B200 (profiles/r1_tc_notes.md): a dependent tcgen05.mma (M=128, K=8, tf32) costs
+// 47 / 48 / 65 / 128 cycles for N = 16 / 64 / 128 / 256; cp.async.bulk sustains ~65 B/clk/SM with
+// ~450 cycles latency; issuing one 16-k stage (6 MMAs + commit) costs the issuer ~550 cycles.
 
 constexpr int TCM = 128;
-constexpr int TCK = 32;
-constexpr int TCT = 512;
+constexpr int TCK = 16;                 // k per stage: 2 MMA k-steps of 8
+constexpr int TC_NS = 4;                // ring depth
+constexpr int TC_NPROD = 512;           // producer / epilogue threads (16 warps)
+constexpr int TCT = TC_NPROD + 64;      // + issuer warp + bulk-copy warp
 constexpr int TC_MAXN = 256;
-constexpr int TC_APT = TCM * (TCK / 4) / TCT;      // A chunks (16 B) per thread per stage = 2
-constexpr uint32_t TC_STAGE_BYTES = 2u * (TCK / 4) * tc::plane_bytes(TCM) + 2u * (TCK / 4) * tc::plane_bytes(TC_MAXN);
-constexpr uint32_t TC_SMEM = 2u * TC_STAGE_BYTES;
+constexpr uint32_t TC_A_BYTES = (TCK / 4) * tc::plane_bytes(TCM);        // one half (hi or lo)
+constexpr uint32_t TC_B_BYTES = (TCK / 4) * tc::plane_bytes(TC_MAXN);
+constexpr uint32_t TC_STAGE_BYTES = 2u * TC_A_BYTES + 2u * TC_B_BYTES;
+constexpr uint32_t TC_SMEM = TC_NS * TC_STAGE_BYTES;
+constexpr int TC_NBARS = 3 * TC_NS + 1;
+
+// phase timestamps of CTA 0 (bring-up / profiling aid; read back with b200ppo_debug_timestamps)
+__device__ long long g_tc_stamp[128];
+__device__ int g_tc_nstamp;
+__device__ int g_tc_stamp_skip_dw;
+__device__ long long g_tc_acc[8];     // dW CTA 0: [0] producer wait_empty, [1] producer work, [2] issuer wait, [3] issuer issue
+__device__ __forceinline__ void tc_stamp(int& n) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && n >= 0 && n < 128) g_tc_stamp[n] = clock64();
+  ++n;
+}
 
 struct TcCtx {
   uint8_t* smem;
-  uint64_t* bar_empty;   // [2] stage buffer free (tcgen05.commit)
-  uint64_t* bar_full;    // [2] B operand landed (cp.async.bulk complete_tx)
+  uint64_t* bar_empty;   // [NS] stage free (tcgen05.commit of the MMAs that read it)
+  uint64_t* bar_full_a;  // [NS] producers finished writing the stage (count = producer warps)
+  uint64_t* bar_full_b;  // [NS] weight planes landed (cp.async.bulk complete_tx)
   uint64_t* bar_done;
   uint32_t tmem_base;
-  uint32_t uses0, uses1;   // commits issued so far on stage buffer 0 / 1
-  uint32_t full0, full1;   // B fills consumed per stage buffer
+  uint32_t g;            // sequence number of the next stage use (ring position = g % NS)
   uint32_t done_uses;
+  int nstamp;
 };
-__device__ __forceinline__ uint32_t tc_full(const TcCtx& cx, int buf) { return buf ? cx.full1 : cx.full0; }
-__device__ __forceinline__ void tc_full_inc(TcCtx& cx, int buf) { if (buf) cx.full1++; else cx.full0++; }
-__device__ __forceinline__ uint32_t tc_uses(const TcCtx& cx, int buf) { return buf ? cx.uses1 : cx.uses0; }
-__device__ __forceinline__ void tc_uses_inc(TcCtx& cx, int buf) { if (buf) cx.uses1++; else cx.uses0++; }
-__device__ __forceinline__ void tc_wait_free(const TcCtx& cx, int buf) {
-  if (tc_uses(cx, buf) > 0u) tc::mbar_wait(&cx.bar_empty[buf], (tc_uses(cx, buf) - 1u) & 1u);
-}
 
 __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot) {
   const int warp = threadIdx.x >> 5;
   if (warp == 0) tc::tmem_alloc(tmem_slot, TC_MAXN);
   if (threadIdx.x == 32) {
 #pragma unroll
-    for (int i = 0; i < 5; ++i) tc::mbar_init(&bars[i], 1);
+    for (int i = 0; i < TC_NS; ++i) {
+      tc::mbar_init(&bars[i], 1);
+      tc::mbar_init(&bars[TC_NS + i], TC_NPROD / 32);   // one arrive per producer warp
+      tc::mbar_init(&bars[2 * TC_NS + i], 1);
+    }
+    tc::mbar_init(&bars[3 * TC_NS], 1);
     tc::mbar_init_fence();
   }
   tc::tc_fence_before();
@@ -55,15 +71,19 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* 
   tc::tc_fence_after();
   cx.smem = smem;
   cx.bar_empty = bars;
-  cx.bar_full = bars + 2;
-  cx.bar_done = bars + 4;
+  cx.bar_full_a = bars + TC_NS;
+  cx.bar_full_b = bars + 2 * TC_NS;
+  cx.bar_done = bars + 3 * TC_NS;
   cx.tmem_base = *tmem_slot;
-  cx.uses0 = cx.uses1 = 0u;
-  cx.full0 = cx.full1 = 0u;
+  cx.g = 0u;
   cx.done_uses = 0u;
+  cx.nstamp = 0;
+  tc_stamp(cx.nstamp);
 }
 
 __device__ __forceinline__ void tc_ctx_fini(TcCtx& cx) {
+  tc_stamp(cx.nstamp);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && cx.nstamp > 0) g_tc_nstamp = cx.nstamp;
   tc::tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(cx.tmem_base, TC_MAXN);
@@ -74,53 +94,104 @@ struct TcStage {
 };
 __device__ __forceinline__ TcStage tc_stage(const TcCtx& cx, int buf) {
   TcStage s;
-  s.a_hi = cx.smem + buf * TC_STAGE_BYTES;
-  s.a_lo = s.a_hi + (TCK / 4) * tc::plane_bytes(TCM);
-  s.b_hi = s.a_lo + (TCK / 4) * tc::plane_bytes(TCM);
-  s.b_lo = s.b_hi + (TCK / 4) * tc::plane_bytes(TC_MAXN);
+  // all A stages first (the idle A area doubles as the epilogue transpose buffer), then all B stages
+  s.a_hi = cx.smem + buf * 2u * TC_A_BYTES;
+  s.a_lo = s.a_hi + TC_A_BYTES;
+  s.b_hi = cx.smem + TC_NS * 2u * TC_A_BYTES + buf * 2u * TC_B_BYTES;
+  s.b_lo = s.b_hi + TC_B_BYTES;
   return s;
 }
 
-// issue the MMAs of one staged block (4 k-steps of 8) and commit
-__device__ __forceinline__ void tc_issue(TcCtx& cx, const TcStage& st, int buf, int npad, int split, bool first,
-                                         bool last) {
+// wait until ring slot `buf` may be overwritten by its `use`-th user (use counts from 0)
+__device__ __forceinline__ void tc_wait_empty(const TcCtx& cx, int buf, uint32_t use) {
+  if (use > 0u) tc::mbar_wait(&cx.bar_empty[buf], (use - 1u) & 1u);
+}
+
+// Issue the MMAs of one staged block (TCK/8 k-steps) and commit.  The issuing thread is a single
+// dependent instruction stream, so descriptors are not rebuilt per MMA (that cost ~640 cycles per
+// stage): the constant high words and the slot-0 low words are computed once per GEMM, and a
+// descriptor is one 32-bit add (the start-address field holds bytes >> 4 and cannot overflow for
+// shared-memory addresses).
+struct TcIssue {
+  uint32_t a_lo0, b_lo0;        // low descriptor words of slot 0, k-step 0 (hi operand half)
+  uint32_t a_hiw, b_hiw;        // constant high words (SBO, version)
+  uint32_t a_kstep, b_kstep;    // low-word increments per k-step
+  uint32_t b_half;              // low-word increment from the hi half to the lo half of B
+  uint32_t idesc;
+};
+__device__ __forceinline__ TcIssue tc_issue_prepare(const TcCtx& cx, int npad) {
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
-  const uint32_t idesc = tc::make_idesc_tf32(TCM, npad);
+  const TcStage st0 = tc_stage(cx, 0);
+  const uint64_t da = tc::make_desc(tc::smem_u32(st0.a_hi), pa, 128);
+  const uint64_t db = tc::make_desc(tc::smem_u32(st0.b_hi), pb, 128);
+  TcIssue t;
+  t.a_lo0 = static_cast<uint32_t>(da); t.a_hiw = static_cast<uint32_t>(da >> 32);
+  t.b_lo0 = static_cast<uint32_t>(db); t.b_hiw = static_cast<uint32_t>(db >> 32);
+  t.a_kstep = (2u * pa) >> 4;
+  t.b_kstep = (2u * pb) >> 4;
+  t.b_half = TC_B_BYTES >> 4;
+  t.idesc = tc::make_idesc_tf32(TCM, npad);
+  return t;
+}
+__device__ __forceinline__ uint64_t tc_desc(uint32_t hiw, uint32_t low) {
+  return (static_cast<uint64_t>(hiw) << 32) | low;
+}
+__device__ __forceinline__ void tc_issue(TcCtx& cx, const TcIssue& t, int buf, int split, bool first, bool last) {
+  const uint32_t a0 = t.a_lo0 + static_cast<uint32_t>(buf) * ((2u * TC_A_BYTES) >> 4);
+  const uint32_t b0 = t.b_lo0 + static_cast<uint32_t>(buf) * ((2u * TC_B_BYTES) >> 4);
   tc::tc_fence_after();
 #pragma unroll
   for (int j = 0; j < TCK / 8; ++j) {
-    const uint64_t ah = tc::make_desc(tc::smem_u32(st.a_hi + 2 * j * pa), pa, 128);
-    const uint64_t bh = tc::make_desc(tc::smem_u32(st.b_hi + 2 * j * pb), pb, 128);
+    const uint64_t ah = tc_desc(t.a_hiw, a0 + j * t.a_kstep);
+    const uint64_t bh = tc_desc(t.b_hiw, b0 + j * t.b_kstep);
     const uint32_t acc0 = (!first || j > 0) ? 1u : 0u;
     if (split) {
-      const uint64_t al = tc::make_desc(tc::smem_u32(st.a_lo + 2 * j * pa), pa, 128);
-      const uint64_t bl = tc::make_desc(tc::smem_u32(st.b_lo + 2 * j * pb), pb, 128);
-      tc::mma_tf32(cx.tmem_base, al, bh, idesc, acc0);
-      tc::mma_tf32(cx.tmem_base, ah, bl, idesc, 1u);
-      tc::mma_tf32(cx.tmem_base, ah, bh, idesc, 1u);
+      const uint64_t al = tc_desc(t.a_hiw, a0 + j * t.a_kstep + (TC_A_BYTES >> 4));
+      const uint64_t bl = tc_desc(t.b_hiw, b0 + j * t.b_kstep + t.b_half);
+      tc::mma_tf32(cx.tmem_base, al, bh, t.idesc, acc0);
+      tc::mma_tf32(cx.tmem_base, ah, bl, t.idesc, 1u);
+      tc::mma_tf32(cx.tmem_base, ah, bh, t.idesc, 1u);
     } else {
-      tc::mma_tf32(cx.tmem_base, ah, bh, idesc, acc0);
+      tc::mma_tf32(cx.tmem_base, ah, bh, t.idesc, acc0);
     }
   }
   tc::commit(&cx.bar_empty[buf]);
   if (last) tc::commit(cx.bar_done);
 }
 
-// wait for the accumulator, run the epilogue functor on 16-column groups, release the accumulator
-template <class Epi>
-__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, Epi epi) {
-  tc::mbar_wait(cx.bar_done, cx.done_uses & 1u);
-  cx.done_uses++;
-  tc::tc_fence_after();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sub = warp & 3;
-  for (int c = (warp >> 2) * 16; c < npad; c += (TCT / 128) * 16) {
-    float v[16];
-    tc::tmem_ld16(cx.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
-    epi(sub * 32 + lane, c, v);
+// Epilogue of the producer warps, in steps of 64 accumulator columns:
+//   phase A  warp (sub, cg) reads its 32 rows x 16 columns from TMEM, `fa(r, c, v)` may modify v
+//            (bias) and accumulate thread-private results, v goes to the smem transpose buffer
+//            (the idle A area of the ring; row pitch 272 B = conflict-free for both phases);
+//   phase B  all 512 threads stream the 128 x 64 block out: `fb(r, col, float4)` does the global
+//            I/O with full 256-byte row segments per half-warp (the direct TMEM->global version
+//            wrote 16 B per lane at a 1 KB stride: 9 K cycles of LSU time per 256-wide layer).
+constexpr int TC_EP_PITCH = 68;   // floats
+template <class FA, class FB>
+__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, FB fb) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = warp & 3, cg = warp >> 2;
+  float* ebuf = reinterpret_cast<float*>(cx.smem);
+  const int r = sub * 32 + lane;
+  for (int c0 = 0; c0 < npad; c0 += 64) {
+    const int c = c0 + cg * 16;
+    if (c < npad) {
+      float v[16];
+      tc::tmem_ld16(cx.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
+      fa(r, c, v);
+      float4* dst = reinterpret_cast<float4*>(ebuf + r * TC_EP_PITCH + cg * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
+    const int ncol4 = ((npad - c0) < 64 ? (npad - c0) : 64) >> 2;        // float4 per row in this step
+#pragma unroll 4
+    for (int idx = tid; idx < TCM * 16; idx += TC_NPROD) {
+      const int row = idx >> 4, f4 = idx & 15;
+      if (f4 < ncol4) fb(row, c0 + 4 * f4, *reinterpret_cast<const float4*>(ebuf + row * TC_EP_PITCH + 4 * f4));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
   }
-  tc::tc_fence_before();
-  __syncthreads();
 }
 
 __device__ __forceinline__ float4 act4(float4 x, int act) {
@@ -132,102 +203,109 @@ __device__ __forceinline__ float4 act4(float4 x, int act) {
   return x;
 }
 
-// Row-tile GEMM.  A[row][k] (row-major, leading dimension lda, rows row0..row0+127, rows >= nrows
-// read as zero, activation `act` applied on load); B from the pre-split planes Bhi/Blo laid out
-// [K32/4][npad + 1][4] in global memory (K32 = K rounded up to 32; same padded plane stride as in
-// shared memory, so a stage of B is ONE contiguous bulk copy per half).
-template <class Epi>
-__device__ __forceinline__ void tc_gemm_rowtile(TcCtx& cx, const float* __restrict__ A, int lda, int row0,
-                                                int nrows, int K, int act, const float* __restrict__ Bhi,
-                                                const float* __restrict__ Blo, int npad, int split,
-                                                const float* __restrict__ colvec, int ncol, float* colvec_s,
-                                                Epi epi) {
-  const int tid = threadIdx.x;
-  // per-column epilogue vector (bias) staged in shared memory: visible after the first stage barrier
-  if (colvec != nullptr && tid < npad) colvec_s[tid] = tid < ncol ? __ldg(colvec + tid) : 0.0f;
+// Main loop of a row-tile GEMM (no epilogue).  A[row][k] (row-major, leading dimension lda, rows
+// row0..row0+127, rows >= nrows read as zero, activation `act` applied on load); B from the
+// pre-split planes Bhi/Blo laid out [K16/4][npad + 1][4] in global memory (same padded plane
+// stride as in shared memory, so a stage of B is ONE contiguous bulk copy per half).
+__device__ __forceinline__ void tc_mainloop(TcCtx& cx, const float* __restrict__ A, int lda, int row0,
+                                            int nrows, int K, int act, const float* __restrict__ Bhi,
+                                            const float* __restrict__ Blo, int npad, int split) {
+  const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = (K + TCK - 1) / TCK;
-  const uint32_t bbytes = (TCK / 4) * pb;
-  // per-thread chunk coordinates are the same for every stage: hoist pointers and smem offsets
-  const float* ap[TC_APT];
-  uint32_t soff[TC_APT];
-  int kq[TC_APT];
-  bool rv[TC_APT];
-#pragma unroll
-  for (int i = 0; i < TC_APT; ++i) {
-    const int idx = tid + i * TCT;
-    const int q = idx & 7, r = idx >> 3;
-    rv[i] = row0 + r < nrows;
-    ap[i] = A + static_cast<size_t>(rv[i] ? row0 + r : 0) * lda + 4 * q;
-    soff[i] = q * pa + r * 16;
-    kq[i] = 4 * q;
-  }
-  const bool vec = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
-  // A is prefetched TWO stages ahead in registers (global-load latency >> one stage of MMAs)
-  float4 areg[2][TC_APT];
-  auto load_a = [&](int s, float4 (&dst)[TC_APT]) {
-    const int k0 = s * TCK;
-#pragma unroll
-    for (int i = 0; i < TC_APT; ++i) {
+  const uint32_t g0 = cx.g;
+  if (warp < TC_NPROD / 32) {
+    // ---------------- producers ----------------
+    const int q = tid & 3, r = tid >> 2;                  // one 16-byte chunk per thread per stage
+    const bool rv = row0 + r < nrows;
+    const float* ap = A + static_cast<size_t>(rv ? row0 + r : 0) * lda + 4 * q;
+    const uint32_t soff = q * pa + r * 16;
+    const bool vec = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+    auto load_a = [&](int s) {
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rv[i]) {
-        const int k = k0 + kq[i];
+      const int k = s * TCK + 4 * q;
+      if (rv && s < nst) {
         if (vec && k + 3 < K) {
-          x = *reinterpret_cast<const float4*>(ap[i] + k0);
+          x = *reinterpret_cast<const float4*>(ap + s * TCK);
         } else if (k < K) {
-          const float* src = ap[i] + k0;
+          const float* src = ap + s * TCK;
           x.x = src[0];
           if (k + 1 < K) x.y = src[1];
           if (k + 2 < K) x.z = src[2];
           if (k + 3 < K) x.w = src[3];
         }
       }
-      dst[i] = x;
-    }
-  };
-  auto issue_b = [&](int s, int buf) {        // one thread
-    const TcStage st = tc_stage(cx, buf);
-    const size_t off = static_cast<size_t>(s) * (bbytes / 4);     // floats
-    tc::mbar_arrive_expect_tx(&cx.bar_full[buf], split ? 2u * bbytes : bbytes);
-    tc::bulk_g2s(st.b_hi, Bhi + off, bbytes, &cx.bar_full[buf]);
-    if (split) tc::bulk_g2s(st.b_lo, Blo + off, bbytes, &cx.bar_full[buf]);
-  };
-  tc_wait_free(cx, 0);
-  if (tid == 0) issue_b(0, 0);
-  load_a(0, areg[0]);
-  if (nst > 1) load_a(1, areg[1]);
-  for (int s = 0; s < nst; ++s) {
-    const int buf = s & 1;
-    const TcStage st = tc_stage(cx, buf);
-#pragma unroll
-    for (int i = 0; i < TC_APT; ++i) {
+      return x;
+    };
+    // 4 stages in flight: a 64-wide layer is one memory round trip
+    float4 a0 = load_a(0), a1 = load_a(1), a2 = load_a(2), a3 = load_a(3);
+    for (int s = 0; s < nst; ++s) {
+      const uint32_t gs = g0 + s;
+      const int buf = gs % TC_NS;
+      const TcStage st = tc_stage(cx, buf);
+      tc_wait_empty(cx, buf, gs / TC_NS);
       float4 hi, lo;
-      tc::split4(act4(buf ? areg[1][i] : areg[0][i], act), hi, lo);
-      *reinterpret_cast<float4*>(st.a_hi + soff[i]) = hi;
-      if (split) *reinterpret_cast<float4*>(st.a_lo + soff[i]) = lo;
+      tc::split4(act4(a0, act), hi, lo);
+      a0 = a1; a1 = a2; a2 = a3; a3 = load_a(s + 4);
+      *reinterpret_cast<float4*>(st.a_hi + soff) = hi;
+      if (split) *reinterpret_cast<float4*>(st.a_lo + soff) = lo;
+      // 512 per-thread arrives on one mbarrier word serialise (~1-2 K cycles per stage, measured):
+      // every lane fences its own writes, the warp converges, one lane arrives for the warp
+      tc::fence_proxy_async();
+      __syncwarp();
+      if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
     }
-    if (s + 2 < nst) {                          // refill the register set just consumed
-      if (buf) load_a(s + 2, areg[1]); else load_a(s + 2, areg[0]);
+  } else if (warp == TC_NPROD / 32) {
+    // ---------------- MMA issuer ----------------
+    if ((tid & 31) == 0) {
+      const TcIssue ti = tc_issue_prepare(cx, npad);
+      for (int s = 0; s < nst; ++s) {
+        const uint32_t gs = g0 + s;
+        const int buf = gs % TC_NS;
+        const uint32_t par = (gs / TC_NS) & 1u;
+        tc::mbar_wait(&cx.bar_full_a[buf], par);
+        tc::mbar_wait(&cx.bar_full_b[buf], par);
+        tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
+      }
     }
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc::mbar_wait(&cx.bar_full[buf], tc_full(cx, buf) & 1u);
-      tc_issue(cx, st, buf, npad, split, s == 0, s == nst - 1);
+    __syncwarp();
+  } else {
+    // ------- weight (B operand) bulk-copy producer: never joins the per-layer barriers, so it
+    // ------- runs ahead into the next layer as soon as ring slots free up
+    if ((tid & 31) == 0) {
+      const uint32_t bbytes = (TCK / 4) * pb;
+      for (int s = 0; s < nst; ++s) {
+        const uint32_t gs = g0 + s;
+        const int buf = gs % TC_NS;
+        tc_wait_empty(cx, buf, gs / TC_NS);
+        const TcStage st = tc_stage(cx, buf);
+        const size_t off = static_cast<size_t>(s) * (bbytes / 4);     // floats
+        tc::mbar_arrive_expect_tx(&cx.bar_full_b[buf], split ? 2u * bbytes : bbytes);
+        tc::bulk_g2s(st.b_hi, Bhi + off, bbytes, &cx.bar_full_b[buf]);
+        if (split) tc::bulk_g2s(st.b_lo, Blo + off, bbytes, &cx.bar_full_b[buf]);
+      }
     }
-    tc_uses_inc(cx, buf);
-    tc_full_inc(cx, buf);
-    if (s + 1 < nst) {
-      tc_wait_free(cx, buf ^ 1);
-      if (tid == 0) issue_b(s + 1, buf ^ 1);
-    }
+    __syncwarp();
   }
-  tc_epilogue(cx, npad, epi);
+  cx.g = g0 + nst;
+}
+
+// wait for the accumulator (producer warps) / finish a GEMM (everybody but the weight-copy warp)
+__device__ __forceinline__ void tc_wait_acc(TcCtx& cx) {
+  tc::mbar_wait(cx.bar_done, cx.done_uses & 1u);
+  tc::tc_fence_after();
+}
+__device__ __forceinline__ void tc_gemm_end(TcCtx& cx) {
+  cx.done_uses++;
+  if ((threadIdx.x >> 5) <= TC_NPROD / 32) {              // producers + issuer
+    tc::tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(TC_NPROD + 32) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // weight pre-split: Wf (forward operand, Bop(n, k) = W[k][n]) and Wb (dX operand,
-// Bop(kout, nred) = W[kout][nred]), each as hi / lo planes [red32/4][rows_pad + 1][4]
+// Bop(kout, nred) = W[kout][nred]), each as hi / lo planes [red16/4][rows_pad + 1][4]
 // ------------------------------------------------------------------------------------------
 struct PrepArgs {
   b200ppo_plan plan;
@@ -246,7 +324,7 @@ __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
   const float* W = a.params + ch.w_off[l];
   const bool fwd = blockIdx.z == 0;
   const int rows = fwd ? t.npad : t.kout_pad;          // operand rows
-  const int red = fwd ? t.kpad : t.nred_pad;           // reduction length (padded to 32)
+  const int red = fwd ? t.kpad : t.nred_pad;           // reduction length (padded to TCK)
   float4* hi = reinterpret_cast<float4*>(a.ws + (fwd ? t.wf_hi : t.wb_hi));
   float4* lo = reinterpret_cast<float4*>(a.ws + (fwd ? t.wf_lo : t.wb_lo));
   const int prow = rows + 1;                           // padded plane stride (float4), see tc.cuh
@@ -272,44 +350,112 @@ __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
 // ------------------------------------------------------------------------------------------
 // FWD (tensor cores)
 // ------------------------------------------------------------------------------------------
+struct TcFwdSmem {
+  float bias[TC_MAXN];
+  float thin_w[TC_MAXN * 4];          // weights of a fused thin (<= 4 outputs) last layer
+  __align__(16) float thin_part[4 * TCM * 4];   // [column group][row][output] partial dots
+};
+
+// both threads groups that take part in the per-layer hand-off (producers + issuer)
+__device__ __forceinline__ void tc_layer_sync() {
+  if ((threadIdx.x >> 5) <= TC_NPROD / 32) asm volatile("bar.sync 2, %0;" ::"n"(TC_NPROD + 32) : "memory");
+}
+
 __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,
                                                  const float* __restrict__ P, float* ws, const size_t* zoff,
-                                                 size_t xhat_off, int row0, int nrows, int split, float* bias_s) {
-  for (int l = 0; l < ch.n_layers; ++l) {
+                                                 size_t xhat_off, int row0, int nrows, int split, TcFwdSmem& sm) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int L = ch.n_layers;
+  // a thin last layer (the critic's 256 -> 1 head) is a per-row dot product: fused into the
+  // epilogue of the layer before it instead of running a 16-column padded GEMM
+  const bool fuse_thin = L >= 2 && ch.dims[L] <= 4 && ch.dims[L - 1] <= TC_MAXN;
+  const int Lg = fuse_thin ? L - 1 : L;
+  for (int l = 0; l < Lg; ++l) {
     const int K = ch.dims[l], N = ch.dims[l + 1];
     const float* A = l == 0 ? ws + xhat_off : ws + zoff[l - 1];
     const int act_in = l == 0 ? B200PPO_ACT_NONE : ch.act;
     const float* bias = P + ch.b_off[l];
     float* Z = ws + zoff[l];
-    tc_gemm_rowtile(cx, A, K, row0, nrows, K, act_in, ws + tl[l].wf_hi, ws + tl[l].wf_lo, tl[l].npad, split,
-                    bias, N, bias_s, [&](int r, int c, const float (&v)[16]) {
-                      const int row = row0 + r;
-                      if (row < nrows) {
-                        float* dst = Z + static_cast<size_t>(row) * N + c;
-                        if ((N & 3) == 0) {
+    const int npad = tl[l].npad;
+    const bool thin = fuse_thin && l == L - 2;
+    const int NT = thin ? ch.dims[L] : 0;
+    if (tid < TC_NPROD) {
+      if (tid < npad) sm.bias[tid] = tid < N ? __ldg(bias + tid) : 0.0f;
+      if (thin) {
+        const float* Wt = P + ch.w_off[L - 1];
+        for (int i = tid; i < N * NT; i += TC_NPROD) sm.thin_w[i] = __ldg(Wt + i);
+      }
+    }
+    tc_mainloop(cx, A, K, row0, nrows, K, act_in, ws + tl[l].wf_hi, ws + tl[l].wf_lo, npad, split);
+    tc_stamp(cx.nstamp);                                                 // producer loop done
+    if (warp < TC_NPROD / 32) {
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");       // sm.bias / sm.thin_w visible
+      tc_wait_acc(cx);
+      tc_stamp(cx.nstamp);                                               // accumulator complete
+      float tp[4] = {0.f, 0.f, 0.f, 0.f};
+      const int act = ch.act;
+      tc_epilogue(
+          cx, npad,
+          [&](int r, int c, float (&v)[16]) {
 #pragma unroll
-                          for (int i = 0; i < 16; i += 4)
-                            if (c + i < N) {
-                              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + i);
-                              *reinterpret_cast<float4*>(dst + i) =
-                                  make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
-                            }
-                        } else {
+            for (int i = 0; i < 16; ++i) v[i] += sm.bias[c + i];
+            if (thin) {
 #pragma unroll
-                          for (int i = 0; i < 16; ++i)
-                            if (c + i < N) dst[i] = v[i] + bias_s[c + i];
-                        }
-                      }
-                    });
+              for (int i = 0; i < 16; ++i) {
+                if (c + i < N) {
+                  const float h = act_fwd(v[i], act);
+                  const float* w = sm.thin_w + (c + i) * NT;
+                  tp[0] = fmaf(h, w[0], tp[0]);           // fixed indices: tp[] stays in registers
+                  if (NT > 1) tp[1] = fmaf(h, w[1], tp[1]);
+                  if (NT > 2) tp[2] = fmaf(h, w[2], tp[2]);
+                  if (NT > 3) tp[3] = fmaf(h, w[3], tp[3]);
+                }
+              }
+            }
+          },
+          [&](int r, int col, const float4 val) {
+            const int row = row0 + r;
+            if (row < nrows && col < N) {
+              float* dst = Z + static_cast<size_t>(row) * N + col;
+              if ((N & 3) == 0) {
+                *reinterpret_cast<float4*>(dst) = val;
+              } else {
+                dst[0] = val.x;
+                if (col + 1 < N) dst[1] = val.y;
+                if (col + 2 < N) dst[2] = val.z;
+                if (col + 3 < N) dst[3] = val.w;
+              }
+            }
+          });
+      tc_stamp(cx.nstamp);                                               // epilogue body done
+      if (thin) {
+        const int r = (warp & 3) * 32 + (tid & 31), cg = warp >> 2;
+        *reinterpret_cast<float4*>(&sm.thin_part[(cg * TCM + r) * 4]) = make_float4(tp[0], tp[1], tp[2], tp[3]);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
+        const float* bt = P + ch.b_off[L - 1];
+        float* Zt = ws + zoff[L - 1];
+        for (int i = tid; i < TCM * NT; i += TC_NPROD) {
+          const int rr = i / NT, j = i - rr * NT;
+          if (row0 + rr < nrows) {
+            float acc = 0.0f;
+            for (int g = 0; g < 4; ++g) acc += sm.thin_part[(g * TCM + rr) * 4 + j];
+            Zt[static_cast<size_t>(row0 + rr) * NT + j] = acc + __ldg(bt + j);
+          }
+        }
+      }
+    }
+    else cx.nstamp += 2;
+    tc_gemm_end(cx);
+    tc_stamp(cx.nstamp);                                                 // epilogue + hand-off done
   }
 }
 
 __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, const int split) {
   extern __shared__ __align__(128) uint8_t tsmem[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ const float* rowsrc[TCM];
-  __shared__ __align__(16) float bias_s[TC_MAXN];
+  __shared__ __align__(16) TcFwdSmem sm;
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
   const int O = a.plan.obs_dim;
@@ -328,30 +474,38 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
     rowsrc[m] = src;
   }
   __syncthreads();
-  constexpr int XB = 4;
-  for (int i0 = threadIdx.x; i0 < TCM * O; i0 += TCT * XB) {
-    float xv[XB];
-#pragma unroll
-    for (int j = 0; j < XB; ++j) {
-      const int idx = i0 + j * TCT;
-      const int m = idx / O, k = idx - m * O;
-      xv[j] = 0.0f;
-      if (idx < TCM * O && rowsrc[m] != nullptr) xv[j] = rowsrc[m][k];
+  // gather + normalise this tile's observations (ppo.py:297 gather; normalizer.py:78-80)
+  if ((O & 3) == 0) {
+    const int O4 = O >> 2;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < TCM * O4; idx += TCT) {
+      const int m = idx / O4, c4 = idx - m * O4;
+      const float* src = rowsrc[m];
+      if (src != nullptr) {
+        float4 x = *reinterpret_cast<const float4*>(src + 4 * c4);
+        if (a.plan.normalize) {
+          const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean) + c4);
+          const float4 sd = __ldg(reinterpret_cast<const float4*>(a.std) + c4);
+          x.x = __fdiv_rn(x.x - mu.x, sd.x); x.y = __fdiv_rn(x.y - mu.y, sd.y);
+          x.z = __fdiv_rn(x.z - mu.z, sd.z); x.w = __fdiv_rn(x.w - mu.w, sd.w);
+        }
+        *reinterpret_cast<float4*>(xhat + static_cast<size_t>(row0 + m) * O + 4 * c4) = x;
+      }
     }
-#pragma unroll
-    for (int j = 0; j < XB; ++j) {
-      const int idx = i0 + j * TCT;
+  } else {
+    for (int idx = threadIdx.x; idx < TCM * O; idx += TCT) {
       const int m = idx / O, k = idx - m * O;
-      if (idx < TCM * O && rowsrc[m] != nullptr) {
-        float x = xv[j];
+      if (rowsrc[m] != nullptr) {
+        float x = rowsrc[m][k];
         if (a.plan.normalize) x = __fdiv_rn(x - __ldg(a.mean + k), __ldg(a.std + k));
         xhat[static_cast<size_t>(row0 + m) * O + k] = x;
       }
     }
   }
   __syncthreads();
-  tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, bias_s);
-  if (row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, bias_s);
+  tc_stamp(cx.nstamp);
+  tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, sm);
+  if (row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, sm);
   tc_ctx_fini(cx);
 }
 
@@ -359,67 +513,96 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
 // BWD dX (tensor cores): dpre_{l-1} = (dpre_l W_l^T) ⊙ act'(z_{l-1})
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,
-                                                  float* ws, const size_t* zoff, const size_t* doff, int row0,
-                                                  int nrows, int split) {
+                                                  const float* __restrict__ P, float* ws, const size_t* zoff,
+                                                  const size_t* doff, int row0, int nrows, int split) {
+  const int tid = threadIdx.x, warp = tid >> 5;
   for (int l = ch.n_layers - 1; l >= 1; --l) {
     const int Kl = ch.dims[l], Nl = ch.dims[l + 1];
     const float* dY = ws + doff[l];
     const float* zprev = ws + zoff[l - 1];
     float* dprev = ws + doff[l - 1];
     const int act = ch.act;
-    tc_gemm_rowtile(cx, dY, Nl, row0, nrows, Nl, B200PPO_ACT_NONE, ws + tl[l].wb_hi, ws + tl[l].wb_lo,
-                    tl[l].kout_pad, split, nullptr, 0, nullptr, [&](int r, int c, const float (&v)[16]) {
-                      const int row = row0 + r;
-                      if (row < nrows) {
-                        const size_t o = static_cast<size_t>(row) * Kl + c;
-                        if ((Kl & 3) == 0) {
-#pragma unroll
-                          for (int i = 0; i < 16; i += 4)
-                            if (c + i < Kl) {
-                              const float4 z = *reinterpret_cast<const float4*>(zprev + o + i);
-                              float4 g;
-                              if (act == B200PPO_ACT_RELU) {
-                                g = make_float4(z.x > 0.f ? v[i] : 0.f, z.y > 0.f ? v[i + 1] : 0.f,
-                                                z.z > 0.f ? v[i + 2] : 0.f, z.w > 0.f ? v[i + 3] : 0.f);
-                              } else {
-                                g = make_float4(v[i] * act_grad(z.x, act), v[i + 1] * act_grad(z.y, act),
-                                                v[i + 2] * act_grad(z.z, act), v[i + 3] * act_grad(z.w, act));
-                              }
-                              *reinterpret_cast<float4*>(dprev + o + i) = g;
-                            }
-                        } else {
-#pragma unroll
-                          for (int i = 0; i < 16; ++i)
-                            if (c + i < Kl) dprev[o + i] = v[i] * act_grad(zprev[o + i], act);
-                        }
-                      }
-                    });
+    if (Nl <= 4) {
+      // thin layer (value head): dX is a rank-Nl outer product, done element-wise and coalesced
+      if (tid < TC_NPROD) {
+        const float* W = P + ch.w_off[l];
+        for (int idx = tid; idx < TCM * Kl; idx += TC_NPROD) {
+          const int rr = idx / Kl, k = idx - rr * Kl;
+          const int row = row0 + rr;
+          if (row < nrows) {
+            float acc = 0.0f;
+            for (int j = 0; j < Nl; ++j) acc = fmaf(dY[static_cast<size_t>(row) * Nl + j], __ldg(W + static_cast<size_t>(k) * Nl + j), acc);
+            const size_t o = static_cast<size_t>(row) * Kl + k;
+            dprev[o] = acc * act_grad(zprev[o], act);
+          }
+        }
+      }
+      tc_layer_sync();
+      tc_stamp(cx.nstamp);
+      continue;
+    }
+    const int npad = tl[l].kout_pad;
+    tc_mainloop(cx, dY, Nl, row0, nrows, Nl, B200PPO_ACT_NONE, ws + tl[l].wb_hi, ws + tl[l].wb_lo, npad, split);
+    tc_stamp(cx.nstamp);
+    if (warp < TC_NPROD / 32) {
+      tc_wait_acc(cx);
+      tc_stamp(cx.nstamp);
+      tc_epilogue(
+          cx, npad, [&](int, int, float (&)[16]) {},
+          [&](int r, int col, const float4 val) {
+            const int row = row0 + r;
+            if (row < nrows && col < Kl) {
+              const size_t o = static_cast<size_t>(row) * Kl + col;
+              if ((Kl & 3) == 0) {
+                const float4 z = *reinterpret_cast<const float4*>(zprev + o);
+                float4 g;
+                if (act == B200PPO_ACT_RELU) {
+                  g = make_float4(z.x > 0.f ? val.x : 0.f, z.y > 0.f ? val.y : 0.f, z.z > 0.f ? val.z : 0.f,
+                                  z.w > 0.f ? val.w : 0.f);
+                } else {
+                  g = make_float4(val.x * act_grad(z.x, act), val.y * act_grad(z.y, act),
+                                  val.z * act_grad(z.z, act), val.w * act_grad(z.w, act));
+                }
+                *reinterpret_cast<float4*>(dprev + o) = g;
+              } else {
+                const float vv[4] = {val.x, val.y, val.z, val.w};
+                for (int i = 0; i < 4; ++i)
+                  if (col + i < Kl) dprev[o + i] = vv[i] * act_grad(zprev[o + i], act);
+              }
+            }
+          });
+    }
+    else ++cx.nstamp;
+    tc_gemm_end(cx);
+    tc_stamp(cx.nstamp);
   }
 }
 
 __global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, const int split) {
   extern __shared__ __align__(128) uint8_t tsmem[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
   const int row0 = blockIdx.x * TCM;
-  tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
-  tc_chain_backward(cx, a.plan.actor, a.L.tca, a.ws, a.L.za, a.L.da, row0, a.L.R, split);
+  tc_stamp(cx.nstamp);
+  tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
+  tc_chain_backward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.da, row0, a.L.R, split);
   tc_ctx_fini(cx);
 }
 
 // ------------------------------------------------------------------------------------------
 // BWD dW (tensor cores): dW_l[k][n] = sum_r act(z_{l-1})[r][k] * dpre_l[r][n]
 // D rows = k (tiles of 128), D cols = n (padded to 16), reduction over this CTA's row range; both
-// operands are transposed gathers (a 16-byte chunk = the same column of 4 consecutive data rows).
-// The threads that stage column n of dpre also accumulate its sum: the bias gradient.
+// operands are transposed gathers (a 16-byte chunk = the same column of 4 consecutive data rows)
+// staged by the producer warps.  The threads that stage column n of dpre also accumulate its sum:
+// the bias gradient.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, const int split) {
   extern __shared__ __align__(128) uint8_t tsmem[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
-  __shared__ float bred[TCT];
+  __shared__ float bred[TC_NPROD];
   int item = blockIdx.x;
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
@@ -438,6 +621,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   if (layer < 0) return;                                   // uniform per CTA
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  if (g_tc_stamp_skip_dw & 1) cx.nstamp = -100000;
   const int K = ch->dims[layer], N = ch->dims[layer + 1];
   const int npad = (N + 15) & ~15;
   const int m0 = mt * TCM;
@@ -448,124 +632,141 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   const int r_begin = sp * a.L.tc_rows_per_split;
   int r_end = r_begin + a.L.tc_rows_per_split;
   if (r_end > a.L.R) r_end = a.L.R;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = (r_end - r_begin + TCK - 1) / TCK;
-  // A: thread -> (m = idx & 127, q = idx >> 7), idx = tid + i*512: same coordinates every stage
-  const float* ap[TC_APT];
-  uint32_t aoff[TC_APT];
-  int aq[TC_APT];
-  bool av[TC_APT];
-#pragma unroll
-  for (int i = 0; i < TC_APT; ++i) {
-    const int idx = tid + i * TCT;
-    const int m = idx & (TCM - 1), q = idx >> 7;
-    av[i] = m0 + m < K;
-    aq[i] = 4 * q;
-    ap[i] = H + static_cast<size_t>(r_begin + 4 * q) * K + (av[i] ? m0 + m : 0);
-    aoff[i] = q * pa + m * 16;
-  }
-  // B: thread -> column n = tid & 255 (if < npad), plane half = tid >> 8 (planes 4*half .. +3)
-  const int bn = tid & 255, bh = tid >> 8;
-  const bool bv = bn < N;
-  const bool bstage = bn < npad;
-  const float* bp = D + static_cast<size_t>(r_begin + 16 * bh) * N + (bv ? bn : 0);
   float bsum = 0.0f;
-  float4 areg[TC_APT], breg[4];
-  auto load_stage = [&](int s) {
-    const int rs = r_begin + s * TCK;
-    const size_t so = static_cast<size_t>(s) * TCK;
-    if (rs + TCK <= r_end) {                                    // full stage: no row bounds checks
-#pragma unroll
-      for (int i = 0; i < TC_APT; ++i) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (av[i]) {
-          const float* src = ap[i] + so * K;
-          x = make_float4(src[0], src[K], src[2 * static_cast<size_t>(K)], src[3 * static_cast<size_t>(K)]);
+  if (warp < TC_NPROD / 32) {
+    // A: thread -> (m = tid & 127, plane q = tid >> 7); B: thread -> (column n = tid & 255, planes 2h, 2h+1)
+    const int am = tid & (TCM - 1), aq = tid >> 7;
+    const bool av = m0 + am < K;
+    const float* ap = H + static_cast<size_t>(r_begin + 4 * aq) * K + (av ? m0 + am : 0);
+    const uint32_t aoff = aq * pa + am * 16;
+    const int bn = tid & 255, bh = tid >> 8;
+    const bool bv = bn < N, bstage = bn < npad;
+    const float* bp = D + static_cast<size_t>(r_begin + 8 * bh) * N + (bv ? bn : 0);
+    struct Regs { float4 a, b0, b1; };
+    auto load_stage = [&](int s) {
+      Regs x;
+      x.a = x.b0 = x.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s >= nst) return x;
+      const int rs = r_begin + s * TCK;
+      const size_t so = static_cast<size_t>(s) * TCK;
+      if (rs + TCK <= r_end) {                                  // full stage: no row bounds checks
+        if (av) {
+          const float* src = ap + so * K;
+          x.a = make_float4(src[0], src[K], src[2 * static_cast<size_t>(K)], src[3 * static_cast<size_t>(K)]);
         }
-        areg[i] = x;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bv) {
-          const float* src = bp + (so + 4 * j) * N;
-          x = make_float4(src[0], src[N], src[2 * static_cast<size_t>(N)], src[3 * static_cast<size_t>(N)]);
+          const float* src = bp + so * N;
+          x.b0 = make_float4(src[0], src[N], src[2 * static_cast<size_t>(N)], src[3 * static_cast<size_t>(N)]);
+          src += 4 * static_cast<size_t>(N);
+          x.b1 = make_float4(src[0], src[N], src[2 * static_cast<size_t>(N)], src[3 * static_cast<size_t>(N)]);
         }
-        breg[j] = x;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < TC_APT; ++i) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (av[i]) {
-          const float* src = ap[i] + so * K;
-          const int r = rs + aq[i];
-          if (r + 0 < r_end) x.x = src[0];
-          if (r + 1 < r_end) x.y = src[K];
-          if (r + 2 < r_end) x.z = src[2 * static_cast<size_t>(K)];
-          if (r + 3 < r_end) x.w = src[3 * static_cast<size_t>(K)];
+      } else {
+        if (av) {
+          const float* src = ap + so * K;
+          const int r = rs + 4 * aq;
+          if (r + 0 < r_end) x.a.x = src[0];
+          if (r + 1 < r_end) x.a.y = src[K];
+          if (r + 2 < r_end) x.a.z = src[2 * static_cast<size_t>(K)];
+          if (r + 3 < r_end) x.a.w = src[3 * static_cast<size_t>(K)];
         }
-        areg[i] = x;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bv) {
-          const float* src = bp + (so + 4 * j) * N;
-          const int r = rs + 16 * bh + 4 * j;
-          if (r + 0 < r_end) x.x = src[0];
-          if (r + 1 < r_end) x.y = src[N];
-          if (r + 2 < r_end) x.z = src[2 * static_cast<size_t>(N)];
-          if (r + 3 < r_end) x.w = src[3 * static_cast<size_t>(N)];
+          const float* src = bp + so * N;
+          int r = rs + 8 * bh;
+          if (r + 0 < r_end) x.b0.x = src[0];
+          if (r + 1 < r_end) x.b0.y = src[N];
+          if (r + 2 < r_end) x.b0.z = src[2 * static_cast<size_t>(N)];
+          if (r + 3 < r_end) x.b0.w = src[3 * static_cast<size_t>(N)];
+          src += 4 * static_cast<size_t>(N);
+          r += 4;
+          if (r + 0 < r_end) x.b1.x = src[0];
+          if (r + 1 < r_end) x.b1.y = src[N];
+          if (r + 2 < r_end) x.b1.z = src[2 * static_cast<size_t>(N)];
+          if (r + 3 < r_end) x.b1.w = src[3 * static_cast<size_t>(N)];
         }
-        breg[j] = x;
       }
-    }
-  };
-  if (nst > 0) load_stage(0);
-  for (int s = 0; s < nst; ++s) {
-    const int buf = s & 1;
-    const TcStage st = tc_stage(cx, buf);
-    tc_wait_free(cx, buf);
-#pragma unroll
-    for (int i = 0; i < TC_APT; ++i) {
+      return x;
+    };
+    Regs x0 = load_stage(0), x1 = load_stage(1), x2 = load_stage(2);
+    long long t_wait = 0, t_work = 0;
+    const bool probe = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    for (int s = 0; s < nst; ++s) {
+      const uint32_t gs = cx.g + s;
+      const int buf = gs % TC_NS;
+      const TcStage st = tc_stage(cx, buf);
+      const long long tA = probe ? clock64() : 0;
+      tc_wait_empty(cx, buf, gs / TC_NS);
+      const long long tB = probe ? clock64() : 0;
+      t_wait += tB - tA;
       float4 hi, lo;
-      tc::split4(act4(areg[i], act_in), hi, lo);       // act(0) == 0 for relu / tanh / swish
-      *reinterpret_cast<float4*>(st.a_hi + aoff[i]) = hi;
-      if (split) *reinterpret_cast<float4*>(st.a_lo + aoff[i]) = lo;
-    }
-    if (bstage) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 hi, lo;
-        tc::split4(breg[j], hi, lo);
-        bsum += (breg[j].x + breg[j].y) + (breg[j].z + breg[j].w);
-        const uint32_t o = (4 * bh + j) * pb + bn * 16;
+      tc::split4(act4(x0.a, act_in), hi, lo);               // act(0) == 0 for relu / tanh / swish
+      *reinterpret_cast<float4*>(st.a_hi + aoff) = hi;
+      if (split) *reinterpret_cast<float4*>(st.a_lo + aoff) = lo;
+      if (bstage) {
+        bsum += ((x0.b0.x + x0.b0.y) + (x0.b0.z + x0.b0.w)) + ((x0.b1.x + x0.b1.y) + (x0.b1.z + x0.b1.w));
+        tc::split4(x0.b0, hi, lo);
+        uint32_t o = (2 * bh) * pb + bn * 16;
+        *reinterpret_cast<float4*>(st.b_hi + o) = hi;
+        if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
+        tc::split4(x0.b1, hi, lo);
+        o += pb;
         *reinterpret_cast<float4*>(st.b_hi + o) = hi;
         if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
       }
+      x0 = x1; x1 = x2; x2 = load_stage(s + 3);
+      tc::fence_proxy_async();
+      __syncwarp();
+      if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
+      if (probe) t_work += clock64() - tB;
     }
-    tc::fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) tc_issue(cx, st, buf, npad, split, s == 0, s == nst - 1);
-    tc_uses_inc(cx, buf);
-    if (s + 1 < nst) load_stage(s + 1);
+    if (probe) { g_tc_acc[0] = t_wait; g_tc_acc[1] = t_work; }
+  } else if (warp == TC_NPROD / 32) {
+    if ((tid & 31) == 0) {
+      long long t_wait = 0, t_issue = 0;
+      const TcIssue ti = tc_issue_prepare(cx, npad);
+      for (int s = 0; s < nst; ++s) {
+        const uint32_t gs = cx.g + s;
+        const int buf = gs % TC_NS;
+        const long long tA = clock64();
+        tc::mbar_wait(&cx.bar_full_a[buf], (gs / TC_NS) & 1u);
+        const long long tB = clock64();
+        tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
+        t_wait += tB - tA;
+        t_issue += clock64() - tB;
+      }
+      if (blockIdx.x == 0 && blockIdx.y == 0) { g_tc_acc[2] = t_wait; g_tc_acc[3] = t_issue; }
+    }
+    __syncwarp();
   }
+  cx.g += nst;
   float* gpart = a.ws + a.L.gpart + static_cast<size_t>(sp) * a.plan.n_params;
   float* gp = gpart + ch->w_off[layer];
-  if (nst > 0) {
-    tc_epilogue(cx, npad, [&](int r, int c, const float (&v)[16]) {
-      const int k = m0 + r;
-      if (k < K) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c + i < N) gp[static_cast<size_t>(k) * N + c + i] = v[i];
-      }
-    });
+  tc_stamp(cx.nstamp);
+  if (warp < TC_NPROD / 32 && nst > 0) {
+    tc_wait_acc(cx);
+    tc_stamp(cx.nstamp);
+    tc_epilogue(
+        cx, npad, [&](int, int, float (&)[16]) {},
+        [&](int r, int col, const float4 val) {
+          const int k = m0 + r;
+          if (k < K && col < N) {
+            float* dst = gp + static_cast<size_t>(k) * N + col;
+            if ((N & 3) == 0) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              dst[0] = val.x;
+              if (col + 1 < N) dst[1] = val.y;
+              if (col + 2 < N) dst[2] = val.z;
+              if (col + 3 < N) dst[3] = val.w;
+            }
+          }
+        });
   }
+  cx.done_uses++;
   if (mt == 0) {                                           // bias gradient: fixed-order column sums
-    bred[tid] = bsum;
+    if (tid < TC_NPROD) bred[tid] = bsum;
     __syncthreads();
     if (tid < N && tid < 256) gpart[ch->b_off[layer] + tid] = bred[tid] + bred[tid + 256];
   }

@@ -132,7 +132,8 @@ def time_stages(eng, ts_env_state, lib, _lib, torch):
     net = eng.net
     T, B, mb = eng.T, eng.B, eng.mb
     stages = [("fwd", _lib.STAGE_FWD), ("gae", _lib.STAGE_GAE), ("loss", _lib.STAGE_LOSS),
-              ("bwd", _lib.STAGE_BWD), ("red", _lib.STAGE_RED), ("adam", _lib.STAGE_ADAM)]
+              ("bwd_dx", _lib.STAGE_BWD_DX), ("bwd_dw", _lib.STAGE_BWD_DW), ("red", _lib.STAGE_RED),
+              ("adam", _lib.STAGE_ADAM)]
     tot = {k: 0.0 for k, _ in stages}
     s = _lib.current_stream()
     evs = []
@@ -262,16 +263,22 @@ def run_own(args):
         eng.net.advance_rng(0)
         pa, pc, pa_dx, pc_dx = _p_mm(cfg)
         R, Rv, U = cfg["T"] * eng.mb, (cfg["T"] + 1) * eng.mb, eng.n_updates
-        flops = {"fwd": 2.0 * (pa * R + pc * Rv), "bwd": 2.0 * ((pa_dx + pc_dx) * R + (pa + pc) * R)}
-        dom = max(("fwd", "bwd"), key=lambda k: stage_ms[k])
+        flops = {"fwd": 2.0 * (pa * R + pc * Rv), "bwd_dx": 2.0 * (pa_dx + pc_dx) * R, "bwd_dw": 2.0 * (pa + pc) * R}
+        dom = max(flops, key=lambda k: stage_ms[k])
         ach = flops[dom] * U / (stage_ms[dom] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": {"fwd": "upd_fwd_kernel", "bwd": "upd_bwd_dx_kernel+upd_bwd_dw_kernel"}[dom],
+        mode = int(lib.b200ppo_set_gemm_mode(-1))
+        tc = mode != 0
+        kname = {"fwd": "upd_fwd", "bwd_dx": "upd_bwd_dx", "bwd_dw": "upd_bwd_dw"}[dom] + ("_tc_kernel" if tc else "_kernel")
+        line["roofline"] = {"bound": "tensor", "kernel": kname,
                             "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                             "traffic": None, "peak_source": f"{which} bf16 tensor (sustained)",
-                            "compute_path": "fp32 FFMA (CUDA cores); fp32 parity with the reference forbids bf16 operands",
+                            "compute_path": ("tcgen05.mma kind::tf32, error-compensated 3xTF32 (3 MMAs per algorithmic product, fp32 accumulate in TMEM): "
+                                             "achieved counts ALGORITHMIC flops; tensor-pipe work is 3x that" if mode == 1 else
+                                             ("tcgen05.mma kind::tf32, plain TF32 (not fp32 parity)" if mode == 2 else "fp32 FFMA (CUDA cores)")),
                             "ffma_peak_tflops": ffma_tf, "frac_of_ffma_peak": ach / ffma_tf,
                             "flop_per_launch": flops[dom], "launch_ms": stage_ms[dom] / U,
-                            "stage_ms_per_iteration": stage_ms}
+                            "stage_ms_per_iteration": stage_ms,
+                            "stage_tflops_algorithmic": {k: flops[k] * U / (stage_ms[k] * 1e-3) / 1e12 for k in flops}}
         # CPU baseline: the oracle on a bounded sample of the same workload
         from oracle import env as oenv, nets as onets, ppo as oppo
         Bs = args.ref_envs

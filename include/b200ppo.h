@@ -197,6 +197,9 @@ int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_
 #define B200PPO_STAGE_RED 16
 #define B200PPO_STAGE_ADAM 32
 #define B200PPO_STAGE_ALL 63
+/* finer selection inside BWD (either bit alone runs only that kernel; BWD = both) */
+#define B200PPO_STAGE_BWD_DX 64
+#define B200PPO_STAGE_BWD_DW 128
 
 int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb);
 int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,

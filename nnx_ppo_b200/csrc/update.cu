@@ -1123,18 +1123,20 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     else upd_loss_kernel<<<cdiv(L.R, 128), 128, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
-  if (stages & B200PPO_STAGE_BWD) {
+  if (stages & (B200PPO_STAGE_BWD | B200PPO_STAGE_BWD_DX | B200PPO_STAGE_BWD_DW)) {
+    const bool do_dx = (stages & B200PPO_STAGE_BWD) || (stages & B200PPO_STAGE_BWD_DX);
+    const bool do_dw = (stages & B200PPO_STAGE_BWD) || (stages & B200PPO_STAGE_BWD_DW);
     BwdArgs a;
     a.plan = *plan; a.L = L; a.params = b->params; a.ws = ws;
     if (use_tc) {
-      upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
+      if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
       B200PPO_LAUNCH_CHECK();
-      upd_bwd_dw_tc_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, TC_SMEM, s>>>(a, tc_split);
+      if (do_dw) upd_bwd_dw_tc_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, TC_SMEM, s>>>(a, tc_split);
       B200PPO_LAUNCH_CHECK();
     } else {
-      upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
+      if (do_dx) upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
       B200PPO_LAUNCH_CHECK();
-      upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
+      if (do_dw) upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
       B200PPO_LAUNCH_CHECK();
     }
   }

@@ -167,13 +167,29 @@ __device__ __forceinline__ void tc_issue(TcCtx& cx, const TcIssue& t, int buf, i
 //            I/O with full 256-byte row segments per half-warp (the direct TMEM->global version
 //            wrote 16 B per lane at a 1 KB stride: 9 K cycles of LSU time per 256-wide layer).
 constexpr int TC_EP_PITCH = 68;   // floats
-template <class FA, class FB>
-__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, FB fb) {
+struct TcNoPre {
+  __device__ __forceinline__ float4 operator()(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+// `pre(r, col)` (optional) fetches a per-element global operand of phase B (e.g. z of the previous
+// layer for act'); it is issued BEFORE the TMEM read and the barrier so that its latency is hidden
+// (loading it inside phase B cost one memory round trip per element: 22 K cycles on a 256-wide layer).
+template <class FA, class PRE, class FB>
+__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, PRE pre, FB fb) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = warp & 3, cg = warp >> 2;
   float* ebuf = reinterpret_cast<float*>(cx.smem);
   const int r = sub * 32 + lane;
+  constexpr int PB = TCM * 16 / TC_NPROD;                 // phase-B float4 per thread per step = 4
   for (int c0 = 0; c0 < npad; c0 += 64) {
+    const int ncol4 = ((npad - c0) < 64 ? (npad - c0) : 64) >> 2;        // float4 per row in this step
+    float4 pz[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int idx = tid + j * TC_NPROD;
+      const int row = idx >> 4, f4 = idx & 15;
+      pz[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f4 < ncol4) pz[j] = pre(row, c0 + 4 * f4);
+    }
     const int c = c0 + cg * 16;
     if (c < npad) {
       float v[16];
@@ -184,11 +200,11 @@ __device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, FB fb) {
       for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
-    const int ncol4 = ((npad - c0) < 64 ? (npad - c0) : 64) >> 2;        // float4 per row in this step
-#pragma unroll 4
-    for (int idx = tid; idx < TCM * 16; idx += TC_NPROD) {
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int idx = tid + j * TC_NPROD;
       const int row = idx >> 4, f4 = idx & 15;
-      if (f4 < ncol4) fb(row, c0 + 4 * f4, *reinterpret_cast<const float4*>(ebuf + row * TC_EP_PITCH + 4 * f4));
+      if (f4 < ncol4) fb(row, c0 + 4 * f4, *reinterpret_cast<const float4*>(ebuf + row * TC_EP_PITCH + 4 * f4), pz[j]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
   }
@@ -413,7 +429,8 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
               }
             }
           },
-          [&](int r, int col, const float4 val) {
+          TcNoPre(),
+          [&](int r, int col, const float4 val, const float4) {
             const int row = row0 + r;
             if (row < nrows && col < N) {
               float* dst = Z + static_cast<size_t>(row) * N + col;
@@ -523,17 +540,61 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
     float* dprev = ws + doff[l - 1];
     const int act = ch.act;
     if (Nl <= 4) {
-      // thin layer (value head): dX is a rank-Nl outer product, done element-wise and coalesced
+      // thin layer (value head): dX is a rank-Nl outer product, done element-wise, coalesced, with
+      // all loads of a batch in flight together (a dependent-load loop here cost 80 K cycles)
       if (tid < TC_NPROD) {
         const float* W = P + ch.w_off[l];
-        for (int idx = tid; idx < TCM * Kl; idx += TC_NPROD) {
-          const int rr = idx / Kl, k = idx - rr * Kl;
-          const int row = row0 + rr;
-          if (row < nrows) {
-            float acc = 0.0f;
-            for (int j = 0; j < Nl; ++j) acc = fmaf(dY[static_cast<size_t>(row) * Nl + j], __ldg(W + static_cast<size_t>(k) * Nl + j), acc);
-            const size_t o = static_cast<size_t>(row) * Kl + k;
-            dprev[o] = acc * act_grad(zprev[o], act);
+        if ((Kl & 3) == 0) {
+          const int K4 = Kl >> 2;
+          constexpr int TB = 8;
+          for (int i0 = tid; i0 < TCM * K4; i0 += TC_NPROD * TB) {
+            float4 zz[TB];
+            float dy[TB][4];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) {
+              const int idx = i0 + b * TC_NPROD;
+              const int rr = idx / K4, k4 = idx - rr * K4;
+              const int row = row0 + rr;
+              zz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dy[b][j] = 0.f;
+              if (idx < TCM * K4 && row < nrows) {
+                zz[b] = *reinterpret_cast<const float4*>(zprev + static_cast<size_t>(row) * Kl + 4 * k4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < Nl) dy[b][j] = dY[static_cast<size_t>(row) * Nl + j];
+              }
+            }
+#pragma unroll
+            for (int b = 0; b < TB; ++b) {
+              const int idx = i0 + b * TC_NPROD;
+              const int rr = idx / K4, k4 = idx - rr * K4;
+              const int row = row0 + rr;
+              if (idx < TCM * K4 && row < nrows) {
+                const float zv[4] = {zz[b].x, zz[b].y, zz[b].z, zz[b].w};
+                float g[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float acc = 0.0f;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j < Nl) acc = fmaf(dy[b][j], __ldg(W + static_cast<size_t>(4 * k4 + e) * Nl + j), acc);
+                  g[e] = acc * act_grad(zv[e], act);
+                }
+                *reinterpret_cast<float4*>(dprev + static_cast<size_t>(row) * Kl + 4 * k4) = make_float4(g[0], g[1], g[2], g[3]);
+              }
+            }
+          }
+        } else {
+          for (int idx = tid; idx < TCM * Kl; idx += TC_NPROD) {
+            const int rr = idx / Kl, k = idx - rr * Kl;
+            const int row = row0 + rr;
+            if (row < nrows) {
+              float acc = 0.0f;
+              for (int j = 0; j < Nl; ++j) acc = fmaf(dY[static_cast<size_t>(row) * Nl + j], __ldg(W + static_cast<size_t>(k) * Nl + j), acc);
+              const size_t o = static_cast<size_t>(row) * Kl + k;
+              dprev[o] = acc * act_grad(zprev[o], act);
+            }
           }
         }
       }
@@ -547,14 +608,20 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
     if (warp < TC_NPROD / 32) {
       tc_wait_acc(cx);
       tc_stamp(cx.nstamp);
+      const bool kvec = (Kl & 3) == 0;
       tc_epilogue(
           cx, npad, [&](int, int, float (&)[16]) {},
-          [&](int r, int col, const float4 val) {
+          [&](int r, int col) {
+            const int row = row0 + r;
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kvec && row < nrows && col < Kl) z = *reinterpret_cast<const float4*>(zprev + static_cast<size_t>(row) * Kl + col);
+            return z;
+          },
+          [&](int r, int col, const float4 val, const float4 z) {
             const int row = row0 + r;
             if (row < nrows && col < Kl) {
               const size_t o = static_cast<size_t>(row) * Kl + col;
-              if ((Kl & 3) == 0) {
-                const float4 z = *reinterpret_cast<const float4*>(zprev + o);
+              if (kvec) {
                 float4 g;
                 if (act == B200PPO_ACT_RELU) {
                   g = make_float4(z.x > 0.f ? val.x : 0.f, z.y > 0.f ? val.y : 0.f, z.z > 0.f ? val.z : 0.f,
@@ -748,8 +815,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
     tc_wait_acc(cx);
     tc_stamp(cx.nstamp);
     tc_epilogue(
-        cx, npad, [&](int, int, float (&)[16]) {},
-        [&](int r, int col, const float4 val) {
+        cx, npad, [&](int, int, float (&)[16]) {}, TcNoPre(),
+        [&](int r, int col, const float4 val, const float4) {
           const int k = m0 + r;
           if (k < K && col < N) {
             float* dst = gp + static_cast<size_t>(k) * N + col;

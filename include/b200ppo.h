@@ -212,7 +212,7 @@ int b200ppo_set_gemm_mode(int mode);
 /* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *
  * kernel -> out_host; returns -(1000 + count).                                                   */
 int b200ppo_debug_timestamps(long long* out_host, int32_t max_n);
-int b200ppo_debug_select(int skip_dw);   /* 1: the dW kernel does not overwrite the stamps (keeps dX's) */
+int b200ppo_debug_select(int flags);     /* bit 0: the dW kernel keeps dX's stamps; bits 8..: blockIdx.x of the stamped CTA */
 /* Number of kernels b200ppo_update launches for the given stage mask (for launch accounting).   */
 int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
                                 int32_t mb, int32_t stages);

@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("B200PPO_NVCC_EXTRA", "").split()      # e.g. -DTC_PROBE (clock64 probes)
     objs = []
     procs = []
     for src in SOURCES:

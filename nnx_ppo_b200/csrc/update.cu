@@ -53,7 +53,7 @@ struct TcLayer {
 
 struct Layout {
   int R, Rv, S, n_tiles, rows_per_split;
-  int tc_ok, tc_tiles, tc_S, tc_rows_per_split;
+  int tc_ok, tc_tiles, tc_S, tc_rows_per_split, tc_dw_bulk;
   TcLayer tca[MAXL], tcc[MAXL];
   size_t xhat, adv, gpart, grad;
   size_t za[MAXL], zc[MAXL], da[MAXL], dc[MAXL];
@@ -101,12 +101,14 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
   // tensor-core path: D rows tiled by 128, one row-range split per CTA, <= 1 CTA per SM
   L.tc_ok = 1;
   L.tc_tiles = 0;
+  L.tc_dw_bulk = 1;
   for (int c = 0; c < 2; ++c) {
     const b200ppo_chain& ch = c == 0 ? p.actor : p.critic;
     TcLayer* tl = c == 0 ? L.tca : L.tcc;
     for (int l = 0; l < ch.n_layers; ++l) {
       const int K = ch.dims[l], N = ch.dims[l + 1];
       if (N > 256) L.tc_ok = 0;
+      if (K > 256) L.tc_dw_bulk = 0;                         // dW v2 stages full rows of H (<= 256 wide)
       tl[l].kpad = (K + 31) & ~31;
       tl[l].npad = (N + 15) & ~15;
       tl[l].nred_pad = (N + 31) & ~31;
@@ -129,6 +131,7 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
   const int smax = L.tc_S > S ? L.tc_S : S;
   L.gpart = take(static_cast<size_t>(smax) * p.n_params);
   L.grad = take(p.n_params);
+  take(16 * 256);                                           // slack: dW v2 copies whole 16-row blocks
   L.total_floats = o;
   return L;
 }
@@ -966,6 +969,8 @@ int set_attrs() {
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(upd_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(upd_bwd_dw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW2_SMEM);
+  if (e != cudaSuccess) return static_cast<int>(e);
   g_attr_done = true;
   return 0;
 }
@@ -997,8 +1002,8 @@ extern "C" int b200ppo_debug_timestamps(long long* out_host, int32_t max_n) {
     e = cudaMemcpyFromSymbol(out_host, g_tc_stamp, sizeof(long long) * n);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  if (n + 4 <= max_n) {     // dW probe accumulators appended after the stamps
-    e = cudaMemcpyFromSymbol(out_host + n, g_tc_acc, sizeof(long long) * 4);
+  if (n + 8 <= max_n) {     // probe accumulators (TC_PROBE builds) appended after the stamps
+    e = cudaMemcpyFromSymbol(out_host + n, g_tc_acc, sizeof(long long) * 8);
     if (e != cudaSuccess) return static_cast<int>(e);
   }
   return -1000 - n;   // encodes the count: n = -(rc + 1000)
@@ -1131,7 +1136,10 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     if (use_tc) {
       if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
       B200PPO_LAUNCH_CHECK();
-      if (do_dw) upd_bwd_dw_tc_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, TC_SMEM, s>>>(a, tc_split);
+      if (do_dw) {
+        if (L.tc_dw_bulk) upd_bwd_dw_tc2_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, DW2_SMEM, s>>>(a, tc_split);
+        else upd_bwd_dw_tc_kernel<<<dim3(L.tc_tiles, L.tc_S), TCT, TC_SMEM, s>>>(a, tc_split);
+      }
       B200PPO_LAUNCH_CHECK();
     } else {
       if (do_dx) upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);

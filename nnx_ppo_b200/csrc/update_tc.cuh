@@ -35,11 +35,23 @@ constexpr int TC_NBARS = 3 * TC_NS + 1;
 __device__ long long g_tc_stamp[128];
 __device__ int g_tc_nstamp;
 __device__ int g_tc_stamp_skip_dw;
-__device__ long long g_tc_acc[8];     // dW CTA 0: [0] producer wait_empty, [1] producer work, [2] issuer wait, [3] issuer issue
+__device__ long long g_tc_acc[8];     // scratch for ad-hoc clock64 probes
 __device__ __forceinline__ void tc_stamp(int& n) {
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && n >= 0 && n < 128) g_tc_stamp[n] = clock64();
+  if (threadIdx.x == 0 && n >= 0 && n < 128) g_tc_stamp[n] = clock64();
   ++n;
 }
+
+#ifdef TC_PROBE
+#define TC_PROBE_DECL long long pb_t0 = 0, pb_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const bool pb_on = cx.nstamp >= 0 && (threadIdx.x & 31) == 0;
+#define TC_PROBE_START() do { if (pb_on) pb_t0 = clock64(); } while (0)
+#define TC_PROBE_LAP(i) do { if (pb_on) { const long long t_ = clock64(); pb_acc[i] += t_ - pb_t0; pb_t0 = t_; } } while (0)
+#define TC_PROBE_FLUSH(base, n) do { if (pb_on) for (int i_ = 0; i_ < (n); ++i_) g_tc_acc[(base) + i_] = pb_acc[i_]; } while (0)
+#else
+#define TC_PROBE_DECL
+#define TC_PROBE_START() do { } while (0)
+#define TC_PROBE_LAP(i) do { } while (0)
+#define TC_PROBE_FLUSH(base, n) do { } while (0)
+#endif
 
 struct TcCtx {
   uint8_t* smem;
@@ -50,6 +62,7 @@ struct TcCtx {
   uint32_t tmem_base;
   uint32_t g;            // sequence number of the next stage use (ring position = g % NS)
   uint32_t done_uses;
+  uint32_t b_base;       // byte offset of the B stages (after all A stages)
   int nstamp;
 };
 
@@ -77,13 +90,14 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* 
   cx.tmem_base = *tmem_slot;
   cx.g = 0u;
   cx.done_uses = 0u;
-  cx.nstamp = 0;
+  cx.b_base = TC_NS * 2u * TC_A_BYTES;
+  cx.nstamp = (static_cast<int>(blockIdx.x) == (g_tc_stamp_skip_dw >> 8) && blockIdx.y == 0) ? 0 : -100000;
   tc_stamp(cx.nstamp);
 }
 
 __device__ __forceinline__ void tc_ctx_fini(TcCtx& cx) {
   tc_stamp(cx.nstamp);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && cx.nstamp > 0) g_tc_nstamp = cx.nstamp;
+  if (threadIdx.x == 0 && cx.nstamp > 0) g_tc_nstamp = cx.nstamp;
   tc::tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(cx.tmem_base, TC_MAXN);
@@ -97,7 +111,7 @@ __device__ __forceinline__ TcStage tc_stage(const TcCtx& cx, int buf) {
   // all A stages first (the idle A area doubles as the epilogue transpose buffer), then all B stages
   s.a_hi = cx.smem + buf * 2u * TC_A_BYTES;
   s.a_lo = s.a_hi + TC_A_BYTES;
-  s.b_hi = cx.smem + TC_NS * 2u * TC_A_BYTES + buf * 2u * TC_B_BYTES;
+  s.b_hi = cx.smem + cx.b_base + buf * 2u * TC_B_BYTES;
   s.b_lo = s.b_hi + TC_B_BYTES;
   return s;
 }
@@ -253,23 +267,34 @@ __device__ __forceinline__ void tc_mainloop(TcCtx& cx, const float* __restrict__
       }
       return x;
     };
-    // 4 stages in flight: a 64-wide layer is one memory round trip
-    float4 a0 = load_a(0), a1 = load_a(1), a2 = load_a(2), a3 = load_a(3);
-    for (int s = 0; s < nst; ++s) {
-      const uint32_t gs = g0 + s;
-      const int buf = gs % TC_NS;
-      const TcStage st = tc_stage(cx, buf);
-      tc_wait_empty(cx, buf, gs / TC_NS);
-      float4 hi, lo;
-      tc::split4(act4(a0, act), hi, lo);
-      a0 = a1; a1 = a2; a2 = a3; a3 = load_a(s + 4);
-      *reinterpret_cast<float4*>(st.a_hi + soff) = hi;
-      if (split) *reinterpret_cast<float4*>(st.a_lo + soff) = lo;
-      // 512 per-thread arrives on one mbarrier word serialise (~1-2 K cycles per stage, measured):
-      // every lane fences its own writes, the warp converges, one lane arrives for the warp
-      tc::fence_proxy_async();
-      __syncwarp();
-      if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
+    // 4 stages in flight: a 64-wide layer is one memory round trip.  The loop is unrolled by the
+    // prefetch depth so that every in-flight stage has its own statically named registers: a
+    // rotating `a0 = a1; a1 = a2; ...` makes the register moves wait for the newest load, i.e. one
+    // full memory round trip per stage (found in the ncu source view: the stall sat on the moves).
+    float4 areg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) areg[j] = load_a(j);
+    for (int s0 = 0; s0 < nst; s0 += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int s = s0 + j;
+        if (s < nst) {
+          const uint32_t gs = g0 + s;
+          const int buf = gs % TC_NS;
+          const TcStage st = tc_stage(cx, buf);
+          tc_wait_empty(cx, buf, gs / TC_NS);
+          float4 hi, lo;
+          tc::split4(act4(areg[j], act), hi, lo);
+          areg[j] = load_a(s + 4);
+          *reinterpret_cast<float4*>(st.a_hi + soff) = hi;
+          if (split) *reinterpret_cast<float4*>(st.a_lo + soff) = lo;
+          // 512 per-thread arrives on one mbarrier word serialise (~1-2 K cycles per stage, measured):
+          // every lane fences its own writes, the warp converges, one lane arrives for the warp
+          tc::fence_proxy_async();
+          __syncwarp();
+          if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
+        }
+      }
     }
   } else if (warp == TC_NPROD / 32) {
     // ---------------- MMA issuer ----------------
@@ -546,7 +571,7 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
         const float* W = P + ch.w_off[l];
         if ((Kl & 3) == 0) {
           const int K4 = Kl >> 2;
-          constexpr int TB = 8;
+          constexpr int TB = 4;
           for (int i0 = tid; i0 < TCM * K4; i0 += TC_NPROD * TB) {
             float4 zz[TB];
             float dy[TB][4];
@@ -756,54 +781,51 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
       }
       return x;
     };
-    Regs x0 = load_stage(0), x1 = load_stage(1), x2 = load_stage(2);
-    long long t_wait = 0, t_work = 0;
-    const bool probe = blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
-    for (int s = 0; s < nst; ++s) {
-      const uint32_t gs = cx.g + s;
-      const int buf = gs % TC_NS;
-      const TcStage st = tc_stage(cx, buf);
-      const long long tA = probe ? clock64() : 0;
-      tc_wait_empty(cx, buf, gs / TC_NS);
-      const long long tB = probe ? clock64() : 0;
-      t_wait += tB - tA;
-      float4 hi, lo;
-      tc::split4(act4(x0.a, act_in), hi, lo);               // act(0) == 0 for relu / tanh / swish
-      *reinterpret_cast<float4*>(st.a_hi + aoff) = hi;
-      if (split) *reinterpret_cast<float4*>(st.a_lo + aoff) = lo;
-      if (bstage) {
-        bsum += ((x0.b0.x + x0.b0.y) + (x0.b0.z + x0.b0.w)) + ((x0.b1.x + x0.b1.y) + (x0.b1.z + x0.b1.w));
-        tc::split4(x0.b0, hi, lo);
-        uint32_t o = (2 * bh) * pb + bn * 16;
-        *reinterpret_cast<float4*>(st.b_hi + o) = hi;
-        if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
-        tc::split4(x0.b1, hi, lo);
-        o += pb;
-        *reinterpret_cast<float4*>(st.b_hi + o) = hi;
-        if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
+    // statically named prefetch ring (see tc_mainloop): DW_PF stages of loads in flight
+    constexpr int DW_PF = 4;
+    Regs x[DW_PF];
+#pragma unroll
+    for (int j = 0; j < DW_PF; ++j) x[j] = load_stage(j);
+    for (int s0 = 0; s0 < nst; s0 += DW_PF) {
+#pragma unroll
+      for (int j = 0; j < DW_PF; ++j) {
+        const int s = s0 + j;
+        if (s < nst) {
+          const uint32_t gs = cx.g + s;
+          const int buf = gs % TC_NS;
+          const TcStage st = tc_stage(cx, buf);
+          tc_wait_empty(cx, buf, gs / TC_NS);
+          float4 hi, lo;
+          tc::split4(act4(x[j].a, act_in), hi, lo);             // act(0) == 0 for relu / tanh / swish
+          *reinterpret_cast<float4*>(st.a_hi + aoff) = hi;
+          if (split) *reinterpret_cast<float4*>(st.a_lo + aoff) = lo;
+          if (bstage) {
+            bsum += ((x[j].b0.x + x[j].b0.y) + (x[j].b0.z + x[j].b0.w)) + ((x[j].b1.x + x[j].b1.y) + (x[j].b1.z + x[j].b1.w));
+            tc::split4(x[j].b0, hi, lo);
+            uint32_t o = (2 * bh) * pb + bn * 16;
+            *reinterpret_cast<float4*>(st.b_hi + o) = hi;
+            if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
+            tc::split4(x[j].b1, hi, lo);
+            o += pb;
+            *reinterpret_cast<float4*>(st.b_hi + o) = hi;
+            if (split) *reinterpret_cast<float4*>(st.b_lo + o) = lo;
+          }
+          x[j] = load_stage(s + DW_PF);
+          tc::fence_proxy_async();
+          __syncwarp();
+          if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
+        }
       }
-      x0 = x1; x1 = x2; x2 = load_stage(s + 3);
-      tc::fence_proxy_async();
-      __syncwarp();
-      if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[buf]);
-      if (probe) t_work += clock64() - tB;
     }
-    if (probe) { g_tc_acc[0] = t_wait; g_tc_acc[1] = t_work; }
   } else if (warp == TC_NPROD / 32) {
     if ((tid & 31) == 0) {
-      long long t_wait = 0, t_issue = 0;
       const TcIssue ti = tc_issue_prepare(cx, npad);
       for (int s = 0; s < nst; ++s) {
         const uint32_t gs = cx.g + s;
         const int buf = gs % TC_NS;
-        const long long tA = clock64();
         tc::mbar_wait(&cx.bar_full_a[buf], (gs / TC_NS) & 1u);
-        const long long tB = clock64();
         tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
-        t_wait += tB - tA;
-        t_issue += clock64() - tB;
       }
-      if (blockIdx.x == 0 && blockIdx.y == 0) { g_tc_acc[2] = t_wait; g_tc_acc[3] = t_issue; }
     }
     __syncwarp();
   }
@@ -836,6 +858,247 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
     if (tid < TC_NPROD) bred[tid] = bsum;
     __syncthreads();
     if (tid < N && tid < 256) gpart[ch->b_off[layer] + tid] = bred[tid] + bred[tid + 256];
+  }
+  tc_ctx_fini(cx);
+}
+
+// ------------------------------------------------------------------------------------------
+// BWD dW, v2: the 16-row blocks of both operands are CONTIGUOUS in global memory (row-major
+// [rows][K] / [rows][N]), so one thread streams them raw into a shared-memory ring with
+// cp.async.bulk and the producer warps transpose shared -> shared (conflict-free LDS.32 down the
+// rows, hi/lo split, STS.128 into the UMMA planes).  The v1 kernel gathered the transposed chunks
+// straight from global memory: ~200 instructions per warp and stage, mostly 64-bit address and
+// predicate arithmetic, and the SM's issue slots were the bottleneck (ncu: issue active 49 % of the
+// whole launch, tensor pipe 16 %; profiles/r1_tc_notes.md).
+// Needs K <= 128 or K % 4 == 0 for every layer (bulk copies are 16-byte granular); otherwise the
+// host keeps v1.
+// ------------------------------------------------------------------------------------------
+constexpr int DW2_NS = 3;                                    // UMMA stage ring
+constexpr int DW2_NR = 2;                                    // raw ring
+constexpr int DW2_MAXK = 256;                                // widest H the raw ring holds (full rows)
+constexpr uint32_t DW2_RAW_A = TCK * DW2_MAXK * 4u;          // 16 full rows of H
+constexpr uint32_t DW2_RAW_B = TCK * TC_MAXN * 4u;           // 16 rows x <= 256 columns
+constexpr uint32_t DW2_RAW_BYTES = DW2_RAW_A + DW2_RAW_B;
+constexpr uint32_t DW2_SMEM = DW2_NS * TC_STAGE_BYTES + DW2_NR * DW2_RAW_BYTES;
+
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split) {
+  extern __shared__ __align__(128) uint8_t tsmem[];
+  __shared__ uint64_t bars[TC_NBARS];
+  __shared__ uint64_t rbar[2 * DW2_NR];                      // [0..NR) raw full, [NR..2NR) raw empty
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bred[2][TC_NPROD];
+  int item = blockIdx.x;
+  const b200ppo_chain* ch = &a.plan.actor;
+  const size_t* zoff = a.L.za;
+  const size_t* doff = a.L.da;
+  int layer = -1, mt = 0;
+  for (int c = 0; c < 2 && layer < 0; ++c) {
+    ch = c == 0 ? &a.plan.actor : &a.plan.critic;
+    zoff = c == 0 ? a.L.za : a.L.zc;
+    doff = c == 0 ? a.L.da : a.L.dc;
+    for (int l = 0; l < ch->n_layers; ++l) {
+      const int nm = (ch->dims[l] + TCM - 1) / TCM;
+      if (item < nm) { layer = l; mt = item; break; }
+      item -= nm;
+    }
+  }
+  if (layer < 0) return;                                   // uniform per CTA
+  if (threadIdx.x == 64) {
+#pragma unroll
+    for (int i = 0; i < DW2_NR; ++i) {
+      tc::mbar_init(&rbar[i], 1);
+      tc::mbar_init(&rbar[DW2_NR + i], TC_NPROD / 32);
+    }
+    tc::mbar_init_fence();
+  }
+  TcCtx cx;
+  tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  cx.b_base = DW2_NS * 2u * TC_A_BYTES;
+  if (g_tc_stamp_skip_dw & 1) cx.nstamp = -100000;
+  const int K = ch->dims[layer], N = ch->dims[layer + 1];
+  const int npad = (N + 15) & ~15;
+  const int m0 = mt * TCM;
+  const int kw = (K - m0) < TCM ? (K - m0) : TCM;          // columns of H this CTA owns
+  const float* H = layer == 0 ? a.ws + a.L.xhat : a.ws + zoff[layer - 1];
+  const int act_in = layer == 0 ? B200PPO_ACT_NONE : ch->act;
+  const float* D = a.ws + doff[layer];
+  const int sp = blockIdx.y;
+  const int r_begin = sp * a.L.tc_rows_per_split;
+  int r_end = r_begin + a.L.tc_rows_per_split;
+  if (r_end > a.L.R) r_end = a.L.R;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
+  const int nst = r_end > r_begin ? (r_end - r_begin + TCK - 1) / TCK : 0;
+  uint8_t* raw = tsmem + DW2_NS * TC_STAGE_BYTES;
+  uint64_t* raw_full = rbar;
+  uint64_t* raw_empty = rbar + DW2_NR;
+  float bsum0 = 0.0f, bsum1 = 0.0f;
+  const bool spin = (g_tc_stamp_skip_dw & 2) != 0;
+  auto wait = [&](uint64_t* bar, uint32_t par) {
+    if (spin) tc::mbar_wait_spin(bar, par);
+    else tc::mbar_wait(bar, par);
+  };
+  if (warp < TC_NPROD / 32) {
+    // A: thread -> (m = tid & 127, plane q = tid >> 7): rows 4q..4q+3 of column m
+    const int am = tid & (TCM - 1), aq = tid >> 7;
+    const bool av = am < kw;
+    const uint32_t a_src = static_cast<uint32_t>(((4 * aq) * K + m0 + (av ? am : 0)) * 4);
+    const uint32_t a_dst = aq * pa + am * 16;
+    const uint32_t a_rs = static_cast<uint32_t>(K) * 4u;
+    // B: chunk ids tid and tid + 512 -> (plane p = id / npad, column = id % npad)
+    const int c0 = tid, c1 = tid + TC_NPROD;
+    const bool bs0 = c0 < 4 * npad, bs1 = c1 < 4 * npad;
+    const int p0 = c0 / npad, col0 = c0 - p0 * npad;
+    const int p1 = c1 / npad, col1 = c1 - p1 * npad;
+    const bool bv0 = bs0 && col0 < N, bv1 = bs1 && col1 < N;
+    const uint32_t b_rs = static_cast<uint32_t>(N) * 4u;
+    const uint32_t b_src0 = DW2_RAW_A + static_cast<uint32_t>(((4 * p0) * N + (bv0 ? col0 : 0)) * 4);
+    const uint32_t b_src1 = DW2_RAW_A + static_cast<uint32_t>(((4 * p1) * N + (bv1 ? col1 : 0)) * 4);
+    const uint32_t b_dst0 = p0 * pb + col0 * 16, b_dst1 = p1 * pb + col1 * 16;
+    int rslot = 0, uslot = 0;
+    uint32_t rpar = 0u, upar = 1u;                          // upar: parity to wait on `empty` (first lap skipped)
+    bool ufirst = true;
+    TC_PROBE_DECL
+    for (int s = 0; s < nst; ++s) {
+      const uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
+      TC_PROBE_START();
+      wait(&raw_full[rslot], rpar);
+      TC_PROBE_LAP(0);
+      float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb0 = xa, xb1 = xa;
+      if (av) {
+        const uint8_t* q = rw + a_src;
+        xa = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + a_rs),
+                         *reinterpret_cast<const float*>(q + 2 * a_rs), *reinterpret_cast<const float*>(q + 3 * a_rs));
+      }
+      if (bv0) {
+        const uint8_t* q = rw + b_src0;
+        xb0 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
+                          *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
+      }
+      if (bv1) {
+        const uint8_t* q = rw + b_src1;
+        xb1 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
+                          *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
+      }
+      const int rs = r_begin + s * TCK;
+      if (rs + TCK > r_end) {                               // ragged last block: rows >= r_end are garbage
+        const int ra = rs + 4 * aq, rb0 = rs + 4 * p0, rb1 = rs + 4 * p1;
+        if (ra + 0 >= r_end) xa.x = 0.f;
+        if (ra + 1 >= r_end) xa.y = 0.f;
+        if (ra + 2 >= r_end) xa.z = 0.f;
+        if (ra + 3 >= r_end) xa.w = 0.f;
+        if (rb0 + 0 >= r_end) xb0.x = 0.f;
+        if (rb0 + 1 >= r_end) xb0.y = 0.f;
+        if (rb0 + 2 >= r_end) xb0.z = 0.f;
+        if (rb0 + 3 >= r_end) xb0.w = 0.f;
+        if (rb1 + 0 >= r_end) xb1.x = 0.f;
+        if (rb1 + 1 >= r_end) xb1.y = 0.f;
+        if (rb1 + 2 >= r_end) xb1.z = 0.f;
+        if (rb1 + 3 >= r_end) xb1.w = 0.f;
+      }
+      TC_PROBE_LAP(1);
+      if (!ufirst) wait(&cx.bar_empty[uslot], upar);
+      TC_PROBE_LAP(2);
+      uint8_t* ua = cx.smem + uslot * 2u * TC_A_BYTES;
+      uint8_t* ub = cx.smem + cx.b_base + uslot * 2u * TC_B_BYTES;
+      float4 hi, lo;
+      tc::split4_fast(av ? act4(xa, act_in) : xa, hi, lo);
+      *reinterpret_cast<float4*>(ua + a_dst) = hi;
+      if (split) *reinterpret_cast<float4*>(ua + TC_A_BYTES + a_dst) = lo;
+      if (bs0) {
+        bsum0 += (xb0.x + xb0.y) + (xb0.z + xb0.w);
+        tc::split4_fast(xb0, hi, lo);
+        *reinterpret_cast<float4*>(ub + b_dst0) = hi;
+        if (split) *reinterpret_cast<float4*>(ub + TC_B_BYTES + b_dst0) = lo;
+      }
+      if (bs1) {
+        bsum1 += (xb1.x + xb1.y) + (xb1.z + xb1.w);
+        tc::split4_fast(xb1, hi, lo);
+        *reinterpret_cast<float4*>(ub + b_dst1) = hi;
+        if (split) *reinterpret_cast<float4*>(ub + TC_B_BYTES + b_dst1) = lo;
+      }
+      TC_PROBE_LAP(3);
+      tc::fence_proxy_async();
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        tc::mbar_arrive(&cx.bar_full_a[uslot]);
+        tc::mbar_arrive(&raw_empty[rslot]);
+      }
+      TC_PROBE_LAP(4);
+      if (++rslot == DW2_NR) { rslot = 0; rpar ^= 1u; }
+      if (++uslot == DW2_NS) { uslot = 0; upar ^= 1u; ufirst = false; }
+    }
+    if (tid == 0) TC_PROBE_FLUSH(0, 5);
+  } else if (warp == TC_NPROD / 32) {
+    if ((tid & 31) == 0) {
+      const TcIssue ti = tc_issue_prepare(cx, npad);
+      int uslot = 0;
+      uint32_t par = 0u;
+      TC_PROBE_DECL
+      for (int s = 0; s < nst; ++s) {
+        TC_PROBE_START();
+        wait(&cx.bar_full_a[uslot], par);
+        TC_PROBE_LAP(0);
+        tc_issue(cx, ti, uslot, split, s == 0, s == nst - 1);
+        TC_PROBE_LAP(1);
+        if (++uslot == DW2_NS) { uslot = 0; par ^= 1u; }
+      }
+      TC_PROBE_FLUSH(5, 2);
+    }
+    __syncwarp();
+  } else {
+    // raw-block streamer: 16 full rows of H and of D per stage, one bulk copy each (many small
+    // copies are slow: ~100 cycles apiece through the copy engine, measured with 512-byte segments)
+    if ((tid & 31) == 0) {
+      const uint32_t bytes_a = static_cast<uint32_t>(TCK) * K * 4u, bytes_b = static_cast<uint32_t>(TCK) * N * 4u;
+      int rslot = 0;
+      uint32_t epar = 1u;
+      bool first = true;
+      for (int s = 0; s < nst; ++s) {
+        uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
+        const size_t rs = static_cast<size_t>(r_begin) + static_cast<size_t>(s) * TCK;
+        if (!first) wait(&raw_empty[rslot], epar);
+        tc::mbar_arrive_expect_tx(&raw_full[rslot], bytes_a + bytes_b);
+        tc::bulk_g2s(rw, H + rs * K, bytes_a, &raw_full[rslot]);
+        tc::bulk_g2s(rw + DW2_RAW_A, D + rs * N, bytes_b, &raw_full[rslot]);
+        if (++rslot == DW2_NR) { rslot = 0; epar ^= 1u; first = false; }
+      }
+    }
+    __syncwarp();
+  }
+  cx.g += nst;
+  float* gpart = a.ws + a.L.gpart + static_cast<size_t>(sp) * a.plan.n_params;
+  float* gp = gpart + ch->w_off[layer];
+  tc_stamp(cx.nstamp);
+  if (warp < TC_NPROD / 32 && nst > 0) {
+    tc_wait_acc(cx);
+    tc_stamp(cx.nstamp);
+    tc_epilogue(
+        cx, npad, [&](int, int, float (&)[16]) {}, TcNoPre(),
+        [&](int r, int col, const float4 val, const float4) {
+          const int k = m0 + r;
+          if (k < K && col < N) {
+            float* dst = gp + static_cast<size_t>(k) * N + col;
+            if ((N & 3) == 0) {
+              *reinterpret_cast<float4*>(dst) = val;
+            } else {
+              dst[0] = val.x;
+              if (col + 1 < N) dst[1] = val.y;
+              if (col + 2 < N) dst[2] = val.z;
+              if (col + 3 < N) dst[3] = val.w;
+            }
+          }
+        });
+  }
+  cx.done_uses++;
+  if (mt == 0) {                                           // bias gradient: fixed-order column sums
+    if (tid < TC_NPROD) { bred[0][tid] = bsum0; bred[1][tid] = bsum1; }
+    __syncthreads();
+    if (tid < N && tid < TC_MAXN) {
+      float acc = 0.0f;
+      for (int cc = tid; cc < 4 * npad; cc += npad) acc += bred[cc / TC_NPROD][cc % TC_NPROD];
+      gpart[ch->b_off[layer] + tid] = acc;
+    }
   }
   tc_ctx_fini(cx);
 }

@@ -20,7 +20,7 @@ def stamps(mask, name):
     e1.record(); torch.cuda.synchronize()
     rc = lib.b200ppo_debug_timestamps(buf, 128); n = -(rc + 1000)
     t = np.array(buf[:n], dtype=np.int64); d = np.diff(t)
-    print(name, 'us', round(e0.elapsed_time(e1)*1e3,1), 'n', n, 'total cycles', t[-1]-t[0]); print(d.tolist()); print('  dW probe [prod wait_empty, prod work, issuer wait, issuer issue]:', list(buf[n:n+4]))
+    print(name, 'us', round(e0.elapsed_time(e1)*1e3,1), 'n', n, 'total cycles', t[-1]-t[0]); print(d.tolist()); print('  probes:', list(buf[n:n+8]))
 for _ in range(2): stamps(_lib.STAGE_FWD, 'fwd')
 lib.b200ppo_set_gemm_mode(2)
 stamps(_lib.STAGE_FWD, 'fwd-tf32x1')
@@ -31,4 +31,8 @@ stamps(_lib.STAGE_BWD, 'bwd(dw last)')
 for flag, nm in ((1,'dx'),):
     lib.b200ppo_debug_select(flag)
     stamps(_lib.STAGE_BWD, 'bwd(dw) '+nm)
+for spin in (0,):
+  for bx in (0, 5, 6, 8):
+    lib.b200ppo_debug_select((bx << 8) | spin)
+    stamps(_lib.STAGE_BWD, 'bwd(dw item %d spin %d)' % (bx, spin))
 lib.b200ppo_debug_select(0)

@@ -213,7 +213,13 @@ __device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, PRE pre,
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
     }
+#ifdef TC_PROBE
+    tc_stamp(cx.nstamp);
+#endif
     asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
+#ifdef TC_PROBE
+    tc_stamp(cx.nstamp);
+#endif
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int idx = tid + j * TC_NPROD;
@@ -284,7 +290,7 @@ __device__ __forceinline__ void tc_mainloop(TcCtx& cx, const float* __restrict__
           const TcStage st = tc_stage(cx, buf);
           tc_wait_empty(cx, buf, gs / TC_NS);
           float4 hi, lo;
-          tc::split4(act4(areg[j], act), hi, lo);
+          tc::split4_fast(act4(areg[j], act), hi, lo);
           areg[j] = load_a(s + 4);
           *reinterpret_cast<float4*>(st.a_hi + soff) = hi;
           if (split) *reinterpret_cast<float4*>(st.a_lo + soff) = lo;
@@ -392,8 +398,8 @@ __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
 // FWD (tensor cores)
 // ------------------------------------------------------------------------------------------
 struct TcFwdSmem {
-  float bias[TC_MAXN];
-  float thin_w[TC_MAXN * 4];          // weights of a fused thin (<= 4 outputs) last layer
+  __align__(16) float bias[TC_MAXN];
+  __align__(16) float thin_w[TC_MAXN * 4];   // weights of a fused thin (<= 4 outputs) last layer
   __align__(16) float thin_part[4 * TCM * 4];   // [column group][row][output] partial dots
 };
 
@@ -433,23 +439,45 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
       asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");       // sm.bias / sm.thin_w visible
       tc_wait_acc(cx);
       tc_stamp(cx.nstamp);                                               // accumulator complete
-      float tp[4] = {0.f, 0.f, 0.f, 0.f};
+      float tp0 = 0.f, tp1 = 0.f, tp2 = 0.f, tp3 = 0.f;    // scalars: an array here ends up in local memory
       const int act = ch.act;
       tc_epilogue(
           cx, npad,
           [&](int r, int c, float (&v)[16]) {
+            {
+              const float4* b4 = reinterpret_cast<const float4*>(sm.bias + c);     // c is a multiple of 16
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += sm.bias[c + i];
+              for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              }
+            }
             if (thin) {
+              if (NT == 1 && c + 16 <= N && (act == B200PPO_ACT_RELU || act == B200PPO_ACT_NONE)) {
+                // branch-free common case (one output, relu / identity): the per-element version
+                // below compiles to a branch + dependent LDS -> FFMA per element (~220 cycles each)
+                const float4* w4 = reinterpret_cast<const float4*>(sm.thin_w + c);
+                const float4 w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+                const float ww[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                                      w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (c + i < N) {
-                  const float h = act_fwd(v[i], act);
-                  const float* w = sm.thin_w + (c + i) * NT;
-                  tp[0] = fmaf(h, w[0], tp[0]);           // fixed indices: tp[] stays in registers
-                  if (NT > 1) tp[1] = fmaf(h, w[1], tp[1]);
-                  if (NT > 2) tp[2] = fmaf(h, w[2], tp[2]);
-                  if (NT > 3) tp[3] = fmaf(h, w[3], tp[3]);
+                for (int i = 0; i < 16; ++i) {
+                  const float h = act == B200PPO_ACT_RELU ? fmaxf(v[i], 0.0f) : v[i];
+                  s4[i & 3] = fmaf(h, ww[i], s4[i & 3]);
+                }
+                tp0 += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  if (c + i < N) {
+                    const float h = act_fwd(v[i], act);
+                    const float* w = sm.thin_w + (c + i) * NT;
+                    tp0 = fmaf(h, w[0], tp0);
+                    if (NT > 1) tp1 = fmaf(h, w[1], tp1);
+                    if (NT > 2) tp2 = fmaf(h, w[2], tp2);
+                    if (NT > 3) tp3 = fmaf(h, w[3], tp3);
+                  }
                 }
               }
             }
@@ -472,7 +500,7 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
       tc_stamp(cx.nstamp);                                               // epilogue body done
       if (thin) {
         const int r = (warp & 3) * 32 + (tid & 31), cg = warp >> 2;
-        *reinterpret_cast<float4*>(&sm.thin_part[(cg * TCM + r) * 4]) = make_float4(tp[0], tp[1], tp[2], tp[3]);
+        *reinterpret_cast<float4*>(&sm.thin_part[(cg * TCM + r) * 4]) = make_float4(tp0, tp1, tp2, tp3);
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
         const float* bt = P + ch.b_off[L - 1];
         float* Zt = ws + zoff[L - 1];
@@ -955,80 +983,88 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     const uint32_t b_src0 = DW2_RAW_A + static_cast<uint32_t>(((4 * p0) * N + (bv0 ? col0 : 0)) * 4);
     const uint32_t b_src1 = DW2_RAW_A + static_cast<uint32_t>(((4 * p1) * N + (bv1 ? col1 : 0)) * 4);
     const uint32_t b_dst0 = p0 * pb + col0 * 16, b_dst1 = p1 * pb + col1 * 16;
-    int rslot = 0, uslot = 0;
-    uint32_t rpar = 0u, upar = 1u;                          // upar: parity to wait on `empty` (first lap skipped)
+    static_assert(DW2_NR == 2, "raw slot / parity below are derived from the stage number");
+    int uslot = 0;
+    uint32_t upar = 1u;                                     // parity to wait on `empty` (first lap skipped)
     bool ufirst = true;
-    TC_PROBE_DECL
-    for (int s = 0; s < nst; ++s) {
+    struct Raw { float4 a, b0, b1; };
+    // shared -> registers for stage s, then hand the raw slot straight back to the streamer
+    auto ld = [&](int s, Raw& x) {
+      const int rslot = s & 1;
       const uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
-      TC_PROBE_START();
-      wait(&raw_full[rslot], rpar);
-      TC_PROBE_LAP(0);
-      float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb0 = xa, xb1 = xa;
+      wait(&raw_full[rslot], static_cast<uint32_t>(s >> 1) & 1u);
+      x.a = x.b0 = x.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (av) {
         const uint8_t* q = rw + a_src;
-        xa = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + a_rs),
-                         *reinterpret_cast<const float*>(q + 2 * a_rs), *reinterpret_cast<const float*>(q + 3 * a_rs));
+        x.a = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + a_rs),
+                          *reinterpret_cast<const float*>(q + 2 * a_rs), *reinterpret_cast<const float*>(q + 3 * a_rs));
       }
       if (bv0) {
         const uint8_t* q = rw + b_src0;
-        xb0 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
-                          *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
+        x.b0 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
+                           *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
       }
       if (bv1) {
         const uint8_t* q = rw + b_src1;
-        xb1 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
-                          *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
+        x.b1 = make_float4(*reinterpret_cast<const float*>(q), *reinterpret_cast<const float*>(q + b_rs),
+                           *reinterpret_cast<const float*>(q + 2 * b_rs), *reinterpret_cast<const float*>(q + 3 * b_rs));
       }
       const int rs = r_begin + s * TCK;
       if (rs + TCK > r_end) {                               // ragged last block: rows >= r_end are garbage
         const int ra = rs + 4 * aq, rb0 = rs + 4 * p0, rb1 = rs + 4 * p1;
-        if (ra + 0 >= r_end) xa.x = 0.f;
-        if (ra + 1 >= r_end) xa.y = 0.f;
-        if (ra + 2 >= r_end) xa.z = 0.f;
-        if (ra + 3 >= r_end) xa.w = 0.f;
-        if (rb0 + 0 >= r_end) xb0.x = 0.f;
-        if (rb0 + 1 >= r_end) xb0.y = 0.f;
-        if (rb0 + 2 >= r_end) xb0.z = 0.f;
-        if (rb0 + 3 >= r_end) xb0.w = 0.f;
-        if (rb1 + 0 >= r_end) xb1.x = 0.f;
-        if (rb1 + 1 >= r_end) xb1.y = 0.f;
-        if (rb1 + 2 >= r_end) xb1.z = 0.f;
-        if (rb1 + 3 >= r_end) xb1.w = 0.f;
+        if (ra + 0 >= r_end) x.a.x = 0.f;
+        if (ra + 1 >= r_end) x.a.y = 0.f;
+        if (ra + 2 >= r_end) x.a.z = 0.f;
+        if (ra + 3 >= r_end) x.a.w = 0.f;
+        if (rb0 + 0 >= r_end) x.b0.x = 0.f;
+        if (rb0 + 1 >= r_end) x.b0.y = 0.f;
+        if (rb0 + 2 >= r_end) x.b0.z = 0.f;
+        if (rb0 + 3 >= r_end) x.b0.w = 0.f;
+        if (rb1 + 0 >= r_end) x.b1.x = 0.f;
+        if (rb1 + 1 >= r_end) x.b1.y = 0.f;
+        if (rb1 + 2 >= r_end) x.b1.z = 0.f;
+        if (rb1 + 3 >= r_end) x.b1.w = 0.f;
       }
-      TC_PROBE_LAP(1);
+      __syncwarp();
+      if ((tid & 31) == 0) tc::mbar_arrive(&raw_empty[rslot]);   // release: ordered after the reads above
+    };
+    // registers -> activation, hi/lo split -> UMMA planes of the next ring slot
+    auto proc = [&](const Raw& x) {
       if (!ufirst) wait(&cx.bar_empty[uslot], upar);
-      TC_PROBE_LAP(2);
       uint8_t* ua = cx.smem + uslot * 2u * TC_A_BYTES;
       uint8_t* ub = cx.smem + cx.b_base + uslot * 2u * TC_B_BYTES;
       float4 hi, lo;
-      tc::split4_fast(av ? act4(xa, act_in) : xa, hi, lo);
+      tc::split4_fast(av ? act4(x.a, act_in) : x.a, hi, lo);
       *reinterpret_cast<float4*>(ua + a_dst) = hi;
       if (split) *reinterpret_cast<float4*>(ua + TC_A_BYTES + a_dst) = lo;
       if (bs0) {
-        bsum0 += (xb0.x + xb0.y) + (xb0.z + xb0.w);
-        tc::split4_fast(xb0, hi, lo);
+        bsum0 += (x.b0.x + x.b0.y) + (x.b0.z + x.b0.w);
+        tc::split4_fast(x.b0, hi, lo);
         *reinterpret_cast<float4*>(ub + b_dst0) = hi;
         if (split) *reinterpret_cast<float4*>(ub + TC_B_BYTES + b_dst0) = lo;
       }
       if (bs1) {
-        bsum1 += (xb1.x + xb1.y) + (xb1.z + xb1.w);
-        tc::split4_fast(xb1, hi, lo);
+        bsum1 += (x.b1.x + x.b1.y) + (x.b1.z + x.b1.w);
+        tc::split4_fast(x.b1, hi, lo);
         *reinterpret_cast<float4*>(ub + b_dst1) = hi;
         if (split) *reinterpret_cast<float4*>(ub + TC_B_BYTES + b_dst1) = lo;
       }
-      TC_PROBE_LAP(3);
       tc::fence_proxy_async();
       __syncwarp();
-      if ((tid & 31) == 0) {
-        tc::mbar_arrive(&cx.bar_full_a[uslot]);
-        tc::mbar_arrive(&raw_empty[rslot]);
-      }
-      TC_PROBE_LAP(4);
-      if (++rslot == DW2_NR) { rslot = 0; rpar ^= 1u; }
+      if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[uslot]);
       if (++uslot == DW2_NS) { uslot = 0; upar ^= 1u; ufirst = false; }
+    };
+    // software pipeline: the shared-memory reads of stage s+1 are in flight while stage s is split
+    Raw xA, xB;
+    if (nst > 0) ld(0, xA);
+    for (int s = 0; s < nst; s += 2) {
+      if (s + 1 < nst) ld(s + 1, xB);
+      proc(xA);
+      if (s + 1 < nst) {
+        if (s + 2 < nst) ld(s + 2, xA);
+        proc(xB);
+      }
     }
-    if (tid == 0) TC_PROBE_FLUSH(0, 5);
   } else if (warp == TC_NPROD / 32) {
     if ((tid & 31) == 0) {
       const TcIssue ti = tc_issue_prepare(cx, npad);

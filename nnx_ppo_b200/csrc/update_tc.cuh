@@ -61,14 +61,20 @@ struct TcCtx {
   uint64_t* bar_done;
   uint32_t tmem_base;
   uint32_t g;            // sequence number of the next stage use (ring position = g % NS)
-  uint32_t done_uses;
+  uint32_t done_uses;    // GEMMs finished so far (selects the bar_done phase and the TMEM half)
   uint32_t b_base;       // byte offset of the B stages (after all A stages)
+  uint32_t b_half;       // bytes from the hi planes of a B stage to its lo planes
+  uint32_t ebuf_off;     // byte offset of the epilogue transpose buffer
+  uint32_t tmem_cols;    // allocated TMEM columns (2 x TC_MAXN: consecutive GEMMs ping-pong)
+  uint32_t acc_col;      // accumulator column offset of the current GEMM
+  bool chain_ok;         // the epilogue buffer is outside the ring: an epilogue may feed the next GEMM's A stages
   int nstamp;
 };
 
-__device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot) {
+__device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot,
+                                            uint32_t tmem_cols = TC_MAXN) {
   const int warp = threadIdx.x >> 5;
-  if (warp == 0) tc::tmem_alloc(tmem_slot, TC_MAXN);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
   if (threadIdx.x == 32) {
 #pragma unroll
     for (int i = 0; i < TC_NS; ++i) {
@@ -91,6 +97,11 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* 
   cx.g = 0u;
   cx.done_uses = 0u;
   cx.b_base = TC_NS * 2u * TC_A_BYTES;
+  cx.b_half = TC_B_BYTES;
+  cx.ebuf_off = 0u;
+  cx.tmem_cols = tmem_cols;
+  cx.acc_col = 0u;
+  cx.chain_ok = false;
   cx.nstamp = (static_cast<int>(blockIdx.x) == (g_tc_stamp_skip_dw >> 8) && blockIdx.y == 0) ? 0 : -100000;
   tc_stamp(cx.nstamp);
 }
@@ -100,7 +111,7 @@ __device__ __forceinline__ void tc_ctx_fini(TcCtx& cx) {
   if (threadIdx.x == 0 && cx.nstamp > 0) g_tc_nstamp = cx.nstamp;
   tc::tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(cx.tmem_base, TC_MAXN);
+  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(cx.tmem_base, cx.tmem_cols);
 }
 
 struct TcStage {
@@ -111,8 +122,8 @@ __device__ __forceinline__ TcStage tc_stage(const TcCtx& cx, int buf) {
   // all A stages first (the idle A area doubles as the epilogue transpose buffer), then all B stages
   s.a_hi = cx.smem + buf * 2u * TC_A_BYTES;
   s.a_lo = s.a_hi + TC_A_BYTES;
-  s.b_hi = cx.smem + cx.b_base + buf * 2u * TC_B_BYTES;
-  s.b_lo = s.b_hi + TC_B_BYTES;
+  s.b_hi = cx.smem + cx.b_base + buf * 2u * cx.b_half;
+  s.b_lo = s.b_hi + cx.b_half;
   return s;
 }
 
@@ -131,6 +142,7 @@ struct TcIssue {
   uint32_t a_hiw, b_hiw;        // constant high words (SBO, version)
   uint32_t a_kstep, b_kstep;    // low-word increments per k-step
   uint32_t b_half;              // low-word increment from the hi half to the lo half of B
+  uint32_t b_slot;              // low-word increment per ring slot of B
   uint32_t idesc;
 };
 __device__ __forceinline__ TcIssue tc_issue_prepare(const TcCtx& cx, int npad) {
@@ -143,34 +155,43 @@ __device__ __forceinline__ TcIssue tc_issue_prepare(const TcCtx& cx, int npad) {
   t.b_lo0 = static_cast<uint32_t>(db); t.b_hiw = static_cast<uint32_t>(db >> 32);
   t.a_kstep = (2u * pa) >> 4;
   t.b_kstep = (2u * pb) >> 4;
-  t.b_half = TC_B_BYTES >> 4;
+  t.b_half = cx.b_half >> 4;
+  t.b_slot = (2u * cx.b_half) >> 4;
   t.idesc = tc::make_idesc_tf32(TCM, npad);
   return t;
 }
 __device__ __forceinline__ uint64_t tc_desc(uint32_t hiw, uint32_t low) {
   return (static_cast<uint64_t>(hiw) << 32) | low;
 }
+// Called by the WHOLE (converged) issuer warp: every operand is warp-uniform, so the descriptors
+// live in uniform registers and one elected lane issues.  (Issued from inside an `if (lane == 0)`
+// region the compiler wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop: ~10 dependent
+// instructions per MMA, ~600 cycles per 16-k stage.)
 __device__ __forceinline__ void tc_issue(TcCtx& cx, const TcIssue& t, int buf, int split, bool first, bool last) {
   const uint32_t a0 = t.a_lo0 + static_cast<uint32_t>(buf) * ((2u * TC_A_BYTES) >> 4);
-  const uint32_t b0 = t.b_lo0 + static_cast<uint32_t>(buf) * ((2u * TC_B_BYTES) >> 4);
+  const uint32_t b0 = t.b_lo0 + static_cast<uint32_t>(buf) * t.b_slot;
+  const uint32_t dcol = cx.tmem_base + cx.acc_col;
   tc::tc_fence_after();
+  if (tc::elect_one()) {
 #pragma unroll
-  for (int j = 0; j < TCK / 8; ++j) {
-    const uint64_t ah = tc_desc(t.a_hiw, a0 + j * t.a_kstep);
-    const uint64_t bh = tc_desc(t.b_hiw, b0 + j * t.b_kstep);
-    const uint32_t acc0 = (!first || j > 0) ? 1u : 0u;
-    if (split) {
-      const uint64_t al = tc_desc(t.a_hiw, a0 + j * t.a_kstep + (TC_A_BYTES >> 4));
-      const uint64_t bl = tc_desc(t.b_hiw, b0 + j * t.b_kstep + t.b_half);
-      tc::mma_tf32(cx.tmem_base, al, bh, t.idesc, acc0);
-      tc::mma_tf32(cx.tmem_base, ah, bl, t.idesc, 1u);
-      tc::mma_tf32(cx.tmem_base, ah, bh, t.idesc, 1u);
-    } else {
-      tc::mma_tf32(cx.tmem_base, ah, bh, t.idesc, acc0);
+    for (int j = 0; j < TCK / 8; ++j) {
+      const uint64_t ah = tc_desc(t.a_hiw, a0 + j * t.a_kstep);
+      const uint64_t bh = tc_desc(t.b_hiw, b0 + j * t.b_kstep);
+      const uint32_t acc0 = (!first || j > 0) ? 1u : 0u;
+      if (split) {
+        const uint64_t al = tc_desc(t.a_hiw, a0 + j * t.a_kstep + (TC_A_BYTES >> 4));
+        const uint64_t bl = tc_desc(t.b_hiw, b0 + j * t.b_kstep + t.b_half);
+        tc::mma_tf32(dcol, al, bh, t.idesc, acc0);
+        tc::mma_tf32(dcol, ah, bl, t.idesc, 1u);
+        tc::mma_tf32(dcol, ah, bh, t.idesc, 1u);
+      } else {
+        tc::mma_tf32(dcol, ah, bh, t.idesc, acc0);
+      }
     }
+    tc::commit(&cx.bar_empty[buf]);
+    if (last) tc::commit(cx.bar_done);
   }
-  tc::commit(&cx.bar_empty[buf]);
-  if (last) tc::commit(cx.bar_done);
+  __syncwarp();
 }
 
 // Epilogue of the producer warps, in steps of 64 accumulator columns:
@@ -187,13 +208,31 @@ struct TcNoPre {
 // `pre(r, col)` (optional) fetches a per-element global operand of phase B (e.g. z of the previous
 // layer for act'); it is issued BEFORE the TMEM read and the barrier so that its latency is hidden
 // (loading it inside phase B cost one memory round trip per element: 22 K cycles on a 256-wide layer).
-template <class FA, class PRE, class FB>
-__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, PRE pre, FB fb) {
+// Chained output (CHAIN): phase A also converts the next GEMM's A operand (`h` from `fa`: act(z)
+// in the forward chain, dpre in the backward chain) to hi / lo planes and stores it straight into
+// the ring stages of the NEXT GEMM (sequence numbers g_next ..): a phase-A thread owns one row and
+// 16 consecutive columns = the four 16-byte chunks of one 16-k stage, and consecutive lanes own
+// consecutive rows (conflict-free).  The next GEMM therefore starts right after phase A, with no
+// global-memory round trip and no producer pass, while phase B streams this layer's result out.
+struct TcChainOut {
+  uint32_t g_next;       // sequence number of the next GEMM's first stage
+  int nst_next;          // its number of 16-k stages
+  int split;
+};
+__device__ __forceinline__ void tc_wait_acc(TcCtx& cx);
+// CHAIN = 0: plain epilogue.  CHAIN = 1: chained operand h[16] produced by `fa` in phase A (forward
+// chain).  CHAIN = 2: chained operand returned by `fb` in phase B (backward chain: it needs the
+// coalesced act'(z) operand of phase B; a phase-B thread always owns the same 4-column chunk
+// f4 = tid & 15, i.e. one (stage, plane) of the 4 stages a 64-column step covers; the stores are
+// 2-way bank conflicted).  `pre(row, col)` prefetches a phase-B operand before the accumulator wait.
+template <int CHAIN, class FA, class PRE, class FB>
+__device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, const TcChainOut co, FA fa, PRE pre, FB fb) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sub = warp & 3, cg = warp >> 2;
-  float* ebuf = reinterpret_cast<float*>(cx.smem);
+  float* ebuf = reinterpret_cast<float*>(cx.smem + cx.ebuf_off);
   const int r = sub * 32 + lane;
   constexpr int PB = TCM * 16 / TC_NPROD;                 // phase-B float4 per thread per step = 4
+  const uint32_t pa = tc::plane_bytes(TCM);
   for (int c0 = 0; c0 < npad; c0 += 64) {
     const int ncol4 = ((npad - c0) < 64 ? (npad - c0) : 64) >> 2;        // float4 per row in this step
     float4 pz[PB];
@@ -204,14 +243,39 @@ __device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, PRE pre,
       pz[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f4 < ncol4) pz[j] = pre(row, c0 + 4 * f4);
     }
+    if (c0 == 0) {
+      tc_wait_acc(cx);
+      tc_stamp(cx.nstamp);                                               // accumulator complete
+    }
     const int c = c0 + cg * 16;
     if (c < npad) {
-      float v[16];
-      tc::tmem_ld16(cx.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
-      fa(r, c, v);
+      float v[16], h[16];
+      tc::tmem_ld16(cx.tmem_base + cx.acc_col + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
+      fa(r, c, v, h);
       float4* dst = reinterpret_cast<float4*>(ebuf + r * TC_EP_PITCH + cg * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (CHAIN == 1) {
+        const int st = c >> 4;
+        if (st < co.nst_next) {
+          const uint32_t gs = co.g_next + static_cast<uint32_t>(st);
+          const int slot = gs % TC_NS;
+          tc_wait_empty(cx, slot, gs / TC_NS);
+          uint8_t* cdst = cx.smem + slot * 2u * TC_A_BYTES + r * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 hi, lo;
+            tc::split4_fast(make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]), hi, lo);
+            *reinterpret_cast<float4*>(cdst + q * pa) = hi;
+            if (co.split) *reinterpret_cast<float4*>(cdst + TC_A_BYTES + q * pa) = lo;
+          }
+          tc::tc_fence_before();
+          tc::fence_proxy_async();
+          __syncwarp();
+          // 4 of the 16 producer warps feed one stage: each arrives for 4
+          if (lane == 0) tc::mbar_arrive_cnt(&cx.bar_full_a[slot], TC_NPROD / 32 / 4);
+        }
+      }
     }
 #ifdef TC_PROBE
     tc_stamp(cx.nstamp);
@@ -220,11 +284,41 @@ __device__ __forceinline__ void tc_epilogue(TcCtx& cx, int npad, FA fa, PRE pre,
 #ifdef TC_PROBE
     tc_stamp(cx.nstamp);
 #endif
+    const int f4t = tid & 15;
+    const int cstage = (c0 >> 4) + (f4t >> 2);
+    const bool cwrite = CHAIN == 2 && f4t < ncol4 && cstage < co.nst_next;
+    uint8_t* cdst2 = nullptr;
+    if (cwrite) {
+      const uint32_t gs = co.g_next + static_cast<uint32_t>(cstage);
+      const int slot = gs % TC_NS;
+      tc_wait_empty(cx, slot, gs / TC_NS);
+      cdst2 = cx.smem + slot * 2u * TC_A_BYTES + (f4t & 3) * pa;
+    }
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int idx = tid + j * TC_NPROD;
       const int row = idx >> 4, f4 = idx & 15;
-      if (f4 < ncol4) fb(row, c0 + 4 * f4, *reinterpret_cast<const float4*>(ebuf + row * TC_EP_PITCH + 4 * f4), pz[j]);
+      if (f4 < ncol4) {
+        const float4 nxt = fb(row, c0 + 4 * f4, *reinterpret_cast<const float4*>(ebuf + row * TC_EP_PITCH + 4 * f4), pz[j]);
+        if (cwrite) {
+          float4 hi, lo;
+          tc::split4_fast(nxt, hi, lo);
+          *reinterpret_cast<float4*>(cdst2 + row * 16) = hi;
+          if (co.split) *reinterpret_cast<float4*>(cdst2 + TC_A_BYTES + row * 16) = lo;
+        }
+      }
+    }
+    if (CHAIN == 2) {
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int st = (c0 >> 4) + q;
+          if (4 * q < ncol4 && st < co.nst_next) tc::mbar_arrive(&cx.bar_full_a[(co.g_next + st) % TC_NS]);
+        }
+      }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
   }
@@ -245,12 +339,18 @@ __device__ __forceinline__ float4 act4(float4 x, int act) {
 // stride as in shared memory, so a stage of B is ONE contiguous bulk copy per half).
 __device__ __forceinline__ void tc_mainloop(TcCtx& cx, const float* __restrict__ A, int lda, int row0,
                                             int nrows, int K, int act, const float* __restrict__ Bhi,
-                                            const float* __restrict__ Blo, int npad, int split) {
+                                            const float* __restrict__ Blo, int npad, int split,
+                                            bool skip_a = false) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = (K + TCK - 1) / TCK;
   const uint32_t g0 = cx.g;
-  if (warp < TC_NPROD / 32) {
+  // consecutive GEMMs alternate between the two halves of the TMEM allocation, so the MMAs of the
+  // next GEMM never touch the accumulator the epilogue is still reading
+  cx.acc_col = (cx.tmem_cols > TC_MAXN && (cx.done_uses & 1u)) ? TC_MAXN : 0u;
+  if (warp < TC_NPROD / 32 && skip_a) {
+    // the previous epilogue already produced this GEMM's A stages on chip
+  } else if (warp < TC_NPROD / 32) {
     // ---------------- producers ----------------
     const int q = tid & 3, r = tid >> 2;                  // one 16-byte chunk per thread per stage
     const bool rv = row0 + r < nrows;
@@ -303,19 +403,16 @@ __device__ __forceinline__ void tc_mainloop(TcCtx& cx, const float* __restrict__
       }
     }
   } else if (warp == TC_NPROD / 32) {
-    // ---------------- MMA issuer ----------------
-    if ((tid & 31) == 0) {
-      const TcIssue ti = tc_issue_prepare(cx, npad);
-      for (int s = 0; s < nst; ++s) {
-        const uint32_t gs = g0 + s;
-        const int buf = gs % TC_NS;
-        const uint32_t par = (gs / TC_NS) & 1u;
-        tc::mbar_wait(&cx.bar_full_a[buf], par);
-        tc::mbar_wait(&cx.bar_full_b[buf], par);
-        tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
-      }
+    // ---------------- MMA issuer (whole warp, converged; see tc_issue) ----------------
+    const TcIssue ti = tc_issue_prepare(cx, npad);
+    for (int s = 0; s < nst; ++s) {
+      const uint32_t gs = g0 + s;
+      const int buf = gs % TC_NS;
+      const uint32_t par = (gs / TC_NS) & 1u;
+      tc::mbar_wait(&cx.bar_full_a[buf], par);
+      tc::mbar_wait(&cx.bar_full_b[buf], par);
+      tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
     }
-    __syncwarp();
   } else {
     // ------- weight (B operand) bulk-copy producer: never joins the per-layer barriers, so it
     // ------- runs ahead into the next layer as soon as ring slots free up
@@ -344,10 +441,10 @@ __device__ __forceinline__ void tc_wait_acc(TcCtx& cx) {
 }
 __device__ __forceinline__ void tc_gemm_end(TcCtx& cx) {
   cx.done_uses++;
-  if ((threadIdx.x >> 5) <= TC_NPROD / 32) {              // producers + issuer
-    tc::tc_fence_before();
-    asm volatile("bar.sync 2, %0;" ::"n"(TC_NPROD + 32) : "memory");
-  }
+  // producers only: their global writes of this layer become visible to each other.  The issuer
+  // does not take part: it is gated by the full_a barriers of the next GEMM and writes the other
+  // TMEM half.
+  if ((threadIdx.x >> 5) < TC_NPROD / 32) asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -398,14 +495,35 @@ __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
 // FWD (tensor cores)
 // ------------------------------------------------------------------------------------------
 struct TcFwdSmem {
-  __align__(16) float bias[TC_MAXN];
+  __align__(16) float bias[MAXL][TC_MAXN];   // all layers of the current chain, staged once
   __align__(16) float thin_w[TC_MAXN * 4];   // weights of a fused thin (<= 4 outputs) last layer
   __align__(16) float thin_part[4 * TCM * 4];   // [column group][row][output] partial dots
 };
 
-// both threads groups that take part in the per-layer hand-off (producers + issuer)
+// hand-off between layers that do not run a GEMM (element-wise thin layers): producers only
 __device__ __forceinline__ void tc_layer_sync() {
-  if ((threadIdx.x >> 5) <= TC_NPROD / 32) asm volatile("bar.sync 2, %0;" ::"n"(TC_NPROD + 32) : "memory");
+  if ((threadIdx.x >> 5) < TC_NPROD / 32) asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");
+}
+
+// Per-chain shared-memory layout: B slots sized for the chain's widest operand; when that leaves
+// room for the epilogue transpose buffer outside the ring, epilogues may feed the next GEMM on chip.
+// The weight streamer runs ahead of everybody else, so before the layout changes it waits for the
+// last GEMM issued under the old layout.
+constexpr uint32_t TC_EBUF_BYTES = TCM * TC_EP_PITCH * 4u;
+__device__ __forceinline__ void tc_chain_setup(TcCtx& cx, const b200ppo_chain& ch, bool backward) {
+  int maxn = 16;
+  for (int l = 0; l < ch.n_layers; ++l) {
+    const int n = backward ? ch.dims[l] : ch.dims[l + 1];
+    if ((!backward || l >= 1) && n > maxn) maxn = n;
+  }
+  maxn = (maxn + 15) & ~15;
+  const uint32_t bh = (TCK / 4) * tc::plane_bytes(maxn);
+  if (bh != cx.b_half && (threadIdx.x >> 5) > TC_NPROD / 32 && cx.done_uses > 0u)
+    tc::mbar_wait(cx.bar_done, (cx.done_uses - 1u) & 1u);
+  cx.b_half = bh;
+  const uint32_t ring_end = cx.b_base + TC_NS * 2u * bh;
+  cx.chain_ok = ring_end + TC_EBUF_BYTES <= TC_SMEM;
+  cx.ebuf_off = cx.chain_ok ? ring_end : 0u;
 }
 
 __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,
@@ -417,35 +535,42 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
   // epilogue of the layer before it instead of running a 16-column padded GEMM
   const bool fuse_thin = L >= 2 && ch.dims[L] <= 4 && ch.dims[L - 1] <= TC_MAXN;
   const int Lg = fuse_thin ? L - 1 : L;
+  tc_chain_setup(cx, ch, false);
+  if (tid < TC_NPROD) {
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");         // previous chain done with sm.bias
+    for (int i = tid; i < Lg * TC_MAXN; i += TC_NPROD) {
+      const int l = i / TC_MAXN, n = i - l * TC_MAXN;
+      sm.bias[l][n] = n < ch.dims[l + 1] ? __ldg(P + ch.b_off[l] + n) : 0.0f;
+    }
+  }
+  bool chain_in = false;                 // this GEMM's A stages come from the previous epilogue
   for (int l = 0; l < Lg; ++l) {
     const int K = ch.dims[l], N = ch.dims[l + 1];
     const float* A = l == 0 ? ws + xhat_off : ws + zoff[l - 1];
     const int act_in = l == 0 ? B200PPO_ACT_NONE : ch.act;
-    const float* bias = P + ch.b_off[l];
     float* Z = ws + zoff[l];
     const int npad = tl[l].npad;
     const bool thin = fuse_thin && l == L - 2;
     const int NT = thin ? ch.dims[L] : 0;
     if (tid < TC_NPROD) {
-      if (tid < npad) sm.bias[tid] = tid < N ? __ldg(bias + tid) : 0.0f;
       if (thin) {
         const float* Wt = P + ch.w_off[L - 1];
         for (int i = tid; i < N * NT; i += TC_NPROD) sm.thin_w[i] = __ldg(Wt + i);
       }
     }
-    tc_mainloop(cx, A, K, row0, nrows, K, act_in, ws + tl[l].wf_hi, ws + tl[l].wf_lo, npad, split);
+    tc_mainloop(cx, A, K, row0, nrows, K, act_in, ws + tl[l].wf_hi, ws + tl[l].wf_lo, npad, split, chain_in);
     tc_stamp(cx.nstamp);                                                 // producer loop done
+    const bool chain_out = cx.chain_ok && l + 1 < Lg;
     if (warp < TC_NPROD / 32) {
       asm volatile("bar.sync 1, %0;" ::"n"(TC_NPROD) : "memory");       // sm.bias / sm.thin_w visible
-      tc_wait_acc(cx);
-      tc_stamp(cx.nstamp);                                               // accumulator complete
       float tp0 = 0.f, tp1 = 0.f, tp2 = 0.f, tp3 = 0.f;    // scalars: an array here ends up in local memory
       const int act = ch.act;
-      tc_epilogue(
-          cx, npad,
-          [&](int r, int c, float (&v)[16]) {
+      const TcChainOut co{cx.g, npad / TCK, split};
+      const float* lbias = sm.bias[l];
+      auto fa =
+          [&](int r, int c, float (&v)[16], float (&h)[16]) {
             {
-              const float4* b4 = reinterpret_cast<const float4*>(sm.bias + c);     // c is a multiple of 16
+              const float4* b4 = reinterpret_cast<const float4*>(lbias + c);       // c is a multiple of 16
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 b = b4[i];
@@ -481,22 +606,33 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
                 }
               }
             }
-          },
-          TcNoPre(),
-          [&](int r, int col, const float4 val, const float4) {
-            const int row = row0 + r;
-            if (row < nrows && col < N) {
-              float* dst = Z + static_cast<size_t>(row) * N + col;
-              if ((N & 3) == 0) {
-                *reinterpret_cast<float4*>(dst) = val;
+            if (chain_out) {                               // next layer's A operand (padding columns: act(0) = 0)
+              if (act == B200PPO_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = fmaxf(v[i], 0.0f);
               } else {
-                dst[0] = val.x;
-                if (col + 1 < N) dst[1] = val.y;
-                if (col + 2 < N) dst[2] = val.z;
-                if (col + 3 < N) dst[3] = val.w;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h[i] = act_fwd(v[i], act);
               }
             }
-          });
+          };
+      auto fb = [&](int r, int col, const float4 val, const float4) {
+        const int row = row0 + r;
+        if (row < nrows && col < N) {
+          float* dst = Z + static_cast<size_t>(row) * N + col;
+          if ((N & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = val;
+          } else {
+            dst[0] = val.x;
+            if (col + 1 < N) dst[1] = val.y;
+            if (col + 2 < N) dst[2] = val.z;
+            if (col + 3 < N) dst[3] = val.w;
+          }
+        }
+        return val;
+      };
+      if (chain_out) tc_epilogue<1>(cx, npad, co, fa, TcNoPre(), fb);
+      else tc_epilogue<0>(cx, npad, co, fa, TcNoPre(), fb);
       tc_stamp(cx.nstamp);                                               // epilogue body done
       if (thin) {
         const int r = (warp & 3) * 32 + (tid & 31), cg = warp >> 2;
@@ -516,6 +652,7 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
     }
     else cx.nstamp += 2;
     tc_gemm_end(cx);
+    chain_in = chain_out;
     tc_stamp(cx.nstamp);                                                 // epilogue + hand-off done
   }
 }
@@ -527,7 +664,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   __shared__ const float* rowsrc[TCM];
   __shared__ __align__(16) TcFwdSmem sm;
   TcCtx cx;
-  tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
   const int O = a.plan.obs_dim;
   const int row0 = blockIdx.x * TCM;
   const int R = a.L.R, Rv = a.L.Rv;
@@ -586,6 +723,8 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
                                                   const float* __restrict__ P, float* ws, const size_t* zoff,
                                                   const size_t* doff, int row0, int nrows, int split) {
   const int tid = threadIdx.x, warp = tid >> 5;
+  tc_chain_setup(cx, ch, true);
+  bool chain_in = false;
   for (int l = ch.n_layers - 1; l >= 1; --l) {
     const int Kl = ch.dims[l], Nl = ch.dims[l + 1];
     const float* dY = ws + doff[l];
@@ -597,44 +736,40 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
       // all loads of a batch in flight together (a dependent-load loop here cost 80 K cycles)
       if (tid < TC_NPROD) {
         const float* W = P + ch.w_off[l];
-        if ((Kl & 3) == 0) {
-          const int K4 = Kl >> 2;
-          constexpr int TB = 4;
-          for (int i0 = tid; i0 < TCM * K4; i0 += TC_NPROD * TB) {
+        const int K4 = Kl >> 2;
+        if ((Kl & 3) == 0 && K4 <= TC_NPROD && TC_NPROD % K4 == 0 && Nl == 1) {
+          // one output (value head): a thread keeps its 4 columns' weights in registers and walks
+          // down the rows, 8 independent 16-byte loads in flight
+          const int k4 = tid % K4, r0 = tid / K4, rstep = TC_NPROD / K4;
+          const float4 w = make_float4(__ldg(W + 4 * k4), __ldg(W + 4 * k4 + 1), __ldg(W + 4 * k4 + 2),
+                                       __ldg(W + 4 * k4 + 3));                    // W is [Kl][1]
+          constexpr int TB = 8;
+          for (int rb = r0; rb < TCM; rb += rstep * TB) {
             float4 zz[TB];
-            float dy[TB][4];
+            float dy[TB];
 #pragma unroll
             for (int b = 0; b < TB; ++b) {
-              const int idx = i0 + b * TC_NPROD;
-              const int rr = idx / K4, k4 = idx - rr * K4;
-              const int row = row0 + rr;
+              const int rr = rb + b * rstep, row = row0 + rr;
               zz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) dy[b][j] = 0.f;
-              if (idx < TCM * K4 && row < nrows) {
+              dy[b] = 0.f;
+              if (rr < TCM && row < nrows) {
                 zz[b] = *reinterpret_cast<const float4*>(zprev + static_cast<size_t>(row) * Kl + 4 * k4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j < Nl) dy[b][j] = dY[static_cast<size_t>(row) * Nl + j];
+                dy[b] = dY[row];
               }
             }
 #pragma unroll
             for (int b = 0; b < TB; ++b) {
-              const int idx = i0 + b * TC_NPROD;
-              const int rr = idx / K4, k4 = idx - rr * K4;
-              const int row = row0 + rr;
-              if (idx < TCM * K4 && row < nrows) {
-                const float zv[4] = {zz[b].x, zz[b].y, zz[b].z, zz[b].w};
-                float g[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float acc = 0.0f;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    if (j < Nl) acc = fmaf(dy[b][j], __ldg(W + static_cast<size_t>(4 * k4 + e) * Nl + j), acc);
-                  g[e] = acc * act_grad(zv[e], act);
+              const int rr = rb + b * rstep, row = row0 + rr;
+              if (rr < TCM && row < nrows) {
+                float4 g;
+                if (act == B200PPO_ACT_RELU) {
+                  g = make_float4(zz[b].x > 0.f ? dy[b] * w.x : 0.f, zz[b].y > 0.f ? dy[b] * w.y : 0.f,
+                                  zz[b].z > 0.f ? dy[b] * w.z : 0.f, zz[b].w > 0.f ? dy[b] * w.w : 0.f);
+                } else {
+                  g = make_float4(dy[b] * w.x * act_grad(zz[b].x, act), dy[b] * w.y * act_grad(zz[b].y, act),
+                                  dy[b] * w.z * act_grad(zz[b].z, act), dy[b] * w.w * act_grad(zz[b].w, act));
                 }
-                *reinterpret_cast<float4*>(dprev + static_cast<size_t>(row) * Kl + 4 * k4) = make_float4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<float4*>(dprev + static_cast<size_t>(row) * Kl + 4 * k4) = g;
               }
             }
           }
@@ -656,44 +791,48 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
       continue;
     }
     const int npad = tl[l].kout_pad;
-    tc_mainloop(cx, dY, Nl, row0, nrows, Nl, B200PPO_ACT_NONE, ws + tl[l].wb_hi, ws + tl[l].wb_lo, npad, split);
+    tc_mainloop(cx, dY, Nl, row0, nrows, Nl, B200PPO_ACT_NONE, ws + tl[l].wb_hi, ws + tl[l].wb_lo, npad, split,
+                chain_in);
     tc_stamp(cx.nstamp);
+    const bool kvec = (Kl & 3) == 0;
+    const bool chain_out = cx.chain_ok && l >= 2 && kvec;  // the next GEMM (layer l-1) reduces over these Kl columns
     if (warp < TC_NPROD / 32) {
-      tc_wait_acc(cx);
-      tc_stamp(cx.nstamp);
-      const bool kvec = (Kl & 3) == 0;
-      tc_epilogue(
-          cx, npad, [&](int, int, float (&)[16]) {},
-          [&](int r, int col) {
-            const int row = row0 + r;
-            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kvec && row < nrows && col < Kl) z = *reinterpret_cast<const float4*>(zprev + static_cast<size_t>(row) * Kl + col);
-            return z;
-          },
-          [&](int r, int col, const float4 val, const float4 z) {
-            const int row = row0 + r;
-            if (row < nrows && col < Kl) {
-              const size_t o = static_cast<size_t>(row) * Kl + col;
-              if (kvec) {
-                float4 g;
-                if (act == B200PPO_ACT_RELU) {
-                  g = make_float4(z.x > 0.f ? val.x : 0.f, z.y > 0.f ? val.y : 0.f, z.z > 0.f ? val.z : 0.f,
-                                  z.w > 0.f ? val.w : 0.f);
-                } else {
-                  g = make_float4(val.x * act_grad(z.x, act), val.y * act_grad(z.y, act),
-                                  val.z * act_grad(z.z, act), val.w * act_grad(z.w, act));
-                }
-                *reinterpret_cast<float4*>(dprev + o) = g;
-              } else {
-                const float vv[4] = {val.x, val.y, val.z, val.w};
-                for (int i = 0; i < 4; ++i)
-                  if (col + i < Kl) dprev[o + i] = vv[i] * act_grad(zprev[o + i], act);
-              }
+      const TcChainOut co{cx.g, npad / TCK, split};
+      auto pre = [&](int r, int col) {
+        const int row = row0 + r;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kvec && row < nrows && col < Kl) z = *reinterpret_cast<const float4*>(zprev + static_cast<size_t>(row) * Kl + col);
+        return z;
+      };
+      auto fa = [&](int, int, float (&)[16], float (&)[16]) {};
+      auto fb = [&](int r, int col, const float4 val, const float4 z) {
+        const int row = row0 + r;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < nrows && col < Kl) {
+          const size_t o = static_cast<size_t>(row) * Kl + col;
+          if (kvec) {
+            if (act == B200PPO_ACT_RELU) {
+              g = make_float4(z.x > 0.f ? val.x : 0.f, z.y > 0.f ? val.y : 0.f, z.z > 0.f ? val.z : 0.f,
+                              z.w > 0.f ? val.w : 0.f);
+            } else {
+              g = make_float4(val.x * act_grad(z.x, act), val.y * act_grad(z.y, act),
+                              val.z * act_grad(z.z, act), val.w * act_grad(z.w, act));
             }
-          });
+            *reinterpret_cast<float4*>(dprev + o) = g;
+          } else {
+            const float vv[4] = {val.x, val.y, val.z, val.w};
+            for (int i = 0; i < 4; ++i)
+              if (col + i < Kl) dprev[o + i] = vv[i] * act_grad(zprev[o + i], act);
+          }
+        }
+        return g;                                        // the next GEMM's A operand (zero outside the tile)
+      };
+      if (chain_out) tc_epilogue<2>(cx, npad, co, fa, pre, fb);
+      else tc_epilogue<0>(cx, npad, co, fa, pre, fb);
     }
     else ++cx.nstamp;
     tc_gemm_end(cx);
+    chain_in = chain_out;
     tc_stamp(cx.nstamp);
   }
 }
@@ -703,7 +842,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, 
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   TcCtx cx;
-  tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
   const int row0 = blockIdx.x * TCM;
   tc_stamp(cx.nstamp);
   tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
@@ -846,26 +985,21 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
       }
     }
   } else if (warp == TC_NPROD / 32) {
-    if ((tid & 31) == 0) {
-      const TcIssue ti = tc_issue_prepare(cx, npad);
-      for (int s = 0; s < nst; ++s) {
-        const uint32_t gs = cx.g + s;
-        const int buf = gs % TC_NS;
-        tc::mbar_wait(&cx.bar_full_a[buf], (gs / TC_NS) & 1u);
-        tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
-      }
+    const TcIssue ti = tc_issue_prepare(cx, npad);
+    for (int s = 0; s < nst; ++s) {
+      const uint32_t gs = cx.g + s;
+      const int buf = gs % TC_NS;
+      tc::mbar_wait(&cx.bar_full_a[buf], (gs / TC_NS) & 1u);
+      tc_issue(cx, ti, buf, split, s == 0, s == nst - 1);
     }
-    __syncwarp();
   }
   cx.g += nst;
   float* gpart = a.ws + a.L.gpart + static_cast<size_t>(sp) * a.plan.n_params;
   float* gp = gpart + ch->w_off[layer];
   tc_stamp(cx.nstamp);
   if (warp < TC_NPROD / 32 && nst > 0) {
-    tc_wait_acc(cx);
-    tc_stamp(cx.nstamp);
-    tc_epilogue(
-        cx, npad, [&](int, int, float (&)[16]) {}, TcNoPre(),
+    tc_epilogue<0>(
+        cx, npad, TcChainOut{0u, 0, 0}, [&](int, int, float (&)[16], float (&)[16]) {}, TcNoPre(),
         [&](int r, int col, const float4 val, const float4) {
           const int k = m0 + r;
           if (k < K && col < N) {
@@ -879,6 +1013,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
               if (col + 3 < N) dst[3] = val.w;
             }
           }
+          return val;
         });
   }
   cx.done_uses++;
@@ -1066,22 +1201,19 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
       }
     }
   } else if (warp == TC_NPROD / 32) {
-    if ((tid & 31) == 0) {
-      const TcIssue ti = tc_issue_prepare(cx, npad);
-      int uslot = 0;
-      uint32_t par = 0u;
-      TC_PROBE_DECL
-      for (int s = 0; s < nst; ++s) {
-        TC_PROBE_START();
-        wait(&cx.bar_full_a[uslot], par);
-        TC_PROBE_LAP(0);
-        tc_issue(cx, ti, uslot, split, s == 0, s == nst - 1);
-        TC_PROBE_LAP(1);
-        if (++uslot == DW2_NS) { uslot = 0; par ^= 1u; }
-      }
-      TC_PROBE_FLUSH(5, 2);
+    const TcIssue ti = tc_issue_prepare(cx, npad);
+    int uslot = 0;
+    uint32_t par = 0u;
+    TC_PROBE_DECL
+    for (int s = 0; s < nst; ++s) {
+      TC_PROBE_START();
+      wait(&cx.bar_full_a[uslot], par);
+      TC_PROBE_LAP(0);
+      tc_issue(cx, ti, uslot, split, s == 0, s == nst - 1);
+      TC_PROBE_LAP(1);
+      if (++uslot == DW2_NS) { uslot = 0; par ^= 1u; }
     }
-    __syncwarp();
+    TC_PROBE_FLUSH(5, 2);
   } else {
     // raw-block streamer: 16 full rows of H and of D per stage, one bulk copy each (many small
     // copies are slow: ~100 cycles apiece through the copy engine, measured with 512-byte segments)
@@ -1107,10 +1239,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   float* gp = gpart + ch->w_off[layer];
   tc_stamp(cx.nstamp);
   if (warp < TC_NPROD / 32 && nst > 0) {
-    tc_wait_acc(cx);
-    tc_stamp(cx.nstamp);
-    tc_epilogue(
-        cx, npad, [&](int, int, float (&)[16]) {}, TcNoPre(),
+    tc_epilogue<0>(
+        cx, npad, TcChainOut{0u, 0, 0}, [&](int, int, float (&)[16], float (&)[16]) {}, TcNoPre(),
         [&](int r, int col, const float4 val, const float4) {
           const int k = m0 + r;
           if (k < K && col < N) {
@@ -1124,6 +1254,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
               if (col + 3 < N) dst[3] = val.w;
             }
           }
+          return val;
         });
   }
   cx.done_uses++;

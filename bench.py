@@ -269,9 +269,15 @@ def run_own(args):
         mode = int(lib.b200ppo_set_gemm_mode(-1))
         tc = mode != 0
         kname = {"fwd": "upd_fwd", "bwd_dx": "upd_bwd_dx", "bwd_dw": "upd_bwd_dw"}[dom] + ("_tc_kernel" if tc else "_kernel")
+        if tc and dom == "bwd_dw":
+            kname = "upd_bwd_dw_tc2_kernel"       # bulk-copy + shared-memory transpose variant (every layer <= 256 wide)
+        traffic = None                            # dram bytes per launch from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(kname)
         line["roofline"] = {"bound": "tensor", "kernel": kname,
                             "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                            "traffic": None, "peak_source": f"{which} bf16 tensor (sustained)",
+                            "traffic": traffic, "peak_source": f"{which} bf16 tensor (sustained)",
                             "compute_path": ("tcgen05.mma kind::tf32, error-compensated 3xTF32 (3 MMAs per algorithmic product, fp32 accumulate in TMEM): "
                                              "achieved counts ALGORITHMIC flops; tensor-pipe work is 3x that" if mode == 1 else
                                              ("tcgen05.mma kind::tf32, plain TF32 (not fp32 parity)" if mode == 2 else "fp32 FFMA (CUDA cores)")),

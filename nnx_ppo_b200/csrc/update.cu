@@ -382,7 +382,7 @@ struct GaeArgs {
 };
 
 constexpr int GAE_THREADS = 64;
-constexpr int GAE_CHUNK = 8;
+constexpr int GAE_CHUNK = 32;  // a whole T = 32 rollout in one memory round trip
 
 __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
   __shared__ double red[2][4];

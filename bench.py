@@ -236,6 +236,9 @@ def run_own(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_envs": cfg["n_envs"] * world, "parallelism": f"dp{world} (env-sharded)",
                            "l2": "no flush: every update streams a ~150 MB working set (> 126 MB L2) that the iteration itself rewrites",
+                           "collectives": ("none" if world == 1 else
+                                           ("peer memory: epoch flags + P2P loads inside the GAE / loss / Adam kernels"
+                                            if eng.p2p else "NCCL all-reduce x2 per update")),
                            "cuda_graph": eng.graph is not None, "done_rate": float(eng.done.float().mean()),
                            "truncation_rate": float(eng.trunc.float().mean())},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(),

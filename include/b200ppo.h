@@ -78,6 +78,7 @@ typedef struct b200ppo_hparams {
   float grad_clip;          /* <= 0: no clip_by_global_norm                               */
   int32_t normalize_advantages;
   int32_t world_size;       /* data-parallel ranks sharing this update (means are global) */
+  int32_t rank;             /* this process' rank (only read when bufs->comm is set)      */
 } b200ppo_hparams;
 
 /* Device buffers of one minibatch update.  ws is a scratch arena of
@@ -103,6 +104,10 @@ typedef struct b200ppo_update_bufs {
   const uint32_t* rng_state;   /* dev uint32[4]                                                    */
   float* metrics_out;          /* dev [4]: actor loss, critic loss, regularisation loss, grad norm */
   void* ws;                    /* dev scratch                                                      */
+  /* optional peer-memory exchange (NULL: the caller all-reduces adv_sums and the gradient between
+   * the stages).  dev uint64[world_size]: base address of every rank's comm buffer
+   * (b200ppo_comm_alloc / b200ppo_comm_ipc_open), entry [rank] being this rank's own. */
+  const uint64_t* comm;
 } b200ppo_update_bufs;
 
 /* -------- library -------------------------------------------------------------------------- */
@@ -205,6 +210,24 @@ int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int3
 int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,
                    const b200ppo_update_bufs* bufs, int32_t T, int32_t B, int32_t mb,
                    uint32_t rng_count_offset, int32_t update_index, int32_t stages);
+/* -------- peer-memory exchange of the data-parallel update (replaces the two per-update NCCL
+ * all-reduces of DESIGN.md section 5: advantage moment sums and the flat gradient) ---------------
+ * Every rank owns one comm buffer (cudaMalloc'ed, exported with CUDA IPC) holding epoch flags, the
+ * per-rank advantage sums and a double-buffered copy of its locally reduced gradient.  Kernels
+ * publish with remote stores + __threadfence_system and wait by spinning on LOCAL flags:
+ *   GAE kernel   -> writes its (sum a, sum a^2) into every peer's slot, then the flag;
+ *   loss kernel  -> waits for all ranks' flags, sums the slots in rank order;
+ *   Adam kernel  -> publishes "gradient ready", waits for all ranks, pulls and sums the peers'
+ *                   gradients in rank order (bit-identical parameters on every rank).
+ * epoch = adam count base + update_index + 1 (monotonic; buffers alternate on its parity).       */
+#define B200PPO_MAX_RANKS 16
+int64_t b200ppo_comm_bytes(const b200ppo_plan* plan);
+int b200ppo_comm_alloc(int64_t bytes, void** out);                 /* zero-initialised device memory */
+int b200ppo_comm_free(void* p);
+int b200ppo_comm_ipc_get(void* p, uint8_t* handle64);              /* 64-byte cudaIpcMemHandle_t     */
+int b200ppo_comm_ipc_open(const uint8_t* handle64, void** out);
+int b200ppo_comm_ipc_close(void* p);
+
 /* GEMM engine of the update: 0 = fp32 FFMA on CUDA cores, 1 = tcgen05 3xTF32 (default; error-   *
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */

@@ -36,13 +36,13 @@ class HParams(C.Structure):
                 ("critic_loss_weight", C.c_float), ("learning_rate", C.c_float),
                 ("adam_b1", C.c_float), ("adam_b2", C.c_float), ("adam_eps", C.c_float),
                 ("weight_decay", C.c_float), ("grad_clip", C.c_float),
-                ("normalize_advantages", C.c_int32), ("world_size", C.c_int32)]
+                ("normalize_advantages", C.c_int32), ("world_size", C.c_int32), ("rank", C.c_int32)]
 
 
 class UpdateBufs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "raw_action", "loglik_old", "reward", "done", "truncated", "next_obs_last", "inds",
-        "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws")]
+        "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm")]
 
 
 class SynthEnv(C.Structure):
@@ -82,6 +82,12 @@ SYMBOLS = {
     "b200ppo_update_adv_sums_ptr": (_vp, [_PP, _i32, _i32, _vp]),
     "b200ppo_update_grad_ptr": (_vp, [_PP, _i32, _i32, _vp]),
     "b200ppo_update_debug_ptr": (_vp, [_PP, _i32, _i32, _vp, _i32]),
+    "b200ppo_comm_bytes": (_i64, [_PP]),
+    "b200ppo_comm_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
+    "b200ppo_comm_free": (C.c_int, [_vp]),
+    "b200ppo_comm_ipc_get": (C.c_int, [_vp, C.c_char_p]),
+    "b200ppo_comm_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "b200ppo_comm_ipc_close": (C.c_int, [_vp]),
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
     "b200ppo_tc_microbench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),

@@ -121,6 +121,12 @@ class PPOEngine:
             b.ws = wsp
             self.bufs.append(b)
         self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
+        # data-parallel exchange of the per-update advantage sums and gradients: peer memory
+        # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
+        self.p2p = False
+        self._comm_local, self._comm_peers, self.comm_table = None, [], None
+        if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0" and not self.hp.grad_clip > 0.0:
+            self._setup_p2p()
         if use_graph is None:
             use_graph = os.environ.get("B200PPO_GRAPH", "1") != "0"
         self.use_graph = use_graph
@@ -130,6 +136,53 @@ class PPOEngine:
         self._env_state = None
 
     # ------------------------------------------------------------------------------------
+    def _setup_p2p(self):
+        """Allocate this rank's comm buffer, exchange CUDA IPC handles, map every peer's buffer
+        (include/b200ppo.h, 'peer-memory exchange').  Raises if the GPUs cannot map each other."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        lib, world = self.lib, self.world
+        rank = dist.get_rank(self.group)
+        nbytes = int(lib.b200ppo_comm_bytes(self.net.plan))
+        if nbytes <= 0 or world > 16:
+            raise _lib.B200PPOError("peer exchange: unsupported plan or world size")
+        p = C.c_void_p()
+        _lib.check(lib.b200ppo_comm_alloc(nbytes, C.byref(p)), "comm_alloc")
+        self._comm_local = p.value
+        h = C.create_string_buffer(64)
+        _lib.check(lib.b200ppo_comm_ipc_get(p, h), "comm_ipc_get")
+        mine = torch.tensor(list(h.raw), dtype=torch.uint8, device=self.dev)
+        allh = torch.zeros(world * 64, dtype=torch.uint8, device=self.dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        allh = allh.cpu().numpy().reshape(world, 64)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(self._comm_local)
+                continue
+            q = C.c_void_p()
+            _lib.check(lib.b200ppo_comm_ipc_open(allh[r].tobytes(), C.byref(q)), f"comm_ipc_open(rank {r})")
+            self._comm_peers.append(q.value)
+            ptrs.append(q.value)
+        self.comm_table = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for b in self.bufs:
+            b.comm = self.comm_table.data_ptr()
+        self.hp.rank = rank
+        self.p2p = True
+
+    def close(self):
+        """Unmap / free the peer-exchange buffers (safe to call twice)."""
+        lib = self.lib
+        for q in self._comm_peers:
+            lib.b200ppo_comm_ipc_close(q)
+        self._comm_peers = []
+        if self._comm_local is not None:
+            lib.b200ppo_comm_free(self._comm_local)
+            self._comm_local = None
+
     def _allreduce(self, t):
         parallel.all_reduce_sum(t, self.group)
 
@@ -168,8 +221,9 @@ class PPOEngine:
         for u in range(self.n_updates):
             off = rng_offset0 + u * 2 * (T + 1)
             args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
-            if self.world == 1:
+            if self.world == 1 or self.p2p:
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL), "update")
+                n += 1 if self.p2p else 0       # the partial reduction is its own launch on this path
             else:
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE), "update/fwd")
                 if self.hp.normalize_advantages:

@@ -137,6 +137,37 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
 }
 
 // ------------------------------------------------------------------------------------------
+// peer-memory exchange (include/b200ppo.h): comm buffer layout and device helpers
+// ------------------------------------------------------------------------------------------
+constexpr int MAXR = B200PPO_MAX_RANKS;
+constexpr size_t COMM_FLAG_ADV = 0;                       // uint32[MAXR], written by the peers
+constexpr size_t COMM_FLAG_GRAD = 64;                     // uint32[MAXR]
+constexpr size_t COMM_ADV = 128;                          // double[2 parity][MAXR][2]
+constexpr size_t COMM_GRAD = 1024;                        // float[2 parity][Ppad]
+inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n_params)); }
+
+struct PeerComm {
+  const uint64_t* table;   // device: comm base of every rank (nullptr: exchange disabled)
+  int world, rank;
+};
+__device__ __forceinline__ uint8_t* comm_base(const PeerComm& c, int r) {
+  return reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(c.table[r]));
+}
+// spin until every rank's flag (written into OUR buffer by that rank) has reached `epoch`
+__device__ __forceinline__ void comm_wait_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
+  const volatile uint32_t* fl = reinterpret_cast<const volatile uint32_t*>(comm_base(c, c.rank) + flag_off);
+  for (int r = 0; r < c.world; ++r)
+    while (static_cast<int32_t>(fl[r] - epoch) < 0) {}
+  __threadfence_system();
+}
+// tell every rank (ourselves included) that our data of `epoch` is in place
+__device__ __forceinline__ void comm_signal_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
+  __threadfence_system();
+  for (int r = 0; r < c.world; ++r)
+    *reinterpret_cast<volatile uint32_t*>(comm_base(c, r) + flag_off + 4u * c.rank) = epoch;
+}
+
+// ------------------------------------------------------------------------------------------
 // the shared GEMM routine:  C[TM x N] = act_in(A)[rows x K] * B[K x N]
 //   A: global row-major, row r at A + r*lda (rows >= nrows read as zero), act_in applied on load
 //   B: TRANS_B ? Bm[n*ldb + k] : Bm[k*ldb + n]
@@ -379,6 +410,9 @@ struct GaeArgs {
   float* ws; size_t v_off;
   int T, B, mb;
   float gamma, lambda_;
+  PeerComm comm;
+  const uint32_t* rng_state;
+  int update_index;
 };
 
 constexpr int GAE_THREADS = 64;
@@ -451,6 +485,16 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
       }
       dbl[0] = t1;   // adv_sums: a data-parallel caller all-reduces these two doubles
       dbl[1] = t2;
+      if (a.comm.table != nullptr) {             // ... or every peer gets them through its comm buffer
+        const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
+        for (int r = 0; r < a.comm.world; ++r) {
+          volatile double* slot = reinterpret_cast<volatile double*>(comm_base(a.comm, r) + COMM_ADV) +
+                                  ((epoch & 1u) * MAXR + a.comm.rank) * 2;
+          slot[0] = t1;
+          slot[1] = t2;
+        }
+        comm_signal_all(a.comm, COMM_FLAG_ADV, epoch);
+      }
     }
   }
 }
@@ -470,23 +514,43 @@ struct LossArgs {
   float clip, critic_w;
   int normalize_adv;
   double n_global;
+  PeerComm comm;
+  int update_index;
 };
+
+// global advantage moments: the local sums, or (peer exchange) all ranks' sums in rank order
+__device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean, float& a_den) {
+  a_mean = 0.0f;
+  a_den = 1.0f;
+  if (!a.normalize_adv) return;
+  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
+  double s1 = dbl[0], s2 = dbl[1];
+  if (a.comm.table != nullptr) {
+    const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
+    comm_wait_all(a.comm, COMM_FLAG_ADV, epoch);
+    const volatile double* slot = reinterpret_cast<const volatile double*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) +
+                                  (epoch & 1u) * MAXR * 2;
+    s1 = 0.0;
+    s2 = 0.0;
+    for (int r = 0; r < a.comm.world; ++r) { s1 += slot[2 * r]; s2 += slot[2 * r + 1]; }
+  }
+  const double m = s1 / a.n_global;
+  double var = s2 / a.n_global - m * m;
+  var = var > 0.0 ? var : 0.0;
+  a_mean = static_cast<float>(m);
+  a_den = static_cast<float>(sqrt(var)) + 1e-8f;
+}
 
 __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   __shared__ double red[3][4];
+  __shared__ float stats0_s[2];
   const int A = a.plan.act_dim;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
   const double ng = a.n_global;
   const float inv_n = static_cast<float>(1.0 / ng);
-  float a_mean = 0.0f, a_den = 1.0f;
-  if (a.normalize_adv) {
-    const double m = dbl[0] / ng;
-    double var = dbl[1] / ng - m * m;
-    var = var > 0.0 ? var : 0.0;
-    a_mean = static_cast<float>(m);
-    a_den = static_cast<float>(sqrt(var)) + 1e-8f;
-  }
+  if (threadIdx.x == 0) loss_adv_stats(a, stats0_s[0], stats0_s[1]);
+  __syncthreads();
+  const float a_mean = stats0_s[0], a_den = stats0_s[1];
   double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
   if (r < a.L.R) {
     const int t = r / a.mb, j = r - t * a.mb;
@@ -550,7 +614,7 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double* part = const_cast<double*>(dbl) + DBL_LOSS_PART;
+    double* part = reinterpret_cast<double*>(a.ws + a.L.dbl) + DBL_LOSS_PART;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
     for (int q = 0; q < 3; ++q) part[3 * blockIdx.x + q] = red[q][0] + red[q][1] + red[q][2] + red[q][3];
     __threadfence();
@@ -576,23 +640,8 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   const int A = a.plan.act_dim;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gid / A, d = gid - r * A;
-  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
   const double ng = a.n_global;
   const float inv_n = static_cast<float>(1.0 / ng);
-  if (threadIdx.x == 0) {                       // fp64 moment math once per block (fp64 is slow)
-    float am = 0.0f, ad = 1.0f;
-    if (a.normalize_adv) {
-      const double m = dbl[0] / ng;
-      double var = dbl[1] / ng - m * m;
-      var = var > 0.0 ? var : 0.0;
-      am = static_cast<float>(m);
-      ad = static_cast<float>(sqrt(var)) + 1e-8f;
-    }
-    stats_s[0] = am;
-    stats_s[1] = ad;
-  }
-  __syncthreads();
-  const float a_mean = stats_s[0], a_den = stats_s[1];
   const bool valid = r < a.L.R;
   float llt = 0.0f, entt = 0.0f, mu = 0.f, rho = 0.f, z = 0.f, sigma = 1.f, eps2 = 0.f, th = 0.f;
   size_t grow = 0;
@@ -618,6 +667,12 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     ll += __shfl_xor_sync(0xffffffffu, ll, o);
     ent += __shfl_xor_sync(0xffffffffu, ent, o);
   }
+  // global advantage moments (fp64 once per block).  Taken AFTER the sampler math: with the peer
+  // exchange this is where a rank waits for the other ranks' GAE sums, and the NVLink latency
+  // hides behind the threefry / erfinv / transcendental work above.
+  if (threadIdx.x == 0) loss_adv_stats(a, stats_s[0], stats_s[1]);
+  __syncthreads();
+  const float a_mean = stats_s[0], a_den = stats_s[1];
   double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
   if (valid) {
     const float adv = a.ws[a.L.adv + r];
@@ -658,7 +713,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   }
   __syncthreads();
   __shared__ bool is_last_s;
-  double* part = const_cast<double*>(dbl) + DBL_LOSS_PART;
+  double* part = reinterpret_cast<double*>(a.ws + a.L.dbl) + DBL_LOSS_PART;
   if (threadIdx.x == 0) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
     for (int q = 0; q < 3; ++q) {
@@ -858,12 +913,20 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
 // ------------------------------------------------------------------------------------------
 // RED / grad-norm / ADAM
 // ------------------------------------------------------------------------------------------
+// fixed-order sum of the dW row-split partials.  With the peer exchange the result goes to this
+// rank's comm buffer (slot = epoch parity), where the other ranks' Adam kernels read it.
 __global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ gpart, int S, int64_t P,
-                                                      float* __restrict__ grad) {
+                                                      float* __restrict__ grad, const PeerComm comm,
+                                                      const uint32_t* __restrict__ rng_state, int update_index,
+                                                      size_t ppad) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= P) return;
   float g = 0.0f;
   for (int s = 0; s < S; ++s) g += gpart[static_cast<size_t>(s) * P + i];
+  if (comm.table != nullptr) {
+    const uint32_t epoch = rng_state[3] + static_cast<uint32_t>(update_index) + 1u;
+    grad = reinterpret_cast<float*>(comm_base(comm, comm.rank) + COMM_GRAD) + (epoch & 1u) * ppad;
+  }
   grad[i] = g;
 }
 
@@ -903,6 +966,8 @@ struct AdamArgs {
   int64_t P;
   int update_index;
   float lr, b1, b2, eps, wd, clip;
+  PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of every rank's comm copy
+  size_t comm_ppad;
 };
 
 // optax.adam / adamw (scale_by_adam -> [add_decayed_weights] -> scale(-lr)), optionally preceded by
@@ -914,9 +979,26 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
     gn = sqrtf(static_cast<float>(*a.gnorm2));
     if (i == 0) a.metrics_out[3] = gn;
   }
+  const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
+  if (a.comm.table != nullptr) {
+    // the local reduction (previous kernel on this stream) is complete: publish, then wait for everyone
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) comm_signal_all(a.comm, COMM_FLAG_GRAD, epoch);
+      comm_wait_all(a.comm, COMM_FLAG_GRAD, epoch);
+    }
+    __syncthreads();
+  }
   if (i >= a.P) return;
   float g;
-  if (a.S > 0) {
+  if (a.comm.table != nullptr) {
+    g = 0.0f;
+    for (int r = 0; r < a.comm.world; ++r) {
+      const volatile float* pg = reinterpret_cast<const volatile float*>(comm_base(a.comm, r) + COMM_GRAD) +
+                                 (epoch & 1u) * a.comm_ppad;
+      g += pg[i];
+    }
+    a.grad_out[i] = g;
+  } else if (a.S > 0) {
     g = 0.0f;
     for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
     a.grad_out[i] = g;
@@ -924,7 +1006,7 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
     g = a.grad[i];
   }
   if (a.clip > 0.0f && !(gn < a.clip)) g = __fmul_rn(__fdiv_rn(g, gn), a.clip);
-  const float t = static_cast<float>(a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u);
+  const float t = static_cast<float>(epoch);
   const float m = __fadd_rn(__fmul_rn(1.0f - a.b1, g), __fmul_rn(a.b1, a.mu[i]));
   const float v = __fadd_rn(__fmul_rn(1.0f - a.b2, __fmul_rn(g, g)), __fmul_rn(a.b2, a.nu[i]));
   a.mu[i] = m;
@@ -1076,6 +1158,13 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   if (plan->normalize && (!b->norm_mean || !b->norm_std)) return B200PPO_EINVAL;
   if (reinterpret_cast<uintptr_t>(b->ws) & 255) return B200PPO_EALIGN;
   if (hp->world_size < 1) return B200PPO_EINVAL;
+  const bool use_comm = b->comm != nullptr && hp->world_size > 1;
+  PeerComm pc{nullptr, 1, 0};
+  if (use_comm) {
+    if (hp->world_size > MAXR || hp->rank < 0 || hp->rank >= hp->world_size) return B200PPO_EINVAL;
+    if (hp->grad_clip > 0.0f) return B200PPO_EINVAL;   // the global norm needs the summed gradient first: use the staged path
+    pc = PeerComm{b->comm, hp->world_size, hp->rank};
+  }
   rc = set_attrs();
   if (rc) return rc;
   const Layout L = make_layout(*plan, T, mb);
@@ -1111,6 +1200,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     GaeArgs a;
     a.L = L; a.reward = b->reward; a.done = b->done; a.trunc = b->truncated; a.inds = b->inds;
     a.ws = ws; a.v_off = v_off; a.T = T; a.B = B; a.mb = mb; a.gamma = hp->gamma; a.lambda_ = hp->lambda_;
+    a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
+    a.rng_state = b->rng_state; a.update_index = update_index;
     upd_gae_kernel<<<cdiv(mb, GAE_THREADS), GAE_THREADS, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
@@ -1122,6 +1213,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.T = T; a.B = B; a.mb = mb; a.count_offset = rng_count_offset;
     a.clip = hp->clip_range; a.critic_w = hp->critic_loss_weight; a.normalize_adv = hp->normalize_advantages;
     a.n_global = static_cast<double>(L.R) * hp->world_size;
+    a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
+    a.update_index = update_index;
     const int A = plan->act_dim;
     const bool par = A <= 32 && (A & (A - 1)) == 0 && cdiv(static_cast<int64_t>(L.R) * A, 256) <= MAX_LOSS_BLOCKS;
     if (par) upd_loss_par_kernel<<<cdiv(static_cast<int64_t>(L.R) * A, 256), 256, 0, s>>>(a);
@@ -1149,9 +1242,12 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     }
   }
   // reduce + adam fuse into one launch when both stages are requested and no global norm is needed
-  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f);
+  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f) &&
+                        !use_comm;
   if ((stages & B200PPO_STAGE_RED) && !fuse_red) {
-    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, use_tc ? L.tc_S : L.S, plan->n_params, ws + L.grad);
+    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, use_tc ? L.tc_S : L.S, plan->n_params,
+                                                             ws + L.grad, pc, b->rng_state, update_index,
+                                                             comm_ppad(plan->n_params));
     B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_ADAM) {
@@ -1168,8 +1264,61 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.P = plan->n_params; a.update_index = update_index;
     a.lr = hp->learning_rate; a.b1 = hp->adam_b1; a.b2 = hp->adam_b2; a.eps = hp->adam_eps;
     a.wd = hp->weight_decay; a.clip = hp->grad_clip;
+    a.comm = pc; a.comm_ppad = comm_ppad(plan->n_params);
     upd_adam_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange: buffer management (CUDA IPC between the one-process-per-GPU ranks)
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan) {
+  if (check_plan_u(plan)) return -1;
+  return static_cast<int64_t>(COMM_GRAD + 2 * comm_ppad(plan->n_params) * sizeof(float));
+}
+
+extern "C" int b200ppo_comm_alloc(int64_t bytes, void** out) {
+  if (!out || bytes <= 0) return B200PPO_EINVAL;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) { cudaFree(p); return static_cast<int>(e); }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { cudaFree(p); return static_cast<int>(e); }
+  *out = p;
+  return 0;
+}
+
+extern "C" int b200ppo_comm_free(void* p) {
+  if (!p) return 0;
+  return static_cast<int>(cudaFree(p));
+}
+
+extern "C" int b200ppo_comm_ipc_get(void* p, uint8_t* handle64) {
+  if (!p || !handle64) return B200PPO_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  std::memcpy(handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int b200ppo_comm_ipc_open(const uint8_t* handle64, void** out) {
+  if (!handle64 || !out) return B200PPO_EINVAL;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  *out = p;
+  return 0;
+}
+
+extern "C" int b200ppo_comm_ipc_close(void* p) {
+  if (!p) return 0;
+  return static_cast<int>(cudaIpcCloseMemHandle(p));
 }

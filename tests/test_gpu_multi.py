@@ -1,0 +1,70 @@
+"""2-GPU checks of the data-parallel engine (needs >= 2 visible GPUs; skipped otherwise).
+
+The peer-memory exchange (epoch flags + P2P loads inside the GAE / loss / Adam kernels,
+include/b200ppo.h) must give the same parameters as the NCCL all-reduce path: with two ranks the
+rank-ordered sum a + b is the same float as NCCL's, so the comparison is bit-exact; and the replicas
+must stay in sync (identical parameters on both ranks).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, p2p, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), B200PPO_P2P="1" if p2p else "0")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import ppo
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_mlp_actor_critic
+    env = SyntheticEnv(24, 4, 16, 2048)
+    nets = make_mlp_actor_critic(24, 4, [64, 64], [128, 128], Rngs(0))
+    ts = ppo.new_training_state(env, nets, 256, 17)
+    hyper = (256, 8, 0.95, 0.99, 0.2, True, False, 2, 4)
+    metrics = None
+    for _ in range(3):                       # iteration 0 eager, 1 captures the graph, 2 replays it
+        ts, metrics = ppo.ppo_step(env, ts, *hyper)
+    eng = ppo._engine_for(env, ts, 256, 8, 0.95, 0.99, 0.2, True, 2, 4, 1.0)
+    assert eng.p2p == bool(p2p)
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"r{rank}_{int(p2p)}.npz"), params=eng.net.arena.cpu().numpy(),
+             mu=eng.opt.mu.cpu().numpy(), m=np.array([float(v) for v in metrics.values()], np.float64))
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)                              # NCCL kernels captured in a graph: skip the slow teardown
+
+
+@pytest.mark.timeout(300)
+def test_peer_exchange_matches_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    res = {}
+    for p2p, port in ((True, 29611), (False, 29612)):
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, p2p, str(tmp_path))) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(240)
+            assert p.exitcode == 0
+        for r in range(2):
+            res[(r, p2p)] = np.load(tmp_path / f"r{r}_{int(p2p)}.npz")
+    for p2p in (True, False):                # replicas in sync
+        np.testing.assert_array_equal(res[(0, p2p)]["params"], res[(1, p2p)]["params"])
+    np.testing.assert_array_equal(res[(0, True)]["params"], res[(0, False)]["params"])
+    np.testing.assert_array_equal(res[(0, True)]["mu"], res[(0, False)]["mu"])
+    np.testing.assert_allclose(res[(0, True)]["m"], res[(0, False)]["m"], rtol=1e-6)
+    assert np.all(np.isfinite(res[(0, True)]["params"]))

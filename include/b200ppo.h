@@ -213,15 +213,17 @@ int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams
 /* -------- peer-memory exchange of the data-parallel update (replaces the two per-update NCCL
  * all-reduces of DESIGN.md section 5: advantage moment sums and the flat gradient) ---------------
  * Every rank owns one comm buffer (cudaMalloc'ed, exported with CUDA IPC) holding epoch flags, the
- * per-rank advantage sums and a double-buffered copy of its locally reduced gradient.  Kernels
- * publish with remote stores + __threadfence_system and wait by spinning on LOCAL flags:
- *   GAE kernel   -> writes its (sum a, sum a^2) into every peer's slot, then the flag;
- *   loss kernel  -> waits for all ranks' flags, sums the slots in rank order;
- *   Adam kernel  -> publishes "gradient ready", waits for all ranks, pulls and sums the peers'
- *                   gradients in rank order (bit-identical parameters on every rank).
+ * per-rank advantage sums and, double-buffered, one gradient slot per source rank.  Everything is
+ * PUSHED (remote stores over NVLink, st.release.sys on the flag); readers poll LOCAL flags with
+ * ld.acquire.sys and read only their own memory:
+ *   GAE kernel    -> writes its (sum a, sum a^2) into every rank's slot, then the flag;
+ *   loss kernel   -> waits for all ranks' flags, sums the slots in rank order;
+ *   reduce kernel -> pushes its locally reduced gradient into every rank's buffer;
+ *   Adam kernel   -> publishes "gradient pushed", waits for all ranks, sums the slots in rank
+ *                    order (bit-identical parameters on every rank).
  * epoch = adam count base + update_index + 1 (monotonic; buffers alternate on its parity).       */
 #define B200PPO_MAX_RANKS 16
-int64_t b200ppo_comm_bytes(const b200ppo_plan* plan);
+int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size);
 int b200ppo_comm_alloc(int64_t bytes, void** out);                 /* zero-initialised device memory */
 int b200ppo_comm_free(void* p);
 int b200ppo_comm_ipc_get(void* p, uint8_t* handle64);              /* 64-byte cudaIpcMemHandle_t     */

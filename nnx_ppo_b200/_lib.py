@@ -82,7 +82,7 @@ SYMBOLS = {
     "b200ppo_update_adv_sums_ptr": (_vp, [_PP, _i32, _i32, _vp]),
     "b200ppo_update_grad_ptr": (_vp, [_PP, _i32, _i32, _vp]),
     "b200ppo_update_debug_ptr": (_vp, [_PP, _i32, _i32, _vp, _i32]),
-    "b200ppo_comm_bytes": (_i64, [_PP]),
+    "b200ppo_comm_bytes": (_i64, [_PP, _i32]),
     "b200ppo_comm_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
     "b200ppo_comm_free": (C.c_int, [_vp]),
     "b200ppo_comm_ipc_get": (C.c_int, [_vp, C.c_char_p]),

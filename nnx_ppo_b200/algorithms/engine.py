@@ -144,7 +144,7 @@ class PPOEngine:
         import torch.distributed as dist
         lib, world = self.lib, self.world
         rank = dist.get_rank(self.group)
-        nbytes = int(lib.b200ppo_comm_bytes(self.net.plan))
+        nbytes = int(lib.b200ppo_comm_bytes(self.net.plan, world))
         if nbytes <= 0 or world > 16:
             raise _lib.B200PPOError("peer exchange: unsupported plan or world size")
         p = C.c_void_p()

@@ -143,7 +143,7 @@ constexpr int MAXR = B200PPO_MAX_RANKS;
 constexpr size_t COMM_FLAG_ADV = 0;                       // uint32[MAXR], written by the peers
 constexpr size_t COMM_FLAG_GRAD = 64;                     // uint32[MAXR]
 constexpr size_t COMM_ADV = 128;                          // double[2 parity][MAXR][2]
-constexpr size_t COMM_GRAD = 1024;                        // float[2 parity][Ppad]
+constexpr size_t COMM_GRAD = 1024;                        // float[2 parity][world][Ppad]: every rank PUSHES its gradient here
 inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n_params)); }
 
 struct PeerComm {
@@ -153,18 +153,26 @@ struct PeerComm {
 __device__ __forceinline__ uint8_t* comm_base(const PeerComm& c, int r) {
   return reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(c.table[r]));
 }
-// spin until every rank's flag (written into OUR buffer by that rank) has reached `epoch`
-__device__ __forceinline__ void comm_wait_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
-  const volatile uint32_t* fl = reinterpret_cast<const volatile uint32_t*>(comm_base(c, c.rank) + flag_off);
-  for (int r = 0; r < c.world; ++r)
-    while (static_cast<int32_t>(fl[r] - epoch) < 0) {}
-  __threadfence_system();
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
-// tell every rank (ourselves included) that our data of `epoch` is in place
-__device__ __forceinline__ void comm_signal_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
-  __threadfence_system();
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until every rank's flag (written into OUR buffer by that rank) has reached `epoch`; the
+// acquire orders the data reads that follow (all data is pushed into our own buffer: no remote loads)
+__device__ __forceinline__ void comm_wait_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
+  const uint32_t* fl = reinterpret_cast<const uint32_t*>(comm_base(c, c.rank) + flag_off);
   for (int r = 0; r < c.world; ++r)
-    *reinterpret_cast<volatile uint32_t*>(comm_base(c, r) + flag_off + 4u * c.rank) = epoch;
+    while (static_cast<int32_t>(ld_acquire_sys(fl + r) - epoch) < 0) {}
+}
+// tell every rank (ourselves included) that our data of `epoch` is in place: release after this
+// thread's own pushes; pushes of an earlier kernel on the stream are ordered by the kernel boundary
+__device__ __forceinline__ void comm_signal_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
+  for (int r = 0; r < c.world; ++r)
+    st_release_sys(reinterpret_cast<uint32_t*>(comm_base(c, r) + flag_off) + c.rank, epoch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -488,8 +496,8 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
       if (a.comm.table != nullptr) {             // ... or every peer gets them through its comm buffer
         const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
         for (int r = 0; r < a.comm.world; ++r) {
-          volatile double* slot = reinterpret_cast<volatile double*>(comm_base(a.comm, r) + COMM_ADV) +
-                                  ((epoch & 1u) * MAXR + a.comm.rank) * 2;
+          double* slot = reinterpret_cast<double*>(comm_base(a.comm, r) + COMM_ADV) +
+                         ((epoch & 1u) * MAXR + a.comm.rank) * 2;
           slot[0] = t1;
           slot[1] = t2;
         }
@@ -528,11 +536,11 @@ __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean,
   if (a.comm.table != nullptr) {
     const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
     comm_wait_all(a.comm, COMM_FLAG_ADV, epoch);
-    const volatile double* slot = reinterpret_cast<const volatile double*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) +
-                                  (epoch & 1u) * MAXR * 2;
+    const double* slot = reinterpret_cast<const double*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) +
+                         (epoch & 1u) * MAXR * 2;
     s1 = 0.0;
     s2 = 0.0;
-    for (int r = 0; r < a.comm.world; ++r) { s1 += slot[2 * r]; s2 += slot[2 * r + 1]; }
+    for (int r = 0; r < a.comm.world; ++r) { s1 += __ldcg(slot + 2 * r); s2 += __ldcg(slot + 2 * r + 1); }
   }
   const double m = s1 / a.n_global;
   double var = s2 / a.n_global - m * m;
@@ -913,8 +921,8 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
 // ------------------------------------------------------------------------------------------
 // RED / grad-norm / ADAM
 // ------------------------------------------------------------------------------------------
-// fixed-order sum of the dW row-split partials.  With the peer exchange the result goes to this
-// rank's comm buffer (slot = epoch parity), where the other ranks' Adam kernels read it.
+// fixed-order sum of the dW row-split partials.  With the peer exchange the result is pushed into
+// every rank's comm buffer (slot = epoch parity, source rank).
 __global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ gpart, int S, int64_t P,
                                                       float* __restrict__ grad, const PeerComm comm,
                                                       const uint32_t* __restrict__ rng_state, int update_index,
@@ -924,8 +932,13 @@ __global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ 
   float g = 0.0f;
   for (int s = 0; s < S; ++s) g += gpart[static_cast<size_t>(s) * P + i];
   if (comm.table != nullptr) {
+    // push: slot [parity][this rank] of EVERY rank's buffer (stores over NVLink are fire-and-forget;
+    // the Adam kernels then read only their own memory)
     const uint32_t epoch = rng_state[3] + static_cast<uint32_t>(update_index) + 1u;
-    grad = reinterpret_cast<float*>(comm_base(comm, comm.rank) + COMM_GRAD) + (epoch & 1u) * ppad;
+    const size_t slot = ((epoch & 1u) * comm.world + comm.rank) * ppad;
+    for (int r = 0; r < comm.world; ++r)
+      (reinterpret_cast<float*>(comm_base(comm, r) + COMM_GRAD) + slot)[i] = g;
+    return;
   }
   grad[i] = g;
 }
@@ -966,7 +979,7 @@ struct AdamArgs {
   int64_t P;
   int update_index;
   float lr, b1, b2, eps, wd, clip;
-  PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of every rank's comm copy
+  PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of the copies every rank pushed here
   size_t comm_ppad;
 };
 
@@ -983,7 +996,10 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   if (a.comm.table != nullptr) {
     // the local reduction (previous kernel on this stream) is complete: publish, then wait for everyone
     if (threadIdx.x == 0) {
-      if (blockIdx.x == 0) comm_signal_all(a.comm, COMM_FLAG_GRAD, epoch);
+      if (blockIdx.x == 0) {
+        __threadfence_system();                  // one thread per launch: the pushes of the reduce kernel are out
+        comm_signal_all(a.comm, COMM_FLAG_GRAD, epoch);
+      }
       comm_wait_all(a.comm, COMM_FLAG_GRAD, epoch);
     }
     __syncthreads();
@@ -992,11 +1008,9 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   float g;
   if (a.comm.table != nullptr) {
     g = 0.0f;
-    for (int r = 0; r < a.comm.world; ++r) {
-      const volatile float* pg = reinterpret_cast<const volatile float*>(comm_base(a.comm, r) + COMM_GRAD) +
-                                 (epoch & 1u) * a.comm_ppad;
-      g += pg[i];
-    }
+    const float* pg = reinterpret_cast<const float*>(comm_base(a.comm, a.comm.rank) + COMM_GRAD) +
+                      (epoch & 1u) * a.comm.world * a.comm_ppad;
+    for (int r = 0; r < a.comm.world; ++r) g += __ldcg(pg + r * a.comm_ppad + i);   // rank order: identical on every rank
     a.grad_out[i] = g;
   } else if (a.S > 0) {
     g = 0.0f;
@@ -1274,9 +1288,9 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
 // ------------------------------------------------------------------------------------------
 // peer-memory exchange: buffer management (CUDA IPC between the one-process-per-GPU ranks)
 // ------------------------------------------------------------------------------------------
-extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan) {
-  if (check_plan_u(plan)) return -1;
-  return static_cast<int64_t>(COMM_GRAD + 2 * comm_ppad(plan->n_params) * sizeof(float));
+extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size) {
+  if (check_plan_u(plan) || world_size < 1 || world_size > MAXR) return -1;
+  return static_cast<int64_t>(COMM_GRAD + 2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(float));
 }
 
 extern "C" int b200ppo_comm_alloc(int64_t bytes, void** out) {

@@ -205,6 +205,10 @@ int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_
 /* finer selection inside BWD (either bit alone runs only that kernel; BWD = both) */
 #define B200PPO_STAGE_BWD_DX 64
 #define B200PPO_STAGE_BWD_DW 128
+/* with FWD: skip the weight pre-split launch of the tensor-core path.  Only valid when the previous
+ * call on this workspace was an update whose ADAM stage ran (it refreshes the split operand planes
+ * together with the parameters) and nothing else has touched `params` since. */
+#define B200PPO_STAGE_NO_PREP 256
 
 int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb);
 int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,

@@ -17,6 +17,7 @@ ACT_IDS = {"none": 0, None: 0, "relu": 1, "swish": 2, "silu": 2, "tanh": 3}
 STAGE_FWD, STAGE_GAE, STAGE_LOSS, STAGE_BWD, STAGE_RED, STAGE_ADAM = 1, 2, 4, 8, 16, 32
 STAGE_ALL = 63
 STAGE_BWD_DX, STAGE_BWD_DW = 64, 128
+STAGE_NO_PREP = 256
 
 
 class Chain(C.Structure):

@@ -123,6 +123,7 @@ class PPOEngine:
         self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory
         # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
+        self.fuse_prep = os.environ.get("B200PPO_FUSE_PREP", "1") != "0"
         self.p2p = False
         self._comm_local, self._comm_peers, self.comm_table = None, [], None
         if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0" and not self.hp.grad_clip > 0.0:
@@ -217,15 +218,18 @@ class PPOEngine:
         n = 0
         _lib.check(lib.b200ppo_permutation(s, self.iter_keys.data_ptr() + 8, B, self.E, self.inds.data_ptr(),
                                            self.perm_scratch.data_ptr()), "permutation"); n += 1
-        per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, _lib.STAGE_ALL))
         for u in range(self.n_updates):
             off = rng_offset0 + u * 2 * (T + 1)
             args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
+            # the Adam kernel of update u-1 refreshed the split weight planes: only the first update
+            # of an iteration (parameters may have been touched from outside) runs the prep launch
+            noprep = _lib.STAGE_NO_PREP if (u > 0 and self.fuse_prep) else 0
+            per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, _lib.STAGE_ALL | noprep))
             if self.world == 1 or self.p2p:
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL), "update")
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL | noprep), "update")
                 n += 1 if self.p2p else 0       # the partial reduction is its own launch on this path
             else:
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE), "update/fwd")
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE | noprep), "update/fwd")
                 if self.hp.normalize_advantages:
                     self._allreduce(self.adv_sums)
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")

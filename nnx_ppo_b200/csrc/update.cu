@@ -981,6 +981,11 @@ struct AdamArgs {
   float lr, b1, b2, eps, wd, clip;
   PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of the copies every rank pushed here
   size_t comm_ppad;
+  // tensor-core path: the updated weight is also re-split into the hi / lo operand planes of the next
+  // update (what upd_prep_w_kernel does from scratch), so that update can skip its prep launch
+  int n_seg;                                   // 0: no refresh
+  float* ws;
+  struct Seg { int64_t w_off; int K, N, prow_f, prow_b; size_t wf_hi, wf_lo, wb_hi, wb_lo; } seg[2 * MAXL];
 };
 
 // optax.adam / adamw (scale_by_adam -> [add_decayed_weights] -> scale(-lr)), optionally preceded by
@@ -1030,7 +1035,22 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   float u = __fdiv_rn(mh, __fadd_rn(sqrtf(vh), a.eps));
   const float p = a.params[i];
   if (a.wd >= 0.0f) u = __fadd_rn(u, __fmul_rn(a.wd, p));
-  a.params[i] = __fadd_rn(p, __fmul_rn(-a.lr, u));
+  const float pn = __fadd_rn(p, __fmul_rn(-a.lr, u));
+  a.params[i] = pn;
+  for (int q = 0; q < a.n_seg; ++q) {
+    const int64_t o = i - a.seg[q].w_off;
+    if (o >= 0 && o < static_cast<int64_t>(a.seg[q].K) * a.seg[q].N) {
+      const int k = static_cast<int>(o / a.seg[q].N), n = static_cast<int>(o - static_cast<int64_t>(k) * a.seg[q].N);
+      const float hi = tc::tf32_round(pn), lo = tc::tf32_round(pn - hi);      // same split as upd_prep_w_kernel
+      const size_t f = (static_cast<size_t>(k >> 2) * a.seg[q].prow_f + n) * 4 + (k & 3);   // Bop(n, k) = W[k][n]
+      const size_t b = (static_cast<size_t>(n >> 2) * a.seg[q].prow_b + k) * 4 + (n & 3);   // Bop(k, n) = W[k][n]
+      a.ws[a.seg[q].wf_hi + f] = hi;
+      a.ws[a.seg[q].wf_lo + f] = lo;
+      a.ws[a.seg[q].wb_hi + b] = hi;
+      a.ws[a.seg[q].wb_lo + b] = lo;
+      break;
+    }
+  }
 }
 
 int check_plan_u(const b200ppo_plan* p) {
@@ -1122,7 +1142,7 @@ extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200p
   const Layout L = make_layout(*plan, T, mb);
   const bool use_tc = gemm_mode() != 0 && L.tc_ok;
   int n = 0;
-  if (stages & B200PPO_STAGE_FWD) n += use_tc ? 2 : 1;
+  if (stages & B200PPO_STAGE_FWD) n += (use_tc && !(stages & B200PPO_STAGE_NO_PREP)) ? 2 : 1;
   if (stages & B200PPO_STAGE_GAE) n += 1;
   if (stages & B200PPO_STAGE_LOSS) n += 1;
   if (stages & B200PPO_STAGE_BWD) n += 2;
@@ -1200,10 +1220,12 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.mean = b->norm_mean; a.std = b->norm_std; a.params = b->params; a.ws = ws;
     a.T = T; a.B = B; a.mb = mb;
     if (use_tc) {
-      PrepArgs pa;
-      pa.plan = *plan; pa.L = L; pa.params = b->params; pa.ws = ws;
-      upd_prep_w_kernel<<<dim3(16, 2 * MAXL, 2), 256, 0, s>>>(pa);
-      B200PPO_LAUNCH_CHECK();
+      if (!(stages & B200PPO_STAGE_NO_PREP)) {
+        PrepArgs pa;
+        pa.plan = *plan; pa.L = L; pa.params = b->params; pa.ws = ws;
+        upd_prep_w_kernel<<<dim3(16, 2 * MAXL, 2), 256, 0, s>>>(pa);
+        B200PPO_LAUNCH_CHECK();
+      }
       upd_fwd_tc_kernel<<<cdiv(L.Rv, TCM), TCT, TC_SMEM, s>>>(a, tc_split);
     } else {
       upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
@@ -1279,6 +1301,19 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.lr = hp->learning_rate; a.b1 = hp->adam_b1; a.b2 = hp->adam_b2; a.eps = hp->adam_eps;
     a.wd = hp->weight_decay; a.clip = hp->grad_clip;
     a.comm = pc; a.comm_ppad = comm_ppad(plan->n_params);
+    a.n_seg = 0; a.ws = ws;
+    if (use_tc) {
+      for (int c = 0; c < 2; ++c) {
+        const b200ppo_chain& ch = c == 0 ? plan->actor : plan->critic;
+        const TcLayer* tl = c == 0 ? L.tca : L.tcc;
+        for (int l = 0; l < ch.n_layers; ++l) {
+          AdamArgs::Seg& g = a.seg[a.n_seg++];
+          g.w_off = ch.w_off[l]; g.K = ch.dims[l]; g.N = ch.dims[l + 1];
+          g.prow_f = tl[l].npad + 1; g.prow_b = tl[l].kout_pad + 1;
+          g.wf_hi = tl[l].wf_hi; g.wf_lo = tl[l].wf_lo; g.wb_hi = tl[l].wb_hi; g.wb_lo = tl[l].wb_lo;
+        }
+      }
+    }
     upd_adam_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }

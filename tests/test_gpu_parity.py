@@ -432,6 +432,24 @@ def _iterations(dev, cfg):
     assert eng.graph is not None            # iterations >= 2 ran from the captured CUDA graph
 
 
+def test_adam_refreshes_split_weight_planes(dev, monkeypatch):
+    """The Adam kernel re-splits the updated weights into the tensor-core operand planes, so updates
+    2..E*M skip the prep launch (B200PPO_STAGE_NO_PREP): must be bit-identical to always prepping."""
+    res = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("B200PPO_FUSE_PREP", fuse)
+        nets, _ = _pair(40, 6, [64, 48], [96, 32], 0)
+        env = SyntheticEnv(40, 6, max_len=48, term_thresh16=700)
+        ts = ppo.new_training_state(env, nets, 128, 17)
+        net = compile_network(nets)
+        for _ in range(3):
+            ts, _m = ppo.ppo_step(env, ts, 128, 8, 0.95, 0.99, 0.2, True, False, 2, 4)
+        eng = next(iter(net.engines.values()))
+        assert eng.fuse_prep == (fuse == "1")
+        res.append(net.arena.cpu().numpy().copy())
+    assert np.array_equal(res[0], res[1])
+
+
 def test_train_ppo_api(dev):
     """ppo_test.py:213-227 / 307-349 style: total steps, counter, finite metrics, log cadence."""
     env = SyntheticEnv(16, 4, max_len=32)

@@ -657,7 +657,10 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
   }
 }
 
-__global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, const int split) {
+// chains: bit 0 = critic, bit 1 = actor.  The host launches the two chains as two kernels on forked
+// streams (they are independent until the loss), so GAE overlaps the actor chain and the block
+// scheduler back-fills SMs the other kernel leaves idle; both kernels write the same xhat values.
+__global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, const int split, const int chains) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
@@ -711,8 +714,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   }
   __syncthreads();
   tc_stamp(cx.nstamp);
-  tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, sm);
-  if (row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, sm);
+  if (chains & 1) tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, sm);
+  if ((chains & 2) && row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, sm);
   tc_ctx_fini(cx);
 }
 
@@ -837,7 +840,7 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
   }
 }
 
-__global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, const int split) {
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, const int split, const int chains) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
@@ -845,8 +848,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, 
   tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
   const int row0 = blockIdx.x * TCM;
   tc_stamp(cx.nstamp);
-  tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
-  tc_chain_backward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.da, row0, a.L.R, split);
+  if (chains & 1) tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
+  if (chains & 2) tc_chain_backward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.da, row0, a.L.R, split);
   tc_ctx_fini(cx);
 }
 
@@ -857,12 +860,12 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, 
 // staged by the producer warps.  The threads that stage column n of dpre also accumulate its sum:
 // the bias gradient.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, const int split) {
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, const int split, const int item_base) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[TC_NPROD];
-  int item = blockIdx.x;
+  int item = blockIdx.x + item_base;   // items: actor M-tiles first, then critic (the host may launch the chains separately)
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
   const size_t* doff = a.L.da;
@@ -1044,13 +1047,13 @@ constexpr uint32_t DW2_RAW_B = TCK * TC_MAXN * 4u;           // 16 rows x <= 256
 constexpr uint32_t DW2_RAW_BYTES = DW2_RAW_A + DW2_RAW_B;
 constexpr uint32_t DW2_SMEM = DW2_NS * TC_STAGE_BYTES + DW2_NR * DW2_RAW_BYTES;
 
-__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split) {
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split, const int item_base) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint64_t rbar[2 * DW2_NR];                      // [0..NR) raw full, [NR..2NR) raw empty
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[2][TC_NPROD];
-  int item = blockIdx.x;
+  int item = blockIdx.x + item_base;   // items: actor M-tiles first, then critic (the host may launch the chains separately)
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
   const size_t* doff = a.L.da;

@@ -660,7 +660,10 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
 // chains: bit 0 = critic, bit 1 = actor.  The host launches the two chains as two kernels on forked
 // streams (they are independent until the loss), so GAE overlaps the actor chain and the block
 // scheduler back-fills SMs the other kernel leaves idle; both kernels write the same xhat values.
-__global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, const int split, const int chains) {
+// tile_rows <= 128: rows of the minibatch per CTA.  The MMAs always run M = 128; a CTA just owns fewer
+// live rows, so that the grid covers all SMs (16 384 rows / 128 = 128 CTAs would leave 20 of 148 SMs idle).
+__global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, const int split, const int chains,
+                                                            const int tile_rows) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
@@ -669,8 +672,9 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
   const int O = a.plan.obs_dim;
-  const int row0 = blockIdx.x * TCM;
-  const int R = a.L.R, Rv = a.L.Rv;
+  const int row0 = blockIdx.x * tile_rows;
+  const int rend = row0 + tile_rows;
+  const int R = a.L.R < rend ? a.L.R : rend, Rv = a.L.Rv < rend ? a.L.Rv : rend;   // clipped to this tile
   float* xhat = a.ws + a.L.xhat;
   for (int m = threadIdx.x; m < TCM; m += TCT) {
     const int r = row0 + m;
@@ -678,8 +682,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
     if (r < R) {
       const int t = r / a.mb, j = r - t * a.mb;
       src = a.obs + (static_cast<size_t>(t) * a.B + a.inds[j]) * O;
-    } else if (r < Rv) {
-      src = a.next_obs_last + static_cast<size_t>(a.inds[r - R]) * O;
+    } else if (r >= a.L.R && r < Rv) {
+      src = a.next_obs_last + static_cast<size_t>(a.inds[r - a.L.R]) * O;
     }
     rowsrc[m] = src;
   }
@@ -840,16 +844,18 @@ __device__ __forceinline__ void tc_chain_backward(TcCtx& cx, const b200ppo_chain
   }
 }
 
-__global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, const int split, const int chains) {
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, const int split, const int chains,
+                                                               const int tile_rows) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
-  const int row0 = blockIdx.x * TCM;
+  const int row0 = blockIdx.x * tile_rows;
   tc_stamp(cx.nstamp);
-  if (chains & 1) tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, a.L.R, split);
-  if (chains & 2) tc_chain_backward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.da, row0, a.L.R, split);
+  const int rend = (row0 + tile_rows) < a.L.R ? (row0 + tile_rows) : a.L.R;        // this tile's live rows
+  if (chains & 1) tc_chain_backward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.dc, row0, rend, split);
+  if (chains & 2) tc_chain_backward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.da, row0, rend, split);
   tc_ctx_fini(cx);
 }
 

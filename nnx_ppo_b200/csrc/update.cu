@@ -1248,6 +1248,13 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + L.tickets);
   ForkRes* fk = use_tc ? get_fork(s) : nullptr;
   bool fwd_forked = false;
+  // rows per CTA of the row-tiled tensor-core kernels: spread the minibatch over all SMs
+  auto tile_for = [](int rows) {
+    int t = cdiv(rows, b200ppo_num_sms());
+    t = t < 32 ? 32 : t;
+    return t > TCM ? TCM : t;
+  };
+  const int tile_f = tile_for(L.Rv), tile_b = tile_for(L.R);
 
   if (stages & B200PPO_STAGE_FWD) {
     FwdArgs a;
@@ -1265,13 +1272,13 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
         // actor chain on the second stream; critic chain (then GAE) on this one; joined before the loss
         if (cudaEventRecord(fk->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(fk->aux, fk->ev[0], 0) != cudaSuccess)
           return static_cast<int>(cudaGetLastError());
-        upd_fwd_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2);
+        upd_fwd_tc_kernel<<<cdiv(L.R, tile_f), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2, tile_f);
         B200PPO_LAUNCH_CHECK();
         if (cudaEventRecord(fk->ev[1], fk->aux) != cudaSuccess) return static_cast<int>(cudaGetLastError());
-        upd_fwd_tc_kernel<<<cdiv(L.Rv, TCM), TCT, TC_SMEM, s>>>(a, tc_split, 1);
+        upd_fwd_tc_kernel<<<cdiv(L.Rv, tile_f), TCT, TC_SMEM, s>>>(a, tc_split, 1, tile_f);
         fwd_forked = true;
       } else {
-        upd_fwd_tc_kernel<<<cdiv(L.Rv, TCM), TCT, TC_SMEM, s>>>(a, tc_split, 3);
+        upd_fwd_tc_kernel<<<cdiv(L.Rv, tile_f), TCT, TC_SMEM, s>>>(a, tc_split, 3, tile_f);
       }
     } else {
       upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
@@ -1321,9 +1328,9 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
         // actor dX -> actor dW on the second stream, critic dX -> critic dW on this one
         if (cudaEventRecord(fk->ev[2], s) != cudaSuccess || cudaStreamWaitEvent(fk->aux, fk->ev[2], 0) != cudaSuccess)
           return static_cast<int>(cudaGetLastError());
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split, 1);
+        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, s>>>(a, tc_split, 1, tile_b);
         B200PPO_LAUNCH_CHECK();
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2);
+        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2, tile_b);
         B200PPO_LAUNCH_CHECK();
         if (do_dw) launch_dw(s, items_actor, items_critic);
         B200PPO_LAUNCH_CHECK();
@@ -1332,7 +1339,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
         if (cudaEventRecord(fk->ev[3], fk->aux) != cudaSuccess || cudaStreamWaitEvent(s, fk->ev[3], 0) != cudaSuccess)
           return static_cast<int>(cudaGetLastError());
       } else {
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, TCM), TCT, TC_SMEM, s>>>(a, tc_split, 3);
+        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, s>>>(a, tc_split, 3, tile_b);
         B200PPO_LAUNCH_CHECK();
         if (do_dw) launch_dw(s, 0, L.tc_tiles);
         B200PPO_LAUNCH_CHECK();

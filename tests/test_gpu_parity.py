@@ -450,6 +450,40 @@ def test_adam_refreshes_split_weight_planes(dev, monkeypatch):
     assert np.array_equal(res[0], res[1])
 
 
+def test_full_size_iteration_properties(dev):
+    """BASELINE configs[1] at full size (4096 envs x 32 steps, 4 epochs x 8 minibatches): the oracle
+    needs minutes here, so check size-independent properties instead — two runs from the same seed
+    are bit-identical (fixed-order reductions everywhere), every minibatch is a permutation slice,
+    masks are consistent, counters / step bookkeeping are exact, everything stays finite."""
+    B, T, E, M = 4096, 32, 4, 8
+    runs = []
+    for _ in range(2):
+        nets, _o = _pair(64, 8, [64] * 4, [256] * 2, 0)
+        env = SyntheticEnv(64, 8, max_len=64, term_thresh16=512)
+        ts = ppo.new_training_state(env, nets, B, 17)
+        net = compile_network(nets)
+        for _it in range(3):
+            ts, m = ppo.ppo_step(env, ts, B, T, 0.95, 0.99, 0.2, True, False, E, M)
+        eng = next(iter(net.engines.values()))
+        runs.append(dict(p=net.arena.cpu().numpy().copy(), inds=eng.inds.cpu().numpy().copy(),
+                         done=eng.done.cpu().numpy().copy(), trunc=eng.trunc.cpu().numpy().copy(),
+                         mean=net.normalizer.mean.numpy().copy(), m=dict(m), cnt=u32(net.counters).copy(),
+                         steps=float(ts.steps_taken), ncount=float(net.normalizer.counter.numpy()[0])))
+    a, b = runs
+    assert np.array_equal(a["p"], b["p"]) and np.array_equal(a["mean"], b["mean"])      # deterministic
+    assert np.array_equal(a["inds"], b["inds"]) and np.array_equal(a["done"], b["done"])
+    for e in range(E):                                                                  # permutations
+        assert np.array_equal(np.sort(a["inds"][e]), np.arange(B))
+    assert not np.any(a["trunc"].astype(bool) & ~a["done"].astype(bool))                # truncated => done
+    assert 0.005 < a["done"].mean() < 0.2
+    assert a["steps"] == 3 * T * B == a["ncount"]
+    assert a["cnt"][3] == 3 * E * M                                                     # Adam count
+    assert a["cnt"][2] - u32(compile_network(_pair(64, 8, [64] * 4, [256] * 2, 0)[0]).counters)[2] == \
+        3 * (2 * T + E * M * 2 * (T + 1))                                               # sampler draws per iteration
+    assert np.all(np.isfinite(a["p"])) and all(np.isfinite(v) for v in a["m"].values())
+    assert eng.graph is not None
+
+
 def test_train_ppo_api(dev):
     """ppo_test.py:213-227 / 307-349 style: total steps, counter, finite metrics, log cadence."""
     env = SyntheticEnv(16, 4, max_len=32)

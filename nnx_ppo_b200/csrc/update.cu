@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -165,8 +166,18 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 // acquire orders the data reads that follow (all data is pushed into our own buffer: no remote loads)
 __device__ __forceinline__ void comm_wait_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
   const uint32_t* fl = reinterpret_cast<const uint32_t*>(comm_base(c, c.rank) + flag_off);
-  for (int r = 0; r < c.world; ++r)
-    while (static_cast<int32_t>(ld_acquire_sys(fl + r) - epoch) < 0) {}
+  for (int r = 0; r < c.world; ++r) {
+    // bounded: a peer that died must not hang this GPU forever (about a minute of polling, then trap,
+    // which surfaces as a launch failure on the host)
+    unsigned long long spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(fl + r) - epoch) < 0) {
+      if (++spins > (1ull << 27)) {
+        printf("b200ppo: rank %d waited too long for rank %d (flag offset %llu, epoch %u)\n", c.rank, r,
+               static_cast<unsigned long long>(flag_off), epoch);
+        __trap();
+      }
+    }
+  }
 }
 // tell every rank (ourselves included) that our data of `epoch` is in place: release after this
 // thread's own pushes; pushes of an earlier kernel on the stream are ordered by the kernel boundary

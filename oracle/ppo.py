@@ -103,33 +103,20 @@ def _chain_backward(chain, x0, zs, d_out):
     return dWs, dbs
 
 
-def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_count_base: int,
-                       clip_range=0.2, normalize_advantages=True, discounting_factor=0.99,
-                       gae_lambda=0.95, critic_loss_weight=1.0, want_grads=True,
-                       n_global: Optional[int] = None, adv_stats=None):
-    """Loss (and flat analytic gradient) of one minibatch, restating ``ppo_loss``.
-
-    ``rng_count_base`` is the sampler stream count at the start of this loss call; replay step t
-    consumes counts base+2t (unused sample draw) and base+2t+1 (entropy noise), the bootstrap
-    call consumes two more (``sampling_layers.py:96,143-145``; ``ppo.py:425-436``).
-    ``n_global`` / ``adv_stats`` let a data-parallel caller use global means (defaults: local).
-    """
+def loss_head(net, ro: Rollout, inds: np.ndarray, rng_count_base: int, y, v, v_last,
+              clip_range=0.2, normalize_advantages=True, discounting_factor=0.99, gae_lambda=0.95,
+              critic_loss_weight=1.0, want_grads=True, n_global: Optional[int] = None, adv_stats=None):
+    """Everything of ``ppo_loss`` downstream of the network outputs (ppo.py:447-531): sampler
+    log-lik / entropy, GAE, advantage normalisation, clipped surrogate, value loss — and the
+    analytic gradients w.r.t. the actor output ``y`` [T*mb, 2A] and the values ``v`` [T*mb].
+    Shared by the MLP path below and the recurrent path (oracle/recurrent.py)."""
     T = ro.obs.shape[0]
     mb = inds.shape[0]
     A = net.act_dim
     N = T * mb
     Ng = F(N if n_global is None else n_global)
-    obs = ro.obs[:, inds].reshape(N, -1)
     z = ro.raw_action[:, inds].reshape(N, A)
     ll_old = ro.loglik[:, inds].reshape(N)
-
-    x = net.normalize_obs(obs)
-    y, zs_a = net.actor.forward(x, keep=True)
-    v, zs_c = net.critic.forward(x, keep=True)
-    v = v[:, 0]
-    x_last = net.normalize_obs(ro.next_obs_last[inds])
-    v_last = net.critic.forward(x_last)[0][:, 0]                       # ppo.py:433-437
-
     mu, rho = y[:, :A], y[:, A:]
     sigma = sampler_std(rho, net.min_std, net.std_scale)
     ll = loglikelihood(z, mu, sigma)
@@ -166,7 +153,7 @@ def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_coun
                "adv_std": adv.std(dtype=F), "adv": adv.reshape(T, mb), "values": v.reshape(T, mb),
                "v_last": v_last, "loglik": ll.reshape(T, mb), "eps2": eps2.reshape(T, mb, A)}
     if not want_grads:
-        return total, metrics, None
+        return total, metrics, None, None
 
     # ---- analytic backward (JAX tie rules: minimum / clip split the gradient 0.5/0.5) ----
     w1 = np.where(c1 < c2, F(1), np.where(c1 == c2, F(0.5), F(0)))
@@ -185,7 +172,36 @@ def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_coun
     d_rho = (d_sig * sigmoid(rho) * F(net.std_scale)).astype(F)
     d_y = np.concatenate([d_mu, d_rho], axis=1).astype(F)
     d_v = (F(critic_loss_weight) * diff / Ng).astype(F)[:, None]
+    metrics["d_y"], metrics["d_v"] = d_y, d_v[:, 0]
+    return total, metrics, d_y, d_v
 
+
+def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_count_base: int,
+                       clip_range=0.2, normalize_advantages=True, discounting_factor=0.99,
+                       gae_lambda=0.95, critic_loss_weight=1.0, want_grads=True,
+                       n_global: Optional[int] = None, adv_stats=None):
+    """Loss (and flat analytic gradient) of one minibatch, restating ``ppo_loss``.
+
+    ``rng_count_base`` is the sampler stream count at the start of this loss call; replay step t
+    consumes counts base+2t (unused sample draw) and base+2t+1 (entropy noise), the bootstrap
+    call consumes two more (``sampling_layers.py:96,143-145``; ``ppo.py:425-436``).
+    ``n_global`` / ``adv_stats`` let a data-parallel caller use global means (defaults: local).
+    """
+    T = ro.obs.shape[0]
+    mb = inds.shape[0]
+    N = T * mb
+    obs = ro.obs[:, inds].reshape(N, -1)
+    x = net.normalize_obs(obs)
+    y, zs_a = net.actor.forward(x, keep=True)
+    v, zs_c = net.critic.forward(x, keep=True)
+    v = v[:, 0]
+    x_last = net.normalize_obs(ro.next_obs_last[inds])
+    v_last = net.critic.forward(x_last)[0][:, 0]                       # ppo.py:433-437
+    total, metrics, d_y, d_v = loss_head(net, ro, inds, rng_count_base, y, v, v_last, clip_range,
+                                         normalize_advantages, discounting_factor, gae_lambda,
+                                         critic_loss_weight, want_grads, n_global, adv_stats)
+    if not want_grads:
+        return total, metrics, None
     dWa, dba = _chain_backward(net.actor, x, zs_a, d_y)
     dWc, dbc = _chain_backward(net.critic, x, zs_c, d_v)
     parts = []
@@ -193,7 +209,6 @@ def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_coun
         for dW, db in zip(dWs, dbs):
             parts += [dW.ravel(), db.ravel()]
     grads = np.concatenate(parts).astype(F)
-    metrics["d_y"], metrics["d_v"] = d_y, d_v[:, 0]
     return total, metrics, grads
 
 

@@ -234,6 +234,40 @@ int b200ppo_comm_ipc_get(void* p, uint8_t* handle64);              /* 64-byte cu
 int b200ppo_comm_ipc_open(const uint8_t* handle64, void** out);
 int b200ppo_comm_ipc_close(void* p);
 
+/* -------- recurrent actor: one time step of obs -> Normalizer -> Dense(act) -> LSTM -> Dense ------
+ * Replaces, per time step, `networks(state, obs)` for an actor built as
+ * Sequential([Dense, LSTM, Dense]) (networks/recurrent.py:89-161 over flax's OptimizedLSTMCell;
+ * the architecture of recurrent_test.py:245-258) in the rollout (rollout.py:18) and in the replay
+ * scan of ppo_loss (ppo.py:409-431), and its reverse-mode step.  Gate order (i, f, g, o); the LSTM
+ * kernels are stored as one matrix Wcat = [Wi; Wh] ([pre_dim + hidden, 4*hidden], row-major) with
+ * the hidden kernels' bias [4*hidden].  After a forward step the carry of rows whose `done` flag is
+ * set is zeroed (reset_state); the backward step applies the same mask to the incoming carry
+ * gradient, so nothing flows across an episode boundary.  The host loops over time. */
+typedef struct b200ppo_lstm_plan {
+  int32_t obs_dim, pre_dim, hidden, out_dim;   /* out_dim = 2 * action_size                       */
+  int32_t act;                                  /* activation of the pre Dense (B200PPO_ACT_*)     */
+  int32_t normalize;
+  int64_t w1_off, b1_off;                       /* pre Dense  [obs_dim, pre_dim], [pre_dim]        */
+  int64_t wcat_off, bl_off;                     /* LSTM       [pre_dim + hidden, 4 hidden], [4 hidden] */
+  int64_t w2_off, b2_off;                       /* post Dense [hidden, out_dim], [out_dim]         */
+  int64_t n_params;
+} b200ppo_lstm_plan;
+/* floats of the per-step activation cache the backward step needs, for `rows` rows */
+int64_t b200ppo_lstm_cache_floats(const b200ppo_lstm_plan* plan, int32_t rows);
+/* obs: dev [.][obs_dim]; row j reads obs[inds ? inds[j] : j]; done (nullable): dev uint8, indexed
+ * like obs; c, h: dev [rows][hidden] carry, updated in place; y: dev [rows][out_dim];
+ * cache (nullable): dev, b200ppo_lstm_cache_floats() floats. */
+int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                          const float* norm_mean, const float* norm_std, const float* obs,
+                          const int32_t* inds, const uint8_t* done, int32_t rows, float* c, float* h,
+                          float* y, float* cache);
+/* d_y: dev [rows][out_dim]; dc, dh: dev [rows][hidden], on entry the gradient w.r.t. the carry this
+ * step handed on (zeros for the last step), on exit w.r.t. the carry it received; grad: dev
+ * [n_params], accumulated with atomics (zero it before the first step). */
+int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                          const float* d_y, const float* cache, const int32_t* inds,
+                          const uint8_t* done, int32_t rows, float* dc, float* dh, float* grad);
+
 /* GEMM engine of the update: 0 = fp32 FFMA on CUDA cores, 1 = tcgen05 3xTF32 (default; error-   *
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */

@@ -46,6 +46,13 @@ class UpdateBufs(C.Structure):
         "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm")]
 
 
+class LstmPlan(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("pre_dim", C.c_int32), ("hidden", C.c_int32), ("out_dim", C.c_int32),
+                ("act", C.c_int32), ("normalize", C.c_int32),
+                ("w1_off", C.c_int64), ("b1_off", C.c_int64), ("wcat_off", C.c_int64), ("bl_off", C.c_int64),
+                ("w2_off", C.c_int64), ("b2_off", C.c_int64), ("n_params", C.c_int64)]
+
+
 class SynthEnv(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("max_len", C.c_int32),
                 ("term_thresh16", C.c_int32), ("Wo", C.c_void_p), ("Wa", C.c_void_p)]
@@ -89,6 +96,9 @@ SYMBOLS = {
     "b200ppo_comm_ipc_get": (C.c_int, [_vp, C.c_char_p]),
     "b200ppo_comm_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "b200ppo_comm_ipc_close": (C.c_int, [_vp]),
+    "b200ppo_lstm_cache_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
+    "b200ppo_lstm_step_fwd": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "b200ppo_lstm_step_bwd": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
     "b200ppo_tc_microbench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),

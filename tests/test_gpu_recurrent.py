@@ -1,0 +1,106 @@
+"""GPU parity of the recurrent-actor step kernels (csrc/recurrent.cu) against oracle/recurrent.py:
+the replay forward over T steps from the minibatch's start carry with the rollout's resets, and the
+BPTT backward fed with the oracle's d loss / d y.  SURVEY section 8 row a15 (first CUDA path; the
+public-API integration of recurrent networks is the next step)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from nnx_ppo_b200 import _lib                                    # noqa: E402
+from oracle import env as oenv, prng, recurrent as orec          # noqa: E402
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def _plan(net):
+    """flat layout = RecurrentActorCritic.param_list(): W1, b1, Wi, Wh, bl, W2, b2, critic..."""
+    p = _lib.LstmPlan()
+    O, P, H, Y = net.obs_dim, net.pre.W[0].shape[1], net.lstm.hidden, net.post.W[0].shape[1]
+    p.obs_dim, p.pre_dim, p.hidden, p.out_dim = O, P, H, Y
+    p.act, p.normalize = net.pre.act, 1 if net.normalize else 0
+    o = 0
+    p.w1_off = o; o += O * P
+    p.b1_off = o; o += P
+    p.wcat_off = o; o += (P + H) * 4 * H
+    p.bl_off = o; o += 4 * H
+    p.w2_off = o; o += H * Y
+    p.b2_off = o; o += Y
+    p.n_params = net.flat_params().size
+    return p, o
+
+
+@pytest.mark.parametrize("cfg", [dict(O=10, A=3, B=12, T=9, P=7, H=8, act="tanh", mb=[0, 3, 4, 7, 9, 11]),
+                                 dict(O=64, A=8, B=40, T=16, P=64, H=256, act="relu", mb=list(range(0, 40, 2))),
+                                 dict(O=16, A=4, B=37, T=20, P=32, H=32, act="relu", mb=list(range(37)))])
+def test_recurrent_replay_and_bptt_match_oracle(cuda_device, cfg):
+    import torch
+    dev = cuda_device
+    lib = _lib.load()
+    O, A, B, T, H = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["H"]
+    net = orec.make_recurrent_actor_critic(O, A, [cfg["P"]], H, [], [6], seed=3, activation=cfg["act"])
+    e = oenv.SyntheticEnv(O, A, max_len=6, term_thresh16=9000)
+    es = e.reset(prng.split(prng.key(5), B))
+    es, carry, ro, start = orec.unroll_env(e, es, net, net.initialize_state(B), T, prng.key(11))
+    net.update_statistics(ro.obs)                                 # a non-trivial normaliser
+    assert ro.done.sum() > 0
+    inds = np.asarray(cfg["mb"], np.int32)
+    mb = len(inds)
+    base = net.rng_count
+    total, m, g_ref = orec.ppo_loss_and_grads(net, ro, start, inds, base)
+
+    plan, n_rec = _plan(net)
+    t = lambda a, dt=torch.float32: torch.tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    params = t(net.flat_params())
+    mean, std = t(net.mean), t(net.norm_std())
+    obs, done = t(ro.obs), t(ro.done.astype(np.uint8), torch.uint8)
+    ind_d = t(inds, torch.int32)
+    c, h = t(start[0][inds]), t(start[1][inds])
+    Y = 2 * A
+    y = torch.zeros(T, mb, Y, device=dev)
+    cf = int(lib.b200ppo_lstm_cache_floats(plan, mb))
+    cache = torch.zeros(T, cf, device=dev)
+    s = _lib.current_stream()
+    for k in range(T):
+        _lib.check(lib.b200ppo_lstm_step_fwd(s, plan, params.data_ptr(), mean.data_ptr(), std.data_ptr(),
+                                             obs[k].data_ptr(), ind_d.data_ptr(), done[k].data_ptr(), mb,
+                                             c.data_ptr(), h.data_ptr(), y[k].data_ptr(), cache[k].data_ptr()), "fwd")
+    torch.cuda.synchronize()
+    # replay forward: actor outputs of every step (the oracle's loss consumed exactly these)
+    A2 = m["loglik"].shape                                       # (T, mb)
+    y_ref = None
+    # recompute the oracle's y through its own step function
+    cc, hh = start[0][inds].copy(), start[1][inds].copy()
+    ys = []
+    xs = net.normalize_obs(ro.obs[:, inds].reshape(T * mb, -1)).reshape(T, mb, -1)
+    for k in range(T):
+        cc, hh, yk, _ = orec.actor_step(net, cc, hh, xs[k])
+        ys.append(yk)
+        keep = (~ro.done[k, inds])[:, None]
+        cc, hh = cc * keep, hh * keep
+    y_ref = np.stack(ys)
+    assert np.abs(y.cpu().numpy() - y_ref).max() < 2e-5 * max(1.0, np.abs(y_ref).max())
+    assert np.abs(c.cpu().numpy() - cc).max() < 2e-5 and np.abs(h.cpu().numpy() - hh).max() < 2e-5
+    d_last = ro.done[-1, inds]
+    assert np.all(c.cpu().numpy()[d_last] == 0) and np.all(h.cpu().numpy()[d_last] == 0)     # reset: exact zeros
+
+    # BPTT with the oracle's d loss / d y
+    d_y = t(m["d_y"].reshape(T, mb, Y))
+    grad = torch.zeros(plan.n_params, device=dev)
+    dc, dh = torch.zeros(mb, H, device=dev), torch.zeros(mb, H, device=dev)
+    for k in reversed(range(T)):
+        _lib.check(lib.b200ppo_lstm_step_bwd(s, plan, params.data_ptr(), d_y[k].data_ptr(), cache[k].data_ptr(),
+                                             ind_d.data_ptr(), done[k].data_ptr(), mb, dc.data_ptr(), dh.data_ptr(),
+                                             grad.data_ptr()), "bwd")
+    torch.cuda.synchronize()
+    g = grad.cpu().numpy()[:n_rec]
+    ref = g_ref[:n_rec]
+    scale = np.abs(ref).max()
+    assert np.abs(g - ref).max() < 3e-4 * scale, (np.abs(g - ref).max(), scale)
+    assert np.all(grad.cpu().numpy()[n_rec:] == 0)               # the critic's slots are not touched here

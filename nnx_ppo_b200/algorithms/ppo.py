@@ -81,6 +81,11 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
     optimizer moments and Normalizer statistics are updated in place on the device."""
     if combine_advantages:
         raise NotImplementedError("combine_advantages needs dict rewards; single scalar reward only")
+    if compile_network(training_state.networks).recurrent:
+        from . import recurrent as _rec
+        return _rec.ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda,
+                                       discounting_factor, clip_range, normalize_advantages, n_epochs,
+                                       n_minibatches, critic_loss_weight, logging_level, logging_percentiles)
     if not getattr(env, "fused_rollout", False):
         return rollout.ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda,
                                         discounting_factor, clip_range, normalize_advantages,

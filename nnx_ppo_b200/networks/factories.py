@@ -54,3 +54,29 @@ def make_mlp_actor_critic(obs_size: int, action_size: int, actor_hidden_sizes: l
     if normalize_obs:
         return Sequential([Normalizer(obs_size), adapter])
     return adapter
+
+
+def make_recurrent_actor_critic(obs_size: int, action_size: int, pre_size: int, lstm_hidden: int,
+                                critic_hidden_sizes: list[int], rngs: prng.Rngs,
+                                activation: Union[Callable, str] = feedforward.relu,
+                                normalize_obs: bool = True, entropy_weight: float = 1e-2,
+                                min_std: float = 1e-1, std_scale: float = 1.0) -> StatefulModule:
+    """Actor Dense(act) -> LSTM -> Dense with an MLP critic, the network of the reference's
+    recurrent_test.py:245-258 wrapped like make_mlp_actor_critic (Normalizer + PPOAdapter)."""
+    from .recurrent import LSTM
+    if isinstance(activation, str):
+        activation = {"swish": feedforward.swish, "tanh": feedforward.tanh, "relu": feedforward.relu}[activation]
+
+    def kernel_init(key, shape):
+        return prng.variance_scaling_uniform(key, shape[0], shape[1], 1.0)
+
+    actor = [feedforward.Dense(obs_size, pre_size, rngs, activation=activation, kernel_init=kernel_init),
+             LSTM(pre_size, lstm_hidden, rngs),
+             feedforward.Dense(lstm_hidden, action_size * 2, rngs, activation=None, kernel_init=kernel_init)]
+    critic = make_mlp([obs_size] + list(critic_hidden_sizes) + [1], rngs, activation,
+                      activation_last_layer=False, kernel_init=kernel_init)
+    sampler = NormalTanhSampler(rngs, entropy_weight=entropy_weight, min_std=min_std, std_scale=std_scale)
+    adapter = PPOAdapter(action=Sequential([*actor, sampler]), value=critic)
+    if normalize_obs:
+        return Sequential([Normalizer(obs_size), adapter])
+    return adapter

@@ -28,6 +28,7 @@ def _align4(n: int) -> int:
 
 class CompiledNet:
     """Device-side view of one actor-critic network."""
+    recurrent = False
 
     def __init__(self, network: StatefulModule, device):
         import torch
@@ -177,7 +178,8 @@ def compile_network(network: StatefulModule, device=None) -> CompiledNet:
             raise _lib.B200PPOError("no CUDA device: the B200 PPO path has no CPU fallback")
         device = torch.device("cuda", torch.cuda.current_device())
     _lib.load()
-    c = CompiledNet(network, device)
+    from . import rplan
+    c = rplan.RecurrentCompiledNet(network, device) if rplan.is_recurrent(network) else CompiledNet(network, device)
     network._b200_compiled = c
     return c
 

@@ -1,0 +1,41 @@
+"""LSTM layer — mirrors nnx_ppo/networks/recurrent.py:16-161 (flax ``OptimizedLSTMCell`` underneath).
+
+Parameters: ``kernel_i`` [in, 4H] (the four input kernels ii|if|ig|io, no bias), ``kernel_h`` [H, 4H]
+(hi|hf|hg|ho) and their ``bias`` [4H].  The carry is the reference's 2-tuple of [B, H] arrays, zeros
+at start and after a reset (``trainable_initial_state`` is not supported).  Initialisation: uniform
+variance scaling for both kernels (flax's lecun-normal / orthogonal defaults cannot be reproduced
+bit-for-bit without jax).  The arithmetic runs in csrc/recurrent.cu.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import prng
+from .feedforward import Param
+from .types import StatefulModule
+
+
+class LSTM(StatefulModule):
+    def __init__(self, in_features: int, hidden_features: int, rngs: prng.Rngs, *,
+                 trainable_initial_state: bool = False, **unsupported):
+        if trainable_initial_state:
+            raise NotImplementedError("trainable_initial_state is not supported by the B200 plan")
+        bad = {k: v for k, v in unsupported.items() if v is not None and k not in ("use_optimized",)}
+        if bad:
+            raise NotImplementedError(f"unsupported LSTM options: {sorted(bad)}")
+        self.in_features = in_features
+        self.hidden_features = hidden_features
+        H = hidden_features
+        self.kernel_i = Param(prng.variance_scaling_uniform(rngs.params(), in_features, 4 * H, 1.0))
+        self.kernel_h = Param(prng.variance_scaling_uniform(rngs.params(), H, 4 * H, 1.0))
+        self.bias = Param(np.zeros(4 * H, np.float32))
+
+    def initialize_state(self, batch_size: int):
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device())
+        z = lambda: torch.zeros(batch_size, self.hidden_features, dtype=torch.float32, device=dev)
+        return (z(), z())
+
+    def reset_state(self, prev_state):
+        import torch
+        return (torch.zeros_like(prev_state[0]), torch.zeros_like(prev_state[1]))

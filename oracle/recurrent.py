@@ -114,9 +114,7 @@ def make_recurrent_actor_critic(obs_size, action_size, pre_sizes, lstm_hidden, p
     act = ACT_IDS[activation]
 
     def uniform(shape, fan_in):
-        k = rngs()
-        lim = np.sqrt(3.0 / fan_in)
-        return (prng.uniform(k, shape, -lim, lim)).astype(F)
+        return prng.variance_scaling_uniform(rngs(), shape[0], shape[1], 1.0)
 
     def chain(sizes, last_linear=True):   # (a pre chain is evaluated with _chain_all_act instead)
         Ws, bs = [], []

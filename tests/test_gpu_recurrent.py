@@ -104,3 +104,46 @@ def test_recurrent_replay_and_bptt_match_oracle(cuda_device, cfg):
     scale = np.abs(ref).max()
     assert np.abs(g - ref).max() < 3e-4 * scale, (np.abs(g - ref).max(), scale)
     assert np.all(grad.cpu().numpy()[n_rec:] == 0)               # the critic's slots are not touched here
+
+
+def test_recurrent_ppo_step_matches_oracle(cuda_device):
+    """Public API (`ppo.ppo_step`) with an LSTM actor against oracle/recurrent.py over iterations:
+    bit-exact masks / minibatch indices / counters, float32-tolerance losses and parameters
+    (reference: recurrent_test.py:285-330 only checks finiteness and that parameters change)."""
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import ppo
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    O, A, B, T, E, M, P, H = 16, 4, 64, 12, 2, 2, 32, 32
+    nets = make_recurrent_actor_critic(O, A, P, H, [48], Rngs(1))
+    onet = orec.make_recurrent_actor_critic(O, A, [P], H, [], [48], seed=1)
+    env = SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
+    oe = oenv.SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
+    ts = ppo.new_training_state(env, nets, B, 17)
+    ots = orec.new_training_state(oe, onet, B, 17)
+    net = compile_network(nets)
+    assert net.recurrent
+    u32 = lambda t: t.cpu().numpy().view(np.uint32)
+    for it in range(2):
+        ts, m = ppo.ppo_step(env, ts, B, T, 0.95, 0.99, 0.2, True, False, E, M)
+        tr = {}
+        ots, om = orec.ppo_step(oe, ots, B, T, n_epochs=E, n_minibatches=M, trace=tr)
+        eng = next(iter(net.engines.values()))
+        assert np.array_equal(eng.inds.cpu().numpy().reshape(E * M, B // M), tr["indices"])
+        assert np.array_equal(eng.done.cpu().numpy().astype(bool), tr["rollout"].done)
+        assert np.array_equal(eng.trunc.cpu().numpy().astype(bool), tr["rollout"].truncated)
+        assert tr["rollout"].done.sum() > 0
+        assert np.abs(eng.loglik.cpu().numpy() - tr["rollout"].loglik).max() < 2e-4
+        assert tuple(ts.rng_key) == tuple(int(x) for x in ots.rng_key)
+        assert float(ts.steps_taken) == float(ots.steps_taken) == (it + 1) * T * B
+        cnt = u32(net.counters)
+        assert cnt[2] == onet.rng_count and cnt[3] == (it + 1) * E * M == ots.opt.count
+        for k in ("losses/actor/mean", "losses/critic/mean", "losses/regularization/mean"):
+            assert abs(m[k] - om[k]) < 3e-4 * max(1.0, abs(om[k])), (k, m[k], om[k])
+        p, po = net.params_logical(), onet.flat_params()
+        assert p.shape == po.shape
+        assert np.abs(p - po).max() < 1e-4 * 4 and np.mean(np.abs(p - po)) < 3e-6
+        c, h = net.get_carry(ts.network_states)
+        assert np.allclose(c.cpu().numpy(), ots.carry[0], atol=2e-4) and np.allclose(h.cpu().numpy(), ots.carry[1], atol=2e-4)
+        assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)

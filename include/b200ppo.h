@@ -270,11 +270,13 @@ int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan, const flo
 
 /* NormalTanhSampler (sampling_layers.py:88-147) on actor outputs y [B][2A] = [mu | rho] computed
  * elsewhere (the recurrent step): mode bit 0 = replay stored raw actions, bit 1 = deterministic;
- * sample key = fold_in(stream key, rng_state[2] + count_offset), element (row, d) draws index row*A + d. */
+ * keys as in b200ppo_policy_step (sample: count, entropy: the next count; deterministic skips the
+ * sample draw); element (row, d) draws index row*A + d.  reg_loss (nullable): -entropy_weight * H. */
 int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int32_t mode,
-                         float min_std, float std_scale, const uint32_t* rng_state,
-                         uint32_t count_offset, const float* raw_action_in, float* raw_action,
-                         float* action, float* loglik);
+                         float min_std, float std_scale, float entropy_weight,
+                         const uint32_t* rng_state, uint32_t count_offset,
+                         const float* raw_action_in, float* raw_action, float* action,
+                         float* loglik, float* reg_loss);
 
 /* GEMM engine of the update: 0 = fp32 FFMA on CUDA cores, 1 = tcgen05 3xTF32 (default; error-   *
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *

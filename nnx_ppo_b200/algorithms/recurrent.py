@@ -77,8 +77,9 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                              h.data_ptr(), eng.r_y.data_ptr(), 0), "lstm_step_fwd(rollout)")
         _lib.check(lib.b200ppo_sampler_step(s, eng.r_y.data_ptr(), B, A, 0, plan.min_std, plan.std_scale,
-                                            net.counters.data_ptr(), 2 * t, 0, eng.raw_action[t].data_ptr(),
-                                            eng.action[t].data_ptr(), eng.loglik[t].data_ptr()), "sampler_step")
+                                            plan.entropy_weight, net.counters.data_ptr(), 2 * t, 0,
+                                            eng.raw_action[t].data_ptr(), eng.action[t].data_ptr(),
+                                            eng.loglik[t].data_ptr(), 0), "sampler_step")
         nxt = env.step(env_state, eng.action[t])
         done = nxt.done.bool()
         tr = nxt.info.get("truncated", torch.zeros_like(done)) if isinstance(nxt.info, dict) else torch.zeros_like(done)

@@ -140,6 +140,10 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
         po = out.output
         nxt = env.step(env_state, po.actions)
         done = nxt.done.bool()
+        if net.recurrent:                                                 # rollout.py:33-40: reset the carry on done
+            c, h = net.get_carry(out.next_state)
+            keep = (~done).to(torch.float32)[:, None]
+            network_state = net.set_carry(out.next_state, (c * keep, h * keep))
         tr = nxt.info.get("truncated", torch.zeros_like(done)) if isinstance(nxt.info, dict) else torch.zeros_like(done)
         rec["obs"].append(env_state.obs)
         extras = out.rollout_extras[1] if net.normalizer is not None else out.rollout_extras
@@ -215,6 +219,8 @@ def eval_rollout(env, networks, n_envs: int, max_episode_length: int, key,
     prev_done = env_state.done.bool() if env_state.done is not None else torch.zeros(n_envs, dtype=torch.bool, device=dev)
     for _ in range(max_episode_length):
         out = call_network(networks, net_state, env_state.obs)
+        if net.recurrent:
+            net_state = out.next_state                                    # rollout.py:111-113 carries the state
         nxt = env.step(env_state, out.output.actions)
         done = torch.logical_or(nxt.done.bool(), prev_done)               # rollout.py:115-117
         cuml = cuml + torch.where(prev_done, torch.zeros_like(cuml), nxt.reward.float())

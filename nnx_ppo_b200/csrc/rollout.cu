@@ -560,41 +560,49 @@ struct SamplerArgs {
   float min_std, std_scale, entropy_weight;
   const uint32_t* rng_state; uint32_t count_offset;
   const float* raw_in;
-  float* raw; float* action; float* loglik;
+  float* raw; float* action; float* loglik; float* reg;
 };
 __global__ void __launch_bounds__(256) sampler_step_kernel(const SamplerArgs a) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= a.B) return;
   const Key stream_key{a.rng_state[0], a.rng_state[1]};
-  const uint32_t c = a.rng_state[2] + a.count_offset;
-  const Key k_sample = fold_in(stream_key, c);
-  float ll = 0.0f;
+  uint32_t c = a.rng_state[2] + a.count_offset;
+  // sampling_layers.py:93-96: the sample key is only drawn when not deterministic
+  Key k_sample = stream_key;
+  if (!(a.mode & 2)) { k_sample = fold_in(stream_key, c); c += 1u; }
+  const Key k_ent = fold_in(stream_key, c);
+  const bool want_reg = a.reg != nullptr;
+  float ll = 0.0f, rg = 0.0f;
   for (int d = 0; d < a.A; ++d) {
     const uint32_t j = static_cast<uint32_t>(row) * static_cast<uint32_t>(a.A) + d;
     const float rin = (a.mode & 1) ? a.raw_in[static_cast<size_t>(row) * a.A + d] : 0.0f;
     const SamplerOut s = sampler_elem(a.y[static_cast<size_t>(row) * 2 * a.A + d],
                                       a.y[static_cast<size_t>(row) * 2 * a.A + a.A + d], a.min_std, a.std_scale,
-                                      a.entropy_weight, a.mode, rin, k_sample, k_sample, j, false);
+                                      a.entropy_weight, a.mode, rin, k_sample, k_ent, j, want_reg);
     a.raw[static_cast<size_t>(row) * a.A + d] = s.raw;
     a.action[static_cast<size_t>(row) * a.A + d] = s.action;
     ll += s.llterm;
+    rg += s.regterm;
   }
   a.loglik[row] = ll;
+  if (want_reg) a.reg[row] = rg;
 }
 }  // namespace
 
 extern "C" int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int32_t mode,
-                                    float min_std, float std_scale, const uint32_t* rng_state,
-                                    uint32_t count_offset, const float* raw_action_in, float* raw_action,
-                                    float* action, float* loglik) {
+                                    float min_std, float std_scale, float entropy_weight,
+                                    const uint32_t* rng_state, uint32_t count_offset,
+                                    const float* raw_action_in, float* raw_action, float* action,
+                                    float* loglik, float* reg_loss) {
   if (B < 0 || A <= 0) return B200PPO_EINVAL;
   if (B == 0) return 0;
   if (!y || !rng_state || !raw_action || !action || !loglik) return B200PPO_EINVAL;
   if ((mode & 1) && !raw_action_in) return B200PPO_EINVAL;
   SamplerArgs a;
-  a.y = y; a.B = B; a.A = A; a.mode = mode; a.min_std = min_std; a.std_scale = std_scale; a.entropy_weight = 0.0f;
+  a.y = y; a.B = B; a.A = A; a.mode = mode; a.min_std = min_std; a.std_scale = std_scale;
+  a.entropy_weight = entropy_weight;
   a.rng_state = rng_state; a.count_offset = count_offset; a.raw_in = raw_action_in;
-  a.raw = raw_action; a.action = action; a.loglik = loglik;
+  a.raw = raw_action; a.action = action; a.loglik = loglik; a.reg = reg_loss;
   sampler_step_kernel<<<cdiv(B, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;

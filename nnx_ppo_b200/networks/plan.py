@@ -195,6 +195,8 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     lib = _lib.load()
     obs = obs.contiguous().float()
     _lib.require_cuda(obs)
+    if net.recurrent:
+        return _call_recurrent(net, state, obs, rollout_extras)
     B = obs.shape[0]
     A = net.plan.act_dim
     raw_in = None
@@ -224,6 +226,48 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     adapter_state = {"action": [()] * (na + 1), "value": [()] * nc}
     adapter_extras = {"action": [None] * na + [raw], "value": [None] * nc}
     out = PPONetworkOutput(actions=action, loglikelihoods=ll, value_estimates=value)
+    if net.normalizer is not None:
+        return StatefulModuleOutput([(), adapter_state], out, reg, {}, [obs, adapter_extras])
+    return StatefulModuleOutput(adapter_state, out, reg, {}, adapter_extras)
+
+
+def _call_recurrent(net, state: Any, obs, rollout_extras: Any):
+    """One call of a recurrent actor-critic (networks/rplan.py): recurrent step kernel + sampler +
+    critic.  Functional like the reference: the input state is not modified, the new carry is in
+    ``next_state`` at the LSTM's position of the reference-shaped state pytree."""
+    import copy
+    import torch
+    lib = _lib.load()
+    B, A, Y = obs.shape[0], net.plan.act_dim, net.lplan.out_dim
+    dev = obs.device
+    c, h = net.get_carry(state)
+    c, h = c.clone().contiguous(), h.clone().contiguous()
+    raw_in = None
+    if rollout_extras is not None:
+        extras = rollout_extras[1] if net.normalizer is not None else rollout_extras
+        raw_in = extras["action"][-1].contiguous().float()
+    mode = (1 if raw_in is not None else 0) | (2 if net.sampler.deterministic else 0)
+    y = torch.empty(B, Y, device=dev)
+    raw, action = torch.empty(B, A, device=dev), torch.empty(B, A, device=dev)
+    ll, reg = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    s = _lib.current_stream()
+    if net.normalizer is not None:
+        net.normalizer.prepare(s)
+    net.sync_counters_to_device()
+    mean_p, std_p = net.norm_ptrs()
+    _lib.check(lib.b200ppo_lstm_step_fwd(s, net.lplan, _lib.ptr(net.arena), mean_p, std_p, _lib.ptr(obs), 0, 0, B,
+                                         _lib.ptr(c), _lib.ptr(h), _lib.ptr(y), 0), "lstm_step_fwd")
+    _lib.check(lib.b200ppo_sampler_step(s, _lib.ptr(y), B, A, mode, net.plan.min_std, net.plan.std_scale,
+                                        net.plan.entropy_weight, _lib.ptr(net.counters), 0, _lib.ptr(raw_in),
+                                        _lib.ptr(raw), _lib.ptr(action), _lib.ptr(ll), _lib.ptr(reg)), "sampler_step")
+    from ..algorithms.rollout import policy_values
+    value = policy_values(net, obs)
+    net.advance_rng(1 if net.sampler.deterministic else 2)
+    nc = len(net.critic_layers)
+    adapter_state = {"action": [(), (c, h), (), ()], "value": [()] * nc}
+    adapter_extras = {"action": [None, None, None, raw], "value": [None] * nc}
+    out = PPONetworkOutput(actions=action, loglikelihoods=ll, value_estimates=value)
+    del copy
     if net.normalizer is not None:
         return StatefulModuleOutput([(), adapter_state], out, reg, {}, [obs, adapter_extras])
     return StatefulModuleOutput(adapter_state, out, reg, {}, adapter_extras)

@@ -147,3 +147,39 @@ def test_recurrent_ppo_step_matches_oracle(cuda_device):
         c, h = net.get_carry(ts.network_states)
         assert np.allclose(c.cpu().numpy(), ots.carry[0], atol=2e-4) and np.allclose(h.cpu().numpy(), ots.carry[1], atol=2e-4)
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
+
+
+def test_recurrent_network_call_and_eval(cuda_device):
+    """`networks(state, obs)` with an LSTM actor: functional carry (input state untouched), replay of the
+    stored raw actions reproduces the log-likelihoods (adapter_test.py:61-75), eval_rollout runs."""
+    import torch
+    from nnx_ppo_b200 import Rngs, prng as pprng
+    from nnx_ppo_b200.algorithms import rollout
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    O, A, B, H = 12, 3, 20, 16
+    nets = make_recurrent_actor_critic(O, A, 8, H, [10], Rngs(2))
+    onet = orec.make_recurrent_actor_critic(O, A, [8], H, [], [10], seed=2)
+    net = compile_network(nets)
+    obs = torch.randn(B, O, device=cuda_device)
+    s0 = nets.initialize_state(B)
+    out1 = nets(s0, obs)
+    c0, h0 = net.get_carry(s0)
+    assert float(c0.abs().max()) == 0.0 and float(h0.abs().max()) == 0.0          # input state not modified
+    c1, h1 = net.get_carry(out1.next_state)
+    oc, oh = onet.initialize_state(B)
+    (oc, oh), oo = orec.policy_forward(onet, (oc, oh), obs.cpu().numpy())
+    assert np.allclose(h1.cpu().numpy(), oh, atol=2e-5) and np.allclose(c1.cpu().numpy(), oc, atol=2e-5)
+    assert np.allclose(out1.output.actions.cpu().numpy(), oo["action"], atol=2e-5)
+    assert np.allclose(out1.output.loglikelihoods.cpu().numpy(), oo["loglik"], atol=2e-4)
+    assert np.allclose(out1.output.value_estimates.cpu().numpy(), oo["value"], atol=2e-5)
+    assert np.allclose(out1.regularization_loss.cpu().numpy(), oo["reg"], atol=2e-5)
+    assert net.rng_count == onet.rng_count
+    out2 = nets(s0, obs, out1.rollout_extras)                                      # replay
+    assert np.allclose(out2.output.loglikelihoods.cpu().numpy(), out1.output.loglikelihoods.cpu().numpy(), atol=1e-6)
+    env = SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
+    nets.eval()
+    m = rollout.eval_rollout(env, nets, 16, 12, pprng.key(3))
+    nets.train()
+    assert np.isfinite(m["episode_reward/mean"]) and 0 <= m["lifespan_mean"] <= 12

@@ -16,8 +16,9 @@
 namespace {
 using namespace b200ppo;
 
-constexpr int RT = 16;     // rows per CTA
 constexpr int NTH = 256;
+// rows per CTA: 16 when there are enough rows to fill the GPU (each weight load feeds 16 FMAs),
+// 4 for minibatch-sized calls (512 rows -> 128 CTAs instead of 32)
 
 struct LstmDims {
   int O, P, H, Y, C;       // obs, lstm input, hidden, output (2A), cache floats per row
@@ -39,7 +40,7 @@ struct FwdArgs {
 };
 
 // out[r][n] (+)= sum_k in[r][k] * W[k*ldw + n]  for the RT rows of the tile; thread per column n
-template <class Epi>
+template <int RT, class Epi>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ in, int ldin, int K,
                                           const float* __restrict__ W, int ldw, int N, Epi epi) {
   for (int n = threadIdx.x; n < N; n += NTH) {
@@ -55,6 +56,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ in, int ldin
   }
 }
 
+template <int RT>
 __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   __syncthreads();
   float* crow = a.cache;
   // ---- pre Dense: z1 = x W1 + b1, u = act(z1)
-  tile_gemm(xs, O, O, Pm + a.plan.w1_off, P, P, [&](int n, float (&acc)[RT]) {
+  tile_gemm<RT>(xs, O, O, Pm + a.plan.w1_off, P, P, [&](int n, float (&acc)[RT]) {
     const float b = Pm[a.plan.b1_off + n];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   });
   __syncthreads();
   // ---- gates: a = [u, h] Wcat + b, activation applied
-  tile_gemm(cat, P + H, P + H, Pm + a.plan.wcat_off, 4 * H, 4 * H, [&](int n, float (&acc)[RT]) {
+  tile_gemm<RT>(cat, P + H, P + H, Pm + a.plan.wcat_off, 4 * H, 4 * H, [&](int n, float (&acc)[RT]) {
     const float b = Pm[a.plan.bl_off + n];
     const bool is_g = n >= 2 * H && n < 3 * H;
 #pragma unroll
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
     }
   __syncthreads();
   // ---- post Dense (linear): y = h' W2 + b2
-  tile_gemm(hn, H, H, Pm + a.plan.w2_off, Y, Y, [&](int n, float (&acc)[RT]) {
+  tile_gemm<RT>(hn, H, H, Pm + a.plan.w2_off, Y, Y, [&](int n, float (&acc)[RT]) {
     const float b = Pm[a.plan.b2_off + n];
 #pragma unroll
     for (int r = 0; r < RT; ++r)
@@ -158,6 +160,7 @@ struct BwdArgs {
 };
 
 // grad[k][n] += sum_r A[r][k] * D[r][n]   (A, D shared-memory tiles); thread per column n
+template <int RT>
 __device__ __forceinline__ void tile_outer_acc(const float* __restrict__ A, int lda, int K,
                                                const float* __restrict__ D, int ldd, int N,
                                                float* __restrict__ G, float* __restrict__ gbias) {
@@ -177,7 +180,7 @@ __device__ __forceinline__ void tile_outer_acc(const float* __restrict__ A, int 
 }
 
 // out[r][k] = sum_n D[r][n] * W[k*ldw + n]  (D shared tile [RT][N]); one warp per k, lanes over n
-template <class Epi>
+template <int RT, class Epi>
 __device__ __forceinline__ void tile_gemm_t(const float* __restrict__ D, int ldd, int N,
                                             const float* __restrict__ W, int ldw, int K, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,6 +199,7 @@ __device__ __forceinline__ void tile_gemm_t(const float* __restrict__ D, int ldd
   }
 }
 
+template <int RT>
 __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
@@ -231,10 +235,10 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // ---- post Dense: dW2 += h'^T dY, db2 += sum dY
-  tile_outer_acc(hn, H, H, dy, Y, Y, a.grad + a.plan.w2_off, a.grad + a.plan.b2_off);
+  tile_outer_acc<RT>(hn, H, H, dy, Y, Y, a.grad + a.plan.w2_off, a.grad + a.plan.b2_off);
   __syncthreads();
   // ---- dh_total = dY W2^T + keep * dh_next ; then gate gradients
-  tile_gemm_t(dy, Y, Y, Pm + a.plan.w2_off, Y, H, [&](int k, float (&acc)[RT]) {
+  tile_gemm_t<RT>(dy, Y, Y, Pm + a.plan.w2_off, Y, H, [&](int k, float (&acc)[RT]) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) hn[r * H + k] = acc[r];
   });
@@ -259,9 +263,9 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // ---- dWcat += [u, h_in]^T da, dbl += sum da
-  tile_outer_acc(cat, P + H, P + H, da, 4 * H, 4 * H, a.grad + a.plan.wcat_off, a.grad + a.plan.bl_off);
+  tile_outer_acc<RT>(cat, P + H, P + H, da, 4 * H, 4 * H, a.grad + a.plan.wcat_off, a.grad + a.plan.bl_off);
   // ---- d[u, h_in] = da Wcat^T : u part -> dz1 (x act'), h part -> dh of the previous step
-  tile_gemm_t(da, 4 * H, 4 * H, Pm + a.plan.wcat_off, 4 * H, P + H, [&](int k, float (&acc)[RT]) {
+  tile_gemm_t<RT>(da, 4 * H, 4 * H, Pm + a.plan.wcat_off, 4 * H, P + H, [&](int k, float (&acc)[RT]) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const int row = row0 + r;
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   });
   __syncthreads();
   // ---- pre Dense: dW1 += x^T dz1, db1 += sum dz1
-  tile_outer_acc(xs, O, O, dz, P, P, a.grad + a.plan.w1_off, a.grad + a.plan.b1_off);
+  tile_outer_acc<RT>(xs, O, O, dz, P, P, a.grad + a.plan.w1_off, a.grad + a.plan.b1_off);
 }
 
 int check_lstm_plan(const b200ppo_lstm_plan* p) {
@@ -291,8 +295,9 @@ int check_lstm_plan(const b200ppo_lstm_plan* p) {
   return 0;
 }
 
-size_t fwd_smem(const LstmDims& d) { return sizeof(float) * RT * (d.O + (d.P + d.H) + 4 * d.H + d.H); }
-size_t bwd_smem(const LstmDims& d) { return sizeof(float) * RT * (d.O + (d.P + d.H) + 4 * d.H + d.H + d.Y + d.P); }
+size_t fwd_smem(const LstmDims& d, int RT) { return sizeof(float) * RT * (d.O + (d.P + d.H) + 4 * d.H + d.H); }
+size_t bwd_smem(const LstmDims& d, int RT) { return sizeof(float) * RT * (d.O + (d.P + d.H) + 4 * d.H + d.H + d.Y + d.P); }
+int rows_per_cta(int rows) { return cdiv(rows, 16) >= 100 ? 16 : 4; }
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 }  // namespace
@@ -313,15 +318,20 @@ extern "C" int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan
   if (!params || !obs || !c || !h || !y) return B200PPO_EINVAL;
   if (plan->normalize && (!norm_mean || !norm_std)) return B200PPO_EINVAL;
   const LstmDims d = dims_of(*plan);
-  const size_t smem = fwd_smem(d);
+  const int RT = rows_per_cta(rows);
+  const size_t smem = fwd_smem(d, RT);
   if (smem > SMEM_MAX) return B200PPO_ELIMIT;
-  cudaError_t e = cudaFuncSetAttribute(lstm_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(lstm_step_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(SMEM_MAX));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_step_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(SMEM_MAX));
   if (e != cudaSuccess) return static_cast<int>(e);
   FwdArgs a;
   a.plan = *plan; a.params = params; a.mean = norm_mean; a.std = norm_std; a.obs = obs; a.inds = inds;
   a.done = done; a.c = c; a.h = h; a.y = y; a.cache = cache; a.rows = rows;
-  lstm_step_fwd_kernel<<<cdiv(rows, RT), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (RT == 16) lstm_step_fwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  else lstm_step_fwd_kernel<4><<<cdiv(rows, 4), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -335,15 +345,20 @@ extern "C" int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan
   if (rows == 0) return 0;
   if (!params || !d_y || !cache || !dc || !dh || !grad) return B200PPO_EINVAL;
   const LstmDims d = dims_of(*plan);
-  const size_t smem = bwd_smem(d);
+  const int RT = rows_per_cta(rows);
+  const size_t smem = bwd_smem(d, RT);
   if (smem > SMEM_MAX) return B200PPO_ELIMIT;
-  cudaError_t e = cudaFuncSetAttribute(lstm_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(lstm_step_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(SMEM_MAX));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_step_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(SMEM_MAX));
   if (e != cudaSuccess) return static_cast<int>(e);
   BwdArgs a;
   a.plan = *plan; a.params = params; a.d_y = d_y; a.cache = cache; a.inds = inds; a.done = done;
   a.rows = rows; a.dc = dc; a.dh = dh; a.grad = grad;
-  lstm_step_bwd_kernel<<<cdiv(rows, RT), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (RT == 16) lstm_step_bwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  else lstm_step_bwd_kernel<4><<<cdiv(rows, 4), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

@@ -108,6 +108,10 @@ typedef struct b200ppo_update_bufs {
    * the stages).  dev uint64[world_size]: base address of every rank's comm buffer
    * (b200ppo_comm_alloc / b200ppo_comm_ipc_open), entry [rank] being this rank's own. */
   const uint64_t* comm;
+  /* optional dev uint8[n_params]: 0 marks a structural zero (the off-diagonal blocks when per-key
+   * encoders — containers.py Concat — are laid out as one block-diagonal Dense layer); such entries
+   * are excluded from the gradient norm and never updated.  NULL: every entry is a parameter. */
+  const uint8_t* param_mask;
 } b200ppo_update_bufs;
 
 /* -------- library -------------------------------------------------------------------------- */

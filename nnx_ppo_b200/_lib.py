@@ -43,7 +43,8 @@ class HParams(C.Structure):
 class UpdateBufs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "raw_action", "loglik_old", "reward", "done", "truncated", "next_obs_last", "inds",
-        "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm")]
+        "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm",
+        "param_mask")]
 
 
 class LstmPlan(C.Structure):

@@ -119,6 +119,8 @@ class PPOEngine:
             b.rng_state = net.counters.data_ptr()
             b.metrics_out = self.metrics.data_ptr() + 16 * u
             b.ws = wsp
+            pm = getattr(net, "param_mask", None)
+            b.param_mask = pm.data_ptr() if pm is not None else 0
             self.bufs.append(b)
         self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory

@@ -963,11 +963,13 @@ __global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ 
 
 __global__ void __launch_bounds__(256) upd_gnorm_kernel(const float* __restrict__ grad, int64_t P,
                                                         double* __restrict__ part, double* __restrict__ out,
-                                                        unsigned int* __restrict__ ticket) {
+                                                        unsigned int* __restrict__ ticket,
+                                                        const uint8_t* __restrict__ mask) {
   __shared__ double red[8];
   double s = 0.0;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (mask && !mask[i]) continue;              // structural zero of a block-diagonal layer: not a parameter
     const double g = grad[i];
     s += g * g;
   }
@@ -999,6 +1001,7 @@ struct AdamArgs {
   float lr, b1, b2, eps, wd, clip;
   PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of the copies every rank pushed here
   size_t comm_ppad;
+  const uint8_t* mask;  // nullable: 0 = structural zero (off-diagonal block of per-key encoders), never updated
   // tensor-core path: the updated weight is also re-split into the hi / lo operand planes of the next
   // update (what upd_prep_w_kernel does from scratch), so that update can skip its prep launch
   int n_seg;                                   // 0: no refresh
@@ -1039,6 +1042,7 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   } else {
     g = a.grad[i];
   }
+  if (a.mask && !a.mask[i]) return;
   if (a.clip > 0.0f && !(gn < a.clip)) g = __fmul_rn(__fdiv_rn(g, gn), a.clip);
   const float t = static_cast<float>(epoch);
   const float m = __fadd_rn(__fmul_rn(1.0f - a.b1, g), __fmul_rn(a.b1, a.mu[i]));
@@ -1379,7 +1383,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     if (hp->grad_clip > 0.0f) {
       int nb = cdiv(plan->n_params, 256 * 8);
       if (nb > MAX_PART_BLOCKS) nb = MAX_PART_BLOCKS;
-      upd_gnorm_kernel<<<nb, 256, 0, s>>>(ws + L.grad, plan->n_params, dbl + DBL_GN_PART, dbl + 2, tickets + 2);
+      upd_gnorm_kernel<<<nb, 256, 0, s>>>(ws + L.grad, plan->n_params, dbl + DBL_GN_PART, dbl + 2, tickets + 2,
+                                          b->param_mask);
       B200PPO_LAUNCH_CHECK();
     }
     AdamArgs a;
@@ -1390,6 +1395,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.lr = hp->learning_rate; a.b1 = hp->adam_b1; a.b2 = hp->adam_b2; a.eps = hp->adam_eps;
     a.wd = hp->weight_decay; a.clip = hp->grad_clip;
     a.comm = pc; a.comm_ppad = comm_ppad(plan->n_params);
+    a.mask = b->param_mask;
     a.n_seg = 0; a.ws = ws;
     if (use_tc) {
       for (int c = 0; c < 2; ++c) {

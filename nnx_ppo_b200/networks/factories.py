@@ -7,7 +7,7 @@ from typing import Callable, Union
 from .. import prng
 from . import feedforward
 from .adapter import PPOAdapter
-from .containers import Sequential
+from .containers import Concat, Sequential
 from .feedforward import Dense
 from .normalizer import Normalizer
 from .sampling_layers import NormalTanhSampler
@@ -79,4 +79,36 @@ def make_recurrent_actor_critic(obs_size: int, action_size: int, pre_size: int, 
     adapter = PPOAdapter(action=Sequential([*actor, sampler]), value=critic)
     if normalize_obs:
         return Sequential([Normalizer(obs_size), adapter])
+    return adapter
+
+
+def make_dict_actor_critic(obs_sizes: dict, action_size: int, encoder_hidden: dict,
+                           actor_trunk_sizes: list[int], critic_trunk_sizes: list[int], rngs: prng.Rngs,
+                           activation: Union[Callable, str] = feedforward.relu, normalize_obs: bool = True,
+                           entropy_weight: float = 1e-2, min_std: float = 1e-1,
+                           std_scale: float = 1.0) -> StatefulModule:
+    """Dict observations routed to per-key encoders (BASELINE configs[3]): actor and critic each are
+    Sequential([Concat(key=MLP encoder, ...), trunk Dense..., head]) over the observation dict
+    (containers.py:55-110).  ``obs_sizes`` / ``encoder_hidden`` map key -> size / hidden sizes (all
+    encoders must have the same depth; every encoder layer is followed by the activation)."""
+    if isinstance(activation, str):
+        activation = {"swish": feedforward.swish, "tanh": feedforward.tanh, "relu": feedforward.relu}[activation]
+
+    def kernel_init(key, shape):
+        return prng.variance_scaling_uniform(key, shape[0], shape[1], 1.0)
+
+    def tower(trunk, out):
+        encs = {k: make_mlp([obs_sizes[k]] + list(encoder_hidden[k]), rngs, activation,
+                            activation_last_layer=True, kernel_init=kernel_init) for k in obs_sizes}
+        width = sum(encoder_hidden[k][-1] for k in obs_sizes)
+        rest = make_mlp_layers([width] + list(trunk) + [out], rngs, activation, activation_last_layer=False,
+                               kernel_init=kernel_init)
+        return [Concat(encs), *rest]
+
+    actor = tower(actor_trunk_sizes, action_size * 2)
+    critic = Sequential(tower(critic_trunk_sizes, 1))
+    sampler = NormalTanhSampler(rngs, entropy_weight=entropy_weight, min_std=min_std, std_scale=std_scale)
+    adapter = PPOAdapter(action=Sequential([*actor, sampler]), value=critic)
+    if normalize_obs:
+        return Sequential([Normalizer(sum(obs_sizes.values())), adapter])
     return adapter

@@ -15,7 +15,7 @@ import numpy as np
 
 from .. import _lib
 from .adapter import PPOAdapter
-from .containers import Sequential
+from .containers import Concat, Sequential
 from .feedforward import Dense
 from .normalizer import Normalizer
 from .sampling_layers import NormalTanhSampler
@@ -24,6 +24,51 @@ from .types import PPONetworkOutput, StatefulModule, StatefulModuleOutput
 
 def _align4(n: int) -> int:
     return (n + 3) & ~3
+
+
+class _VLayer:
+    """One layer of a lowered chain: a plain Dense (one block) or the block-diagonal union of the
+    same-depth Dense layers of a Concat's per-key encoders (blocks = [(row0, col0, Dense)])."""
+
+    def __init__(self, blocks):
+        self.blocks = blocks
+        self.in_features = sum(d.in_features for _, _, d in blocks)
+        self.out_features = sum(d.out_features for _, _, d in blocks)
+        names = {d.activation_name for _, _, d in blocks}
+        if len(names) != 1:
+            raise NotImplementedError("per-key encoders must use the same activation at the same depth")
+        self.activation_name = names.pop()
+
+
+def _lower_chain(layers):
+    """[Concat(k=Sequential([Dense...])...)?, Dense...] -> ([_VLayer...], key order, per-key input sizes)."""
+    out, keys, sizes = [], None, None
+    layers = list(layers)
+    if layers and isinstance(layers[0], Concat):
+        comps = layers[0].components
+        stacks = []
+        for k, c in comps.items():
+            ls = list(c.layers) if isinstance(c, Sequential) else [c]
+            if not ls or not all(isinstance(l, Dense) for l in ls):
+                raise NotImplementedError("Concat components must be Dense stacks")
+            stacks.append(ls)
+        depth = {len(ls) for ls in stacks}
+        if len(depth) != 1:
+            raise NotImplementedError("per-key encoders must have the same depth")
+        keys, sizes = list(comps.keys()), [ls[0].in_features for ls in stacks]
+        for j in range(depth.pop()):
+            blocks, r0, c0 = [], 0, 0
+            for ls in stacks:
+                blocks.append((r0, c0, ls[j]))
+                r0 += ls[j].in_features
+                c0 += ls[j].out_features
+            out.append(_VLayer(blocks))
+        layers = layers[1:]
+    for l in layers:
+        if not isinstance(l, Dense):
+            raise NotImplementedError(f"unsupported layer {type(l).__name__} in the MLP plan")
+        out.append(_VLayer([(0, 0, l)]))
+    return out, keys, sizes
 
 
 class CompiledNet:
@@ -51,16 +96,19 @@ class CompiledNet:
         action = adapter.action
         if not isinstance(action, Sequential) or not isinstance(action.layers[-1], NormalTanhSampler):
             raise NotImplementedError("action port must be Sequential([Dense..., NormalTanhSampler])")
-        actor_layers = list(action.layers[:-1])
         self.sampler: NormalTanhSampler = action.layers[-1]
         value = adapter.value
-        critic_layers = list(value.layers) if isinstance(value, Sequential) else [value]
-        for l in actor_layers + critic_layers:
-            if not isinstance(l, Dense):
-                raise NotImplementedError(f"unsupported layer {type(l).__name__} in the MLP plan")
+        actor_layers, self.obs_keys, self.obs_sizes = _lower_chain(action.layers[:-1])
+        critic_layers, ck, cs = _lower_chain(list(value.layers) if isinstance(value, Sequential) else [value])
+        if ck is not None and self.obs_keys is not None and (ck != self.obs_keys or cs != self.obs_sizes):
+            raise NotImplementedError("actor and critic must split the observation dict the same way")
+        if self.obs_keys is None:
+            self.obs_keys, self.obs_sizes = ck, cs
         self.normalizer = normalizer
         self.adapter = adapter
-        self.actor_layers, self.critic_layers = actor_layers, critic_layers
+        # module lists (for the reference-shaped state / extras pytrees) vs lowered virtual layers
+        self.actor_layers = list(action.layers[:-1])
+        self.critic_layers = list(value.layers) if isinstance(value, Sequential) else [value]
 
         plan = _lib.Plan()
         off = 0
@@ -104,19 +152,51 @@ class CompiledNet:
         self.plan = plan
         self.n_params = off
 
-        # one flat arena; every Dense parameter becomes a view into it
+        # one flat arena; every Dense parameter becomes a view into it (a sub-block view for the
+        # per-key encoders of a Concat, whose layers are stored block-diagonally)
         host = np.zeros(off, np.float32)
+        mask = np.ones(off, np.uint8)
+        masked = False
         for chain, layers in ((plan.actor, actor_layers), (plan.critic, critic_layers)):
-            for i, l in enumerate(layers):
-                w, b = l.linear.kernel.numpy(), l.linear.bias.numpy()
-                host[chain.w_off[i]:chain.w_off[i] + w.size] = w.ravel()
-                host[chain.b_off[i]:chain.b_off[i] + b.size] = b.ravel()
+            for i, vl in enumerate(layers):
+                K, N = vl.in_features, vl.out_features
+                Wd = np.zeros((K, N), np.float32)
+                Md = np.zeros((K, N), np.uint8)
+                bd = np.zeros(N, np.float32)
+                for r0, c0, d in vl.blocks:
+                    Wd[r0:r0 + d.in_features, c0:c0 + d.out_features] = d.linear.kernel.numpy()
+                    Md[r0:r0 + d.in_features, c0:c0 + d.out_features] = 1
+                    bd[c0:c0 + d.out_features] = d.linear.bias.numpy()
+                host[chain.w_off[i]:chain.w_off[i] + K * N] = Wd.ravel()
+                mask[chain.w_off[i]:chain.w_off[i] + K * N] = Md.ravel()
+                host[chain.b_off[i]:chain.b_off[i] + N] = bd
+                masked = masked or len(vl.blocks) > 1
         self.arena = torch.from_numpy(host).to(device)
+        self.param_mask = torch.from_numpy(mask).to(device) if masked else None
+        self._logical_params = []
+        index = []
         for chain, layers in ((plan.actor, actor_layers), (plan.critic, critic_layers)):
-            for i, l in enumerate(layers):
-                kin, kout = l.in_features, l.out_features
-                l.linear.kernel._dev = self.arena[chain.w_off[i]:chain.w_off[i] + kin * kout].view(kin, kout)
-                l.linear.bias._dev = self.arena[chain.b_off[i]:chain.b_off[i] + kout]
+            # logical (oracle) order: per key, the encoder's layers; then the shared trunk layers
+            nkeys = max(len(vl.blocks) for vl in layers)
+            enc_depth = sum(1 for vl in layers if len(vl.blocks) > 1)
+            order = [(j, kb) for kb in range(nkeys) for j in range(enc_depth)] if nkeys > 1 else []
+            order += [(j, 0) for j in range(enc_depth if nkeys > 1 else 0, len(layers))]
+            for i, vl in enumerate(layers):
+                K, N = vl.in_features, vl.out_features
+                Wv = self.arena[chain.w_off[i]:chain.w_off[i] + K * N].view(K, N)
+                bv = self.arena[chain.b_off[i]:chain.b_off[i] + N]
+                for r0, c0, d in vl.blocks:
+                    d.linear.kernel._dev = Wv[r0:r0 + d.in_features, c0:c0 + d.out_features]
+                    d.linear.bias._dev = bv[c0:c0 + d.out_features]
+            for j, kb in order:
+                r0, c0, d = layers[j].blocks[kb]
+                N = layers[j].out_features
+                self._logical_params += [d.linear.kernel, d.linear.bias]
+                rr = np.arange(r0, r0 + d.in_features, dtype=np.int64)[:, None]
+                cc = np.arange(c0, c0 + d.out_features, dtype=np.int64)[None, :]
+                index.append((int(chain.w_off[j]) + rr * N + cc).ravel())
+                index.append(int(chain.b_off[j]) + cc.ravel())
+        self._logical_index = np.concatenate(index)
         if normalizer is not None:
             normalizer._bind(device)
         # counters: [0..1] sampler stream key, [2] sampler count, [3] adam count
@@ -127,25 +207,16 @@ class CompiledNet:
         self.adam_step = 0   # host mirror of counters[3] (optimizer step count)
 
     # ---- flat <-> logical parameter order (actor W0,b0,..., critic W0,b0,...; no padding) ----
-    def logical_slices(self):
-        out = []
-        for chain, layers in ((self.plan.actor, self.actor_layers), (self.plan.critic, self.critic_layers)):
-            for i, l in enumerate(layers):
-                out.append((int(chain.w_off[i]), l.in_features * l.out_features))
-                out.append((int(chain.b_off[i]), l.out_features))
-        return out
-
     def params_logical(self, arena=None) -> np.ndarray:
+        """An arena-shaped tensor (parameters by default; also gradients, Adam moments) in the
+        oracle's flat order: no padding, no structural zeros."""
         a = (self.arena if arena is None else arena).detach().cpu().numpy()
-        return np.concatenate([a[o:o + n] for o, n in self.logical_slices()])
+        return a[self._logical_index]
 
     def load_params_logical(self, flat: np.ndarray) -> None:
         import torch
-        host = np.zeros(self.n_params, np.float32)
-        p = 0
-        for o, n in self.logical_slices():
-            host[o:o + n] = flat[p:p + n]
-            p += n
+        host = self.arena.detach().cpu().numpy().copy()
+        host[self._logical_index] = np.asarray(flat, np.float32)
         self.arena.copy_(torch.from_numpy(host))
 
     # ---- sampler stream bookkeeping (host mirror of counters[2]) ----
@@ -189,8 +260,14 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     the fused policy-step kernel (K1).  Mirrors the output structure of containers.py:18-39 /
     adapter.py:100-117: rollout_extras = [raw_obs, {"action": [None..., raw_action], "value": [...]}]."""
     import torch
+    if isinstance(obs, dict):
+        # dict observations (Concat plan): concatenated in the Concat's key order (plumbing only)
+        net0 = compile_network(network, next(iter(obs.values())).device)
+        if net0.obs_keys is None:
+            raise TypeError("dict observations need a network whose actor / critic start with a Concat")
+        obs = torch.cat([obs[k].float() for k in net0.obs_keys], dim=-1)
     if not isinstance(obs, torch.Tensor):
-        raise TypeError("observations must be a CUDA float32 torch tensor [B, obs_size]")
+        raise TypeError("observations must be a CUDA float32 torch tensor [B, obs_size] (or a dict of them)")
     net = compile_network(network, obs.device)
     lib = _lib.load()
     obs = obs.contiguous().float()

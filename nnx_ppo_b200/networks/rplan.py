@@ -122,9 +122,11 @@ class RecurrentCompiledNet(CompiledNet):
         self.engines = {}
         self.adam_step = 0
 
-    def logical_slices(self):
-        """Oracle order (oracle/recurrent.py param_list): W1 b1 Wi Wh bl W2 b2, critic W0 b0 ..."""
-        return [(int(o), int(np.prod(p.shape))) for o, p in self._params]
+        # oracle order (oracle/recurrent.py param_list): W1 b1 Wi Wh bl W2 b2, critic W0 b0 ...
+        self._logical_index = np.concatenate([np.arange(o, o + int(np.prod(p.shape)), dtype=np.int64)
+                                              for o, p in params])
+        self.param_mask = None
+        self.obs_keys = self.obs_sizes = None
 
     # ---- carry inside the reference-shaped network_states pytree ----
     def get_carry(self, network_states):

@@ -91,6 +91,8 @@ def unroll_env(env: SyntheticEnv, env_state: EnvState, net: ActorCritic, T: int,
 def _chain_backward(chain, x0, zs, d_out):
     """Backprop ``d_out`` (grad w.r.t. the last layer's output) through a Chain.
     Returns ([dW], [db])."""
+    if hasattr(chain, "backward"):          # dictnet.EncChain: per-key encoders + trunk
+        return chain.backward(x0, zs, d_out)
     L = chain.n_layers
     dWs, dbs = [None] * L, [None] * L
     d = d_out

@@ -384,6 +384,34 @@ def test_ppo_step_matches_oracle_over_iterations(dev, cfg):
     _iterations(dev, cfg)
 
 
+@pytest.mark.parametrize("gemm", [0, 1])
+def test_dict_observation_network_matches_oracle(dev, gemm):
+    """BASELINE configs[3] topology at test size: dict observations routed to per-key encoders
+    (containers.py Concat), lowered to block-diagonal layers with masked structural zeros."""
+    _lib.load().b200ppo_set_gemm_mode(gemm)
+    try:
+        _iterations(dev, dict(O=40, A=5, B=128, T=12, E=2, M=2, iters=2, ah=[32], ch=[48],
+                              obs_sizes={"proprio": 16, "target": 24}, enc={"proprio": [24, 12], "target": [40, 20]}))
+    finally:
+        _lib.load().b200ppo_set_gemm_mode(1)
+    # structural zeros stay exactly zero, and a dict of tensors is accepted at the API boundary
+    import torch
+    from nnx_ppo_b200.networks.factories import make_dict_actor_critic
+    nets = make_dict_actor_critic({"a": 8, "b": 8}, 2, {"a": [8], "b": [8]}, [8], [8], Rngs(3))
+    env = SyntheticEnv(16, 2, max_len=16, term_thresh16=700)
+    ts = ppo.new_training_state(env, nets, 64, 5)
+    for _ in range(2):
+        ts, _m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+    net = compile_network(nets)
+    assert net.param_mask is not None
+    assert float(net.arena[net.param_mask == 0].abs().max()) == 0.0
+    obs = torch.randn(10, 16, device=dev)
+    o1 = nets(nets.initialize_state(10), {"a": obs[:, :8], "b": obs[:, 8:]})
+    net.sampler.rng.count -= 2
+    o2 = nets(nets.initialize_state(10), obs)
+    assert torch.equal(o1.output.actions, o2.output.actions)
+
+
 def test_ppo_step_matches_oracle_ffma_engine(dev):
     """Same check with the fp32 CUDA-core GEMM kernels (B200PPO_GEMM=ffma)."""
     _lib.load().b200ppo_set_gemm_mode(0)
@@ -395,7 +423,13 @@ def test_ppo_step_matches_oracle_ffma_engine(dev):
 
 def _iterations(dev, cfg):
     O, A, B, T, E, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["E"], cfg["M"]
-    nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
+    if "obs_sizes" in cfg:          # dict observations -> per-key encoders (Concat) -> trunk
+        from nnx_ppo_b200.networks.factories import make_dict_actor_critic
+        from oracle import dictnet
+        nets = make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], Rngs(0))
+        onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], seed=0)
+    else:
+        nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
     env = SyntheticEnv(O, A, max_len=48, term_thresh16=700)
     oe = oenv.SyntheticEnv(O, A, max_len=48, term_thresh16=700)
     ts = ppo.new_training_state(env, nets, B, 17)

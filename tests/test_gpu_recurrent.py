@@ -183,3 +183,25 @@ def test_recurrent_network_call_and_eval(cuda_device):
     m = rollout.eval_rollout(env, nets, 16, 12, pprng.key(3))
     nets.train()
     assert np.isfinite(m["episode_reward/mean"]) and 0 <= m["lifespan_mean"] <= 12
+
+
+def test_train_ppo_with_recurrent_actor(cuda_device):
+    """The drop-in entry point with an LSTM actor (recurrent_test.py:285-330 through train_ppo):
+    iterations run, evaluation (deterministic, carry threaded through eval_rollout) runs, parameters move."""
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import ppo
+    from nnx_ppo_b200.algorithms.config import EvalConfig, PPOConfig, TrainConfig
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    env = SyntheticEnv(12, 3, max_len=16)
+    nets = make_recurrent_actor_critic(12, 3, 16, 16, [24], Rngs(4))
+    p0 = compile_network(nets).params_logical().copy()
+    logged = []
+    cfg = TrainConfig(ppo=PPOConfig(n_envs=32, rollout_length=8, total_steps=32 * 8 * 3, n_minibatches=2, n_epochs=2),
+                      eval=EvalConfig(enabled=True, every_steps=32 * 8 * 2, n_envs=8, max_episode_length=10))
+    res = ppo.train_ppo(env, nets, cfg, seed=5, log_fn=lambda m, s: logged.append((s, dict(m))))
+    assert res.total_iterations == 3 and res.total_steps == 32 * 8 * 3
+    assert all(np.isfinite(float(v)) for _, m in logged for v in m.values() if np.isscalar(v) or hasattr(v, "__float__"))
+    assert any(k.startswith("eval") or "episode_reward" in k for _, m in logged for k in m)
+    assert np.abs(compile_network(nets).params_logical() - p0).max() > 0

@@ -126,10 +126,11 @@ class PPOEngine:
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory
         # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
         self.fuse_prep = os.environ.get("B200PPO_FUSE_PREP", "1") != "0"
+        self._side = torch.cuda.Stream(device=dev)
         self.p2p = False
         self._comm_local, self._comm_peers, self.comm_table = None, [], None
         if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0" and not self.hp.grad_clip > 0.0:
-            self._setup_p2p()
+            self._setup_p2p_collective()
         if use_graph is None:
             use_graph = os.environ.get("B200PPO_GRAPH", "1") != "0"
         self.use_graph = use_graph
@@ -139,40 +140,70 @@ class PPOEngine:
         self._env_state = None
 
     # ------------------------------------------------------------------------------------
-    def _setup_p2p(self):
+    def _setup_p2p_collective(self):
         """Allocate this rank's comm buffer, exchange CUDA IPC handles, map every peer's buffer
-        (include/b200ppo.h, 'peer-memory exchange').  Raises if the GPUs cannot map each other."""
+        (include/b200ppo.h, 'peer-memory exchange').  Every rank executes the same collectives whatever
+        happens locally and the outcome is agreed with a MIN over ranks after each phase: if any rank
+        cannot allocate / export / map (no P2P access between some GPUs, IPC disabled in the container)
+        all ranks use the NCCL all-reduce path instead — still a GPU collective, reported in
+        bench.py's `config.collectives`."""
         import ctypes as C
+        import sys
         import torch
         import torch.distributed as dist
         lib, world = self.lib, self.world
         rank = dist.get_rank(self.group)
-        nbytes = int(lib.b200ppo_comm_bytes(self.net.plan, world))
-        if nbytes <= 0 or world > 16:
-            raise _lib.B200PPOError("peer exchange: unsupported plan or world size")
-        p = C.c_void_p()
-        _lib.check(lib.b200ppo_comm_alloc(nbytes, C.byref(p)), "comm_alloc")
-        self._comm_local = p.value
-        h = C.create_string_buffer(64)
-        _lib.check(lib.b200ppo_comm_ipc_get(p, h), "comm_ipc_get")
-        mine = torch.tensor(list(h.raw), dtype=torch.uint8, device=self.dev)
+
+        def agree(ok: int) -> bool:
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            return int(flag.item()) == 1
+
+        err = None
+        handle = bytes(64)
+        try:                                                     # phase 1: local allocation + export
+            nbytes = int(lib.b200ppo_comm_bytes(self.net.plan, world))
+            if nbytes <= 0 or world > 16:
+                raise _lib.B200PPOError("peer exchange: unsupported plan or world size")
+            p = C.c_void_p()
+            _lib.check(lib.b200ppo_comm_alloc(nbytes, C.byref(p)), "comm_alloc")
+            self._comm_local = p.value
+            h = C.create_string_buffer(64)
+            _lib.check(lib.b200ppo_comm_ipc_get(p, h), "comm_ipc_get")
+            handle = h.raw
+        except Exception as e:                                   # noqa: BLE001 - decided collectively
+            err = e
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
         allh = torch.zeros(world * 64, dtype=torch.uint8, device=self.dev)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        allh = allh.cpu().numpy().reshape(world, 64)
+        ok = agree(0 if err is not None else 1)
         ptrs = []
-        for r in range(world):
-            if r == rank:
-                ptrs.append(self._comm_local)
-                continue
-            q = C.c_void_p()
-            _lib.check(lib.b200ppo_comm_ipc_open(allh[r].tobytes(), C.byref(q)), f"comm_ipc_open(rank {r})")
-            self._comm_peers.append(q.value)
-            ptrs.append(q.value)
+        if ok:
+            allh = allh.cpu().numpy().reshape(world, 64)
+            try:                                                 # phase 2: map the peers
+                for r in range(world):
+                    if r == rank:
+                        ptrs.append(self._comm_local)
+                        continue
+                    q = C.c_void_p()
+                    _lib.check(lib.b200ppo_comm_ipc_open(allh[r].tobytes(), C.byref(q)), f"comm_ipc_open(rank {r})")
+                    self._comm_peers.append(q.value)
+                    ptrs.append(q.value)
+            except Exception as e:                               # noqa: BLE001
+                err = e
+            ok = agree(0 if err is not None else 1)
+        if not ok:
+            if err is not None:
+                sys.stderr.write(f"[b200ppo] peer-memory exchange unavailable ({err}); using NCCL all-reduce\n")
+            self.close()
+            self.p2p = False
+            dist.barrier(group=self.group)
+            return
         self.comm_table = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
-        for b in self.bufs:
-            b.comm = self.comm_table.data_ptr()
+        for bf in self.bufs:
+            bf.comm = self.comm_table.data_ptr()
         self.hp.rank = rank
         self.p2p = True
 
@@ -191,9 +222,21 @@ class PPOEngine:
 
     def _enqueue(self, env_state) -> int:
         """Enqueue one whole iteration on the current stream.  Returns the number of kernel
-        launches issued by this library (NCCL kernels not counted)."""
-        n = self._enqueue_rollout(env_state)
-        n += self._enqueue_updates(2 * self.T, self.rng_per_iter)
+        launches issued by this library (NCCL kernels not counted).
+
+        Two small pieces do not depend on what runs next to them and go to a side stream (forked /
+        joined with events, so the captured graph gets parallel branches): the minibatch permutation
+        (depends only on the key) runs beside the rollout, and the Normalizer's batch statistics
+        (depend only on the rollout's observations) run beside the updates."""
+        import torch
+        cur = torch.cuda.current_stream()
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            n = self._enqueue_permutation()
+        n += self._enqueue_rollout(env_state)
+        cur.wait_stream(side)
+        n += self._enqueue_updates(2 * self.T, self.rng_per_iter, permute=False, side_stats=True)
         return n
 
     def _enqueue_rollout(self, env_state) -> int:
@@ -212,14 +255,33 @@ class PPOEngine:
             self.trunc.data_ptr(), self.next_obs_last.data_ptr()), "rollout_synth"); n += 1
         return n
 
-    def _enqueue_updates(self, rng_offset0: int, rng_advance: int) -> int:
+    def _enqueue_permutation(self) -> int:
+        _lib.check(self.lib.b200ppo_permutation(_lib.current_stream(), self.iter_keys.data_ptr() + 8, self.B, self.E,
+                                                self.inds.data_ptr(), self.perm_scratch.data_ptr()), "permutation")
+        return 1
+
+    def _enqueue_batch_stats(self) -> int:
+        nz = self.net.normalizer
+        _lib.check(self.lib.b200ppo_norm_batch_stats(_lib.current_stream(), self.obs.data_ptr(), self.T * self.B, nz.size,
+                                                     self.batch_stats.data_ptr(), self.norm_scratch.data_ptr()),
+                   "norm_batch_stats")
+        return 2
+
+    def _enqueue_updates(self, rng_offset0: int, rng_advance: int, permute: bool = True,
+                         side_stats: bool = False) -> int:
         """Permutation indices, the E*M minibatch updates, Normalizer statistics, counters.
         ``rng_offset0`` = sampler counts already consumed since counters[2] was last advanced."""
+        import torch
         lib, net, T, B = self.lib, self.net, self.T, self.B
         s = _lib.current_stream()
         n = 0
-        _lib.check(lib.b200ppo_permutation(s, self.iter_keys.data_ptr() + 8, B, self.E, self.inds.data_ptr(),
-                                           self.perm_scratch.data_ptr()), "permutation"); n += 1
+        if permute:
+            n += self._enqueue_permutation()
+        cur = torch.cuda.current_stream()
+        if side_stats and net.normalizer is not None:
+            self._side.wait_stream(cur)                      # the rollout's observations are complete
+            with torch.cuda.stream(self._side):
+                n += self._enqueue_batch_stats()
         for u in range(self.n_updates):
             off = rng_offset0 + u * 2 * (T + 1)
             args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
@@ -242,9 +304,10 @@ class PPOEngine:
             self._allreduce(self.metrics)
         if net.normalizer is not None:
             nz = net.normalizer
-            _lib.check(lib.b200ppo_norm_batch_stats(s, self.obs.data_ptr(), T * B, nz.size,
-                                                    self.batch_stats.data_ptr(), self.norm_scratch.data_ptr()),
-                       "norm_batch_stats"); n += 2
+            if side_stats:
+                cur.wait_stream(self._side)
+            else:
+                n += self._enqueue_batch_stats()
             src = self.batch_stats
             if self.world > 1:
                 parallel.all_gather_into(self.batch_stats_all.view(-1), self.batch_stats, self.group)

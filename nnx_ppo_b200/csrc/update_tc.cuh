@@ -1132,11 +1132,14 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     uint32_t upar = 1u;                                     // parity to wait on `empty` (first lap skipped)
     bool ufirst = true;
     struct Raw { float4 a, b0, b1; };
+    TC_PROBE_DECL
     // shared -> registers for stage s, then hand the raw slot straight back to the streamer
     auto ld = [&](int s, Raw& x) {
       const int rslot = s & 1;
       const uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
+      TC_PROBE_START();
       wait(&raw_full[rslot], static_cast<uint32_t>(s >> 1) & 1u);
+      TC_PROBE_LAP(0);
       x.a = x.b0 = x.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (av) {
         const uint8_t* q = rw + a_src;
@@ -1171,10 +1174,13 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
       }
       __syncwarp();
       if ((tid & 31) == 0) tc::mbar_arrive(&raw_empty[rslot]);   // release: ordered after the reads above
+      TC_PROBE_LAP(1);
     };
     // registers -> activation, hi/lo split -> UMMA planes of the next ring slot
     auto proc = [&](const Raw& x) {
+      TC_PROBE_START();
       if (!ufirst) wait(&cx.bar_empty[uslot], upar);
+      TC_PROBE_LAP(2);
       uint8_t* ua = cx.smem + uslot * 2u * TC_A_BYTES;
       uint8_t* ub = cx.smem + cx.b_base + uslot * 2u * TC_B_BYTES;
       float4 hi, lo;
@@ -1193,9 +1199,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
         *reinterpret_cast<float4*>(ub + b_dst1) = hi;
         if (split) *reinterpret_cast<float4*>(ub + TC_B_BYTES + b_dst1) = lo;
       }
+      TC_PROBE_LAP(3);
       tc::fence_proxy_async();
       __syncwarp();
       if ((tid & 31) == 0) tc::mbar_arrive(&cx.bar_full_a[uslot]);
+      TC_PROBE_LAP(4);
       if (++uslot == DW2_NS) { uslot = 0; upar ^= 1u; ufirst = false; }
     };
     // software pipeline: the shared-memory reads of stage s+1 are in flight while stage s is split
@@ -1209,6 +1217,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
         proc(xB);
       }
     }
+    if (tid == 0) TC_PROBE_FLUSH(0, 5);
   } else if (warp == TC_NPROD / 32) {
     const TcIssue ti = tc_issue_prepare(cx, npad);
     int uslot = 0;

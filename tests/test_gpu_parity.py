@@ -518,6 +518,38 @@ def test_full_size_iteration_properties(dev):
     assert eng.graph is not None
 
 
+def test_checkpoint_resume_is_bit_identical(dev, tmp_path):
+    """checkpointing.py:42-204 API: save after 2 iterations, keep training; restore into fresh
+    templates and train the same number of iterations -> identical parameters, statistics, keys."""
+    from nnx_ppo_b200.algorithms import checkpointing
+    hyper = (64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+
+    def fresh():
+        nets = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+        env = SyntheticEnv(12, 3, max_len=16, term_thresh16=2000)
+        return env, nets, ppo.new_training_state(env, nets, 64, 3)
+
+    env, nets, ts = fresh()
+    for _ in range(2):
+        ts, _m = ppo.ppo_step(env, ts, *hyper)
+    ck = checkpointing.make_checkpoint_fn(str(tmp_path), config=TrainConfig())
+    ck(ts, 1024)
+    for _ in range(2):
+        ts, _m = ppo.ppo_step(env, ts, *hyper)
+    net = compile_network(nets)
+    ref = (net.params_logical().copy(), net.normalizer.mean.numpy().copy(), tuple(ts.rng_key), float(ts.steps_taken))
+
+    env2, nets2, ts2 = fresh()
+    out = checkpointing.load_checkpoint(os.path.join(str(tmp_path), "step_0000001024"), nets2, ts2.optimizer)
+    assert out["step"] == 1024 and isinstance(out["config"], TrainConfig)
+    ts2 = out["training_state"]
+    for _ in range(2):
+        ts2, _m = ppo.ppo_step(env2, ts2, *hyper)
+    net2 = compile_network(nets2)
+    assert np.array_equal(net2.params_logical(), ref[0]) and np.array_equal(net2.normalizer.mean.numpy(), ref[1])
+    assert tuple(ts2.rng_key) == ref[2] and float(ts2.steps_taken) == ref[3]
+
+
 def test_train_ppo_api(dev):
     """ppo_test.py:213-227 / 307-349 style: total steps, counter, finite metrics, log cadence."""
     env = SyntheticEnv(16, 4, max_len=32)

@@ -97,9 +97,48 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
     per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
     metrics = _loss_metrics(per_update, logging_level, logging_percentiles)
+    if LoggingLevel.GRAD_NORM in logging_level and eng.hp.grad_clip > 0.0:
+        metrics["grad_norm"] = per_update[:, 3].copy()                   # ppo.py:313-315 (one value per update)
+    _extra_metrics(metrics, eng.net, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps                                 # ppo.py:333
     new_state = training_state.replace(rng_key=new_key, steps_taken=total_steps)
     return new_state, metrics
+
+
+def _log_metric(m: dict, name: str, x, percentiles) -> None:
+    """metrics.py:72-100 on a CUDA tensor: bool -> fraction true; else mean / std or percentiles.
+    (Logging only: a handful of reductions over buffers the kernels already wrote.)"""
+    import torch
+    if x.dtype in (torch.bool, torch.uint8):
+        m[name] = np.float32(x.float().mean().item())
+    elif not percentiles:
+        x = x.float()
+        m[f"{name}/mean"] = np.float32(x.mean().item())
+        m[f"{name}/std"] = np.float32(x.std(unbiased=False).item())
+    else:
+        q = torch.tensor([p / 100.0 for p in percentiles], device=x.device)
+        xs = x.float().reshape(-1)
+        if xs.numel() > 1_000_000:                       # torch.quantile's input limit: subsample evenly
+            xs = xs[:: xs.numel() // 1_000_000 + 1]
+        for pl, v in zip(percentiles, torch.quantile(xs, q).tolist()):
+            m[f"{name}/p{int(pl)}"] = np.float32(v)
+
+
+def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
+    """The parts of metrics.compute_metrics / log_weight_stats (metrics.py:17-121) that only need the
+    rollout buffers and the parameter arena.  Not produced by this build: losses/clipping_fraction,
+    losses/critic_R^2, losses/advantages, losses/predicted_value (the fused rollout does not evaluate
+    the critic), per-update grad_norm without gradient clipping, env metrics, ROLLOUT_OBS."""
+    if LoggingLevel.TRAIN_ROLLOUT_STATS in logging_level:
+        _log_metric(m, "rollout_batch/reward", eng.reward, percentiles)
+        _log_metric(m, "rollout_batch/action", eng.action, percentiles)
+        _log_metric(m, "rollout_batch/done_rate", eng.done, percentiles)
+        _log_metric(m, "rollout_batch/truncation_rate", eng.trunc, percentiles)
+    if LoggingLevel.ACTOR_EXTRA in logging_level:
+        _log_metric(m, "loglikelihood", eng.loglik, percentiles)
+    if LoggingLevel.WEIGHTS in logging_level:
+        w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask != 0]
+        _log_metric(m, "weights", w, percentiles)
 
 
 def _loss_metrics(per_update: np.ndarray, logging_level, percentiles) -> dict[str, Any]:

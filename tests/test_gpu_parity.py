@@ -550,6 +550,25 @@ def test_checkpoint_resume_is_bit_identical(dev, tmp_path):
     assert tuple(ts2.rng_key) == ref[2] and float(ts2.steps_taken) == ref[3]
 
 
+def test_logging_levels(dev):
+    """metrics.py:17-121 keys for the levels this build produces (values against the rollout buffers)."""
+    from nnx_ppo_b200.algorithms.types import LoggingLevel
+    nets = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    env = SyntheticEnv(12, 3, max_len=16, term_thresh16=2000)
+    ts = ppo.new_training_state(env, nets, 64, 3, gradient_clipping=0.5)
+    lvl = LoggingLevel.LOSSES | LoggingLevel.TRAIN_ROLLOUT_STATS | LoggingLevel.ACTOR_EXTRA | LoggingLevel.WEIGHTS | LoggingLevel.GRAD_NORM
+    ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2, logging_level=lvl)
+    eng = next(iter(compile_network(nets).engines.values()))
+    assert abs(m["rollout_batch/reward/mean"] - float(eng.reward.mean())) < 1e-6
+    assert abs(m["rollout_batch/done_rate"] - float(eng.done.float().mean())) < 1e-7
+    assert {"rollout_batch/action/std", "rollout_batch/truncation_rate", "loglikelihood/mean", "weights/std"} <= set(m)
+    assert m["grad_norm"].shape == (4,) and np.all(m["grad_norm"] > 0)
+    ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2, logging_level=lvl,
+                         logging_percentiles=(0, 50, 100))
+    assert m["rollout_batch/reward/p0"] <= m["rollout_batch/reward/p50"] <= m["rollout_batch/reward/p100"]
+    assert "losses/actor/p50" in m and "weights/p100" in m
+
+
 def test_train_ppo_api(dev):
     """ppo_test.py:213-227 / 307-349 style: total steps, counter, finite metrics, log cadence."""
     env = SyntheticEnv(16, 4, max_len=32)

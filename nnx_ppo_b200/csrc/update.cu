@@ -55,6 +55,10 @@ struct TcLayer {
 struct Layout {
   int R, Rv, S, n_tiles, rows_per_split;
   int tc_ok, tc_tiles, tc_S, tc_rows_per_split, tc_dw_bulk;
+  // per dW item (M-tile of a layer): number of row splits and rows per split.  Items whose operand is
+  // wider than 128 columns cost ~1.2x per stage (tensor bound), so they get more, shorter splits;
+  // tc_S is the maximum (rows of the partial-gradient buffer); slots an item does not use are zeroed
+  int tc_item_S[32], tc_item_rps[32];
   TcLayer tca[MAXL], tcc[MAXL];
   size_t xhat, adv, gpart, grad;
   size_t za[MAXL], zc[MAXL], da[MAXL], dc[MAXL];
@@ -122,13 +126,33 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
       L.tc_tiles += cdiv(K, 128);
     }
   }
-  int tS = sms / (L.tc_tiles > 0 ? L.tc_tiles : 1);
-  if (tS < 1) tS = 1;
-  if (tS > 64) tS = 64;
-  int trps = cdiv(cdiv(L.R, tS), 32) * 32;
-  if (trps < 32) trps = 32;
-  L.tc_S = cdiv(L.R, trps);
-  L.tc_rows_per_split = trps;
+  {
+    double wsum = 0.0;
+    double wts[32];
+    int ni = 0;
+    for (int c = 0; c < 2; ++c) {
+      const b200ppo_chain& ch = c == 0 ? p.actor : p.critic;
+      for (int l = 0; l < ch.n_layers; ++l)
+        for (int m = 0; m < cdiv(ch.dims[l], 128) && ni < 32; ++m) {
+          wts[ni] = ch.dims[l + 1] > 128 ? 1.2 : 1.0;
+          wsum += wts[ni++];
+        }
+    }
+    if (L.tc_tiles > 32) L.tc_ok = 0;
+    L.tc_S = 1;
+    for (int i = 0; i < ni; ++i) {
+      int Si = static_cast<int>(sms * wts[i] / wsum);
+      if (Si < 1) Si = 1;
+      if (Si > 64) Si = 64;
+      int rps_i = cdiv(cdiv(L.R, Si), 32) * 32;
+      if (rps_i < 32) rps_i = 32;
+      L.tc_item_rps[i] = rps_i;
+      L.tc_item_S[i] = cdiv(L.R, rps_i);
+      if (L.tc_item_S[i] > L.tc_S) L.tc_S = L.tc_item_S[i];
+    }
+    for (int i = ni; i < 32; ++i) { L.tc_item_S[i] = 0; L.tc_item_rps[i] = 32; }
+    L.tc_rows_per_split = L.tc_item_rps[0];
+  }
   const int smax = L.tc_S > S ? L.tc_S : S;
   L.gpart = take(static_cast<size_t>(smax) * p.n_params);
   L.grad = take(p.n_params);
@@ -158,9 +182,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // spin until every rank's flag (written into OUR buffer by that rank) has reached `epoch`; the
 // acquire orders the data reads that follow (all data is pushed into our own buffer: no remote loads)

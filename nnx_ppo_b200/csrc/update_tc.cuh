@@ -887,6 +887,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
     }
   }
   if (layer < 0) return;                                   // uniform per CTA
+  if (static_cast<int>(blockIdx.y) >= a.L.tc_item_S[blockIdx.x + item_base]) return;   // this item has fewer row splits
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
   if (g_tc_stamp_skip_dw & 1) cx.nstamp = -100000;
@@ -897,9 +898,15 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   const int act_in = layer == 0 ? B200PPO_ACT_NONE : ch->act;
   const float* D = a.ws + doff[layer];
   const int sp = blockIdx.y;
-  const int r_begin = sp * a.L.tc_rows_per_split;
-  int r_end = r_begin + a.L.tc_rows_per_split;
+  const int item_id = blockIdx.x + item_base;
+  const int Si = a.L.tc_item_S[item_id];                   // this item's number of row splits (<= gridDim.y)
+  const int rps = a.L.tc_item_rps[item_id];
+  const int r_begin = sp * rps;
+  int r_end = r_begin + rps;
   if (r_end > a.L.R) r_end = a.L.R;
+  // partial-gradient slots this item leaves unused (sp + Si, sp + 2 Si, ... < tc_S) are zeroed here,
+  // so the fixed-order reduction over all tc_S slots stays valid whatever ran on this workspace before
+  const int S_all = a.L.tc_S;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = (r_end - r_begin + TCK - 1) / TCK;
@@ -1021,6 +1028,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
               if (col + 2 < N) dst[2] = val.z;
               if (col + 3 < N) dst[3] = val.w;
             }
+            for (int s2 = sp + Si; s2 < S_all; s2 += Si) {
+              float* dz = dst + static_cast<size_t>(s2 - sp) * a.plan.n_params;
+              for (int i = 0; i < 4; ++i)
+                if (col + i < N) dz[i] = 0.0f;
+            }
           }
           return val;
         });
@@ -1029,7 +1041,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   if (mt == 0) {                                           // bias gradient: fixed-order column sums
     if (tid < TC_NPROD) bred[tid] = bsum;
     __syncthreads();
-    if (tid < N && tid < 256) gpart[ch->b_off[layer] + tid] = bred[tid] + bred[tid + 256];
+    if (tid < N && tid < 256) {
+      gpart[ch->b_off[layer] + tid] = bred[tid] + bred[tid + 256];
+      for (int s2 = sp + Si; s2 < S_all; s2 += Si)
+        gpart[static_cast<size_t>(s2 - sp) * a.plan.n_params + ch->b_off[layer] + tid] = 0.0f;
+    }
   }
   tc_ctx_fini(cx);
 }
@@ -1075,6 +1091,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     }
   }
   if (layer < 0) return;                                   // uniform per CTA
+  if (static_cast<int>(blockIdx.y) >= a.L.tc_item_S[blockIdx.x + item_base]) return;   // this item has fewer row splits
   if (threadIdx.x == 64) {
 #pragma unroll
     for (int i = 0; i < DW2_NR; ++i) {
@@ -1095,9 +1112,15 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   const int act_in = layer == 0 ? B200PPO_ACT_NONE : ch->act;
   const float* D = a.ws + doff[layer];
   const int sp = blockIdx.y;
-  const int r_begin = sp * a.L.tc_rows_per_split;
-  int r_end = r_begin + a.L.tc_rows_per_split;
+  const int item_id = blockIdx.x + item_base;
+  const int Si = a.L.tc_item_S[item_id];                   // this item's number of row splits (<= gridDim.y)
+  const int rps = a.L.tc_item_rps[item_id];
+  const int r_begin = sp * rps;
+  int r_end = r_begin + rps;
   if (r_end > a.L.R) r_end = a.L.R;
+  // partial-gradient slots this item leaves unused (sp + Si, sp + 2 Si, ... < tc_S) are zeroed here,
+  // so the fixed-order reduction over all tc_S slots stays valid whatever ran on this workspace before
+  const int S_all = a.L.tc_S;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t pa = tc::plane_bytes(TCM), pb = tc::plane_bytes(npad);
   const int nst = r_end > r_begin ? (r_end - r_begin + TCK - 1) / TCK : 0;
@@ -1271,6 +1294,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
               if (col + 2 < N) dst[2] = val.z;
               if (col + 3 < N) dst[3] = val.w;
             }
+            for (int s2 = sp + Si; s2 < S_all; s2 += Si) {
+              float* dz = dst + static_cast<size_t>(s2 - sp) * a.plan.n_params;
+              for (int i = 0; i < 4; ++i)
+                if (col + i < N) dz[i] = 0.0f;
+            }
           }
           return val;
         });
@@ -1283,6 +1311,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
       float acc = 0.0f;
       for (int cc = tid; cc < 4 * npad; cc += npad) acc += bred[cc / TC_NPROD][cc % TC_NPROD];
       gpart[ch->b_off[layer] + tid] = acc;
+      for (int s2 = sp + Si; s2 < S_all; s2 += Si)
+        gpart[static_cast<size_t>(s2 - sp) * a.plan.n_params + ch->b_off[layer] + tid] = 0.0f;
     }
   }
   tc_ctx_fini(cx);

@@ -49,6 +49,24 @@ class AdamOptimizer:
         return float(self.weight_decay)
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(dev):
+    """One side stream per device, shared by every engine.  torch hands out streams round-robin from
+    a pool of 32 per priority, so a stream per engine eventually aliases another stream object —
+    including the one `torch.cuda.graph` captures on (seen as cudaErrorStreamCaptureInvalidated after
+    ~40 engines in one process).  The high-priority pool is separate from the default-priority one
+    torch's capture stream comes from."""
+    import torch
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=dev, priority=-1)
+        _SIDE_STREAMS[key] = st
+    return st
+
+
 class PPOEngine:
     def __init__(self, net: CompiledNet, env, opt: AdamOptimizer, n_envs: int, rollout_length: int,
                  n_epochs: int, n_minibatches: int, gae_lambda: float, discounting_factor: float,
@@ -126,7 +144,7 @@ class PPOEngine:
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory
         # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
         self.fuse_prep = os.environ.get("B200PPO_FUSE_PREP", "1") != "0"
-        self._side = torch.cuda.Stream(device=dev)
+        self._side = _side_stream(dev)
         self.p2p = False
         self._comm_local, self._comm_peers, self.comm_table = None, [], None
         if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0" and not self.hp.grad_clip > 0.0:

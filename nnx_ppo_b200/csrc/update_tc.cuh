@@ -528,7 +528,8 @@ __device__ __forceinline__ void tc_chain_setup(TcCtx& cx, const b200ppo_chain& c
 
 __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,
                                                  const float* __restrict__ P, float* ws, const size_t* zoff,
-                                                 size_t xhat_off, int row0, int nrows, int split, TcFwdSmem& sm) {
+                                                 size_t xhat_off, int row0, int nrows, int split, TcFwdSmem& sm,
+                                                 bool chain_in0 = false) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const int L = ch.n_layers;
   // a thin last layer (the critic's 256 -> 1 head) is a per-row dot product: fused into the
@@ -543,7 +544,7 @@ __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain&
       sm.bias[l][n] = n < ch.dims[l + 1] ? __ldg(P + ch.b_off[l] + n) : 0.0f;
     }
   }
-  bool chain_in = false;                 // this GEMM's A stages come from the previous epilogue
+  bool chain_in = chain_in0;             // this GEMM's A stages are already staged (previous epilogue / obs gather)
   for (int l = 0; l < Lg; ++l) {
     const int K = ch.dims[l], N = ch.dims[l + 1];
     const float* A = l == 0 ? ws + xhat_off : ws + zoff[l - 1];
@@ -689,7 +690,42 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   }
   __syncthreads();
   // gather + normalise this tile's observations (ppo.py:297 gather; normalizer.py:78-80)
-  if ((O & 3) == 0) {
+  // For obs_dim <= 64 the normalised chunk also goes straight into the first critic GEMM's A stages
+  // (hi / lo split, ring slots 0..nst-1: the ring is still empty), so that GEMM needs no producer pass
+  // and no global round trip; xhat is still written for the actor's first layer and for dW.
+  const bool fuse0 = (chains & 1) && (O & 3) == 0 && O <= TC_NS * TCK;
+  if (fuse0) {
+    if (threadIdx.x < TC_NPROD) {
+      const int O4 = O >> 2;
+      const int nst0 = (O + TCK - 1) / TCK, C4 = nst0 * 4;
+      const uint32_t pa0 = tc::plane_bytes(TCM);
+#pragma unroll 4
+      for (int idx = threadIdx.x; idx < TCM * C4; idx += TC_NPROD) {
+        const int m = idx / C4, c4 = idx - m * C4;
+        const float* src = rowsrc[m];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src != nullptr && c4 < O4) {
+          x = *reinterpret_cast<const float4*>(src + 4 * c4);
+          if (a.plan.normalize) {
+            const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mean) + c4);
+            const float4 sd = __ldg(reinterpret_cast<const float4*>(a.std) + c4);
+            x.x = __fdiv_rn(x.x - mu.x, sd.x); x.y = __fdiv_rn(x.y - mu.y, sd.y);
+            x.z = __fdiv_rn(x.z - mu.z, sd.z); x.w = __fdiv_rn(x.w - mu.w, sd.w);
+          }
+          *reinterpret_cast<float4*>(xhat + static_cast<size_t>(row0 + m) * O + 4 * c4) = x;
+        }
+        float4 hi, lo;
+        tc::split4_fast(x, hi, lo);
+        uint8_t* dst = cx.smem + (c4 >> 2) * 2u * TC_A_BYTES + (c4 & 3) * pa0 + m * 16;
+        *reinterpret_cast<float4*>(dst) = hi;
+        if (split) *reinterpret_cast<float4*>(dst + TC_A_BYTES) = lo;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0)
+        for (int st = 0; st < nst0; ++st) tc::mbar_arrive(&cx.bar_full_a[st]);
+    }
+  } else if ((O & 3) == 0) {
     const int O4 = O >> 2;
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < TCM * O4; idx += TCT) {
@@ -718,7 +754,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   }
   __syncthreads();
   tc_stamp(cx.nstamp);
-  if (chains & 1) tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, sm);
+  if (chains & 1) tc_chain_forward(cx, a.plan.critic, a.L.tcc, a.params, a.ws, a.L.zc, a.L.xhat, row0, Rv, split, sm, fuse0);
   if ((chains & 2) && row0 < R) tc_chain_forward(cx, a.plan.actor, a.L.tca, a.params, a.ws, a.L.za, a.L.xhat, row0, R, split, sm);
   tc_ctx_fini(cx);
 }

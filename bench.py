@@ -284,6 +284,9 @@ def run_own(args):
                             "compute_path": ("tcgen05.mma kind::tf32, error-compensated 3xTF32 (3 MMAs per algorithmic product, fp32 accumulate in TMEM): "
                                              "achieved counts ALGORITHMIC flops; tensor-pipe work is 3x that" if mode == 1 else
                                              ("tcgen05.mma kind::tf32, plain TF32 (not fp32 parity)" if mode == 2 else "fp32 FFMA (CUDA cores)")),
+                            # tf32 MMAs run at half the bf16 rate and every algorithmic product costs three of
+                            # them: the ceiling of this formulation is peak / 6
+                            "ceiling_3xtf32_tflops": tf_peak / 6.0, "frac_of_3xtf32_ceiling": ach / (tf_peak / 6.0),
                             "ffma_peak_tflops": ffma_tf, "frac_of_ffma_peak": ach / ffma_tf,
                             "flop_per_launch": flops[dom], "launch_ms": stage_ms[dom] / U,
                             "stage_ms_per_iteration": stage_ms,

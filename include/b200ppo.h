@@ -81,6 +81,8 @@ typedef struct b200ppo_hparams {
   int32_t rank;             /* this process' rank (only read when bufs->comm is set)      */
 } b200ppo_hparams;
 
+#define B200PPO_METRICS_STRIDE 12
+
 /* Device buffers of one minibatch update.  ws is a scratch arena of
  * b200ppo_update_workspace_bytes() bytes, 256-byte aligned. */
 typedef struct b200ppo_update_bufs {
@@ -102,7 +104,10 @@ typedef struct b200ppo_update_bufs {
   float* adam_nu;              /* dev [P]                                                          */
   /* counters: [0..1] sampler stream key, [2] sampler count base, [3] adam count base */
   const uint32_t* rng_state;   /* dev uint32[4]                                                    */
-  float* metrics_out;          /* dev [4]: actor loss, critic loss, regularisation loss, grad norm */
+  float* metrics_out;          /* dev [B200PPO_METRICS_STRIDE]: [0] actor loss, [1] critic loss,
+                                * [2] regularisation loss, [3] grad norm (with gradient clipping),
+                                * [4] clipping fraction, [5] E[target], [6] E[target^2], [7] E[adv],
+                                * [8] E[adv^2] - all divided by the global sample count */
   void* ws;                    /* dev scratch                                                      */
   /* optional peer-memory exchange (NULL: the caller all-reduces adv_sums and the gradient between
    * the stages).  dev uint64[world_size]: base address of every rank's comm buffer

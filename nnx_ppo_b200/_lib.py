@@ -18,6 +18,7 @@ STAGE_FWD, STAGE_GAE, STAGE_LOSS, STAGE_BWD, STAGE_RED, STAGE_ADAM = 1, 2, 4, 8,
 STAGE_ALL = 63
 STAGE_BWD_DX, STAGE_BWD_DW = 64, 128
 STAGE_NO_PREP = 256
+METRICS_STRIDE = 12   # B200PPO_METRICS_STRIDE
 
 
 class Chain(C.Structure):

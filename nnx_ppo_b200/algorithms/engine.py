@@ -103,8 +103,8 @@ class PPOEngine:
         # zero-initialised: tickets and the alignment padding of the gradient arena rely on it
         self.ws = torch.zeros(ws_bytes // 4, **f32)
         self.n_updates = self.E * self.M
-        self.metrics = torch.zeros(self.n_updates, 4, **f32)
-        self.metrics_host = torch.zeros(self.n_updates, 4, dtype=torch.float32).pin_memory()
+        self.metrics = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, **f32)
+        self.metrics_host = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, dtype=torch.float32).pin_memory()
         self.iter_keys = torch.zeros(4, dtype=torch.int32, device=dev)
         self.iter_keys_host = torch.zeros(4, dtype=torch.int32).pin_memory()
         self.norm_scratch = torch.zeros(int(self.lib.b200ppo_norm_scratch_bytes(O)) // 4 + 64, **f32)
@@ -135,7 +135,7 @@ class PPOEngine:
             b.norm_mean, b.norm_std = net.norm_ptrs()
             b.params, b.adam_mu, b.adam_nu = net.arena.data_ptr(), opt.mu.data_ptr(), opt.nu.data_ptr()
             b.rng_state = net.counters.data_ptr()
-            b.metrics_out = self.metrics.data_ptr() + 16 * u
+            b.metrics_out = self.metrics.data_ptr() + 4 * _lib.METRICS_STRIDE * u
             b.ws = wsp
             pm = getattr(net, "param_mask", None)
             b.param_mask = pm.data_ptr() if pm is not None else 0
@@ -377,4 +377,4 @@ class PPOEngine:
         return 16
 
     def d2h_bytes_per_step(self) -> int:
-        return self.n_updates * 16
+        return self.n_updates * 4 * _lib.METRICS_STRIDE

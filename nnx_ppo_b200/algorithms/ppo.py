@@ -126,9 +126,9 @@ def _log_metric(m: dict, name: str, x, percentiles) -> None:
 
 def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
     """The parts of metrics.compute_metrics / log_weight_stats (metrics.py:17-121) that only need the
-    rollout buffers and the parameter arena.  Not produced by this build: losses/clipping_fraction,
-    losses/critic_R^2, losses/advantages, losses/predicted_value (the fused rollout does not evaluate
-    the critic), per-update grad_norm without gradient clipping, env metrics, ROLLOUT_OBS."""
+    rollout buffers and the parameter arena.  Not produced by this build: losses/predicted_value (the
+    fused rollout does not evaluate the critic), percentiles of losses/advantages, per-update grad_norm
+    without gradient clipping, env metrics, ROLLOUT_OBS."""
     if LoggingLevel.TRAIN_ROLLOUT_STATS in logging_level:
         _log_metric(m, "rollout_batch/reward", eng.reward, percentiles)
         _log_metric(m, "rollout_batch/action", eng.action, percentiles)
@@ -153,6 +153,25 @@ def _loss_metrics(per_update: np.ndarray, logging_level, percentiles) -> dict[st
             else:
                 m[f"{name}/mean"] = x.mean(dtype=np.float32)
                 m[f"{name}/std"] = x.std(dtype=np.float32)
+
+    def log(name, x):
+        if percentiles:
+            for pl, p in zip(percentiles, np.percentile(x, percentiles)):
+                m[f"{name}/p{int(pl)}"] = np.float32(p)
+        else:
+            m[f"{name}/mean"] = x.mean(dtype=np.float32)
+            m[f"{name}/std"] = x.std(dtype=np.float32)
+
+    if per_update.shape[1] > 8:
+        if LoggingLevel.ACTOR_EXTRA in logging_level:                      # ppo.py:514-520
+            log("losses/clipping_fraction", per_update[:, 4])
+        if LoggingLevel.CRITIC_EXTRA in logging_level:                     # ppo.py:522-527
+            var_t = np.maximum(per_update[:, 6].astype(np.float64) - per_update[:, 5].astype(np.float64) ** 2, 0.0)
+            log("losses/critic_R^2", (1.0 - 2.0 * per_update[:, 1] / (var_t + 1e-8)).astype(np.float32))
+            # losses/advantages is the raw [updates, T, mb] array in the reference: mean / std over all of it
+            mean = per_update[:, 7].astype(np.float64).mean()
+            m["losses/advantages/mean"] = np.float32(mean)
+            m["losses/advantages/std"] = np.float32(np.sqrt(max(per_update[:, 8].astype(np.float64).mean() - mean * mean, 0.0)))
     return m
 
 

@@ -43,7 +43,8 @@ constexpr int MAX_PART_BLOCKS = 1024;   // GAE / grad-norm partial blocks
 constexpr int MAX_LOSS_BLOCKS = 4096;   // loss partial blocks (R <= 524288 rows per update)
 constexpr int DBL_GAE_PART = 8;
 constexpr int DBL_LOSS_PART = DBL_GAE_PART + 2 * MAX_PART_BLOCKS;
-constexpr int DBL_GN_PART = DBL_LOSS_PART + 3 * MAX_LOSS_BLOCKS;
+constexpr int NLQ = 6;                   // loss partial sums: actor, critic, reg, clipped count, sum target, sum target^2
+constexpr int DBL_GN_PART = DBL_LOSS_PART + NLQ * MAX_LOSS_BLOCKS;
 constexpr int DBL_TOTAL = DBL_GN_PART + MAX_PART_BLOCKS;
 
 // pre-split (hi / lo tf32) weight operands of one layer for the tensor-core path
@@ -588,8 +589,23 @@ __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean,
   a_den = static_cast<float>(sqrt(var)) + 1e-8f;
 }
 
+// metrics_out (B200PPO_METRICS_STRIDE floats per update, include/b200ppo.h): [0] actor loss, [1] critic
+// loss, [2] regularisation loss, [3] grad norm (Adam kernel), [4] clipping fraction (ppo.py:514-520),
+// [5] E[target], [6] E[target^2] (for critic R^2, ppo.py:522-527), [7] E[adv], [8] E[adv^2] — all
+// divided by the GLOBAL sample count, so a data-parallel SUM over ranks gives the global means.
+__device__ __forceinline__ void loss_write_metrics(const LossArgs& a, const double (&s)[NLQ]) {
+  const double ng = a.n_global;
+  const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
+  for (int q = 0; q < 3; ++q) a.metrics_out[q] = static_cast<float>(s[q] / ng);
+  a.metrics_out[4] = static_cast<float>(s[3] / ng);
+  a.metrics_out[5] = static_cast<float>(s[4] / ng);
+  a.metrics_out[6] = static_cast<float>(s[5] / ng);
+  a.metrics_out[7] = static_cast<float>(__ldcg(dbl) / ng);          // this rank's advantage sums (GAE kernel)
+  a.metrics_out[8] = static_cast<float>(__ldcg(dbl + 1) / ng);
+}
+
 __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
-  __shared__ double red[3][4];
+  __shared__ double red[NLQ][4];
   __shared__ float stats0_s[2];
   const int A = a.plan.act_dim;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   if (threadIdx.x == 0) loss_adv_stats(a, stats0_s[0], stats0_s[1]);
   __syncthreads();
   const float a_mean = stats0_s[0], a_den = stats0_s[1];
-  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
+  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0, l_clip = 0.0, l_t1 = 0.0, l_t2 = 0.0;
   if (r < a.L.R) {
     const int t = r / a.mb, j = r - t * a.mb;
     const size_t grow = static_cast<size_t>(t) * a.B + a.inds[j];
@@ -631,6 +647,9 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
     l_actor = -static_cast<double>(fminf(c1, c2));
     l_critic = 0.5 * static_cast<double>(diff) * diff;
     l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
+    l_clip = fabsf(ratio - 1.0f) > a.clip ? 1.0 : 0.0;
+    l_t1 = target;
+    l_t2 = static_cast<double>(target) * target;
     // JAX tie rules: minimum and clip split the cotangent 0.5 / 0.5 on exact ties
     const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
     const float w2 = 1.0f - w1;
@@ -651,28 +670,26 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
     }
     a.ws[a.dv_off + r] = a.critic_w * diff * inv_n;
   }
-  l_actor = warp_sum_d(l_actor);
-  l_critic = warp_sum_d(l_critic);
-  l_reg = warp_sum_d(l_reg);
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = l_actor;
-    red[1][threadIdx.x >> 5] = l_critic;
-    red[2][threadIdx.x >> 5] = l_reg;
+  double lq[NLQ] = {l_actor, l_critic, l_reg, l_clip, l_t1, l_t2};
+#pragma unroll
+  for (int q = 0; q < NLQ; ++q) {
+    lq[q] = warp_sum_d(lq[q]);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = lq[q];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double* part = reinterpret_cast<double*>(a.ws + a.L.dbl) + DBL_LOSS_PART;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
-    for (int q = 0; q < 3; ++q) part[3 * blockIdx.x + q] = red[q][0] + red[q][1] + red[q][2] + red[q][3];
+    for (int q = 0; q < NLQ; ++q) part[NLQ * blockIdx.x + q] = red[q][0] + red[q][1] + red[q][2] + red[q][3];
     __threadfence();
     const unsigned int tk = atomicAdd(&ticket[1], 1u);
     if (tk == gridDim.x - 1) {
       ticket[1] = 0u;
       __threadfence();
-      double s[3] = {0.0, 0.0, 0.0};
+      double s[NLQ] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (unsigned int b = 0; b < gridDim.x; ++b)
-        for (int q = 0; q < 3; ++q) s[q] += __ldcg(&part[3 * b + q]);
-      for (int q = 0; q < 3; ++q) a.metrics_out[q] = static_cast<float>(s[q] / ng);
+        for (int q = 0; q < NLQ; ++q) s[q] += __ldcg(&part[NLQ * b + q]);
+      loss_write_metrics(a, s);
     }
   }
 }
@@ -682,7 +699,7 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
 // (log-lik, entropy) are butterfly reductions over the A adjacent lanes.  ncu: the thread-per-row
 // version ran 4 warps per SM on long dependent chains (27 us per launch).
 __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
-  __shared__ double red[3][8];
+  __shared__ double red[NLQ][8];
   __shared__ float stats_s[2];
   const int A = a.plan.act_dim;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -720,7 +737,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   if (threadIdx.x == 0) loss_adv_stats(a, stats_s[0], stats_s[1]);
   __syncthreads();
   const float a_mean = stats_s[0], a_den = stats_s[1];
-  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0;
+  double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0, l_clip = 0.0, l_t1 = 0.0, l_t2 = 0.0;
   if (valid) {
     const float adv = a.ws[a.L.adv + r];
     const float v = a.ws[a.v_off + r];
@@ -748,25 +765,26 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
       l_actor = -static_cast<double>(fminf(c1, c2));
       l_critic = 0.5 * static_cast<double>(diff) * diff;
       l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
+      l_clip = fabsf(ratio - 1.0f) > a.clip ? 1.0 : 0.0;
+      l_t1 = target;
+      l_t2 = static_cast<double>(target) * target;
     }
   }
-  l_actor = warp_sum_d(l_actor);
-  l_critic = warp_sum_d(l_critic);
-  l_reg = warp_sum_d(l_reg);
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = l_actor;
-    red[1][threadIdx.x >> 5] = l_critic;
-    red[2][threadIdx.x >> 5] = l_reg;
+  double lq[NLQ] = {l_actor, l_critic, l_reg, l_clip, l_t1, l_t2};
+#pragma unroll
+  for (int q = 0; q < NLQ; ++q) {
+    lq[q] = warp_sum_d(lq[q]);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = lq[q];
   }
   __syncthreads();
   __shared__ bool is_last_s;
   double* part = reinterpret_cast<double*>(a.ws + a.L.dbl) + DBL_LOSS_PART;
   if (threadIdx.x == 0) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets);
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < NLQ; ++q) {
       double sacc = 0.0;
       for (int w = 0; w < 8; ++w) sacc += red[q][w];
-      part[3 * blockIdx.x + q] = sacc;
+      part[NLQ * blockIdx.x + q] = sacc;
     }
     __threadfence();
     const unsigned int tk = atomicAdd(&ticket[1], 1u);
@@ -778,18 +796,22 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     // the last block sums the per-block partials with all its threads (strided loads in flight
     // together, then a fixed-order tree): deterministic, and not a serial latency chain
     __threadfence();
-    double acc[3] = {0.0, 0.0, 0.0};
+    double acc[NLQ] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-      for (int q = 0; q < 3; ++q) acc[q] += __ldcg(&part[3 * b + q]);
-    for (int q = 0; q < 3; ++q) acc[q] = warp_sum_d(acc[q]);
+      for (int q = 0; q < NLQ; ++q) acc[q] += __ldcg(&part[NLQ * b + q]);
+    for (int q = 0; q < NLQ; ++q) acc[q] = warp_sum_d(acc[q]);
     __syncthreads();
     if ((threadIdx.x & 31) == 0)
-      for (int q = 0; q < 3; ++q) red[q][threadIdx.x >> 5] = acc[q];
+      for (int q = 0; q < NLQ; ++q) red[q][threadIdx.x >> 5] = acc[q];
     __syncthreads();
-    if (threadIdx.x < 3) {
-      double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
-      a.metrics_out[threadIdx.x] = static_cast<float>(t / ng);
+    if (threadIdx.x == 0) {
+      double tot[NLQ];
+      for (int q = 0; q < NLQ; ++q) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[q][w];
+        tot[q] = t;
+      }
+      loss_write_metrics(a, tot);
     }
   }
 }

@@ -153,7 +153,10 @@ def loss_head(net, ro: Rollout, inds: np.ndarray, rng_count_base: int, y, v, v_l
     metrics = {"losses/actor": actor_loss, "losses/critic": critic_loss,
                "losses/regularization": reg_loss, "adv_mean": adv.mean(dtype=F),
                "adv_std": adv.std(dtype=F), "adv": adv.reshape(T, mb), "values": v.reshape(T, mb),
-               "v_last": v_last, "loglik": ll.reshape(T, mb), "eps2": eps2.reshape(T, mb, A)}
+               "v_last": v_last, "loglik": ll.reshape(T, mb), "eps2": eps2.reshape(T, mb, A),
+               # ppo.py:514-527 (ACTOR_EXTRA / CRITIC_EXTRA)
+               "losses/clipping_fraction": F(np.mean(np.abs(ratio - F(1)) > F(clip_range))),
+               "losses/critic_R^2": F(1.0 - 2.0 * float(critic_loss) / (float(np.var(target.astype(np.float64))) + 1e-8))}
     if not want_grads:
         return total, metrics, None, None
 

@@ -347,6 +347,11 @@ def _single_update(dev, cfg, loose):
     met = eng.metrics[0].cpu().numpy()
     assert abs(met[0] - m["losses/actor"]) < 1e-5 * loose and abs(met[1] - m["losses/critic"]) < 1e-4 * loose * max(1, abs(m["losses/critic"]))
     assert abs(met[2] - m["losses/regularization"]) < 1e-5 * loose
+    # ACTOR_EXTRA / CRITIC_EXTRA statistics of the same launch (ppo.py:514-527)
+    assert abs(met[4] - m["losses/clipping_fraction"]) <= (2.0 / R) * loose + 1e-7      # a borderline ratio may flip
+    r2 = 1.0 - 2.0 * met[1] / (max(met[6] - met[5] ** 2, 0.0) + 1e-8)
+    assert abs(r2 - m["losses/critic_R^2"]) < 2e-3 * loose * max(1.0, abs(m["losses/critic_R^2"]))
+    assert abs(met[7] - m["adv_mean"]) < 1e-5 * loose
     if loose > 1.0:
         # plain TF32 is not fp32 parity (clip decisions can flip): only require a sane gradient
         got_g = net.params_logical(eng.grad)
@@ -556,13 +561,16 @@ def test_logging_levels(dev):
     nets = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
     env = SyntheticEnv(12, 3, max_len=16, term_thresh16=2000)
     ts = ppo.new_training_state(env, nets, 64, 3, gradient_clipping=0.5)
-    lvl = LoggingLevel.LOSSES | LoggingLevel.TRAIN_ROLLOUT_STATS | LoggingLevel.ACTOR_EXTRA | LoggingLevel.WEIGHTS | LoggingLevel.GRAD_NORM
+    lvl = (LoggingLevel.LOSSES | LoggingLevel.TRAIN_ROLLOUT_STATS | LoggingLevel.ACTOR_EXTRA | LoggingLevel.WEIGHTS
+           | LoggingLevel.GRAD_NORM | LoggingLevel.CRITIC_EXTRA)
     ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2, logging_level=lvl)
     eng = next(iter(compile_network(nets).engines.values()))
     assert abs(m["rollout_batch/reward/mean"] - float(eng.reward.mean())) < 1e-6
     assert abs(m["rollout_batch/done_rate"] - float(eng.done.float().mean())) < 1e-7
     assert {"rollout_batch/action/std", "rollout_batch/truncation_rate", "loglikelihood/mean", "weights/std"} <= set(m)
     assert m["grad_norm"].shape == (4,) and np.all(m["grad_norm"] > 0)
+    assert 0.0 <= m["losses/clipping_fraction/mean"] <= 1.0 and m["losses/critic_R^2/mean"] <= 1.0
+    assert m["losses/advantages/std"] > 0
     ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2, logging_level=lvl,
                          logging_percentiles=(0, 50, 100))
     assert m["rollout_batch/reward/p0"] <= m["rollout_batch/reward/p50"] <= m["rollout_batch/reward/p100"]

@@ -489,16 +489,18 @@ def test_adam_refreshes_split_weight_planes(dev, monkeypatch):
     assert np.array_equal(res[0], res[1])
 
 
-def test_full_size_iteration_properties(dev):
-    """BASELINE configs[1] at full size (4096 envs x 32 steps, 4 epochs x 8 minibatches): the oracle
-    needs minutes here, so check size-independent properties instead — two runs from the same seed
-    are bit-identical (fixed-order reductions everywhere), every minibatch is a permutation slice,
-    masks are consistent, counters / step bookkeeping are exact, everything stays finite."""
-    B, T, E, M = 4096, 32, 4, 8
+@pytest.mark.parametrize("shape", [dict(O=64, A=8, B=4096, T=32, E=4, M=8),      # BASELINE configs[1]
+                                   dict(O=5, A=1, B=1024, T=30, E=4, M=4)])      # configs[0] (CartpoleBalance shapes)
+def test_full_size_iteration_properties(dev, shape):
+    """BASELINE configs at full size: the oracle needs minutes here, so check size-independent
+    properties instead — two runs from the same seed are bit-identical (fixed-order reductions
+    everywhere), every minibatch is a permutation slice, masks are consistent, counters / step
+    bookkeeping are exact, everything stays finite."""
+    B, T, E, M = shape["B"], shape["T"], shape["E"], shape["M"]
     runs = []
     for _ in range(2):
-        nets, _o = _pair(64, 8, [64] * 4, [256] * 2, 0)
-        env = SyntheticEnv(64, 8, max_len=64, term_thresh16=512)
+        nets, _o = _pair(shape["O"], shape["A"], [64] * 4, [256] * 2, 0)
+        env = SyntheticEnv(shape["O"], shape["A"], max_len=64, term_thresh16=512)
         ts = ppo.new_training_state(env, nets, B, 17)
         net = compile_network(nets)
         for _it in range(3):
@@ -517,7 +519,7 @@ def test_full_size_iteration_properties(dev):
     assert 0.005 < a["done"].mean() < 0.2
     assert a["steps"] == 3 * T * B == a["ncount"]
     assert a["cnt"][3] == 3 * E * M                                                     # Adam count
-    assert a["cnt"][2] - u32(compile_network(_pair(64, 8, [64] * 4, [256] * 2, 0)[0]).counters)[2] == \
+    assert a["cnt"][2] - u32(compile_network(_pair(shape["O"], shape["A"], [64] * 4, [256] * 2, 0)[0]).counters)[2] == \
         3 * (2 * T + E * M * 2 * (T + 1))                                               # sampler draws per iteration
     assert np.all(np.isfinite(a["p"])) and all(np.isfinite(v) for v in a["m"].values())
     assert eng.graph is not None

@@ -271,11 +271,22 @@ int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan, const flo
                           const int32_t* inds, const uint8_t* done, int32_t rows, float* c, float* h,
                           float* y, float* cache);
 /* d_y: dev [rows][out_dim]; dc, dh: dev [rows][hidden], on entry the gradient w.r.t. the carry this
- * step handed on (zeros for the last step), on exit w.r.t. the carry it received; grad: dev
- * [n_params], accumulated with atomics (zero it before the first step). */
+ * step handed on (zeros for the last step), on exit w.r.t. the carry it received.  Weight gradients,
+ * two ways: (a) all four *_out NULL: accumulated into grad (dev [n_params], zero it first) with
+ * atomics; (b) deterministic: the step writes its GEMM operands - cat_out [rows][pre_dim + hidden]
+ * = [u | h_in], hn_out [rows][hidden] = h', da_out [rows][4 hidden], dz_out [rows][pre_dim] - and
+ * b200ppo_lstm_weight_grads() reduces the operands of ALL steps (buffers laid out step-major) with
+ * three batched GEMMs and fixed-order partial sums (grad may be NULL then). */
 int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan, const float* params,
                           const float* d_y, const float* cache, const int32_t* inds,
-                          const uint8_t* done, int32_t rows, float* dc, float* dh, float* grad);
+                          const uint8_t* done, int32_t rows, float* dc, float* dh, float* grad,
+                          float* cat_out, float* hn_out, float* da_out, float* dz_out);
+int64_t b200ppo_lstm_wgrad_scratch_floats(const b200ppo_lstm_plan* plan, int32_t rows_total);
+/* cache / cat / hn / da / dz / d_y: the step-major [steps * rows][width] operand matrices; writes (not
+ * accumulates) the recurrent actor's weight and bias gradients into grad (dev [n_params]). */
+int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const float* cache,
+                              const float* cat, const float* hn, const float* da, const float* dz,
+                              const float* d_y, int32_t rows_total, float* grad, float* scratch);
 
 /* NormalTanhSampler (sampling_layers.py:88-147) on actor outputs y [B][2A] = [mu | rho] computed
  * elsewhere (the recurrent step): mode bit 0 = replay stored raw actions, bit 1 = deterministic;

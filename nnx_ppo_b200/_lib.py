@@ -100,7 +100,10 @@ SYMBOLS = {
     "b200ppo_comm_ipc_close": (C.c_int, [_vp]),
     "b200ppo_lstm_cache_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
     "b200ppo_lstm_step_fwd": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
-    "b200ppo_lstm_step_bwd": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "b200ppo_lstm_step_bwd": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp]),
+    "b200ppo_lstm_wgrad_scratch_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
+    "b200ppo_lstm_weight_grads": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200ppo_sampler_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),

@@ -35,6 +35,13 @@ def _engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     eng.r_c, eng.r_h = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
     eng.r_dc, eng.r_dh = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
     eng.r_y = torch.zeros(n_envs, Y, **f32)
+    # GEMM operands of the deterministic weight-gradient pass, step-major [T][mb][width]
+    P = lp.pre_dim
+    eng.r_cat = torch.zeros(T, mb, P + H, **f32)
+    eng.r_hn = torch.zeros(T, mb, H, **f32)
+    eng.r_da = torch.zeros(T, mb, 4 * H, **f32)
+    eng.r_dz = torch.zeros(T, mb, P, **f32)
+    eng.r_scratch = torch.zeros(int(lib.b200ppo_lstm_wgrad_scratch_floats(lp, T * mb)), **f32)
     wsp = eng.ws.data_ptr()
     eng.r_y_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 2), C.c_void_p).value)
     eng.r_dy_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 3), C.c_void_p).value)
@@ -122,8 +129,14 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         for t in reversed(range(T)):                                                  # BPTT
             _lib.check(lib.b200ppo_lstm_step_bwd(s, lp, arena, eng.r_dy_ptr + 4 * t * mb * Y,
                                                  eng.r_cache[t].data_ptr(), ip, eng.done[t].data_ptr(), mb,
-                                                 eng.r_dc.data_ptr(), eng.r_dh.data_ptr(), eng.r_grad_ptr),
-                       "lstm_step_bwd")
+                                                 eng.r_dc.data_ptr(), eng.r_dh.data_ptr(), 0,
+                                                 eng.r_cat[t].data_ptr(), eng.r_hn[t].data_ptr(),
+                                                 eng.r_da[t].data_ptr(), eng.r_dz[t].data_ptr()), "lstm_step_bwd")
+        # weight gradients of the recurrent actor: three batched GEMMs over all T steps, fixed-order sums
+        _lib.check(lib.b200ppo_lstm_weight_grads(s, lp, eng.r_cache.data_ptr(), eng.r_cat.data_ptr(),
+                                                 eng.r_hn.data_ptr(), eng.r_da.data_ptr(), eng.r_dz.data_ptr(),
+                                                 eng.r_dy_ptr, T * mb, eng.r_grad_ptr, eng.r_scratch.data_ptr()),
+                   "lstm_weight_grads")
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_ADAM), "update/adam")
 
     # ---------------- Normalizer statistics, counters (ppo.py:329-346)

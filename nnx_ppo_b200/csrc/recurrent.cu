@@ -3,7 +3,8 @@
 // tile of rows, forward (rollout / replay) and backward (one step of BPTT).  sm_100a, fp32 FFMA.
 //
 // First correct version of the row: the time loop lives on the host (T launches forward, T launches
-// backward per minibatch), weights stream from L2, weight gradients are accumulated with atomics.
+// backward per minibatch), weights stream from L2; weight gradients are three batched GEMMs over all
+// steps with fixed-order partial sums (b200ppo_lstm_weight_grads; an atomics mode remains).
 // The persistent per-row-tile version (rows are independent, so a CTA can walk all T steps) and the
 // tcgen05 gate GEMM are the follow-ups; the arithmetic and the reset semantics are the contract and
 // are pinned against oracle/recurrent.py (tests/test_gpu_recurrent.py).
@@ -157,6 +158,9 @@ struct BwdArgs {
   const float* d_y; const float* cache; const uint8_t* done; const int32_t* inds;
   float* dc; float* dh; float* grad;
   int rows;
+  // deterministic weight gradients: instead of atomics into `grad`, this step's GEMM operands are
+  // written out ([u | h_in], h', da, dz1) and b200ppo_lstm_weight_grads reduces them over all steps
+  float* cat_out; float* hn_out; float* da_out; float* dz_out;
 };
 
 // grad[k][n] += sum_r A[r][k] * D[r][n]   (A, D shared-memory tiles); thread per column n
@@ -235,7 +239,19 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // ---- post Dense: dW2 += h'^T dY, db2 += sum dY
-  tile_outer_acc<RT>(hn, H, H, dy, Y, Y, a.grad + a.plan.w2_off, a.grad + a.plan.b2_off);
+  const bool defer = a.da_out != nullptr;
+  if (defer) {
+    for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+      const int r = idx / H, k = idx - r * H;
+      if (row0 + r < a.rows) a.hn_out[static_cast<size_t>(row0 + r) * H + k] = hn[idx];
+    }
+    for (int idx = threadIdx.x; idx < RT * (P + H); idx += NTH) {
+      const int r = idx / (P + H), k = idx - r * (P + H);
+      if (row0 + r < a.rows) a.cat_out[static_cast<size_t>(row0 + r) * (P + H) + k] = cat[idx];
+    }
+  } else {
+    tile_outer_acc<RT>(hn, H, H, dy, Y, Y, a.grad + a.plan.w2_off, a.grad + a.plan.b2_off);
+  }
   __syncthreads();
   // ---- dh_total = dY W2^T + keep * dh_next ; then gate gradients
   tile_gemm_t<RT>(dy, Y, Y, Pm + a.plan.w2_off, Y, H, [&](int k, float (&acc)[RT]) {
@@ -263,7 +279,14 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   }
   __syncthreads();
   // ---- dWcat += [u, h_in]^T da, dbl += sum da
-  tile_outer_acc<RT>(cat, P + H, P + H, da, 4 * H, 4 * H, a.grad + a.plan.wcat_off, a.grad + a.plan.bl_off);
+  if (defer) {
+    for (int idx = threadIdx.x; idx < RT * 4 * H; idx += NTH) {
+      const int r = idx / (4 * H), n = idx - r * 4 * H;
+      if (row0 + r < a.rows) a.da_out[static_cast<size_t>(row0 + r) * 4 * H + n] = da[idx];
+    }
+  } else {
+    tile_outer_acc<RT>(cat, P + H, P + H, da, 4 * H, 4 * H, a.grad + a.plan.wcat_off, a.grad + a.plan.bl_off);
+  }
   // ---- d[u, h_in] = da Wcat^T : u part -> dz1 (x act'), h part -> dh of the previous step
   tile_gemm_t<RT>(da, 4 * H, 4 * H, Pm + a.plan.wcat_off, 4 * H, P + H, [&](int k, float (&acc)[RT]) {
 #pragma unroll
@@ -279,7 +302,115 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   });
   __syncthreads();
   // ---- pre Dense: dW1 += x^T dz1, db1 += sum dz1
-  tile_outer_acc<RT>(xs, O, O, dz, P, P, a.grad + a.plan.w1_off, a.grad + a.plan.b1_off);
+  if (defer) {
+    for (int idx = threadIdx.x; idx < RT * P; idx += NTH) {
+      const int r = idx / P, k = idx - r * P;
+      if (row0 + r < a.rows) a.dz_out[static_cast<size_t>(row0 + r) * P + k] = dz[idx];
+    }
+  } else {
+    tile_outer_acc<RT>(xs, O, O, dz, P, P, a.grad + a.plan.w1_off, a.grad + a.plan.b1_off);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight gradients of the recurrent actor as three batched GEMMs over ALL time steps:
+//   out[K x N] = sum_rows A[row][k] * B[row][n],  bias[n] = sum_rows B[row][n]
+// 64 x 64 output tiles x row splits; partials are reduced in fixed order => deterministic.
+// ------------------------------------------------------------------------------------------
+constexpr int GT = 64, GR = 32;          // output tile, rows per shared-memory slab
+
+__global__ void __launch_bounds__(256) atb_partial_kernel(const float* __restrict__ A, int lda, int K,
+                                                          const float* __restrict__ B, int ldb, int N,
+                                                          int rows, int rows_per_split,
+                                                          float* __restrict__ part, float* __restrict__ bpart) {
+  __shared__ float As[GR][GT + 1];
+  __shared__ float Bs[GR][GT + 1];
+  const int k0 = blockIdx.x * GT, n0 = blockIdx.y * GT, sp = blockIdx.z;
+  const int r_begin = sp * rows_per_split;
+  int r_end = r_begin + rows_per_split;
+  if (r_end > rows) r_end = rows;
+  const int tk = threadIdx.x >> 4, tn = threadIdx.x & 15;     // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r0 = r_begin; r0 < r_end; r0 += GR) {
+    for (int idx = threadIdx.x; idx < GR * GT; idx += 256) {
+      const int r = idx / GT, c = idx - r * GT;
+      const int row = r0 + r;
+      As[r][c] = (row < r_end && k0 + c < K) ? A[static_cast<size_t>(row) * lda + k0 + c] : 0.0f;
+      Bs[r][c] = (row < r_end && n0 + c < N) ? B[static_cast<size_t>(row) * ldb + n0 + c] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < GR; ++r) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[r][tk * 4 + i]; bv[i] = Bs[r][tn * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      if (tk == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bs[j] += bv[j];
+      }
+    }
+    __syncthreads();
+  }
+  float* po = part + static_cast<size_t>(sp) * K * N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + i, n = n0 + tn * 4 + j;
+      if (k < K && n < N) po[static_cast<size_t>(k) * N + n] = acc[i][j];
+    }
+  if (blockIdx.x == 0 && tk == 0 && bpart != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tn * 4 + j;
+      if (n < N) bpart[static_cast<size_t>(sp) * N + n] = bs[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) atb_reduce_kernel(const float* __restrict__ part, int64_t n, int S,
+                                                         float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int sp = 0; sp < S; ++sp) s += part[static_cast<size_t>(sp) * n + i];
+  out[i] = s;
+}
+
+int atb_splits(int K, int N, int rows) {
+  const int tiles = cdiv(K, GT) * cdiv(N, GT);
+  int S = cdiv(2 * 148, tiles);
+  const int smax = cdiv(rows, 4 * GR);
+  if (S > smax) S = smax;
+  if (S < 1) S = 1;
+  if (S > 64) S = 64;
+  return S;
+}
+size_t atb_scratch_floats(int K, int N, int rows) {
+  return static_cast<size_t>(atb_splits(K, N, rows)) * (static_cast<size_t>(K) * N + N);
+}
+int atb_run(cudaStream_t s, const float* A, int lda, int K, const float* B, int ldb, int N, int rows, float* scratch,
+            float* gw, float* gb) {
+  const int S = atb_splits(K, N, rows);
+  const int rps = cdiv(cdiv(rows, S), GR) * GR;
+  float* part = scratch;
+  float* bpart = scratch + static_cast<size_t>(S) * K * N;
+  atb_partial_kernel<<<dim3(cdiv(K, GT), cdiv(N, GT), S), 256, 0, s>>>(A, lda, K, B, ldb, N, rows, rps, part, bpart);
+  B200PPO_LAUNCH_CHECK();
+  atb_reduce_kernel<<<cdiv(static_cast<int64_t>(K) * N, 256), 256, 0, s>>>(part, static_cast<int64_t>(K) * N, S, gw);
+  B200PPO_LAUNCH_CHECK();
+  atb_reduce_kernel<<<cdiv(N, 256), 256, 0, s>>>(bpart, N, S, gb);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
 }
 
 int check_lstm_plan(const b200ppo_lstm_plan* p) {
@@ -338,12 +469,15 @@ extern "C" int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan
 
 extern "C" int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan, const float* params,
                                      const float* d_y, const float* cache, const int32_t* inds,
-                                     const uint8_t* done, int32_t rows, float* dc, float* dh, float* grad) {
+                                     const uint8_t* done, int32_t rows, float* dc, float* dh, float* grad,
+                                     float* cat_out, float* hn_out, float* da_out, float* dz_out) {
   int rc = check_lstm_plan(plan);
   if (rc) return rc;
   if (rows < 0) return B200PPO_EINVAL;
   if (rows == 0) return 0;
-  if (!params || !d_y || !cache || !dc || !dh || !grad) return B200PPO_EINVAL;
+  const bool defer = cat_out || hn_out || da_out || dz_out;
+  if (defer && !(cat_out && hn_out && da_out && dz_out)) return B200PPO_EINVAL;
+  if (!params || !d_y || !cache || !dc || !dh || (!grad && !defer)) return B200PPO_EINVAL;
   const LstmDims d = dims_of(*plan);
   const int RT = rows_per_cta(rows);
   const size_t smem = bwd_smem(d, RT);
@@ -357,8 +491,36 @@ extern "C" int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan
   BwdArgs a;
   a.plan = *plan; a.params = params; a.d_y = d_y; a.cache = cache; a.inds = inds; a.done = done;
   a.rows = rows; a.dc = dc; a.dh = dh; a.grad = grad;
+  a.cat_out = cat_out; a.hn_out = hn_out; a.da_out = da_out; a.dz_out = dz_out;
   if (RT == 16) lstm_step_bwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
   else lstm_step_bwd_kernel<4><<<cdiv(rows, 4), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int64_t b200ppo_lstm_wgrad_scratch_floats(const b200ppo_lstm_plan* plan, int32_t rows_total) {
+  if (check_lstm_plan(plan) || rows_total < 0) return -1;
+  const LstmDims d = dims_of(*plan);
+  size_t m = atb_scratch_floats(d.P + d.H, 4 * d.H, rows_total);
+  const size_t m1 = atb_scratch_floats(d.O, d.P, rows_total), m2 = atb_scratch_floats(d.H, d.Y, rows_total);
+  m = m1 > m ? m1 : m;
+  m = m2 > m ? m2 : m;
+  return static_cast<int64_t>(m);
+}
+
+extern "C" int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const float* cache,
+                                         const float* cat, const float* hn, const float* da, const float* dz,
+                                         const float* d_y, int32_t rows_total, float* grad, float* scratch) {
+  int rc = check_lstm_plan(plan);
+  if (rc) return rc;
+  if (rows_total <= 0 || !cache || !cat || !hn || !da || !dz || !d_y || !grad || !scratch) return B200PPO_EINVAL;
+  const LstmDims d = dims_of(*plan);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // every operand is one [steps * rows, width] matrix (step-major); x is the first O columns of the cache rows
+  rc = atb_run(s, cat, d.P + d.H, d.P + d.H, da, 4 * d.H, 4 * d.H, rows_total, scratch, grad + plan->wcat_off,
+               grad + plan->bl_off);
+  if (rc) return rc;
+  rc = atb_run(s, cache, d.C, d.O, dz, d.P, d.P, rows_total, scratch, grad + plan->w1_off, grad + plan->b1_off);
+  if (rc) return rc;
+  return atb_run(s, hn, d.H, d.H, d_y, d.Y, d.Y, rows_total, scratch, grad + plan->w2_off, grad + plan->b2_off);
 }

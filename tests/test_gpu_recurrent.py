@@ -97,13 +97,36 @@ def test_recurrent_replay_and_bptt_match_oracle(cuda_device, cfg):
     for k in reversed(range(T)):
         _lib.check(lib.b200ppo_lstm_step_bwd(s, plan, params.data_ptr(), d_y[k].data_ptr(), cache[k].data_ptr(),
                                              ind_d.data_ptr(), done[k].data_ptr(), mb, dc.data_ptr(), dh.data_ptr(),
-                                             grad.data_ptr()), "bwd")
+                                             grad.data_ptr(), 0, 0, 0, 0), "bwd")
     torch.cuda.synchronize()
     g = grad.cpu().numpy()[:n_rec]
     ref = g_ref[:n_rec]
     scale = np.abs(ref).max()
     assert np.abs(g - ref).max() < 3e-4 * scale, (np.abs(g - ref).max(), scale)
     assert np.all(grad.cpu().numpy()[n_rec:] == 0)               # the critic's slots are not touched here
+
+    # deterministic variant: the steps write their GEMM operands, three batched GEMMs reduce them
+    P = cfg["P"]
+    cat, hn = torch.zeros(T, mb, P + H, device=dev), torch.zeros(T, mb, H, device=dev)
+    da, dz = torch.zeros(T, mb, 4 * H, device=dev), torch.zeros(T, mb, P, device=dev)
+    scratch = torch.zeros(int(lib.b200ppo_lstm_wgrad_scratch_floats(plan, T * mb)), device=dev)
+    outs = []
+    for _rep in range(2):
+        grad2 = torch.full((plan.n_params,), 7.0, device=dev)        # must be overwritten, not accumulated
+        dc.zero_(); dh.zero_()
+        for k in reversed(range(T)):
+            _lib.check(lib.b200ppo_lstm_step_bwd(s, plan, params.data_ptr(), d_y[k].data_ptr(), cache[k].data_ptr(),
+                                                 ind_d.data_ptr(), done[k].data_ptr(), mb, dc.data_ptr(), dh.data_ptr(),
+                                                 0, cat[k].data_ptr(), hn[k].data_ptr(), da[k].data_ptr(),
+                                                 dz[k].data_ptr()), "bwd(deferred)")
+        _lib.check(lib.b200ppo_lstm_weight_grads(s, plan, cache.data_ptr(), cat.data_ptr(), hn.data_ptr(),
+                                                 da.data_ptr(), dz.data_ptr(), d_y.data_ptr(), T * mb,
+                                                 grad2.data_ptr(), scratch.data_ptr()), "weight_grads")
+        torch.cuda.synchronize()
+        outs.append(grad2.cpu().numpy().copy())
+    assert np.abs(outs[0][:n_rec] - ref).max() < 3e-4 * scale
+    assert np.array_equal(outs[0], outs[1])                      # fixed-order sums: bit-reproducible
+    assert np.all(outs[0][n_rec:] == 7.0)
 
 
 def test_recurrent_ppo_step_matches_oracle(cuda_device):

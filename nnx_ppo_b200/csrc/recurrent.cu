@@ -19,7 +19,9 @@ using namespace b200ppo;
 
 constexpr int NTH = 256;
 // rows per CTA: 16 when there are enough rows to fill the GPU (each weight load feeds 16 FMAs),
-// 4 for minibatch-sized calls (512 rows -> 128 CTAs instead of 32)
+// 4 for minibatch-sized calls (512 rows -> 128 CTAs instead of 32); the 4-row kernels run 1024
+// threads (one output column each: 4x the weight loads in flight on a kernel that is bound by the
+// latency of streaming the gate matrix from L2)
 
 struct LstmDims {
   int O, P, H, Y, C;       // obs, lstm input, hidden, output (2A), cache floats per row
@@ -44,7 +46,7 @@ struct FwdArgs {
 template <int RT, class Epi>
 __device__ __forceinline__ void tile_gemm(const float* __restrict__ in, int ldin, int K,
                                           const float* __restrict__ W, int ldw, int N, Epi epi) {
-  for (int n = threadIdx.x; n < N; n += NTH) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float acc[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r] = 0.0f;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ in, int ldin
 }
 
 template <int RT>
-__global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(RT == 4 ? 1024 : NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
   const int O = d.O, P = d.P, H = d.H, Y = d.Y;
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   const int row0 = blockIdx.x * RT;
   const float* Pm = a.params;
   // ---- load + normalise the observations, load the carry
-  for (int idx = threadIdx.x; idx < RT * O; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * O; idx += blockDim.x) {
     const int r = idx / O, k = idx - r * O;
     const int row = row0 + r;
     float x = 0.0f;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
     }
     xs[idx] = x;
   }
-  for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * H; idx += blockDim.x) {
     const int r = idx / H, k = idx - r * H;
     const int row = row0 + r;
     cat[r * (P + H) + P + k] = row < a.rows ? a.h[static_cast<size_t>(row) * H + k] : 0.0f;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
   });
   __syncthreads();
   // ---- cell update, cache, carry out (with reset)
-  for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * H; idx += blockDim.x) {
     const int r = idx / H, k = idx - r * H;
     const int row = row0 + r;
     if (row >= a.rows) { hn[idx] = 0.0f; continue; }
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_fwd_kernel(const FwdArgs a) {
     a.h[static_cast<size_t>(row) * H + k] = dn ? 0.0f : h2;
   }
   if (crow)
-    for (int idx = threadIdx.x; idx < RT * O; idx += NTH) {
+    for (int idx = threadIdx.x; idx < RT * O; idx += blockDim.x) {
       const int r = idx / O, k = idx - r * O;
       if (row0 + r < a.rows) crow[static_cast<size_t>(row0 + r) * d.C + k] = xs[idx];
     }
@@ -168,7 +170,7 @@ template <int RT>
 __device__ __forceinline__ void tile_outer_acc(const float* __restrict__ A, int lda, int K,
                                                const float* __restrict__ D, int ldd, int N,
                                                float* __restrict__ G, float* __restrict__ gbias) {
-  for (int n = threadIdx.x; n < N; n += NTH) {
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
     float dv[RT];
     float bs = 0.0f;
 #pragma unroll
@@ -188,7 +190,7 @@ template <int RT, class Epi>
 __device__ __forceinline__ void tile_gemm_t(const float* __restrict__ D, int ldd, int N,
                                             const float* __restrict__ W, int ldw, int K, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = warp; k < K; k += NTH / 32) {
+  for (int k = warp; k < K; k += blockDim.x / 32) {
     float acc[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r] = 0.0f;
@@ -204,7 +206,7 @@ __device__ __forceinline__ void tile_gemm_t(const float* __restrict__ D, int ldd
 }
 
 template <int RT>
-__global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(RT == 4 ? 1024 : NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
   const int O = d.O, P = d.P, H = d.H, Y = d.Y;
@@ -217,23 +219,23 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   const int row0 = blockIdx.x * RT;
   const float* Pm = a.params;
   // ---- load caches
-  for (int idx = threadIdx.x; idx < RT * O; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * O; idx += blockDim.x) {
     const int r = idx / O, k = idx - r * O;
     xs[idx] = row0 + r < a.rows ? a.cache[static_cast<size_t>(row0 + r) * d.C + k] : 0.0f;
   }
-  for (int idx = threadIdx.x; idx < RT * P; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * P; idx += blockDim.x) {
     const int r = idx / P, k = idx - r * P;
     const float z = row0 + r < a.rows ? a.cache[static_cast<size_t>(row0 + r) * d.C + O + k] : 0.0f;
     cat[r * (P + H) + k] = act_fwd(z, a.plan.act);
   }
-  for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * H; idx += blockDim.x) {
     const int r = idx / H, k = idx - r * H;
     const bool ok = row0 + r < a.rows;
     const float* cr = a.cache + static_cast<size_t>(row0 + r) * d.C + O + P;
     cat[r * (P + H) + P + k] = ok ? cr[k] : 0.0f;
     hn[idx] = ok ? cr[5 * H + k] * cr[6 * H + k] : 0.0f;          // h' = o * tanh(c')
   }
-  for (int idx = threadIdx.x; idx < RT * Y; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * Y; idx += blockDim.x) {
     const int r = idx / Y, n = idx - r * Y;
     dy[idx] = row0 + r < a.rows ? a.d_y[static_cast<size_t>(row0 + r) * Y + n] : 0.0f;
   }
@@ -241,11 +243,11 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   // ---- post Dense: dW2 += h'^T dY, db2 += sum dY
   const bool defer = a.da_out != nullptr;
   if (defer) {
-    for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+    for (int idx = threadIdx.x; idx < RT * H; idx += blockDim.x) {
       const int r = idx / H, k = idx - r * H;
       if (row0 + r < a.rows) a.hn_out[static_cast<size_t>(row0 + r) * H + k] = hn[idx];
     }
-    for (int idx = threadIdx.x; idx < RT * (P + H); idx += NTH) {
+    for (int idx = threadIdx.x; idx < RT * (P + H); idx += blockDim.x) {
       const int r = idx / (P + H), k = idx - r * (P + H);
       if (row0 + r < a.rows) a.cat_out[static_cast<size_t>(row0 + r) * (P + H) + k] = cat[idx];
     }
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
     for (int r = 0; r < RT; ++r) hn[r * H + k] = acc[r];
   });
   __syncthreads();
-  for (int idx = threadIdx.x; idx < RT * H; idx += NTH) {
+  for (int idx = threadIdx.x; idx < RT * H; idx += blockDim.x) {
     const int r = idx / H, k = idx - r * H;
     const int row = row0 + r;
     float* g4 = da + r * 4 * H;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   __syncthreads();
   // ---- dWcat += [u, h_in]^T da, dbl += sum da
   if (defer) {
-    for (int idx = threadIdx.x; idx < RT * 4 * H; idx += NTH) {
+    for (int idx = threadIdx.x; idx < RT * 4 * H; idx += blockDim.x) {
       const int r = idx / (4 * H), n = idx - r * 4 * H;
       if (row0 + r < a.rows) a.da_out[static_cast<size_t>(row0 + r) * 4 * H + n] = da[idx];
     }
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(NTH) lstm_step_bwd_kernel(const BwdArgs a) {
   __syncthreads();
   // ---- pre Dense: dW1 += x^T dz1, db1 += sum dz1
   if (defer) {
-    for (int idx = threadIdx.x; idx < RT * P; idx += NTH) {
+    for (int idx = threadIdx.x; idx < RT * P; idx += blockDim.x) {
       const int r = idx / P, k = idx - r * P;
       if (row0 + r < a.rows) a.dz_out[static_cast<size_t>(row0 + r) * P + k] = dz[idx];
     }
@@ -462,7 +464,7 @@ extern "C" int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan
   a.plan = *plan; a.params = params; a.mean = norm_mean; a.std = norm_std; a.obs = obs; a.inds = inds;
   a.done = done; a.c = c; a.h = h; a.y = y; a.cache = cache; a.rows = rows;
   if (RT == 16) lstm_step_fwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  else lstm_step_fwd_kernel<4><<<cdiv(rows, 4), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  else lstm_step_fwd_kernel<4><<<cdiv(rows, 4), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -493,7 +495,7 @@ extern "C" int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan
   a.rows = rows; a.dc = dc; a.dh = dh; a.grad = grad;
   a.cat_out = cat_out; a.hn_out = hn_out; a.da_out = da_out; a.dz_out = dz_out;
   if (RT == 16) lstm_step_bwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  else lstm_step_bwd_kernel<4><<<cdiv(rows, 4), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  else lstm_step_bwd_kernel<4><<<cdiv(rows, 4), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

@@ -60,7 +60,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ in, int ldin
 }
 
 template <int RT>
-__global__ void __launch_bounds__(RT == 4 ? 1024 : NTH) lstm_step_fwd_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(1024) lstm_step_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
   const int O = d.O, P = d.P, H = d.H, Y = d.Y;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void tile_gemm_t(const float* __restrict__ D, int ldd
 }
 
 template <int RT>
-__global__ void __launch_bounds__(RT == 4 ? 1024 : NTH) lstm_step_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(1024) lstm_step_bwd_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   const LstmDims d = dims_of(a.plan);
   const int O = d.O, P = d.P, H = d.H, Y = d.Y;
@@ -463,7 +463,7 @@ extern "C" int b200ppo_lstm_step_fwd(void* stream, const b200ppo_lstm_plan* plan
   FwdArgs a;
   a.plan = *plan; a.params = params; a.mean = norm_mean; a.std = norm_std; a.obs = obs; a.inds = inds;
   a.done = done; a.c = c; a.h = h; a.y = y; a.cache = cache; a.rows = rows;
-  if (RT == 16) lstm_step_fwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (RT == 16) lstm_step_fwd_kernel<16><<<cdiv(rows, 16), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   else lstm_step_fwd_kernel<4><<<cdiv(rows, 4), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
@@ -494,7 +494,7 @@ extern "C" int b200ppo_lstm_step_bwd(void* stream, const b200ppo_lstm_plan* plan
   a.plan = *plan; a.params = params; a.d_y = d_y; a.cache = cache; a.inds = inds; a.done = done;
   a.rows = rows; a.dc = dc; a.dh = dh; a.grad = grad;
   a.cat_out = cat_out; a.hn_out = hn_out; a.da_out = da_out; a.dz_out = dz_out;
-  if (RT == 16) lstm_step_bwd_kernel<16><<<cdiv(rows, 16), NTH, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  if (RT == 16) lstm_step_bwd_kernel<16><<<cdiv(rows, 16), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   else lstm_step_bwd_kernel<4><<<cdiv(rows, 4), 1024, smem, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;

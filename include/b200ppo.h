@@ -193,6 +193,19 @@ int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_
                           float* reward /*dev [T][B]*/, uint8_t* done /*dev [T][B]*/,
                           uint8_t* truncated /*dev [T][B]*/, float* next_obs_last /*dev [B][O]*/);
 
+/* -------- K1 (persistent, evaluation): eval_rollout (rollout.py:97-148) on the synthetic env --- *
+ * L policy + env steps per env from the given (freshly reset) env state, which is only read: no  *
+ * transition record, no reset; done is sticky, episode_reward sums the rewards of the steps      *
+ * taken while the env was not yet done, lifespan counts the steps that did not end in done.      *
+ * mode: 0 = sample (sampler counts rng_state[2] + 2t), 2 = deterministic (networks.eval(),       *
+ * ppo.py:122; no sample draw).  The caller advances the sampler count by L (mode 2) or 2L.        */
+int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                       const float* params /*dev*/, const float* norm_mean, const float* norm_std,
+                       const uint32_t* rng_state /*dev*/, int32_t mode, int32_t L, int32_t B,
+                       const float* env_obs /*dev [B][O]*/, const int32_t* env_counter /*dev [B]*/,
+                       const uint32_t* env_term /*dev [B]*/, float* episode_reward /*dev [B]*/,
+                       float* lifespan /*dev [B]*/);
+
 /* -------- K3 + K4: one minibatch update (ppo.py:296-317 update_step, 397-531 ppo_loss) ------ *
  * Stages (bit mask, launched in this order):                                                    *
  *   FWD   critic+actor forward over the gathered minibatch (+ bootstrap rows)                   *

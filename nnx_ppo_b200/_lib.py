@@ -83,6 +83,8 @@ SYMBOLS = {
     "b200ppo_synth_init_keys": (C.c_int, [_vp, _u32, _u32, _i32, _vp]),
     "b200ppo_rollout_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ppo_eval_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
+                                     _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_update_workspace_bytes": (_i64, [_PP, _i32, _i32]),
     "b200ppo_update": (C.c_int, [_vp, _PP, _HP, _BP, _i32, _i32, _i32, _u32, _i32, _i32]),
     "b200ppo_debug_select": (C.c_int, [C.c_int]),

@@ -90,6 +90,8 @@ class PPOEngine:
         self.raw_action = torch.zeros(T, B, A, **f32)
         self.action = torch.zeros(T, B, A, **f32)
         self.loglik = torch.zeros(T, B, **f32)
+        self.value = None            # [T, B] rollout-time value estimates: only with enable_values()
+        self.env_metrics: dict = {}  # Transition.metrics of the rollout (envs stepped from Python only)
         self.reward = torch.zeros(T, B, **f32)
         self.done = torch.zeros(T, B, dtype=torch.uint8, device=dev)
         self.trunc = torch.zeros(T, B, dtype=torch.uint8, device=dev)
@@ -253,6 +255,8 @@ class PPOEngine:
         with torch.cuda.stream(side):
             n = self._enqueue_permutation()
         n += self._enqueue_rollout(env_state)
+        if self.value is not None:
+            n += self._enqueue_values()          # before the first Adam step touches the parameters
         cur.wait_stream(side)
         n += self._enqueue_updates(2 * self.T, self.rng_per_iter, permute=False, side_stats=True)
         return n
@@ -272,6 +276,31 @@ class PPOEngine:
             self.action.data_ptr(), self.loglik.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
             self.trunc.data_ptr(), self.next_obs_last.data_ptr()), "rollout_synth"); n += 1
         return n
+
+    def enable_values(self) -> None:
+        """Also evaluate the critic on the rollout's observations with the rollout-time parameters
+        (``Transition.network_output.value_estimates``; logged as losses/predicted_value at
+        LoggingLevel.CRITIC_EXTRA, metrics.py:62-68).  The training math never reads them
+        (ppo.py:425-446 replays the critic), so the pass is off unless asked for."""
+        import torch
+        if self.value is not None:
+            return
+        T, B, A = self.T, self.B, self.net.plan.act_dim
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.value = torch.zeros(T, B, **f32)
+        self._val_scratch = (torch.empty(T * B, A, **f32), torch.empty(T * B, A, **f32), torch.empty(T * B, **f32))
+        self.graph = None            # the captured iteration does not contain the pass: capture again
+
+    def _enqueue_values(self) -> int:
+        net = self.net
+        raw, act, ll = self._val_scratch
+        mean_p, std_p = net.norm_ptrs()
+        # replay mode on the stored raw actions: no sampler count is consumed
+        _lib.check(self.lib.b200ppo_policy_step(
+            _lib.current_stream(), net.plan, net.arena.data_ptr(), mean_p, std_p, self.obs.data_ptr(),
+            self.T * self.B, 1, net.counters.data_ptr(), 0, self.raw_action.data_ptr(), raw.data_ptr(),
+            act.data_ptr(), ll.data_ptr(), self.value.data_ptr(), 0, 0), "policy_step(values)")
+        return 1
 
     def _enqueue_permutation(self) -> int:
         _lib.check(self.lib.b200ppo_permutation(_lib.current_stream(), self.iter_keys.data_ptr() + 8, self.B, self.E,

@@ -93,16 +93,26 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
                                         logging_percentiles)
     eng = _engine_for(env, training_state, n_envs, rollout_length, gae_lambda, discounting_factor,
                       clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight)
+    if LoggingLevel.CRITIC_EXTRA in logging_level:
+        eng.enable_values()
     reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
     per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
-    metrics = _loss_metrics(per_update, logging_level, logging_percentiles)
-    if LoggingLevel.GRAD_NORM in logging_level and eng.hp.grad_clip > 0.0:
-        metrics["grad_norm"] = per_update[:, 3].copy()                   # ppo.py:313-315 (one value per update)
-    _extra_metrics(metrics, eng.net, eng, logging_level, logging_percentiles)
+    metrics = _iteration_metrics(per_update, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps                                 # ppo.py:333
     new_state = training_state.replace(rng_key=new_key, steps_taken=total_steps)
     return new_state, metrics
+
+
+def _iteration_metrics(per_update: np.ndarray, eng, logging_level, percentiles) -> dict[str, Any]:
+    """compute_metrics + the grad-norm / weight extras of ppo_step (ppo.py:313-315,329-335) from the
+    per-update metric rows and the engine's rollout buffers; shared by the fused, per-step and
+    recurrent paths."""
+    metrics = _loss_metrics(per_update, logging_level, percentiles)
+    if LoggingLevel.GRAD_NORM in logging_level and eng.hp.grad_clip > 0.0:
+        metrics["grad_norm"] = per_update[:, 3].copy()                   # one value per update
+    _extra_metrics(metrics, eng.net, eng, logging_level, percentiles)
+    return metrics
 
 
 def _log_metric(m: dict, name: str, x, percentiles) -> None:
@@ -124,11 +134,23 @@ def _log_metric(m: dict, name: str, x, percentiles) -> None:
             m[f"{name}/p{int(pl)}"] = np.float32(v)
 
 
+def _log_tree(m: dict, name: str, x, percentiles) -> None:
+    """metrics.py:87-90: nested mappings are logged leaf by leaf under ``name/key``."""
+    if isinstance(x, dict):
+        for k, v in x.items():
+            _log_tree(m, f"{name}/{k}", v, percentiles)
+    else:
+        _log_metric(m, name, x, percentiles)
+
+
 def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
     """The parts of metrics.compute_metrics / log_weight_stats (metrics.py:17-121) that only need the
-    rollout buffers and the parameter arena.  Not produced by this build: losses/predicted_value (the
-    fused rollout does not evaluate the critic), percentiles of losses/advantages, per-update grad_norm
-    without gradient clipping, env metrics, ROLLOUT_OBS."""
+    rollout buffers and the parameter arena.  ROLLOUT_OBS logs nothing in the reference either
+    (metrics.py:55-56).  Not produced by this build: percentiles of losses/advantages (mean / std
+    only) and per-update grad_norm without gradient clipping."""
+    if LoggingLevel.TRAINING_ENV_METRICS in logging_level:                # metrics.py:38-40
+        for k, v in getattr(eng, "env_metrics", {}).items():
+            _log_tree(m, k, v, percentiles)
     if LoggingLevel.TRAIN_ROLLOUT_STATS in logging_level:
         _log_metric(m, "rollout_batch/reward", eng.reward, percentiles)
         _log_metric(m, "rollout_batch/action", eng.action, percentiles)
@@ -136,6 +158,8 @@ def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
         _log_metric(m, "rollout_batch/truncation_rate", eng.trunc, percentiles)
     if LoggingLevel.ACTOR_EXTRA in logging_level:
         _log_metric(m, "loglikelihood", eng.loglik, percentiles)
+    if LoggingLevel.CRITIC_EXTRA in logging_level and getattr(eng, "value", None) is not None:
+        _log_metric(m, "losses/predicted_value", eng.value, percentiles)  # metrics.py:62-68
     if LoggingLevel.WEIGHTS in logging_level:
         w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask != 0]
         _log_metric(m, "weights", w, percentiles)

@@ -15,6 +15,7 @@ import numpy as np
 from .. import _lib, prng
 from ..networks.plan import compile_network
 from .rollout import policy_values, split_keys_device, tree_where
+from .types import LoggingLevel
 
 
 def _engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
@@ -101,6 +102,9 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         h.mul_(keep)
         env_state = tree_where(done, env.reset(keys_all[t].contiguous()), nxt)
     network_states = net.set_carry(training_state.network_states, (c, h))
+    if LoggingLevel.CRITIC_EXTRA in logging_level:
+        # rollout-time value estimates (logging only; the MLP critic does not see the carry)
+        eng.value = policy_values(net, eng.obs.reshape(T * B, -1)).reshape(T, B)
 
     # ---------------- E x M minibatch updates (ppo.py:284-328)
     k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
@@ -154,7 +158,7 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
     net.adam_step = opt.step
     per_update = eng.metrics.cpu().numpy()
     total_steps = np.float32(training_state.steps_taken + np.float32(T * B))
-    metrics = _ppo._loss_metrics(per_update, logging_level, logging_percentiles)
+    metrics = _ppo._iteration_metrics(per_update, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps
     return training_state.replace(network_states=network_states, env_states=env_state, rng_key=new_key,
                                   steps_taken=total_steps), metrics

@@ -100,6 +100,15 @@ def unroll_env(env, env_state, networks, network_state, unroll_length: int, rng_
     return _unroll_generic(env, env_state, networks, network_state, T, rng_key_for_env_reset)
 
 
+def _stack_tree(steps: list, dev):
+    """Stack a list of per-step metric pytrees (nested dicts of [B] tensors / scalars) along time."""
+    import torch
+    first = steps[0]
+    if isinstance(first, dict):
+        return {k: _stack_tree([m[k] for m in steps], dev) for k in first if all(k in m for m in steps)}
+    return torch.stack([torch.as_tensor(m, device=dev) for m in steps])
+
+
 def _extras(net, obs, raw):
     na, nc = len(net.actor_layers), len(net.critic_layers)
     ad = {"action": [None] * na + [raw], "value": [None] * nc}
@@ -134,6 +143,7 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
     # split(reset_key, (T, B)): element t*B + b
     keys_all = split_keys_device(reset_key, T * B, dev).reshape(T, B, 2)
     rec = {k: [] for k in ("obs", "raw", "act", "ll", "val", "rew", "done", "trunc")}
+    env_metrics: list = []
     next_obs = None
     for t in range(T):
         out = call_network(networks, network_state, env_state.obs)
@@ -150,13 +160,17 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
         rec["raw"].append(extras["action"][-1]); rec["act"].append(po.actions)
         rec["ll"].append(po.loglikelihoods); rec["val"].append(po.value_estimates)
         rec["rew"].append(nxt.reward.float()); rec["done"].append(done); rec["trunc"].append(tr.bool())
+        env_metrics.append(nxt.metrics if isinstance(getattr(nxt, "metrics", None), dict) else {})
         next_obs = nxt.obs
         reset_states = env.reset(keys_all[t].contiguous())
         env_state = tree_where(done, reset_states, nxt)
     st = {k: torch.stack(v) for k, v in rec.items()}
+    # Transition.metrics["env"] (rollout.py:31-34), stacked over time; "net" (the sampler's mu / sigma)
+    # is not recorded by this build
+    stacked_env = _stack_tree(env_metrics, dev) if env_metrics else {}
     tr = Transition(obs=st["obs"], network_output=PPONetworkOutput(st["act"], st["ll"], st["val"]),
                     rewards=st["rew"], done=st["done"], truncated=st["trunc"], next_obs=next_obs,
-                    metrics={}, rollout_extras=_extras(net, st["obs"], st["raw"]))
+                    metrics={"env": stacked_env}, rollout_extras=_extras(net, st["obs"], st["raw"]))
     return network_state, env_state, tr
 
 
@@ -186,6 +200,9 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
     eng.obs.copy_(tr.obs); eng.raw_action.copy_(tr.rollout_extras[1]["action"][-1] if net.normalizer is not None
                                                 else tr.rollout_extras["action"][-1])
     eng.loglik.copy_(tr.network_output.loglikelihoods); eng.reward.copy_(tr.rewards)
+    eng.action.copy_(tr.network_output.actions)
+    eng.value = tr.network_output.value_estimates                         # logging only
+    eng.env_metrics = tr.metrics
     eng.done.copy_(tr.done.to(torch.uint8)); eng.trunc.copy_(tr.truncated.to(torch.uint8))
     eng.next_obs_last.copy_(tr.next_obs)
     k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
@@ -201,7 +218,7 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
     net.adam_step = opt.step
     per_update = eng.metrics.cpu().numpy()
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
-    metrics = _ppo._loss_metrics(per_update, logging_level, logging_percentiles)
+    metrics = _ppo._iteration_metrics(per_update, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps
     return training_state.replace(env_states=next_env_state, rng_key=new_key, steps_taken=total_steps), metrics
 
@@ -213,6 +230,9 @@ def eval_rollout(env, networks, n_envs: int, max_episode_length: int, key,
     net = compile_network(networks)
     dev = net.device
     env_state = env.reset(split_keys_device(key, n_envs, dev))
+    if getattr(env, "fused_rollout", False) and not net.recurrent:
+        cuml, lifespan = _eval_fused(env, net, env_state, n_envs, max_episode_length)
+        return _eval_metrics(cuml, lifespan, logging_percentiles)
     net_state = networks.initialize_state(n_envs)
     cuml = torch.zeros(n_envs, device=dev)
     lifespan = torch.zeros(n_envs, device=dev)
@@ -227,6 +247,37 @@ def eval_rollout(env, networks, n_envs: int, max_episode_length: int, key,
         lifespan = lifespan + torch.where(done, 0.0, 1.0)
         prev_done = done
         env_state = nxt
+    return _eval_metrics(cuml, lifespan, logging_percentiles)
+
+
+def _eval_fused(env, net, env_state, n_envs: int, L: int):
+    """The whole evaluation episode in ONE launch of the persistent eval kernel (csrc/rollout.cu):
+    policy step + env step + the sticky-done bookkeeping for all L steps, env tile resident in
+    shared memory.  Consumes the sampler counts the per-step path would (sampling_layers.py:93-96)."""
+    import torch
+    lib = _lib.load()
+    dev = net.device
+    s = _lib.current_stream()
+    if net.normalizer is not None:
+        net.normalizer.prepare(s)
+    net.sync_counters_to_device()
+    mean_p, std_p = net.norm_ptrs()
+    deterministic = bool(net.sampler.deterministic)
+    cuml = torch.empty(n_envs, dtype=torch.float32, device=dev)
+    lifespan = torch.empty(n_envs, dtype=torch.float32, device=dev)
+    _lib.check(lib.b200ppo_eval_synth(
+        s, net.plan, env.c_struct(dev), net.arena.data_ptr(), mean_p, std_p, net.counters.data_ptr(),
+        2 if deterministic else 0, L, n_envs, env_state.obs.data_ptr(), env_state.step_counter.data_ptr(),
+        env_state.term_state.data_ptr(), cuml.data_ptr(), lifespan.data_ptr()), "eval_synth")
+    net.advance_rng(L * (1 if deterministic else 2))
+    net.sync_counters_to_device()
+    return cuml, lifespan
+
+
+def _eval_metrics(cuml, lifespan, logging_percentiles) -> dict[str, Any]:
+    """rollout.py:141-148 / _add_reward_metrics :76-94."""
+    import torch
+    dev = cuml.device
     metrics = {"lifespan_mean": float(lifespan.mean()), "lifespan_std": float(lifespan.std(unbiased=False))}
     if logging_percentiles is not None:
         q = torch.tensor([p / 100.0 for p in logging_percentiles], device=dev)

@@ -342,6 +342,126 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent fused evaluation rollout (rollout.py:97-148): no transition record, no env reset;
+// done is sticky, the reward is accumulated while the env was alive BEFORE the step, lifespan
+// counts the steps that did not end in done.  Once every env of the tile is done nothing
+// observable changes any more, so the CTA leaves the time loop early.
+// ------------------------------------------------------------------------------------------
+struct EvalArgs {
+  b200ppo_plan plan;
+  int O, A, max_len, term_thresh16;
+  const float* Wenv;
+  const float* params;
+  const float* mean;
+  const float* std;
+  const uint32_t* rng_state;
+  int L, B, mode;
+  const float* env_obs; const int32_t* env_counter; const uint32_t* env_term;
+  float* episode_reward; float* lifespan;
+  int stage_actor, stage_env, actor_span, ld;
+};
+
+__global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.O, A = a.A, ld = a.ld;
+  const int env0 = blockIdx.x * TE;
+  float* sp = smem;
+  float* bufA = sp; sp += TE * ld;
+  float* bufB = sp; sp += TE * ld;
+  float* obs_s = sp; sp += TE * O;
+  float* act_s = sp; sp += TE * A;
+  float* mean_s = sp; sp += O;
+  float* std_s = sp; sp += O;
+  float* rew_s = sp; sp += TE;
+  sp = smem + ((sp - smem + 3) & ~3);
+  const float* P = a.params;
+  if (a.stage_actor) {
+    float* ps = sp; sp += (a.actor_span + 3) & ~3;
+    for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
+    P = ps;
+  }
+  const float* Wenv = a.Wenv;
+  if (a.stage_env) {
+    float* ws = sp; sp += (O + A) * O;
+    for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
+    Wenv = ws;
+  }
+  for (int i = threadIdx.x; i < O; i += NT) {
+    mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
+    std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
+  }
+  for (int i = threadIdx.x; i < TE * O; i += NT) {
+    const int e = i / O;
+    obs_s[i] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0) * O + i] : 0.0f;
+  }
+  // per-env scalars live in the registers of thread e < TE
+  const bool mine = threadIdx.x < TE && env0 + threadIdx.x < a.B;
+  int32_t cnt = mine ? a.env_counter[env0 + threadIdx.x] : 0;
+  uint32_t term = mine ? a.env_term[env0 + threadIdx.x] : 0u;
+  bool prev_done = !mine;            // env.reset leaves done = 0; padding rows never hold the CTA back
+  float cuml = 0.0f, life = 0.0f;
+  const Key stream_key{a.rng_state[0], a.rng_state[1]};
+  const uint32_t count0 = a.rng_state[2];
+  const bool deterministic = (a.mode & 2) != 0;
+  __syncthreads();
+
+  for (int t = 0; t < a.L; ++t) {
+    for (int i = threadIdx.x; i < TE * O; i += NT) {
+      const int e = i / O, o = i - e * O;
+      const float x = obs_s[i];
+      bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
+    }
+    __syncthreads();
+    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld);
+    // sampling_layers.py:93-96: one count per call when deterministic (the entropy draw), two otherwise
+    const Key k_sample = deterministic ? stream_key : fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
+    for (int i = threadIdx.x; i < TE * A; i += NT) {
+      const int e = i / A, d = i - e * A;
+      const uint32_t j = static_cast<uint32_t>(env0 + e) * static_cast<uint32_t>(A) + d;
+      act_s[i] = sampler_elem(y[e * ld + d], y[e * ld + A + d], a.plan.min_std, a.plan.std_scale,
+                              a.plan.entropy_weight, a.mode & 2, 0.0f, k_sample, k_sample, j, false).action;
+    }
+    __syncthreads();
+    float* xin = (y == bufA) ? bufB : bufA;
+    float* xout = (y == bufA) ? bufA : bufB;
+    for (int i = threadIdx.x; i < TE * (O + A); i += NT) {
+      const int e = i / (O + A), c = i - e * (O + A);
+      xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
+    }
+    __syncthreads();
+    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH);
+    __syncthreads();
+    for (int e = threadIdx.x >> 5; e < TE; e += NT / 32) {
+      float s = 0.0f;
+      for (int o = threadIdx.x & 31; o < O; o += 32) { const float v = xout[e * ld + o]; s = fmaf(v, v, s); }
+      s = warp_sum(s);
+      if ((threadIdx.x & 31) == 0) rew_s[e] = -(s / static_cast<float>(O));
+    }
+    for (int i = threadIdx.x; i < TE * O; i += NT) {
+      const int e = i / O, o = i - e * O;
+      obs_s[i] = xout[e * ld + o];
+    }
+    __syncthreads();
+    bool all_done = true;
+    if (threadIdx.x < TE) {
+      cnt += 1;
+      term = term * 1664525u + 1013904223u;
+      const bool dn = (term >> 16) < static_cast<uint32_t>(a.term_thresh16) || cnt >= a.max_len;
+      const bool done = dn || prev_done;                       // rollout.py:115-117
+      if (!prev_done) cuml = __fadd_rn(cuml, rew_s[threadIdx.x]);   // rollout.py:119-123
+      if (!done) life += 1.0f;                                 // rollout.py:124
+      prev_done = done;
+      all_done = done;
+    }
+    if (__syncthreads_and(all_done)) break;
+  }
+  if (mine) {
+    a.episode_reward[env0 + threadIdx.x] = cuml;
+    a.lifespan[env0 + threadIdx.x] = life;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // generic single policy step on B rows (used for host/torch envs, replay checks and eval)
 // ------------------------------------------------------------------------------------------
 struct PolicyArgs {
@@ -511,6 +631,52 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   cudaError_t e = cudaFuncSetAttribute(rollout_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (e != cudaSuccess) return static_cast<int>(e);
   rollout_synth_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                                  const float* params, const float* norm_mean, const float* norm_std,
+                                  const uint32_t* rng_state, int32_t mode, int32_t L, int32_t B,
+                                  const float* env_obs, const int32_t* env_counter, const uint32_t* env_term,
+                                  float* episode_reward, float* lifespan) {
+  int rc = check_plan(plan);
+  if (rc) return rc;
+  if (!env || !params || !rng_state || !env_obs || !env_counter || !env_term || !episode_reward || !lifespan)
+    return B200PPO_EINVAL;
+  if (plan->normalize && (!norm_mean || !norm_std)) return B200PPO_EINVAL;
+  if (L <= 0 || B <= 0 || (mode & ~2)) return B200PPO_EINVAL;
+  if (env->obs_dim != plan->obs_dim || env->act_dim != plan->act_dim || !env->Wo || !env->Wa) return B200PPO_EINVAL;
+  const int O = plan->obs_dim, A = plan->act_dim;
+  if (env->Wa != env->Wo + static_cast<size_t>(O) * O) return B200PPO_EINVAL;
+  EvalArgs a;
+  a.plan = *plan;
+  a.O = O; a.A = A; a.max_len = env->max_len; a.term_thresh16 = env->term_thresh16;
+  a.Wenv = env->Wo; a.params = params; a.mean = norm_mean; a.std = norm_std;
+  a.rng_state = rng_state; a.L = L; a.B = B; a.mode = mode;
+  a.env_obs = env_obs; a.env_counter = env_counter; a.env_term = env_term;
+  a.episode_reward = episode_reward; a.lifespan = lifespan;
+  int md = max_dim(plan->actor);
+  if (O + A > md) md = O + A;
+  a.ld = md + 1;
+  int64_t span = 0;
+  for (int l = 0; l < plan->actor.n_layers; ++l) {
+    int64_t we = plan->actor.w_off[l] + static_cast<int64_t>(plan->actor.dims[l]) * plan->actor.dims[l + 1];
+    int64_t be = plan->actor.b_off[l] + plan->actor.dims[l + 1];
+    span = we > span ? we : span;
+    span = be > span ? be : span;
+  }
+  int64_t bytes = 4ll * (2ll * TE * a.ld + static_cast<int64_t>(TE) * O + static_cast<int64_t>(TE) * A + 2ll * O + TE + 8);
+  if (bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
+  a.actor_span = static_cast<int>(span);
+  a.stage_actor = 0;
+  a.stage_env = 0;
+  if (bytes + 4 * ((span + 3) & ~3ll) <= SMEM_LIMIT) { a.stage_actor = 1; bytes += 4 * ((span + 3) & ~3ll); }
+  const int64_t envw = 4ll * (O + A) * O;
+  if (bytes + envw <= SMEM_LIMIT) { a.stage_env = 1; bytes += envw; }
+  cudaError_t e = cudaFuncSetAttribute(eval_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  eval_synth_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

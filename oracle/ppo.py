@@ -85,6 +85,27 @@ def unroll_env(env: SyntheticEnv, env_state: EnvState, net: ActorCritic, T: int,
     return s, ro
 
 
+def eval_rollout(env: SyntheticEnv, net: ActorCritic, n_envs: int, max_episode_length: int,
+                 key: np.ndarray, deterministic: bool = True):
+    """rollout.py:97-148 -> (cumulative reward [B], lifespan [B]).  ``done`` is sticky (:115-117),
+    a step's reward counts while the env was not done BEFORE it (:119-123), lifespan counts the
+    steps that did not end in done (:124).  train_ppo calls it under ``networks.eval()``
+    (ppo.py:122), i.e. with the deterministic sampler."""
+    s = env.reset_fast(prng.split(key, n_envs))                          # rollout.py:105-106
+    prev_done = np.zeros(n_envs, bool)
+    cuml = np.zeros(n_envs, F)
+    lifespan = np.zeros(n_envs, F)
+    for _ in range(max_episode_length):
+        out = policy_forward(net, s.obs, deterministic=deterministic)
+        nxt = env.step(s, out["action"])
+        done = nxt.done | prev_done
+        cuml = (cuml + np.where(prev_done, F(0), nxt.reward)).astype(F)
+        lifespan = (lifespan + np.where(done, F(0), F(1))).astype(F)
+        prev_done = done
+        s = nxt
+    return cuml, lifespan
+
+
 # ------------------------------------------------------------------------------------------
 # ppo_loss forward + analytic backward — ppo.py:397-531, SURVEY App. A
 # ------------------------------------------------------------------------------------------

@@ -635,3 +635,130 @@ def test_eval_rollout_bookkeeping(dev):
     # lifespan counts the steps before the first done; reward also counts the terminal step
     assert abs(m["lifespan_mean"] - float((life - 1).mean())) < 1e-6
     assert abs(m["episode_reward/mean"] - float(life.mean())) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------
+# fused evaluation rollout: one launch per episode batch
+# ------------------------------------------------------------------------------------------
+class _PerStepEnv:
+    """Hides ``fused_rollout`` so eval_rollout takes the per-step path on the same env."""
+    fused_rollout = False
+
+    def __init__(self, env):
+        self.reset, self.step = env.reset, env.step
+
+
+@pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=200, L=60, max_len=24, thr=1500),
+                                  dict(O=5, A=1, ah=[32, 32], ch=[32], B=37, L=7, max_len=16, thr=3000),
+                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=64, L=20, max_len=40, thr=0)])
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_fused_eval_rollout_matches_oracle(dev, cfg, deterministic):
+    nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 5)
+    g = np.random.default_rng(2)
+    hist = (0.5 * g.standard_normal((3, 40, cfg["O"]))).astype(np.float32)
+    nets.layers[0].update_statistics(torch.from_numpy(hist).to(dev))
+    onet.update_statistics(hist)
+    env = SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
+    oe = oenv.SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
+    key = hprng.key(9)
+    net = compile_network(nets)
+    sampler = nets.layers[1].action.layers[-1]
+    if deterministic:
+        nets.eval()
+    c0 = sampler.rng.count
+    st = env.reset(rollout.split_keys_device(key, cfg["B"], dev))
+    cuml, life = rollout._eval_fused(env, net, st, cfg["B"], cfg["L"])
+    assert sampler.rng.count == c0 + cfg["L"] * (1 if deterministic else 2)
+    onet.rng_count = c0
+    ocuml, olife = oppo.eval_rollout(oe, onet, cfg["B"], cfg["L"], np.array(key, np.uint32), deterministic)
+    assert onet.rng_count == sampler.rng.count
+    assert np.array_equal(life.cpu().numpy(), olife)                       # integer-valued: exact
+    assert np.allclose(cuml.cpu().numpy(), ocuml, rtol=2e-4, atol=2e-4)
+    assert 0 < olife.min() + 1 and olife.max() <= cfg["L"]
+    # the public entry point: fused and per-step paths report the same metrics and RNG counts
+    sampler.rng.count = c0
+    m_fused = rollout.eval_rollout(env, nets, cfg["B"], cfg["L"], key, (0, 50, 100))
+    c_fused = sampler.rng.count
+    sampler.rng.count = c0
+    m_step = rollout.eval_rollout(_PerStepEnv(env), nets, cfg["B"], cfg["L"], key, (0, 50, 100))
+    assert sampler.rng.count == c_fused
+    nets.train()
+    assert set(m_fused) == set(m_step)
+    for k in m_fused:
+        assert abs(m_fused[k] - m_step[k]) <= 2e-4 * max(1.0, abs(m_step[k])), k
+    assert abs(m_fused["lifespan_mean"] - float(olife.mean())) < 1e-5
+
+
+def test_predicted_value_metric(dev):
+    """losses/predicted_value (metrics.py:62-68) = the critic on the rollout's observations with the
+    ROLLOUT-time parameters.  The pass is switched on when CRITIC_EXTRA is first asked for, which
+    re-captures the iteration graph."""
+    from nnx_ppo_b200.algorithms.types import LoggingLevel
+    nets = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    env = SyntheticEnv(12, 3, max_len=16, term_thresh16=2000)
+    ts = ppo.new_training_state(env, nets, 64, 3)
+    net = compile_network(nets)
+    args = (64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+    for _ in range(2):                                   # eager iteration, then the captured graph
+        ts, m = ppo.ppo_step(env, ts, *args)
+        assert "losses/predicted_value/mean" not in m
+    eng = next(iter(net.engines.values()))
+    assert eng.value is None
+    lvl = LoggingLevel.LOSSES | LoggingLevel.CRITIC_EXTRA
+    for _ in range(2):                                   # re-capture, then replay with the pass inside
+        p0, mean0 = net.arena.clone(), net.normalizer.mean._dev.clone()
+        ts, m = ppo.ppo_step(env, ts, *args, logging_level=lvl)
+        p1, mean1 = net.arena.clone(), net.normalizer.mean._dev.clone()
+        assert not torch.equal(p0, p1)
+        net.arena.copy_(p0); net.normalizer.mean._dev.copy_(mean0)
+        v = rollout.policy_values(net, eng.obs.reshape(-1, 12)).reshape(8, 64)
+        net.arena.copy_(p1); net.normalizer.mean._dev.copy_(mean1)
+        assert torch.equal(v, eng.value)
+        assert abs(m["losses/predicted_value/mean"] - float(v.mean())) < 1e-6
+        assert abs(m["losses/predicted_value/std"] - float(v.std(unbiased=False))) < 1e-6
+
+
+def test_per_step_env_path_matches_fused_path(dev):
+    """ppo_step on an env stepped from Python (one policy-step launch per time step, rollout.py:11-45)
+    against the fused rollout on the same env definition: same masks / counters, same losses and
+    parameters to float32 accuracy; env metrics are logged under env/* (metrics.py:38-40)."""
+    from nnx_ppo_b200.algorithms.types import LoggingLevel
+
+    class MetricEnv(_PerStepEnv):
+        def __init__(self, env):
+            super().__init__(env)
+            inner = env.step
+
+            def step(s, a):
+                n = inner(s, a)
+                n.metrics = {"speed": 2.0 * n.reward, "group": {"alive": 1.0 - n.done}}
+                return n
+            self.step = step
+
+    kw = dict(max_len=16, term_thresh16=2000)
+    env_f, env_p = SyntheticEnv(12, 3, **kw), MetricEnv(SyntheticEnv(12, 3, **kw))
+    nets_f = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    nets_p = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    ts_f = ppo.new_training_state(env_f, nets_f, 64, 3, gradient_clipping=0.5)
+    ts_p = ppo.new_training_state(env_p, nets_p, 64, 3, gradient_clipping=0.5)
+    lvl = LoggingLevel.ALL
+    args = (64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+    for it in range(3):
+        ts_f, m_f = ppo.ppo_step(env_f, ts_f, *args, logging_level=lvl)
+        ts_p, m_p = ppo.ppo_step(env_p, ts_p, *args, logging_level=lvl)
+        assert tuple(ts_f.rng_key) == tuple(ts_p.rng_key) and ts_f.steps_taken == ts_p.steps_taken
+        assert torch.equal(ts_f.env_states.step_counter, ts_p.env_states.step_counter)       # bit exact
+        assert torch.equal(ts_f.env_states.term_state, ts_p.env_states.term_state)
+        assert m_f["rollout_batch/done_rate"] == m_p["rollout_batch/done_rate"]
+        assert m_f["rollout_batch/truncation_rate"] == m_p["rollout_batch/truncation_rate"]
+        assert set(m_f) <= set(m_p)
+        assert set(m_p) - set(m_f) == {"env/speed/mean", "env/speed/std", "env/group/alive/mean",
+                                       "env/group/alive/std"}
+        for k in m_f:
+            a, b = np.asarray(m_f[k], np.float64), np.asarray(m_p[k], np.float64)
+            assert np.allclose(a, b, rtol=2e-3, atol=2e-4), (it, k, a, b)
+        assert abs(m_p["env/speed/mean"] - 2.0 * m_p["rollout_batch/reward/mean"]) < 1e-6
+        assert abs(m_p["env/group/alive/mean"] - (1.0 - m_p["rollout_batch/done_rate"])) < 1e-6
+    pf, pp = compile_network(nets_f).params_logical(), compile_network(nets_p).params_logical()
+    assert np.abs(pf - pp).mean() < 5e-6 and np.abs(pf - pp).max() < 4e-4
+    assert compile_network(nets_f).rng_count == compile_network(nets_p).rng_count

@@ -291,6 +291,19 @@ class PPOEngine:
         self._val_scratch = (torch.empty(T * B, A, **f32), torch.empty(T * B, A, **f32), torch.empty(T * B, **f32))
         self.graph = None            # the captured iteration does not contain the pass: capture again
 
+    def enable_grad_norm(self) -> bool:
+        """LoggingLevel.GRAD_NORM without gradient clipping (ppo.py:313-315): run the global-norm
+        kernel with a clip threshold no finite norm reaches, so metrics[3] is written and the
+        gradient is used unscaled.  Not available on the peer-memory exchange path (its fused
+        reduce + Adam launch has no place for the norm): returns False there."""
+        if self.hp.grad_clip > 0.0:
+            return True
+        if self.p2p:
+            return False
+        self.hp.grad_clip = float(np.finfo(np.float32).max)
+        self.graph = None
+        return True
+
     def _enqueue_values(self) -> int:
         net = self.net
         raw, act, ll = self._val_scratch

@@ -95,6 +95,8 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
                       clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight)
     if LoggingLevel.CRITIC_EXTRA in logging_level:
         eng.enable_values()
+    if LoggingLevel.GRAD_NORM in logging_level:
+        eng.enable_grad_norm()
     reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
     per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
@@ -147,7 +149,7 @@ def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
     """The parts of metrics.compute_metrics / log_weight_stats (metrics.py:17-121) that only need the
     rollout buffers and the parameter arena.  ROLLOUT_OBS logs nothing in the reference either
     (metrics.py:55-56).  Not produced by this build: percentiles of losses/advantages (mean / std
-    only) and per-update grad_norm without gradient clipping."""
+    only) and the sampler's net/* mu / sigma arrays."""
     if LoggingLevel.TRAINING_ENV_METRICS in logging_level:                # metrics.py:38-40
         for k, v in getattr(eng, "env_metrics", {}).items():
             _log_tree(m, k, v, percentiles)

@@ -63,6 +63,8 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
     T, B = rollout_length, n_envs
     eng = _engine(net, opt, B, T, n_epochs, n_minibatches, gae_lambda, discounting_factor, clip_range,
                   normalize_advantages, critic_loss_weight)
+    if LoggingLevel.GRAD_NORM in logging_level:
+        eng.enable_grad_norm()
     lib, lp, plan, mb, dev = eng.lib, net.lplan, net.plan, eng.mb, net.device
     A, Y, H = plan.act_dim, lp.out_dim, lp.hidden
     s = _lib.current_stream()

@@ -194,6 +194,8 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
                            gae_lambda, discounting_factor, clip_range, normalize_advantages,
                            critic_loss_weight, world_size=world, group=group, use_graph=False)
         net.engines[key] = eng
+    if _ppo.LoggingLevel.GRAD_NORM in logging_level:
+        eng.enable_grad_norm()
     reset_key, new_key = prng.split(training_state.rng_key)
     _, next_env_state, tr = _unroll_generic(env, training_state.env_states, training_state.networks,
                                             training_state.network_states, rollout_length, reset_key)

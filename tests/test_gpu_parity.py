@@ -762,3 +762,25 @@ def test_per_step_env_path_matches_fused_path(dev):
     pf, pp = compile_network(nets_f).params_logical(), compile_network(nets_p).params_logical()
     assert np.abs(pf - pp).mean() < 5e-6 and np.abs(pf - pp).max() < 4e-4
     assert compile_network(nets_f).rng_count == compile_network(nets_p).rng_count
+
+
+def test_grad_norm_metric_without_clipping(dev):
+    """LoggingLevel.GRAD_NORM with gradient_clipping=None (ppo.py:313-315): the norm is reported per
+    update and the update itself is bit-identical to a run that does not log it."""
+    from nnx_ppo_b200.algorithms.types import LoggingLevel
+    env = SyntheticEnv(12, 3, max_len=16, term_thresh16=2000)
+    args = (64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+    runs = []
+    for lvl in (LoggingLevel.LOSSES, LoggingLevel.LOSSES | LoggingLevel.GRAD_NORM):
+        nets = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+        ts = ppo.new_training_state(env, nets, 64, 3)
+        for _ in range(3):
+            ts, m = ppo.ppo_step(env, ts, *args, logging_level=lvl)
+        net = compile_network(nets)
+        eng = next(iter(net.engines.values()))
+        runs.append((net.arena.clone(), m, float(eng.grad.double().norm())))
+    assert torch.equal(runs[0][0], runs[1][0])
+    assert "grad_norm" not in runs[0][1]
+    gn = runs[1][1]["grad_norm"]
+    assert gn.shape == (4,) and np.all(gn > 0) and np.all(np.isfinite(gn))
+    assert abs(gn[-1] - runs[1][2]) < 1e-5 * max(1.0, runs[1][2])

@@ -151,6 +151,19 @@ def time_stages(eng, ts_env_state, lib, _lib, torch):
     for row in evs:
         for name, e0, e1 in row:
             tot[name] += e0.elapsed_time(e1)
+    # the rollout launch alone, on a scratch copy of the env state (sampler counts are not advanced, so
+    # the training state is untouched); median of 5
+    scratch = type(ts_env_state)(ts_env_state.obs.clone(), ts_env_state.step_counter.clone(),
+                                 ts_env_state.term_state.clone())
+    times = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng._enqueue_rollout(scratch)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    tot["rollout"] = sorted(times)[2]
     return tot
 
 

@@ -20,71 +20,146 @@ constexpr int NT = 256;         // threads per CTA
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 // out[e][n] = act( sum_k in[e][k] * W[k][n] + bias[n] )  for e < TE, n < N.
-// `in`/`out` are shared-memory tiles; W/bias may live in shared or global memory.
-template <int RP>   // rows (envs) per thread: 2 when there are enough outputs to keep every thread busy, else 1
-__device__ __forceinline__ void dense_tile_rp(const float* __restrict__ in, int ldin, int K,
-                                              const float* __restrict__ W, const float* __restrict__ bias,
-                                              int N, float* __restrict__ out, int ldout, int act) {
-  const int ng = (N + 3) >> 2;
-  const int total = (TE / RP) * ng;
-  const bool vec = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  for (int item = threadIdx.x; item < total; item += NT) {
-    const int eg = item / ng, nq = item - eg * ng;
-    const int e0 = eg * RP, n0 = nq * 4;
-    float acc[RP][4];
+// `in`/`out`/`scratch` are shared-memory tiles; W/bias live in shared memory (staged) or in global memory.
+//
+// Each work item is an RP-row x 4-column register tile.  When a layer has fewer items than the CTA has
+// threads (a 64-wide layer on 16 envs is 128 items), the k range is split over the otherwise idle
+// threads and the partial tiles are summed through `scratch` — the layer's latency is the k loop, so
+// this is what shortens a rollout step.  Activation rows are read 4 k at a time (tile strides are
+// multiples of 4 floats, see tile_ld) so a 4-k step is 2 + 4 vector loads for 32 FMAs.
+template <int RP>
+__device__ __forceinline__ void dense_accumulate(const float* __restrict__ x0, int ldin,
+                                                 const float* __restrict__ W, int N, int n0, int k0, int k1,
+                                                 bool vec, float (&acc)[RP][4]) {
+  int k = k0;
+  if (vec) {
+#pragma unroll 2
+    for (; k + 4 <= k1; k += 4) {
+      float4 xv[RP];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float b = (bias != nullptr && n0 + j < N) ? bias[n0 + j] : 0.0f;
+      for (int r = 0; r < RP; ++r) xv[r] = *reinterpret_cast<const float4*>(x0 + r * ldin + k);
+      const float* wp = W + k * N + n0;
+      const float4 w0 = *reinterpret_cast<const float4*>(wp);
+      const float4 w1 = *reinterpret_cast<const float4*>(wp + N);
+      const float4 w2 = *reinterpret_cast<const float4*>(wp + 2 * N);
+      const float4 w3 = *reinterpret_cast<const float4*>(wp + 3 * N);
 #pragma unroll
-      for (int r = 0; r < RP; ++r) acc[r][j] = b;
-    }
-    const float* x0 = in + e0 * ldin;
-    if (vec) {
-#pragma unroll 4
-      for (int k = 0; k < K; ++k) {
-        const float4 w = *reinterpret_cast<const float4*>(W + static_cast<size_t>(k) * N + n0);
-#pragma unroll
-        for (int r = 0; r < RP; ++r) {
-          const float a0 = x0[r * ldin + k];
-          acc[r][0] = fmaf(a0, w.x, acc[r][0]); acc[r][1] = fmaf(a0, w.y, acc[r][1]);
-          acc[r][2] = fmaf(a0, w.z, acc[r][2]); acc[r][3] = fmaf(a0, w.w, acc[r][3]);
-        }
-      }
-    } else {
-      for (int k = 0; k < K; ++k) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float w = (n0 + j < N) ? W[static_cast<size_t>(k) * N + n0 + j] : 0.0f;
-#pragma unroll
-          for (int r = 0; r < RP; ++r) acc[r][j] = fmaf(x0[r * ldin + k], w, acc[r][j]);
-        }
+      for (int r = 0; r < RP; ++r) {
+        acc[r][0] = fmaf(xv[r].x, w0.x, acc[r][0]); acc[r][1] = fmaf(xv[r].x, w0.y, acc[r][1]);
+        acc[r][2] = fmaf(xv[r].x, w0.z, acc[r][2]); acc[r][3] = fmaf(xv[r].x, w0.w, acc[r][3]);
+        acc[r][0] = fmaf(xv[r].y, w1.x, acc[r][0]); acc[r][1] = fmaf(xv[r].y, w1.y, acc[r][1]);
+        acc[r][2] = fmaf(xv[r].y, w1.z, acc[r][2]); acc[r][3] = fmaf(xv[r].y, w1.w, acc[r][3]);
+        acc[r][0] = fmaf(xv[r].z, w2.x, acc[r][0]); acc[r][1] = fmaf(xv[r].z, w2.y, acc[r][1]);
+        acc[r][2] = fmaf(xv[r].z, w2.z, acc[r][2]); acc[r][3] = fmaf(xv[r].z, w2.w, acc[r][3]);
+        acc[r][0] = fmaf(xv[r].w, w3.x, acc[r][0]); acc[r][1] = fmaf(xv[r].w, w3.y, acc[r][1]);
+        acc[r][2] = fmaf(xv[r].w, w3.z, acc[r][2]); acc[r][3] = fmaf(xv[r].w, w3.w, acc[r][3]);
       }
     }
+    for (; k < k1; ++k) {
+      const float4 w = *reinterpret_cast<const float4*>(W + k * N + n0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (n0 + j < N) {
+      for (int r = 0; r < RP; ++r) {
+        const float a0 = x0[r * ldin + k];
+        acc[r][0] = fmaf(a0, w.x, acc[r][0]); acc[r][1] = fmaf(a0, w.y, acc[r][1]);
+        acc[r][2] = fmaf(a0, w.z, acc[r][2]); acc[r][3] = fmaf(a0, w.w, acc[r][3]);
+      }
+    }
+  } else {
+    for (; k < k1; ++k) {
 #pragma unroll
-        for (int r = 0; r < RP; ++r) out[(e0 + r) * ldout + n0 + j] = act_fwd(acc[r][j], act);
+      for (int j = 0; j < 4; ++j) {
+        const float w = (n0 + j < N) ? W[k * N + n0 + j] : 0.0f;
+#pragma unroll
+        for (int r = 0; r < RP; ++r) acc[r][j] = fmaf(x0[r * ldin + k], w, acc[r][j]);
       }
     }
   }
 }
+
+template <int RP>
+__device__ __forceinline__ void dense_finish(float (&acc)[RP][4], const float* __restrict__ bias, int N, int n0,
+                                             int e0, float* __restrict__ out, int ldout, int act, bool vec) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float b = (bias != nullptr && n0 + j < N) ? bias[n0 + j] : 0.0f;
+#pragma unroll
+    for (int r = 0; r < RP; ++r) acc[r][j] = act_fwd(acc[r][j] + b, act);
+  }
+  if (vec) {
+#pragma unroll
+    for (int r = 0; r < RP; ++r)
+      *reinterpret_cast<float4*>(out + (e0 + r) * ldout + n0) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + j < N) {
+#pragma unroll
+        for (int r = 0; r < RP; ++r) out[(e0 + r) * ldout + n0 + j] = acc[r][j];
+      }
+    }
+  }
+}
+
+constexpr int RP = 2;   // rows per item: 1 row per thread was measured slower (twice the weight loads per FMA)
+
+// Every thread of the CTA must call this (the split path has a barrier inside); the caller
+// synchronises before `out` is read.
 __device__ __forceinline__ void dense_tile(const float* __restrict__ in, int ldin, int K,
                                            const float* __restrict__ W, const float* __restrict__ bias,
-                                           int N, float* __restrict__ out, int ldout, int act) {
-  // 2 rows per thread even when that leaves threads idle: 1 row per thread was measured slower
-  // (two shared-memory loads per 4 FMAs instead of three per 8)
-  dense_tile_rp<2>(in, ldin, K, W, bias, N, out, ldout, act);
+                                           int N, float* __restrict__ out, int ldout, int act,
+                                           float* __restrict__ scratch, int scratch_floats) {
+  const int ng = (N + 3) >> 2;
+  const int items = (TE / RP) * ng;
+  const bool vec = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldin | ldout) & 3) == 0;
+  // k-split factor: a power of two that fills the CTA, leaves >= 4 k per part and fits the scratch tile
+  int S = 1;
+  if (vec && scratch != nullptr)
+    while (S < 8 && 2 * S * items <= NT && K >= 8 * S && (2 * S - 1) * TE * N <= scratch_floats) S *= 2;
+  if (S == 1) {
+    for (int item = threadIdx.x; item < items; item += NT) {
+      const int eg = item / ng, nq = item - eg * ng;
+      float acc[RP][4] = {};
+      dense_accumulate<RP>(in + eg * RP * ldin, ldin, W, N, nq * 4, 0, K, vec, acc);
+      dense_finish<RP>(acc, bias, N, nq * 4, eg * RP, out, ldout, act, vec);
+    }
+    return;
+  }
+  const int part = threadIdx.x / items, item = threadIdx.x - part * items;
+  const int eg = item / ng, nq = item - eg * ng;
+  const int e0 = eg * RP, n0 = nq * 4;
+  const int kc = (((K + S - 1) / S) + 3) & ~3;          // k per part, a multiple of 4 (vector loads of `in`)
+  float acc[RP][4] = {};
+  if (part < S) {
+    const int k0 = part * kc, k1 = min(K, k0 + kc);
+    dense_accumulate<RP>(in + e0 * ldin, ldin, W, N, n0, k0, k1, true, acc);
+    if (part > 0) {
+#pragma unroll
+      for (int r = 0; r < RP; ++r)
+        *reinterpret_cast<float4*>(scratch + ((part - 1) * TE + e0 + r) * N + n0) =
+            make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    }
+  }
+  __syncthreads();
+  if (part == 0) {
+    for (int p = 1; p < S; ++p) {                        // fixed order: the sum is deterministic
+#pragma unroll
+      for (int r = 0; r < RP; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(scratch + ((p - 1) * TE + e0 + r) * N + n0);
+        acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
+      }
+    }
+    dense_finish<RP>(acc, bias, N, n0, e0, out, ldout, act, true);
+  }
 }
 
 // Runs one Dense chain on a smem tile; returns the buffer holding the last layer's output.
 __device__ __forceinline__ float* run_chain(const b200ppo_chain& ch, const float* __restrict__ P,
-                                            float* bufA, float* bufB, int ld) {
+                                            float* bufA, float* bufB, int ld, float* scratch) {
   float* cur = bufA;
   float* nxt = bufB;
   for (int l = 0; l < ch.n_layers; ++l) {
     const int act = (l + 1 < ch.n_layers) ? ch.act : B200PPO_ACT_NONE;
-    dense_tile(cur, ld, ch.dims[l], P + ch.w_off[l], P + ch.b_off[l], ch.dims[l + 1], nxt, ld, act);
+    dense_tile(cur, ld, ch.dims[l], P + ch.w_off[l], P + ch.b_off[l], ch.dims[l + 1], nxt, ld, act, scratch, TE * ld);
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
   }
@@ -187,13 +262,18 @@ struct RolloutArgs {
   int ld;                     // row stride of the activation tiles
 };
 
+// SA / SE: actor parameters / env weights staged in shared memory.  Compile-time so that the weight
+// loads of the k loops are LDS (or LDG) instead of generic loads with 64-bit address arithmetic.
+template <bool SA, bool SE>
 __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int O = a.O, A = a.A, ld = a.ld;
   const int env0 = blockIdx.x * TE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = smem;
   float* bufA = sp; sp += TE * ld;
   float* bufB = sp; sp += TE * ld;
+  float* bufC = sp; sp += TE * ld;      // partial tiles of the k-split layers
   float* obs_s = sp; sp += TE * O;
   float* act_s = sp; sp += TE * A;
   float* raw_s = sp; sp += TE * A;
@@ -206,26 +286,20 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
   uint32_t* kb_s = reinterpret_cast<uint32_t*>(sp); sp += 2 * TE;
   int32_t* done_s = reinterpret_cast<int32_t*>(sp); sp += TE;
   sp = smem + ((sp - smem + 3) & ~3);
-  const float* P = a.params;
-  if (a.stage_actor) {
-    float* ps = sp; sp += (a.actor_span + 3) & ~3;
-    for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
-    P = ps;
-  }
-  const float* Wenv = a.Wenv;
-  if (a.stage_env) {
-    float* ws = sp; sp += (O + A) * O;
-    for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
-    Wenv = ws;
-  }
+  float* ps = sp; if (SA) sp += (a.actor_span + 3) & ~3;
+  float* ws = sp; if (SE) sp += (O + A) * O;
+  if (SA) for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
+  if (SE) for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
+  const float* P = SA ? ps : a.params;
+  const float* Wenv = SE ? ws : a.Wenv;
   for (int i = threadIdx.x; i < O; i += NT) {
     mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
     std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
   }
-  for (int i = threadIdx.x; i < TE * O; i += NT) {
-    const int e = i / O;
-    obs_s[i] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0) * O + i] : 0.0f;
-  }
+  // tile loops: one warp per env row, lanes over the row (no integer division by a runtime width)
+  for (int e = warp; e < TE; e += NT / 32)
+    for (int o = lane; o < O; o += 32)
+      obs_s[e * O + o] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f;
   if (threadIdx.x < TE) {
     const bool ok = env0 + threadIdx.x < a.B;
     cnt_s[threadIdx.x] = ok ? a.env_counter[env0 + threadIdx.x] : 0;
@@ -239,15 +313,15 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
   for (int t = 0; t < a.T; ++t) {
     // (1) record the raw observation, normalise into bufA  (rollout.py:23; normalizer.py:78-80)
     const size_t row0 = static_cast<size_t>(t) * a.B + env0;
-    for (int i = threadIdx.x; i < TE * O; i += NT) {
-      const int e = i / O, o = i - e * O;
-      const float x = obs_s[i];
-      if (env0 + e < a.B) a.obs[row0 * O + i] = x;
-      bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
-    }
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int o = lane; o < O; o += 32) {
+        const float x = obs_s[e * O + o];
+        if (env0 + e < a.B) a.obs[(row0 + e) * O + o] = x;
+        bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
+      }
     __syncthreads();
     // (2) actor MLP
-    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld);
+    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC);
     // (3) sampler: one fresh normal draw per (env, action dim); count = count0 + 2t
     //     (the entropy draw at count0 + 2t + 1 does not influence the rollout and is skipped)
     const Key k_sample = fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
@@ -265,12 +339,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
     // (4) env step input = [obs, action]  ->  obs' = tanh([obs, action] @ [Wo; Wa])
     float* xin = (y == bufA) ? bufB : bufA;
     float* xout = (y == bufA) ? bufA : bufB;   // y is dead after the sampler
-    for (int i = threadIdx.x; i < TE * (O + A); i += NT) {
-      const int e = i / (O + A), c = i - e * (O + A);
-      xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
-    }
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int c = lane; c < O + A; c += 32)
+        xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
     __syncthreads();
-    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH);
+    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH, bufC, TE * ld);
     __syncthreads();
     // (5) reward = -mean(obs'^2): one warp per env
     for (int e = threadIdx.x >> 5; e < TE; e += NT / 32) {
@@ -321,20 +394,19 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
     }
     __syncthreads();
     // (7) next_obs[-1] is the pre-reset observation (rollout.py:30); then tree_where(done, reset, next)
-    for (int i = threadIdx.x; i < TE * O; i += NT) {
-      const int e = i / O, o = i - e * O;
-      const float v = xout[e * ld + o];
-      if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0) * O + i] = v;
-      obs_s[i] = done_s[e] ? bits_to_normal(random_bits_at(Key{kb_s[2 * e], kb_s[2 * e + 1]},
-                                                            static_cast<uint32_t>(o)))
-                           : v;
-    }
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int o = lane; o < O; o += 32) {
+        const float v = xout[e * ld + o];
+        if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0 + e) * O + o] = v;
+        obs_s[e * O + o] = done_s[e] ? bits_to_normal(random_bits_at(Key{kb_s[2 * e], kb_s[2 * e + 1]},
+                                                                      static_cast<uint32_t>(o)))
+                                     : v;
+      }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < TE * O; i += NT) {
-    const int e = i / O;
-    if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0) * O + i] = obs_s[i];
-  }
+  for (int e = warp; e < TE; e += NT / 32)
+    for (int o = lane; o < O; o += 32)
+      if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0 + e) * O + o] = obs_s[e * O + o];
   if (threadIdx.x < TE && env0 + threadIdx.x < a.B) {
     a.env_counter[env0 + threadIdx.x] = cnt_s[threadIdx.x];
     a.env_term[env0 + threadIdx.x] = term_s[threadIdx.x];
@@ -361,39 +433,35 @@ struct EvalArgs {
   int stage_actor, stage_env, actor_span, ld;
 };
 
+template <bool SA, bool SE>
 __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int O = a.O, A = a.A, ld = a.ld;
   const int env0 = blockIdx.x * TE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = smem;
   float* bufA = sp; sp += TE * ld;
   float* bufB = sp; sp += TE * ld;
+  float* bufC = sp; sp += TE * ld;
   float* obs_s = sp; sp += TE * O;
   float* act_s = sp; sp += TE * A;
   float* mean_s = sp; sp += O;
   float* std_s = sp; sp += O;
   float* rew_s = sp; sp += TE;
   sp = smem + ((sp - smem + 3) & ~3);
-  const float* P = a.params;
-  if (a.stage_actor) {
-    float* ps = sp; sp += (a.actor_span + 3) & ~3;
-    for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
-    P = ps;
-  }
-  const float* Wenv = a.Wenv;
-  if (a.stage_env) {
-    float* ws = sp; sp += (O + A) * O;
-    for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
-    Wenv = ws;
-  }
+  float* ps = sp; if (SA) sp += (a.actor_span + 3) & ~3;
+  float* ws = sp; if (SE) sp += (O + A) * O;
+  if (SA) for (int i = threadIdx.x; i < a.actor_span; i += NT) ps[i] = a.params[i];
+  if (SE) for (int i = threadIdx.x; i < (O + A) * O; i += NT) ws[i] = a.Wenv[i];
+  const float* P = SA ? ps : a.params;
+  const float* Wenv = SE ? ws : a.Wenv;
   for (int i = threadIdx.x; i < O; i += NT) {
     mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
     std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
   }
-  for (int i = threadIdx.x; i < TE * O; i += NT) {
-    const int e = i / O;
-    obs_s[i] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0) * O + i] : 0.0f;
-  }
+  for (int e = warp; e < TE; e += NT / 32)
+    for (int o = lane; o < O; o += 32)
+      obs_s[e * O + o] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f;
   // per-env scalars live in the registers of thread e < TE
   const bool mine = threadIdx.x < TE && env0 + threadIdx.x < a.B;
   int32_t cnt = mine ? a.env_counter[env0 + threadIdx.x] : 0;
@@ -406,13 +474,13 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
   __syncthreads();
 
   for (int t = 0; t < a.L; ++t) {
-    for (int i = threadIdx.x; i < TE * O; i += NT) {
-      const int e = i / O, o = i - e * O;
-      const float x = obs_s[i];
-      bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
-    }
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int o = lane; o < O; o += 32) {
+        const float x = obs_s[e * O + o];
+        bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
+      }
     __syncthreads();
-    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld);
+    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC);
     // sampling_layers.py:93-96: one count per call when deterministic (the entropy draw), two otherwise
     const Key k_sample = deterministic ? stream_key : fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
     for (int i = threadIdx.x; i < TE * A; i += NT) {
@@ -424,22 +492,21 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
     __syncthreads();
     float* xin = (y == bufA) ? bufB : bufA;
     float* xout = (y == bufA) ? bufA : bufB;
-    for (int i = threadIdx.x; i < TE * (O + A); i += NT) {
-      const int e = i / (O + A), c = i - e * (O + A);
-      xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
-    }
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int c = lane; c < O + A; c += 32)
+        xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
     __syncthreads();
-    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH);
+    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH, bufC, TE * ld);
     __syncthreads();
-    for (int e = threadIdx.x >> 5; e < TE; e += NT / 32) {
+    for (int e = warp; e < TE; e += NT / 32) {      // reward and the next observation of one env per warp
       float s = 0.0f;
-      for (int o = threadIdx.x & 31; o < O; o += 32) { const float v = xout[e * ld + o]; s = fmaf(v, v, s); }
+      for (int o = lane; o < O; o += 32) {
+        const float v = xout[e * ld + o];
+        s = fmaf(v, v, s);
+        obs_s[e * O + o] = v;
+      }
       s = warp_sum(s);
-      if ((threadIdx.x & 31) == 0) rew_s[e] = -(s / static_cast<float>(O));
-    }
-    for (int i = threadIdx.x; i < TE * O; i += NT) {
-      const int e = i / O, o = i - e * O;
-      obs_s[i] = xout[e * ld + o];
+      if (lane == 0) rew_s[e] = -(s / static_cast<float>(O));
     }
     __syncthreads();
     bool all_done = true;
@@ -467,7 +534,7 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
 struct PolicyArgs {
   b200ppo_plan plan;
   const float* params; const float* mean; const float* std; const float* obs;
-  int B, mode, ld;
+  int B, mode, ld, use_scratch;
   const uint32_t* rng_state; uint32_t count_offset;
   const float* raw_in;
   float* raw; float* action; float* loglik; float* value; float* reg;
@@ -479,7 +546,8 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
   const int row0 = blockIdx.x * TE;
   float* bufA = smem;
   float* bufB = bufA + TE * ld;
-  float* x_s = bufB + TE * ld;          // normalised obs, kept for the critic
+  float* bufC = a.use_scratch ? bufB + TE * ld : nullptr;   // partial tiles of the k-split layers
+  float* x_s = bufB + (a.use_scratch ? 2 : 1) * TE * ld;    // normalised obs, kept for the critic
   float* llt_s = x_s + TE * ld;
   float* reg_s = llt_s + TE * A;
   for (int i = threadIdx.x; i < TE * O; i += NT) {
@@ -490,7 +558,7 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
     bufA[e * ld + o] = x;
   }
   __syncthreads();
-  const float* y = run_chain(a.plan.actor, a.params, bufA, bufB, ld);
+  const float* y = run_chain(a.plan.actor, a.params, bufA, bufB, ld, bufC);
   const Key stream_key{a.rng_state[0], a.rng_state[1]};
   uint32_t c = a.rng_state[2] + a.count_offset;
   const bool deterministic = (a.mode & 2) != 0;
@@ -533,8 +601,16 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
   }
   __syncthreads();
   float* cb = (ca == bufA) ? bufB : bufA;
-  const float* v = run_chain(a.plan.critic, a.params, ca, cb, ld);
+  const float* v = run_chain(a.plan.critic, a.params, ca, cb, ld, bufC);
   if (threadIdx.x < TE && row0 + threadIdx.x < a.B) a.value[row0 + threadIdx.x] = v[threadIdx.x * ld];
+}
+
+// Row stride of the activation tiles: a multiple of 4 floats (float4 loads / stores of rows) that is
+// 4 mod 8, so the row pairs read by the two half-warps of an item group are 8 or 24 banks apart.
+int tile_ld(int md) {
+  int ld = (md + 3) & ~3;
+  if ((ld & 7) == 0) ld += 4;
+  return ld;
 }
 
 int max_dim(const b200ppo_chain& c) {
@@ -610,7 +686,7 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   a.done = done; a.trunc = truncated; a.next_obs_last = next_obs_last;
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
-  a.ld = md + 1;  // odd stride: the two rows a thread reads land in different banks
+  a.ld = tile_ld(md);
   // actor parameters occupy the arena prefix [0, actor_span)
   int64_t span = 0;
   for (int l = 0; l < plan->actor.n_layers; ++l) {
@@ -619,7 +695,7 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
     span = we > span ? we : span;
     span = be > span ? be : span;
   }
-  int64_t base_bytes = 4ll * (2ll * TE * a.ld + static_cast<int64_t>(TE) * O + 3ll * TE * A + 2ll * O + 6ll * TE + 8);
+  int64_t base_bytes = 4ll * (3ll * TE * a.ld + static_cast<int64_t>(TE) * O + 3ll * TE * A + 2ll * O + 6ll * TE + 8);
   if (base_bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   int64_t bytes = base_bytes;
   a.actor_span = static_cast<int>(span);
@@ -628,9 +704,15 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   if (bytes + 4 * ((span + 3) & ~3ll) <= SMEM_LIMIT) { a.stage_actor = 1; bytes += 4 * ((span + 3) & ~3ll); }
   const int64_t envw = 4ll * (O + A) * O;
   if (bytes + envw <= SMEM_LIMIT) { a.stage_env = 1; bytes += envw; }
-  cudaError_t e = cudaFuncSetAttribute(rollout_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  rollout_synth_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  auto launch = [&](auto kernel) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+    return 0;
+  };
+  rc = a.stage_actor ? (a.stage_env ? launch(rollout_synth_kernel<true, true>) : launch(rollout_synth_kernel<true, false>))
+                     : (a.stage_env ? launch(rollout_synth_kernel<false, true>) : launch(rollout_synth_kernel<false, false>));
+  if (rc) return rc;
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -658,7 +740,7 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
   a.episode_reward = episode_reward; a.lifespan = lifespan;
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
-  a.ld = md + 1;
+  a.ld = tile_ld(md);
   int64_t span = 0;
   for (int l = 0; l < plan->actor.n_layers; ++l) {
     int64_t we = plan->actor.w_off[l] + static_cast<int64_t>(plan->actor.dims[l]) * plan->actor.dims[l + 1];
@@ -666,7 +748,7 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
     span = we > span ? we : span;
     span = be > span ? be : span;
   }
-  int64_t bytes = 4ll * (2ll * TE * a.ld + static_cast<int64_t>(TE) * O + static_cast<int64_t>(TE) * A + 2ll * O + TE + 8);
+  int64_t bytes = 4ll * (3ll * TE * a.ld + static_cast<int64_t>(TE) * O + static_cast<int64_t>(TE) * A + 2ll * O + TE + 8);
   if (bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   a.actor_span = static_cast<int>(span);
   a.stage_actor = 0;
@@ -674,9 +756,15 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
   if (bytes + 4 * ((span + 3) & ~3ll) <= SMEM_LIMIT) { a.stage_actor = 1; bytes += 4 * ((span + 3) & ~3ll); }
   const int64_t envw = 4ll * (O + A) * O;
   if (bytes + envw <= SMEM_LIMIT) { a.stage_env = 1; bytes += envw; }
-  cudaError_t e = cudaFuncSetAttribute(eval_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  eval_synth_kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+  auto launch = [&](auto kernel) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    kernel<<<cdiv(B, TE), NT, bytes, static_cast<cudaStream_t>(stream)>>>(a);
+    return 0;
+  };
+  rc = a.stage_actor ? (a.stage_env ? launch(eval_synth_kernel<true, true>) : launch(eval_synth_kernel<true, false>))
+                     : (a.stage_env ? launch(eval_synth_kernel<false, true>) : launch(eval_synth_kernel<false, false>));
+  if (rc) return rc;
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -706,8 +794,13 @@ extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const
   int md = max_dim(plan->actor);
   const int mc = max_dim(plan->critic);
   md = mc > md ? mc : md;
-  a.ld = md + 1;
-  const int64_t bytes = 4ll * (3ll * TE * a.ld + 2ll * TE * plan->act_dim);
+  a.ld = tile_ld(md);
+  int64_t bytes = 4ll * (4ll * TE * a.ld + 2ll * TE * plan->act_dim);
+  a.use_scratch = 1;
+  if (bytes > SMEM_LIMIT) {               // very wide layers: no room for the k-split scratch tile (not needed there)
+    a.use_scratch = 0;
+    bytes -= 4ll * TE * a.ld;
+  }
   if (bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   cudaError_t e = cudaFuncSetAttribute(policy_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
   if (e != cudaSuccess) return static_cast<int>(e);

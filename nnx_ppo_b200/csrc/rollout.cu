@@ -27,10 +27,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 // threads and the partial tiles are summed through `scratch` — the layer's latency is the k loop, so
 // this is what shortens a rollout step.  Activation rows are read 4 k at a time (tile strides are
 // multiples of 4 floats, see tile_ld) so a 4-k step is 2 + 4 vector loads for 32 FMAs.
-template <int RP>
+template <int RP, int NC = 0>   // NC: compile-time layer width (the weight rows become immediate offsets), 0 = runtime
 __device__ __forceinline__ void dense_accumulate(const float* __restrict__ x0, int ldin,
-                                                 const float* __restrict__ W, int N, int n0, int k0, int k1,
+                                                 const float* __restrict__ W, int Nrt, int n0, int k0, int k1,
                                                  bool vec, float (&acc)[RP][4]) {
+  const int N = NC ? NC : Nrt;
   int k = k0;
   if (vec) {
 #pragma unroll 2
@@ -103,19 +104,16 @@ __device__ __forceinline__ void dense_finish(float (&acc)[RP][4], const float* _
 constexpr int RP = 2;   // rows per item: 1 row per thread was measured slower (twice the weight loads per FMA)
 
 // Every thread of the CTA must call this (the split path has a barrier inside); the caller
-// synchronises before `out` is read.
+// synchronises before `out` is read.  `log2S` > 0 (host-computed, ksplit_log2) selects the k-split
+// path: N / 4 is a power of two there, so a thread's (part, row group, column group) are shifts.
 __device__ __forceinline__ void dense_tile(const float* __restrict__ in, int ldin, int K,
                                            const float* __restrict__ W, const float* __restrict__ bias,
                                            int N, float* __restrict__ out, int ldout, int act,
-                                           float* __restrict__ scratch, int scratch_floats) {
-  const int ng = (N + 3) >> 2;
-  const int items = (TE / RP) * ng;
-  const bool vec = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldin | ldout) & 3) == 0;
-  // k-split factor: a power of two that fills the CTA, leaves >= 4 k per part and fits the scratch tile
-  int S = 1;
-  if (vec && scratch != nullptr)
-    while (S < 8 && 2 * S * items <= NT && K >= 8 * S && (2 * S - 1) * TE * N <= scratch_floats) S *= 2;
-  if (S == 1) {
+                                           float* __restrict__ scratch, int log2S) {
+  if (log2S == 0) {
+    const int ng = (N + 3) >> 2;
+    const int items = (TE / RP) * ng;
+    const bool vec = (N & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) & 15) == 0) && ((ldin | ldout) & 3) == 0;
     for (int item = threadIdx.x; item < items; item += NT) {
       const int eg = item / ng, nq = item - eg * ng;
       float acc[RP][4] = {};
@@ -124,14 +122,18 @@ __device__ __forceinline__ void dense_tile(const float* __restrict__ in, int ldi
     }
     return;
   }
-  const int part = threadIdx.x / items, item = threadIdx.x - part * items;
-  const int eg = item / ng, nq = item - eg * ng;
+  static_assert(TE / RP == 8, "row-group decomposition below assumes 8 row groups");
+  const int ng = N >> 2;
+  const int q = static_cast<int>(threadIdx.x) >> (__ffs(ng) - 1);
+  const int nq = threadIdx.x & (ng - 1), eg = q & 7, part = q >> 3;
   const int e0 = eg * RP, n0 = nq * 4;
-  const int kc = (((K + S - 1) / S) + 3) & ~3;          // k per part, a multiple of 4 (vector loads of `in`)
+  const int S = 1 << log2S;
+  const int kc = (((K + S - 1) >> log2S) + 3) & ~3;    // k per part, a multiple of 4 (vector loads of `in`)
   float acc[RP][4] = {};
   if (part < S) {
     const int k0 = part * kc, k1 = min(K, k0 + kc);
-    dense_accumulate<RP>(in + e0 * ldin, ldin, W, N, n0, k0, k1, true, acc);
+    if (N == 64) dense_accumulate<RP, 64>(in + e0 * ldin, ldin, W, N, n0, k0, k1, true, acc);
+    else dense_accumulate<RP>(in + e0 * ldin, ldin, W, N, n0, k0, k1, true, acc);
     if (part > 0) {
 #pragma unroll
       for (int r = 0; r < RP; ++r)
@@ -153,13 +155,16 @@ __device__ __forceinline__ void dense_tile(const float* __restrict__ in, int ldi
 }
 
 // Runs one Dense chain on a smem tile; returns the buffer holding the last layer's output.
+// split[l]: log2 of layer l's k-split factor (0 when there is no scratch tile).
 __device__ __forceinline__ float* run_chain(const b200ppo_chain& ch, const float* __restrict__ P,
-                                            float* bufA, float* bufB, int ld, float* scratch) {
+                                            float* bufA, float* bufB, int ld, float* scratch,
+                                            const int8_t* __restrict__ split) {
   float* cur = bufA;
   float* nxt = bufB;
   for (int l = 0; l < ch.n_layers; ++l) {
     const int act = (l + 1 < ch.n_layers) ? ch.act : B200PPO_ACT_NONE;
-    dense_tile(cur, ld, ch.dims[l], P + ch.w_off[l], P + ch.b_off[l], ch.dims[l + 1], nxt, ld, act, scratch, TE * ld);
+    dense_tile(cur, ld, ch.dims[l], P + ch.w_off[l], P + ch.b_off[l], ch.dims[l + 1], nxt, ld, act, scratch,
+               scratch != nullptr ? split[l] : 0);
     __syncthreads();
     float* t = cur; cur = nxt; nxt = t;
   }
@@ -256,6 +261,7 @@ struct RolloutArgs {
   float* env_obs; int32_t* env_counter; uint32_t* env_term;
   float* obs; float* raw_action; float* action; float* loglik; float* reward;
   uint8_t* done; uint8_t* trunc; float* next_obs_last;
+  int8_t split[B200PPO_MAX_LAYERS + 1];   // log2 k-split per actor layer; [MAX_LAYERS] = the env step
   int stage_actor;            // actor parameters staged in smem
   int stage_env;              // env weights staged in smem
   int actor_span;             // floats of the arena covered by the actor chain (starts at 0)
@@ -274,13 +280,11 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
   float* bufA = sp; sp += TE * ld;
   float* bufB = sp; sp += TE * ld;
   float* bufC = sp; sp += TE * ld;      // partial tiles of the k-split layers
-  float* obs_s = sp; sp += TE * O;
-  float* act_s = sp; sp += TE * A;
+  float* bufX = sp; sp += TE * ld;      // env-step input tile, resident across steps: [obs | action] per env row
   float* raw_s = sp; sp += TE * A;
   float* llt_s = sp; sp += TE * A;
   float* mean_s = sp; sp += O;
   float* std_s = sp; sp += O;
-  float* rew_s = sp; sp += TE;
   int32_t* cnt_s = reinterpret_cast<int32_t*>(sp); sp += TE;
   uint32_t* term_s = reinterpret_cast<uint32_t*>(sp); sp += TE;
   uint32_t* kb_s = reinterpret_cast<uint32_t*>(sp); sp += 2 * TE;
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
   // tile loops: one warp per env row, lanes over the row (no integer division by a runtime width)
   for (int e = warp; e < TE; e += NT / 32)
     for (int o = lane; o < O; o += 32)
-      obs_s[e * O + o] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f;
+      bufX[e * ld + o] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f;
   if (threadIdx.x < TE) {
     const bool ok = env0 + threadIdx.x < a.B;
     cnt_s[threadIdx.x] = ok ? a.env_counter[env0 + threadIdx.x] : 0;
@@ -315,15 +319,16 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
     const size_t row0 = static_cast<size_t>(t) * a.B + env0;
     for (int e = warp; e < TE; e += NT / 32)
       for (int o = lane; o < O; o += 32) {
-        const float x = obs_s[e * O + o];
+        const float x = bufX[e * ld + o];
         if (env0 + e < a.B) a.obs[(row0 + e) * O + o] = x;
         bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
       }
     __syncthreads();
     // (2) actor MLP
-    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC);
+    float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC, a.split);
     // (3) sampler: one fresh normal draw per (env, action dim); count = count0 + 2t
-    //     (the entropy draw at count0 + 2t + 1 does not influence the rollout and is skipped)
+    //     (the entropy draw at count0 + 2t + 1 does not influence the rollout and is skipped).
+    //     The action goes straight into the env-step input tile.
     const Key k_sample = fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
     for (int i = threadIdx.x; i < TE * A; i += NT) {
       const int e = i / A, d = i - e * A;
@@ -332,28 +337,16 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
                                         a.plan.std_scale, a.plan.entropy_weight, 0, 0.0f, k_sample,
                                         k_sample, j, false);
       raw_s[i] = s.raw;
-      act_s[i] = s.action;
+      bufX[e * ld + O + d] = s.action;
       llt_s[i] = s.llterm;
+      if (env0 + e < a.B) {
+        a.raw_action[row0 * A + i] = s.raw;
+        a.action[row0 * A + i] = s.action;
+      }
     }
     __syncthreads();
-    // (4) env step input = [obs, action]  ->  obs' = tanh([obs, action] @ [Wo; Wa])
-    float* xin = (y == bufA) ? bufB : bufA;
-    float* xout = (y == bufA) ? bufA : bufB;   // y is dead after the sampler
-    for (int e = warp; e < TE; e += NT / 32)
-      for (int c = lane; c < O + A; c += 32)
-        xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
-    __syncthreads();
-    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH, bufC, TE * ld);
-    __syncthreads();
-    // (5) reward = -mean(obs'^2): one warp per env
-    for (int e = threadIdx.x >> 5; e < TE; e += NT / 32) {
-      float s = 0.0f;
-      for (int o = threadIdx.x & 31; o < O; o += 32) { const float v = xout[e * ld + o]; s = fmaf(v, v, s); }
-      s = warp_sum(s);
-      if ((threadIdx.x & 31) == 0) rew_s[e] = -(s / static_cast<float>(O));
-    }
-    __syncthreads();
-    // (6) episode bookkeeping (integer-exact), transition record, reset scalars
+    // (4) episode bookkeeping (integer-exact) and reset scalars: independent of the env arithmetic, so the
+    //     16 threads that own an env do it while the others already start the env-step GEMM
     if (threadIdx.x < TE) {
       const int e = threadIdx.x;
       const int ge = env0 + e;
@@ -366,7 +359,6 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
       const bool dn = terminated || truncated;
       if (ge < a.B) {
         a.loglik[row0 + e] = ll;
-        a.reward[row0 + e] = rew_s[e];
         a.done[row0 + e] = dn ? 1 : 0;
         a.trunc[row0 + e] = truncated ? 1 : 0;
       }
@@ -385,28 +377,29 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
         term_s[e] = ts;
       }
     }
-    for (int i = threadIdx.x; i < TE * A; i += NT) {
-      const int e = i / A;
-      if (env0 + e < a.B) {
-        a.raw_action[row0 * A + i] = raw_s[i];
-        a.action[row0 * A + i] = act_s[i];
-      }
-    }
+    // (5) env step: obs' = tanh([obs, action] @ [Wo; Wa]) into the (dead) actor-output tile
+    dense_tile(bufX, ld, O + A, Wenv, nullptr, O, y, ld, B200PPO_ACT_TANH, bufC, a.split[B200PPO_MAX_LAYERS]);
     __syncthreads();
-    // (7) next_obs[-1] is the pre-reset observation (rollout.py:30); then tree_where(done, reset, next)
-    for (int e = warp; e < TE; e += NT / 32)
+    // (6) one warp per env: reward = -mean(obs'^2); next_obs[-1] is the pre-reset observation
+    //     (rollout.py:30); then tree_where(done, reset, next) back into the input tile
+    for (int e = warp; e < TE; e += NT / 32) {
+      const bool dn = done_s[e] != 0;
+      const Key kb{kb_s[2 * e], kb_s[2 * e + 1]};
+      float sq = 0.0f;
       for (int o = lane; o < O; o += 32) {
-        const float v = xout[e * ld + o];
+        const float v = y[e * ld + o];
+        sq = fmaf(v, v, sq);
         if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0 + e) * O + o] = v;
-        obs_s[e * O + o] = done_s[e] ? bits_to_normal(random_bits_at(Key{kb_s[2 * e], kb_s[2 * e + 1]},
-                                                                      static_cast<uint32_t>(o)))
-                                     : v;
+        bufX[e * ld + o] = dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v;
       }
+      sq = warp_sum(sq);
+      if (lane == 0 && env0 + e < a.B) a.reward[row0 + e] = -(sq / static_cast<float>(O));
+    }
     __syncthreads();
   }
   for (int e = warp; e < TE; e += NT / 32)
     for (int o = lane; o < O; o += 32)
-      if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0 + e) * O + o] = obs_s[e * O + o];
+      if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0 + e) * O + o] = bufX[e * ld + o];
   if (threadIdx.x < TE && env0 + threadIdx.x < a.B) {
     a.env_counter[env0 + threadIdx.x] = cnt_s[threadIdx.x];
     a.env_term[env0 + threadIdx.x] = term_s[threadIdx.x];
@@ -430,6 +423,7 @@ struct EvalArgs {
   int L, B, mode;
   const float* env_obs; const int32_t* env_counter; const uint32_t* env_term;
   float* episode_reward; float* lifespan;
+  int8_t split[B200PPO_MAX_LAYERS + 1];
   int stage_actor, stage_env, actor_span, ld;
 };
 
@@ -480,7 +474,7 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
         bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
       }
     __syncthreads();
-    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC);
+    const float* y = run_chain(a.plan.actor, P, bufA, bufB, ld, bufC, a.split);
     // sampling_layers.py:93-96: one count per call when deterministic (the entropy draw), two otherwise
     const Key k_sample = deterministic ? stream_key : fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
     for (int i = threadIdx.x; i < TE * A; i += NT) {
@@ -496,7 +490,7 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
       for (int c = lane; c < O + A; c += 32)
         xin[e * ld + c] = c < O ? obs_s[e * O + c] : act_s[e * A + (c - O)];
     __syncthreads();
-    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH, bufC, TE * ld);
+    dense_tile(xin, ld, O + A, Wenv, nullptr, O, xout, ld, B200PPO_ACT_TANH, bufC, a.split[B200PPO_MAX_LAYERS]);
     __syncthreads();
     for (int e = warp; e < TE; e += NT / 32) {      // reward and the next observation of one env per warp
       float s = 0.0f;
@@ -535,6 +529,7 @@ struct PolicyArgs {
   b200ppo_plan plan;
   const float* params; const float* mean; const float* std; const float* obs;
   int B, mode, ld, use_scratch;
+  int8_t split_a[B200PPO_MAX_LAYERS], split_c[B200PPO_MAX_LAYERS];
   const uint32_t* rng_state; uint32_t count_offset;
   const float* raw_in;
   float* raw; float* action; float* loglik; float* value; float* reg;
@@ -558,7 +553,7 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
     bufA[e * ld + o] = x;
   }
   __syncthreads();
-  const float* y = run_chain(a.plan.actor, a.params, bufA, bufB, ld, bufC);
+  const float* y = run_chain(a.plan.actor, a.params, bufA, bufB, ld, bufC, a.split_a);
   const Key stream_key{a.rng_state[0], a.rng_state[1]};
   uint32_t c = a.rng_state[2] + a.count_offset;
   const bool deterministic = (a.mode & 2) != 0;
@@ -601,7 +596,7 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
   }
   __syncthreads();
   float* cb = (ca == bufA) ? bufB : bufA;
-  const float* v = run_chain(a.plan.critic, a.params, ca, cb, ld, bufC);
+  const float* v = run_chain(a.plan.critic, a.params, ca, cb, ld, bufC, a.split_c);
   if (threadIdx.x < TE && row0 + threadIdx.x < a.B) a.value[row0 + threadIdx.x] = v[threadIdx.x * ld];
 }
 
@@ -611,6 +606,22 @@ int tile_ld(int md) {
   int ld = (md + 3) & ~3;
   if ((ld & 7) == 0) ld += 4;
   return ld;
+}
+
+// log2 of the k-split factor of a K x N layer on a TE-row tile (see dense_tile): a power of two that
+// fills the CTA, leaves >= 4 k per part and fits the TE * ld scratch tile.  0 = no split.
+int ksplit_log2(int K, int N, int ld) {
+  if (N <= 0 || (N & 3)) return 0;
+  const int ng = N >> 2;
+  if (ng & (ng - 1)) return 0;
+  const int items = (TE / 2) * ng;
+  int S = 1, l = 0;
+  while (S < 8 && 2 * S * items <= NT && K >= 8 * S && (2 * S - 1) * TE * N <= TE * ld) { S *= 2; ++l; }
+  return l;
+}
+void fill_split(const b200ppo_chain& c, int ld, int8_t* split) {
+  for (int l = 0; l < B200PPO_MAX_LAYERS; ++l)
+    split[l] = l < c.n_layers ? static_cast<int8_t>(ksplit_log2(c.dims[l], c.dims[l + 1], ld)) : 0;
 }
 
 int max_dim(const b200ppo_chain& c) {
@@ -687,6 +698,11 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
   a.ld = tile_ld(md);
+  fill_split(plan->actor, a.ld, a.split);
+  a.split[B200PPO_MAX_LAYERS] = static_cast<int8_t>(ksplit_log2(O + A, O, a.ld));
+  // the split path loads weight rows as float4: fall back to the unsplit path for unaligned buffers
+  if (reinterpret_cast<uintptr_t>(params) & 15) fill_split(b200ppo_chain{}, a.ld, a.split);
+  if (reinterpret_cast<uintptr_t>(env->Wo) & 15) a.split[B200PPO_MAX_LAYERS] = 0;
   // actor parameters occupy the arena prefix [0, actor_span)
   int64_t span = 0;
   for (int l = 0; l < plan->actor.n_layers; ++l) {
@@ -695,7 +711,7 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
     span = we > span ? we : span;
     span = be > span ? be : span;
   }
-  int64_t base_bytes = 4ll * (3ll * TE * a.ld + static_cast<int64_t>(TE) * O + 3ll * TE * A + 2ll * O + 6ll * TE + 8);
+  int64_t base_bytes = 4ll * (4ll * TE * a.ld + 2ll * TE * A + 2ll * O + 5ll * TE + 8);
   if (base_bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   int64_t bytes = base_bytes;
   a.actor_span = static_cast<int>(span);
@@ -741,6 +757,11 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
   a.ld = tile_ld(md);
+  fill_split(plan->actor, a.ld, a.split);
+  a.split[B200PPO_MAX_LAYERS] = static_cast<int8_t>(ksplit_log2(O + A, O, a.ld));
+  // the split path loads weight rows as float4: fall back to the unsplit path for unaligned buffers
+  if (reinterpret_cast<uintptr_t>(params) & 15) fill_split(b200ppo_chain{}, a.ld, a.split);
+  if (reinterpret_cast<uintptr_t>(env->Wo) & 15) a.split[B200PPO_MAX_LAYERS] = 0;
   int64_t span = 0;
   for (int l = 0; l < plan->actor.n_layers; ++l) {
     int64_t we = plan->actor.w_off[l] + static_cast<int64_t>(plan->actor.dims[l]) * plan->actor.dims[l + 1];
@@ -795,6 +816,12 @@ extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const
   const int mc = max_dim(plan->critic);
   md = mc > md ? mc : md;
   a.ld = tile_ld(md);
+  fill_split(plan->actor, a.ld, a.split_a);
+  fill_split(plan->critic, a.ld, a.split_c);
+  if (reinterpret_cast<uintptr_t>(params) & 15) {
+    fill_split(b200ppo_chain{}, a.ld, a.split_a);
+    fill_split(b200ppo_chain{}, a.ld, a.split_c);
+  }
   int64_t bytes = 4ll * (4ll * TE * a.ld + 2ll * TE * plan->act_dim);
   a.use_scratch = 1;
   if (bytes > SMEM_LIMIT) {               // very wide layers: no room for the k-split scratch tile (not needed there)

@@ -170,3 +170,33 @@ def test_ppo_step_bookkeeping():
         assert ro.truncated.sum() > 0 or n == 1
         assert np.all(ro.done[ro.truncated])                           # truncated ⇒ done
         assert sorted(tr["indices"][:4].ravel().tolist()) == list(range(32))
+
+
+def test_eval_rollout_bookkeeping_against_per_env_simulation():
+    """rollout.py:97-148: the batched scan against a literal one-env-at-a-time restatement
+    (deterministic sampler, so an env's trajectory does not depend on the batch it is in): the reward
+    of the terminal step counts, later ones do not; lifespan = steps before the first done."""
+    O, A, B, L = 6, 2, 24, 20
+    env = oenv.SyntheticEnv(O, A, max_len=12, term_thresh16=4000)
+    net = nets.make_mlp_actor_critic(O, A, [16], [16], seed=3)
+    key = prng.key(11)
+    c0 = net.rng_count                                                   # the init draws of the shared stream
+    cuml, life = ppo.eval_rollout(env, net, B, L, key, deterministic=True)
+    assert net.rng_count == c0 + L                                       # one (entropy) draw per call
+    keys = prng.split(key, B)
+    s0 = env.reset_fast(keys)
+    for b in range(B):
+        s = oenv.EnvState(s0.obs[b:b + 1], s0.step_counter[b:b + 1], s0.term_state[b:b + 1],
+                          s0.reward[b:b + 1], s0.done[b:b + 1], s0.truncated[b:b + 1])
+        total, steps, dead = np.float32(0), 0, False
+        for _ in range(L):
+            out = nets.policy_forward(net, s.obs, deterministic=True)
+            s = env.step(s, out["action"])
+            if not dead:
+                total = np.float32(total + s.reward[0])
+            dead = dead or bool(s.done[0])
+            if not dead:
+                steps += 1
+        assert life[b] == steps
+        assert abs(cuml[b] - total) < 1e-5
+    assert life.max() <= 11 and life.min() >= 0 and len(set(life.tolist())) > 1

@@ -262,6 +262,7 @@ struct RolloutArgs {
   float* obs; float* raw_action; float* action; float* loglik; float* reward;
   uint8_t* done; uint8_t* trunc; float* next_obs_last;
   int8_t split[B200PPO_MAX_LAYERS + 1];   // log2 k-split per actor layer; [MAX_LAYERS] = the env step
+  int use_scratch;            // the scratch tile of the k-split layers fits in shared memory
   int stage_actor;            // actor parameters staged in smem
   int stage_env;              // env weights staged in smem
   int actor_span;             // floats of the arena covered by the actor chain (starts at 0)
@@ -279,7 +280,8 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
   float* sp = smem;
   float* bufA = sp; sp += TE * ld;
   float* bufB = sp; sp += TE * ld;
-  float* bufC = sp; sp += TE * ld;      // partial tiles of the k-split layers
+  float* bufC = nullptr;                // partial tiles of the k-split layers (dropped for very wide tiles)
+  if (a.use_scratch) { bufC = sp; sp += TE * ld; }
   float* bufX = sp; sp += TE * ld;      // env-step input tile, resident across steps: [obs | action] per env row
   float* raw_s = sp; sp += TE * A;
   float* llt_s = sp; sp += TE * A;
@@ -424,6 +426,7 @@ struct EvalArgs {
   const float* env_obs; const int32_t* env_counter; const uint32_t* env_term;
   float* episode_reward; float* lifespan;
   int8_t split[B200PPO_MAX_LAYERS + 1];
+  int use_scratch;
   int stage_actor, stage_env, actor_span, ld;
 };
 
@@ -436,7 +439,8 @@ __global__ void __launch_bounds__(NT, 2) eval_synth_kernel(const EvalArgs a) {
   float* sp = smem;
   float* bufA = sp; sp += TE * ld;
   float* bufB = sp; sp += TE * ld;
-  float* bufC = sp; sp += TE * ld;
+  float* bufC = nullptr;
+  if (a.use_scratch) { bufC = sp; sp += TE * ld; }
   float* obs_s = sp; sp += TE * O;
   float* act_s = sp; sp += TE * A;
   float* mean_s = sp; sp += O;
@@ -712,6 +716,12 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
     span = be > span ? be : span;
   }
   int64_t base_bytes = 4ll * (4ll * TE * a.ld + 2ll * TE * A + 2ll * O + 5ll * TE + 8);
+  a.use_scratch = 1;
+  if (base_bytes > SMEM_LIMIT) {          // very wide tiles: run the layers unsplit, without the scratch tile
+    a.use_scratch = 0;
+    base_bytes -= 4ll * TE * a.ld;
+    for (int8_t& v : a.split) v = 0;
+  }
   if (base_bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   int64_t bytes = base_bytes;
   a.actor_span = static_cast<int>(span);
@@ -770,6 +780,12 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
     span = be > span ? be : span;
   }
   int64_t bytes = 4ll * (3ll * TE * a.ld + static_cast<int64_t>(TE) * O + static_cast<int64_t>(TE) * A + 2ll * O + TE + 8);
+  a.use_scratch = 1;
+  if (bytes > SMEM_LIMIT) {
+    a.use_scratch = 0;
+    bytes -= 4ll * TE * a.ld;
+    for (int8_t& v : a.split) v = 0;
+  }
   if (bytes > SMEM_LIMIT) return B200PPO_ELIMIT;
   a.actor_span = static_cast<int>(span);
   a.stage_actor = 0;

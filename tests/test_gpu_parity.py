@@ -242,7 +242,9 @@ def test_env_reset_matches_oracle(dev):
 
 @pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=200, T=40, max_len=24, thr=1500),
                                   dict(O=5, A=1, ah=[32, 32], ch=[32], B=64, T=30, max_len=16, thr=3000),
-                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=31, T=9, max_len=8, thr=0)])
+                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=31, T=9, max_len=8, thr=0),
+                                  # tiles too wide for the k-split scratch tile: the unsplit path
+                                  dict(O=900, A=4, ah=[32], ch=[16], B=20, T=5, max_len=8, thr=1500)])
 def test_fused_rollout_matches_oracle(dev, cfg):
     nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 11)
     env = SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
@@ -650,7 +652,8 @@ class _PerStepEnv:
 
 @pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=200, L=60, max_len=24, thr=1500),
                                   dict(O=5, A=1, ah=[32, 32], ch=[32], B=37, L=7, max_len=16, thr=3000),
-                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=64, L=20, max_len=40, thr=0)])
+                                  dict(O=12, A=3, ah=[48], ch=[16, 16], B=64, L=20, max_len=40, thr=0),
+                                  dict(O=900, A=4, ah=[32], ch=[16], B=20, L=6, max_len=8, thr=1500)])
 @pytest.mark.parametrize("deterministic", [True, False])
 def test_fused_eval_rollout_matches_oracle(dev, cfg, deterministic):
     nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 5)

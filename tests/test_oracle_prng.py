@@ -20,6 +20,18 @@ def test_jax_split_and_fold_in_known_values():
     assert prng.fold_in(prng.key(0), 1).tolist() == [928981903, 3453687069]
 
 
+def test_normal_published_value():
+    """``jax.random.normal(jax.random.key(42))`` as printed in the JAX documentation's PRNG tutorial
+    for the partitionable threefry default (JAX >= 0.5): -0.028304616.  (Quoted from the published
+    docs — this image has no JAX to regenerate it; the legacy-threefry value was -0.18471177.)  It pins
+    the whole chain bits -> uniform(nextafter(-1, 0), 1) -> sqrt(2) * erfinv for one element."""
+    x = prng.normal(prng.key(42), ())
+    assert abs(float(x) - (-0.028304616)) < 5e-9
+    assert float(prng.normal(prng.key(42), (5,))[0]) == float(x)       # partitionable: element 0 is shape-independent
+    # same tutorial: ``new_key, subkey = jax.random.split(key)`` prints new_key = [1832780943 270669613]
+    assert prng.split(prng.key(42))[0].tolist() == [1832780943, 270669613]
+
+
 def test_uniform_and_normal_ranges_and_moments():
     u = prng.uniform(prng.key(7), (1 << 16,))
     assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3

@@ -42,6 +42,31 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.SynthEnv) == 32
 
 
+def test_header_is_plain_c_and_matches_the_ctypes_mirror(tmp_path):
+    """The boundary is a C ABI: include/b200ppo.h must compile as C99 (no C++ / torch types), and the
+    struct layouts a C caller sees must be the ones the ctypes binding (and the tests) use."""
+    import subprocess
+    structs = {"b200ppo_chain": _lib.Chain, "b200ppo_plan": _lib.Plan, "b200ppo_hparams": _lib.HParams,
+               "b200ppo_update_bufs": _lib.UpdateBufs, "b200ppo_synth_env": _lib.SynthEnv,
+               "b200ppo_lstm_plan": _lib.LstmPlan}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200ppo.h"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(out[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+
+
 def test_argument_validation_without_gpu(lib):
     """Error behaviour of the ABI: bad arguments are rejected before any launch."""
     assert lib.b200ppo_gae(None, None, None, None, None, None, 4, 4, 0.9, 0.9, None) == -1

@@ -133,3 +133,34 @@ def test_no_cuda_means_loud_failure():
     nets = factories.make_mlp_actor_critic(8, 2, [16], [16], prng.Rngs(0))
     with pytest.raises(_lib.B200PPOError):
         ppo.new_training_state(SyntheticEnv(8, 2), nets, 16, 0)
+
+
+def test_reward_scaling_wrapper_scales_reset_and_step_rewards():
+    """wrappers/reward_scaling_wrapper.py:8-28 on a batched (CPU tensor) env state."""
+    import torch
+    from nnx_ppo_b200.wrappers import RewardScalingWrapper
+
+    @dataclasses.dataclass
+    class S:
+        obs: torch.Tensor
+        reward: torch.Tensor
+        done: torch.Tensor
+        info: dict
+        metrics: dict
+
+    class Env:
+        observation_size, action_size = 3, 2
+
+        def reset(self, keys):
+            B = keys.shape[0]
+            return S(torch.zeros(B, 3), torch.full((B,), 2.0), torch.zeros(B), {}, {})
+
+        def step(self, s, a):
+            return S(s.obs + 1, a.sum(dim=1), s.done, s.info, s.metrics)
+
+    w = RewardScalingWrapper(Env(), 0.25)
+    assert (w.observation_size, w.action_size) == (3, 2)
+    s0 = w.reset(torch.zeros(4, 2, dtype=torch.int32))
+    assert torch.equal(s0.reward, torch.full((4,), 0.5))
+    s1 = w.step(s0, torch.ones(4, 2))
+    assert torch.equal(s1.reward, torch.full((4,), 0.5)) and torch.equal(s1.obs, torch.ones(4, 3))

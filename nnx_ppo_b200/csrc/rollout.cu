@@ -8,7 +8,9 @@
 // Design: every env is an independent unit, so one CTA owns a tile of TE envs for ALL T steps
 // (no grid-wide synchronisation, one launch per rollout).  Actor + env weights are staged once
 // in shared memory and re-used for T steps; activations ping-pong between two smem tiles;
-// each thread computes a 2-env x 4-column register tile per layer.
+// each thread computes a 2-env x 4-column register tile per layer, and layers with fewer tiles than
+// threads split their k range over the idle threads (dense_tile).  The evaluation rollout
+// (rollout.py:97-148) is the same loop without the transition record and with sticky done flags.
 #include "common.cuh"
 
 using namespace b200ppo;

@@ -1,0 +1,107 @@
+"""Host-side metric assembly (algorithms/ppo.py) against a literal NumPy restatement of the reference's
+``compute_metrics`` / ``_log_metric`` / ``log_weight_stats`` (nnx_ppo/algorithms/metrics.py:17-121) and of
+the ``losses/*`` extras of ``ppo_loss`` (ppo.py:509-528).  CPU tensors stand in for the engine's device
+buffers: the functions only reduce what the kernels wrote."""
+import types
+
+import numpy as np
+import torch
+
+from nnx_ppo_b200.algorithms import ppo
+from nnx_ppo_b200.algorithms.types import LoggingLevel
+
+
+def _ref_log(m, name, x, pct):
+    """metrics.py:72-100."""
+    if isinstance(x, dict):
+        for k, v in x.items():
+            _ref_log(m, f"{name}/{k}", v, pct)
+    elif x.dtype == bool:
+        m[name] = x.mean()
+    elif not pct:
+        m[f"{name}/mean"], m[f"{name}/std"] = x.mean(), x.std()
+    else:
+        for p, v in zip(pct, np.percentile(x, pct)):
+            m[f"{name}/p{int(p)}"] = v
+
+
+def _fake_engine(g, T=6, B=10, A=3, P=40):
+    f = lambda *s: torch.from_numpy(g.standard_normal(s).astype(np.float32))
+    net = types.SimpleNamespace(arena=f(P), param_mask=torch.from_numpy((g.random(P) > 0.2).astype(np.uint8)))
+    done = torch.from_numpy((g.random((T, B)) < 0.3).astype(np.uint8))
+    trunc = done * torch.from_numpy((g.random((T, B)) < 0.5).astype(np.uint8))
+    return types.SimpleNamespace(net=net, reward=f(T, B), action=f(T, B, A), done=done, trunc=trunc,
+                                 loglik=f(T, B), value=f(T, B),
+                                 env_metrics={"env": {"speed": f(T, B), "sub": {"alive": 1.0 - done.float()}}},
+                                 hp=types.SimpleNamespace(grad_clip=-1.0))
+
+
+def _per_update(g, n=8):
+    pu = np.zeros((n, 12), np.float32)
+    pu[:, 0] = g.standard_normal(n) * 0.01            # actor
+    pu[:, 1] = g.random(n) + 0.1                      # critic
+    pu[:, 2] = -g.random(n) * 0.05                    # regularization
+    pu[:, 3] = g.random(n) + 0.5                      # grad norm
+    pu[:, 4] = g.random(n) * 0.3                      # clipping fraction
+    t = g.standard_normal((n, 50))
+    adv = g.standard_normal((n, 50)) * 2 + 0.3
+    pu[:, 5], pu[:, 6] = t.mean(1), (t * t).mean(1)
+    pu[:, 7], pu[:, 8] = adv.mean(1), (adv * adv).mean(1)
+    return pu, t, adv
+
+
+def test_iteration_metrics_mean_std_mode():
+    g = np.random.default_rng(0)
+    eng = _fake_engine(g)
+    pu, t, adv = _per_update(g)
+    lvl = LoggingLevel.ALL
+    m = ppo._iteration_metrics(pu, eng, lvl, None)
+    want = {}
+    for i, k in enumerate(("losses/actor", "losses/critic", "losses/regularization")):
+        _ref_log(want, k, pu[:, i], None)
+    _ref_log(want, "losses/clipping_fraction", pu[:, 4], None)                         # ppo.py:514-520
+    _ref_log(want, "losses/critic_R^2", 1.0 - 2.0 * pu[:, 1] / (t.var(1) + 1e-8), None)  # ppo.py:524-527
+    _ref_log(want, "losses/advantages", adv, None)                                     # ppo.py:523 (raw array)
+    _ref_log(want, "env", {"speed": eng.env_metrics["env"]["speed"].numpy(),
+                           "sub": {"alive": eng.env_metrics["env"]["sub"]["alive"].numpy()}}, None)
+    _ref_log(want, "rollout_batch/reward", eng.reward.numpy(), None)
+    _ref_log(want, "rollout_batch/action", eng.action.numpy(), None)
+    want["rollout_batch/done_rate"] = eng.done.numpy().astype(bool).mean()
+    want["rollout_batch/truncation_rate"] = eng.trunc.numpy().astype(bool).mean()
+    _ref_log(want, "loglikelihood", eng.loglik.numpy(), None)
+    _ref_log(want, "losses/predicted_value", eng.value.numpy(), None)
+    _ref_log(want, "weights", eng.net.arena.numpy()[eng.net.param_mask.numpy() != 0], None)
+    assert set(m) == set(want), set(m) ^ set(want)      # no grad_norm: clipping is off and the kernel did not run
+    for k, v in want.items():
+        assert np.allclose(np.float64(m[k]), v, rtol=2e-5, atol=2e-6), (k, m[k], v)
+
+
+def test_iteration_metrics_percentile_mode_and_grad_norm():
+    g = np.random.default_rng(1)
+    eng = _fake_engine(g)
+    eng.hp.grad_clip = 0.5
+    pu, _, _ = _per_update(g)
+    pct = (0, 25, 50, 100)
+    lvl = LoggingLevel.LOSSES | LoggingLevel.TRAIN_ROLLOUT_STATS | LoggingLevel.GRAD_NORM | LoggingLevel.WEIGHTS
+    m = ppo._iteration_metrics(pu, eng, lvl, pct)
+    want = {}
+    for i, k in enumerate(("losses/actor", "losses/critic", "losses/regularization")):
+        _ref_log(want, k, pu[:, i], pct)
+    _ref_log(want, "rollout_batch/reward", eng.reward.numpy(), pct)
+    _ref_log(want, "rollout_batch/action", eng.action.numpy(), pct)
+    want["rollout_batch/done_rate"] = eng.done.numpy().astype(bool).mean()
+    want["rollout_batch/truncation_rate"] = eng.trunc.numpy().astype(bool).mean()
+    _ref_log(want, "weights", eng.net.arena.numpy()[eng.net.param_mask.numpy() != 0], pct)
+    assert np.array_equal(m.pop("grad_norm"), pu[:, 3])                              # ppo.py:313-315: one per update
+    assert set(m) == set(want), set(m) ^ set(want)
+    for k, v in want.items():
+        assert np.allclose(np.float64(m[k]), v, rtol=2e-5, atol=2e-6), (k, m[k], v)
+
+
+def test_logging_level_none_and_basic():
+    g = np.random.default_rng(2)
+    eng = _fake_engine(g)
+    pu, _, _ = _per_update(g)
+    assert ppo._iteration_metrics(pu, eng, LoggingLevel.NONE, None) == {}
+    assert set(ppo._iteration_metrics(pu, eng, LoggingLevel.BASIC, None)) == {
+        f"losses/{k}/{s}" for k in ("actor", "critic", "regularization") for s in ("mean", "std")}

@@ -105,3 +105,48 @@ def test_logging_level_none_and_basic():
     assert ppo._iteration_metrics(pu, eng, LoggingLevel.NONE, None) == {}
     assert set(ppo._iteration_metrics(pu, eng, LoggingLevel.BASIC, None)) == {
         f"losses/{k}/{s}" for k in ("actor", "critic", "regularization") for s in ("mean", "std")}
+
+
+def test_train_ppo_cadence_matches_reference_rules(monkeypatch):
+    """Host loop of train_ppo (ppo.py:169-251) with the device work stubbed out: eval / checkpoint / log
+    cadence (`_should_run`, incl. the step-0 calls), stop condition, TrainResult bookkeeping."""
+    from nnx_ppo_b200.algorithms.config import EvalConfig, PPOConfig, TrainConfig
+    from nnx_ppo_b200.algorithms.types import TrainingState
+
+    class Nets:
+        mode = []
+
+        def eval(self):
+            self.mode.append("eval")
+
+        def train(self):
+            self.mode.append("train")
+
+    def fake_step(env, ts, n_envs, rollout_length, *rest):
+        return ts.replace(steps_taken=np.float32(ts.steps_taken + n_envs * rollout_length)), {"losses/x": 1.0}
+
+    evals, ckpts, logs = [], [], []
+    monkeypatch.setattr(ppo, "ppo_step", fake_step)
+    monkeypatch.setattr(ppo.rollout, "eval_rollout",
+                        lambda env, nets, n, L, key, pct: evals.append((n, L, key, pct)) or {"episode_reward/mean": 0.5})
+    nets = Nets()
+    cfg = TrainConfig(ppo=PPOConfig(n_envs=10, rollout_length=10, total_steps=1000,
+                                    logging_level=LoggingLevel.LOSSES | LoggingLevel.THROUGHPUT),
+                      eval=EvalConfig(every_steps=250, n_envs=7, max_episode_length=33), seed=5,
+                      checkpoint_every_steps=400)
+    ts = TrainingState(nets, None, None, None, (0, 1), np.float32(0.0))
+    res = ppo.train_ppo(None, nets, cfg, log_fn=lambda m, s: logs.append((s, dict(m))),
+                        checkpoint_fn=lambda st, s: ckpts.append(s), initial_state=ts)
+    assert res.total_iterations == 10 and res.total_steps == 1000
+    assert [e["step"] for e in res.eval_history] == [0, 300, 500, 800, 1000]
+    assert ckpts == [0, 400, 800]
+    assert [s for s, _ in logs] == [0] + list(range(100, 1001, 100))
+    assert evals[0] == (7, 33, (0, 5), (0, 25, 50, 75, 100))          # key(config.seed), eval config
+    assert nets.mode == ["eval", "train"] * 5                         # ppo.py:122,139
+    assert "throughput/train_sps" in logs[1][1] and "throughput/eval_sps" in logs[0][1]
+    assert "episode_reward/mean" in logs[3][1] and "episode_reward/mean" not in logs[2][1]
+    # total_steps / seed overrides, eval disabled: nothing at step 0, so no step-0 log either
+    logs.clear(); evals.clear()
+    cfg2 = TrainConfig(ppo=PPOConfig(n_envs=10, rollout_length=10), eval=EvalConfig(enabled=False))
+    res = ppo.train_ppo(None, nets, cfg2, total_steps=250, seed=9, log_fn=lambda m, s: logs.append(s), initial_state=ts)
+    assert res.total_steps == 300 and res.total_iterations == 3 and evals == [] and logs == [100, 200, 300]

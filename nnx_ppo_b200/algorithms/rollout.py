@@ -16,6 +16,7 @@ import numpy as np
 from .. import _lib, prng
 from ..networks.plan import call_network, compile_network
 from ..networks.types import PPONetworkOutput
+from ..networks.utils import tree_leaves
 from .types import LoggingLevel, Transition
 
 
@@ -112,7 +113,7 @@ def _stack_tree(steps: list, dev):
 def _extras(net, obs, raw):
     na, nc = len(net.actor_layers), len(net.critic_layers)
     ad = {"action": [None] * na + [raw], "value": [None] * nc}
-    return [obs, ad] if net.normalizer is not None else ad
+    return net.wrap(obs, ad, None) if not net.recurrent else ([obs, ad] if net.normalizer is not None else ad)
 
 
 def policy_values(net, obs_flat):
@@ -139,7 +140,7 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
     import torch
     net = compile_network(networks)
     dev = net.device
-    B = env_state.obs.shape[0]
+    B = tree_leaves(env_state.obs)[0].shape[0]
     # split(reset_key, (T, B)): element t*B + b
     keys_all = split_keys_device(reset_key, T * B, dev).reshape(T, B, 2)
     rec = {k: [] for k in ("obs", "raw", "act", "ll", "val", "rew", "done", "trunc")}
@@ -155,13 +156,13 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
             keep = (~done).to(torch.float32)[:, None]
             network_state = net.set_carry(out.next_state, (c * keep, h * keep))
         tr = nxt.info.get("truncated", torch.zeros_like(done)) if isinstance(nxt.info, dict) else torch.zeros_like(done)
-        rec["obs"].append(env_state.obs)
-        extras = out.rollout_extras[1] if net.normalizer is not None else out.rollout_extras
+        rec["obs"].append(net.flat_obs(env_state.obs))               # what the kernels saw (adapters applied)
+        extras = net.adapter_extras(out.rollout_extras)
         rec["raw"].append(extras["action"][-1]); rec["act"].append(po.actions)
         rec["ll"].append(po.loglikelihoods); rec["val"].append(po.value_estimates)
         rec["rew"].append(nxt.reward.float()); rec["done"].append(done); rec["trunc"].append(tr.bool())
         env_metrics.append(nxt.metrics if isinstance(getattr(nxt, "metrics", None), dict) else {})
-        next_obs = nxt.obs
+        next_obs = net.flat_obs(nxt.obs) if t == T - 1 else None
         reset_states = env.reset(keys_all[t].contiguous())
         env_state = tree_where(done, reset_states, nxt)
     st = {k: torch.stack(v) for k, v in rec.items()}
@@ -199,8 +200,7 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
     reset_key, new_key = prng.split(training_state.rng_key)
     _, next_env_state, tr = _unroll_generic(env, training_state.env_states, training_state.networks,
                                             training_state.network_states, rollout_length, reset_key)
-    eng.obs.copy_(tr.obs); eng.raw_action.copy_(tr.rollout_extras[1]["action"][-1] if net.normalizer is not None
-                                                else tr.rollout_extras["action"][-1])
+    eng.obs.copy_(tr.obs); eng.raw_action.copy_(net.adapter_extras(tr.rollout_extras)["action"][-1])
     eng.loglik.copy_(tr.network_output.loglikelihoods); eng.reward.copy_(tr.rewards)
     eng.action.copy_(tr.network_output.actions)
     eng.value = tr.network_output.value_estimates                         # logging only

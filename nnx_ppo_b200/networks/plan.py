@@ -20,6 +20,7 @@ from .feedforward import Dense
 from .normalizer import Normalizer
 from .sampling_layers import NormalTanhSampler
 from .types import PPONetworkOutput, StatefulModule, StatefulModuleOutput
+from .utils import Filter, Flattener, tree_leaves
 
 
 def _align4(n: int) -> int:
@@ -74,6 +75,7 @@ def _lower_chain(layers):
 class CompiledNet:
     """Device-side view of one actor-critic network."""
     recurrent = False
+    obs_adapters: list = []        # leading Flattener / Filter layers (none for recurrent plans)
 
     def __init__(self, network: StatefulModule, device):
         import torch
@@ -81,16 +83,21 @@ class CompiledNet:
         self.device = device
         normalizer: Optional[Normalizer] = None
         adapter = network
+        # leading observation adapters (networks/utils.py: Flattener / Filter) are host plumbing
+        # applied to the observation before the kernels see it; the plan starts after them
+        self.obs_adapters = []
         if isinstance(network, Sequential):
             layers = list(network.layers)
+            while len(layers) > 1 and isinstance(layers[0], (Flattener, Filter)):
+                self.obs_adapters.append(layers.pop(0))
             if len(layers) == 2 and isinstance(layers[0], Normalizer) and isinstance(layers[1], PPOAdapter):
                 normalizer, adapter = layers
             elif len(layers) == 1 and isinstance(layers[0], PPOAdapter):
                 adapter = layers[0]
             else:
                 raise NotImplementedError(
-                    "unsupported network topology: expected Sequential([Normalizer, PPOAdapter]) "
-                    "or PPOAdapter (the MLP plan of make_mlp_actor_critic)")
+                    "unsupported network topology: expected Sequential([Flattener / Filter..., Normalizer?, "
+                    "PPOAdapter]) or PPOAdapter (the MLP plan of make_mlp_actor_critic)")
         if not isinstance(adapter, PPOAdapter):
             raise NotImplementedError("unsupported network topology: no PPOAdapter found")
         action = adapter.action
@@ -206,6 +213,36 @@ class CompiledNet:
         self.engines: dict = {}
         self.adam_step = 0   # host mirror of counters[3] (optimizer step count)
 
+    # ---- observation plumbing and the reference-shaped state / extras pytrees (containers.py:18-39) ----
+    def flat_obs(self, obs):
+        """The [B, obs_size] float32 tensor the kernels consume: leading adapters applied, then a dict
+        observation of a Concat plan concatenated in the Concat's key order."""
+        import torch
+        for m in self.obs_adapters:
+            obs = m((), obs).output
+        if isinstance(obs, dict):
+            if self.obs_keys is None:
+                raise TypeError("dict observations need a network whose actor / critic start with a Concat "
+                                "(or a Flattener in front of the network)")
+            obs = torch.cat([obs[k].float() for k in self.obs_keys], dim=-1)
+        return obs
+
+    def wrap(self, obs_flat, adapter_part, leaf):
+        """Per-layer list of the enclosing Sequential: `leaf` for every adapter, then the Normalizer's
+        entry (`obs_flat` for extras, `()` for state), then the PPOAdapter's part."""
+        n = len(self.obs_adapters)
+        if self.normalizer is not None:
+            return [leaf] * n + [obs_flat, adapter_part]
+        if n:
+            return [leaf] * n + [adapter_part]
+        return adapter_part
+
+    def adapter_extras(self, rollout_extras):
+        """The PPOAdapter's part of a rollout_extras pytree produced by ``wrap``."""
+        if self.normalizer is not None or self.obs_adapters:
+            return rollout_extras[-1]
+        return rollout_extras
+
     # ---- flat <-> logical parameter order (actor W0,b0,..., critic W0,b0,...; no padding) ----
     def params_logical(self, arena=None) -> np.ndarray:
         """An arena-shaped tensor (parameters by default; also gradients, Adam moments) in the
@@ -260,12 +297,11 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     the fused policy-step kernel (K1).  Mirrors the output structure of containers.py:18-39 /
     adapter.py:100-117: rollout_extras = [raw_obs, {"action": [None..., raw_action], "value": [...]}]."""
     import torch
-    if isinstance(obs, dict):
-        # dict observations (Concat plan): concatenated in the Concat's key order (plumbing only)
-        net0 = compile_network(network, next(iter(obs.values())).device)
-        if net0.obs_keys is None:
-            raise TypeError("dict observations need a network whose actor / critic start with a Concat")
-        obs = torch.cat([obs[k].float() for k in net0.obs_keys], dim=-1)
+    leaves = tree_leaves(obs)
+    if not leaves or not all(isinstance(x, torch.Tensor) for x in leaves):
+        raise TypeError("observations must be a CUDA float32 torch tensor [B, obs_size] (or a pytree of them)")
+    # adapters / dict observations (Concat plan): plumbing only
+    obs = compile_network(network, leaves[0].device).flat_obs(obs)
     if not isinstance(obs, torch.Tensor):
         raise TypeError("observations must be a CUDA float32 torch tensor [B, obs_size] (or a dict of them)")
     net = compile_network(network, obs.device)
@@ -278,10 +314,7 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     A = net.plan.act_dim
     raw_in = None
     if rollout_extras is not None:
-        extras = rollout_extras
-        if net.normalizer is not None:
-            extras = extras[1]
-        raw_in = extras["action"][-1].contiguous().float()
+        raw_in = net.adapter_extras(rollout_extras)["action"][-1].contiguous().float()
     mode = (1 if raw_in is not None else 0) | (2 if net.sampler.deterministic else 0)
     dev = obs.device
     raw = torch.empty(B, A, device=dev)
@@ -303,9 +336,7 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     adapter_state = {"action": [()] * (na + 1), "value": [()] * nc}
     adapter_extras = {"action": [None] * na + [raw], "value": [None] * nc}
     out = PPONetworkOutput(actions=action, loglikelihoods=ll, value_estimates=value)
-    if net.normalizer is not None:
-        return StatefulModuleOutput([(), adapter_state], out, reg, {}, [obs, adapter_extras])
-    return StatefulModuleOutput(adapter_state, out, reg, {}, adapter_extras)
+    return StatefulModuleOutput(net.wrap((), adapter_state, ()), out, reg, {}, net.wrap(obs, adapter_extras, None))
 
 
 def _call_recurrent(net, state: Any, obs, rollout_extras: Any):

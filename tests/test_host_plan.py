@@ -44,3 +44,104 @@ def test_unsupported_chains_raise():
         Concat()
     with pytest.raises(ValueError):
         Concat({"a": enc([4, 8])}, b=enc([4, 8]))
+
+
+# ------------------------------------------------------------------------------------------
+# observation adapters (networks/utils.py: Flattener / Filter) — the reference's own unit tests
+# (networks/utils_test.py:36-148) on torch CPU tensors
+# ------------------------------------------------------------------------------------------
+import torch                                                              # noqa: E402
+
+from nnx_ppo_b200.networks.adapter import PPOAdapter                      # noqa: E402
+from nnx_ppo_b200.networks.normalizer import Normalizer                   # noqa: E402
+from nnx_ppo_b200.networks.plan import CompiledNet                        # noqa: E402
+from nnx_ppo_b200.networks.utils import Filter, Flattener                 # noqa: E402
+
+
+def test_filter_specs():
+    out = Filter({"out": "a"})((), {"a": torch.ones(2, 3), "b": torch.zeros(2, 4)}).output
+    assert torch.equal(out["out"], torch.ones(2, 3)) and "b" not in out
+    obs = {"arm": {"proprio": torch.ones(2, 4), "target": torch.zeros(2, 5)}, "head": torch.full((2, 3), 5.0)}
+    out = Filter({"p": ("arm", "proprio"), "z": "head", "calc": lambda o: o["head"] * 2})((), obs).output
+    assert torch.equal(out["p"], torch.ones(2, 4)) and torch.equal(out["z"], obs["head"])
+    assert torch.equal(out["calc"], torch.full((2, 3), 10.0)) and set(out) == {"p", "z", "calc"}
+    with pytest.raises(TypeError):
+        Filter({"x": 5})
+    with pytest.raises(TypeError):
+        Filter([("a", "b")])
+
+
+def test_flattener_levels():
+    x = {"b": torch.full((2, 5), 4.0), "a": torch.ones(2, 3)}
+    flat = Flattener()((), x).output
+    assert flat.shape == (2, 8) and torch.equal(flat[0], torch.tensor([1.0] * 3 + [4.0] * 5))   # jax.tree order: sorted keys
+    assert Flattener()((), torch.ones(2, 7)).output.shape == (2, 7)
+    assert Flattener()((), {"img": torch.ones(2, 3, 4)}).output.shape == (2, 12)
+    nested = {"arm": {"proprio": torch.ones(2, 4), "target": torch.zeros(2, 8)}, "root": torch.full((2, 6), 3.0)}
+    out = Flattener(preserve_levels=1)((), nested).output
+    assert set(out) == {"arm", "root"} and out["arm"].shape == (2, 12) and out["root"].shape == (2, 6)
+    same = Flattener(preserve_levels=1)((), x).output
+    assert torch.equal(same["a"], x["a"]) and torch.equal(same["b"], x["b"])
+    deep = {"arm": {"p": {"a": torch.ones(2, 3), "b": torch.zeros(2, 4)}, "t": torch.ones(2, 5)}}
+    out = Flattener(preserve_levels=2)((), deep).output
+    assert out["arm"]["p"].shape == (2, 7) and out["arm"]["t"].shape == (2, 5)
+    with pytest.raises(ValueError):
+        Flattener(preserve_levels=-1)
+    with pytest.raises(TypeError):
+        Flattener(preserve_levels=2)((), {"a": torch.ones(2, 3)})
+
+
+def _adapter_net(normalize=True):
+    base = factories.make_mlp_actor_critic(9, 2, [8], [8], prng.Rngs(0), normalize_obs=normalize)
+    tail = list(base.layers) if normalize else [base]
+    return Sequential([Filter({"p": ("arm", "proprio"), "h": "head"}), Flattener(), *tail])
+
+
+def test_plan_recognises_leading_observation_adapters():
+    """The plan compiler (no kernel is launched by it, so it runs on CPU tensors) strips leading
+    Flattener / Filter layers, applies them as host plumbing and keeps the reference-shaped per-layer
+    state / rollout_extras lists of the enclosing Sequential (containers.py:18-39)."""
+    obs = {"arm": {"proprio": torch.arange(8.0).reshape(2, 4), "target": torch.zeros(2, 3)},
+           "head": torch.full((2, 5), 7.0)}
+    for normalize in (True, False):
+        nets = _adapter_net(normalize)
+        net = CompiledNet(nets, torch.device("cpu"))
+        assert [type(m).__name__ for m in net.obs_adapters] == ["Filter", "Flattener"]
+        assert net.plan.obs_dim == 9 and (net.normalizer is not None) == normalize
+        flat = net.flat_obs(obs)
+        assert torch.equal(flat, torch.cat([obs["head"], obs["arm"]["proprio"]], dim=-1))      # sorted keys: h, p
+        state = nets.initialize_state(2)
+        assert len(state) == (4 if normalize else 3) and state[0] == () and state[1] == ()
+        ad_state, ad_extras = {"action": [(), ()], "value": [(), ()]}, {"action": [None, "raw"], "value": [None, None]}
+        assert net.wrap((), ad_state, ()) == ([(), (), (), ad_state] if normalize else [(), (), ad_state])
+        extras = net.wrap(flat, ad_extras, None)
+        assert extras[:2] == [None, None] and extras[-1] is ad_extras and net.adapter_extras(extras) is ad_extras
+        if normalize:
+            assert extras[2] is flat
+            seen = []                                                                  # Sequential zips layers with extras
+            nets.layers[2].update_statistics = seen.append
+            nets.update_statistics(extras)
+            assert len(seen) == 1 and seen[0] is flat
+    # adapters alone are not a network
+    with pytest.raises(NotImplementedError):
+        CompiledNet(Sequential([Flattener()]), torch.device("cpu"))
+
+
+def test_plan_of_existing_topologies_is_unchanged():
+    for nets, wrapped in ((factories.make_mlp_actor_critic(5, 2, [8], [8], prng.Rngs(0)), True),
+                          (factories.make_mlp_actor_critic(5, 2, [8], [8], prng.Rngs(0), normalize_obs=False), False)):
+        net = CompiledNet(nets, torch.device("cpu"))
+        assert net.obs_adapters == []
+        x = torch.ones(3, 5)
+        assert net.flat_obs(x) is x
+        ad = {"action": [None, "raw"], "value": [None, None]}
+        assert net.wrap(x, ad, None) == ([x, ad] if wrapped else ad)
+        assert net.wrap((), ad, ()) == ([(), ad] if wrapped else ad)
+        assert net.adapter_extras(net.wrap(x, ad, None)) is ad
+    d = factories.make_dict_actor_critic({"a": 4, "b": 6}, 2, {"a": [8], "b": [8]}, [16], [16], prng.Rngs(0))
+    net = CompiledNet(d, torch.device("cpu"))
+    o = {"b": torch.ones(2, 6), "a": torch.zeros(2, 4)}
+    assert torch.equal(net.flat_obs(o), torch.cat([o["a"], o["b"]], dim=-1))                   # the Concat's key order
+    plain = CompiledNet(factories.make_mlp_actor_critic(10, 2, [8], [8], prng.Rngs(0)), torch.device("cpu"))
+    with pytest.raises(TypeError):
+        plain.flat_obs(o)

@@ -145,3 +145,58 @@ def test_plan_of_existing_topologies_is_unchanged():
     plain = CompiledNet(factories.make_mlp_actor_critic(10, 2, [8], [8], prng.Rngs(0)), torch.device("cpu"))
     with pytest.raises(TypeError):
         plain.flat_obs(o)
+
+
+# ------------------------------------------------------------------------------------------
+# parameter arena layout and logical (oracle) order — the plan compiler on CPU tensors
+# ------------------------------------------------------------------------------------------
+def _check_arena(net, oracle_flat):
+    logical = net.params_logical()
+    assert logical.shape == oracle_flat.shape and np.array_equal(logical, oracle_flat)     # same init, same order
+    for ch in (net.plan.actor, net.plan.critic):
+        for l in range(ch.n_layers):
+            assert ch.w_off[l] % 4 == 0 and ch.b_off[l] % 4 == 0                               # float4-aligned blocks
+            assert ch.b_off[l] + ch.dims[l + 1] <= net.n_params
+    # the logical index addresses every real parameter exactly once; padding and structural zeros are 0
+    assert len(np.unique(net._logical_index)) == oracle_flat.size
+    real = np.zeros(net.n_params, bool)
+    real[net._logical_index] = True
+    assert np.all(net.arena.numpy()[~real] == 0.0)
+    if net.param_mask is not None:
+        assert np.all(net.param_mask.numpy()[net._logical_index] == 1)
+    # every module parameter is a VIEW into the arena: training mutates the user's network in place
+    net.arena.add_(1.0)
+    assert np.array_equal(net.params_logical(), oracle_flat + 1.0)
+    p0 = net._logical_params[0]
+    assert np.array_equal(p0.numpy().ravel(), (oracle_flat + 1.0)[:p0.numpy().size])
+    net.load_params_logical(oracle_flat)
+    assert np.array_equal(net.params_logical(), oracle_flat)
+
+
+def test_arena_layout_mlp_and_dict_plans_match_oracle_order():
+    from oracle import dictnet, nets as onets
+    nets = factories.make_mlp_actor_critic(24, 5, [64, 32], [48], prng.Rngs(7), activation="tanh")
+    onet = onets.make_mlp_actor_critic(24, 5, [64, 32], [48], seed=7, activation="tanh")
+    net = CompiledNet(nets, torch.device("cpu"))
+    assert (net.plan.obs_dim, net.plan.act_dim, net.plan.normalize) == (24, 5, 1) and net.param_mask is None
+    _check_arena(net, onet.flat_params())
+    sizes, enc = {"proprio": 6, "target": 10}, {"proprio": [8, 4], "target": [12, 5]}
+    nets = factories.make_dict_actor_critic(sizes, 3, enc, [16], [7, 7], prng.Rngs(2))
+    onet = dictnet.make_dict_actor_critic(sizes, 3, enc, [16], [7, 7], seed=2)
+    net = CompiledNet(nets, torch.device("cpu"))
+    assert net.plan.obs_dim == 16 and net.param_mask is not None
+    # block-diagonal layers: the off-diagonal blocks are masked structural zeros
+    n_struct_zero = 2 * ((6 * 12 + 10 * 8) + (8 * 5 + 12 * 4))                                # actor + critic towers
+    assert int((net.param_mask == 0).sum()) == n_struct_zero
+    assert float(net.arena[net.param_mask == 0].abs().max()) == 0.0
+    _check_arena(net, onet.flat_params())
+
+
+def test_arena_layout_recurrent_plan_matches_oracle_order():
+    from nnx_ppo_b200.networks.rplan import RecurrentCompiledNet
+    from oracle import recurrent as orec
+    nets = factories.make_recurrent_actor_critic(16, 4, 32, 24, [48], prng.Rngs(1))
+    onet = orec.make_recurrent_actor_critic(16, 4, [32], 24, [], [48], seed=1)
+    net = RecurrentCompiledNet(nets, torch.device("cpu"))
+    assert net.recurrent and net.obs_adapters == []
+    assert np.array_equal(net.params_logical(), onet.flat_params())

@@ -164,3 +164,36 @@ def test_reward_scaling_wrapper_scales_reset_and_step_rewards():
     assert torch.equal(s0.reward, torch.full((4,), 0.5))
     s1 = w.step(s0, torch.ones(4, 2))
     assert torch.equal(s1.reward, torch.full((4,), 0.5)) and torch.equal(s1.obs, torch.ones(4, 3))
+
+
+def test_host_side_sizing_entry_points_for_the_bench_configuration(lib):
+    """The ABI's host-only entry points (no launch) on the BASELINE configs[1] plan: workspace size,
+    kernel launches per update (what `bench.py` reports as gpu_launches), scratch sizes, pointer
+    helpers stay inside the workspace.  The plan compiler runs without a device."""
+    import torch
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    nets = factories.make_mlp_actor_critic(64, 8, [64] * 4, [256] * 2, prng.Rngs(0))
+    net = CompiledNet(nets, torch.device("cpu"))
+    assert net.n_params == 100_372                                        # DESIGN.md section 2
+    T, mb = 32, 512
+    ws = int(lib.b200ppo_update_workspace_bytes(net.plan, T, mb))
+    assert 100e6 < ws < 130e6 and ws % 16 == 0                            # "~113 MB at cfg 2"
+    assert int(lib.b200ppo_update_workspace_bytes(net.plan, T, 2 * mb)) > ws
+    hp = _lib.HParams()
+    hp.gamma, hp.lambda_, hp.clip_range, hp.critic_loss_weight = 0.99, 0.95, 0.2, 1.0
+    hp.learning_rate, hp.adam_b1, hp.adam_b2, hp.adam_eps = 1e-4, 0.9, 0.999, 1e-8
+    hp.weight_decay, hp.grad_clip, hp.normalize_advantages, hp.world_size = -1.0, -1.0, 1, 1
+    first = int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL))
+    later = int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP))
+    assert (first, later) == (7, 6)            # prep + fwd, gae, loss, dX, dW, reduce+adam
+    # one iteration: 32 updates + norm prepare, rollout, permutation, 2 stats passes, merge, finalize
+    assert first + 31 * later + 7 == 200       # bench.py's gpu_launches at configs[1]
+    hp.grad_clip = 0.5                         # clip_by_global_norm: separate reduce, norm and Adam launches
+    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP)) == 8
+    base = 1 << 20
+    for fn in (lib.b200ppo_update_adv_sums_ptr, lib.b200ppo_update_grad_ptr):
+        p = int(fn(net.plan, T, mb, base))
+        assert base <= p < base + ws and p % 16 == 0
+    assert int(lib.b200ppo_permutation_scratch_bytes(4096, 4)) > 0
+    assert int(lib.b200ppo_norm_scratch_bytes(64)) > 0
+    assert int(lib.b200ppo_comm_bytes(net.plan, 8)) > 8 * 2 * 4 * net.n_params   # two parities x 8 rank slots

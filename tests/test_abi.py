@@ -197,3 +197,21 @@ def test_host_side_sizing_entry_points_for_the_bench_configuration(lib):
     assert int(lib.b200ppo_permutation_scratch_bytes(4096, 4)) > 0
     assert int(lib.b200ppo_norm_scratch_bytes(64)) > 0
     assert int(lib.b200ppo_comm_bytes(net.plan, 8)) > 8 * 2 * 4 * net.n_params   # two parities x 8 rank slots
+
+
+def test_host_key_arithmetic_equals_the_oracle_restatement():
+    """nnx_ppo_b200/prng.py (host key flow of the product) against oracle/prng.py (NumPy restatement) on
+    random keys: split, fold_in, uniform and the variance-scaling initializer draw."""
+    from oracle import prng as oprng
+    g = np.random.default_rng(5)
+    for _ in range(20):
+        k = (int(g.integers(0, 2 ** 32)), int(g.integers(0, 2 ** 32)))
+        ok = np.array(k, np.uint32)
+        n = int(g.integers(1, 9))
+        assert prng.split(k, n) == [tuple(int(x) for x in r) for r in oprng.split(ok, n)]
+        d = int(g.integers(0, 2 ** 32))
+        assert prng.fold_in(k, d) == tuple(int(x) for x in oprng.fold_in(ok, d))
+        shape = (int(g.integers(1, 7)), int(g.integers(1, 7)))
+        assert np.array_equal(prng.uniform(k, shape, -1.0, 1.0), oprng.uniform(ok, shape, -1.0, 1.0))
+        assert np.array_equal(prng.variance_scaling_uniform(k, *shape), oprng.variance_scaling_uniform(ok, *shape, 1.0))
+    assert prng.key(2 ** 40 + 3) == (2 ** 8, 3) and prng.key(17) == (0, 17)

@@ -215,3 +215,48 @@ def test_host_key_arithmetic_equals_the_oracle_restatement():
         assert np.array_equal(prng.uniform(k, shape, -1.0, 1.0), oprng.uniform(ok, shape, -1.0, 1.0))
         assert np.array_equal(prng.variance_scaling_uniform(k, *shape), oprng.variance_scaling_uniform(ok, *shape, 1.0))
     assert prng.key(2 ** 40 + 3) == (2 ** 8, 3) and prng.key(17) == (0, 17)
+
+
+def test_rollout_and_policy_launchers_reject_before_launching(lib):
+    """Error behaviour of the K1 launchers with a valid plan but unusable arguments: every check runs on
+    the host before the first CUDA call, so the codes can be observed without a GPU (the fake pointers
+    are never dereferenced on these paths)."""
+    import torch
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    EINVAL, ELIMIT = -1, -2
+    net = CompiledNet(factories.make_mlp_actor_critic(12, 3, [16], [16], prng.Rngs(0)), torch.device("cpu"))
+    env = _lib.SynthEnv()
+    env.obs_dim, env.act_dim, env.max_len, env.term_thresh16 = 12, 3, 16, 100
+    env.Wo, env.Wa = 0x10000, 0x10000 + 4 * 12 * 12
+    p = 0x20000                                           # any non-null, 16-byte aligned address
+    ok_args = [None, net.plan, env, p, p, p, p, p, 8, 32] + [p] * 11
+    def rollout(**kw):
+        a = list(ok_args)
+        for i, v in kw.items():
+            a[int(i[1:])] = v
+        return lib.b200ppo_rollout_synth(*a)
+    assert rollout(a3=None) == EINVAL                      # params
+    assert rollout(a8=0) == EINVAL and rollout(a9=0) == EINVAL      # T, B
+    assert rollout(a4=None) == EINVAL                      # normalising plan without statistics
+    bad_env = _lib.SynthEnv()
+    bad_env.obs_dim, bad_env.act_dim, bad_env.max_len, bad_env.term_thresh16 = 11, 3, 16, 100
+    bad_env.Wo, bad_env.Wa = env.Wo, env.Wa
+    assert rollout(a2=bad_env) == EINVAL                   # env / plan size mismatch
+    env.Wa += 4
+    assert rollout() == EINVAL                             # Wa must follow Wo contiguously
+    env.Wa -= 4
+    assert lib.b200ppo_eval_synth(None, net.plan, env, p, p, p, p, 1, 10, 32, p, p, p, p, p) == EINVAL   # mode: 0 or 2
+    assert lib.b200ppo_eval_synth(None, net.plan, env, p, p, p, p, 2, 0, 32, p, p, p, p, p) == EINVAL    # L
+    # tiles that cannot fit in shared memory even without the k-split scratch tile
+    wide = CompiledNet(factories.make_mlp_actor_critic(6000, 3, [16], [16], prng.Rngs(0)), torch.device("cpu"))
+    wenv = _lib.SynthEnv()
+    wenv.obs_dim, wenv.act_dim, wenv.max_len, wenv.term_thresh16 = 6000, 3, 16, 100
+    wenv.Wo, wenv.Wa = 0x10000, 0x10000 + 4 * 6000 * 6000
+    a = list(ok_args)
+    a[1], a[2] = wide.plan, wenv
+    assert lib.b200ppo_rollout_synth(*a) == ELIMIT
+    assert lib.b200ppo_eval_synth(None, wide.plan, wenv, p, p, p, p, 2, 10, 32, p, p, p, p, p) == ELIMIT
+    assert lib.b200ppo_policy_step(None, wide.plan, p, p, p, p, 32, 0, p, 0, None, p, p, p, p, None, None) == ELIMIT
+    assert lib.b200ppo_policy_step(None, net.plan, p, p, p, p, 0, 0, p, 0, None, p, p, p, p, None, None) == 0   # empty batch
+    assert lib.b200ppo_policy_step(None, net.plan, p, p, p, p, 32, 1, p, 0, None, p, p, p, p, None, None) == EINVAL  # replay needs raw actions
+    assert b"limit" in lib.b200ppo_error_string(ELIMIT).lower()

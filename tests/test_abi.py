@@ -260,3 +260,40 @@ def test_rollout_and_policy_launchers_reject_before_launching(lib):
     assert lib.b200ppo_policy_step(None, net.plan, p, p, p, p, 0, 0, p, 0, None, p, p, p, p, None, None) == 0   # empty batch
     assert lib.b200ppo_policy_step(None, net.plan, p, p, p, p, 32, 1, p, 0, None, p, p, p, p, None, None) == EINVAL  # replay needs raw actions
     assert b"limit" in lib.b200ppo_error_string(ELIMIT).lower()
+
+
+def test_update_launcher_rejects_before_launching(lib):
+    """b200ppo_update's host-side argument checks (all before the first CUDA call)."""
+    import torch
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    EINVAL, EALIGN = -1, -3
+    net = CompiledNet(factories.make_mlp_actor_critic(12, 3, [16], [16], prng.Rngs(0)), torch.device("cpu"))
+    hp = _lib.HParams()
+    hp.world_size = 1
+    b = _lib.UpdateBufs()
+    p = 0x40000
+    for name, _ in _lib.UpdateBufs._fields_:
+        if name not in ("comm", "param_mask"):
+            setattr(b, name, p)
+    call = lambda T=8, B=32, mb=16, u=0, hp_=hp, b_=b, plan=net.plan: lib.b200ppo_update(
+        None, plan, hp_, b_, T, B, mb, 0, u, _lib.STAGE_ALL)
+    assert call(T=0) == EINVAL and call(mb=0) == EINVAL and call(mb=64) == EINVAL and call(u=-1) == EINVAL
+    assert call(plan=_lib.Plan()) != 0                                     # empty plan
+    b.ws = p + 16
+    assert call() == EALIGN                                                # workspace must be 256-byte aligned
+    b.ws = p
+    b.norm_mean = 0
+    assert call() == EINVAL                                                # normalising plan without statistics
+    b.norm_mean = p
+    b.obs = 0
+    assert call() == EINVAL
+    b.obs = p
+    hp.world_size = 0
+    assert call() == EINVAL
+    hp.world_size, hp.rank, b.comm, hp.grad_clip = 4, 4, p, -1.0
+    assert call() == EINVAL                                                # rank out of range on the peer-memory path
+    hp.rank, hp.grad_clip = 1, 0.5
+    assert call() == EINVAL                                                # clipping needs the staged (NCCL) path
+    hp.world_size = _lib.MAX_RANKS + 1 if hasattr(_lib, "MAX_RANKS") else 17
+    hp.grad_clip = -1.0
+    assert call() == EINVAL

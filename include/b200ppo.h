@@ -81,6 +81,23 @@ typedef struct b200ppo_hparams {
   int32_t rank;             /* this process' rank (only read when bufs->comm is set)      */
 } b200ppo_hparams;
 
+/* Device copy of the numeric hyper-parameters (b200ppo_update_bufs.hparams_dev): float[B200PPO_HP_FLOATS].
+ * The reference keeps gae_lambda / discounting_factor as TRACED scalars of its jitted step
+ * (ppo.py:105) and the learning rate inside the optax state, i.e. they are run-time data of the
+ * device program; a captured CUDA graph follows a schedule the same way when the kernels read them
+ * from device memory instead of from their (captured) launch arguments. */
+#define B200PPO_HP_GAMMA 0
+#define B200PPO_HP_LAMBDA 1
+#define B200PPO_HP_CLIP_RANGE 2
+#define B200PPO_HP_CRITIC_WEIGHT 3
+#define B200PPO_HP_LEARNING_RATE 4
+#define B200PPO_HP_ADAM_B1 5
+#define B200PPO_HP_ADAM_B2 6
+#define B200PPO_HP_ADAM_EPS 7
+#define B200PPO_HP_WEIGHT_DECAY 8
+#define B200PPO_HP_GRAD_CLIP 9
+#define B200PPO_HP_FLOATS 16
+
 #define B200PPO_METRICS_STRIDE 12
 
 /* Device buffers of one minibatch update.  ws is a scratch arena of
@@ -107,7 +124,11 @@ typedef struct b200ppo_update_bufs {
   float* metrics_out;          /* dev [B200PPO_METRICS_STRIDE]: [0] actor loss, [1] critic loss,
                                 * [2] regularisation loss, [3] grad norm (with gradient clipping),
                                 * [4] clipping fraction, [5] E[target], [6] E[target^2], [7] E[adv],
-                                * [8] E[adv^2] - all divided by the global sample count */
+                                * [8] E[adv^2] of the advantages the surrogate uses (normalised when
+                                * normalize_advantages: ppo.py:477-480 reassigns `advantages` before it is
+                                * logged at :523) - all divided by the global sample count; [9], [10] the
+                                * normalisation constants mean(a), std(a) + 1e-8 (0, 1 when off) divided by
+                                * world_size: a SUM over ranks returns every entry as its global value */
   void* ws;                    /* dev scratch                                                      */
   /* optional peer-memory exchange (NULL: the caller all-reduces adv_sums and the gradient between
    * the stages).  dev uint64[world_size]: base address of every rank's comm buffer
@@ -117,6 +138,15 @@ typedef struct b200ppo_update_bufs {
    * encoders — containers.py Concat — are laid out as one block-diagonal Dense layer); such entries
    * are excluded from the gradient norm and never updated.  NULL: every entry is a parameter. */
   const uint8_t* param_mask;
+  /* optional dev float[B200PPO_HP_FLOATS]: when non-NULL the kernels read the numeric hyper-parameters
+   * (gamma, lambda, clip range, critic weight, learning rate, Adam b1 / b2 / eps, weight-decay and
+   * clip-threshold VALUES) from here instead of from `hp`; `hp` still decides the launch structure
+   * (weight decay on / off, clipping on / off, normalize_advantages, world size). */
+  const float* hparams_dev;
+  /* optional dev uint32[1]: monotonic base of the peer-exchange epoch (epoch = base + update_index +
+   * 1), advanced by b200ppo_iter_finalize.  NULL: the Adam count rng_state[3] is the base (it goes
+   * backwards when a training state is rolled back, which would make stale flags look current). */
+  const uint32_t* comm_epoch;
 } b200ppo_update_bufs;
 
 /* -------- library -------------------------------------------------------------------------- */
@@ -158,7 +188,9 @@ int b200ppo_norm_merge(void* stream, const float* batch_stats /*dev [world][2*O]
 /* -------- K1: policy step (rollout.py:18; sampling_layers.py:82-113; adapter.py:75-117) ----- *
  * One network call on B rows: normalize -> actor -> NormalTanhSampler -> critic.                *
  * mode 0: sample (rollout_extras=None); 1: replay raw_action_in; |2: deterministic (mean).      *
- * count_offset is added to rng_state[2]; the call consumes 2 counts (1 if deterministic).       */
+ * count_offset is added to rng_state[2]; the call consumes 2 counts (1 if deterministic).       *
+ * ws (nullable, b200ppo_policy_workspace_bytes() bytes): receives [B][2A] = [mu | sigma], the     *
+ * sampler's `metrics` dict (sampling_layers.py:111); everything else lives in shared memory.      */
 int64_t b200ppo_policy_workspace_bytes(const b200ppo_plan* plan, int32_t B);
 int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const float* params /*dev*/,
                         const float* norm_mean /*dev*/, const float* norm_std /*dev*/,
@@ -167,7 +199,7 @@ int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const float* par
                         const float* raw_action_in /*dev [B][A] or NULL*/,
                         float* raw_action /*dev [B][A]*/, float* action /*dev [B][A]*/,
                         float* loglik /*dev [B]*/, float* value /*dev [B]*/,
-                        float* reg_loss /*dev [B] or NULL*/, void* ws /*dev*/);
+                        float* reg_loss /*dev [B] or NULL*/, void* ws /*dev [B][2A] or NULL*/);
 
 /* -------- K1 (persistent): fused T-step rollout on the synthetic env (rollout.py:11-73) ---- *
  * env state (in/out): obs [B][O], step_counter int32 [B], term_state uint32 [B].                *
@@ -315,6 +347,11 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
+/* Programmatic dependent launch between the kernels of b200ppo_update (each kernel's prologue overlaps *
+ * its predecessor's tail; griddepcontrol.wait before the first dependent access): 1 = on (default),  *
+ * 0 = plain stream order; also B200PPO_PDL=0|1.  Returns the previous setting; any other value only *
+ * queries.  Takes effect for launches (and graph captures) made afterwards.                         */
+int b200ppo_set_pdl(int on);
 /* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *
  * kernel -> out_host; returns -(1000 + count).                                                   */
 int b200ppo_debug_timestamps(long long* out_host, int32_t max_n);
@@ -329,9 +366,10 @@ float* b200ppo_update_grad_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, 
 float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws,
                                 int32_t which /*0 adv, 1 values, 2 actor out, 3 d_y, 4 d_v*/);
 
-/* End-of-iteration bookkeeping: rng_state[2] += rng_advance; rng_state[3] += adam_advance. */
+/* End-of-iteration bookkeeping: rng_state[2] += rng_advance; rng_state[3] += adam_advance;
+ * comm_epoch (nullable, dev uint32[1]) += adam_advance. */
 int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rng_advance,
-                          uint32_t adam_advance);
+                          uint32_t adam_advance, uint32_t* comm_epoch /*dev or NULL*/);
 
 /* -------- tensor-core bring-up / parity hook: C[M][N] = A[M][K] * B[K][N] with tcgen05.mma ---- *
  * kind::tf32, fp32 accumulation in TMEM; split = 0: plain TF32 operands, 1: error-compensated   *

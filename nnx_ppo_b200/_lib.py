@@ -19,6 +19,10 @@ STAGE_ALL = 63
 STAGE_BWD_DX, STAGE_BWD_DW = 64, 128
 STAGE_NO_PREP = 256
 METRICS_STRIDE = 12   # B200PPO_METRICS_STRIDE
+# layout of the device hyper-parameter block (B200PPO_HP_*)
+HP_GAMMA, HP_LAMBDA, HP_CLIP_RANGE, HP_CRITIC_WEIGHT, HP_LEARNING_RATE = 0, 1, 2, 3, 4
+HP_ADAM_B1, HP_ADAM_B2, HP_ADAM_EPS, HP_WEIGHT_DECAY, HP_GRAD_CLIP = 5, 6, 7, 8, 9
+HP_FLOATS = 16
 
 
 class Chain(C.Structure):
@@ -45,7 +49,7 @@ class UpdateBufs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "raw_action", "loglik_old", "reward", "done", "truncated", "next_obs_last", "inds",
         "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm",
-        "param_mask")]
+        "param_mask", "hparams_dev", "comm_epoch")]
 
 
 class LstmPlan(C.Structure):
@@ -107,7 +111,8 @@ SYMBOLS = {
     "b200ppo_lstm_wgrad_scratch_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
     "b200ppo_lstm_weight_grads": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200ppo_sampler_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
-    "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32]),
+    "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32, _vp]),
+    "b200ppo_set_pdl": (C.c_int, [C.c_int]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
     "b200ppo_tc_microbench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
     "b200ppo_ffma_peak": (C.c_int, [_vp, _i32, _vp, _i32, _i32]),

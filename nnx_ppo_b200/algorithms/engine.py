@@ -5,11 +5,15 @@ ppo.py:254-348) as a fixed launch sequence over preallocated HBM buffers:
     (FWD, GAE, LOSS, BWD, RED, ADAM) -> Normalizer batch statistics + merge -> counters
 
 The sequence is captured once into a CUDA graph and replayed per iteration (the reference relies
-on XLA's jit for the same purpose).  Per-iteration inputs (the two PRNG keys of ppo.py:271) are
-copied from pinned host memory into a 16-byte device block that the kernels read, so the graph
-never needs re-capturing.  With world_size > 1 every rank runs the same sequence on its own env
-shard and two NCCL all-reduces per update (advantage moment sums, flat gradient) plus one
-all-gather per iteration (Normalizer batch statistics) keep the ranks in lock step.
+on XLA's jit for the same purpose).  Per-iteration inputs — the two PRNG keys of ppo.py:271 and the
+numeric hyper-parameters (gamma, lambda, clip range, critic weight, learning rate ..., which the
+reference keeps as traced scalars / optax state, ppo.py:105) — travel in ONE 80-byte block copied
+from a ring of pinned host slots into device memory that the kernels read, so the graph never needs
+re-capturing and a schedule costs nothing.  With world_size > 1 every rank runs the same sequence on
+its own env shard; the per-update exchanges (advantage moment sums, flat gradient) run inside the
+update kernels over peer memory (stores into every rank's comm buffer + per-block epoch flags), or
+as two NCCL all-reduces per update when peer access is unavailable (B200PPO_P2P=0); one all-gather
+per iteration merges the Normalizer batch statistics.
 """
 from __future__ import annotations
 
@@ -51,6 +55,29 @@ class AdamOptimizer:
 
 _SIDE_STREAMS: dict = {}
 
+MAX_CACHED_ENGINES = 4
+
+
+def cached_engine(net: CompiledNet, kind: str, env, opt, shape_key: tuple, factory):
+    """Engine cache of one compiled network, keyed on SHAPES and launch structure only (hyper-parameter
+    values are run-time data, `PPOEngine.set_hparams`).  An entry keeps strong references to the env
+    and optimizer objects it was built for, so their ids cannot be recycled while it is cached, and
+    identity is re-checked on every hit.  Least-recently-used engines beyond MAX_CACHED_ENGINES are
+    closed (peer buffers unmapped) and dropped together with their ~100 MB workspaces."""
+    key = (kind, id(env), id(opt)) + tuple(shape_key)
+    eng = net.engines.pop(key, None)
+    if eng is not None and not (eng._key_refs[0] is env and eng._key_refs[1] is opt):
+        eng.close()
+        eng = None
+    if eng is None:
+        eng = factory()
+        eng._key_refs = (env, opt)
+    net.engines[key] = eng                       # (re)inserted last = most recently used
+    while len(net.engines) > MAX_CACHED_ENGINES:
+        old_key = next(iter(net.engines))
+        net.engines.pop(old_key).close()
+    return eng
+
 
 def _side_stream(dev):
     """One side stream per device, shared by every engine.  torch hands out streams round-robin from
@@ -68,6 +95,8 @@ def _side_stream(dev):
 
 
 class PPOEngine:
+    N_SLOTS = 8
+
     def __init__(self, net: CompiledNet, env, opt: AdamOptimizer, n_envs: int, rollout_length: int,
                  n_epochs: int, n_minibatches: int, gae_lambda: float, discounting_factor: float,
                  clip_range: float, normalize_advantages: bool, critic_loss_weight: float,
@@ -91,6 +120,8 @@ class PPOEngine:
         self.action = torch.zeros(T, B, A, **f32)
         self.loglik = torch.zeros(T, B, **f32)
         self.value = None            # [T, B] rollout-time value estimates: only with enable_values()
+        self.mu_sigma = None         # [T, B, 2A] rollout-time sampler mu | sigma: only with enable_values(net_metrics=True)
+        self.adv_log = None          # [updates, T * mb] raw advantages of every update: only with enable_adv_log()
         self.env_metrics: dict = {}  # Transition.metrics of the rollout (envs stepped from Python only)
         self.reward = torch.zeros(T, B, **f32)
         self.done = torch.zeros(T, B, dtype=torch.uint8, device=dev)
@@ -107,8 +138,16 @@ class PPOEngine:
         self.n_updates = self.E * self.M
         self.metrics = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, **f32)
         self.metrics_host = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, dtype=torch.float32).pin_memory()
-        self.iter_keys = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.iter_keys_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        # per-iteration host -> device block: int32[4] keys | float32[HP_FLOATS] hyper-parameters.  A ring
+        # of pinned slots with one event each: a slot is rewritten only after the copy that read it has
+        # executed, so the host may run many iterations ahead of the GPU (fetch_metrics=False).
+        self.iter_block = torch.zeros(4 + _lib.HP_FLOATS, dtype=torch.int32, device=dev)
+        self.iter_keys = self.iter_block[:4]
+        self.hp_dev = self.iter_block[4:].view(torch.float32)
+        self._slots = [torch.zeros(4 + _lib.HP_FLOATS, dtype=torch.int32).pin_memory() for _ in range(self.N_SLOTS)]
+        self._slot_events = [None] * self.N_SLOTS
+        self._slot = 0
+        self.comm_epoch = torch.zeros(1, dtype=torch.int32, device=dev)   # monotonic exchange epoch (never rolled back)
         self.norm_scratch = torch.zeros(int(self.lib.b200ppo_norm_scratch_bytes(O)) // 4 + 64, **f32)
         self.batch_stats = torch.zeros(2 * O, **f32)
         self.batch_stats_all = torch.zeros(self.world, 2 * O, **f32)
@@ -141,7 +180,12 @@ class PPOEngine:
             b.ws = wsp
             pm = getattr(net, "param_mask", None)
             b.param_mask = pm.data_ptr() if pm is not None else 0
+            b.hparams_dev = self.hp_dev.data_ptr()
+            b.comm_epoch = self.comm_epoch.data_ptr()
             self.bufs.append(b)
+        self._hp_host = np.zeros(_lib.HP_FLOATS, np.float32)
+        self.set_hparams()
+        self._upload_block((0, 0), (0, 0))
         self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory
         # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
@@ -149,7 +193,7 @@ class PPOEngine:
         self._side = _side_stream(dev)
         self.p2p = False
         self._comm_local, self._comm_peers, self.comm_table = None, [], None
-        if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0" and not self.hp.grad_clip > 0.0:
+        if self.world > 1 and os.environ.get("B200PPO_P2P", "1") != "0":
             self._setup_p2p_collective()
         if use_graph is None:
             use_graph = os.environ.get("B200PPO_GRAPH", "1") != "0"
@@ -158,8 +202,51 @@ class PPOEngine:
         self.iters_run = 0
         self.kernel_launches_per_iter = 0
         self._env_state = None
+        self._rng_mirror = None
 
     # ------------------------------------------------------------------------------------
+    def set_hparams(self, gae_lambda=None, discounting_factor=None, clip_range=None, critic_loss_weight=None):
+        """Refresh the host copy of the device hyper-parameter block from the arguments (None: keep)
+        and from the optimizer (learning rate, Adam constants, decay / clip VALUES: a schedule just
+        assigns ``opt.learning_rate``).  Whether decay / clipping exist at all is launch structure and
+        is fixed when the engine is built.  The block reaches the device with the next step()."""
+        hp, opt, h = self.hp, self.opt, self._hp_host
+        if gae_lambda is not None:
+            hp.lambda_ = float(gae_lambda)
+        if discounting_factor is not None:
+            hp.gamma = float(discounting_factor)
+        if clip_range is not None:
+            hp.clip_range = float(clip_range)
+        if critic_loss_weight is not None:
+            hp.critic_loss_weight = float(critic_loss_weight)
+        hp.learning_rate = float(opt.learning_rate)
+        hp.adam_b1, hp.adam_b2, hp.adam_eps = opt.b1, opt.b2, opt.eps
+        if hp.weight_decay >= 0.0 and opt.wd_value >= 0.0:
+            hp.weight_decay = opt.wd_value
+        if hp.grad_clip > 0.0 and opt.gradient_clipping is not None:
+            hp.grad_clip = float(opt.gradient_clipping)
+        h[_lib.HP_GAMMA], h[_lib.HP_LAMBDA] = hp.gamma, hp.lambda_
+        h[_lib.HP_CLIP_RANGE], h[_lib.HP_CRITIC_WEIGHT] = hp.clip_range, hp.critic_loss_weight
+        h[_lib.HP_LEARNING_RATE] = hp.learning_rate
+        h[_lib.HP_ADAM_B1], h[_lib.HP_ADAM_B2], h[_lib.HP_ADAM_EPS] = hp.adam_b1, hp.adam_b2, hp.adam_eps
+        h[_lib.HP_WEIGHT_DECAY], h[_lib.HP_GRAD_CLIP] = hp.weight_decay, hp.grad_clip
+
+    def _upload_block(self, reset_key, new_key) -> None:
+        """Write (keys, hyper-parameters) into the next pinned slot and queue its copy to the device."""
+        import torch
+        i = self._slot
+        self._slot = (i + 1) % self.N_SLOTS
+        ev = self._slot_events[i]
+        if ev is not None:
+            ev.synchronize()                       # the copy that last read this slot has executed
+        host = self._slots[i].numpy()
+        host[:4] = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
+        host[4:] = self._hp_host.view(np.int32)
+        self.iter_block.copy_(self._slots[i], non_blocking=True)
+        if ev is None:
+            ev = self._slot_events[i] = torch.cuda.Event()
+        ev.record()
+
     def _setup_p2p_collective(self):
         """Allocate this rank's comm buffer, exchange CUDA IPC handles, map every peer's buffer
         (include/b200ppo.h, 'peer-memory exchange').  Every rank executes the same collectives whatever
@@ -277,30 +364,46 @@ class PPOEngine:
             self.trunc.data_ptr(), self.next_obs_last.data_ptr()), "rollout_synth"); n += 1
         return n
 
-    def enable_values(self) -> None:
-        """Also evaluate the critic on the rollout's observations with the rollout-time parameters
-        (``Transition.network_output.value_estimates``; logged as losses/predicted_value at
-        LoggingLevel.CRITIC_EXTRA, metrics.py:62-68).  The training math never reads them
-        (ppo.py:425-446 replays the critic), so the pass is off unless asked for."""
+    def enable_values(self, net_metrics: bool = False) -> None:
+        """Also evaluate the network on the rollout's observations with the rollout-time parameters, for
+        logging: ``Transition.network_output.value_estimates`` (losses/predicted_value at
+        LoggingLevel.CRITIC_EXTRA, metrics.py:62-68) and, with ``net_metrics``, the sampler's mu / sigma
+        (``Transition.metrics["net"]``, sampling_layers.py:111, logged at TRAINING_ENV_METRICS).  The
+        training math never reads either (ppo.py:425-446 replays the network), so the pass is off unless
+        asked for."""
         import torch
-        if self.value is not None:
-            return
         T, B, A = self.T, self.B, self.net.plan.act_dim
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.value = torch.zeros(T, B, **f32)
-        self._val_scratch = (torch.empty(T * B, A, **f32), torch.empty(T * B, A, **f32), torch.empty(T * B, **f32))
-        self.graph = None            # the captured iteration does not contain the pass: capture again
+        if self.value is None:
+            self.value = torch.zeros(T, B, **f32)
+            self._val_scratch = (torch.empty(T * B, A, **f32), torch.empty(T * B, A, **f32), torch.empty(T * B, **f32))
+            self.graph = None        # the captured iteration does not contain the pass: capture again
+        if net_metrics and self.mu_sigma is None:
+            self.mu_sigma = torch.zeros(T, B, 2 * A, **f32)
+            self.graph = None
+
+    def enable_adv_log(self) -> None:
+        """Keep every update's advantage tensor (``losses/advantages`` is the [updates, T, mb] array in the
+        reference, ppo.py:523): needed only when percentiles of it are logged; mean / std come from the
+        sums the loss kernel accumulates anyway."""
+        import torch
+        if self.adv_log is None:
+            self.adv_log = torch.zeros(self.n_updates, self.T * self.mb, dtype=torch.float32, device=self.dev)
+            wsp = self.ws.data_ptr()
+            ap = ctypes.cast(self.lib.b200ppo_update_debug_ptr(self.net.plan, self.T, self.mb, wsp, 0), ctypes.c_void_p).value
+            o = (ap - wsp) // 4
+            self._adv_view = self.ws[o:o + self.T * self.mb]
+            self.graph = None
 
     def enable_grad_norm(self) -> bool:
         """LoggingLevel.GRAD_NORM without gradient clipping (ppo.py:313-315): run the global-norm
         kernel with a clip threshold no finite norm reaches, so metrics[3] is written and the
-        gradient is used unscaled.  Not available on the peer-memory exchange path (its fused
-        reduce + Adam launch has no place for the norm): returns False there."""
+        gradient is used unscaled (on the peer-memory path too: the norm is taken from the rank-ordered
+        sum inside the exchange launch)."""
         if self.hp.grad_clip > 0.0:
             return True
-        if self.p2p:
-            return False
         self.hp.grad_clip = float(np.finfo(np.float32).max)
+        self.set_hparams()
         self.graph = None
         return True
 
@@ -312,7 +415,8 @@ class PPOEngine:
         _lib.check(self.lib.b200ppo_policy_step(
             _lib.current_stream(), net.plan, net.arena.data_ptr(), mean_p, std_p, self.obs.data_ptr(),
             self.T * self.B, 1, net.counters.data_ptr(), 0, self.raw_action.data_ptr(), raw.data_ptr(),
-            act.data_ptr(), ll.data_ptr(), self.value.data_ptr(), 0, 0), "policy_step(values)")
+            act.data_ptr(), ll.data_ptr(), self.value.data_ptr(), 0,
+            self.mu_sigma.data_ptr() if self.mu_sigma is not None else 0), "policy_step(values)")
         return 1
 
     def _enqueue_permutation(self) -> int:
@@ -349,18 +453,28 @@ class PPOEngine:
             # of an iteration (parameters may have been touched from outside) runs the prep launch
             noprep = _lib.STAGE_NO_PREP if (u > 0 and self.fuse_prep) else 0
             per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, _lib.STAGE_ALL | noprep))
-            if self.world == 1 or self.p2p:
+            if (self.world == 1 or self.p2p) and self.adv_log is not None:
+                head = _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS
+                _lib.check(lib.b200ppo_update(*args, head | noprep), "update/loss")
+                self.adv_log[u].copy_(self._adv_view)
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL & ~head), "update/bwd")
+            elif self.world == 1 or self.p2p:
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL | noprep), "update")
-                n += 1 if self.p2p else 0       # the partial reduction is its own launch on this path
             else:
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE | noprep), "update/fwd")
                 if self.hp.normalize_advantages:
                     self._allreduce(self.adv_sums)
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")
+                if self.adv_log is not None:
+                    self.adv_log[u].copy_(self._adv_view)
                 self._allreduce(self.grad)
                 _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ADAM), "update/adam")
             n += per_update
         if self.world > 1:
+            # every column is pre-divided by the GLOBAL sample count (SUM = global mean) except the gradient
+            # norm [3], which is computed from the already summed gradient and identical on every rank
+            if self.hp.grad_clip > 0.0 and parallel.dist_info()[1] != 0:
+                self.metrics[:, 3].zero_()
             self._allreduce(self.metrics)
         if net.normalizer is not None:
             nz = net.normalizer
@@ -375,31 +489,40 @@ class PPOEngine:
             _lib.check(lib.b200ppo_norm_merge(s, src.data_ptr(), self.world, float(T * B), nz.size,
                                               nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),
                                               nz.counter._dev.data_ptr()), "norm_merge"); n += 1
-        _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), rng_advance, self.n_updates),
-                   "iter_finalize"); n += 1
+        _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), rng_advance, self.n_updates,
+                                             self.comm_epoch.data_ptr()), "iter_finalize"); n += 1
         return n
+
+    @property
+    def env_state(self):
+        """The env state the engine advances in place (the object the captured graph points at)."""
+        return self._env_state
 
     def step(self, env_state, reset_key, new_key, fetch_metrics: bool = True):
         """Run one iteration.  ``reset_key, new_key = split(rng_key)`` (ppo.py:271) come from the
-        host; everything else stays on the device.  Asynchronous unless ``fetch_metrics``."""
+        host; everything else stays on the device.  Asynchronous unless ``fetch_metrics``.  The env
+        state is advanced IN PLACE in engine-owned tensors (``self.env_state``): the first state passed
+        in is adopted, a different object passed later (a loaded checkpoint, a rolled-back
+        TrainingState) is copied over the live one."""
         import torch
-        k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
-        self.iter_keys_host.numpy()[:] = k
-        self.iter_keys.copy_(self.iter_keys_host, non_blocking=True)
-        if self._env_state is not None and env_state is not self._env_state and self.graph is not None:
-            # a different env-state object: the captured graph points at the old tensors
+        self._upload_block(reset_key, new_key)
+        if self._env_state is None:
+            self._env_state = env_state
+        elif env_state is not self._env_state:
             self._env_state.obs.copy_(env_state.obs)
             self._env_state.step_counter.copy_(env_state.step_counter)
             self._env_state.term_state.copy_(env_state.term_state)
-            env_state = self._env_state
-        if self.iters_run == 0:
+        env_state = self._env_state
+        if self.iters_run == 0 or self.net.adam_step != self.opt.step or self._rng_mirror != self.net.rng_count:
+            # first use, or the optimizer / sampler counters were changed from outside (checkpoint load,
+            # rollback): bring the device counters in line.  The exchange epoch is NOT touched: it only
+            # ever moves forward, so flags left by earlier iterations can never look current.
             self.net.adam_step = self.opt.step
             self.net.sync_counters_to_device()
         if not self.use_graph or self.iters_run == 0:
             self.kernel_launches_per_iter = self._enqueue(env_state)
         else:
             if self.graph is None:
-                self._env_state = env_state
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue(env_state)
@@ -407,6 +530,7 @@ class PPOEngine:
             self.graph.replay()
         self.iters_run += 1
         self.net.advance_rng(self.rng_per_iter)
+        self._rng_mirror = self.net.rng_count
         self.opt.step += self.n_updates
         self.net.adam_step = self.opt.step
         if fetch_metrics:
@@ -416,7 +540,7 @@ class PPOEngine:
         return None
 
     def h2d_bytes_per_step(self) -> int:
-        return 16
+        return 4 * (4 + _lib.HP_FLOATS)
 
     def d2h_bytes_per_step(self) -> int:
         return self.n_updates * 4 * _lib.METRICS_STRIDE

@@ -16,7 +16,7 @@ from ..networks.plan import compile_network
 from ..networks.types import StatefulModule
 from . import rollout
 from .config import EvalConfig, PPOConfig, TrainConfig, TrainResult, VideoConfig, VideoData  # noqa: F401
-from .engine import AdamOptimizer, PPOEngine
+from .engine import AdamOptimizer, PPOEngine, cached_engine
 from .types import LoggingLevel, RLEnv, TrainingState
 
 
@@ -56,18 +56,18 @@ def new_training_state(env: RLEnv, networks: StatefulModule, n_envs: int, seed: 
 def _engine_for(env, training_state: TrainingState, n_envs, rollout_length, gae_lambda,
                 discounting_factor, clip_range, normalize_advantages, n_epochs, n_minibatches,
                 critic_loss_weight) -> PPOEngine:
+    """The engine for these SHAPES (cached per network, LRU); gamma / lambda / clip range / critic
+    weight / learning rate are run-time data of the captured iteration, refreshed here on every call
+    (the reference traces gae_lambda / discounting_factor, ppo.py:105)."""
     net = compile_network(training_state.networks)
     opt: AdamOptimizer = training_state.optimizer
     world, group = _dist_info()
-    key = (id(env), id(opt), n_envs, rollout_length, float(gae_lambda), float(discounting_factor),
-           float(clip_range), bool(normalize_advantages), n_epochs, n_minibatches,
-           float(critic_loss_weight), opt.learning_rate, opt.gradient_clipping, opt.wd_value, world)
-    eng = net.engines.get(key)
-    if eng is None:
-        eng = PPOEngine(net, env, opt, n_envs, rollout_length, n_epochs, n_minibatches, gae_lambda,
-                        discounting_factor, clip_range, normalize_advantages, critic_loss_weight,
-                        world_size=world, group=group)
-        net.engines[key] = eng
+    shape_key = (n_envs, rollout_length, n_epochs, n_minibatches, bool(normalize_advantages),
+                 opt.gradient_clipping is not None, opt.wd_value >= 0.0, world)
+    eng = cached_engine(net, "fused", env, opt, shape_key, lambda: PPOEngine(
+        net, env, opt, n_envs, rollout_length, n_epochs, n_minibatches, gae_lambda, discounting_factor,
+        clip_range, normalize_advantages, critic_loss_weight, world_size=world, group=group))
+    eng.set_hparams(gae_lambda, discounting_factor, clip_range, critic_loss_weight)
     return eng
 
 
@@ -95,6 +95,10 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
                       clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight)
     if LoggingLevel.CRITIC_EXTRA in logging_level:
         eng.enable_values()
+        if logging_percentiles:
+            eng.enable_adv_log()
+    if LoggingLevel.TRAINING_ENV_METRICS in logging_level:
+        eng.enable_values(net_metrics=True)
     if LoggingLevel.GRAD_NORM in logging_level:
         eng.enable_grad_norm()
     reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
@@ -102,7 +106,9 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
     metrics = _iteration_metrics(per_update, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps                                 # ppo.py:333
-    new_state = training_state.replace(rng_key=new_key, steps_taken=total_steps)
+    # the engine advances ITS env-state tensors in place: hand those back, so that the caller's next
+    # TrainingState points at the live state whatever object came in (ppo.py:341-346)
+    new_state = training_state.replace(env_states=eng.env_state, rng_key=new_key, steps_taken=total_steps)
     return new_state, metrics
 
 
@@ -110,11 +116,23 @@ def _iteration_metrics(per_update: np.ndarray, eng, logging_level, percentiles) 
     """compute_metrics + the grad-norm / weight extras of ppo_step (ppo.py:313-315,329-335) from the
     per-update metric rows and the engine's rollout buffers; shared by the fused, per-step and
     recurrent paths."""
-    metrics = _loss_metrics(per_update, logging_level, percentiles)
+    metrics = _loss_metrics(per_update, logging_level, percentiles, getattr(eng, "adv_log", None))
     if LoggingLevel.GRAD_NORM in logging_level and eng.hp.grad_clip > 0.0:
-        metrics["grad_norm"] = per_update[:, 3].copy()                   # one value per update
+        # loss_metrics["grad_norm"] is one scalar per update and goes through _log_metric like every
+        # other loss metric (ppo.py:313-315, metrics.py:36-37): grad_norm/mean, /std or /pN
+        _log_np(metrics, "grad_norm", per_update[:, 3], percentiles)
     _extra_metrics(metrics, eng.net, eng, logging_level, percentiles)
     return metrics
+
+
+def _log_np(m: dict, name: str, x: np.ndarray, percentiles) -> None:
+    """metrics.py:72-100 on a host array."""
+    if percentiles:
+        for pl, p in zip(percentiles, np.percentile(x, percentiles)):
+            m[f"{name}/p{int(pl)}"] = np.float32(p)
+    else:
+        m[f"{name}/mean"] = x.mean(dtype=np.float32)
+        m[f"{name}/std"] = x.std(dtype=np.float32)
 
 
 def _log_metric(m: dict, name: str, x, percentiles) -> None:
@@ -148,11 +166,16 @@ def _log_tree(m: dict, name: str, x, percentiles) -> None:
 def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
     """The parts of metrics.compute_metrics / log_weight_stats (metrics.py:17-121) that only need the
     rollout buffers and the parameter arena.  ROLLOUT_OBS logs nothing in the reference either
-    (metrics.py:55-56).  Not produced by this build: percentiles of losses/advantages (mean / std
-    only) and the sampler's net/* mu / sigma arrays."""
+    (metrics.py:55-56)."""
     if LoggingLevel.TRAINING_ENV_METRICS in logging_level:                # metrics.py:38-40
         for k, v in getattr(eng, "env_metrics", {}).items():
             _log_tree(m, k, v, percentiles)
+        ms = getattr(eng, "mu_sigma", None)                               # Transition.metrics["net"], rollout.py:31-34
+        if ms is not None:
+            A = ms.shape[-1] // 2
+            base = net.sampler_metric_path()
+            _log_metric(m, f"{base}/mu", ms[..., :A], percentiles)
+            _log_metric(m, f"{base}/sigma", ms[..., A:], percentiles)
     if LoggingLevel.TRAIN_ROLLOUT_STATS in logging_level:
         _log_metric(m, "rollout_batch/reward", eng.reward, percentiles)
         _log_metric(m, "rollout_batch/action", eng.action, percentiles)
@@ -163,41 +186,39 @@ def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
     if LoggingLevel.CRITIC_EXTRA in logging_level and getattr(eng, "value", None) is not None:
         _log_metric(m, "losses/predicted_value", eng.value, percentiles)  # metrics.py:62-68
     if LoggingLevel.WEIGHTS in logging_level:
-        w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask != 0]
+        # log_weight_stats (metrics.py:103-121): every nnx.Param leaf, i.e. the arena without its
+        # alignment padding and without the structural zeros of block-diagonal encoder layers
+        if hasattr(net, "logical_index_dev"):
+            w = net.arena[net.logical_index_dev()]
+        else:
+            w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask != 0]
         _log_metric(m, "weights", w, percentiles)
 
 
-def _loss_metrics(per_update: np.ndarray, logging_level, percentiles) -> dict[str, Any]:
+def _loss_metrics(per_update: np.ndarray, logging_level, percentiles, adv_log=None) -> dict[str, Any]:
     """metrics.py:17-100 for the ``losses/*`` keys (mean / std or percentiles over the updates)."""
     m: dict[str, Any] = {}
     if LoggingLevel.LOSSES in logging_level:
         for i, name in enumerate(("losses/actor", "losses/critic", "losses/regularization")):
-            x = per_update[:, i]
-            if percentiles:
-                for pl, p in zip(percentiles, np.percentile(x, percentiles)):
-                    m[f"{name}/p{int(pl)}"] = np.float32(p)
-            else:
-                m[f"{name}/mean"] = x.mean(dtype=np.float32)
-                m[f"{name}/std"] = x.std(dtype=np.float32)
-
-    def log(name, x):
-        if percentiles:
-            for pl, p in zip(percentiles, np.percentile(x, percentiles)):
-                m[f"{name}/p{int(pl)}"] = np.float32(p)
-        else:
-            m[f"{name}/mean"] = x.mean(dtype=np.float32)
-            m[f"{name}/std"] = x.std(dtype=np.float32)
-
+            _log_np(m, name, per_update[:, i], percentiles)
     if per_update.shape[1] > 8:
         if LoggingLevel.ACTOR_EXTRA in logging_level:                      # ppo.py:514-520
-            log("losses/clipping_fraction", per_update[:, 4])
+            _log_np(m, "losses/clipping_fraction", per_update[:, 4], percentiles)
         if LoggingLevel.CRITIC_EXTRA in logging_level:                     # ppo.py:522-527
             var_t = np.maximum(per_update[:, 6].astype(np.float64) - per_update[:, 5].astype(np.float64) ** 2, 0.0)
-            log("losses/critic_R^2", (1.0 - 2.0 * per_update[:, 1] / (var_t + 1e-8)).astype(np.float32))
-            # losses/advantages is the raw [updates, T, mb] array in the reference: mean / std over all of it
-            mean = per_update[:, 7].astype(np.float64).mean()
-            m["losses/advantages/mean"] = np.float32(mean)
-            m["losses/advantages/std"] = np.float32(np.sqrt(max(per_update[:, 8].astype(np.float64).mean() - mean * mean, 0.0)))
+            _log_np(m, "losses/critic_R^2", (1.0 - 2.0 * per_update[:, 1] / (var_t + 1e-8)).astype(np.float32), percentiles)
+            # losses/advantages is the [updates, T, mb] array of the advantages the surrogate used, i.e. the
+            # NORMALISED ones when normalize_advantages (ppo.py:477-480 reassigns the name before :523).
+            # Columns 7 / 8 hold E[a] / E[a^2] of exactly that tensor per update.
+            if percentiles and adv_log is not None:
+                import torch
+                mean = torch.from_numpy(per_update[:, 9].copy()).to(adv_log.device)[:, None]
+                den = torch.from_numpy(per_update[:, 10].copy()).to(adv_log.device)[:, None]
+                _log_metric(m, "losses/advantages", (adv_log - mean) / den, percentiles)
+            elif not percentiles:
+                mean = per_update[:, 7].astype(np.float64).mean()
+                m["losses/advantages/mean"] = np.float32(mean)
+                m["losses/advantages/std"] = np.float32(np.sqrt(max(per_update[:, 8].astype(np.float64).mean() - mean * mean, 0.0)))
     return m
 
 
@@ -217,6 +238,79 @@ def gae(rewards, values_excl_last, last_value, done, truncation, lambda_, gamma)
     _lib.check(lib.b200ppo_gae(_lib.current_stream(), _lib.ptr(r), _lib.ptr(v), _lib.ptr(lv), _lib.ptr(d),
                                _lib.ptr(tr), T, B, float(lambda_), float(gamma), _lib.ptr(out)), "gae")
     return out
+
+
+def ppo_loss(networks: StatefulModule, network_state: Any, rollout_data, clip_range, normalize_advantages: bool,
+             combine_advantages: bool, discounting_factor, gae_lambda, critic_loss_weight,
+             logging_level: LoggingLevel, *, return_grads: bool = False):
+    """ppo.py:397-531 as a callable: ``(total_loss, loss_metrics)`` of one minibatch ``Transition``
+    ([T, mb, ...] leaves, e.g. ``jax.tree.map(lambda x: x[:, inds], rollout_data)`` of ppo.py:297) under
+    the CURRENT parameters — stages FWD | GAE | LOSS of the update kernels (K3) on the rows in their
+    given order.  Like the reference call it advances the sampler stream by 2 * (T + 1) counts (one
+    network call per replayed step plus the bootstrap call, two draws each).  The reference
+    differentiates this function with ``nnx.grad``; here the analytic backward is part of the same
+    kernels: ``return_grads=True`` also runs BWD | RED and returns the flat gradient in the parameter
+    order of ``CompiledNet.params_logical`` as a third element."""
+    import torch
+    if combine_advantages:
+        raise NotImplementedError("combine_advantages needs dict rewards; single scalar reward only")
+    net = compile_network(networks)
+    if net.recurrent:
+        raise NotImplementedError("ppo_loss as a standalone callable supports the MLP plans; recurrent networks "
+                                  "are differentiated inside ppo_step")
+    lib = _lib.load()
+    T, mb = rollout_data.rewards.shape
+
+    def build():
+        eng = PPOEngine.__new__(PPOEngine)
+        fake_env = type("E", (), {"fused_rollout": True})()
+        PPOEngine.__init__(eng, net, fake_env, AdamOptimizer(net), mb, T, 1, 1, gae_lambda, discounting_factor,
+                           clip_range, normalize_advantages, critic_loss_weight, world_size=1, group=None,
+                           use_graph=False)
+        eng.inds.copy_(torch.arange(mb, dtype=torch.int32, device=net.device).reshape(1, mb))
+        return eng
+
+    eng = cached_engine(net, "loss", None, None, (T, mb, bool(normalize_advantages)), build)
+    eng.set_hparams(gae_lambda, discounting_factor, clip_range, critic_loss_weight)
+    eng._upload_block((0, 0), (0, 0))
+    obs = net.flat_obs(rollout_data.obs)
+    eng.obs.copy_(obs.reshape(T, mb, -1))
+    eng.raw_action.copy_(net.adapter_extras(rollout_data.rollout_extras)["action"][-1].reshape(T, mb, -1))
+    eng.loglik.copy_(rollout_data.network_output.loglikelihoods)
+    eng.reward.copy_(rollout_data.rewards)
+    eng.done.copy_(rollout_data.done.to(torch.uint8))
+    eng.trunc.copy_(rollout_data.truncated.to(torch.uint8))
+    nxt = net.flat_obs(rollout_data.next_obs)
+    eng.next_obs_last.copy_(nxt[-1] if nxt.dim() == 3 else nxt)           # ppo.py:433: only next_obs[-1] is read
+    s = _lib.current_stream()
+    if net.normalizer is not None:
+        net.normalizer.prepare(s)
+    net.sync_counters_to_device()
+    stages = _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS
+    if return_grads:
+        stages |= _lib.STAGE_BWD | _lib.STAGE_RED
+    _lib.check(lib.b200ppo_update(s, net.plan, eng.hp, eng.bufs[0], T, mb, mb, 0, 0, stages), "ppo_loss")
+    net.advance_rng(2 * (T + 1))
+    net.sync_counters_to_device()
+    row = eng.metrics[0].cpu().numpy()
+    total = np.float32(row[0] + np.float32(critic_loss_weight) * row[1] + row[2])   # ppo.py:529
+    loss_metrics: dict[str, Any] = {}
+    if LoggingLevel.LOSSES in logging_level:                                        # ppo.py:510-513
+        loss_metrics["losses/actor"] = np.float32(row[0])
+        loss_metrics["losses/critic"] = np.float32(row[1])
+        loss_metrics["losses/regularization"] = np.float32(row[2])
+    if LoggingLevel.ACTOR_EXTRA in logging_level:                                   # ppo.py:514-520
+        loss_metrics["losses/clipping_fraction"] = np.float32(row[4])
+    if LoggingLevel.CRITIC_EXTRA in logging_level:                                  # ppo.py:522-527
+        wsp = eng.ws.data_ptr()
+        o = (int(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 0)) - wsp) // 4
+        adv = eng.ws[o:o + T * mb].reshape(T, mb)
+        loss_metrics["losses/advantages"] = ((adv - float(row[9])) / float(row[10])).clone()
+        var_t = max(float(row[6]) - float(row[5]) ** 2, 0.0)
+        loss_metrics["losses/critic_R^2"] = np.float32(1.0 - 2.0 * float(row[1]) / (var_t + 1e-8))
+    if return_grads:
+        return total, loss_metrics, net.params_logical(eng.grad)
+    return total, loss_metrics
 
 
 def train_ppo(env: RLEnv, networks: StatefulModule, config: Optional[TrainConfig] = None, *,

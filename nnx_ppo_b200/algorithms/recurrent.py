@@ -21,10 +21,17 @@ from .types import LoggingLevel
 def _engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     from .engine import PPOEngine
     import torch
-    key = ("recurrent", id(opt), n_envs, T, E, M, float(lam), float(gamma), float(clip), bool(norm_adv), float(cw))
-    eng = net.engines.get(key)
-    if eng is not None:
-        return eng
+    from .engine import cached_engine
+    shape_key = (n_envs, T, E, M, bool(norm_adv), opt.gradient_clipping is not None, opt.wd_value >= 0.0)
+    eng = cached_engine(net, "recurrent", None, opt, shape_key,
+                        lambda: _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw))
+    eng.set_hparams(lam, gamma, clip, cw)
+    return eng
+
+
+def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
+    from .engine import PPOEngine
+    import torch
     eng = PPOEngine.__new__(PPOEngine)
     fake_env = type("E", (), {"fused_rollout": True})()
     PPOEngine.__init__(eng, net, fake_env, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw,
@@ -47,7 +54,6 @@ def _engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     eng.r_y_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 2), C.c_void_p).value)
     eng.r_dy_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 3), C.c_void_p).value)
     eng.r_grad_ptr = int(C.cast(lib.b200ppo_update_grad_ptr(net.plan, T, mb, wsp), C.c_void_p).value)
-    net.engines[key] = eng
     return eng
 
 
@@ -109,8 +115,7 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         eng.value = policy_values(net, eng.obs.reshape(T * B, -1)).reshape(T, B)
 
     # ---------------- E x M minibatch updates (ppo.py:284-328)
-    k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
-    eng.iter_keys.copy_(torch.from_numpy(k.copy()))
+    eng._upload_block(reset_key, new_key)
     _lib.check(lib.b200ppo_permutation(s, eng.iter_keys.data_ptr() + 8, B, eng.E, eng.inds.data_ptr(),
                                        eng.perm_scratch.data_ptr()), "permutation")
     inds_flat = eng.inds.view(-1)
@@ -154,7 +159,8 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
                                           nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),
                                           nz.counter._dev.data_ptr()), "norm_merge")
     adv = 2 * T + eng.n_updates * 2 * (T + 1)
-    _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), adv, eng.n_updates), "iter_finalize")
+    _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), adv, eng.n_updates, eng.comm_epoch.data_ptr()),
+               "iter_finalize")
     net.advance_rng(adv)
     opt.step += eng.n_updates
     net.adam_step = opt.step

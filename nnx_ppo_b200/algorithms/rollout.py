@@ -145,6 +145,7 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
     keys_all = split_keys_device(reset_key, T * B, dev).reshape(T, B, 2)
     rec = {k: [] for k in ("obs", "raw", "act", "ll", "val", "rew", "done", "trunc")}
     env_metrics: list = []
+    net_metrics: list = []
     next_obs = None
     for t in range(T):
         out = call_network(networks, network_state, env_state.obs)
@@ -162,16 +163,18 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
         rec["ll"].append(po.loglikelihoods); rec["val"].append(po.value_estimates)
         rec["rew"].append(nxt.reward.float()); rec["done"].append(done); rec["trunc"].append(tr.bool())
         env_metrics.append(nxt.metrics if isinstance(getattr(nxt, "metrics", None), dict) else {})
+        net_metrics.append(out.metrics if isinstance(out.metrics, dict) else {})
         next_obs = net.flat_obs(nxt.obs) if t == T - 1 else None
         reset_states = env.reset(keys_all[t].contiguous())
         env_state = tree_where(done, reset_states, nxt)
     st = {k: torch.stack(v) for k, v in rec.items()}
-    # Transition.metrics["env"] (rollout.py:31-34), stacked over time; "net" (the sampler's mu / sigma)
-    # is not recorded by this build
+    # Transition.metrics = {"env": ..., "net": ...} (rollout.py:31-34), stacked over time
     stacked_env = _stack_tree(env_metrics, dev) if env_metrics else {}
+    stacked_net = _stack_tree(net_metrics, dev) if net_metrics else {}
     tr = Transition(obs=st["obs"], network_output=PPONetworkOutput(st["act"], st["ll"], st["val"]),
                     rewards=st["rew"], done=st["done"], truncated=st["trunc"], next_obs=next_obs,
-                    metrics={"env": stacked_env}, rollout_extras=_extras(net, st["obs"], st["raw"]))
+                    metrics={"env": stacked_env, "net": stacked_net},
+                    rollout_extras=_extras(net, st["obs"], st["raw"]))
     return network_state, env_state, tr
 
 
@@ -185,16 +188,22 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
     net = compile_network(training_state.networks)
     opt = training_state.optimizer
     world, group = _ppo._dist_info()
-    key = ("generic", id(env), id(opt), n_envs, rollout_length, float(gae_lambda), float(discounting_factor),
-           float(clip_range), bool(normalize_advantages), n_epochs, n_minibatches, float(critic_loss_weight))
-    eng = net.engines.get(key)
-    if eng is None:
+
+    def build():
         eng = PPOEngine.__new__(PPOEngine)
         _FakeEnv = type("E", (), {"fused_rollout": True})
         PPOEngine.__init__(eng, net, _FakeEnv(), opt, n_envs, rollout_length, n_epochs, n_minibatches,
                            gae_lambda, discounting_factor, clip_range, normalize_advantages,
                            critic_loss_weight, world_size=world, group=group, use_graph=False)
-        net.engines[key] = eng
+        return eng
+
+    from .engine import cached_engine
+    shape_key = (n_envs, rollout_length, n_epochs, n_minibatches, bool(normalize_advantages),
+                 opt.gradient_clipping is not None, opt.wd_value >= 0.0, world)
+    eng = cached_engine(net, "generic", env, opt, shape_key, build)
+    eng.set_hparams(gae_lambda, discounting_factor, clip_range, critic_loss_weight)
+    if _ppo.LoggingLevel.CRITIC_EXTRA in logging_level and logging_percentiles:
+        eng.enable_adv_log()
     if _ppo.LoggingLevel.GRAD_NORM in logging_level:
         eng.enable_grad_norm()
     reset_key, new_key = prng.split(training_state.rng_key)
@@ -207,8 +216,7 @@ def ppo_step_generic(env, training_state, n_envs, rollout_length, gae_lambda, di
     eng.env_metrics = tr.metrics
     eng.done.copy_(tr.done.to(torch.uint8)); eng.trunc.copy_(tr.truncated.to(torch.uint8))
     eng.next_obs_last.copy_(tr.next_obs)
-    k = np.array([reset_key[0], reset_key[1], new_key[0], new_key[1]], np.uint32).view(np.int32)
-    eng.iter_keys.copy_(torch.from_numpy(k.copy()))
+    eng._upload_block(reset_key, new_key)
     net.adam_step = opt.step
     net.sync_counters_to_device()
     if net.normalizer is not None:

@@ -16,6 +16,37 @@
 namespace b200ppo {
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL) between the kernels of one update.  A kernel launched with the
+// programmatic-stream-serialization attribute may start while its predecessor in the stream is still
+// draining: its CTAs become resident, run their prologue (shared-memory / TMEM / mbarrier set-up) and
+// block in griddepcontrol.wait until the predecessor grid has completed and flushed.  Every kernel of
+// the chain executes launch_dependents first (so ITS successor can be scheduled as soon as all its own
+// CTAs are resident) and wait before its first dependent global access; completion stays transitive
+// because every grid waits.  Without the attribute both instructions are no-ops.  B200PPO_PDL=0 turns
+// the attribute off (plain stream order) for A/B timing.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // misc.cu (reads B200PPO_PDL once)
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // threefry2x32 (20 rounds) — jax/_src/prng.py; reference call sites ppo.py:271,288-289,
 // rollout.py:57-59, sampling_layers.py:96,144.  Bit-exact integer work.
 // ------------------------------------------------------------------------------------------

@@ -4,7 +4,24 @@
 
 using namespace b200ppo;
 
+#include <cstdlib>
+
 static int g_num_sms = 0;
+static int g_pdl = -1;
+
+bool b200ppo::pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = std::getenv("B200PPO_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
+extern "C" int b200ppo_set_pdl(int on) {
+  const int prev = b200ppo::pdl_enabled() ? 1 : 0;
+  if (on == 0 || on == 1) g_pdl = on;
+  return prev;
+}
 
 extern "C" int b200ppo_version(void) { return 100; }
 
@@ -372,14 +389,17 @@ extern "C" int b200ppo_norm_merge(void* stream, const float* batch_stats, int32_
 // ------------------------------------------------------------------------------------------
 // iteration bookkeeping
 // ------------------------------------------------------------------------------------------
-__global__ void iter_finalize_kernel(uint32_t* rng_state, uint32_t rng_adv, uint32_t adam_adv) {
+__global__ void iter_finalize_kernel(uint32_t* rng_state, uint32_t rng_adv, uint32_t adam_adv,
+                                     uint32_t* comm_epoch) {
   rng_state[2] += rng_adv;
   rng_state[3] += adam_adv;
+  if (comm_epoch != nullptr) *comm_epoch += adam_adv;
 }
 extern "C" int b200ppo_iter_finalize(void* stream, uint32_t* rng_state, uint32_t rng_advance,
-                                     uint32_t adam_advance) {
+                                     uint32_t adam_advance, uint32_t* comm_epoch) {
   if (!rng_state) return B200PPO_EINVAL;
-  iter_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(rng_state, rng_advance, adam_advance);
+  iter_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(rng_state, rng_advance, adam_advance,
+                                                                       comm_epoch);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

@@ -539,6 +539,7 @@ struct PolicyArgs {
   const uint32_t* rng_state; uint32_t count_offset;
   const float* raw_in;
   float* raw; float* action; float* loglik; float* value; float* reg;
+  float* musig;              // nullable: [B][2A] = [mu | sigma], the sampler's `metrics` (sampling_layers.py:111)
 };
 
 __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) {
@@ -579,6 +580,10 @@ __global__ void __launch_bounds__(NT, 1) policy_step_kernel(const PolicyArgs a) 
                                         k_ent, j, want_reg);
       a.raw[static_cast<size_t>(row) * A + d] = s.raw;
       a.action[static_cast<size_t>(row) * A + d] = s.action;
+      if (a.musig != nullptr) {
+        a.musig[static_cast<size_t>(row) * 2 * A + d] = y[e * ld + d];
+        a.musig[static_cast<size_t>(row) * 2 * A + A + d] = (softplus_f(y[e * ld + A + d]) + a.plan.min_std) * a.plan.std_scale;
+      }
       llt_s[i] = s.llterm;
       reg_s[i] = s.regterm;
     } else {
@@ -809,8 +814,8 @@ extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const 
 }
 
 extern "C" int64_t b200ppo_policy_workspace_bytes(const b200ppo_plan* plan, int32_t B) {
-  (void)plan; (void)B;
-  return 256;  // the policy step keeps everything in shared memory
+  if (check_plan(plan) || B < 0) return B200PPO_EINVAL;
+  return 8ll * plan->act_dim * B;   // the optional [B][2A] mu / sigma output; everything else lives in shared memory
 }
 
 extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const float* params,
@@ -818,7 +823,6 @@ extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const
                                    int32_t B, int32_t mode, const uint32_t* rng_state,
                                    uint32_t count_offset, const float* raw_action_in, float* raw_action,
                                    float* action, float* loglik, float* value, float* reg_loss, void* ws) {
-  (void)ws;
   int rc = check_plan(plan);
   if (rc) return rc;
   if (B < 0) return B200PPO_EINVAL;
@@ -830,6 +834,7 @@ extern "C" int b200ppo_policy_step(void* stream, const b200ppo_plan* plan, const
   a.plan = *plan; a.params = params; a.mean = norm_mean; a.std = norm_std; a.obs = obs;
   a.B = B; a.mode = mode; a.rng_state = rng_state; a.count_offset = count_offset; a.raw_in = raw_action_in;
   a.raw = raw_action; a.action = action; a.loglik = loglik; a.value = value; a.reg = reg_loss;
+  a.musig = static_cast<float*>(ws);
   int md = max_dim(plan->actor);
   const int mc = max_dim(plan->critic);
   md = mc > md ? mc : md;

@@ -39,13 +39,14 @@ constexpr int DW_LD = DW_T + 4;
 constexpr int DW_SMEM = 4 * DW_R * DW_LD * 4;
 
 constexpr int MAXL = B200PPO_MAX_LAYERS;
-constexpr int MAX_PART_BLOCKS = 1024;   // GAE / grad-norm partial blocks
+constexpr int MAX_PART_BLOCKS = 1024;   // GAE partial blocks
+constexpr int MAX_NORM_BLOCKS = 16384;  // grad-norm partial blocks (one per 256 parameters: 4 M parameters)
 constexpr int MAX_LOSS_BLOCKS = 4096;   // loss partial blocks (R <= 524288 rows per update)
 constexpr int DBL_GAE_PART = 8;
 constexpr int DBL_LOSS_PART = DBL_GAE_PART + 2 * MAX_PART_BLOCKS;
 constexpr int NLQ = 6;                   // loss partial sums: actor, critic, reg, clipped count, sum target, sum target^2
 constexpr int DBL_GN_PART = DBL_LOSS_PART + NLQ * MAX_LOSS_BLOCKS;
-constexpr int DBL_TOTAL = DBL_GN_PART + MAX_PART_BLOCKS;
+constexpr int DBL_TOTAL = DBL_GN_PART + MAX_NORM_BLOCKS;
 
 // pre-split (hi / lo tf32) weight operands of one layer for the tensor-core path
 struct TcLayer {
@@ -167,10 +168,14 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
 // ------------------------------------------------------------------------------------------
 constexpr int MAXR = B200PPO_MAX_RANKS;
 constexpr size_t COMM_FLAG_ADV = 0;                       // uint32[MAXR], written by the peers
-constexpr size_t COMM_FLAG_GRAD = 64;                     // uint32[MAXR]
 constexpr size_t COMM_ADV = 128;                          // double[2 parity][MAXR][2]
-constexpr size_t COMM_GRAD = 1024;                        // float[2 parity][world][Ppad]: every rank PUSHES its gradient here
+constexpr size_t COMM_FLAG_BLK = 1024;                    // uint32[MAXR][nblk]: per source rank, per 256-parameter block
 inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n_params)); }
+inline int comm_nblk(int64_t n_params) { return static_cast<int>((cdiv(n_params, 256) + 63) & ~63); }
+// float[2 parity][world][Ppad]: every rank PUSHES its gradient here
+__host__ __device__ inline size_t comm_grad_off(int nblk) {
+  return COMM_FLAG_BLK + static_cast<size_t>(B200PPO_MAX_RANKS) * static_cast<size_t>(nblk) * sizeof(uint32_t);
+}
 
 struct PeerComm {
   const uint64_t* table;   // device: comm base of every rank (nullptr: exchange disabled)
@@ -402,6 +407,8 @@ __device__ __forceinline__ void chain_forward_tile(const b200ppo_chain& ch, cons
 
 __global__ void __launch_bounds__(NTH, 1) upd_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   float* As = smem;
   float* Bs = smem + KB * LDA;
   const int O = a.plan.obs_dim;
@@ -458,10 +465,18 @@ struct GaeArgs {
   float* ws; size_t v_off;
   int T, B, mb;
   float gamma, lambda_;
+  const float* hpd;          // device hyper-parameter block (nullable): overrides gamma / lambda_
   PeerComm comm;
   const uint32_t* rng_state;
+  const uint32_t* comm_epoch;
   int update_index;
 };
+
+// exchange epoch of this update: monotonic base (engine-owned counter, or the Adam count) + index + 1
+__device__ __forceinline__ uint32_t comm_epoch_of(const uint32_t* comm_epoch, const uint32_t* rng_state,
+                                                  int update_index) {
+  return (comm_epoch != nullptr ? *comm_epoch : rng_state[3]) + static_cast<uint32_t>(update_index) + 1u;
+}
 
 constexpr int GAE_THREADS = 64;
 constexpr int GAE_CHUNK = 32;  // a whole T = 32 rollout in one memory round trip
@@ -469,9 +484,13 @@ constexpr int GAE_CHUNK = 32;  // a whole T = 32 rollout in one memory round tri
 __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
   __shared__ double red[2][4];
   __shared__ bool is_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const float* v = a.ws + a.v_off;
   float* adv = a.ws + a.L.adv;
+  const float gamma = a.hpd ? a.hpd[B200PPO_HP_GAMMA] : a.gamma;
+  const float lambda_ = a.hpd ? a.hpd[B200PPO_HP_LAMBDA] : a.lambda_;
   double s1 = 0.0, s2 = 0.0;
   if (threadIdx.x < 4) { red[0][threadIdx.x] = 0.0; red[1][threadIdx.x] = 0.0; }
   if (j < a.mb) {
@@ -497,10 +516,10 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
         if (t >= 0) {
           const bool d = dd[i] != 0, tr = tt[i] != 0;
           const float nv = d ? 0.0f : next_val;
-          float ad = __fsub_rn(__fadd_rn(rr[i], __fmul_rn(a.gamma, nv)), vv[i]);
+          float ad = __fsub_rn(__fadd_rn(rr[i], __fmul_rn(gamma, nv)), vv[i]);
           ad = tr ? 0.0f : ad;
           const float nd = d ? 0.0f : 1.0f;
-          next_adv = __fadd_rn(ad, __fmul_rn(__fmul_rn(__fmul_rn(nd, a.gamma), a.lambda_), next_adv));
+          next_adv = __fadd_rn(ad, __fmul_rn(__fmul_rn(__fmul_rn(nd, gamma), lambda_), next_adv));
           adv[static_cast<size_t>(t) * a.mb + j] = next_adv;
           next_val = vv[i];
           s1 += next_adv;
@@ -534,7 +553,7 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
       dbl[0] = t1;   // adv_sums: a data-parallel caller all-reduces these two doubles
       dbl[1] = t2;
       if (a.comm.table != nullptr) {             // ... or every peer gets them through its comm buffer
-        const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
+        const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
         for (int r = 0; r < a.comm.world; ++r) {
           double* slot = reinterpret_cast<double*>(comm_base(a.comm, r) + COMM_ADV) +
                          ((epoch & 1u) * MAXR + a.comm.rank) * 2;
@@ -560,9 +579,11 @@ struct LossArgs {
   int T, B, mb;
   uint32_t count_offset;
   float clip, critic_w;
+  const float* hpd;          // device hyper-parameter block (nullable): overrides clip / critic_w
   int normalize_adv;
   double n_global;
   PeerComm comm;
+  const uint32_t* comm_epoch;
   int update_index;
 };
 
@@ -574,7 +595,7 @@ __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean,
   const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
   double s1 = dbl[0], s2 = dbl[1];
   if (a.comm.table != nullptr) {
-    const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
+    const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
     comm_wait_all(a.comm, COMM_FLAG_ADV, epoch);
     const double* slot = reinterpret_cast<const double*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) +
                          (epoch & 1u) * MAXR * 2;
@@ -593,20 +614,33 @@ __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean,
 // loss, [2] regularisation loss, [3] grad norm (Adam kernel), [4] clipping fraction (ppo.py:514-520),
 // [5] E[target], [6] E[target^2] (for critic R^2, ppo.py:522-527), [7] E[adv], [8] E[adv^2] — all
 // divided by the GLOBAL sample count, so a data-parallel SUM over ranks gives the global means.
-__device__ __forceinline__ void loss_write_metrics(const LossArgs& a, const double (&s)[NLQ]) {
+// [7], [8]: moments of the advantages the surrogate uses.  ppo.py:477-480 REASSIGNS `advantages` to the
+// normalised tensor before it is logged at :523, so with normalize_advantages these are the moments of
+// (a - mean) / (std + 1e-8), derived from this rank's raw sums (GAE kernel) and the global statistics.
+__device__ __forceinline__ void loss_write_metrics(const LossArgs& a, const double (&s)[NLQ], float a_mean,
+                                                   float a_den) {
   const double ng = a.n_global;
   const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
   for (int q = 0; q < 3; ++q) a.metrics_out[q] = static_cast<float>(s[q] / ng);
   a.metrics_out[4] = static_cast<float>(s[3] / ng);
   a.metrics_out[5] = static_cast<float>(s[4] / ng);
   a.metrics_out[6] = static_cast<float>(s[5] / ng);
-  a.metrics_out[7] = static_cast<float>(__ldcg(dbl) / ng);          // this rank's advantage sums (GAE kernel)
-  a.metrics_out[8] = static_cast<float>(__ldcg(dbl + 1) / ng);
+  const double s1 = __ldcg(dbl), s2 = __ldcg(dbl + 1), n_loc = static_cast<double>(a.L.R);
+  const double m = a_mean, den = a_den;
+  a.metrics_out[7] = static_cast<float>((s1 - n_loc * m) / den / ng);
+  a.metrics_out[8] = static_cast<float>((s2 - 2.0 * m * s1 + n_loc * m * m) / (den * den) / ng);
+  // [9], [10]: the global normalisation constants (mean, std + 1e-8; 0 / 1 without normalisation), divided by
+  // the number of ranks so that the caller's SUM over ranks returns them unchanged
+  const double inv_world = n_loc / ng;
+  a.metrics_out[9] = static_cast<float>(m * inv_world);
+  a.metrics_out[10] = static_cast<float>(den * inv_world);
 }
 
 __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   __shared__ double red[NLQ][4];
   __shared__ float stats0_s[2];
+  pdl_launch_dependents();
+  pdl_wait();
   const int A = a.plan.act_dim;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const double ng = a.n_global;
@@ -614,6 +648,8 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
   if (threadIdx.x == 0) loss_adv_stats(a, stats0_s[0], stats0_s[1]);
   __syncthreads();
   const float a_mean = stats0_s[0], a_den = stats0_s[1];
+  const float clip = a.hpd ? a.hpd[B200PPO_HP_CLIP_RANGE] : a.clip;
+  const float critic_w = a.hpd ? a.hpd[B200PPO_HP_CRITIC_WEIGHT] : a.critic_w;
   double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0, l_clip = 0.0, l_t1 = 0.0, l_t2 = 0.0;
   if (r < a.L.R) {
     const int t = r / a.mb, j = r - t * a.mb;
@@ -641,13 +677,13 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
     const float diff = __fsub_rn(v, target);
     const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
     const float ratio = expf(ll - a.loglik_old[grow]);
-    const float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
+    const float lo = 1.0f - clip, hi = 1.0f + clip;
     const float c1 = __fmul_rn(ratio, an);
     const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
     l_actor = -static_cast<double>(fminf(c1, c2));
     l_critic = 0.5 * static_cast<double>(diff) * diff;
     l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
-    l_clip = fabsf(ratio - 1.0f) > a.clip ? 1.0 : 0.0;
+    l_clip = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
     l_t1 = target;
     l_t2 = static_cast<double>(target) * target;
     // JAX tie rules: minimum and clip split the cotangent 0.5 / 0.5 on exact ties
@@ -668,7 +704,7 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
       dy[d] = d_mu;
       dy[A + d] = d_sig * sigmoid_f(rho) * a.plan.std_scale;
     }
-    a.ws[a.dv_off + r] = a.critic_w * diff * inv_n;
+    a.ws[a.dv_off + r] = critic_w * diff * inv_n;
   }
   double lq[NLQ] = {l_actor, l_critic, l_reg, l_clip, l_t1, l_t2};
 #pragma unroll
@@ -689,7 +725,7 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
       double s[NLQ] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       for (unsigned int b = 0; b < gridDim.x; ++b)
         for (int q = 0; q < NLQ; ++q) s[q] += __ldcg(&part[NLQ * b + q]);
-      loss_write_metrics(a, s);
+      loss_write_metrics(a, s, a_mean, a_den);
     }
   }
 }
@@ -701,6 +737,8 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
 __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   __shared__ double red[NLQ][8];
   __shared__ float stats_s[2];
+  pdl_launch_dependents();
+  pdl_wait();
   const int A = a.plan.act_dim;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gid / A, d = gid - r * A;
@@ -737,6 +775,8 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   if (threadIdx.x == 0) loss_adv_stats(a, stats_s[0], stats_s[1]);
   __syncthreads();
   const float a_mean = stats_s[0], a_den = stats_s[1];
+  const float clip = a.hpd ? a.hpd[B200PPO_HP_CLIP_RANGE] : a.clip;
+  const float critic_w = a.hpd ? a.hpd[B200PPO_HP_CRITIC_WEIGHT] : a.critic_w;
   double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0, l_clip = 0.0, l_t1 = 0.0, l_t2 = 0.0;
   if (valid) {
     const float adv = a.ws[a.L.adv + r];
@@ -745,7 +785,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     const float diff = __fsub_rn(v, target);
     const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
     const float ratio = expf(ll - a.loglik_old[grow]);
-    const float lo = 1.0f - a.clip, hi = 1.0f + a.clip;
+    const float lo = 1.0f - clip, hi = 1.0f + clip;
     const float c1 = __fmul_rn(ratio, an);
     const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
     const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
@@ -761,11 +801,11 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     dy[d] = d_mu;
     dy[A + d] = d_sig * sigmoid_f(rho) * a.plan.std_scale;
     if (d == 0) {
-      a.ws[a.dv_off + r] = a.critic_w * diff * inv_n;
+      a.ws[a.dv_off + r] = critic_w * diff * inv_n;
       l_actor = -static_cast<double>(fminf(c1, c2));
       l_critic = 0.5 * static_cast<double>(diff) * diff;
       l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
-      l_clip = fabsf(ratio - 1.0f) > a.clip ? 1.0 : 0.0;
+      l_clip = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
       l_t1 = target;
       l_t2 = static_cast<double>(target) * target;
     }
@@ -811,7 +851,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
         for (int w = 0; w < 8; ++w) t += red[q][w];
         tot[q] = t;
       }
-      loss_write_metrics(a, tot);
+      loss_write_metrics(a, tot, a_mean, a_den);
     }
   }
 }
@@ -857,6 +897,8 @@ __device__ __forceinline__ void chain_backward_tile(const b200ppo_chain& ch, con
 
 __global__ void __launch_bounds__(NTH, 1) upd_bwd_dx_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   float* As = smem;
   float* Bs = smem + KB * LDA;
   const int row0 = blockIdx.x * TM;
@@ -870,6 +912,8 @@ __global__ void __launch_bounds__(NTH, 1) upd_bwd_dx_kernel(const BwdArgs a) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();
+  pdl_wait();
   float* As = smem;                       // [2][DW_R][DW_LD]
   float* Bs = smem + 2 * DW_R * DW_LD;    // [2][DW_R][DW_LD]
   // decode blockIdx.x -> (chain, layer, k tile, n tile)
@@ -980,70 +1024,27 @@ __global__ void __launch_bounds__(NTH, 2) upd_bwd_dw_kernel(const BwdArgs a) {
 #include "update_tc.cuh"
 
 // ------------------------------------------------------------------------------------------
-// RED / grad-norm / ADAM
+// RED / exchange / grad-norm / ADAM: one kernel, block b owns parameters [256 b, 256 b + 256)
 // ------------------------------------------------------------------------------------------
-// fixed-order sum of the dW row-split partials.  With the peer exchange the result is pushed into
-// every rank's comm buffer (slot = epoch parity, source rank).
-__global__ void __launch_bounds__(256) upd_red_kernel(const float* __restrict__ gpart, int S, int64_t P,
-                                                      float* __restrict__ grad, const PeerComm comm,
-                                                      const uint32_t* __restrict__ rng_state, int update_index,
-                                                      size_t ppad) {
-  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i >= P) return;
-  float g = 0.0f;
-  for (int s = 0; s < S; ++s) g += gpart[static_cast<size_t>(s) * P + i];
-  if (comm.table != nullptr) {
-    // push: slot [parity][this rank] of EVERY rank's buffer (stores over NVLink are fire-and-forget;
-    // the Adam kernels then read only their own memory)
-    const uint32_t epoch = rng_state[3] + static_cast<uint32_t>(update_index) + 1u;
-    const size_t slot = ((epoch & 1u) * comm.world + comm.rank) * ppad;
-    for (int r = 0; r < comm.world; ++r)
-      (reinterpret_cast<float*>(comm_base(comm, r) + COMM_GRAD) + slot)[i] = g;
-    return;
-  }
-  grad[i] = g;
-}
-
-__global__ void __launch_bounds__(256) upd_gnorm_kernel(const float* __restrict__ grad, int64_t P,
-                                                        double* __restrict__ part, double* __restrict__ out,
-                                                        unsigned int* __restrict__ ticket,
-                                                        const uint8_t* __restrict__ mask) {
-  __shared__ double red[8];
-  double s = 0.0;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < P;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (mask && !mask[i]) continue;              // structural zero of a block-diagonal layer: not a parameter
-    const double g = grad[i];
-    s += g * g;
-  }
-  s = warp_sum_d(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    part[blockIdx.x] = t;
-    __threadfence();
-    const unsigned int tk = atomicAdd(ticket, 1u);
-    if (tk == gridDim.x - 1) {
-      *ticket = 0u;
-      __threadfence();
-      double tot = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(&part[b]);
-      *out = tot;
-    }
-  }
-}
-
 struct AdamArgs {
-  const float* gpart; int S; float* grad_out;   // S > 0: fused fixed-order reduction of the dW partials
-  const float* grad; float* params; float* mu; float* nu;
-  const uint32_t* rng_state; const double* gnorm2; float* metrics_out;
+  const float* gpart; int S;        // S > 0: fixed-order reduction of the dW row-split partials first
+  const float* grad;                // S == 0: the (already reduced / all-reduced) flat gradient
+  float* grad_out;                  // nullable: where the gradient this launch ends up with is written
+  float* params; float* mu; float* nu;
+  const uint32_t* rng_state; const uint32_t* comm_epoch; const double* gnorm2; float* metrics_out;
   int64_t P;
   int update_index;
   float lr, b1, b2, eps, wd, clip;
-  PeerComm comm;        // table != nullptr: the gradient is the rank-ordered sum of the copies every rank pushed here
+  const float* hpd;                 // device hyper-parameter block (nullable): overrides the six values above
+  // peer exchange (table != nullptr): push this block's 256 reduced gradients into slot [parity][rank] of
+  // EVERY rank's buffer, raise this block's flag everywhere, wait for every rank's flag of THIS block only
+  // (a block needs nothing but its own 256 parameters from each peer), sum the slots in rank order
+  PeerComm comm;
   size_t comm_ppad;
+  int comm_nblk;
+  int do_adam;                      // 0: reduce / exchange / norm only
+  // nullable: squared global norm of the (summed) gradient -> *norm_out (block partials, ticket, fixed order)
+  double* norm_part; double* norm_out; unsigned int* norm_ticket;
   const uint8_t* mask;  // nullable: 0 = structural zero (off-diagonal block of per-key encoders), never updated
   // tensor-core path: the updated weight is also re-split into the hi / lo operand planes of the next
   // update (what upd_prep_w_kernel does from scratch), so that update can skip its prep launch
@@ -1055,49 +1056,101 @@ struct AdamArgs {
 // optax.adam / adamw (scale_by_adam -> [add_decayed_weights] -> scale(-lr)), optionally preceded by
 // clip_by_global_norm — ppo.py:555-569.
 __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
+  __shared__ double nred[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const bool in = i < a.P;
+  float g = 0.0f;
+  if (in) {
+    if (a.S > 0) {
+      for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
+    } else {
+      g = a.grad[i];
+    }
+  }
+  if (a.comm.table != nullptr) {
+    const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
+    const size_t goff = comm_grad_off(a.comm_nblk);
+    const size_t slot = ((epoch & 1u) * a.comm.world + a.comm.rank) * a.comm_ppad;
+    if (in)
+      for (int r = 0; r < a.comm.world; ++r)        // stores over NVLink are fire-and-forget
+        (reinterpret_cast<float*>(comm_base(a.comm, r) + goff) + slot)[i] = g;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // the barrier ordered the block's pushes before this thread; ONE system-scope fence, then relaxed
+      // flag stores back to back (a st.release.sys per peer is one NVLink round trip each)
+      __threadfence_system();
+      for (int r = 0; r < a.comm.world; ++r)
+        st_relaxed_sys(reinterpret_cast<uint32_t*>(comm_base(a.comm, r) + COMM_FLAG_BLK) +
+                           static_cast<size_t>(a.comm.rank) * a.comm_nblk + blockIdx.x, epoch);
+      const uint32_t* fl = reinterpret_cast<const uint32_t*>(comm_base(a.comm, a.comm.rank) + COMM_FLAG_BLK) + blockIdx.x;
+      for (int r = 0; r < a.comm.world; ++r) {
+        unsigned long long spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys(fl + static_cast<size_t>(r) * a.comm_nblk) - epoch) < 0) {
+          if (++spins > (1ull << 27)) {
+            printf("b200ppo: rank %d block %d waited too long for the gradient of rank %d (epoch %u)\n", a.comm.rank,
+                   static_cast<int>(blockIdx.x), r, epoch);
+            __trap();
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (in) {
+      g = 0.0f;
+      const float* pg = reinterpret_cast<const float*>(comm_base(a.comm, a.comm.rank) + goff) +
+                        (epoch & 1u) * a.comm.world * a.comm_ppad;
+      for (int r = 0; r < a.comm.world; ++r) g += __ldcg(pg + r * a.comm_ppad + i);   // rank order: identical on every rank
+    }
+  }
+  if (in && a.grad_out != nullptr) a.grad_out[i] = g;
+  if (a.norm_part != nullptr) {
+    double sq = (in && !(a.mask && !a.mask[i])) ? static_cast<double>(g) * g : 0.0;
+    sq = warp_sum_d(sq);
+    if ((threadIdx.x & 31) == 0) nred[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += nred[w];
+      a.norm_part[blockIdx.x] = t;
+      __threadfence();
+      const unsigned int tk = atomicAdd(a.norm_ticket, 1u);
+      if (tk == gridDim.x - 1) {
+        *a.norm_ticket = 0u;
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(&a.norm_part[b]);
+        *a.norm_out = tot;
+      }
+    }
+  }
+  if (!a.do_adam) return;
+  const float lr = a.hpd ? a.hpd[B200PPO_HP_LEARNING_RATE] : a.lr;
+  const float b1 = a.hpd ? a.hpd[B200PPO_HP_ADAM_B1] : a.b1;
+  const float b2 = a.hpd ? a.hpd[B200PPO_HP_ADAM_B2] : a.b2;
+  const float eps = a.hpd ? a.hpd[B200PPO_HP_ADAM_EPS] : a.eps;
+  const float wd = a.hpd ? a.hpd[B200PPO_HP_WEIGHT_DECAY] : a.wd;
+  const float clip = a.hpd ? a.hpd[B200PPO_HP_GRAD_CLIP] : a.clip;
   float gn = 0.0f;
-  if (a.clip > 0.0f) {
+  if (a.clip > 0.0f) {                 // structure (clipping on / off) is the host's; the threshold is run-time data
     gn = sqrtf(static_cast<float>(*a.gnorm2));
     if (i == 0) a.metrics_out[3] = gn;
   }
-  const uint32_t epoch = a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u;
-  if (a.comm.table != nullptr) {
-    // the local reduction (previous kernel on this stream) is complete: publish, then wait for everyone
-    if (threadIdx.x == 0) {
-      if (blockIdx.x == 0) comm_signal_all(a.comm, COMM_FLAG_GRAD, epoch);   // one fence: the reduce kernel's pushes are out
-      comm_wait_all(a.comm, COMM_FLAG_GRAD, epoch);
-    }
-    __syncthreads();
-  }
-  if (i >= a.P) return;
-  float g;
-  if (a.comm.table != nullptr) {
-    g = 0.0f;
-    const float* pg = reinterpret_cast<const float*>(comm_base(a.comm, a.comm.rank) + COMM_GRAD) +
-                      (epoch & 1u) * a.comm.world * a.comm_ppad;
-    for (int r = 0; r < a.comm.world; ++r) g += __ldcg(pg + r * a.comm_ppad + i);   // rank order: identical on every rank
-    a.grad_out[i] = g;
-  } else if (a.S > 0) {
-    g = 0.0f;
-    for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
-    a.grad_out[i] = g;
-  } else {
-    g = a.grad[i];
-  }
+  if (!in) return;
   if (a.mask && !a.mask[i]) return;
-  if (a.clip > 0.0f && !(gn < a.clip)) g = __fmul_rn(__fdiv_rn(g, gn), a.clip);
-  const float t = static_cast<float>(epoch);
-  const float m = __fadd_rn(__fmul_rn(1.0f - a.b1, g), __fmul_rn(a.b1, a.mu[i]));
-  const float v = __fadd_rn(__fmul_rn(1.0f - a.b2, __fmul_rn(g, g)), __fmul_rn(a.b2, a.nu[i]));
+  if (a.clip > 0.0f && !(gn < clip)) g = __fmul_rn(__fdiv_rn(g, gn), clip);
+  const float t = static_cast<float>(a.rng_state[3] + static_cast<uint32_t>(a.update_index) + 1u);
+  const float m = __fadd_rn(__fmul_rn(1.0f - b1, g), __fmul_rn(b1, a.mu[i]));
+  const float v = __fadd_rn(__fmul_rn(1.0f - b2, __fmul_rn(g, g)), __fmul_rn(b2, a.nu[i]));
   a.mu[i] = m;
   a.nu[i] = v;
-  const float bc1 = 1.0f - powf(a.b1, t), bc2 = 1.0f - powf(a.b2, t);
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
   const float mh = __fdiv_rn(m, bc1), vh = __fdiv_rn(v, bc2);
-  float u = __fdiv_rn(mh, __fadd_rn(sqrtf(vh), a.eps));
+  float u = __fdiv_rn(mh, __fadd_rn(sqrtf(vh), eps));
   const float p = a.params[i];
-  if (a.wd >= 0.0f) u = __fadd_rn(u, __fmul_rn(a.wd, p));
-  const float pn = __fadd_rn(p, __fmul_rn(-a.lr, u));
+  if (a.wd >= 0.0f) u = __fadd_rn(u, __fmul_rn(wd, p));
+  const float pn = __fadd_rn(p, __fmul_rn(-lr, u));
   a.params[i] = pn;
   for (int q = 0; q < a.n_seg; ++q) {
     const int64_t o = i - a.seg[q].w_off;
@@ -1204,15 +1257,16 @@ extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200p
   const Layout L = make_layout(*plan, T, mb);
   const bool use_tc = gemm_mode() != 0 && L.tc_ok;
   int n = 0;
-  const char* fe = std::getenv("B200PPO_FORK");
-  const int forked = (use_tc && fe && fe[0] == '1') ? 1 : 0;   // critic / actor halves are separate launches
-  if (stages & B200PPO_STAGE_FWD) n += ((use_tc && !(stages & B200PPO_STAGE_NO_PREP)) ? 2 : 1) + forked;
+  if (stages & B200PPO_STAGE_FWD) n += (use_tc && !(stages & B200PPO_STAGE_NO_PREP)) ? 2 : 1;
   if (stages & B200PPO_STAGE_GAE) n += 1;
   if (stages & B200PPO_STAGE_LOSS) n += 1;
-  if (stages & B200PPO_STAGE_BWD) n += 2 + 2 * forked;
-  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f);
-  if ((stages & B200PPO_STAGE_RED) && !fuse_red) n += 1;
-  if (stages & B200PPO_STAGE_ADAM) n += hp->grad_clip > 0.0f ? 2 : 1;
+  if (stages & B200PPO_STAGE_BWD) n += 2;
+  else n += ((stages & B200PPO_STAGE_BWD_DX) ? 1 : 0) + ((stages & B200PPO_STAGE_BWD_DW) ? 1 : 0);
+  const bool red = (stages & B200PPO_STAGE_RED) != 0, adam = (stages & B200PPO_STAGE_ADAM) != 0;
+  const bool clip = hp->grad_clip > 0.0f;
+  if (red && adam) n += clip ? 2 : 1;        // reduce (+ exchange) fused into the Adam launch; the norm needs its own pass
+  else if (red) n += 1;
+  else if (adam) n += clip ? 2 : 1;
   return n;
 }
 
@@ -1243,37 +1297,6 @@ extern "C" float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, 
   }
 }
 
-namespace {
-// Second stream + events used to run the critic and actor halves of the tensor-core update as
-// concurrent kernels (they are independent between the observation gather and the loss, and again
-// between the loss and Adam).  Created lazily per device, OUTSIDE stream capture (the engine runs
-// its first iteration eagerly); captured fork / join edges become parallel branches of the CUDA graph.
-struct ForkRes {
-  cudaStream_t aux = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  int state = 0;   // 0 untried, 1 ok, -1 unavailable
-};
-ForkRes g_fork[64];
-ForkRes* get_fork(cudaStream_t s) {
-  // measured on B200 (cfg 2): 6.34 ms / iteration forked vs 6.10 ms in one stream — every CTA of these
-  // kernels owns a whole SM's shared memory, so the halves cannot co-reside and the extra launches,
-  // duplicated observation gathers and graph edges cost more than hiding GAE saves.  Opt-in only.
-  const char* e = std::getenv("B200PPO_FORK");
-  if (!(e && e[0] == '1')) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  ForkRes& f = g_fork[dev];
-  if (f.state == 0) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return nullptr;  // not now
-    bool ok = cudaStreamCreateWithFlags(&f.aux, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&f.ev[i], cudaEventDisableTiming) == cudaSuccess;
-    f.state = ok ? 1 : -1;
-  }
-  return f.state == 1 ? &f : nullptr;
-}
-}  // namespace
-
 extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,
                               const b200ppo_update_bufs* b, int32_t T, int32_t B, int32_t mb,
                               uint32_t rng_count_offset, int32_t update_index, int32_t stages) {
@@ -1291,7 +1314,6 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   PeerComm pc{nullptr, 1, 0};
   if (use_comm) {
     if (hp->world_size > MAXR || hp->rank < 0 || hp->rank >= hp->world_size) return B200PPO_EINVAL;
-    if (hp->grad_clip > 0.0f) return B200PPO_EINVAL;   // the global norm needs the summed gradient first: use the staged path
     pc = PeerComm{b->comm, hp->world_size, hp->rank};
   }
   rc = set_attrs();
@@ -1300,6 +1322,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   const bool use_tc = gemm_mode() != 0 && L.tc_ok;
   const int tc_split = gemm_mode() == 1 ? 1 : 0;
   if (cdiv(mb, GAE_THREADS) > MAX_PART_BLOCKS || cdiv(L.R, 128) > MAX_LOSS_BLOCKS) return B200PPO_ELIMIT;
+  if (cdiv(plan->n_params, 256) > MAX_NORM_BLOCKS) return B200PPO_ELIMIT;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* ws = static_cast<float*>(b->ws);
   const size_t v_off = L.zc[plan->critic.n_layers - 1];
@@ -1308,8 +1331,6 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
   const size_t dy_off = L.da[plan->actor.n_layers - 1];
   double* dbl = reinterpret_cast<double*>(ws + L.dbl);
   unsigned int* tickets = reinterpret_cast<unsigned int*>(ws + L.tickets);
-  ForkRes* fk = use_tc ? get_fork(s) : nullptr;
-  bool fwd_forked = false;
   // rows per CTA of the row-tiled tensor-core kernels: spread the minibatch over all SMs
   auto tile_for = [](int rows) {
     int t = cdiv(rows, b200ppo_num_sms());
@@ -1317,6 +1338,11 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     return t > TCM ? TCM : t;
   };
   const int tile_f = tile_for(L.Rv), tile_b = tile_for(L.R);
+#define B200PPO_LAUNCH(...)                                           \
+  do {                                                                \
+    const cudaError_t le__ = launch_k(__VA_ARGS__);                   \
+    if (le__ != cudaSuccess) return static_cast<int>(le__);           \
+  } while (0)
 
   if (stages & B200PPO_STAGE_FWD) {
     FwdArgs a;
@@ -1327,36 +1353,22 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
       if (!(stages & B200PPO_STAGE_NO_PREP)) {
         PrepArgs pa;
         pa.plan = *plan; pa.L = L; pa.params = b->params; pa.ws = ws;
-        upd_prep_w_kernel<<<dim3(16, 2 * MAXL, 2), 256, 0, s>>>(pa);
-        B200PPO_LAUNCH_CHECK();
+        B200PPO_LAUNCH(upd_prep_w_kernel, dim3(16, 2 * MAXL, 2), dim3(256), 0, s, pa);
       }
-      if (fk) {
-        // actor chain on the second stream; critic chain (then GAE) on this one; joined before the loss
-        if (cudaEventRecord(fk->ev[0], s) != cudaSuccess || cudaStreamWaitEvent(fk->aux, fk->ev[0], 0) != cudaSuccess)
-          return static_cast<int>(cudaGetLastError());
-        upd_fwd_tc_kernel<<<cdiv(L.R, tile_f), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2, tile_f);
-        B200PPO_LAUNCH_CHECK();
-        if (cudaEventRecord(fk->ev[1], fk->aux) != cudaSuccess) return static_cast<int>(cudaGetLastError());
-        upd_fwd_tc_kernel<<<cdiv(L.Rv, tile_f), TCT, TC_SMEM, s>>>(a, tc_split, 1, tile_f);
-        fwd_forked = true;
-      } else {
-        upd_fwd_tc_kernel<<<cdiv(L.Rv, tile_f), TCT, TC_SMEM, s>>>(a, tc_split, 3, tile_f);
-      }
+      B200PPO_LAUNCH(upd_fwd_tc_kernel, dim3(cdiv(L.Rv, tile_f)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_f);
     } else {
-      upd_fwd_kernel<<<cdiv(L.Rv, TM), NTH, GEMM_SMEM, s>>>(a);
+      B200PPO_LAUNCH(upd_fwd_kernel, dim3(cdiv(L.Rv, TM)), dim3(NTH), GEMM_SMEM, s, a);
     }
-    B200PPO_LAUNCH_CHECK();
   }
   if (stages & B200PPO_STAGE_GAE) {
     GaeArgs a;
     a.L = L; a.reward = b->reward; a.done = b->done; a.trunc = b->truncated; a.inds = b->inds;
     a.ws = ws; a.v_off = v_off; a.T = T; a.B = B; a.mb = mb; a.gamma = hp->gamma; a.lambda_ = hp->lambda_;
+    a.hpd = b->hparams_dev;
     a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
-    a.rng_state = b->rng_state; a.update_index = update_index;
-    upd_gae_kernel<<<cdiv(mb, GAE_THREADS), GAE_THREADS, 0, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
+    a.rng_state = b->rng_state; a.comm_epoch = b->comm_epoch; a.update_index = update_index;
+    B200PPO_LAUNCH(upd_gae_kernel, dim3(cdiv(mb, GAE_THREADS)), dim3(GAE_THREADS), 0, s, a);
   }
-  if (fwd_forked && cudaStreamWaitEvent(s, fk->ev[1], 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
   if (stages & B200PPO_STAGE_LOSS) {
     LossArgs a;
     a.plan = *plan; a.L = L; a.raw_action = b->raw_action; a.loglik_old = b->loglik_old; a.inds = b->inds;
@@ -1364,14 +1376,15 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.y_off = y_off; a.v_off = v_off; a.dy_off = dy_off; a.dv_off = dv_off;
     a.T = T; a.B = B; a.mb = mb; a.count_offset = rng_count_offset;
     a.clip = hp->clip_range; a.critic_w = hp->critic_loss_weight; a.normalize_adv = hp->normalize_advantages;
+    a.hpd = b->hparams_dev;
     a.n_global = static_cast<double>(L.R) * hp->world_size;
     a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
+    a.comm_epoch = b->comm_epoch;
     a.update_index = update_index;
     const int A = plan->act_dim;
     const bool par = A <= 32 && (A & (A - 1)) == 0 && cdiv(static_cast<int64_t>(L.R) * A, 256) <= MAX_LOSS_BLOCKS;
-    if (par) upd_loss_par_kernel<<<cdiv(static_cast<int64_t>(L.R) * A, 256), 256, 0, s>>>(a);
-    else upd_loss_kernel<<<cdiv(L.R, 128), 128, 0, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
+    if (par) B200PPO_LAUNCH(upd_loss_par_kernel, dim3(cdiv(static_cast<int64_t>(L.R) * A, 256)), dim3(256), 0, s, a);
+    else B200PPO_LAUNCH(upd_loss_kernel, dim3(cdiv(L.R, 128)), dim3(128), 0, s, a);
   }
   if (stages & (B200PPO_STAGE_BWD | B200PPO_STAGE_BWD_DX | B200PPO_STAGE_BWD_DW)) {
     const bool do_dx = (stages & B200PPO_STAGE_BWD) || (stages & B200PPO_STAGE_BWD_DX);
@@ -1379,65 +1392,34 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     BwdArgs a;
     a.plan = *plan; a.L = L; a.params = b->params; a.ws = ws;
     if (use_tc) {
-      int items_actor = 0;
-      for (int l = 0; l < plan->actor.n_layers; ++l) items_actor += cdiv(plan->actor.dims[l], 128);
-      const int items_critic = L.tc_tiles - items_actor;
-      auto launch_dw = [&](cudaStream_t st, int base, int count) {
-        if (L.tc_dw_bulk) upd_bwd_dw_tc2_kernel<<<dim3(count, L.tc_S), TCT, DW2_SMEM, st>>>(a, tc_split, base);
-        else upd_bwd_dw_tc_kernel<<<dim3(count, L.tc_S), TCT, TC_SMEM, st>>>(a, tc_split, base);
-      };
-      if (fk) {
-        // actor dX -> actor dW on the second stream, critic dX -> critic dW on this one
-        if (cudaEventRecord(fk->ev[2], s) != cudaSuccess || cudaStreamWaitEvent(fk->aux, fk->ev[2], 0) != cudaSuccess)
-          return static_cast<int>(cudaGetLastError());
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, s>>>(a, tc_split, 1, tile_b);
-        B200PPO_LAUNCH_CHECK();
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, fk->aux>>>(a, tc_split, 2, tile_b);
-        B200PPO_LAUNCH_CHECK();
-        if (do_dw) launch_dw(s, items_actor, items_critic);
-        B200PPO_LAUNCH_CHECK();
-        if (do_dw) launch_dw(fk->aux, 0, items_actor);
-        B200PPO_LAUNCH_CHECK();
-        if (cudaEventRecord(fk->ev[3], fk->aux) != cudaSuccess || cudaStreamWaitEvent(s, fk->ev[3], 0) != cudaSuccess)
-          return static_cast<int>(cudaGetLastError());
-      } else {
-        if (do_dx) upd_bwd_dx_tc_kernel<<<cdiv(L.R, tile_b), TCT, TC_SMEM, s>>>(a, tc_split, 3, tile_b);
-        B200PPO_LAUNCH_CHECK();
-        if (do_dw) launch_dw(s, 0, L.tc_tiles);
-        B200PPO_LAUNCH_CHECK();
+      if (do_dx) B200PPO_LAUNCH(upd_bwd_dx_tc_kernel, dim3(cdiv(L.R, tile_b)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_b);
+      if (do_dw) {
+        if (L.tc_dw_bulk) B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0);
+        else B200PPO_LAUNCH(upd_bwd_dw_tc_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), TC_SMEM, s, a, tc_split, 0);
       }
     } else {
-      if (do_dx) upd_bwd_dx_kernel<<<cdiv(L.R, TM), NTH, GEMM_SMEM, s>>>(a);
-      B200PPO_LAUNCH_CHECK();
-      if (do_dw) upd_bwd_dw_kernel<<<dim3(L.n_tiles, L.S), NTH, DW_SMEM, s>>>(a);
-      B200PPO_LAUNCH_CHECK();
+      if (do_dx) B200PPO_LAUNCH(upd_bwd_dx_kernel, dim3(cdiv(L.R, TM)), dim3(NTH), GEMM_SMEM, s, a);
+      if (do_dw) B200PPO_LAUNCH(upd_bwd_dw_kernel, dim3(L.n_tiles, L.S), dim3(NTH), DW_SMEM, s, a);
     }
   }
-  // reduce + adam fuse into one launch when both stages are requested and no global norm is needed
-  const bool fuse_red = (stages & B200PPO_STAGE_RED) && (stages & B200PPO_STAGE_ADAM) && !(hp->grad_clip > 0.0f) &&
-                        !use_comm;
-  if ((stages & B200PPO_STAGE_RED) && !fuse_red) {
-    upd_red_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(ws + L.gpart, use_tc ? L.tc_S : L.S, plan->n_params,
-                                                             ws + L.grad, pc, b->rng_state, update_index,
-                                                             comm_ppad(plan->n_params));
-    B200PPO_LAUNCH_CHECK();
-  }
-  if (stages & B200PPO_STAGE_ADAM) {
-    if (hp->grad_clip > 0.0f) {
-      int nb = cdiv(plan->n_params, 256 * 8);
-      if (nb > MAX_PART_BLOCKS) nb = MAX_PART_BLOCKS;
-      upd_gnorm_kernel<<<nb, 256, 0, s>>>(ws + L.grad, plan->n_params, dbl + DBL_GN_PART, dbl + 2, tickets + 2,
-                                          b->param_mask);
-      B200PPO_LAUNCH_CHECK();
-    }
+  // RED / ADAM: one kernel does the fixed-order reduction of the dW partials, the peer exchange (when
+  // bufs->comm is set) and the optimizer step.  With clip_by_global_norm the squared norm of the summed
+  // gradient is a grid-wide reduction that must finish first, so the work splits into two launches.
+  const bool do_red = (stages & B200PPO_STAGE_RED) != 0, do_adam = (stages & B200PPO_STAGE_ADAM) != 0;
+  if (do_red || do_adam) {
+    const bool clip = hp->grad_clip > 0.0f;
     AdamArgs a;
-    a.gpart = ws + L.gpart; a.S = fuse_red ? (use_tc ? L.tc_S : L.S) : 0; a.grad_out = ws + L.grad;
-    a.grad = ws + L.grad; a.params = b->params; a.mu = b->adam_mu; a.nu = b->adam_nu;
-    a.rng_state = b->rng_state; a.gnorm2 = dbl + 2; a.metrics_out = b->metrics_out;
+    a.gpart = ws + L.gpart; a.S = do_red ? (use_tc ? L.tc_S : L.S) : 0;
+    a.grad = ws + L.grad; a.grad_out = ws + L.grad;
+    a.params = b->params; a.mu = b->adam_mu; a.nu = b->adam_nu;
+    a.rng_state = b->rng_state; a.comm_epoch = b->comm_epoch; a.gnorm2 = dbl + 2; a.metrics_out = b->metrics_out;
     a.P = plan->n_params; a.update_index = update_index;
     a.lr = hp->learning_rate; a.b1 = hp->adam_b1; a.b2 = hp->adam_b2; a.eps = hp->adam_eps;
-    a.wd = hp->weight_decay; a.clip = hp->grad_clip;
-    a.comm = pc; a.comm_ppad = comm_ppad(plan->n_params);
+    a.wd = hp->weight_decay; a.clip = hp->grad_clip; a.hpd = b->hparams_dev;
+    // the exchange belongs to the ADAM stage: a caller that runs RED alone gets the local gradient
+    a.comm = do_adam ? pc : PeerComm{nullptr, 1, 0};
+    a.comm_ppad = comm_ppad(plan->n_params); a.comm_nblk = comm_nblk(plan->n_params);
+    a.norm_part = nullptr; a.norm_out = dbl + 2; a.norm_ticket = tickets + 2;
     a.mask = b->param_mask;
     a.n_seg = 0; a.ws = ws;
     if (use_tc) {
@@ -1452,9 +1434,22 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
         }
       }
     }
-    upd_adam_kernel<<<cdiv(plan->n_params, 256), 256, 0, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
+    const dim3 grid(cdiv(plan->n_params, 256)), block(256);
+    if (!do_adam) {                         // RED alone
+      a.do_adam = 0;
+      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+    } else if (!clip) {                     // (reduce +) (exchange +) Adam in one launch
+      a.do_adam = 1;
+      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+    } else {                                // pass 1: (reduce +) (exchange +) squared norm; pass 2: clipped Adam
+      AdamArgs p1 = a;
+      p1.do_adam = 0; p1.norm_part = dbl + DBL_GN_PART;
+      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, p1);
+      a.S = 0; a.comm = PeerComm{nullptr, 1, 0}; a.grad_out = nullptr; a.do_adam = 1;
+      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+    }
   }
+#undef B200PPO_LAUNCH
   return 0;
 }
 
@@ -1463,7 +1458,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size) {
   if (check_plan_u(plan) || world_size < 1 || world_size > MAXR) return -1;
-  return static_cast<int64_t>(COMM_GRAD + 2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(float));
+  return static_cast<int64_t>(comm_grad_off(comm_nblk(plan->n_params)) +
+                              2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(float));
 }
 
 extern "C" int b200ppo_comm_alloc(int64_t bytes, void** out) {

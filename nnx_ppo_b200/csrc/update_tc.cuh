@@ -459,6 +459,8 @@ struct PrepArgs {
 };
 
 __global__ void __launch_bounds__(256) upd_prep_w_kernel(const PrepArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   // blockIdx.y = chain * MAXL + layer ; blockIdx.z = 0 (Wf) / 1 (Wb)
   const int chain = blockIdx.y / MAXL, l = blockIdx.y % MAXL;
   const b200ppo_chain& ch = chain == 0 ? a.plan.actor : a.plan.critic;
@@ -670,9 +672,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_fwd_tc_kernel(const FwdArgs a, con
   __shared__ uint32_t tmem_slot;
   __shared__ const float* rowsrc[TCM];
   __shared__ __align__(16) TcFwdSmem sm;
+  pdl_launch_dependents();
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
   const int O = a.plan.obs_dim;
+  pdl_wait();                  // TMEM / barriers are set up; everything below reads the previous kernels' results
   const int row0 = blockIdx.x * tile_rows;
   const int rend = row0 + tile_rows;
   const int R = a.L.R < rend ? a.L.R : rend, Rv = a.L.Rv < rend ? a.L.Rv : rend;   // clipped to this tile
@@ -885,8 +889,10 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dx_tc_kernel(const BwdArgs a, 
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot, 2 * TC_MAXN);
+  pdl_wait();
   const int row0 = blockIdx.x * tile_rows;
   tc_stamp(cx.nstamp);
   const int rend = (row0 + tile_rows) < a.L.R ? (row0 + tile_rows) : a.L.R;        // this tile's live rows
@@ -907,6 +913,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[TC_NPROD];
+  pdl_launch_dependents();
   int item = blockIdx.x + item_base;   // items: actor M-tiles first, then critic (the host may launch the chains separately)
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
@@ -926,6 +933,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
   if (static_cast<int>(blockIdx.y) >= a.L.tc_item_S[blockIdx.x + item_base]) return;   // this item has fewer row splits
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  pdl_wait();
   if (g_tc_stamp_skip_dw & 1) cx.nstamp = -100000;
   const int K = ch->dims[layer], N = ch->dims[layer + 1];
   const int npad = (N + 15) & ~15;
@@ -1111,6 +1119,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   __shared__ uint64_t rbar[2 * DW2_NR];                      // [0..NR) raw full, [NR..2NR) raw empty
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[2][TC_NPROD];
+  pdl_launch_dependents();
   int item = blockIdx.x + item_base;   // items: actor M-tiles first, then critic (the host may launch the chains separately)
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
@@ -1138,6 +1147,7 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   }
   TcCtx cx;
   tc_ctx_init(cx, tsmem, bars, &tmem_slot);
+  pdl_wait();
   cx.b_base = DW2_NS * 2u * TC_A_BYTES;
   if (g_tc_stamp_skip_dw & 1) cx.nstamp = -100000;
   const int K = ch->dims[layer], N = ch->dims[layer + 1];

@@ -243,6 +243,35 @@ class CompiledNet:
             return rollout_extras[-1]
         return rollout_extras
 
+    # ---- the sampler's `metrics` dict (sampling_layers.py:111) inside the reference-shaped metrics tree ----
+    def sampler_metric_keys(self) -> list:
+        """Key path of the sampler's metrics under Transition.metrics["net"]: Sequential layers are keyed
+        by position (containers.py:36), the PPOAdapter by port name (adapter.py:112)."""
+        path = []
+        if self.network is not self.adapter:
+            path.append(len(self.obs_adapters) + (1 if self.normalizer is not None else 0))
+        path += ["action", len(self.adapter.action.layers) - 1]
+        return path
+
+    def sampler_metric_path(self) -> str:
+        return "/".join(["net"] + [str(k) for k in self.sampler_metric_keys()])
+
+    def wrap_sampler_metrics(self, mu_sigma):
+        """{"mu", "sigma"} of one network call nested like the reference's `out.metrics`."""
+        A = mu_sigma.shape[-1] // 2
+        tree = {"mu": mu_sigma[..., :A], "sigma": mu_sigma[..., A:]}
+        for k in reversed(self.sampler_metric_keys()):
+            tree = {k: tree}
+        return tree
+
+    def logical_index_dev(self):
+        """Device int64 index of every real parameter in the arena (no padding, no structural zeros)."""
+        import torch
+        idx = getattr(self, "_logical_index_dev", None)
+        if idx is None:
+            idx = self._logical_index_dev = torch.from_numpy(np.asarray(self._logical_index, np.int64)).to(self.device)
+        return idx
+
     # ---- flat <-> logical parameter order (actor W0,b0,..., critic W0,b0,...; no padding) ----
     def params_logical(self, arena=None) -> np.ndarray:
         """An arena-shaped tensor (parameters by default; also gradients, Adam moments) in the
@@ -322,6 +351,7 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     ll = torch.empty(B, device=dev)
     value = torch.empty(B, device=dev)
     reg = torch.empty(B, device=dev)
+    musig = torch.empty(B, 2 * A, device=dev)            # the sampler's metrics {"mu", "sigma"} (sampling_layers.py:111)
     s = _lib.current_stream()
     if net.normalizer is not None:
         net.normalizer.prepare(s)
@@ -329,14 +359,15 @@ def call_network(network: StatefulModule, state: Any, obs: Any, rollout_extras: 
     mean_p, std_p = net.norm_ptrs()
     _lib.check(lib.b200ppo_policy_step(s, net.plan, _lib.ptr(net.arena), mean_p, std_p, _lib.ptr(obs), B,
                                        mode, _lib.ptr(net.counters), 0, _lib.ptr(raw_in), _lib.ptr(raw),
-                                       _lib.ptr(action), _lib.ptr(ll), _lib.ptr(value), _lib.ptr(reg), 0),
-               "policy_step")
+                                       _lib.ptr(action), _lib.ptr(ll), _lib.ptr(value), _lib.ptr(reg),
+                                       _lib.ptr(musig)), "policy_step")
     net.advance_rng(1 if net.sampler.deterministic else 2)
     na, nc = len(net.actor_layers), len(net.critic_layers)
     adapter_state = {"action": [()] * (na + 1), "value": [()] * nc}
     adapter_extras = {"action": [None] * na + [raw], "value": [None] * nc}
     out = PPONetworkOutput(actions=action, loglikelihoods=ll, value_estimates=value)
-    return StatefulModuleOutput(net.wrap((), adapter_state, ()), out, reg, {}, net.wrap(obs, adapter_extras, None))
+    return StatefulModuleOutput(net.wrap((), adapter_state, ()), out, reg, net.wrap_sampler_metrics(musig),
+                                net.wrap(obs, adapter_extras, None))
 
 
 def _call_recurrent(net, state: Any, obs, rollout_extras: Any):

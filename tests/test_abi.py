@@ -38,7 +38,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.Chain) == 4 + 4 + 9 * 4 + 4 + 8 * 8 + 8 * 8
     assert ctypes.sizeof(_lib.Plan) == 16 + 16 + 8 + 2 * ctypes.sizeof(_lib.Chain)
     assert ctypes.sizeof(_lib.HParams) == 52
-    assert ctypes.sizeof(_lib.UpdateBufs) == 18 * 8
+    assert ctypes.sizeof(_lib.UpdateBufs) == 20 * 8
     assert ctypes.sizeof(_lib.SynthEnv) == 32
 
 
@@ -188,8 +188,10 @@ def test_host_side_sizing_entry_points_for_the_bench_configuration(lib):
     assert (first, later) == (7, 6)            # prep + fwd, gae, loss, dX, dW, reduce+adam
     # one iteration: 32 updates + norm prepare, rollout, permutation, 2 stats passes, merge, finalize
     assert first + 31 * later + 7 == 200       # bench.py's gpu_launches at configs[1]
-    hp.grad_clip = 0.5                         # clip_by_global_norm: separate reduce, norm and Adam launches
-    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP)) == 8
+    hp.grad_clip = 0.5                         # clip_by_global_norm: reduce (+ exchange) + norm, then the clipped Adam
+    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP)) == 7
+    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_RED)) == 1
+    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ADAM)) == 2
     base = 1 << 20
     for fn in (lib.b200ppo_update_adv_sums_ptr, lib.b200ppo_update_grad_ptr):
         p = int(fn(net.plan, T, mb, base))
@@ -292,8 +294,7 @@ def test_update_launcher_rejects_before_launching(lib):
     assert call() == EINVAL
     hp.world_size, hp.rank, b.comm, hp.grad_clip = 4, 4, p, -1.0
     assert call() == EINVAL                                                # rank out of range on the peer-memory path
-    hp.rank, hp.grad_clip = 1, 0.5
-    assert call() == EINVAL                                                # clipping needs the staged (NCCL) path
+    hp.rank = 1
     hp.world_size = _lib.MAX_RANKS + 1 if hasattr(_lib, "MAX_RANKS") else 17
     hp.grad_clip = -1.0
     assert call() == EINVAL

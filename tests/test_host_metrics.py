@@ -61,7 +61,7 @@ def test_iteration_metrics_mean_std_mode():
         _ref_log(want, k, pu[:, i], None)
     _ref_log(want, "losses/clipping_fraction", pu[:, 4], None)                         # ppo.py:514-520
     _ref_log(want, "losses/critic_R^2", 1.0 - 2.0 * pu[:, 1] / (t.var(1) + 1e-8), None)  # ppo.py:524-527
-    _ref_log(want, "losses/advantages", adv, None)                                     # ppo.py:523 (raw array)
+    _ref_log(want, "losses/advantages", adv, None)       # ppo.py:523: the array whose E[a], E[a^2] columns 7 / 8 hold
     _ref_log(want, "env", {"speed": eng.env_metrics["env"]["speed"].numpy(),
                            "sub": {"alive": eng.env_metrics["env"]["sub"]["alive"].numpy()}}, None)
     _ref_log(want, "rollout_batch/reward", eng.reward.numpy(), None)
@@ -92,7 +92,7 @@ def test_iteration_metrics_percentile_mode_and_grad_norm():
     want["rollout_batch/done_rate"] = eng.done.numpy().astype(bool).mean()
     want["rollout_batch/truncation_rate"] = eng.trunc.numpy().astype(bool).mean()
     _ref_log(want, "weights", eng.net.arena.numpy()[eng.net.param_mask.numpy() != 0], pct)
-    assert np.array_equal(m.pop("grad_norm"), pu[:, 3])                              # ppo.py:313-315: one per update
+    _ref_log(want, "grad_norm", pu[:, 3], pct)         # ppo.py:313-315: one scalar per update, logged via _log_metric
     assert set(m) == set(want), set(m) ^ set(want)
     for k, v in want.items():
         assert np.allclose(np.float64(m[k]), v, rtol=2e-5, atol=2e-6), (k, m[k], v)

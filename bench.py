@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: PPO samples/sec (rollout policy + GAE + update) on the synthetic env.
 
-    python bench.py --gpus N --steps K --warmup W            # this build (CUDA engine)
-    python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle restatement)
+    python bench.py --gpus N --steps K --warmup W [--config mlp|cartpole_shapes|recurrent|dict]
+    python bench.py --impl reference --steps K --warmup W [--config ...]
 
-A "step" is one full PPO iteration of BASELINE.json configs[1] on each GPU: fused 32-step rollout
-of 4096 envs (obs 64, act 8, actor 4x64, critic 2x256, normalize_obs), permutation indices,
-4 epochs x 8 minibatches of forward / GAE / loss / backward / Adam, Normalizer statistics.
+A "step" is one full PPO iteration on each GPU: T-step rollout of n_envs envs, permutation indices,
+E epochs x M minibatches of forward / GAE / loss / backward / Adam, Normalizer statistics.
+--config selects the BASELINE.json configuration (default `mlp` = configs[1], the one the metric is
+quoted on; `cartpole_shapes` = configs[0] shapes on the synthetic env, `recurrent` = configs[2],
+`dict` = configs[3]; configs[4] is `mlp` at --gpus 8).
 `value` is device-timed (CUDA events) whole-job samples/sec with everything resident in HBM;
 `e2e` is the same metric through the public `ppo_step` API including the per-iteration
-host->device key block, the device->host metrics read and the host sync (the reference's
-`throughput/train_sps` definition, ppo.py:191-214).
+host->device block (PRNG keys + hyper-parameters, pinned), the device->host metrics read and the
+host sync (the reference's `throughput/train_sps` definition, ppo.py:191-214).
+--impl reference: the real reference (nnx_ppo on the JAX CPU build) when `jax`, `flax`, `optax` and
+`nnx_ppo` are importable (also from baseline/_ref); otherwise the NumPy restatement (oracle/), kind
+"port".
 """
 from __future__ import annotations
 
@@ -25,9 +30,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(obs=64, act=8, actor=[64] * 4, critic=[256] * 2, n_envs=4096, T=32, E=4, M=8,
-           max_len=64, term_thresh16=512, seed=17, net_seed=0)
-WORKLOAD = "configs[1]: synthetic env obs=64 act=8, MLP actor 4x64 / critic 2x256, n_envs=4096/GPU, rollout_length=32, 4 epochs x 8 minibatches"
+CONFIGS = {
+    "mlp": dict(obs=64, act=8, actor=[64] * 4, critic=[256] * 2, n_envs=4096, T=32, E=4, M=8,
+                workload="configs[1]: synthetic env obs=64 act=8, MLP actor 4x64 / critic 2x256, n_envs=4096/GPU, "
+                         "rollout_length=32, 4 epochs x 8 minibatches"),
+    "cartpole_shapes": dict(obs=5, act=1, actor=[64] * 4, critic=[256] * 2, n_envs=1024, T=30, E=4, M=4,
+                            workload="configs[0] shapes (CartpoleBalance: obs=5 act=1) on the synthetic env, MLP actor 4x64 / "
+                                     "critic 2x256, n_envs=1024/GPU, rollout_length=30, 4 epochs x 4 minibatches (MJX absent)"),
+    "recurrent": dict(obs=64, act=8, pre=64, hidden=256, critic=[256] * 2, n_envs=4096, T=32, E=4, M=8,
+                      workload="configs[2]: recurrent actor Dense(64) -> LSTM(256) -> Dense (the reference has an LSTM, no GRU), "
+                               "MLP critic 2x256, carry reset on done, carry replay across epochs, n_envs=4096/GPU, "
+                               "rollout_length=32, 4 epochs x 8 minibatches"),
+    "dict": dict(obs=768, act=21, obs_sizes={"proprio": 256, "target": 512}, enc={"proprio": [128, 64], "target": [128, 64]},
+                 actor=[256, 256], critic=[256, 256], n_envs=8192, T=32, E=4, M=8,
+                 workload="configs[3]: dict observations {proprio 256, target 512} -> per-key encoders 128-64 -> trunk 2x256, "
+                          "act=21, n_envs=8192/GPU, rollout_length=32, 4 epochs x 8 minibatches"),
+}
+ENV_KW = dict(max_len=64, term_thresh16=512)
+SEED, NET_SEED = 17, 0
+METRIC = "PPO samples/sec (rollout policy + GAE + update)"
 
 
 def _peaks():
@@ -38,14 +59,30 @@ def _peaks():
     return 6650.0, 1590.0, "fallback"
 
 
-def _p_mm(cfg):
-    a = [cfg["obs"]] + cfg["actor"] + [2 * cfg["act"]]
-    c = [cfg["obs"]] + cfg["critic"] + [1]
-    pa = sum(x * y for x, y in zip(a[:-1], a[1:]))
-    pc = sum(x * y for x, y in zip(c[:-1], c[1:]))
-    pa_dx = sum(x * y for x, y in zip(a[1:-1], a[2:]))
-    pc_dx = sum(x * y for x, y in zip(c[1:-1], c[2:]))
-    return pa, pc, pa_dx, pc_dx
+def _chain_mm(sizes):
+    return sum(x * y for x, y in zip(sizes[:-1], sizes[1:]))
+
+
+def _flops(name, cfg, mb):
+    """Algorithmic FLOPs per launch of the three GEMM stages of one update (real parameters only: the
+    structural zeros of the block-diagonal encoder layers are not counted)."""
+    T = cfg["T"]
+    R, Rv = T * mb, (T + 1) * mb
+    if name == "dict":
+        def tower(trunk, out):
+            enc = sum(_chain_mm([cfg["obs_sizes"][k]] + cfg["enc"][k]) for k in cfg["obs_sizes"])
+            enc_first = sum(cfg["obs_sizes"][k] * cfg["enc"][k][0] for k in cfg["obs_sizes"])
+            width = sum(cfg["enc"][k][-1] for k in cfg["obs_sizes"])
+            tr = _chain_mm([width] + trunk + [out])
+            return enc + tr, enc + tr - enc_first
+        pa, pa_dx = tower(cfg["actor"], 2 * cfg["act"])
+        pc, pc_dx = tower(cfg["critic"], 1)
+    else:
+        a = [cfg["obs"]] + cfg["actor"] + [2 * cfg["act"]]
+        c = [cfg["obs"]] + cfg["critic"] + [1]
+        pa, pc = _chain_mm(a), _chain_mm(c)
+        pa_dx, pc_dx = _chain_mm(a[1:]), _chain_mm(c[1:])
+    return {"fwd": 2.0 * (pa * R + pc * Rv), "bwd_dx": 2.0 * (pa_dx + pc_dx) * R, "bwd_dw": 2.0 * (pa + pc) * R}
 
 
 class ClockSampler:
@@ -90,52 +127,186 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+# ---------------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------------
+def _oracle_runner(name, cfg, B):
+    """(step_fn, label) for the NumPy restatement of `name` on B envs per step."""
+    from oracle import env as oenv, nets as onets, ppo as oppo
+    oe = oenv.SyntheticEnv(cfg["obs"], cfg["act"], **ENV_KW)
+    kw = dict(n_epochs=cfg["E"], n_minibatches=cfg["M"])
+    if name == "recurrent":
+        from oracle import recurrent as orec
+        onet = orec.make_recurrent_actor_critic(cfg["obs"], cfg["act"], [cfg["pre"]], cfg["hidden"], [], cfg["critic"], seed=NET_SEED)
+        st = [orec.new_training_state(oe, onet, B, SEED)]
+
+        def step():
+            st[0], m = orec.ppo_step(oe, st[0], B, cfg["T"], **kw)
+            return m
+        return step
+    if name == "dict":
+        from oracle import dictnet
+        onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], cfg["act"], cfg["enc"], cfg["actor"], cfg["critic"], seed=NET_SEED)
+    else:
+        onet = onets.make_mlp_actor_critic(cfg["obs"], cfg["act"], cfg["actor"], cfg["critic"], seed=NET_SEED)
+    st = [oppo.new_training_state(oe, onet, B, SEED)]
+
+    def step():
+        st[0], m = oppo.ppo_step(oe, st[0], B, cfg["T"], **kw)
+        return m
+    return step
+
+
+def _try_import_reference():
+    """jax + flax + optax + nnx_ppo importable (also from baseline/_ref)?  Returns the modules or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        import jax  # noqa: F401
+        import flax  # noqa: F401
+        import optax  # noqa: F401
+        from nnx_ppo.algorithms import ppo as rppo  # noqa: F401
+        return True
+    except Exception:
+        return None
+
+
+def _jax_reference_runner(name, cfg, B):
+    """The UNMODIFIED reference (`nnx_ppo.algorithms.ppo.ppo_step` under nnx.jit) on the synthetic env of
+    SURVEY.md section 8(d) restated as a JAX env.  MLP configs only (the reference factory)."""
+    import jax
+    import jax.numpy as jp
+    from flax import nnx
+    from nnx_ppo.algorithms import ppo as rppo
+    from nnx_ppo.algorithms.types import LoggingLevel
+    from nnx_ppo.jax_dataclass import JaxDataclass
+    from nnx_ppo.networks import factories
+    import dataclasses as dc
+    from oracle import env as oenv
+    if name not in ("mlp", "cartpole_shapes"):
+        raise NotImplementedError("reference arm on JAX: MLP configs only")
+    O, A = cfg["obs"], cfg["act"]
+    Wo_np, Wa_np = oenv.make_env_weights(O, A, 0)
+    Wo, Wa = jp.asarray(Wo_np), jp.asarray(Wa_np)
+    max_len, thr = ENV_KW["max_len"], ENV_KW["term_thresh16"]
+
+    @dc.dataclass
+    class S(JaxDataclass):
+        obs: jax.Array
+        reward: jax.Array
+        done: jax.Array
+        info: dict
+        metrics: dict
+
+    class Env:
+        def reset(self, rng):
+            k_base, k_cnt = jax.random.split(rng)
+            kc = jax.random.key_data(k_cnt)
+            return S(jax.random.normal(k_base, (O,)), jp.float32(0.0), jp.float32(0.0),
+                     {"step_counter": jax.random.randint(k_cnt, (), 0, max_len // 2),
+                      "term_state": (kc[0] ^ kc[1]).astype(jp.uint32), "truncated": jp.array(False)}, {})
+
+        def step(self, s, a):
+            obs = jp.tanh(s.obs @ Wo + a @ Wa)
+            cnt = s.info["step_counter"] + 1
+            term = s.info["term_state"] * jp.uint32(1664525) + jp.uint32(1013904223)
+            truncated = cnt >= max_len
+            done = ((term >> 16) < thr) | truncated
+            return S(obs, -jp.mean(obs * obs), done.astype(jp.float32),
+                     {"step_counter": cnt, "term_state": term, "truncated": truncated}, {})
+
+    env = Env()
+    nets = factories.make_mlp_actor_critic(O, A, cfg["actor"], cfg["critic"], nnx.Rngs(NET_SEED))
+    st = [rppo.new_training_state(env, nets, B, SEED)]
+    step_jit = nnx.jit(rppo.ppo_step, static_argnums=(0, 2, 3, 6, 7, 8, 9, 10, 11, 12, 13))
+
+    def step():
+        st[0], m = step_jit(env, st[0], B, cfg["T"], 0.95, 0.99, 0.2, True, False, cfg["E"], cfg["M"], 1.0,
+                            LoggingLevel.LOSSES, None)
+        int(st[0].steps_taken)                       # the reference's per-iteration host sync (ppo.py:209)
+        return m
+    return step
+
+
 def run_reference(args):
-    """CPU arm: the reference's algorithm for this path on the host cores.  The reference itself
-    (JAX/flax/optax) cannot be installed in this image, so this times the NumPy restatement
-    (oracle/), kind="port", on a bounded sample of the same workload: 512 of the 4096 envs
-    (same network, T, epochs and minibatch count; minibatch = 64 envs)."""
+    """CPU arm on rank 0: the reference's own implementation when importable, else the oracle port, on a
+    bounded sample of the workload (B envs of n_envs per step, everything else as configured), with all
+    the host threads BLAS / XLA will use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-    from oracle import env as oenv, nets as onets, ppo as oppo
-    B = args.ref_envs
-    cfg = CFG
-    oe = oenv.SyntheticEnv(cfg["obs"], cfg["act"], cfg["max_len"], cfg["term_thresh16"])
-    onet = onets.make_mlp_actor_critic(cfg["obs"], cfg["act"], cfg["actor"], cfg["critic"], seed=cfg["net_seed"])
-    ots = oppo.new_training_state(oe, onet, B, cfg["seed"])
-    for _ in range(args.warmup):
-        ots, _ = oppo.ppo_step(oe, ots, B, cfg["T"], n_epochs=cfg["E"], n_minibatches=cfg["M"])
+    cores = os.cpu_count() or 1
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):   # torchrun pins these to 1
+        os.environ[v] = str(cores)
+    name, cfg = args.config, CONFIGS[args.config]
+    B = min(args.ref_envs, cfg["n_envs"])
+    kind, step = "port", None
+    if _try_import_reference():
+        try:
+            step = _jax_reference_runner(name, cfg, B)
+            kind = "reference"
+        except Exception as e:                               # noqa: BLE001
+            sys.stderr.write(f"[bench] reference on JAX unavailable for this config ({e}); using the NumPy port\n")
+    if step is None:
+        step = _oracle_runner(name, cfg, B)
+    for _ in range(max(args.warmup, 1)):
+        step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ots, m = oppo.ppo_step(oe, ots, B, cfg["T"], n_epochs=cfg["E"], n_minibatches=cfg["M"])
+        step()
     dt = time.perf_counter() - t0
     sps = B * cfg["T"] * args.steps / dt
-    cores = os.cpu_count() or 1
-    sample = f"{B} of {cfg['n_envs']} envs per step, full T/epochs/minibatch count, NumPy float32 (BLAS threads = host default)"
-    line = {"impl": "reference", "metric": "PPO samples/sec (rollout policy + GAE + update)", "value": sps,
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "reference_arm_sample": sample},
-            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+    sample = (f"{B} of {cfg['n_envs']} envs per step, full T / epochs / minibatch count, "
+              + ("nnx_ppo.ppo_step under nnx.jit on the JAX CPU build" if kind == "reference"
+                 else "NumPy float32 restatement (oracle/), BLAS threads = host cores"))
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "reference_arm_sample": sample},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "reference (JAX) not installable here: NumPy restatement of the same iteration, parity unpinned beyond the reference's KATs"}
+            "gpu_launches": 0}
+    if kind == "port":
+        line["note"] = ("reference (JAX / flax / optax) not importable here: NumPy restatement of the same iteration; "
+                        "pinned by the reference's GAE / Normalizer KATs, the rest parity-unpinned (DESIGN.md section 4)")
     print(json.dumps(line), flush=True)
 
 
-def time_stages(eng, ts_env_state, lib, _lib, torch):
-    """Per-stage CUDA-event timing of the 32 updates of one iteration (eager launches on the
-    current stream).  Returns {stage: total_ms} and leaves the training state consistent."""
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def build_workload(name, cfg):
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks import factories
+    env = SyntheticEnv(cfg["obs"], cfg["act"], **ENV_KW)
+    if name == "recurrent":
+        nets = factories.make_recurrent_actor_critic(cfg["obs"], cfg["act"], cfg["pre"], cfg["hidden"], cfg["critic"], Rngs(NET_SEED))
+    elif name == "dict":
+        nets = factories.make_dict_actor_critic(cfg["obs_sizes"], cfg["act"], cfg["enc"], cfg["actor"], cfg["critic"], Rngs(NET_SEED))
+    else:
+        nets = factories.make_mlp_actor_critic(cfg["obs"], cfg["act"], cfg["actor"], cfg["critic"], Rngs(NET_SEED))
+    return env, nets
+
+
+def time_stages(eng, ts_env_state, lib, _lib, torch, local_only=False):
+    """Per-stage CUDA-event timing of the E*M updates of one iteration (eager launches on the current
+    stream).  `local_only`: the same launches without the peer exchange (world-size-1 arithmetic on this
+    rank's shard), so that the difference is what the cross-GPU synchronisation costs."""
     net = eng.net
     T, B, mb = eng.T, eng.B, eng.mb
     stages = [("fwd", _lib.STAGE_FWD), ("gae", _lib.STAGE_GAE), ("loss", _lib.STAGE_LOSS),
-              ("bwd_dx", _lib.STAGE_BWD_DX), ("bwd_dw", _lib.STAGE_BWD_DW), ("red", _lib.STAGE_RED),
-              ("adam", _lib.STAGE_ADAM)]
+              ("bwd_dx", _lib.STAGE_BWD_DX), ("bwd_dw", _lib.STAGE_BWD_DW), ("red_adam", _lib.STAGE_RED | _lib.STAGE_ADAM)]
     tot = {k: 0.0 for k, _ in stages}
     s = _lib.current_stream()
+    saved = None
+    if local_only:
+        saved = (eng.hp.world_size, [b.comm for b in eng.bufs])
+        eng.hp.world_size = 1
+        for b in eng.bufs:
+            b.comm = 0
     evs = []
     for u in range(eng.n_updates):
         off = 2 * T + u * 2 * (T + 1)
@@ -148,22 +319,27 @@ def time_stages(eng, ts_env_state, lib, _lib, torch):
             row.append((name, e0, e1))
         evs.append(row)
     torch.cuda.synchronize()
+    if saved is not None:
+        eng.hp.world_size = saved[0]
+        for b, c in zip(eng.bufs, saved[1]):
+            b.comm = c
     for row in evs:
         for name, e0, e1 in row:
             tot[name] += e0.elapsed_time(e1)
-    # the rollout launch alone, on a scratch copy of the env state (sampler counts are not advanced, so
-    # the training state is untouched); median of 5
-    scratch = type(ts_env_state)(ts_env_state.obs.clone(), ts_env_state.step_counter.clone(),
-                                 ts_env_state.term_state.clone())
-    times = []
-    for _ in range(5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        eng._enqueue_rollout(scratch)
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    tot["rollout"] = sorted(times)[2]
+    if ts_env_state is not None and not local_only:
+        # the rollout launch alone, on a scratch copy of the env state (sampler counts are not advanced, so
+        # the training state is untouched); median of 5
+        scratch = type(ts_env_state)(ts_env_state.obs.clone(), ts_env_state.step_counter.clone(),
+                                     ts_env_state.term_state.clone())
+        times = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng._enqueue_rollout(scratch)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        tot["rollout"] = sorted(times)[2]
     return tot
 
 
@@ -185,16 +361,18 @@ def run_own(args):
         ge.build()
     if world > 1:
         dist.barrier()
-    from nnx_ppo_b200 import Rngs, _lib, prng
+    from nnx_ppo_b200 import _lib, prng
     from nnx_ppo_b200.algorithms import ppo
-    from nnx_ppo_b200.envs import SyntheticEnv
-    from nnx_ppo_b200.networks.factories import make_mlp_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
     lib = _lib.load()
-    cfg = CFG
-    env = SyntheticEnv(cfg["obs"], cfg["act"], cfg["max_len"], cfg["term_thresh16"])
-    nets = make_mlp_actor_critic(cfg["obs"], cfg["act"], cfg["actor"], cfg["critic"], Rngs(cfg["net_seed"]))
-    ts = ppo.new_training_state(env, nets, cfg["n_envs"], cfg["seed"])
+    name, cfg = args.config, CONFIGS[args.config]
+    env, nets = build_workload(name, cfg)
+    ts = ppo.new_training_state(env, nets, cfg["n_envs"], SEED)
     hyper = (cfg["n_envs"], cfg["T"], 0.95, 0.99, 0.2, True, False, cfg["E"], cfg["M"])
+    net = compile_network(nets)
+    recurrent = bool(net.recurrent)
+    if recurrent and world > 1:
+        raise SystemExit("bench.py: the recurrent configuration is single-GPU")
 
     def barrier():
         if world > 1:
@@ -204,31 +382,35 @@ def run_own(args):
     # warm-up through the public API (iteration 0 eager, iteration 1 captures the CUDA graph)
     for _ in range(max(args.warmup, 3)):
         ts, metrics = ppo.ppo_step(env, ts, *hyper)
-    eng = ppo._engine_for(env, ts, cfg["n_envs"], cfg["T"], 0.95, 0.99, 0.2, True, cfg["E"], cfg["M"], 1.0)
+    eng = next(reversed(net.engines.values()))
     samples_per_step = cfg["n_envs"] * cfg["T"] * world
 
     # ---- device-timed value: K iterations back to back, inputs resident in HBM ----
     clocks = ClockSampler(local) if rank == 0 else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    key = ts.rng_key
     e0.record()
-    for _ in range(args.steps):
-        rk, nk = prng.split(key)
-        eng.step(ts.env_states, rk, nk, fetch_metrics=False)
-        key = nk
+    if recurrent:
+        for _ in range(args.steps):                  # no device-only entry point on this path: the public call
+            ts, metrics = ppo.ppo_step(env, ts, *hyper)
+    else:
+        key = ts.rng_key
+        for _ in range(args.steps):
+            rk, nk = prng.split(key)
+            eng.step(ts.env_states, rk, nk, fetch_metrics=False)
+            key = nk
+        ts = ts.replace(rng_key=key, steps_taken=np.float32(ts.steps_taken + args.steps * cfg["n_envs"] * cfg["T"]))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clock_info = clocks.stop() if clocks is not None else None
-    ts = ts.replace(rng_key=key, steps_taken=np.float32(ts.steps_taken + args.steps * cfg["n_envs"] * cfg["T"]))
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     value = samples_per_step * args.steps / (ms / 1e3)
 
-    # ---- e2e: public API, per-step H2D (pinned key block) + D2H (metrics) + host sync ----
+    # ---- e2e: public API, per-step H2D (pinned key + hyper-parameter block) + D2H (metrics) + host sync ----
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -240,29 +422,29 @@ def run_own(args):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = samples_per_step * args.steps / float(t_e.item())
 
-    line = None
-    if rank == 0:
-        hbm, tf_peak, which = _peaks()
-        line = {"metric": "PPO samples/sec (rollout policy + GAE + update)", "value": value, "unit": "samples/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_envs": cfg["n_envs"] * world, "parallelism": f"dp{world} (env-sharded)",
-                           "l2": "no flush: every update streams a ~150 MB working set (> 126 MB L2) that the iteration itself rewrites",
-                           "collectives": ("none" if world == 1 else
-                                           ("peer memory: epoch flags + P2P loads inside the GAE / loss / Adam kernels"
-                                            if eng.p2p else "NCCL all-reduce x2 per update")),
-                           "cuda_graph": eng.graph is not None, "done_rate": float(eng.done.float().mean()),
-                           "truncation_rate": float(eng.trunc.float().mean())},
-                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(),
-                        "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "api": "ppo.ppo_step",
-                        "ms_per_step": 1e3 * float(t_e.item()) / args.steps},
-                "gpu_launches": eng.kernel_launches_per_iter * args.steps,
-                "clocks": clock_info,
-                "final_metrics": {k: float(v) for k, v in metrics.items()}}
-    # ---- roofline of the dominant kernel + cpu baseline: N = 1 only ----
-    if world == 1 and not args.quick:
-        # FFMA peak probe (fp32 CUDA-core ceiling; not in MEASURED_PEAKS.json)
+    hbm, tf_peak, which = _peaks()
+    line = {"metric": METRIC, "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "global_envs": cfg["n_envs"] * world, "parallelism": f"dp{world} (env-sharded)",
+                       "l2": "no flush: every update streams a > 100 MB working set (around / above the 126 MB L2) that the iteration itself rewrites",
+                       "collectives": ("none" if world == 1 else
+                                       ("peer memory: stores into every rank's comm buffer + per-block epoch flags inside the GAE / loss / Adam kernels"
+                                        if eng.p2p else "NCCL all-reduce x2 per update")),
+                       "rollout_critic": "off: the fused rollout does not evaluate the critic (training replays it, ppo.py:425-446; "
+                                         "value estimates are computed on request for logging)",
+                       "pdl": bool(lib.b200ppo_set_pdl(-1)),
+                       "cuda_graph": getattr(eng, "graph", None) is not None, "done_rate": float(eng.done.float().mean()),
+                       "truncation_rate": float(eng.trunc.float().mean())},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(),
+                    "d2h_bytes_per_step": eng.d2h_bytes_per_step(), "api": "ppo.ppo_step",
+                    "ms_per_step": 1e3 * float(t_e.item()) / args.steps},
+            "gpu_launches": (getattr(eng, "kernel_launches_per_iter", 0) or 0) * args.steps,
+            "clocks": clock_info,
+            "final_metrics": {k: float(v) for k, v in metrics.items()}}
+    # ---- roofline of the dominant kernel (every N); cpu baseline (N = 1) ----
+    if not args.quick and not recurrent:
         blocks, threads, iters = 148 * 8, 256, 20000
         sink = torch.zeros(blocks * threads, device="cuda")
         lib.b200ppo_ffma_peak(_lib.current_stream(), 1000, sink.data_ptr(), blocks, threads)
@@ -273,24 +455,31 @@ def run_own(args):
         f1.record()
         torch.cuda.synchronize()
         ffma_tf = blocks * threads * iters * 16 * 2 / (f0.elapsed_time(f1) * 1e-3) / 1e12
-        # per-stage timing needs a fresh rollout in the buffers: run one API iteration, then re-time
-        # its 32 updates stage by stage (this perturbs parameters once more; harmless for a bench)
+        # per-stage timing re-runs the E*M updates of the last rollout stage by stage (this perturbs the
+        # parameters once more; harmless for a bench).  All ranks do it in lock step.
+        barrier()
         stage_ms = time_stages(eng, ts.env_states, lib, _lib, torch)
-        eng.net.advance_rng(0)
-        pa, pc, pa_dx, pc_dx = _p_mm(cfg)
-        R, Rv, U = cfg["T"] * eng.mb, (cfg["T"] + 1) * eng.mb, eng.n_updates
-        flops = {"fwd": 2.0 * (pa * R + pc * Rv), "bwd_dx": 2.0 * (pa_dx + pc_dx) * R, "bwd_dw": 2.0 * (pa + pc) * R}
+        sync_us = None
+        if world > 1 and eng.p2p:
+            barrier()
+            local_ms = time_stages(eng, None, lib, _lib, torch, local_only=True)
+            sync_us = 1e3 * (sum(stage_ms[k] for k in local_ms) - sum(local_ms.values())) / eng.n_updates
+        barrier()
+        U = eng.n_updates
+        flops = _flops(name, cfg, eng.mb)
         dom = max(flops, key=lambda k: stage_ms[k])
         ach = flops[dom] * U / (stage_ms[dom] * 1e-3) / 1e12
         mode = int(lib.b200ppo_set_gemm_mode(-1))
         tc = mode != 0
         kname = {"fwd": "upd_fwd", "bwd_dx": "upd_bwd_dx", "bwd_dw": "upd_bwd_dw"}[dom] + ("_tc_kernel" if tc else "_kernel")
-        if tc and dom == "bwd_dw":
+        if tc and dom == "bwd_dw" and name != "dict":
             kname = "upd_bwd_dw_tc2_kernel"       # bulk-copy + shared-memory transpose variant (every layer <= 256 wide)
         traffic = None                            # dram bytes per launch from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(kname)
+        for tfile in ("r2_traffic.json", "r1_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tfile)
+            if name == "mlp" and os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(kname)
+                break
         line["roofline"] = {"bound": "tensor", "kernel": kname,
                             "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                             "traffic": traffic, "peak_source": f"{which} bf16 tensor (sustained)",
@@ -303,18 +492,19 @@ def run_own(args):
                             "ffma_peak_tflops": ffma_tf, "frac_of_ffma_peak": ach / ffma_tf,
                             "flop_per_launch": flops[dom], "launch_ms": stage_ms[dom] / U,
                             "stage_ms_per_iteration": stage_ms,
+                            "small_kernel_share": (stage_ms["gae"] + stage_ms["loss"] + stage_ms["red_adam"]) / (ms / args.steps),
                             "stage_tflops_algorithmic": {k: flops[k] * U / (stage_ms[k] * 1e-3) / 1e12 for k in flops}}
+        if sync_us is not None:
+            line["roofline"]["sync_us_per_update"] = sync_us
+    if world == 1 and not args.quick and rank == 0:
         # CPU baseline: the oracle on a bounded sample of the same workload
-        from oracle import env as oenv, nets as onets, ppo as oppo
-        Bs = args.ref_envs
-        oe = oenv.SyntheticEnv(cfg["obs"], cfg["act"], cfg["max_len"], cfg["term_thresh16"])
-        onet = onets.make_mlp_actor_critic(cfg["obs"], cfg["act"], cfg["actor"], cfg["critic"], seed=cfg["net_seed"])
-        ots = oppo.new_training_state(oe, onet, Bs, cfg["seed"])
-        ots, _ = oppo.ppo_step(oe, ots, Bs, cfg["T"], n_epochs=cfg["E"], n_minibatches=cfg["M"])
+        Bs = min(args.ref_envs, cfg["n_envs"])
+        step = _oracle_runner(name, cfg, Bs)
+        step()
         n_cpu = 0
         t0 = time.perf_counter()
-        while n_cpu < 3 or (time.perf_counter() - t0 < 10.0 and n_cpu < 40):
-            ots, _ = oppo.ppo_step(oe, ots, Bs, cfg["T"], n_epochs=cfg["E"], n_minibatches=cfg["M"])
+        while n_cpu < 2 or (time.perf_counter() - t0 < 10.0 and n_cpu < 40):
+            step()
             n_cpu += 1
         cdt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": Bs * cfg["T"] * n_cpu / cdt, "unit": "samples/s", "cores": os.cpu_count(),
@@ -339,6 +529,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="mlp", choices=sorted(CONFIGS))
     ap.add_argument("--ref-envs", type=int, default=512)
     ap.add_argument("--quick", action="store_true", help="skip the roofline stage timing and the CPU baseline (profiling runs)")
     args = ap.parse_args()

@@ -22,13 +22,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the B200 PPO kernels cannot be built")
 
 
+HASH_PATH = os.path.join(LIB_DIR, "libb200ppo.sha256")
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, flags): a prebuilt .so is
+    reused only when it was built from exactly these bytes, whatever the file times say (the snapshot
+    that travels to the GPU box does not preserve them)."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f)))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "b200ppo.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(NVCC_FLAGS + [os.environ.get("B200PPO_NVCC_EXTRA", "")]).encode())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
-        os.path.join(os.path.dirname(HERE), "include", "b200ppo.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return open(HASH_PATH).read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -54,6 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB_PATH
 
 

@@ -1,0 +1,184 @@
+"""Oracle-compared GPU tests at the REAL sizes of the BASELINE configs (round-1 review: the largest
+oracle-compared batch was 256 envs, the full sizes were only compared with themselves), the observation
+adapters on a device, the ``ppo_loss`` callable, and hyper-parameters as run-time data of one captured
+iteration graph.  The oracle needs 2 - 9 s per full-size iteration on the host cores."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from nnx_ppo_b200 import Rngs, _lib, prng as hprng                                 # noqa: E402
+from nnx_ppo_b200.algorithms import ppo, rollout                                   # noqa: E402
+from nnx_ppo_b200.algorithms.types import LoggingLevel                             # noqa: E402
+from nnx_ppo_b200.envs import SyntheticEnv                                         # noqa: E402
+from nnx_ppo_b200.networks.containers import Sequential                            # noqa: E402
+from nnx_ppo_b200.networks.factories import make_mlp_actor_critic                  # noqa: E402
+from nnx_ppo_b200.networks.plan import compile_network                             # noqa: E402
+from nnx_ppo_b200.networks.utils import Filter, Flattener                          # noqa: E402
+from oracle import env as oenv, ppo as oppo                                        # noqa: E402
+
+from test_gpu_parity import _PerStepEnv, _iterations, _pair, _single_update, dev   # noqa: E402,F401
+
+
+@pytest.mark.parametrize("cfg", [
+    # BASELINE configs[1]: synthetic env obs 64 / act 8, 4096 envs x 32 steps, 4 epochs x 8 minibatches
+    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=4096, T=32, E=4, M=8, iters=2, max_len=64, thresh=512),
+    # BASELINE configs[0] shapes (CartpoleBalance: obs 5, act 1), 1024 envs x 30 steps, PPOConfig defaults 4 x 4
+    dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=1024, T=30, E=4, M=4, iters=2, max_len=64, thresh=512)])
+def test_full_size_iterations_match_oracle(dev, cfg):
+    """Whole iterations through ppo.ppo_step (the second one from the captured CUDA graph) against
+    oracle.ppo.ppo_step at the bench size: indices / masks / counters bit-exact, losses and parameters to
+    the float32 tolerances of test_gpu_parity._iterations."""
+    _iterations(dev, cfg)
+
+
+@pytest.mark.parametrize("gemm", [0, 1])
+def test_full_size_dict_update_matches_oracle(dev, gemm):
+    """BASELINE configs[3] at full size: dict observations {proprio 256, target 512} through per-key
+    encoders (768-wide block layer: the > 256-input dW fallback kernel), act 21, 8192 envs x 32 steps,
+    minibatch 1024 envs = 32 768 rows: one update (forward, GAE, loss, backward, reduction, Adam) against
+    oracle/dictnet.py."""
+    _lib.load().b200ppo_set_gemm_mode(gemm)
+    try:
+        _single_update(dev, dict(O=768, A=21, B=8192, T=32, M=8, act="relu", clip=None, wd=None, ah=[256, 256],
+                                 ch=[256, 256], obs_sizes={"proprio": 256, "target": 512},
+                                 enc={"proprio": [128, 64], "target": [128, 64]}), 1.0)
+    finally:
+        _lib.load().b200ppo_set_gemm_mode(1)
+
+
+class _TreeObsEnv(_PerStepEnv):
+    """The synthetic env stepped from Python, handing out its observation as a nested dict with an
+    extra leaf the network does not use (what Filter / Flattener exist for, utils.py:65-165)."""
+
+    def __init__(self, env):
+        self._env = env
+
+    @staticmethod
+    def _tree(st):
+        st.info = dict(st.info, flat=st.obs)
+        st.obs = {"arm": {"proprio": st.obs[:, 5:].contiguous(), "junk": torch.zeros_like(st.obs[:, :2])},
+                  "head": st.obs[:, :5].contiguous()}
+        return st
+
+    def reset(self, keys):
+        return self._tree(self._env.reset(keys))
+
+    def step(self, s, a):
+        import dataclasses
+        flat = dataclasses.replace(s, obs=s.info["flat"])
+        return self._tree(self._env.step(flat, a))
+
+
+def test_observation_adapters_on_the_device(dev):
+    """Filter + Flattener in front of the network (plan compiler: leading adapters), nested-dict
+    observations through the per-step rollout incl. reset-on-done over the dict leaves, the update
+    kernels and the Normalizer statistics: bit-identical to the same network on the flat observation."""
+    kw = dict(max_len=16, term_thresh16=2000)
+    base = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    nets_t = Sequential([Filter({"h": "head", "p": ("arm", "proprio")}), Flattener(), *base.layers])
+    nets_f = make_mlp_actor_critic(12, 3, [16, 16], [16], Rngs(7))
+    env_t, env_f = _TreeObsEnv(SyntheticEnv(12, 3, **kw)), _PerStepEnv(SyntheticEnv(12, 3, **kw))
+    ts_t = ppo.new_training_state(env_t, nets_t, 64, 3)
+    ts_f = ppo.new_training_state(env_f, nets_f, 64, 3)
+    net_t, net_f = compile_network(nets_t), compile_network(nets_f)
+    assert len(net_t.obs_adapters) == 2 and net_t.normalizer is not None
+    args = (64, 8, 0.95, 0.99, 0.2, True, False, 2, 2)
+    for _ in range(3):
+        ts_t, m_t = ppo.ppo_step(env_t, ts_t, *args, logging_level=LoggingLevel.ALL)
+        ts_f, m_f = ppo.ppo_step(env_f, ts_f, *args, logging_level=LoggingLevel.ALL)
+    assert isinstance(ts_t.env_states.obs, dict) and ts_t.env_states.obs["arm"]["proprio"].shape == (64, 7)
+    assert torch.equal(net_t.arena, net_f.arena)
+    assert torch.equal(net_t.normalizer.mean._dev, net_f.normalizer.mean._dev)
+    assert net_t.rng_count == net_f.rng_count
+    eng_t, eng_f = (next(iter(n.engines.values())) for n in (net_t, net_f))
+    assert torch.equal(eng_t.obs, eng_f.obs) and torch.equal(eng_t.done, eng_f.done) and eng_t.done.any()
+    # the sampler sits two Sequential positions further down: net/3/... instead of net/1/...
+    assert m_t["net/3/action/3/mu/mean"] == m_f["net/1/action/3/mu/mean"]
+    for k in ("losses/actor/mean", "losses/critic/mean", "rollout_batch/reward/mean", "weights/std"):
+        assert m_t[k] == m_f[k], k
+    # a single call through the adapters: same outputs as the flat call, reference-shaped pytrees
+    st = env_t.reset(rollout.split_keys_device(hprng.key(1), 10, dev))
+    out_t = nets_t(nets_t.initialize_state(10), st.obs)
+    net_t.sampler.rng.count -= 2
+    net_f.sampler.rng.count = net_t.sampler.rng.count
+    out_f = nets_f(nets_f.initialize_state(10), st.info["flat"])
+    assert torch.equal(out_t.output.actions, out_f.output.actions)
+    assert out_t.rollout_extras[:2] == [None, None] and torch.equal(out_t.rollout_extras[2], st.info["flat"])
+
+
+def test_ppo_loss_callable_matches_oracle(dev):
+    """ppo.ppo_loss (reference ppo.py:397-408 signature) on a minibatch Transition: total loss, loss
+    metrics and, with return_grads, the flat gradient against oracle.ppo.ppo_loss_and_grads."""
+    O, A, B, T = 24, 5, 64, 9
+    nets, onet = _pair(O, A, [48, 40], [72], 5, "tanh")
+    env, oe = SyntheticEnv(O, A, max_len=12, term_thresh16=2500), oenv.SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
+    ts = ppo.new_training_state(env, nets, B, 3)
+    ots = oppo.new_training_state(oe, onet, B, 3)
+    net = compile_network(nets)
+    reset_key, _ = hprng.split(ts.rng_key)
+    _, _, tr = rollout.unroll_env(env, ts.env_states, nets, ts.network_states, T, reset_key)
+    _, oro = oppo.unroll_env(oe, ots.env_state, onet, T, np.array(reset_key, np.uint32))
+    assert np.array_equal(tr.done.cpu().numpy(), oro.done)
+    inds = np.arange(B, dtype=np.int32)[::-1].copy()[:32]          # any env subset, any order
+    ti = torch.from_numpy(inds.astype(np.int64)).to(dev)
+    sub = lambda x: x[:, ti]
+    extras = tr.rollout_extras
+    mb = type(tr)(obs=sub(tr.obs), network_output=type(tr.network_output)(sub(tr.network_output.actions),
+                  sub(tr.network_output.loglikelihoods), sub(tr.network_output.value_estimates)),
+                  rewards=sub(tr.rewards), done=sub(tr.done), truncated=sub(tr.truncated), next_obs=tr.next_obs[ti],
+                  metrics={}, rollout_extras=[sub(extras[0]), {"action": [None] * 3 + [sub(extras[1]["action"][-1])],
+                                                               "value": extras[1]["value"]}])
+    assert net.rng_count == onet.rng_count
+    base = onet.rng_count
+    o_total, om, o_grads = oppo.ppo_loss_and_grads(onet, oro, inds, base)
+    lvl = LoggingLevel.LOSSES | LoggingLevel.ACTOR_EXTRA | LoggingLevel.CRITIC_EXTRA
+    total, lm, grads = ppo.ppo_loss(nets, nets.initialize_state(32), mb, 0.2, True, False, 0.99, 0.95, 1.0, lvl,
+                                    return_grads=True)
+    assert net.rng_count == base + 2 * (T + 1)                    # one network call per step + the bootstrap call
+    assert abs(total - o_total) < 2e-5 * max(1.0, abs(o_total))
+    for k in ("losses/actor", "losses/critic", "losses/regularization", "losses/clipping_fraction"):
+        assert abs(lm[k] - om[k]) < 2e-5 * max(1.0, abs(om[k])), k
+    an = (om["adv"] - om["adv_mean"]) / (om["adv_std"] + 1e-8)     # ppo.py:477-480: the normalised tensor is logged
+    assert np.allclose(lm["losses/advantages"].cpu().numpy(), an, rtol=1e-4, atol=2e-4)
+    assert abs(lm["losses/critic_R^2"] - om["losses/critic_R^2"]) < 2e-3 * max(1.0, abs(om["losses/critic_R^2"]))
+    assert np.abs(grads - o_grads).max() < 2e-4 * np.abs(o_grads).max()
+    total2, lm2 = ppo.ppo_loss(nets, nets.initialize_state(32), mb, 0.2, True, False, 0.99, 0.95, 1.0, LoggingLevel.NONE)
+    assert lm2 == {} and np.isfinite(total2) and total2 != total   # fresh entropy noise: the stream moved on
+
+
+def test_hyper_parameters_are_runtime_data_of_one_graph(dev):
+    """100 distinct learning rates / discount factors: ONE engine, ONE captured graph (the reference traces
+    gae_lambda / discounting_factor, ppo.py:105), and the result equals the oracle driven by the same
+    schedule."""
+    O, A, B, T, E, M = 12, 3, 64, 8, 2, 2
+    nets, onet = _pair(O, A, [16, 16], [16], 7)
+    env, oe = SyntheticEnv(O, A, max_len=16, term_thresh16=2000), oenv.SyntheticEnv(O, A, max_len=16, term_thresh16=2000)
+    ts = ppo.new_training_state(env, nets, B, 3)
+    ots = oppo.new_training_state(oe, onet, B, 3)
+    net = compile_network(nets)
+    graphs = set()
+    for it in range(100):
+        lr = 1e-4 * (1.0 + 0.05 * it)
+        gamma, lam, clip = 0.99 - 0.0005 * it, 0.95 - 0.001 * it, 0.2 + 0.001 * it
+        ts.optimizer.learning_rate = lr
+        ts, m = ppo.ppo_step(env, ts, B, T, lam, gamma, clip, True, False, E, M)
+        assert len(net.engines) == 1
+        eng = next(iter(net.engines.values()))
+        if eng.graph is not None:
+            graphs.add(id(eng.graph))
+        if it < 6:                                                 # the oracle follows the same schedule
+            ots, om = oppo.ppo_step(oe, ots, B, T, gae_lambda=lam, gamma=gamma, clip_range=clip, lr=lr,
+                                    n_epochs=E, n_minibatches=M)
+            for k in ("losses/actor/mean", "losses/critic/mean"):
+                assert abs(m[k] - om[k]) < 2e-4 * max(1.0, abs(om[k])), (it, k, m[k], om[k])
+            d = np.abs(net.params_logical() - onet.flat_params())
+            assert d.max() < 2e-3 * lr * 1e4 and d.mean() < 4e-6, (it, d.max(), d.mean())
+    assert len(graphs) == 1 and all(np.isfinite(v) for v in m.values())
+    # engines are keyed on shapes: another rollout length builds a second one, the cache stays bounded
+    from nnx_ppo_b200.algorithms import engine as engine_mod
+    for T2 in (4, 5, 6, 7, 9):
+        ts, _m = ppo.ppo_step(env, ts, B, T2, 0.95, 0.99, 0.2, True, False, E, M)
+    assert len(net.engines) == engine_mod.MAX_CACHED_ENGINES

@@ -301,7 +301,14 @@ def test_single_update_matches_oracle(dev, cfg, gemm):
 
 def _single_update(dev, cfg, loose):
     O, A, B, T, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["M"]
-    nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
+    if "obs_sizes" in cfg:          # dict observations -> per-key encoders (Concat) -> trunk
+        from nnx_ppo_b200.networks.factories import make_dict_actor_critic
+        from oracle import dictnet
+        nets = make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], Rngs(5), activation=cfg["act"])
+        onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], seed=5,
+                                              activation=cfg["act"])
+    else:
+        nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
     env = SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
     oe = oenv.SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
     ts = ppo.new_training_state(env, nets, B, 3, learning_rate=1e-3, gradient_clipping=cfg["clip"],
@@ -353,7 +360,11 @@ def _single_update(dev, cfg, loose):
     assert abs(met[4] - m["losses/clipping_fraction"]) <= (2.0 / R) * loose + 1e-7      # a borderline ratio may flip
     r2 = 1.0 - 2.0 * met[1] / (max(met[6] - met[5] ** 2, 0.0) + 1e-8)
     assert abs(r2 - m["losses/critic_R^2"]) < 2e-3 * loose * max(1.0, abs(m["losses/critic_R^2"]))
-    assert abs(met[7] - m["adv_mean"]) < 1e-5 * loose
+    # [7], [8]: moments of the NORMALISED advantages (ppo.py:477-480 reassigns the name before it is logged at
+    # :523); [9], [10]: the normalisation constants
+    an = (m["adv"] - m["adv_mean"]) / (m["adv_std"] + 1e-8)
+    assert abs(met[7] - an.mean()) < 2e-5 * loose and abs(met[8] - (an.astype(np.float64) ** 2).mean()) < 2e-4 * loose
+    assert abs(met[9] - m["adv_mean"]) < 1e-5 * loose and abs(met[10] - (m["adv_std"] + 1e-8)) < 1e-4 * loose
     if loose > 1.0:
         # plain TF32 is not fp32 parity (clip decisions can flip): only require a sane gradient
         got_g = net.params_logical(eng.grad)
@@ -437,8 +448,9 @@ def _iterations(dev, cfg):
         onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], seed=0)
     else:
         nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
-    env = SyntheticEnv(O, A, max_len=48, term_thresh16=700)
-    oe = oenv.SyntheticEnv(O, A, max_len=48, term_thresh16=700)
+    ekw = dict(max_len=cfg.get("max_len", 48), term_thresh16=cfg.get("thresh", 700))
+    env = SyntheticEnv(O, A, **ekw)
+    oe = oenv.SyntheticEnv(O, A, **ekw)
     ts = ppo.new_training_state(env, nets, B, 17)
     ots = _oracle_state(oe, onet, B, 17)
     net = compile_network(nets)
@@ -470,7 +482,7 @@ def _iterations(dev, cfg):
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
         assert np.allclose(net.normalizer.M2.numpy(), onet.M2, rtol=2e-3)
         assert np.allclose(ts.env_states.obs.cpu().numpy(), ots.env_state.obs, rtol=1e-3, atol=1e-3)
-    assert eng.graph is not None            # iterations >= 2 ran from the captured CUDA graph
+    assert eng.graph is not None or cfg["iters"] < 2    # iterations >= 2 ran from the captured CUDA graph
 
 
 def test_adam_refreshes_split_weight_planes(dev, monkeypatch):
@@ -572,13 +584,27 @@ def test_logging_levels(dev):
     assert abs(m["rollout_batch/reward/mean"] - float(eng.reward.mean())) < 1e-6
     assert abs(m["rollout_batch/done_rate"] - float(eng.done.float().mean())) < 1e-7
     assert {"rollout_batch/action/std", "rollout_batch/truncation_rate", "loglikelihood/mean", "weights/std"} <= set(m)
-    assert m["grad_norm"].shape == (4,) and np.all(m["grad_norm"] > 0)
+    gn = eng.metrics[:, 3].cpu().numpy()                      # one scalar per update, logged through _log_metric
+    assert gn.shape == (4,) and np.all(gn > 0)
+    assert abs(m["grad_norm/mean"] - gn.mean()) < 1e-6 and abs(m["grad_norm/std"] - gn.std()) < 1e-6
     assert 0.0 <= m["losses/clipping_fraction/mean"] <= 1.0 and m["losses/critic_R^2/mean"] <= 1.0
-    assert m["losses/advantages/std"] > 0
+    # the logged advantages are the normalised ones (ppo.py:477-480, 523): mean 0, std 1 per update
+    assert abs(m["losses/advantages/mean"]) < 1e-4 and abs(m["losses/advantages/std"] - 1.0) < 1e-3
     ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2, logging_level=lvl,
                          logging_percentiles=(0, 50, 100))
     assert m["rollout_batch/reward/p0"] <= m["rollout_batch/reward/p50"] <= m["rollout_batch/reward/p100"]
-    assert "losses/actor/p50" in m and "weights/p100" in m
+    assert "losses/actor/p50" in m and "weights/p100" in m and "grad_norm/p50" in m
+    assert m["losses/advantages/p0"] < -0.5 and abs(m["losses/advantages/p50"]) < 0.5 < m["losses/advantages/p100"]
+    # the sampler's metrics (sampling_layers.py:111) under Transition.metrics["net"] (rollout.py:31-34)
+    ts, m = ppo.ppo_step(env, ts, 64, 8, 0.95, 0.99, 0.2, True, False, 2, 2,
+                         logging_level=LoggingLevel.LOSSES | LoggingLevel.TRAINING_ENV_METRICS)
+    base = "net/1/action/3"                                   # Sequential[1] = PPOAdapter, action Sequential[3] = sampler
+    assert {f"{base}/mu/mean", f"{base}/mu/std", f"{base}/sigma/mean", f"{base}/sigma/std"} <= set(m)
+    assert m[f"{base}/sigma/mean"] > 0.1                      # min_std
+    out = nets(nets.initialize_state(64), eng.obs[3])         # the per-step call reports the same tree
+    compile_network(nets).sampler.rng.count -= 2
+    mu = out.metrics[1]["action"][3]["mu"]
+    assert mu.shape == (64, 3) and torch.isfinite(mu).all()
 
 
 def test_train_ppo_api(dev):
@@ -783,7 +809,8 @@ def test_grad_norm_metric_without_clipping(dev):
         eng = next(iter(net.engines.values()))
         runs.append((net.arena.clone(), m, float(eng.grad.double().norm())))
     assert torch.equal(runs[0][0], runs[1][0])
-    assert "grad_norm" not in runs[0][1]
-    gn = runs[1][1]["grad_norm"]
+    assert "grad_norm/mean" not in runs[0][1]
+    assert runs[1][1]["grad_norm/mean"] > 0 and np.isfinite(runs[1][1]["grad_norm/std"])
+    gn = eng.metrics[:, 3].cpu().numpy()
     assert gn.shape == (4,) and np.all(gn > 0) and np.all(np.isfinite(gn))
     assert abs(gn[-1] - runs[1][2]) < 1e-5 * max(1.0, runs[1][2])

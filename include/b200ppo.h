@@ -348,8 +348,9 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
 /* Programmatic dependent launch between the kernels of b200ppo_update (each kernel's prologue overlaps *
- * its predecessor's tail; griddepcontrol.wait before the first dependent access): 1 = on (default),  *
- * 0 = plain stream order; also B200PPO_PDL=0|1.  Returns the previous setting; any other value only *
+ * its predecessor's tail; griddepcontrol.wait before the first dependent access): 1 = on, 0 = plain   *
+ * stream order (default: inside a captured graph the programmatic edges measured slower on B200);   *
+ * also B200PPO_PDL=0|1.  Returns the previous setting; any other value only *
  * queries.  Takes effect for launches (and graph captures) made afterwards.                         */
 int b200ppo_set_pdl(int on);
 /* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *

@@ -22,8 +22,9 @@ namespace b200ppo {
 // block in griddepcontrol.wait until the predecessor grid has completed and flushed.  Every kernel of
 // the chain executes launch_dependents first (so ITS successor can be scheduled as soon as all its own
 // CTAs are resident) and wait before its first dependent global access; completion stays transitive
-// because every grid waits.  Without the attribute both instructions are no-ops.  B200PPO_PDL=0 turns
-// the attribute off (plain stream order) for A/B timing.
+// because every grid waits.  Without the attribute both instructions are no-ops.  The attribute is OFF
+// unless B200PPO_PDL=1 / b200ppo_set_pdl(1): inside the captured iteration graph the programmatic edges
+// measured slower than plain kernel-to-kernel edges on B200 (profiles/r2_notes.md).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

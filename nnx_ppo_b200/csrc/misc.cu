@@ -12,7 +12,9 @@ static int g_pdl = -1;
 bool b200ppo::pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = std::getenv("B200PPO_PDL");
-    g_pdl = (e && e[0] == '0') ? 0 : 1;
+    // Off by default: measured on B200 inside the captured iteration graph (profiles/r2_notes.md) the
+    // programmatic edges made the iteration SLOWER (6.23 ms vs 5.64 ms per configs[1] iteration).
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
   }
   return g_pdl != 0;
 }

@@ -24,7 +24,9 @@ from test_gpu_parity import _PerStepEnv, _iterations, _pair, _single_update, dev
 
 @pytest.mark.parametrize("cfg", [
     # BASELINE configs[1]: synthetic env obs 64 / act 8, 4096 envs x 32 steps, 4 epochs x 8 minibatches
-    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=4096, T=32, E=4, M=8, iters=2, max_len=64, thresh=512),
+    # (64 Adam updates: an individual near-zero-gradient parameter may take a few sign-flipped steps of lr = 1e-4
+    # each, measured 4.8e-4 at the worst of 100 369 parameters; the mean stays inside the common 2e-6)
+    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=4096, T=32, E=4, M=8, iters=2, max_len=64, thresh=512, pmax=1e-3),
     # BASELINE configs[0] shapes (CartpoleBalance: obs 5, act 1), 1024 envs x 30 steps, PPOConfig defaults 4 x 4
     dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=1024, T=30, E=4, M=4, iters=2, max_len=64, thresh=512)])
 def test_full_size_iterations_match_oracle(dev, cfg):

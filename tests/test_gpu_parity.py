@@ -477,7 +477,7 @@ def _iterations(dev, cfg):
         p, po = net.params_logical(), onet.flat_params()
         # Adam moves each parameter by at most lr per update; rounding differences in tiny
         # gradients can flip individual steps, so compare against a few-steps budget
-        assert np.abs(p - po).max() < 1e-4 * 4, np.abs(p - po).max()
+        assert np.abs(p - po).max() < cfg.get("pmax", 1e-4 * 4), np.abs(p - po).max()
         assert np.mean(np.abs(p - po)) < 2e-6
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
         assert np.allclose(net.normalizer.M2.numpy(), onet.M2, rtol=2e-3)

@@ -214,6 +214,10 @@ typedef struct b200ppo_synth_env {
 int b200ppo_synth_reset(void* stream, const b200ppo_synth_env* env, const uint32_t* keys /*dev [B][2]*/,
                         int32_t B, float* obs, int32_t* step_counter, uint32_t* term_state);
 int b200ppo_synth_init_keys(void* stream, uint32_t k0, uint32_t k1, int32_t B, uint32_t* keys_out);
+/* jax.random.split(key, n)[first : first + count] with the key read from DEVICE memory (dev uint32[2]), so *
+ * that a captured graph follows the per-iteration keys (rollout.py:57-59: split(reset_key, (T, B))).      */
+int b200ppo_split_keys_dev(void* stream, const uint32_t* key /*dev*/, int64_t first, int32_t count,
+                           uint32_t* keys_out /*dev [count][2]*/);
 int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
                           const float* params /*dev*/, const float* norm_mean, const float* norm_std,
                           const uint32_t* rng_state /*dev*/, const uint32_t* iter_keys /*dev*/,
@@ -333,6 +337,41 @@ int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const
                               const float* cat, const float* hn, const float* da, const float* dz,
                               const float* d_y, int32_t rows_total, float* grad, float* scratch);
 
+/* -------- recurrent actor, whole sequences on the tensor cores (tcgen05 3xTF32) -----------------------
+ * The replay scan of ppo_loss over T steps (ppo.py:411-431) and its reverse-mode pass, for the same
+ * Dense(act) -> LSTM -> Dense actor.  Only h_{t-1} Wh is sequential: the input projection, the post
+ * Dense and every weight gradient are batched GEMMs over all T * rows samples; the T step launches
+ * compute 128-row x 16-unit tiles with the gate math, the reset-on-done select and the activation cache
+ * in the GEMM epilogue.  Needs hidden % 16 == 0 and pre_dim % 4 == 0 (b200ppo_lstm_seq_supported;
+ * otherwise use the step kernels above).  ws: b200ppo_lstm_seq_workspace_floats() floats, 256-byte aligned, shared by a
+ * forward call (keep_cache = 1) and the backward call that follows it.
+ *   x     dev [T*rows][obs_dim] inputs in step-major order; normalised on load when norm_mean / norm_std
+ *         are given (rollout: raw observations), else taken as is (replay: the gathered + normalised
+ *         observations the critic pass produced)
+ *   done  dev uint8 [T][B] (nullable): row j of step t resets its carry after the step when
+ *         done[t*B + (inds ? inds[j] : j)] is set
+ *   c, h  dev [rows][hidden]: in = carry entering step 0, out = carry after step T-1 (reset applied)
+ *   y     dev [T*rows][out_dim] actor outputs
+ * backward: d_y dev [T*rows][out_dim]; grad dev [n_params]: the recurrent actor's weight and bias
+ * gradients are WRITTEN (fixed-order sums: bit-reproducible), other entries untouched.               */
+int b200ppo_lstm_seq_supported(const b200ppo_lstm_plan* plan);
+int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows);
+int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t backward);
+int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                             const float* norm_mean, const float* norm_std, const float* x,
+                             const uint8_t* done, const int32_t* inds, int32_t B, float* c, float* h,
+                             int32_t T, int32_t rows, float* ws, float* y, int32_t keep_cache);
+int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                              const float* x, const float* d_y, const uint8_t* done, const int32_t* inds,
+                              int32_t B, int32_t T, int32_t rows, float* ws, float* grad);
+/* parity hooks of the generic tile kernels: C[M][N] = A[M][K] B (b_nt = 0: B [K][N]; 1: B [N][K]), with
+ * k_slices > 1 the partial products land in C[slice][M][N]; W[Kdim][N] = A^T D, b[N] = column sums of D
+ * (scratch: S * (Kdim + 1) * N floats). */
+int b200ppo_rg_gemm_test(void* stream, const float* A, const float* B, float* C, int32_t M, int32_t N,
+                         int32_t K, int32_t b_nt, int32_t k_slices);
+int b200ppo_rg_tn_test(void* stream, const float* A, const float* D, int32_t rows, int32_t Kdim, int32_t N,
+                       int32_t S, float* scratch, float* W, float* b);
+
 /* NormalTanhSampler (sampling_layers.py:88-147) on actor outputs y [B][2A] = [mu | rho] computed
  * elsewhere (the recurrent step): mode bit 0 = replay stored raw actions, bit 1 = deterministic;
  * keys as in b200ppo_policy_step (sample: count, entropy: the next count; deterministic skips the
@@ -365,7 +404,7 @@ double* b200ppo_update_adv_sums_ptr(const b200ppo_plan* plan, int32_t T, int32_t
 float* b200ppo_update_grad_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws);
 /* Debug / parity views into the workspace (after the corresponding stage has run). */
 float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, int32_t mb, void* ws,
-                                int32_t which /*0 adv, 1 values, 2 actor out, 3 d_y, 4 d_v*/);
+                                int32_t which /*0 adv, 1 values, 2 actor out, 3 d_y, 4 d_v, 5 gathered + normalised obs [(T+1)*mb][O]*/);
 
 /* End-of-iteration bookkeeping: rng_state[2] += rng_advance; rng_state[3] += adam_advance;
  * comm_epoch (nullable, dev uint32[1]) += adam_advance. */

@@ -85,6 +85,7 @@ SYMBOLS = {
                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_synth_reset": (C.c_int, [_vp, _EP, _vp, _i32, _vp, _vp, _vp]),
     "b200ppo_synth_init_keys": (C.c_int, [_vp, _u32, _u32, _i32, _vp]),
+    "b200ppo_split_keys_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "b200ppo_rollout_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_eval_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
@@ -110,6 +111,14 @@ SYMBOLS = {
                                         _vp, _vp, _vp, _vp]),
     "b200ppo_lstm_wgrad_scratch_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
     "b200ppo_lstm_weight_grads": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "b200ppo_lstm_seq_supported": (C.c_int, [C.POINTER(LstmPlan)]),
+    "b200ppo_lstm_seq_workspace_floats": (_i64, [C.POINTER(LstmPlan), _i32, _i32]),
+    "b200ppo_lstm_seq_num_launches": (C.c_int, [C.POINTER(LstmPlan), _i32, _i32]),
+    "b200ppo_lstm_seq_forward": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
+                                           _i32, _i32, _vp, _vp, _i32]),
+    "b200ppo_lstm_seq_backward": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "b200ppo_rg_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
+    "b200ppo_rg_tn_test": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200ppo_sampler_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32, _vp]),
     "b200ppo_set_pdl": (C.c_int, [C.c_int]),

@@ -1,32 +1,41 @@
 """ppo_step for a recurrent (LSTM) actor — reference ppo.py:254-348 with the carry handling of
 rollout.py:11-45 (reset on done) and ppo.py:409-431 (replay from the rollout's start carry).
 
-First CUDA path of SURVEY section 8 row a15: the time loops live on the host (one launch of the
-recurrent step kernel per time step, forward and backward), the critic / GAE / loss head /
-gradient reduction / Adam are the MLP path's kernels driven stage by stage (networks/rplan.py).
-Single GPU, no CUDA graph yet.
+SURVEY section 8 row a15.  Only ``h_{t-1} Wh`` is sequential, so a minibatch replay is a handful of batched
+tensor-core GEMMs plus T step launches (csrc/recurrent_tc.cu: ``b200ppo_lstm_seq_forward`` /
+``_backward``); the critic, GAE, the loss head, the gradient reduction and Adam are the MLP path's kernels
+driven stage by stage (networks/rplan.py).  The rollout runs the same sequence kernel with T = 1 per env
+step.  The whole iteration — rollout, permutation, E*M updates, Normalizer statistics — is a fixed launch
+sequence over engine-owned buffers and is captured into ONE CUDA graph on its second run (the reference
+jits ``ppo_step``); per-iteration inputs (PRNG keys, hyper-parameters) reach the kernels through the
+engine's device block, so the graph is never re-captured.  Networks whose sizes the tensor-core kernels do
+not take (hidden % 16, pre_dim % 4) use the per-step FFMA kernels of csrc/recurrent.cu instead, launched
+from the host.  Single GPU.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from .. import _lib, prng
 from ..networks.plan import compile_network
-from .rollout import policy_values, split_keys_device, tree_where
+from .rollout import policy_values, tree_where
 from .types import LoggingLevel
 
 
-def _engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
-    from .engine import PPOEngine
-    import torch
+def _engine(net, opt, env, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     from .engine import cached_engine
     shape_key = (n_envs, T, E, M, bool(norm_adv), opt.gradient_clipping is not None, opt.wd_value >= 0.0)
-    eng = cached_engine(net, "recurrent", None, opt, shape_key,
+    eng = cached_engine(net, "recurrent", env, opt, shape_key,
                         lambda: _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw))
     eng.set_hparams(lam, gamma, clip, cw)
     return eng
+
+
+def _ptr(v) -> int:
+    return int(C.cast(v, C.c_void_p).value)
 
 
 def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
@@ -37,65 +46,85 @@ def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     PPOEngine.__init__(eng, net, fake_env, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw,
                        world_size=1, group=None, use_graph=False)
     lib, lp, mb, dev = eng.lib, net.lplan, eng.mb, net.device
-    H, Y = lp.hidden, lp.out_dim
+    H, Y, P = lp.hidden, lp.out_dim, lp.pre_dim
     f32 = dict(dtype=torch.float32, device=dev)
-    eng.r_cache = torch.zeros(T, int(lib.b200ppo_lstm_cache_floats(lp, mb)), **f32)
+    eng.r_seq = bool(lib.b200ppo_lstm_seq_supported(lp)) and os.environ.get("B200PPO_LSTM", "tc") != "ffma"
     eng.r_c, eng.r_h = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
-    eng.r_dc, eng.r_dh = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
     eng.r_y = torch.zeros(n_envs, Y, **f32)
-    # GEMM operands of the deterministic weight-gradient pass, step-major [T][mb][width]
-    P = lp.pre_dim
-    eng.r_cat = torch.zeros(T, mb, P + H, **f32)
-    eng.r_hn = torch.zeros(T, mb, H, **f32)
-    eng.r_da = torch.zeros(T, mb, 4 * H, **f32)
-    eng.r_dz = torch.zeros(T, mb, P, **f32)
-    eng.r_scratch = torch.zeros(int(lib.b200ppo_lstm_wgrad_scratch_floats(lp, T * mb)), **f32)
+    eng.r_carry = (torch.zeros(n_envs, H, **f32), torch.zeros(n_envs, H, **f32))      # live carry of every env
+    eng.r_start = (torch.zeros(n_envs, H, **f32), torch.zeros(n_envs, H, **f32))      # carry the rollout started from
+    eng.r_inds64 = torch.zeros(E * n_envs, dtype=torch.int64, device=dev)
+    eng.r_keys = torch.zeros(T * n_envs, 2, dtype=torch.int32, device=dev)
     wsp = eng.ws.data_ptr()
-    eng.r_y_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 2), C.c_void_p).value)
-    eng.r_dy_ptr = int(C.cast(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 3), C.c_void_p).value)
-    eng.r_grad_ptr = int(C.cast(lib.b200ppo_update_grad_ptr(net.plan, T, mb, wsp), C.c_void_p).value)
+    eng.r_y_ptr = _ptr(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 2))
+    eng.r_dy_ptr = _ptr(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 3))
+    eng.r_xhat_ptr = _ptr(lib.b200ppo_update_debug_ptr(net.plan, T, mb, wsp, 5))
+    eng.r_grad_ptr = _ptr(lib.b200ppo_update_grad_ptr(net.plan, T, mb, wsp))
+    if eng.r_seq:
+        n_roll = int(lib.b200ppo_lstm_seq_workspace_floats(lp, 1, n_envs))
+        n_upd = int(lib.b200ppo_lstm_seq_workspace_floats(lp, T, mb))
+        eng.r_ws = torch.zeros(max(n_roll, n_upd) + 64, **f32)
+    else:
+        eng.r_cache = torch.zeros(T, int(lib.b200ppo_lstm_cache_floats(lp, mb)), **f32)
+        eng.r_dc, eng.r_dh = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
+        # GEMM operands of the deterministic weight-gradient pass, step-major [T][mb][width]
+        eng.r_cat = torch.zeros(T, mb, P + H, **f32)
+        eng.r_hn = torch.zeros(T, mb, H, **f32)
+        eng.r_da = torch.zeros(T, mb, 4 * H, **f32)
+        eng.r_dz = torch.zeros(T, mb, P, **f32)
+        eng.r_scratch = torch.zeros(int(lib.b200ppo_lstm_wgrad_scratch_floats(lp, T * mb)), **f32)
+    eng.r_env = None            # engine-owned env state (the object a captured graph points at)
+    eng.r_graph = None
+    eng.r_graphable = False
+    eng.r_iters = 0
     return eng
 
 
-def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, discounting_factor,
-                       clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight,
-                       logging_level, logging_percentiles):
-    import torch
-    from . import ppo as _ppo
-    net = compile_network(training_state.networks)
-    if _ppo._dist_info()[0] != 1:
-        raise NotImplementedError("the recurrent path is single-GPU for now")
-    opt = training_state.optimizer
-    T, B = rollout_length, n_envs
-    eng = _engine(net, opt, B, T, n_epochs, n_minibatches, gae_lambda, discounting_factor, clip_range,
-                  normalize_advantages, critic_loss_weight)
-    if LoggingLevel.GRAD_NORM in logging_level:
-        eng.enable_grad_norm()
-    lib, lp, plan, mb, dev = eng.lib, net.lplan, net.plan, eng.mb, net.device
-    A, Y, H = plan.act_dim, lp.out_dim, lp.hidden
-    s = _lib.current_stream()
-    reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
-    net.adam_step = opt.step
-    net.sync_counters_to_device()
-    if net.normalizer is not None:
-        net.normalizer.prepare()
+def _policy(eng, net, obs, t, s):
+    """One network call of the rollout on all envs: recurrent actor + sampler (rollout.py:18)."""
+    lib, lp, plan = eng.lib, net.lplan, net.plan
+    B, A = eng.B, plan.act_dim
+    c, h = eng.r_carry
     mean_p, std_p = net.norm_ptrs()
     arena = net.arena.data_ptr()
-
-    # ---------------- rollout (rollout.py:48-73), one recurrent step launch per time step
-    c, h = net.get_carry(training_state.network_states)
-    c, h = c.contiguous(), h.contiguous()
-    start_c, start_h = c.clone(), h.clone()                              # network_state the replay starts from
-    env_state = training_state.env_states
-    keys_all = split_keys_device(reset_key, T * B, dev).reshape(T, B, 2)
-    for t in range(T):
-        obs = env_state.obs.contiguous()
+    if eng.r_seq:
+        _lib.check(lib.b200ppo_lstm_seq_forward(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
+                                                h.data_ptr(), 1, B, eng.r_ws.data_ptr(), eng.r_y.data_ptr(), 0),
+                   "lstm_seq_forward(rollout)")
+        n = int(lib.b200ppo_lstm_seq_num_launches(lp, 1, 0))
+    else:
         _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                              h.data_ptr(), eng.r_y.data_ptr(), 0), "lstm_step_fwd(rollout)")
-        _lib.check(lib.b200ppo_sampler_step(s, eng.r_y.data_ptr(), B, A, 0, plan.min_std, plan.std_scale,
-                                            plan.entropy_weight, net.counters.data_ptr(), 2 * t, 0,
-                                            eng.raw_action[t].data_ptr(), eng.action[t].data_ptr(),
-                                            eng.loglik[t].data_ptr(), 0), "sampler_step")
+        n = 1
+    _lib.check(lib.b200ppo_sampler_step(s, eng.r_y.data_ptr(), B, A, 0, plan.min_std, plan.std_scale,
+                                        plan.entropy_weight, net.counters.data_ptr(), 2 * t, 0,
+                                        eng.raw_action[t].data_ptr(), eng.action[t].data_ptr(),
+                                        eng.loglik[t].data_ptr(), 0), "sampler_step")
+    return n + 1
+
+
+def _enqueue_iteration(eng, net, env, env_state):
+    """The whole iteration on the current stream.  Returns (final env state, kernel launches of this library)."""
+    import torch
+    lib, lp, plan, mb = eng.lib, net.lplan, net.plan, eng.mb
+    T, B = eng.T, eng.B
+    Y = lp.out_dim
+    s = _lib.current_stream()
+    n = 0
+    if net.normalizer is not None:
+        net.normalizer.prepare(s); n += 1
+    mean_p, std_p = net.norm_ptrs()
+    arena = net.arena.data_ptr()
+    c, h = eng.r_carry
+    eng.r_start[0].copy_(c)                                              # network_state the replay starts from
+    eng.r_start[1].copy_(h)
+    # rng_keys_for_env_reset = split(reset_key, (T, B)) (rollout.py:57-59), from the device key block
+    _lib.check(lib.b200ppo_split_keys_dev(s, eng.iter_keys.data_ptr(), 0, T * B, eng.r_keys.data_ptr()), "split_keys"); n += 1
+    keys_all = eng.r_keys.view(T, B, 2)
+    # ---------------- rollout (rollout.py:48-73)
+    for t in range(T):
+        obs = env_state.obs.contiguous()
+        n += _policy(eng, net, obs, t, s)
         nxt = env.step(env_state, eng.action[t])
         done = nxt.done.bool()
         tr = nxt.info.get("truncated", torch.zeros_like(done)) if isinstance(nxt.info, dict) else torch.zeros_like(done)
@@ -109,47 +138,56 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         c.mul_(keep)
         h.mul_(keep)
         env_state = tree_where(done, env.reset(keys_all[t].contiguous()), nxt)
-    network_states = net.set_carry(training_state.network_states, (c, h))
-    if LoggingLevel.CRITIC_EXTRA in logging_level:
-        # rollout-time value estimates (logging only; the MLP critic does not see the carry)
-        eng.value = policy_values(net, eng.obs.reshape(T * B, -1)).reshape(T, B)
-
     # ---------------- E x M minibatch updates (ppo.py:284-328)
-    eng._upload_block(reset_key, new_key)
     _lib.check(lib.b200ppo_permutation(s, eng.iter_keys.data_ptr() + 8, B, eng.E, eng.inds.data_ptr(),
-                                       eng.perm_scratch.data_ptr()), "permutation")
-    inds_flat = eng.inds.view(-1)
+                                       eng.perm_scratch.data_ptr()), "permutation"); n += 1
+    eng.r_inds64.copy_(eng.inds.view(-1))
     ST = _lib
     for u in range(eng.n_updates):
         off = 2 * T + u * 2 * (T + 1)
         args = (s, plan, eng.hp, eng.bufs[u], T, B, mb, off, u)
         ip = eng.inds.data_ptr() + 4 * u * mb
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_FWD), "update/fwd")            # critic values (+ stand-in actor)
-        idx = inds_flat[u * mb:(u + 1) * mb].long()
-        eng.r_c.copy_(start_c[idx])
-        eng.r_h.copy_(start_h[idx])
-        for t in range(T):                                                            # replay scan, ppo.py:409-431
-            _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, eng.obs[t].data_ptr(), ip,
-                                                 eng.done[t].data_ptr(), mb, eng.r_c.data_ptr(), eng.r_h.data_ptr(),
-                                                 eng.r_y_ptr + 4 * t * mb * Y, eng.r_cache[t].data_ptr()),
-                       "lstm_step_fwd(replay)")
+        n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_FWD))
+        idx = eng.r_inds64[u * mb:(u + 1) * mb]
+        torch.index_select(eng.r_start[0], 0, idx, out=eng.r_c)
+        torch.index_select(eng.r_start[1], 0, idx, out=eng.r_h)
+        if eng.r_seq:                                                                 # replay scan, ppo.py:409-431
+            _lib.check(lib.b200ppo_lstm_seq_forward(s, lp, arena, 0, 0, eng.r_xhat_ptr, eng.done.data_ptr(), ip, B,
+                                                    eng.r_c.data_ptr(), eng.r_h.data_ptr(), T, mb, eng.r_ws.data_ptr(),
+                                                    eng.r_y_ptr, 1), "lstm_seq_forward(replay)")
+            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, 0))
+        else:
+            for t in range(T):
+                _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, eng.obs[t].data_ptr(), ip,
+                                                     eng.done[t].data_ptr(), mb, eng.r_c.data_ptr(), eng.r_h.data_ptr(),
+                                                     eng.r_y_ptr + 4 * t * mb * Y, eng.r_cache[t].data_ptr()),
+                           "lstm_step_fwd(replay)")
+            n += T
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_GAE | ST.STAGE_LOSS), "update/loss")
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
-        eng.r_dc.zero_()
-        eng.r_dh.zero_()
-        for t in reversed(range(T)):                                                  # BPTT
-            _lib.check(lib.b200ppo_lstm_step_bwd(s, lp, arena, eng.r_dy_ptr + 4 * t * mb * Y,
-                                                 eng.r_cache[t].data_ptr(), ip, eng.done[t].data_ptr(), mb,
-                                                 eng.r_dc.data_ptr(), eng.r_dh.data_ptr(), 0,
-                                                 eng.r_cat[t].data_ptr(), eng.r_hn[t].data_ptr(),
-                                                 eng.r_da[t].data_ptr(), eng.r_dz[t].data_ptr()), "lstm_step_bwd")
-        # weight gradients of the recurrent actor: three batched GEMMs over all T steps, fixed-order sums
-        _lib.check(lib.b200ppo_lstm_weight_grads(s, lp, eng.r_cache.data_ptr(), eng.r_cat.data_ptr(),
-                                                 eng.r_hn.data_ptr(), eng.r_da.data_ptr(), eng.r_dz.data_ptr(),
-                                                 eng.r_dy_ptr, T * mb, eng.r_grad_ptr, eng.r_scratch.data_ptr()),
-                   "lstm_weight_grads")
+        n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_GAE | ST.STAGE_LOSS | ST.STAGE_BWD | ST.STAGE_RED))
+        if eng.r_seq:                                                                 # BPTT + weight gradients
+            _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
+                                                     T, mb, eng.r_ws.data_ptr(), eng.r_grad_ptr), "lstm_seq_backward")
+            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, 1))
+        else:
+            eng.r_dc.zero_()
+            eng.r_dh.zero_()
+            for t in reversed(range(T)):
+                _lib.check(lib.b200ppo_lstm_step_bwd(s, lp, arena, eng.r_dy_ptr + 4 * t * mb * Y,
+                                                     eng.r_cache[t].data_ptr(), ip, eng.done[t].data_ptr(), mb,
+                                                     eng.r_dc.data_ptr(), eng.r_dh.data_ptr(), 0,
+                                                     eng.r_cat[t].data_ptr(), eng.r_hn[t].data_ptr(),
+                                                     eng.r_da[t].data_ptr(), eng.r_dz[t].data_ptr()), "lstm_step_bwd")
+            # weight gradients of the recurrent actor: three batched GEMMs over all T steps, fixed-order sums
+            _lib.check(lib.b200ppo_lstm_weight_grads(s, lp, eng.r_cache.data_ptr(), eng.r_cat.data_ptr(),
+                                                     eng.r_hn.data_ptr(), eng.r_da.data_ptr(), eng.r_dz.data_ptr(),
+                                                     eng.r_dy_ptr, T * mb, eng.r_grad_ptr, eng.r_scratch.data_ptr()),
+                       "lstm_weight_grads")
+            n += T + 9
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_ADAM), "update/adam")
-
+        n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_ADAM))
     # ---------------- Normalizer statistics, counters (ppo.py:329-346)
     if net.normalizer is not None:
         nz = net.normalizer
@@ -158,15 +196,102 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
         _lib.check(lib.b200ppo_norm_merge(s, eng.batch_stats.data_ptr(), 1, float(T * B), nz.size,
                                           nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),
                                           nz.counter._dev.data_ptr()), "norm_merge")
-    adv = 2 * T + eng.n_updates * 2 * (T + 1)
-    _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), adv, eng.n_updates, eng.comm_epoch.data_ptr()),
-               "iter_finalize")
-    net.advance_rng(adv)
+        n += 3
+    _lib.check(lib.b200ppo_iter_finalize(s, net.counters.data_ptr(), eng.rng_per_iter, eng.n_updates,
+                                         eng.comm_epoch.data_ptr()), "iter_finalize"); n += 1
+    return env_state, n
+
+
+def _adopt_env_state(eng, env_state):
+    """Engine-owned env state: the first state passed in is adopted, a different object later (checkpoint,
+    rollback) is copied over the live tensors (same rule as PPOEngine.step)."""
+    import dataclasses
+    import torch
+    if eng.r_env is None:
+        eng.r_env = env_state
+        return
+    if env_state is eng.r_env:
+        return
+    for f in dataclasses.fields(env_state) if dataclasses.is_dataclass(env_state) else []:
+        a, b = getattr(eng.r_env, f.name), getattr(env_state, f.name)
+        if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape:
+            a.copy_(b)
+
+
+def _write_back_env(eng, final):
+    """Copy the rollout's final env state into the engine-owned tensors (inside the captured sequence)."""
+    import dataclasses
+    import torch
+    if final is eng.r_env or not dataclasses.is_dataclass(final):
+        eng.r_env = final if not dataclasses.is_dataclass(final) else eng.r_env
+        return
+    for f in dataclasses.fields(final):
+        a, b = getattr(eng.r_env, f.name), getattr(final, f.name)
+        if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape:
+            a.copy_(b.to(a.dtype))
+        elif isinstance(a, dict) and isinstance(b, dict):
+            for k in a:
+                if isinstance(a[k], torch.Tensor) and k in b and isinstance(b[k], torch.Tensor) and a[k].shape == b[k].shape:
+                    a[k].copy_(b[k].to(a[k].dtype))
+
+
+def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, discounting_factor,
+                       clip_range, normalize_advantages, n_epochs, n_minibatches, critic_loss_weight,
+                       logging_level, logging_percentiles):
+    import dataclasses
+    import torch
+    from . import ppo as _ppo
+    net = compile_network(training_state.networks)
+    if _ppo._dist_info()[0] != 1:
+        raise NotImplementedError("the recurrent path is single-GPU for now")
+    opt = training_state.optimizer
+    T, B = rollout_length, n_envs
+    eng = _engine(net, opt, env, B, T, n_epochs, n_minibatches, gae_lambda, discounting_factor, clip_range,
+                  normalize_advantages, critic_loss_weight)
+    if LoggingLevel.GRAD_NORM in logging_level:
+        eng.enable_grad_norm()
+    reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
+    eng._upload_block(reset_key, new_key)
+    if eng.r_iters == 0 or net.adam_step != opt.step or eng._rng_mirror != net.rng_count:
+        net.adam_step = opt.step
+        net.sync_counters_to_device()
+    # the carry and the env state live in engine-owned tensors that the launch sequence updates in place
+    c_in, h_in = net.get_carry(training_state.network_states)
+    if c_in is not eng.r_carry[0]:
+        eng.r_carry[0].copy_(c_in)
+        eng.r_carry[1].copy_(h_in)
+    _adopt_env_state(eng, training_state.env_states)
+    # graph capture needs an env whose state is a dataclass of tensors stepped with device-only torch ops / kernels
+    graphable = (dataclasses.is_dataclass(eng.r_env) and getattr(env, "graph_capturable", getattr(env, "fused_rollout", False))
+                 and os.environ.get("B200PPO_GRAPH", "1") != "0")
+    if not graphable or eng.r_iters == 0:
+        final, eng.kernel_launches_per_iter = _enqueue_iteration(eng, net, env, eng.r_env)
+        if dataclasses.is_dataclass(final) and dataclasses.is_dataclass(eng.r_env):
+            _write_back_env(eng, final)
+        else:
+            eng.r_env = final
+    else:
+        if eng.r_graph is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                final, _ = _enqueue_iteration(eng, net, env, eng.r_env)
+                _write_back_env(eng, final)
+            eng.r_graph = g
+        eng.r_graph.replay()
+    eng.r_iters += 1
+    eng.iters_run = eng.r_iters
+    eng.graph = eng.r_graph
+    network_states = net.set_carry(training_state.network_states, eng.r_carry)
+    net.advance_rng(eng.rng_per_iter)
+    eng._rng_mirror = net.rng_count
     opt.step += eng.n_updates
     net.adam_step = opt.step
+    if LoggingLevel.CRITIC_EXTRA in logging_level:
+        # rollout-time value estimates (logging only; the MLP critic does not see the carry)
+        eng.value = policy_values(net, eng.obs.reshape(T * B, -1)).reshape(T, B)
     per_update = eng.metrics.cpu().numpy()
     total_steps = np.float32(training_state.steps_taken + np.float32(T * B))
     metrics = _ppo._iteration_metrics(per_update, eng, logging_level, logging_percentiles)
     metrics["total_steps"] = total_steps
-    return training_state.replace(network_states=network_states, env_states=env_state, rng_key=new_key,
+    return training_state.replace(network_states=network_states, env_states=eng.r_env, rng_key=new_key,
                                   steps_taken=total_steps), metrics

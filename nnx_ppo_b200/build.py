@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libb200ppo.so")
-SOURCES = ["misc.cu", "rollout.cu", "update.cu", "tcgemm.cu", "recurrent.cu"]
+SOURCES = ["misc.cu", "rollout.cu", "update.cu", "tcgemm.cu", "recurrent.cu", "recurrent_tc.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

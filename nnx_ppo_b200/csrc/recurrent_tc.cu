@@ -1,0 +1,1019 @@
+// Recurrent actor on the tensor cores (reference networks/recurrent.py:89-161
+// over flax's OptimizedLSTMCell, replayed over T in ppo.py:411-431).  sm_100a, tcgen05 kind::tf32 with the
+// error-compensated 3xTF32 split of tc.cuh (fp32 parity), fp32 accumulators in TMEM.
+//
+// What is sequential in   obs -> Normalizer -> Dense(act) -> LSTM -> Dense   is only  h_{t-1} Wh  (and its
+// transpose in BPTT); everything else is a batch over all T * rows samples.  So a replay is
+//   forward : z1 = x W1 + b1, u = act(z1)                      one GEMM over T*rows rows
+//             gx = u Wi + bl                                   one GEMM (N = 4H, tiled by 256)
+//             for t: a_t = gx_t + h_{t-1} Wh -> gates -> (c, h)  T step launches: 128-row x 16-unit tiles; the
+//                                                              gate math, the reset-on-done select and the
+//                                                              activation cache live in the GEMM epilogue
+//             y = h' W2 + b2                                   one GEMM
+//   backward: dh_post = dY W2^T                                one GEMM
+//             for t: da_t (element-wise; sums the split-K partials of step t+1), dh_rec = da_t Wh^T
+//                                                              T x (element-wise launch + split-K GEMM launch)
+//             du = da Wi^T, dz1 = du * act'(z1)                one GEMM
+//             d[Wi; Wh], dbl, dW1, db1, dW2, db2               "TN" GEMMs over all T*rows rows, row-split
+//                                                              partials reduced in fixed order (deterministic)
+// The same forward entry point serves the rollout (rows = n_envs, T = 1 per call, no cache).
+//
+// The kernels are lock-step pipelines: all 256 threads stage a k-slab of both operands (global -> registers
+// one stage ahead -> hi / lo split -> shared memory), one elected lane issues the MMAs, tcgen05.commit hands
+// the buffer back.  Operand layout in shared memory: tc.cuh (K-major, no swizzle, padded planes).
+#include "common.cuh"
+#include "tc.cuh"
+
+using namespace b200ppo;
+
+namespace {
+
+constexpr int RM = 128;        // rows per CTA (UMMA M)
+constexpr int RK = 32;         // k per stage of the NN / NT kernel (4 MMAs of K = 8)
+constexpr int RT = 256;        // threads per CTA
+constexpr int RN_MAX = 256;    // widest N tile
+constexpr int UT = 16;         // hidden units per CTA of the recurrent step (x 4 gates = 64 accumulator columns)
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// C[M x N] = opA(A)[M x K] * Bop[N x K]^T          (one 128-row x N-column tile per CTA)
+// ------------------------------------------------------------------------------------------
+struct GemmArgs {
+  // A: row-major, row r at A + r * lda; reduction columns [a_k0, a_k0 + K); rows >= M read as zero
+  const float* A; int lda; int a_k0; int M; int K;
+  int act_a;                                   // activation applied to A on load (B200PPO_ACT_*)
+  const float* a_mean; const float* a_std;     // nullable: (x - mean[k]) / std[k] on load (Normalizer.__call__)
+  // B, two layouts:
+  //   b_nt = 0: row-major [K][ldb];  Bop(n, k) = B[(b_k0 + k) * ldb + col(n)],
+  //             col(n) = b_col0 + (n >> b_unit_log2) * b_gate_stride + (n & (2^b_unit_log2 - 1))   (gate-interleaved tiles)
+  //   b_nt = 1: row-major [N][ldb];  Bop(n, k) = B[(b_col0 + n) * ldb + b_k0 + k]  (reduction index contiguous)
+  const float* B; int ldb; int b_nt; int b_col0; int b_unit_log2; int b_gate_stride; int b_k0;
+  int N; int n_log2;                           // MMA N of one tile: a power of two in [16, 256]
+  int n_real;                                  // valid columns over all tiles (columns >= n_real are padding)
+  int tile_stride;                             // columns per blockIdx.y tile (added to b_col0 / the C column)
+  // epilogue: C[r * ldc + n] = acc + bias[n]   (n = global column); optional C2 = act(C); optional
+  //           C = acc * act'(Zmul[r * ldz + n])
+  float* C; int ldc;
+  const float* bias;
+  float* C2; int ldc2; int act_c2;
+  const float* Zmul; int ldz; int act_z;
+  // split-K: blockIdx.z = slice; reduction offsets advance by k_slice, C by c_slice_stride floats
+  int k_slice; long long c_slice_stride;
+};
+
+struct StageRegs {
+  float4 a[4];
+  float4 b[RN_MAX / 32];
+};
+
+__host__ __device__ inline uint32_t stage_bytes_nn(int n) {
+  return 2u * (RK / 4) * tc::plane_bytes(RM) + 2u * (RK / 4) * tc::plane_bytes(n);
+}
+
+__device__ __forceinline__ float4 ld4_guard(const float* src, int k, int K, bool aligned) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (aligned && k + 3 < K) {
+    v = *reinterpret_cast<const float4*>(src);
+  } else {
+    v.x = src[0];
+    if (k + 1 < K) v.y = src[1];
+    if (k + 2 < K) v.z = src[2];
+    if (k + 3 < K) v.w = src[3];
+  }
+  return v;
+}
+
+// global -> registers for stage s (every load is issued before any is used)
+template <int NB>
+__device__ __forceinline__ void gemm_load_stage(const GemmArgs& g, int row0, int kbase_a, int kbase_b, int col0, int s,
+                                                int nst, StageRegs& x) {
+  const int tid = threadIdx.x;
+  const int k0 = s * RK;
+  const bool a_al = ((g.lda | kbase_a) & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = tid + j * RT;
+    const int q = idx & 7, r = idx >> 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k = k0 + 4 * q;
+    if (s < nst && row0 + r < g.M && k < g.K) {
+      v = ld4_guard(g.A + static_cast<size_t>(row0 + r) * g.lda + kbase_a + k, k, g.K, a_al);
+      if (g.a_mean != nullptr) {
+        v.x = __fdiv_rn(v.x - g.a_mean[k], g.a_std[k]);
+        if (k + 1 < g.K) v.y = __fdiv_rn(v.y - g.a_mean[k + 1], g.a_std[k + 1]);
+        if (k + 2 < g.K) v.z = __fdiv_rn(v.z - g.a_mean[k + 2], g.a_std[k + 2]);
+        if (k + 3 < g.K) v.w = __fdiv_rn(v.w - g.a_mean[k + 3], g.a_std[k + 3]);
+      }
+    }
+    x.a[j] = v;
+  }
+  const bool b_al = ((g.ldb | kbase_b) & 3) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int idx = tid + j * RT;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.b_nt) {
+      const int q = idx & 7, n = idx >> 3;
+      const int k = k0 + 4 * q;
+      if (s < nst && n < g.N && col0 + n < g.n_real && k < g.K)
+        v = ld4_guard(g.B + static_cast<size_t>(col0 + n) * g.ldb + kbase_b + k, k, g.K, b_al);
+    } else {
+      const int n = idx & (g.N - 1), q = idx >> g.n_log2;   // consecutive lanes -> consecutive columns (coalesced)
+      const int k = k0 + 4 * q;
+      const int col = col0 + (n >> g.b_unit_log2) * g.b_gate_stride + (n & ((1 << g.b_unit_log2) - 1));
+      if (s < nst && q < RK / 4 && (g.b_gate_stride != 0 || col < g.n_real) && k < g.K) {
+        const float* src = g.B + static_cast<size_t>(kbase_b + k) * g.ldb + col;
+        v.x = src[0];
+        if (k + 1 < g.K) v.y = src[g.ldb];
+        if (k + 2 < g.K) v.z = src[2 * static_cast<size_t>(g.ldb)];
+        if (k + 3 < g.K) v.w = src[3 * static_cast<size_t>(g.ldb)];
+      }
+    }
+    x.b[j] = v;
+  }
+}
+
+// registers -> hi / lo operand planes of the stage buffer `st`
+template <int NB>
+__device__ __forceinline__ void gemm_store_stage(const GemmArgs& g, uint8_t* st, const StageRegs& x) {
+  const int tid = threadIdx.x;
+  const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(g.N);
+  uint8_t* a_hi = st;
+  uint8_t* a_lo = a_hi + (RK / 4) * pa;
+  uint8_t* b_hi = a_lo + (RK / 4) * pa;
+  uint8_t* b_lo = b_hi + (RK / 4) * pb;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = tid + j * RT;
+    const int q = idx & 7, r = idx >> 3;
+    float4 v = x.a[j];
+    if (g.act_a == B200PPO_ACT_RELU) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (g.act_a != B200PPO_ACT_NONE) {
+      v.x = act_fwd(v.x, g.act_a); v.y = act_fwd(v.y, g.act_a); v.z = act_fwd(v.z, g.act_a); v.w = act_fwd(v.w, g.act_a);
+    }
+    float4 hi, lo;
+    tc::split4_fast(v, hi, lo);
+    *reinterpret_cast<float4*>(a_hi + q * pa + r * 16) = hi;
+    *reinterpret_cast<float4*>(a_lo + q * pa + r * 16) = lo;
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int idx = tid + j * RT;
+    int n, q;
+    if (g.b_nt) { q = idx & 7; n = idx >> 3; }
+    else { n = idx & (g.N - 1); q = idx >> g.n_log2; }
+    if (n < g.N && q < RK / 4) {
+      float4 hi, lo;
+      tc::split4_fast(x.b[j], hi, lo);
+      *reinterpret_cast<float4*>(b_hi + q * pb + n * 16) = hi;
+      *reinterpret_cast<float4*>(b_lo + q * pb + n * 16) = lo;
+    }
+  }
+}
+
+struct Pipe {
+  uint8_t* smem;
+  uint64_t* bar_empty;   // [2]: tcgen05.commit of the MMAs that read the buffer
+  uint64_t* bar_done;
+  uint32_t tmem_base;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while (c < static_cast<uint32_t>(n)) c <<= 1;
+  return c;
+}
+
+__device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot, int ncols) {
+  const int warp = threadIdx.x >> 5;
+  p.tmem_cols = pow2_cols(ncols);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, p.tmem_cols);
+  if (threadIdx.x == 32) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  p.smem = smem;
+  p.bar_empty = bars;
+  p.bar_done = bars + 2;
+  p.tmem_base = *tmem_slot;
+}
+
+__device__ __forceinline__ void pipe_fini(Pipe& p) {
+  tc::tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(p.tmem_base, p.tmem_cols);
+}
+
+// issue the MMAs of one staged slab (KS k-steps of 8) and commit; called by all threads after the barrier
+template <int KS>
+__device__ __forceinline__ void issue_slab(const Pipe& p, uint8_t* st, uint32_t pa, uint32_t pb, uint32_t idesc, bool first,
+                                           bool last, int buf) {
+  if (threadIdx.x < 32) {               // whole warp 0, converged: one elected lane issues
+    tc::tc_fence_after();
+    if (tc::elect_one()) {
+      uint8_t* a_hi = st;
+      uint8_t* a_lo = a_hi + (KS * 2) * pa;
+      uint8_t* b_hi = a_lo + (KS * 2) * pa;
+      uint8_t* b_lo = b_hi + (KS * 2) * pb;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const uint64_t ah = tc::make_desc(tc::smem_u32(a_hi + 2 * j * pa), pa, 128);
+        const uint64_t al = tc::make_desc(tc::smem_u32(a_lo + 2 * j * pa), pa, 128);
+        const uint64_t bh = tc::make_desc(tc::smem_u32(b_hi + 2 * j * pb), pb, 128);
+        const uint64_t bl = tc::make_desc(tc::smem_u32(b_lo + 2 * j * pb), pb, 128);
+        const uint32_t acc0 = (!first || j > 0) ? 1u : 0u;
+        tc::mma_tf32(p.tmem_base, al, bh, idesc, acc0);       // small terms first, then the dominant product
+        tc::mma_tf32(p.tmem_base, ah, bl, idesc, 1u);
+        tc::mma_tf32(p.tmem_base, ah, bh, idesc, 1u);
+      }
+      tc::commit(&p.bar_empty[buf]);
+      if (last) tc::commit(p.bar_done);
+    }
+    __syncwarp();
+  }
+}
+
+// accumulate into TMEM columns [0, N).  Two statically named register sets ping-pong so that the loads of
+// stage s + 1 are in flight while stage s is split and stored (a rotating `cur = next` copy would make
+// every stage wait for a memory round trip: profiles/r1_tc_notes.md, finding 2).
+template <int NB>
+__device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, int row0, int kbase_a, int kbase_b,
+                                              int col0) {
+  const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(g.N);
+  const uint32_t sbytes = stage_bytes_nn(g.N);
+  const uint32_t idesc = tc::make_idesc_tf32(RM, g.N);
+  const int nst = (g.K + RK - 1) / RK;
+  uint32_t phase0 = 0u, phase1 = 0u;
+  StageRegs x0, x1;
+  gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, 0, nst, x0);
+  for (int s = 0; s < nst; s += 2) {
+    gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 1, nst, x1);
+    if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
+    gemm_store_stage<NB>(g, p.smem, x0);
+    tc::fence_proxy_async();
+    __syncthreads();
+    issue_slab<RK / 8>(p, p.smem, pa, pb, idesc, s == 0, s == nst - 1, 0);
+    if (s + 1 < nst) {
+      gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 2, nst, x0);
+      if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
+      gemm_store_stage<NB>(g, p.smem + sbytes, x1);
+      tc::fence_proxy_async();
+      __syncthreads();
+      issue_slab<RK / 8>(p, p.smem + sbytes, pa, pb, idesc, false, s + 1 == nst - 1, 1);
+    }
+  }
+}
+
+__device__ __forceinline__ void wait_acc(const Pipe& p) {
+  tc::mbar_wait(p.bar_done, 0u);
+  tc::tc_fence_after();
+}
+
+template <int NB>
+__global__ void __launch_bounds__(RT, 1) rg_gemm_kernel(const GemmArgs g) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[3];
+  __shared__ uint32_t tmem_slot;
+  Pipe p;
+  pipe_init(p, smem, bars, &tmem_slot, g.N);
+  const int row0 = blockIdx.x * RM;
+  const int tile = blockIdx.y, slice = blockIdx.z;
+  const int col0 = g.b_col0 + tile * g.tile_stride;
+  const int ccol0 = tile * g.tile_stride;
+  const int kb_a = g.a_k0 + slice * g.k_slice, kb_b = g.b_k0 + slice * g.k_slice;
+  gemm_mainloop<NB>(g, p, row0, kb_a, kb_b, col0);
+  wait_acc(p);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp & 3, cg = warp >> 2;
+  const int row = row0 + sub * 32 + lane;
+  float* Cb = g.C + static_cast<long long>(slice) * g.c_slice_stride;
+  for (int c = cg * 16; c < g.N; c += 32) {
+    float v[16];
+    tc::tmem_ld16(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
+    if (row < g.M) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = ccol0 + c + i;
+        if (n < g.n_real) {
+          float val = v[i];
+          if (g.bias != nullptr) val += g.bias[n];
+          if (g.Zmul != nullptr) val *= act_grad(g.Zmul[static_cast<size_t>(row) * g.ldz + n], g.act_z);
+          Cb[static_cast<size_t>(row) * g.ldc + n] = val;
+          if (g.C2 != nullptr) g.C2[static_cast<size_t>(row) * g.ldc2 + n] = act_fwd(val, g.act_c2);
+        }
+      }
+    }
+  }
+  pipe_fini(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// recurrent step, forward: a = gx_t + h_in Wh (this CTA: 128 rows x 16 hidden units x 4 gates), then
+//   i, f, o = sigmoid, g = tanh;  c' = f c + i g;  h' = o tanh(c');  carry <- done ? 0 : (c', h')
+// ------------------------------------------------------------------------------------------
+struct StepFwdArgs {
+  GemmArgs g;                  // A = h_in (lda = P + H), B = Wh (b_nt = 0, b_unit = 16, b_gate_stride = H), N = 64
+  const float* gx;             // [rows][4H], bias included
+  float* c_cur;                // [rows][H]  in: c entering the step, out: c handed on (reset applied)
+  float* h_next; int ld_hn;    // where the carry h handed on goes (row stride): cat[t + 1] + P, or the h buffer itself
+  float* hn;                   // [rows][H] pre-reset h' (nullable)
+  float* gi; float* gf; float* gg; float* go; float* tcc; float* cin;   // activation cache [rows][H] (all or none)
+  const uint8_t* done; const int32_t* inds;    // done[inds ? inds[row] : row] (nullable: no reset here)
+  int H;
+};
+
+__global__ void __launch_bounds__(RT, 1) lstm_rec_fwd_kernel(const StepFwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[3];
+  __shared__ uint32_t tmem_slot;
+  Pipe p;
+  pipe_init(p, smem, bars, &tmem_slot, 4 * UT);
+  const int row0 = blockIdx.x * RM;
+  const int u_base = blockIdx.y * UT;
+  gemm_mainloop<2>(a.g, p, row0, a.g.a_k0, a.g.b_k0, u_base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp & 3, ub = warp >> 2;
+  const int row = row0 + sub * 32 + lane;
+  const int H = a.H;
+  const int u0 = u_base + 8 * ub;                    // this thread: units u0 .. u0 + 7 of its row
+  const bool ok = row < a.g.M;
+  // operands of the gate math that do not depend on the accumulator: fetched before the wait
+  float gxv[4][8], cv[8];
+  bool dn = false;
+  if (ok) {
+    const float* gr = a.gx + static_cast<size_t>(row) * 4 * H + u0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 lo = *reinterpret_cast<const float4*>(gr + q * H), hi = *reinterpret_cast<const float4*>(gr + q * H + 4);
+      gxv[q][0] = lo.x; gxv[q][1] = lo.y; gxv[q][2] = lo.z; gxv[q][3] = lo.w;
+      gxv[q][4] = hi.x; gxv[q][5] = hi.y; gxv[q][6] = hi.z; gxv[q][7] = hi.w;
+    }
+    const float4 c0 = *reinterpret_cast<const float4*>(a.c_cur + static_cast<size_t>(row) * H + u0);
+    const float4 c1 = *reinterpret_cast<const float4*>(a.c_cur + static_cast<size_t>(row) * H + u0 + 4);
+    cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+    if (a.done != nullptr) dn = a.done[a.inds ? a.inds[row] : row] != 0;
+  }
+  wait_acc(p);
+  float acc[4][8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    tmem_ld8(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(q * UT + 8 * ub), acc[q]);
+  if (ok) {
+    float c2[8], h2[8], iv[8], fv[8], gv[8], ov[8], tv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      iv[k] = sigmoid_f(acc[0][k] + gxv[0][k]);
+      fv[k] = sigmoid_f(acc[1][k] + gxv[1][k]);
+      gv[k] = tanhf(acc[2][k] + gxv[2][k]);
+      ov[k] = sigmoid_f(acc[3][k] + gxv[3][k]);
+      c2[k] = __fadd_rn(__fmul_rn(fv[k], cv[k]), __fmul_rn(iv[k], gv[k]));
+      tv[k] = tanhf(c2[k]);
+      h2[k] = __fmul_rn(ov[k], tv[k]);
+    }
+    auto st8 = [](float* dst, const float (&v)[8]) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    const size_t o = static_cast<size_t>(row) * H + u0;
+    if (a.gi != nullptr) {
+      st8(a.gi + o, iv); st8(a.gf + o, fv); st8(a.gg + o, gv); st8(a.go + o, ov); st8(a.tcc + o, tv); st8(a.cin + o, cv);
+    }
+    if (a.hn != nullptr) st8(a.hn + o, h2);
+    if (dn) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c2[k] = 0.0f; h2[k] = 0.0f; }
+    }
+    st8(a.c_cur + o, c2);
+    st8(a.h_next + static_cast<size_t>(row) * a.ld_hn + u0, h2);
+  }
+  pipe_fini(p);
+}
+
+// ------------------------------------------------------------------------------------------
+// recurrent step, backward, element-wise part (oracle/recurrent.py ppo_loss_and_grads, BPTT loop):
+//   dh = dh_post_t + keep * sum_q dh_rec[q];  dc = dh o (1 - tc^2) + keep * dc_next;  da = gate gradients
+// ------------------------------------------------------------------------------------------
+struct StepBwdArgs {
+  const float* dhp;            // [rows][H] dY_t W2^T
+  const float* dhr; int n_slices; long long slice_stride;   // split-K partials of da_{t+1} Wh^T (nullable: last step)
+  float* dc;                   // [rows][H] in: dc_next, out: dc handed to step t - 1
+  const float* gi; const float* gf; const float* gg; const float* go; const float* tcc; const float* cin;
+  const uint8_t* done; const int32_t* inds;
+  float* da;                   // [rows][4H]
+  int rows, H;
+};
+
+__global__ void __launch_bounds__(256) lstm_rec_bwd_e_kernel(const StepBwdArgs a) {
+  const int H4 = a.H >> 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * H4) return;
+  const int row = idx / H4, k = (idx - row * H4) * 4;
+  const size_t o = static_cast<size_t>(row) * a.H + k;
+  const bool dn = a.done != nullptr && a.done[a.inds ? a.inds[row] : row] != 0;
+  const float keep = dn ? 0.0f : 1.0f;
+  auto ld = [&](const float* p) { return *reinterpret_cast<const float4*>(p + o); };
+  float4 dh = ld(a.dhp);
+  if (a.dhr != nullptr) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < a.n_slices; ++q) {                   // fixed order: deterministic
+      const float4 v = *reinterpret_cast<const float4*>(a.dhr + q * a.slice_stride + o);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dh.x += keep * s.x; dh.y += keep * s.y; dh.z += keep * s.z; dh.w += keep * s.w;
+  }
+  const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dc);
+  const float dhv[4] = {dh.x, dh.y, dh.z, dh.w};
+  const float iv[4] = {i4.x, i4.y, i4.z, i4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+  const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+  const float dcv[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
+  float di[4], df[4], dg[4], dO[4], dco[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float dc = dhv[j] * ov[j] * (1.0f - tv[j] * tv[j]) + keep * dcv[j];
+    di[j] = dc * gv[j] * iv[j] * (1.0f - iv[j]);
+    df[j] = dc * cv[j] * fv[j] * (1.0f - fv[j]);
+    dg[j] = dc * iv[j] * (1.0f - gv[j] * gv[j]);
+    dO[j] = dhv[j] * tv[j] * ov[j] * (1.0f - ov[j]);
+    dco[j] = dc * fv[j];
+  }
+  float* dr = a.da + static_cast<size_t>(row) * 4 * a.H + k;
+  *reinterpret_cast<float4*>(dr) = make_float4(di[0], di[1], di[2], di[3]);
+  *reinterpret_cast<float4*>(dr + a.H) = make_float4(df[0], df[1], df[2], df[3]);
+  *reinterpret_cast<float4*>(dr + 2 * a.H) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+  *reinterpret_cast<float4*>(dr + 3 * a.H) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+  *reinterpret_cast<float4*>(a.dc + o) = make_float4(dco[0], dco[1], dco[2], dco[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// "TN" GEMM for the weight gradients:  part[s][m][n] = sum_{r in split s} A[r][a_col0 + m] * D[r][d_col0 + n]
+// Both operands have the reduction index (rows) as the SLOW index in memory, so a slab of TK rows is copied
+// raw into shared memory (coalesced) and transposed shared -> shared into the K-major operand planes
+// (conflict-free LDS.32 down the rows, one STS.128 per 4-row chunk).  The column sums of D (bias gradients)
+// fall out of the same pass.
+// ------------------------------------------------------------------------------------------
+constexpr int TK = 16;                     // rows per stage (2 MMAs of K = 8)
+constexpr int TN_APITCH = RM + 4;          // floats
+
+struct TnArgs {
+  const float* A; int lda; int a_col0; int Kdim;     // m tiles of 128 over Kdim columns: blockIdx.x
+  int act_a;
+  const float* D; int ldd; int N; int n_log2; int n_real; int tile_stride;   // N = MMA N (power of two, 16..256); blockIdx.y
+  int rows; int rows_per_split;                      // blockIdx.z
+  float* part; long long part_stride; int ldp;       // part[s * part_stride + m * ldp + n]
+  float* bpart; long long bpart_stride;              // nullable: bpart[s * bpart_stride + n] = sum_r D[r][n]
+};
+
+__host__ __device__ inline uint32_t tn_planes_bytes(int n) {
+  return 2u * (TK / 4) * tc::plane_bytes(RM) + 2u * (TK / 4) * tc::plane_bytes(n);
+}
+__host__ __device__ inline uint32_t tn_raw_bytes(int n) { return static_cast<uint32_t>(TK) * (TN_APITCH + n + 4) * 4u; }
+
+struct TnRegs {
+  float4 a[2];
+  float4 d[4];
+};
+
+__device__ __forceinline__ void tn_load(const TnArgs& t, int m0, int n0, int r_begin, int r_end, int s, TnRegs& x) {
+  const int tid = threadIdx.x;
+  const int rs = r_begin + s * TK;
+  const bool a_al = ((t.lda | (t.a_col0 + m0)) & 3) == 0 && (reinterpret_cast<uintptr_t>(t.A) & 15) == 0;
+  const bool d_al = ((t.ldd | n0) & 3) == 0 && (reinterpret_cast<uintptr_t>(t.D) & 15) == 0;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * RT;
+    const int c4 = idx & 31, r = idx >> 5;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int m = 4 * c4;
+    if (rs + r < r_end && m0 + m < t.Kdim)
+      v = ld4_guard(t.A + static_cast<size_t>(rs + r) * t.lda + t.a_col0 + m0 + m, m0 + m, t.Kdim, a_al);
+    x.a[j] = v;
+  }
+  const int n4 = t.N >> 2;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = tid + j * RT;
+    const int c4 = idx & (n4 - 1), r = idx >> (t.n_log2 - 2);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n = 4 * c4;
+    if (r < TK && rs + r < r_end && n0 + n < t.n_real)
+      v = ld4_guard(t.D + static_cast<size_t>(rs + r) * t.ldd + n0 + n, n0 + n, t.n_real, d_al);
+    x.d[j] = v;
+  }
+}
+
+__device__ __forceinline__ void tn_store_raw(const TnArgs& t, float* ra, float* rd, const TnRegs& x) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * RT;
+    const int c4 = idx & 31, r = idx >> 5;
+    float4 v = x.a[j];
+    if (t.act_a == B200PPO_ACT_RELU) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    } else if (t.act_a != B200PPO_ACT_NONE) {
+      v.x = act_fwd(v.x, t.act_a); v.y = act_fwd(v.y, t.act_a); v.z = act_fwd(v.z, t.act_a); v.w = act_fwd(v.w, t.act_a);
+    }
+    *reinterpret_cast<float4*>(ra + r * TN_APITCH + 4 * c4) = v;
+  }
+  const int n4 = t.N >> 2, dp = t.N + 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = tid + j * RT;
+    const int c4 = idx & (n4 - 1), r = idx >> (t.n_log2 - 2);
+    if (r < TK) *reinterpret_cast<float4*>(rd + r * dp + 4 * c4) = x.d[j];
+  }
+}
+
+// raw slab -> operand planes of buffer `st`; accumulates this thread's share of the column sums of D
+__device__ __forceinline__ void tn_transpose(const TnArgs& t, const float* ra, const float* rd, uint8_t* st, float (&bsum)[4]) {
+  const int tid = threadIdx.x;
+  const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(t.N);
+  uint8_t* a_hi = st;
+  uint8_t* a_lo = a_hi + (TK / 4) * pa;
+  uint8_t* b_hi = a_lo + (TK / 4) * pa;
+  uint8_t* b_lo = b_hi + (TK / 4) * pb;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int idx = tid + j * RT;
+    const int m = idx & (RM - 1), q = idx >> 7;        // 4 planes x 128 columns
+    const float* src = ra + (4 * q) * TN_APITCH + m;
+    const float4 v = make_float4(src[0], src[TN_APITCH], src[2 * TN_APITCH], src[3 * TN_APITCH]);
+    float4 hi, lo;
+    tc::split4_fast(v, hi, lo);
+    *reinterpret_cast<float4*>(a_hi + q * pa + m * 16) = hi;
+    *reinterpret_cast<float4*>(a_lo + q * pa + m * 16) = lo;
+  }
+  const int dp = t.N + 4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = tid + j * RT;
+    const int n = idx & (t.N - 1), q = idx >> t.n_log2;   // N is a power of two
+    if (q < TK / 4) {
+      const float* src = rd + (4 * q) * dp + n;
+      const float4 v = make_float4(src[0], src[dp], src[2 * dp], src[3 * dp]);
+      bsum[j] += (v.x + v.y) + (v.z + v.w);
+      float4 hi, lo;
+      tc::split4_fast(v, hi, lo);
+      *reinterpret_cast<float4*>(b_hi + q * pb + n * 16) = hi;
+      *reinterpret_cast<float4*>(b_lo + q * pb + n * 16) = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RT, 1) rg_tn_kernel(const TnArgs t) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[3];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bred[4 * RT];
+  Pipe p;
+  pipe_init(p, smem, bars, &tmem_slot, t.N);
+  const int m0 = blockIdx.x * RM, n0 = blockIdx.y * t.tile_stride, sp = blockIdx.z;
+  const int r_begin = sp * t.rows_per_split;
+  int r_end = r_begin + t.rows_per_split;
+  if (r_end > t.rows) r_end = t.rows;
+  const int nst = r_end > r_begin ? (r_end - r_begin + TK - 1) / TK : 0;
+  const uint32_t pbytes = tn_planes_bytes(t.N);
+  float* ra = reinterpret_cast<float*>(smem + 2 * pbytes);
+  float* rd = ra + TK * TN_APITCH;
+  const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(t.N);
+  const uint32_t idesc = tc::make_idesc_tf32(RM, t.N);
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t phase0 = 0u, phase1 = 0u;
+  TnRegs x0, x1;
+  if (nst > 0) tn_load(t, m0, n0, r_begin, r_end, 0, x0);
+  for (int s = 0; s < nst; s += 2) {
+    if (s + 1 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 1, x1);
+    tn_store_raw(t, ra, rd, x0);
+    __syncthreads();
+    if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
+    tn_transpose(t, ra, rd, p.smem, bsum);
+    tc::fence_proxy_async();
+    __syncthreads();                       // planes complete; everybody is done reading the raw slab
+    issue_slab<TK / 8>(p, p.smem, pa, pb, idesc, s == 0, s == nst - 1, 0);
+    if (s + 1 < nst) {
+      if (s + 2 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 2, x0);
+      tn_store_raw(t, ra, rd, x1);
+      __syncthreads();
+      if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
+      tn_transpose(t, ra, rd, p.smem + pbytes, bsum);
+      tc::fence_proxy_async();
+      __syncthreads();
+      issue_slab<TK / 8>(p, p.smem + pbytes, pa, pb, idesc, false, s + 1 == nst - 1, 1);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp & 3, cg = warp >> 2;
+  const int m = m0 + sub * 32 + lane;
+  float* po = t.part + static_cast<long long>(sp) * t.part_stride;
+  if (nst > 0) wait_acc(p);
+  for (int c = cg * 16; c < t.N; c += 32) {
+    float v[16];
+    if (nst > 0) {
+      tc::tmem_ld16(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    }
+    if (m < t.Kdim) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = n0 + c + i;
+        if (n < t.n_real) po[static_cast<size_t>(m) * t.ldp + n] = v[i];
+      }
+    }
+  }
+  if (t.bpart != nullptr && blockIdx.x == 0) {          // column sums: thread (n, q) partials -> fixed-order sum over q
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bred[threadIdx.x + j * RT] = bsum[j];
+    __syncthreads();
+    for (int n = threadIdx.x; n < t.N; n += RT) {
+      float s = 0.0f;
+      for (int q = 0; q < TK / 4; ++q) {
+        const int idx = q * t.N + n;                     // chunk id of (n, q): idx = tid + j * RT
+        s += bred[idx];
+      }
+      if (n0 + n < t.n_real) t.bpart[static_cast<long long>(sp) * t.bpart_stride + n0 + n] = s;
+    }
+  }
+  pipe_fini(p);
+}
+
+// sum of S partial matrices in fixed order
+__global__ void __launch_bounds__(256) rg_reduce_kernel(const float* __restrict__ part, long long n, int S,
+                                                        long long stride, float* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.0f;
+  for (int sp = 0; sp < S; ++sp) s += part[sp * stride + i];
+  out[i] = s;
+}
+
+// carry in / out of the sequence workspace: dst[r][0..H) = src[r][0..H) with row strides
+__global__ void __launch_bounds__(256) rg_copy_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst,
+                                                           int ldd, int rows, int H) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * H) return;
+  const int r = idx / H, k = idx - r * H;
+  dst[static_cast<size_t>(r) * ldd + k] = src[static_cast<size_t>(r) * lds + k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct SeqLayout {
+  size_t z1, cat, gx, gi, gf, gg, go, tcc, cin, hn, c_cur, da, dhp, dhr, dc, dz1, part, bpart, total;
+  int S_cat, S_w1, S_w2;
+};
+
+inline size_t al64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
+
+int split_for(int tiles, int rows) {
+  int S = (2 * 148) / (tiles > 0 ? tiles : 1);
+  const int smax = (rows + 4 * TK - 1) / (4 * TK);
+  if (S > smax) S = smax;
+  if (S > 64) S = 64;
+  if (S < 1) S = 1;
+  return S;
+}
+
+SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
+  SeqLayout L;
+  const size_t R = static_cast<size_t>(T) * rows;
+  const size_t O = p.obs_dim, P = p.pre_dim, H = p.hidden, Y = p.out_dim;
+  (void)O;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
+  L.z1 = take(R * P);
+  L.cat = take((R + rows) * (P + H));
+  L.gx = take(R * 4 * H);
+  L.gi = take(R * H); L.gf = take(R * H); L.gg = take(R * H); L.go = take(R * H); L.tcc = take(R * H); L.cin = take(R * H);
+  L.hn = take(R * H);
+  L.c_cur = take(static_cast<size_t>(rows) * H);
+  L.da = take(R * 4 * H);
+  L.dhp = take(R * H);
+  L.dhr = take(4 * static_cast<size_t>(rows) * H);
+  L.dc = take(static_cast<size_t>(rows) * H);
+  L.dz1 = take(R * P);
+  const int Rr = static_cast<int>(R);
+  L.S_cat = split_for(cdiv(P + H, RM) * cdiv(4 * H, 256), Rr);
+  L.S_w1 = split_for(cdiv(p.obs_dim, RM), Rr);
+  L.S_w2 = split_for(cdiv(H, RM), Rr);
+  size_t pmax = static_cast<size_t>(L.S_cat) * (P + H) * 4 * H;
+  const size_t p1 = static_cast<size_t>(L.S_w1) * p.obs_dim * P, p2 = static_cast<size_t>(L.S_w2) * H * Y;
+  pmax = p1 > pmax ? p1 : pmax;
+  pmax = p2 > pmax ? p2 : pmax;
+  L.part = take(pmax);
+  size_t nb = 4 * H;
+  nb = P > nb ? P : nb;
+  nb = Y > nb ? Y : nb;
+  L.bpart = take(64 * nb);
+  L.total = o;
+  return L;
+}
+
+int check_plan_tc(const b200ppo_lstm_plan* p) {
+  if (!p || p->obs_dim <= 0 || p->pre_dim <= 0 || p->hidden <= 0 || p->out_dim <= 0 || p->n_params <= 0) return B200PPO_EINVAL;
+  if (p->act < 0 || p->act > 3) return B200PPO_EINVAL;
+  // 16-unit tiles, and the carry inside [u | h] rows must stay 16-byte aligned; the FFMA step kernels
+  // (b200ppo_lstm_step_fwd / _bwd) have no such limits
+  if (p->hidden % UT || p->pre_dim % 4) return B200PPO_ELIMIT;
+  if (p->pre_dim > 4096 || p->out_dim > 4096 || p->obs_dim > 65536) return B200PPO_ELIMIT;
+  return 0;
+}
+
+int mma_n(int n) {          // MMA N for n valid columns: a power of two in [16, 256]
+  int v = 16;
+  while (v < n && v < 256) v <<= 1;
+  return v;
+}
+
+bool g_attr_tc = false;
+int set_attrs_tc() {
+  if (g_attr_tc) return 0;
+  const int big = 2 * static_cast<int>(stage_bytes_nn(256));
+  cudaError_t e;
+  e = cudaFuncSetAttribute(rg_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(rg_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(rg_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(rg_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(2 * tn_planes_bytes(256) + tn_raw_bytes(256)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  g_attr_tc = true;
+  return 0;
+}
+
+GemmArgs gemm_defaults() {
+  GemmArgs g;
+  g.A = nullptr; g.lda = 0; g.a_k0 = 0; g.M = 0; g.K = 0; g.act_a = B200PPO_ACT_NONE; g.a_mean = nullptr; g.a_std = nullptr;
+  g.B = nullptr; g.ldb = 0; g.b_nt = 0; g.b_col0 = 0; g.b_unit_log2 = 30; g.b_gate_stride = 0; g.b_k0 = 0;
+  g.N = 16; g.n_log2 = 4; g.n_real = 0; g.tile_stride = 0;
+  g.C = nullptr; g.ldc = 0; g.bias = nullptr; g.C2 = nullptr; g.ldc2 = 0; g.act_c2 = B200PPO_ACT_NONE;
+  g.Zmul = nullptr; g.ldz = 0; g.act_z = B200PPO_ACT_NONE;
+  g.k_slice = 0; g.c_slice_stride = 0;
+  return g;
+}
+
+int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// launch the generic GEMM over n_real columns (tiles of at most n_tile columns) and `slices` k slices
+int launch_gemm(cudaStream_t s, GemmArgs g, int n_real, int slices, int n_tile = 256) {
+  g.n_real = n_real;
+  g.N = mma_n(n_real < n_tile ? n_real : n_tile);
+  g.n_log2 = ilog2(g.N);
+  g.tile_stride = g.N;
+  const int tiles = cdiv(n_real, g.N);
+  const dim3 grid(cdiv(g.M, RM), tiles, slices);
+  const size_t smem = 2 * static_cast<size_t>(stage_bytes_nn(g.N));
+  if (g.N <= 32) rg_gemm_kernel<1><<<grid, RT, smem, s>>>(g);
+  else if (g.N <= 64) rg_gemm_kernel<2><<<grid, RT, smem, s>>>(g);
+  else rg_gemm_kernel<8><<<grid, RT, smem, s>>>(g);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+// weight gradient out[Kdim][n_real] (+ bias gradient) = A^T D over `rows` rows, S row splits, fixed-order reduction
+int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int act_a, const float* D, int ldd, int n_real,
+              int rows, int S, float* part, float* bpart, float* gw, float* gb) {
+  TnArgs t;
+  t.A = A; t.lda = lda; t.a_col0 = a_col0; t.Kdim = Kdim; t.act_a = act_a;
+  t.D = D; t.ldd = ldd; t.n_real = n_real; t.N = mma_n(n_real); t.n_log2 = ilog2(t.N); t.tile_stride = t.N;
+  t.rows = rows;
+  t.rows_per_split = cdiv(cdiv(rows, S), TK) * TK;
+  S = cdiv(rows, t.rows_per_split);
+  t.part = part; t.part_stride = static_cast<long long>(Kdim) * n_real; t.ldp = n_real;
+  t.bpart = gb != nullptr ? bpart : nullptr; t.bpart_stride = n_real;
+  const dim3 grid(cdiv(Kdim, RM), cdiv(n_real, t.N), S);
+  const size_t smem = 2 * static_cast<size_t>(tn_planes_bytes(t.N)) + tn_raw_bytes(t.N);
+  rg_tn_kernel<<<grid, RT, smem, s>>>(t);
+  B200PPO_LAUNCH_CHECK();
+  const long long n = static_cast<long long>(Kdim) * n_real;
+  rg_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, n, S, n, gw);
+  B200PPO_LAUNCH_CHECK();
+  if (gb != nullptr) {
+    rg_reduce_kernel<<<cdiv(n_real, 256), 256, 0, s>>>(bpart, n_real, S, n_real, gb);
+    B200PPO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int b200ppo_lstm_seq_supported(const b200ppo_lstm_plan* plan) { return check_plan_tc(plan) == 0 ? 1 : 0; }
+
+extern "C" int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows) {
+  if (check_plan_tc(plan) || T <= 0 || rows <= 0) return -1;
+  return static_cast<int64_t>(seq_layout(*plan, T, rows).total);
+}
+
+extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t backward) {
+  if (check_plan_tc(plan) || T <= 0) return -1;
+  if (!backward) return 2 /* carry in */ + 2 /* pre, proj */ + T + 1 /* post */ + 2 /* carry out */;
+  return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */;
+}
+
+extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                                        const float* norm_mean, const float* norm_std, const float* x,
+                                        const uint8_t* done, const int32_t* inds, int32_t B, float* c, float* h,
+                                        int32_t T, int32_t rows, float* ws, float* y, int32_t keep_cache) {
+  int rc = check_plan_tc(plan);
+  if (rc) return rc;
+  if (T <= 0 || rows <= 0 || B <= 0 || !params || !x || !c || !h || !ws || !y) return B200PPO_EINVAL;
+  if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200PPO_EINVAL;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return B200PPO_EALIGN;
+  rc = set_attrs_tc();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const SeqLayout L = seq_layout(*plan, T, rows);
+  const int O = plan->obs_dim, P = plan->pre_dim, H = plan->hidden, Y = plan->out_dim;
+  const int R = T * rows, LC = P + H;
+  float* z1 = ws + L.z1;
+  float* cat = ws + L.cat;
+  // carry in: cat[0][:, P:] = h, c_cur = c
+  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(h, H, cat + P, LC, rows, H);
+  B200PPO_LAUNCH_CHECK();
+  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(c, H, ws + L.c_cur, H, rows, H);
+  B200PPO_LAUNCH_CHECK();
+  // z1 = x W1 + b1;  u = act(z1) -> cat[:, :P]
+  {
+    GemmArgs g = gemm_defaults();
+    g.A = x; g.lda = O; g.M = R; g.K = O; g.a_mean = norm_mean; g.a_std = norm_std;
+    g.B = params + plan->w1_off; g.ldb = P;
+    g.C = z1; g.ldc = P; g.bias = params + plan->b1_off;
+    g.C2 = cat; g.ldc2 = LC; g.act_c2 = plan->act;
+    rc = launch_gemm(s, g, P, 1);
+    if (rc) return rc;
+  }
+  // gx = u Wi + bl
+  {
+    GemmArgs g = gemm_defaults();
+    g.A = cat; g.lda = LC; g.M = R; g.K = P;
+    g.B = params + plan->wcat_off; g.ldb = 4 * H;
+    g.C = ws + L.gx; g.ldc = 4 * H; g.bias = params + plan->bl_off;
+    rc = launch_gemm(s, g, 4 * H, 1);
+    if (rc) return rc;
+  }
+  // the recurrence
+  for (int t = 0; t < T; ++t) {
+    StepFwdArgs a;
+    a.g = gemm_defaults();
+    a.g.A = cat + static_cast<size_t>(t) * rows * LC; a.g.lda = LC; a.g.a_k0 = P; a.g.M = rows; a.g.K = H;
+    a.g.B = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H; a.g.ldb = 4 * H;
+    a.g.b_nt = 0; a.g.b_unit_log2 = 4; a.g.b_gate_stride = H; a.g.N = 4 * UT; a.g.n_log2 = 6; a.g.n_real = 4 * H;
+    a.gx = ws + L.gx + static_cast<size_t>(t) * rows * 4 * H;
+    a.c_cur = ws + L.c_cur;
+    a.h_next = cat + static_cast<size_t>(t + 1) * rows * LC + P; a.ld_hn = LC;
+    const size_t so = static_cast<size_t>(t) * rows * H;
+    a.hn = ws + L.hn + so;
+    if (keep_cache) {
+      a.gi = ws + L.gi + so; a.gf = ws + L.gf + so; a.gg = ws + L.gg + so; a.go = ws + L.go + so;
+      a.tcc = ws + L.tcc + so; a.cin = ws + L.cin + so;
+    } else {
+      a.gi = a.gf = a.gg = a.go = a.tcc = a.cin = nullptr;
+    }
+    a.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
+    a.inds = inds;
+    a.H = H;
+    lstm_rec_fwd_kernel<<<dim3(cdiv(rows, RM), H / UT), RT, 2 * stage_bytes_nn(4 * UT), s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  // y = h' W2 + b2
+  {
+    GemmArgs g = gemm_defaults();
+    g.A = ws + L.hn; g.lda = H; g.M = R; g.K = H;
+    g.B = params + plan->w2_off; g.ldb = Y;
+    g.C = y; g.ldc = Y; g.bias = params + plan->b2_off;
+    rc = launch_gemm(s, g, Y, 1);
+    if (rc) return rc;
+  }
+  // carry out (reset already applied by the last step)
+  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(cat + static_cast<size_t>(T) * rows * LC + P, LC, h,
+                                                                             H, rows, H);
+  B200PPO_LAUNCH_CHECK();
+  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(ws + L.c_cur, H, c, H, rows, H);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
+                                         const float* x, const float* d_y, const uint8_t* done, const int32_t* inds,
+                                         int32_t B, int32_t T, int32_t rows, float* ws, float* grad) {
+  int rc = check_plan_tc(plan);
+  if (rc) return rc;
+  if (T <= 0 || rows <= 0 || B <= 0 || !params || !x || !d_y || !ws || !grad) return B200PPO_EINVAL;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return B200PPO_EALIGN;
+  rc = set_attrs_tc();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const SeqLayout L = seq_layout(*plan, T, rows);
+  const int O = plan->obs_dim, P = plan->pre_dim, H = plan->hidden, Y = plan->out_dim;
+  const int R = T * rows, LC = P + H;
+  float* cat = ws + L.cat;
+  float* da = ws + L.da;
+  // dh_post = dY W2^T
+  {
+    GemmArgs g = gemm_defaults();
+    g.A = d_y; g.lda = Y; g.M = R; g.K = Y;
+    g.B = params + plan->w2_off; g.ldb = Y; g.b_nt = 1;
+    g.C = ws + L.dhp; g.ldc = H;
+    rc = launch_gemm(s, g, H, 1);
+    if (rc) return rc;
+  }
+  if (cudaMemsetAsync(ws + L.dc, 0, sizeof(float) * static_cast<size_t>(rows) * H, s) != cudaSuccess)
+    return static_cast<int>(cudaGetLastError());
+  const int n_slices = 4;                                   // one k slice per gate block of Wh's columns
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t so = static_cast<size_t>(t) * rows * H;
+    StepBwdArgs e;
+    e.dhp = ws + L.dhp + so;
+    e.dhr = t == T - 1 ? nullptr : ws + L.dhr; e.n_slices = n_slices; e.slice_stride = static_cast<long long>(rows) * H;
+    e.dc = ws + L.dc;
+    e.gi = ws + L.gi + so; e.gf = ws + L.gf + so; e.gg = ws + L.gg + so; e.go = ws + L.go + so;
+    e.tcc = ws + L.tcc + so; e.cin = ws + L.cin + so;
+    e.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
+    e.inds = inds;
+    e.da = da + static_cast<size_t>(t) * rows * 4 * H;
+    e.rows = rows; e.H = H;
+    lstm_rec_bwd_e_kernel<<<cdiv(static_cast<int64_t>(rows) * (H / 4), 256), 256, 0, s>>>(e);
+    B200PPO_LAUNCH_CHECK();
+    if (t > 0) {
+      // dh_rec[q] = da_t[:, gate q] Wh[:, gate q]^T   (split-K over the four gate blocks)
+      GemmArgs g = gemm_defaults();
+      g.A = e.da; g.lda = 4 * H; g.M = rows; g.K = H;
+      g.B = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H; g.ldb = 4 * H; g.b_nt = 1;
+      g.C = ws + L.dhr; g.ldc = H;
+      g.k_slice = H; g.c_slice_stride = static_cast<long long>(rows) * H;
+      rc = launch_gemm(s, g, H, n_slices, 64);             // 64-column tiles: rows / 128 x H / 64 x 4 CTAs per step
+      if (rc) return rc;
+    }
+  }
+  // du = da Wi^T;  dz1 = du * act'(z1)
+  {
+    GemmArgs g = gemm_defaults();
+    g.A = da; g.lda = 4 * H; g.M = R; g.K = 4 * H;
+    g.B = params + plan->wcat_off; g.ldb = 4 * H; g.b_nt = 1;
+    g.C = ws + L.dz1; g.ldc = P;
+    g.Zmul = ws + L.z1; g.ldz = P; g.act_z = plan->act;
+    rc = launch_gemm(s, g, P, 1);
+    if (rc) return rc;
+  }
+  // weight gradients (x: the NORMALISED observations the forward pass saw)
+  rc = launch_tn(s, cat, LC, 0, LC, B200PPO_ACT_NONE, da, 4 * H, 4 * H, R, L.S_cat, ws + L.part, ws + L.bpart,
+                 grad + plan->wcat_off, grad + plan->bl_off);
+  if (rc) return rc;
+  rc = launch_tn(s, x, O, 0, O, B200PPO_ACT_NONE, ws + L.dz1, P, P, R, L.S_w1, ws + L.part, ws + L.bpart,
+                 grad + plan->w1_off, grad + plan->b1_off);
+  if (rc) return rc;
+  return launch_tn(s, ws + L.hn, H, 0, H, B200PPO_ACT_NONE, d_y, Y, Y, R, L.S_w2, ws + L.part, ws + L.bpart,
+                   grad + plan->w2_off, grad + plan->b2_off);
+}
+
+// test hook: C[M][N] = A[M][K] B (b_nt = 0: B is [K][N]; 1: B is [N][K]) through the generic tile kernel
+extern "C" int b200ppo_rg_gemm_test(void* stream, const float* A, const float* B, float* C, int32_t M, int32_t N,
+                                    int32_t K, int32_t b_nt, int32_t k_slices) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || k_slices < 1 || K % k_slices) return B200PPO_EINVAL;
+  int rc = set_attrs_tc();
+  if (rc) return rc;
+  GemmArgs g = gemm_defaults();
+  g.A = A; g.lda = K; g.M = M; g.K = K / k_slices;
+  g.B = B; g.ldb = b_nt ? K : N; g.b_nt = b_nt;
+  g.C = C; g.ldc = N;
+  g.k_slice = K / k_slices; g.c_slice_stride = static_cast<long long>(M) * N;
+  return launch_gemm(static_cast<cudaStream_t>(stream), g, N, k_slices);
+}
+
+// test hook: W[Kdim][N] = A[rows][Kdim]^T D[rows][N], b[N] = column sums of D
+extern "C" int b200ppo_rg_tn_test(void* stream, const float* A, const float* D, int32_t rows, int32_t Kdim, int32_t N,
+                                  int32_t S, float* scratch, float* W, float* b) {
+  if (!A || !D || !scratch || !W || rows <= 0 || Kdim <= 0 || N <= 0 || S < 1 || S > 64) return B200PPO_EINVAL;
+  int rc = set_attrs_tc();
+  if (rc) return rc;
+  float* part = scratch;
+  float* bpart = scratch + static_cast<size_t>(S) * Kdim * N;
+  return launch_tn(static_cast<cudaStream_t>(stream), A, Kdim, 0, Kdim, B200PPO_ACT_NONE, D, N, N, rows, S, part, bpart, W, b);
+}

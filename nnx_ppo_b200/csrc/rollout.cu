@@ -231,6 +231,16 @@ __global__ void synth_init_keys_kernel(Key k, int B, uint32_t* __restrict__ keys
   }
 }
 
+__global__ void split_keys_dev_kernel(const uint32_t* __restrict__ key, int64_t first, int count,
+                                      uint32_t* __restrict__ keys) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    const Key o = split_at(Key{key[0], key[1]}, static_cast<uint32_t>(first + i));
+    keys[2 * i] = o.a;
+    keys[2 * i + 1] = o.b;
+  }
+}
+
 __global__ void synth_reset_kernel(const uint32_t* __restrict__ keys, int B, int O, int max_len,
                                    float* __restrict__ obs, int32_t* __restrict__ counter,
                                    uint32_t* __restrict__ term) {
@@ -666,6 +676,14 @@ int check_plan(const b200ppo_plan* p) {
 extern "C" int b200ppo_synth_init_keys(void* stream, uint32_t k0, uint32_t k1, int32_t B, uint32_t* keys_out) {
   if (B <= 0 || !keys_out) return B200PPO_EINVAL;
   synth_init_keys_kernel<<<cdiv(B, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(Key{k0, k1}, B, keys_out);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_split_keys_dev(void* stream, const uint32_t* key, int64_t first, int32_t count, uint32_t* keys_out) {
+  if (count < 0 || first < 0 || !key || (count > 0 && !keys_out)) return B200PPO_EINVAL;
+  if (count == 0) return 0;
+  split_keys_dev_kernel<<<cdiv(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(key, first, count, keys_out);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

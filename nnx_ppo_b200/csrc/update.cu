@@ -1293,6 +1293,7 @@ extern "C" float* b200ppo_update_debug_ptr(const b200ppo_plan* plan, int32_t T, 
     case 2: return w + L.za[plan->actor.n_layers - 1];
     case 3: return w + L.da[plan->actor.n_layers - 1];
     case 4: return w + L.dc[plan->critic.n_layers - 1];
+    case 5: return w + L.xhat;
     default: return nullptr;
   }
 }

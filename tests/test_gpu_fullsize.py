@@ -172,8 +172,8 @@ def test_hyper_parameters_are_runtime_data_of_one_graph(dev):
         if eng.graph is not None:
             graphs.add(id(eng.graph))
         if it < 6:                                                 # the oracle follows the same schedule
-            ots, om = oppo.ppo_step(oe, ots, B, T, gae_lambda=lam, gamma=gamma, clip_range=clip, lr=lr,
-                                    n_epochs=E, n_minibatches=M)
+            ots, om = oppo.ppo_step(oe, ots, B, T, gae_lambda=lam, discounting_factor=gamma, clip_range=clip,
+                                    learning_rate=lr, n_epochs=E, n_minibatches=M)
             for k in ("losses/actor/mean", "losses/critic/mean"):
                 assert abs(m[k] - om[k]) < 2e-4 * max(1.0, abs(om[k])), (it, k, m[k], om[k])
             d = np.abs(net.params_logical() - onet.flat_params())

@@ -478,7 +478,7 @@ def _iterations(dev, cfg):
         # Adam moves each parameter by at most lr per update; rounding differences in tiny
         # gradients can flip individual steps, so compare against a few-steps budget
         assert np.abs(p - po).max() < cfg.get("pmax", 1e-4 * 4), np.abs(p - po).max()
-        assert np.mean(np.abs(p - po)) < 2e-6
+        assert np.mean(np.abs(p - po)) < cfg.get("pmean", 2e-6), np.mean(np.abs(p - po))
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
         assert np.allclose(net.normalizer.M2.numpy(), onet.M2, rtol=2e-3)
         assert np.allclose(ts.env_states.obs.cpu().numpy(), ots.env_state.obs, rtol=1e-3, atol=1e-3)

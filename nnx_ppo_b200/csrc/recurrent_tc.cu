@@ -64,6 +64,7 @@ struct GemmArgs {
   // epilogue: C[r * ldc + n] = acc + bias[n]   (n = global column); optional C2 = act(C); optional
   //           C = acc * act'(Zmul[r * ldz + n])
   float* C; int ldc;
+  int c_planes; int c_cols4;                   // c_planes: C is stored as planes [row / 128][c_cols4][128][4] (see recurrent_tc_step.cuh)
   const float* bias;
   float* C2; int ldc2; int act_c2;
   const float* Zmul; int ldz; int act_z;
@@ -304,19 +305,43 @@ __global__ void __launch_bounds__(RT, 1) rg_gemm_kernel(const GemmArgs g) {
   const int sub = warp & 3, cg = warp >> 2;
   const int row = row0 + sub * 32 + lane;
   float* Cb = g.C + static_cast<long long>(slice) * g.c_slice_stride;
+  const bool vec_c = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0;
   for (int c = cg * 16; c < g.N; c += 32) {
     float v[16];
     tc::tmem_ld16(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
     if (row < g.M) {
+      const int n0 = ccol0 + c;
+      // every global operand of the 16 columns is fetched before the first store (a load -> store -> load chain
+      // per column cost one memory round trip each: 27 us for a 256-column tile, profiles/r2_recurrent_notes.md)
+      float bz[16], zz[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int n = ccol0 + c + i;
-        if (n < g.n_real) {
-          float val = v[i];
-          if (g.bias != nullptr) val += g.bias[n];
-          if (g.Zmul != nullptr) val *= act_grad(g.Zmul[static_cast<size_t>(row) * g.ldz + n], g.act_z);
-          Cb[static_cast<size_t>(row) * g.ldc + n] = val;
-          if (g.C2 != nullptr) g.C2[static_cast<size_t>(row) * g.ldc2 + n] = act_fwd(val, g.act_c2);
+        bz[i] = (g.bias != nullptr && n0 + i < g.n_real) ? g.bias[n0 + i] : 0.0f;
+        zz[i] = (g.Zmul != nullptr && n0 + i < g.n_real) ? g.Zmul[static_cast<size_t>(row) * g.ldz + n0 + i] : 0.0f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] += bz[i];
+        if (g.Zmul != nullptr) v[i] *= act_grad(zz[i], g.act_z);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + 4 * i;
+        if (n >= g.n_real) break;
+        const float4 val = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (g.c_planes) {
+          *reinterpret_cast<float4*>(Cb + (static_cast<size_t>(row >> 7) * g.c_cols4 + (n >> 2)) * (RM * 4) + (row & (RM - 1)) * 4) = val;
+        } else if (vec_c && n + 3 < g.n_real) {
+          *reinterpret_cast<float4*>(Cb + static_cast<size_t>(row) * g.ldc + n) = val;
+        } else {
+          const float vv[4] = {val.x, val.y, val.z, val.w};
+          for (int j = 0; j < 4; ++j)
+            if (n + j < g.n_real) Cb[static_cast<size_t>(row) * g.ldc + n + j] = vv[j];
+        }
+        if (g.C2 != nullptr) {
+          const float vv[4] = {val.x, val.y, val.z, val.w};
+          for (int j = 0; j < 4; ++j)
+            if (n + j < g.n_real) g.C2[static_cast<size_t>(row) * g.ldc2 + n + j] = act_fwd(vv[j], g.act_c2);
         }
       }
     }
@@ -324,142 +349,7 @@ __global__ void __launch_bounds__(RT, 1) rg_gemm_kernel(const GemmArgs g) {
   pipe_fini(p);
 }
 
-// ------------------------------------------------------------------------------------------
-// recurrent step, forward: a = gx_t + h_in Wh (this CTA: 128 rows x 16 hidden units x 4 gates), then
-//   i, f, o = sigmoid, g = tanh;  c' = f c + i g;  h' = o tanh(c');  carry <- done ? 0 : (c', h')
-// ------------------------------------------------------------------------------------------
-struct StepFwdArgs {
-  GemmArgs g;                  // A = h_in (lda = P + H), B = Wh (b_nt = 0, b_unit = 16, b_gate_stride = H), N = 64
-  const float* gx;             // [rows][4H], bias included
-  float* c_cur;                // [rows][H]  in: c entering the step, out: c handed on (reset applied)
-  float* h_next; int ld_hn;    // where the carry h handed on goes (row stride): cat[t + 1] + P, or the h buffer itself
-  float* hn;                   // [rows][H] pre-reset h' (nullable)
-  float* gi; float* gf; float* gg; float* go; float* tcc; float* cin;   // activation cache [rows][H] (all or none)
-  const uint8_t* done; const int32_t* inds;    // done[inds ? inds[row] : row] (nullable: no reset here)
-  int H;
-};
-
-__global__ void __launch_bounds__(RT, 1) lstm_rec_fwd_kernel(const StepFwdArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bars[3];
-  __shared__ uint32_t tmem_slot;
-  Pipe p;
-  pipe_init(p, smem, bars, &tmem_slot, 4 * UT);
-  const int row0 = blockIdx.x * RM;
-  const int u_base = blockIdx.y * UT;
-  gemm_mainloop<2>(a.g, p, row0, a.g.a_k0, a.g.b_k0, u_base);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sub = warp & 3, ub = warp >> 2;
-  const int row = row0 + sub * 32 + lane;
-  const int H = a.H;
-  const int u0 = u_base + 8 * ub;                    // this thread: units u0 .. u0 + 7 of its row
-  const bool ok = row < a.g.M;
-  // operands of the gate math that do not depend on the accumulator: fetched before the wait
-  float gxv[4][8], cv[8];
-  bool dn = false;
-  if (ok) {
-    const float* gr = a.gx + static_cast<size_t>(row) * 4 * H + u0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 lo = *reinterpret_cast<const float4*>(gr + q * H), hi = *reinterpret_cast<const float4*>(gr + q * H + 4);
-      gxv[q][0] = lo.x; gxv[q][1] = lo.y; gxv[q][2] = lo.z; gxv[q][3] = lo.w;
-      gxv[q][4] = hi.x; gxv[q][5] = hi.y; gxv[q][6] = hi.z; gxv[q][7] = hi.w;
-    }
-    const float4 c0 = *reinterpret_cast<const float4*>(a.c_cur + static_cast<size_t>(row) * H + u0);
-    const float4 c1 = *reinterpret_cast<const float4*>(a.c_cur + static_cast<size_t>(row) * H + u0 + 4);
-    cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
-    if (a.done != nullptr) dn = a.done[a.inds ? a.inds[row] : row] != 0;
-  }
-  wait_acc(p);
-  float acc[4][8];
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    tmem_ld8(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(q * UT + 8 * ub), acc[q]);
-  if (ok) {
-    float c2[8], h2[8], iv[8], fv[8], gv[8], ov[8], tv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      iv[k] = sigmoid_f(acc[0][k] + gxv[0][k]);
-      fv[k] = sigmoid_f(acc[1][k] + gxv[1][k]);
-      gv[k] = tanhf(acc[2][k] + gxv[2][k]);
-      ov[k] = sigmoid_f(acc[3][k] + gxv[3][k]);
-      c2[k] = __fadd_rn(__fmul_rn(fv[k], cv[k]), __fmul_rn(iv[k], gv[k]));
-      tv[k] = tanhf(c2[k]);
-      h2[k] = __fmul_rn(ov[k], tv[k]);
-    }
-    auto st8 = [](float* dst, const float (&v)[8]) {
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    };
-    const size_t o = static_cast<size_t>(row) * H + u0;
-    if (a.gi != nullptr) {
-      st8(a.gi + o, iv); st8(a.gf + o, fv); st8(a.gg + o, gv); st8(a.go + o, ov); st8(a.tcc + o, tv); st8(a.cin + o, cv);
-    }
-    if (a.hn != nullptr) st8(a.hn + o, h2);
-    if (dn) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { c2[k] = 0.0f; h2[k] = 0.0f; }
-    }
-    st8(a.c_cur + o, c2);
-    st8(a.h_next + static_cast<size_t>(row) * a.ld_hn + u0, h2);
-  }
-  pipe_fini(p);
-}
-
-// ------------------------------------------------------------------------------------------
-// recurrent step, backward, element-wise part (oracle/recurrent.py ppo_loss_and_grads, BPTT loop):
-//   dh = dh_post_t + keep * sum_q dh_rec[q];  dc = dh o (1 - tc^2) + keep * dc_next;  da = gate gradients
-// ------------------------------------------------------------------------------------------
-struct StepBwdArgs {
-  const float* dhp;            // [rows][H] dY_t W2^T
-  const float* dhr; int n_slices; long long slice_stride;   // split-K partials of da_{t+1} Wh^T (nullable: last step)
-  float* dc;                   // [rows][H] in: dc_next, out: dc handed to step t - 1
-  const float* gi; const float* gf; const float* gg; const float* go; const float* tcc; const float* cin;
-  const uint8_t* done; const int32_t* inds;
-  float* da;                   // [rows][4H]
-  int rows, H;
-};
-
-__global__ void __launch_bounds__(256) lstm_rec_bwd_e_kernel(const StepBwdArgs a) {
-  const int H4 = a.H >> 2;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.rows * H4) return;
-  const int row = idx / H4, k = (idx - row * H4) * 4;
-  const size_t o = static_cast<size_t>(row) * a.H + k;
-  const bool dn = a.done != nullptr && a.done[a.inds ? a.inds[row] : row] != 0;
-  const float keep = dn ? 0.0f : 1.0f;
-  auto ld = [&](const float* p) { return *reinterpret_cast<const float4*>(p + o); };
-  float4 dh = ld(a.dhp);
-  if (a.dhr != nullptr) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < a.n_slices; ++q) {                   // fixed order: deterministic
-      const float4 v = *reinterpret_cast<const float4*>(a.dhr + q * a.slice_stride + o);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-    dh.x += keep * s.x; dh.y += keep * s.y; dh.z += keep * s.z; dh.w += keep * s.w;
-  }
-  const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dc);
-  const float dhv[4] = {dh.x, dh.y, dh.z, dh.w};
-  const float iv[4] = {i4.x, i4.y, i4.z, i4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
-  const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
-  const float dcv[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
-  float di[4], df[4], dg[4], dO[4], dco[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float dc = dhv[j] * ov[j] * (1.0f - tv[j] * tv[j]) + keep * dcv[j];
-    di[j] = dc * gv[j] * iv[j] * (1.0f - iv[j]);
-    df[j] = dc * cv[j] * fv[j] * (1.0f - fv[j]);
-    dg[j] = dc * iv[j] * (1.0f - gv[j] * gv[j]);
-    dO[j] = dhv[j] * tv[j] * ov[j] * (1.0f - ov[j]);
-    dco[j] = dc * fv[j];
-  }
-  float* dr = a.da + static_cast<size_t>(row) * 4 * a.H + k;
-  *reinterpret_cast<float4*>(dr) = make_float4(di[0], di[1], di[2], di[3]);
-  *reinterpret_cast<float4*>(dr + a.H) = make_float4(df[0], df[1], df[2], df[3]);
-  *reinterpret_cast<float4*>(dr + 2 * a.H) = make_float4(dg[0], dg[1], dg[2], dg[3]);
-  *reinterpret_cast<float4*>(dr + 3 * a.H) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-  *reinterpret_cast<float4*>(a.dc + o) = make_float4(dco[0], dco[1], dco[2], dco[3]);
-}
+#include "recurrent_tc_step.cuh"
 
 // ------------------------------------------------------------------------------------------
 // "TN" GEMM for the weight gradients:  part[s][m][n] = sum_{r in split s} A[r][a_col0 + m] * D[r][d_col0 + n]
@@ -678,7 +568,19 @@ __global__ void __launch_bounds__(256) rg_copy_rows_kernel(const float* __restri
 // host side
 // ------------------------------------------------------------------------------------------
 struct SeqLayout {
-  size_t z1, cat, gx, gi, gf, gg, go, tcc, cin, hn, c_cur, da, dhp, dhr, dc, dz1, part, bpart, total;
+  // row-major matrices over the R = T * rows row space
+  size_t z1, cat, hn, da, dz1;
+  // plane layouts (recurrent_tc_step.cuh)
+  size_t gxp, dhpp;                       // over the R row space: [R / 128][cols / 4][PLC]
+  size_t hp;                              // A planes of h: [2 buffers][2 halves][tiles][H / 4][PLA]
+  size_t cp, dcp;                         // state planes [tiles][H / 4][PLC]
+  size_t cache[6];                        // gi gf gg go tc cin: [T][tiles][H / 4][PLC]
+  size_t dap;                             // A planes of da: [2 halves][tiles][4 gates][H / 4][PLA]
+  size_t dhr;                             // split-K partials [4][tiles][H / 4][PLC]
+  size_t whf, whb;                        // weight planes
+  size_t part, bpart, total;
+  int tiles, NBT, nbt;
+  size_t hp_half, hp_buf, st_tile, cache_step, dap_half;
   int S_cat, S_w1, S_w2;
 };
 
@@ -693,24 +595,39 @@ int split_for(int tiles, int rows) {
   return S;
 }
 
+int mma_n(int n);
+
 SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   SeqLayout L;
   const size_t R = static_cast<size_t>(T) * rows;
-  const size_t O = p.obs_dim, P = p.pre_dim, H = p.hidden, Y = p.out_dim;
-  (void)O;
+  const size_t P = p.pre_dim, H = p.hidden, Y = p.out_dim;
+  const size_t planes = H / 4;
+  L.tiles = cdiv(rows, RM);
+  const size_t tiles = L.tiles, Rtiles = cdiv(static_cast<int64_t>(R), RM);
+  L.NBT = mma_n(static_cast<int>(H < 64 ? H : 64));
+  L.nbt = cdiv(static_cast<int64_t>(H), L.NBT);
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
   L.z1 = take(R * P);
   L.cat = take((R + rows) * (P + H));
-  L.gx = take(R * 4 * H);
-  L.gi = take(R * H); L.gf = take(R * H); L.gg = take(R * H); L.go = take(R * H); L.tcc = take(R * H); L.cin = take(R * H);
   L.hn = take(R * H);
-  L.c_cur = take(static_cast<size_t>(rows) * H);
   L.da = take(R * 4 * H);
-  L.dhp = take(R * H);
-  L.dhr = take(4 * static_cast<size_t>(rows) * H);
-  L.dc = take(static_cast<size_t>(rows) * H);
   L.dz1 = take(R * P);
+  L.gxp = take(Rtiles * H * PLC);                     // 4H / 4 = H planes per row tile
+  L.dhpp = take(Rtiles * planes * PLC);
+  L.hp_half = tiles * planes * PLA;
+  L.hp_buf = 2 * L.hp_half;
+  L.hp = take(2 * L.hp_buf);
+  L.st_tile = planes * PLC;
+  L.cp = take(tiles * L.st_tile);
+  L.dcp = take(tiles * L.st_tile);
+  L.cache_step = tiles * L.st_tile;
+  for (int i = 0; i < 6; ++i) L.cache[i] = take(static_cast<size_t>(T) * L.cache_step);
+  L.dap_half = tiles * 4 * planes * PLA;
+  L.dap = take(2 * L.dap_half);
+  L.dhr = take(4 * tiles * L.st_tile);
+  L.whf = take((H / UT) * 2 * planes * plb(4 * UT));
+  L.whb = take(static_cast<size_t>(L.nbt) * 4 * 2 * planes * plb(L.NBT));
   const int Rr = static_cast<int>(R);
   L.S_cat = split_for(cdiv(P + H, RM) * cdiv(4 * H, 256), Rr);
   L.S_w1 = split_for(cdiv(p.obs_dim, RM), Rr);
@@ -755,7 +672,11 @@ int set_attrs_tc() {
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(rg_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return static_cast<int>(e);
-  e = cudaFuncSetAttribute(lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  e = cudaFuncSetAttribute(lstm_step_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(SP_NS * sp_slot_bytes(4 * UT)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_step_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(SP_NS * sp_slot_bytes(64)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(rg_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(2 * tn_planes_bytes(256) + tn_raw_bytes(256)));
@@ -769,7 +690,7 @@ GemmArgs gemm_defaults() {
   g.A = nullptr; g.lda = 0; g.a_k0 = 0; g.M = 0; g.K = 0; g.act_a = B200PPO_ACT_NONE; g.a_mean = nullptr; g.a_std = nullptr;
   g.B = nullptr; g.ldb = 0; g.b_nt = 0; g.b_col0 = 0; g.b_unit_log2 = 30; g.b_gate_stride = 0; g.b_k0 = 0;
   g.N = 16; g.n_log2 = 4; g.n_real = 0; g.tile_stride = 0;
-  g.C = nullptr; g.ldc = 0; g.bias = nullptr; g.C2 = nullptr; g.ldc2 = 0; g.act_c2 = B200PPO_ACT_NONE;
+  g.C = nullptr; g.ldc = 0; g.c_planes = 0; g.c_cols4 = 0; g.bias = nullptr; g.C2 = nullptr; g.ldc2 = 0; g.act_c2 = B200PPO_ACT_NONE;
   g.Zmul = nullptr; g.ldz = 0; g.act_z = B200PPO_ACT_NONE;
   g.k_slice = 0; g.c_slice_stride = 0;
   return g;
@@ -833,7 +754,7 @@ extern "C" int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* pl
 
 extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t backward) {
   if (check_plan_tc(plan) || T <= 0) return -1;
-  if (!backward) return 2 /* carry in */ + 2 /* pre, proj */ + T + 1 /* post */ + 2 /* carry out */;
+  if (!backward) return 1 /* weight planes */ + 2 /* carry in */ + 2 /* pre, proj */ + T + 1 /* post */ + 2 /* carry out */;
   return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */;
 }
 
@@ -851,14 +772,29 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const SeqLayout L = seq_layout(*plan, T, rows);
   const int O = plan->obs_dim, P = plan->pre_dim, H = plan->hidden, Y = plan->out_dim;
-  const int R = T * rows, LC = P + H;
+  const int R = T * rows, LC = P + H, planes = H / 4;
   float* z1 = ws + L.z1;
   float* cat = ws + L.cat;
-  // carry in: cat[0][:, P:] = h, c_cur = c
-  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(h, H, cat + P, LC, rows, H);
-  B200PPO_LAUNCH_CHECK();
-  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(c, H, ws + L.c_cur, H, rows, H);
-  B200PPO_LAUNCH_CHECK();
+  const float* Wh = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H;
+  // Wh -> operand planes (forward and transposed forms)
+  {
+    PrepWhArgs a;
+    a.Wh = Wh; a.H = H; a.NBT = L.NBT; a.whf = ws + L.whf; a.whb = ws + L.whb;
+    const long long n = static_cast<long long>(H / UT) * planes * 64 + static_cast<long long>(L.nbt) * 4 * planes * L.NBT;
+    lstm_prep_wh_kernel<<<cdiv(n, 256), 256, 0, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+  }
+  // carry in: h -> A planes of step 0 (and row-major cat[0][:, P:] for the weight gradients), c -> state planes
+  {
+    CarryInArgs a;
+    a.c = c; a.h = h; a.rows = rows; a.H = H;
+    a.hp_hi = ws + L.hp; a.hp_lo = ws + L.hp + L.hp_half; a.hp_tile = static_cast<long long>(planes) * PLA;
+    a.cp = ws + L.cp; a.cp_tile = static_cast<long long>(L.st_tile);
+    lstm_carry_in_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(a);
+    B200PPO_LAUNCH_CHECK();
+    rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(h, H, cat + P, LC, rows, H);
+    B200PPO_LAUNCH_CHECK();
+  }
   // z1 = x W1 + b1;  u = act(z1) -> cat[:, :P]
   {
     GemmArgs g = gemm_defaults();
@@ -869,37 +805,37 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     rc = launch_gemm(s, g, P, 1);
     if (rc) return rc;
   }
-  // gx = u Wi + bl
+  // gx = u Wi + bl, stored as planes over the R row space
   {
     GemmArgs g = gemm_defaults();
     g.A = cat; g.lda = LC; g.M = R; g.K = P;
     g.B = params + plan->wcat_off; g.ldb = 4 * H;
-    g.C = ws + L.gx; g.ldc = 4 * H; g.bias = params + plan->bl_off;
+    g.C = ws + L.gxp; g.c_planes = 1; g.c_cols4 = H; g.bias = params + plan->bl_off;
     rc = launch_gemm(s, g, 4 * H, 1);
     if (rc) return rc;
   }
   // the recurrence
   for (int t = 0; t < T; ++t) {
-    StepFwdArgs a;
-    a.g = gemm_defaults();
-    a.g.A = cat + static_cast<size_t>(t) * rows * LC; a.g.lda = LC; a.g.a_k0 = P; a.g.M = rows; a.g.K = H;
-    a.g.B = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H; a.g.ldb = 4 * H;
-    a.g.b_nt = 0; a.g.b_unit_log2 = 4; a.g.b_gate_stride = H; a.g.N = 4 * UT; a.g.n_log2 = 6; a.g.n_real = 4 * H;
-    a.gx = ws + L.gx + static_cast<size_t>(t) * rows * 4 * H;
-    a.c_cur = ws + L.c_cur;
-    a.h_next = cat + static_cast<size_t>(t + 1) * rows * LC + P; a.ld_hn = LC;
-    const size_t so = static_cast<size_t>(t) * rows * H;
-    a.hn = ws + L.hn + so;
+    StepFwd2Args a;
+    const size_t cur = static_cast<size_t>(t & 1) * L.hp_buf, nxt = static_cast<size_t>((t + 1) & 1) * L.hp_buf;
+    a.hp_hi = ws + L.hp + cur; a.hp_lo = ws + L.hp + cur + L.hp_half; a.hp_tile = static_cast<long long>(planes) * PLA;
+    a.whf = ws + L.whf; a.whf_tile = 2LL * planes * plb(4 * UT);
+    a.gxp = ws + L.gxp; a.r0 = static_cast<long long>(t) * rows; a.gx_cols4 = H;
+    a.cp = ws + L.cp; a.cp_tile = static_cast<long long>(L.st_tile);
+    a.hn_hi = ws + L.hp + nxt; a.hn_lo = ws + L.hp + nxt + L.hp_half;
+    a.h_next_rm = cat + static_cast<size_t>(t + 1) * rows * LC + P; a.ld_hn = LC;
+    a.hn_rm = ws + L.hn + static_cast<size_t>(t) * rows * H;
     if (keep_cache) {
-      a.gi = ws + L.gi + so; a.gf = ws + L.gf + so; a.gg = ws + L.gg + so; a.go = ws + L.go + so;
-      a.tcc = ws + L.tcc + so; a.cin = ws + L.cin + so;
+      const size_t so = static_cast<size_t>(t) * L.cache_step;
+      a.gi = ws + L.cache[0] + so; a.gf = ws + L.cache[1] + so; a.gg = ws + L.cache[2] + so;
+      a.go = ws + L.cache[3] + so; a.tcc = ws + L.cache[4] + so; a.cin = ws + L.cache[5] + so;
     } else {
       a.gi = a.gf = a.gg = a.go = a.tcc = a.cin = nullptr;
     }
     a.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
     a.inds = inds;
-    a.H = H;
-    lstm_rec_fwd_kernel<<<dim3(cdiv(rows, RM), H / UT), RT, 2 * stage_bytes_nn(4 * UT), s>>>(a);
+    a.rows = rows; a.H = H;
+    lstm_step_fwd2_kernel<<<dim3(L.tiles, H / UT), RT, SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
   // y = h' W2 + b2
@@ -915,7 +851,8 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
   rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(cat + static_cast<size_t>(T) * rows * LC + P, LC, h,
                                                                              H, rows, H);
   B200PPO_LAUNCH_CHECK();
-  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(ws + L.c_cur, H, c, H, rows, H);
+  lstm_carry_out_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(ws + L.cp, static_cast<long long>(L.st_tile),
+                                                                                            c, rows, H);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -932,44 +869,47 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const SeqLayout L = seq_layout(*plan, T, rows);
   const int O = plan->obs_dim, P = plan->pre_dim, H = plan->hidden, Y = plan->out_dim;
-  const int R = T * rows, LC = P + H;
+  const int R = T * rows, LC = P + H, planes = H / 4;
   float* cat = ws + L.cat;
   float* da = ws + L.da;
-  // dh_post = dY W2^T
+  // dh_post = dY W2^T, as planes over the R row space
   {
     GemmArgs g = gemm_defaults();
     g.A = d_y; g.lda = Y; g.M = R; g.K = Y;
     g.B = params + plan->w2_off; g.ldb = Y; g.b_nt = 1;
-    g.C = ws + L.dhp; g.ldc = H;
+    g.C = ws + L.dhpp; g.c_planes = 1; g.c_cols4 = planes;
     rc = launch_gemm(s, g, H, 1);
     if (rc) return rc;
   }
-  if (cudaMemsetAsync(ws + L.dc, 0, sizeof(float) * static_cast<size_t>(rows) * H, s) != cudaSuccess)
+  if (cudaMemsetAsync(ws + L.dcp, 0, sizeof(float) * L.tiles * L.st_tile, s) != cudaSuccess)
     return static_cast<int>(cudaGetLastError());
-  const int n_slices = 4;                                   // one k slice per gate block of Wh's columns
+  const long long dap_slice = static_cast<long long>(planes) * PLA, dap_tile = 4 * dap_slice;
+  const long long dhr_slice = static_cast<long long>(L.tiles) * L.st_tile;
   for (int t = T - 1; t >= 0; --t) {
-    const size_t so = static_cast<size_t>(t) * rows * H;
-    StepBwdArgs e;
-    e.dhp = ws + L.dhp + so;
-    e.dhr = t == T - 1 ? nullptr : ws + L.dhr; e.n_slices = n_slices; e.slice_stride = static_cast<long long>(rows) * H;
-    e.dc = ws + L.dc;
-    e.gi = ws + L.gi + so; e.gf = ws + L.gf + so; e.gg = ws + L.gg + so; e.go = ws + L.go + so;
-    e.tcc = ws + L.tcc + so; e.cin = ws + L.cin + so;
+    const size_t so = static_cast<size_t>(t) * L.cache_step;
+    StepBwd2Args e;
+    e.dhp = ws + L.dhpp; e.r0 = static_cast<long long>(t) * rows; e.dhp_cols4 = planes;
+    e.dhr = t == T - 1 ? nullptr : ws + L.dhr; e.dhr_slice = dhr_slice; e.n_slices = 4;
+    e.dcp = ws + L.dcp;
+    e.gi = ws + L.cache[0] + so; e.gf = ws + L.cache[1] + so; e.gg = ws + L.cache[2] + so;
+    e.go = ws + L.cache[3] + so; e.tcc = ws + L.cache[4] + so; e.cin = ws + L.cache[5] + so;
+    e.st_tile = static_cast<long long>(L.st_tile);
     e.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
     e.inds = inds;
-    e.da = da + static_cast<size_t>(t) * rows * 4 * H;
+    e.da_rm = da + static_cast<size_t>(t) * rows * 4 * H;
+    e.dap_hi = ws + L.dap; e.dap_lo = ws + L.dap + L.dap_half; e.dap_tile = dap_tile; e.dap_slice = dap_slice;
     e.rows = rows; e.H = H;
-    lstm_rec_bwd_e_kernel<<<cdiv(static_cast<int64_t>(rows) * (H / 4), 256), 256, 0, s>>>(e);
+    lstm_step_bwd2_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(e);
     B200PPO_LAUNCH_CHECK();
     if (t > 0) {
       // dh_rec[q] = da_t[:, gate q] Wh[:, gate q]^T   (split-K over the four gate blocks)
-      GemmArgs g = gemm_defaults();
-      g.A = e.da; g.lda = 4 * H; g.M = rows; g.K = H;
-      g.B = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H; g.ldb = 4 * H; g.b_nt = 1;
-      g.C = ws + L.dhr; g.ldc = H;
-      g.k_slice = H; g.c_slice_stride = static_cast<long long>(rows) * H;
-      rc = launch_gemm(s, g, H, n_slices, 64);             // 64-column tiles: rows / 128 x H / 64 x 4 CTAs per step
-      if (rc) return rc;
+      StepBwdGemmArgs g;
+      g.dap_hi = e.dap_hi; g.dap_lo = e.dap_lo; g.dap_tile = dap_tile; g.dap_slice = dap_slice;
+      g.whb = ws + L.whb; g.whb_slice = 2LL * planes * plb(L.NBT); g.whb_tile = 4 * g.whb_slice;
+      g.dhr = ws + L.dhr; g.dhr_slice = dhr_slice; g.st_tile = static_cast<long long>(L.st_tile);
+      g.rows = rows; g.H = H; g.NBT = L.NBT;
+      lstm_step_bwd_gemm_kernel<<<dim3(L.tiles, L.nbt, 4), RT, SP_NS * sp_slot_bytes(L.NBT), s>>>(g);
+      B200PPO_LAUNCH_CHECK();
     }
   }
   // du = da Wi^T;  dz1 = du * act'(z1)

@@ -1,9 +1,15 @@
 """2-GPU checks of the data-parallel engine (needs >= 2 visible GPUs; skipped otherwise).
 
-The peer-memory exchange (epoch flags + P2P loads inside the GAE / loss / Adam kernels,
-include/b200ppo.h) must give the same parameters as the NCCL all-reduce path: with two ranks the
-rank-ordered sum a + b is the same float as NCCL's, so the comparison is bit-exact; and the replicas
-must stay in sync (identical parameters on both ranks).
+The peer-memory exchange (stores into every rank's comm buffer + epoch flags inside the GAE / loss /
+Adam kernels, include/b200ppo.h) must give the same parameters as the NCCL all-reduce path: with two
+ranks the rank-ordered sum a + b is the same float as NCCL's, so the comparison is bit-exact; and the
+replicas must stay in sync (identical parameters on both ranks).  Also with clip_by_global_norm (the
+norm is taken from the summed gradient inside the exchange launch) and with the gradient norm logged:
+the norm is identical on every rank and must not be multiplied by the world size when the metrics are
+summed over ranks.
+
+The driver's round-end GPU box has one GPU (this file is skipped there); the log of a 2-GPU run of this
+file is kept under profiles/ (r2_gputest_2gpu.log).
 """
 import os
 import sys
@@ -17,7 +23,7 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, p2p, out_dir):
+def _worker(rank, world, port, p2p, out_dir, clip=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank), B200PPO_P2P="1" if p2p else "0")
     import torch
@@ -30,31 +36,35 @@ def _worker(rank, world, port, p2p, out_dir):
     from nnx_ppo_b200.networks.factories import make_mlp_actor_critic
     env = SyntheticEnv(24, 4, 16, 2048)
     nets = make_mlp_actor_critic(24, 4, [64, 64], [128, 128], Rngs(0))
-    ts = ppo.new_training_state(env, nets, 256, 17)
+    from nnx_ppo_b200.algorithms.types import LoggingLevel
+    ts = ppo.new_training_state(env, nets, 256, 17, gradient_clipping=clip)
     hyper = (256, 8, 0.95, 0.99, 0.2, True, False, 2, 4)
+    lvl = LoggingLevel.LOSSES | (LoggingLevel.GRAD_NORM if clip is not None else LoggingLevel.NONE)
     metrics = None
     for _ in range(3):                       # iteration 0 eager, 1 captures the graph, 2 replays it
-        ts, metrics = ppo.ppo_step(env, ts, *hyper)
+        ts, metrics = ppo.ppo_step(env, ts, *hyper, logging_level=lvl)
     eng = ppo._engine_for(env, ts, 256, 8, 0.95, 0.99, 0.2, True, 2, 4, 1.0)
     assert eng.p2p == bool(p2p)
     torch.cuda.synchronize()
     np.savez(os.path.join(out_dir, f"r{rank}_{int(p2p)}.npz"), params=eng.net.arena.cpu().numpy(),
-             mu=eng.opt.mu.cpu().numpy(), m=np.array([float(v) for v in metrics.values()], np.float64))
+             mu=eng.opt.mu.cpu().numpy(), m=np.array([float(v) for v in metrics.values()], np.float64),
+             gn_logged=eng.metrics_host[:, 3].numpy().copy(), gn_last=float(eng.grad.double().norm()))
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)                              # NCCL kernels captured in a graph: skip the slow teardown
 
 
-@pytest.mark.timeout(300)
-def test_peer_exchange_matches_nccl(tmp_path):
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("clip", [None, 0.05])
+def test_peer_exchange_matches_nccl(tmp_path, clip):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     res = {}
-    for p2p, port in ((True, 29611), (False, 29612)):
+    for p2p, port in ((True, 29611 + (2 if clip else 0)), (False, 29612 + (2 if clip else 0))):
         ctx = mp.get_context("spawn")
-        procs = [ctx.Process(target=_worker, args=(r, 2, port, p2p, str(tmp_path))) for r in range(2)]
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, p2p, str(tmp_path), clip)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:
@@ -68,3 +78,11 @@ def test_peer_exchange_matches_nccl(tmp_path):
     np.testing.assert_array_equal(res[(0, True)]["mu"], res[(0, False)]["mu"])
     np.testing.assert_allclose(res[(0, True)]["m"], res[(0, False)]["m"], rtol=1e-6)
     assert np.all(np.isfinite(res[(0, True)]["params"]))
+    if clip is not None:
+        for p2p in (True, False):
+            gn = res[(0, p2p)]["gn_logged"]
+            # the logged norm of the last update is the norm of the summed gradient, not world_size times it
+            assert abs(gn[-1] - res[(0, p2p)]["gn_last"]) < 1e-5 * max(1.0, gn[-1]), (p2p, gn[-1], res[(0, p2p)]["gn_last"])
+            np.testing.assert_array_equal(gn, res[(1, p2p)]["gn_logged"])
+            assert gn.min() > clip                      # the threshold really clips in this test
+        np.testing.assert_allclose(res[(0, True)]["gn_logged"], res[(0, False)]["gn_logged"], rtol=1e-6)

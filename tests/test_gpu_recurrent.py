@@ -148,7 +148,7 @@ def test_recurrent_ppo_step_matches_oracle(cuda_device):
     net = compile_network(nets)
     assert net.recurrent
     u32 = lambda t: t.cpu().numpy().view(np.uint32)
-    for it in range(2):
+    for it in range(3):             # eager iteration, then the captured CUDA graph (capture + replay, replay)
         ts, m = ppo.ppo_step(env, ts, B, T, 0.95, 0.99, 0.2, True, False, E, M)
         tr = {}
         ots, om = orec.ppo_step(oe, ots, B, T, n_epochs=E, n_minibatches=M, trace=tr)
@@ -170,6 +170,39 @@ def test_recurrent_ppo_step_matches_oracle(cuda_device):
         c, h = net.get_carry(ts.network_states)
         assert np.allclose(c.cpu().numpy(), ots.carry[0], atol=2e-4) and np.allclose(h.cpu().numpy(), ots.carry[1], atol=2e-4)
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
+    assert eng.r_seq and eng.r_graph is not None and eng.kernel_launches_per_iter > 0    # tensor-core sequence kernels, one graph
+
+
+def test_recurrent_ffma_fallback_matches_tensor_core_path(cuda_device, monkeypatch):
+    """Sizes the tensor-core kernels do not take (hidden % 16 != 0) run the per-step FFMA kernels; on a size both
+    take, the two paths agree to float32 accuracy."""
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import ppo
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    res = []
+    for mode in ("tc", "ffma"):
+        monkeypatch.setenv("B200PPO_LSTM", mode)
+        nets = make_recurrent_actor_critic(16, 4, 32, 32, [48], Rngs(1))
+        env = SyntheticEnv(16, 4, max_len=10, term_thresh16=3000)
+        ts = ppo.new_training_state(env, nets, 64, 17)
+        for _ in range(3):
+            ts, m = ppo.ppo_step(env, ts, 64, 12, 0.95, 0.99, 0.2, True, False, 2, 2)
+        net = compile_network(nets)
+        eng = next(iter(net.engines.values()))
+        assert eng.r_seq == (mode == "tc")
+        res.append((net.params_logical().copy(), eng.done.cpu().numpy().copy(), m))
+    assert np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][0] - res[1][0]).max() < 4e-4 and np.mean(np.abs(res[0][0] - res[1][0])) < 3e-6
+    nets = make_recurrent_actor_critic(10, 3, 7, 8, [6], Rngs(1))            # hidden 8: FFMA kernels only
+    env = SyntheticEnv(10, 3, max_len=10, term_thresh16=3000)
+    ts = ppo.new_training_state(env, nets, 16, 17)
+    monkeypatch.delenv("B200PPO_LSTM")
+    for _ in range(3):
+        ts, m = ppo.ppo_step(env, ts, 16, 6, 0.95, 0.99, 0.2, True, False, 2, 2)
+    eng = next(iter(compile_network(nets).engines.values()))
+    assert not eng.r_seq and all(np.isfinite(float(v)) for v in m.values())
 
 
 def test_recurrent_network_call_and_eval(cuda_device):

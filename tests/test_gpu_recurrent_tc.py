@@ -134,4 +134,4 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg):
     assert np.abs(outs[0][:n_rec] - ref).max() < 3e-4 * scale, (np.abs(outs[0][:n_rec] - ref).max(), scale)
     assert np.array_equal(outs[0], outs[1])                      # fixed-order sums: bit-reproducible
     assert np.all(outs[0][n_rec:] == 7.0)                        # the critic's slots are not touched
-    assert lib.b200ppo_lstm_seq_num_launches(plan, T, 0) == T + 7 and lib.b200ppo_lstm_seq_num_launches(plan, T, 1) == 2 * T + 10
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, 0) == T + 8 and lib.b200ppo_lstm_seq_num_launches(plan, T, 1) == 2 * T + 10

@@ -274,16 +274,19 @@ int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams
                    uint32_t rng_count_offset, int32_t update_index, int32_t stages);
 /* -------- peer-memory exchange of the data-parallel update (replaces the two per-update NCCL
  * all-reduces of DESIGN.md section 5: advantage moment sums and the flat gradient) ---------------
- * Every rank owns one comm buffer (cudaMalloc'ed, exported with CUDA IPC) holding epoch flags, the
- * per-rank advantage sums and, double-buffered, one gradient slot per source rank.  Everything is
- * PUSHED (remote stores over NVLink, st.release.sys on the flag); readers poll LOCAL flags with
- * ld.acquire.sys and read only their own memory:
- *   GAE kernel    -> writes its (sum a, sum a^2) into every rank's slot, then the flag;
- *   loss kernel   -> waits for all ranks' flags, sums the slots in rank order;
- *   reduce kernel -> pushes its locally reduced gradient into every rank's buffer;
- *   Adam kernel   -> publishes "gradient pushed", waits for all ranks, sums the slots in rank
- *                    order (bit-identical parameters on every rank).
- * epoch = adam count base + update_index + 1 (monotonic; buffers alternate on its parity).       */
+ * Every rank owns one comm buffer (cudaMalloc'ed, exported with CUDA IPC) with, double-buffered on the
+ * parity of the exchange epoch, one slot per source rank for the advantage sums and for the gradient.
+ * Everything is PUSHED: a sender stores each 32-bit word together with the epoch as ONE 8-byte word
+ * {payload, epoch} (single-copy atomic; the idea of NCCL's LL protocol) straight into every rank's buffer
+ * over NVLink; a receiver polls the words of its OWN buffer until the epoch half matches.  No flags, no
+ * system fences, no remote loads, one one-way NVLink latency per exchange:
+ *   GAE kernel  -> its last block pushes (sum a, sum a^2) into every rank's slot;
+ *   loss kernel -> collects all ranks' sums in rank order;
+ *   Adam kernel -> every thread pushes its (locally reduced) gradient element and sums the W slots of its
+ *                  own buffer in rank order (bit-identical parameters on every rank); with
+ *                  clip_by_global_norm the same launch also produces the squared norm of the summed
+ *                  gradient and the clipped optimizer step is a second launch.
+ * epoch = (bufs->comm_epoch ? *comm_epoch : adam count) + update_index + 1 (monotonic, >= 1).            */
 #define B200PPO_MAX_RANKS 16
 int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size);
 int b200ppo_comm_alloc(int64_t bytes, void** out);                 /* zero-initialised device memory */

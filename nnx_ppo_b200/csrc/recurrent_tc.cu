@@ -30,7 +30,9 @@ namespace {
 
 constexpr int RM = 128;        // rows per CTA (UMMA M)
 constexpr int RK = 32;         // k per stage of the NN / NT kernel (4 MMAs of K = 8)
-constexpr int RT = 256;        // threads per CTA
+constexpr int RT = 256;        // staging / epilogue threads per CTA
+constexpr int RTI = RT + 32;   // + one warp that only issues MMAs (an issuing warp that also stages serialises the
+                               //   ~90-cycle-per-MMA issue with its share of the staging: profiles/r2_recurrent_notes.md)
 constexpr int RN_MAX = 256;    // widest N tile
 constexpr int UT = 16;         // hidden units per CTA of the recurrent step (x 4 gates = 64 accumulator columns)
 
@@ -186,6 +188,7 @@ __device__ __forceinline__ void gemm_store_stage(const GemmArgs& g, uint8_t* st,
 struct Pipe {
   uint8_t* smem;
   uint64_t* bar_empty;   // [2]: tcgen05.commit of the MMAs that read the buffer
+  uint64_t* bar_full;    // [2]: the staging warps finished writing the buffer
   uint64_t* bar_done;
   uint32_t tmem_base;
   uint32_t tmem_cols;
@@ -197,14 +200,17 @@ __device__ __forceinline__ uint32_t pow2_cols(int n) {
   return c;
 }
 
-__device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot, int ncols) {
+// bars: [0..1] empty, [2..3] full (`full_count` arrivals each), [4] done
+__device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot, int ncols, int full_count) {
   const int warp = threadIdx.x >> 5;
   p.tmem_cols = pow2_cols(ncols);
   if (warp == 0) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   if (threadIdx.x == 32) {
     tc::mbar_init(&bars[0], 1);
     tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], 1);
+    tc::mbar_init(&bars[2], full_count);
+    tc::mbar_init(&bars[3], full_count);
+    tc::mbar_init(&bars[4], 1);
     tc::mbar_init_fence();
   }
   tc::tc_fence_before();
@@ -212,7 +218,8 @@ __device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars
   tc::tc_fence_after();
   p.smem = smem;
   p.bar_empty = bars;
-  p.bar_done = bars + 2;
+  p.bar_full = bars + 2;
+  p.bar_done = bars + 4;
   p.tmem_base = *tmem_slot;
 }
 
@@ -222,11 +229,11 @@ __device__ __forceinline__ void pipe_fini(Pipe& p) {
   if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(p.tmem_base, p.tmem_cols);
 }
 
-// issue the MMAs of one staged slab (KS k-steps of 8) and commit; called by all threads after the barrier
+// issue the MMAs of one staged slab (KS k-steps of 8) and commit; called by the whole (converged) issuer warp
 template <int KS>
 __device__ __forceinline__ void issue_slab(const Pipe& p, uint8_t* st, uint32_t pa, uint32_t pb, uint32_t idesc, bool first,
                                            bool last, int buf) {
-  if (threadIdx.x < 32) {               // whole warp 0, converged: one elected lane issues
+  {
     tc::tc_fence_after();
     if (tc::elect_one()) {
       uint8_t* a_hi = st;
@@ -251,16 +258,26 @@ __device__ __forceinline__ void issue_slab(const Pipe& p, uint8_t* st, uint32_t 
   }
 }
 
-// accumulate into TMEM columns [0, N).  Two statically named register sets ping-pong so that the loads of
-// stage s + 1 are in flight while stage s is split and stored (a rotating `cur = next` copy would make
-// every stage wait for a memory round trip: profiles/r1_tc_notes.md, finding 2).
+// accumulate into TMEM columns [0, N).  Warps 0-7 stage (two statically named register sets ping-pong so that the
+// loads of stage s + 1 are in flight while stage s is split and stored; a rotating `cur = next` copy would make
+// every stage wait for a memory round trip: profiles/r1_tc_notes.md, finding 2) and hand each buffer to the issuer
+// warp through an mbarrier (one arrive per staging warp); tcgen05.commit hands it back.
 template <int NB>
 __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, int row0, int kbase_a, int kbase_b,
                                               int col0) {
   const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(g.N);
   const uint32_t sbytes = stage_bytes_nn(g.N);
-  const uint32_t idesc = tc::make_idesc_tf32(RM, g.N);
   const int nst = (g.K + RK - 1) / RK;
+  if (threadIdx.x >= RT) {                                   // issuer warp
+    const uint32_t idesc = tc::make_idesc_tf32(RM, g.N);
+    for (int s = 0; s < nst; ++s) {
+      const int buf = s & 1;
+      tc::mbar_wait(&p.bar_full[buf], static_cast<uint32_t>(s >> 1) & 1u);
+      issue_slab<RK / 8>(p, p.smem + buf * sbytes, pa, pb, idesc, s == 0, s == nst - 1, buf);
+    }
+    return;
+  }
+  const bool lane0 = (threadIdx.x & 31) == 0;
   uint32_t phase0 = 0u, phase1 = 0u;
   StageRegs x0, x1;
   gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, 0, nst, x0);
@@ -268,16 +285,16 @@ __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, 
     gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 1, nst, x1);
     if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
     gemm_store_stage<NB>(g, p.smem, x0);
-    tc::fence_proxy_async();
-    __syncthreads();
-    issue_slab<RK / 8>(p, p.smem, pa, pb, idesc, s == 0, s == nst - 1, 0);
+    tc::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
+    __syncwarp();
+    if (lane0) tc::mbar_arrive(&p.bar_full[0]);
     if (s + 1 < nst) {
       gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 2, nst, x0);
       if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
       gemm_store_stage<NB>(g, p.smem + sbytes, x1);
       tc::fence_proxy_async();
-      __syncthreads();
-      issue_slab<RK / 8>(p, p.smem + sbytes, pa, pb, idesc, false, s + 1 == nst - 1, 1);
+      __syncwarp();
+      if (lane0) tc::mbar_arrive(&p.bar_full[1]);
     }
   }
 }
@@ -288,25 +305,25 @@ __device__ __forceinline__ void wait_acc(const Pipe& p) {
 }
 
 template <int NB>
-__global__ void __launch_bounds__(RT, 1) rg_gemm_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bars[3];
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   Pipe p;
-  pipe_init(p, smem, bars, &tmem_slot, g.N);
+  pipe_init(p, smem, bars, &tmem_slot, g.N, RT / 32);
   const int row0 = blockIdx.x * RM;
   const int tile = blockIdx.y, slice = blockIdx.z;
   const int col0 = g.b_col0 + tile * g.tile_stride;
   const int ccol0 = tile * g.tile_stride;
   const int kb_a = g.a_k0 + slice * g.k_slice, kb_b = g.b_k0 + slice * g.k_slice;
   gemm_mainloop<NB>(g, p, row0, kb_a, kb_b, col0);
-  wait_acc(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp & 3, cg = warp >> 2;
   const int row = row0 + sub * 32 + lane;
   float* Cb = g.C + static_cast<long long>(slice) * g.c_slice_stride;
   const bool vec_c = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0;
-  for (int c = cg * 16; c < g.N; c += 32) {
+  if (threadIdx.x < RT) wait_acc(p);
+  for (int c = cg * 16; c < g.N && threadIdx.x < RT; c += 32) {
     float v[16];
     tc::tmem_ld16(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
     if (row < g.M) {
@@ -467,13 +484,13 @@ __device__ __forceinline__ void tn_transpose(const TnArgs& t, const float* ra, c
   }
 }
 
-__global__ void __launch_bounds__(RT, 1) rg_tn_kernel(const TnArgs t) {
+__global__ void __launch_bounds__(RTI, 1) rg_tn_kernel(const TnArgs t) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bars[3];
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[4 * RT];
   Pipe p;
-  pipe_init(p, smem, bars, &tmem_slot, t.N);
+  pipe_init(p, smem, bars, &tmem_slot, t.N, 1);
   const int m0 = blockIdx.x * RM, n0 = blockIdx.y * t.tile_stride, sp = blockIdx.z;
   const int r_begin = sp * t.rows_per_split;
   int r_end = r_begin + t.rows_per_split;
@@ -485,35 +502,45 @@ __global__ void __launch_bounds__(RT, 1) rg_tn_kernel(const TnArgs t) {
   const uint32_t pa = tc::plane_bytes(RM), pb = tc::plane_bytes(t.N);
   const uint32_t idesc = tc::make_idesc_tf32(RM, t.N);
   float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t phase0 = 0u, phase1 = 0u;
-  TnRegs x0, x1;
-  if (nst > 0) tn_load(t, m0, n0, r_begin, r_end, 0, x0);
-  for (int s = 0; s < nst; s += 2) {
-    if (s + 1 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 1, x1);
-    tn_store_raw(t, ra, rd, x0);
-    __syncthreads();
-    if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
-    tn_transpose(t, ra, rd, p.smem, bsum);
-    tc::fence_proxy_async();
-    __syncthreads();                       // planes complete; everybody is done reading the raw slab
-    issue_slab<TK / 8>(p, p.smem, pa, pb, idesc, s == 0, s == nst - 1, 0);
-    if (s + 1 < nst) {
-      if (s + 2 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 2, x0);
-      tn_store_raw(t, ra, rd, x1);
-      __syncthreads();
-      if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
-      tn_transpose(t, ra, rd, p.smem + pbytes, bsum);
+  const bool stager = threadIdx.x < RT;
+  if (!stager) {                                             // issuer warp
+    for (int s = 0; s < nst; ++s) {
+      const int buf = s & 1;
+      tc::mbar_wait(&p.bar_full[buf], static_cast<uint32_t>(s >> 1) & 1u);
+      issue_slab<TK / 8>(p, p.smem + buf * pbytes, pa, pb, idesc, s == 0, s == nst - 1, buf);
+    }
+  } else {
+    uint32_t phase0 = 0u, phase1 = 0u;
+    TnRegs x0, x1;
+    auto stager_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory"); };
+    if (nst > 0) tn_load(t, m0, n0, r_begin, r_end, 0, x0);
+    for (int s = 0; s < nst; s += 2) {
+      if (s + 1 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 1, x1);
+      tn_store_raw(t, ra, rd, x0);
+      stager_sync();
+      if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
+      tn_transpose(t, ra, rd, p.smem, bsum);
       tc::fence_proxy_async();
-      __syncthreads();
-      issue_slab<TK / 8>(p, p.smem + pbytes, pa, pb, idesc, false, s + 1 == nst - 1, 1);
+      stager_sync();                       // planes complete; everybody is done reading the raw slab
+      if (threadIdx.x == 0) tc::mbar_arrive(&p.bar_full[0]);
+      if (s + 1 < nst) {
+        if (s + 2 < nst) tn_load(t, m0, n0, r_begin, r_end, s + 2, x0);
+        tn_store_raw(t, ra, rd, x1);
+        stager_sync();
+        if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
+        tn_transpose(t, ra, rd, p.smem + pbytes, bsum);
+        tc::fence_proxy_async();
+        stager_sync();
+        if (threadIdx.x == 0) tc::mbar_arrive(&p.bar_full[1]);
+      }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp & 3, cg = warp >> 2;
   const int m = m0 + sub * 32 + lane;
   float* po = t.part + static_cast<long long>(sp) * t.part_stride;
-  if (nst > 0) wait_acc(p);
-  for (int c = cg * 16; c < t.N; c += 32) {
+  if (nst > 0 && stager) wait_acc(p);
+  for (int c = cg * 16; c < t.N && stager; c += 32) {
     float v[16];
     if (nst > 0) {
       tc::tmem_ld16(p.tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);
@@ -530,10 +557,12 @@ __global__ void __launch_bounds__(RT, 1) rg_tn_kernel(const TnArgs t) {
     }
   }
   if (t.bpart != nullptr && blockIdx.x == 0) {          // column sums: thread (n, q) partials -> fixed-order sum over q
+    if (stager) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bred[threadIdx.x + j * RT] = bsum[j];
+      for (int j = 0; j < 4; ++j) bred[threadIdx.x + j * RT] = bsum[j];
+    }
     __syncthreads();
-    for (int n = threadIdx.x; n < t.N; n += RT) {
+    for (int n = threadIdx.x; n < t.N && stager; n += RT) {
       float s = 0.0f;
       for (int q = 0; q < TK / 4; ++q) {
         const int idx = q * t.N + n;                     // chunk id of (n, q): idx = tid + j * RT
@@ -711,9 +740,9 @@ int launch_gemm(cudaStream_t s, GemmArgs g, int n_real, int slices, int n_tile =
   const int tiles = cdiv(n_real, g.N);
   const dim3 grid(cdiv(g.M, RM), tiles, slices);
   const size_t smem = 2 * static_cast<size_t>(stage_bytes_nn(g.N));
-  if (g.N <= 32) rg_gemm_kernel<1><<<grid, RT, smem, s>>>(g);
-  else if (g.N <= 64) rg_gemm_kernel<2><<<grid, RT, smem, s>>>(g);
-  else rg_gemm_kernel<8><<<grid, RT, smem, s>>>(g);
+  if (g.N <= 32) rg_gemm_kernel<1><<<grid, RTI, smem, s>>>(g);
+  else if (g.N <= 64) rg_gemm_kernel<2><<<grid, RTI, smem, s>>>(g);
+  else rg_gemm_kernel<8><<<grid, RTI, smem, s>>>(g);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -731,7 +760,7 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
   t.bpart = gb != nullptr ? bpart : nullptr; t.bpart_stride = n_real;
   const dim3 grid(cdiv(Kdim, RM), cdiv(n_real, t.N), S);
   const size_t smem = 2 * static_cast<size_t>(tn_planes_bytes(t.N)) + tn_raw_bytes(t.N);
-  rg_tn_kernel<<<grid, RT, smem, s>>>(t);
+  rg_tn_kernel<<<grid, RTI, smem, s>>>(t);
   B200PPO_LAUNCH_CHECK();
   const long long n = static_cast<long long>(Kdim) * n_real;
   rg_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, n, S, n, gw);

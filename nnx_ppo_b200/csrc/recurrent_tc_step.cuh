@@ -452,3 +452,207 @@ __global__ void __launch_bounds__(RT, 1) lstm_step_bwd_gemm_kernel(const StepBwd
   }
   step_fini(tmem_base, tmem_cols);
 }
+
+// ------------------------------------------------------------------------------------------
+// The whole forward recurrence in ONE launch (replay: T > 1).  A CTA keeps its 16-unit slice of Wh resident in
+// shared memory for all T steps and only streams the carry planes; the CTAs of a 128-row tile hand the carry
+// on through global memory and a per-(tile, step) arrival counter (release: bar.sync, __threadfence, atomicAdd
+// by one thread; acquire: one polling lane).  Needs every CTA resident at once (grid <= SMs; one CTA per SM
+// because of the resident weights): the host falls back to one lstm_step_fwd2_kernel launch per step otherwise.
+// What the launch saves per step: the kernel boundary, TMEM / barrier set-up and re-reading 133 KB of weights.
+// ------------------------------------------------------------------------------------------
+constexpr int PF_NS = 2;                                   // A ring depth (the weights take 133 KB of the 227)
+
+struct SeqFwdPArgs {
+  StepFwd2Args s;              // the arguments of step 0; the per-step pointers advance by the strides below
+  int T;
+  long long hp_buf;            // floats between the two carry-plane buffers
+  long long cat_step, hn_step, cache_step, done_step;
+  int* flags;                  // [tiles][T + 1] zero-initialised arrival counters
+  int n_ut;                    // CTAs per row tile (H / 16)
+};
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(RT, 1) lstm_seq_fwd_persistent_kernel(const SeqFwdPArgs pa) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[PF_NS], empty[PF_NS], bdone, bfull;
+  __shared__ uint32_t tmem_slot;
+  const StepFwd2Args& a = pa.s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, ut = blockIdx.y;
+  const int H = a.H, planes = H >> 2;
+  const uint32_t pa_b = tc::plane_bytes(RM), pb_b = tc::plane_bytes(4 * UT);
+  const uint32_t b_half_bytes = static_cast<uint32_t>(planes) * pb_b;
+  const uint32_t a_slot_bytes = 2u * (RK / 4) * pa_b;
+  uint8_t* b_smem = smem;                                   // [hi | lo][planes][plb(64)]
+  uint8_t* a_ring = smem + 2u * b_half_bytes;
+  const uint32_t tmem_cols = pow2_cols(4 * UT);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < PF_NS; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(&bdone, 1);
+    tc::mbar_init(&bfull, 1);
+    tc::mbar_init_fence();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int nst = (planes + RK / 4 - 1) / (RK / 4);
+  if (warp == 1 && lane == 0) {                             // the weights: once
+    const float* whf = a.whf + static_cast<size_t>(ut) * a.whf_tile;
+    tc::mbar_arrive_expect_tx(&bfull, 2u * b_half_bytes);
+    tc::bulk_g2s(b_smem, whf, b_half_bytes, &bfull);
+    tc::bulk_g2s(b_smem + b_half_bytes, whf + static_cast<size_t>(planes) * plb(4 * UT), b_half_bytes, &bfull);
+  }
+  const int sub = warp & 3, ub = warp >> 2;
+  const int r = sub * 32 + lane;
+  const int row = tile * RM + r;
+  const int u0 = ut * UT + 8 * ub;
+  const int pl0 = u0 >> 2;
+  const bool ok = row < a.rows;
+  const size_t so = static_cast<size_t>(tile) * a.cp_tile + static_cast<size_t>(pl0) * PLC + r * 4;
+  const size_t ho = static_cast<size_t>(tile) * a.hp_tile + static_cast<size_t>(pl0) * PLA + r * 4;
+  int* flags = pa.flags + static_cast<size_t>(tile) * (pa.T + 1);
+  uint32_t gstage = 0;                                      // ring position, counted over all steps (copier / issuer)
+  for (int t = 0; t < pa.T; ++t) {
+    const size_t cur = static_cast<size_t>(t & 1) * pa.hp_buf, nxt = static_cast<size_t>((t + 1) & 1) * pa.hp_buf;
+    if (warp == 1) {
+      if (lane == 0) {
+        if (t > 0) {                                        // every CTA of this row tile has written its part of h_{t-1}
+          unsigned long long spins = 0;
+          while (ld_acquire_gpu(flags + t) < pa.n_ut) {
+            if (++spins > (1ull << 26)) { printf("b200ppo: recurrent forward, tile %d step %d: peers missing\n", tile, t); __trap(); }
+          }
+          fence_proxy_async_all();
+        }
+        const float* ah = a.hp_hi + cur + static_cast<size_t>(tile) * a.hp_tile;
+        const float* al = a.hp_lo + cur + static_cast<size_t>(tile) * a.hp_tile;
+        for (int s = 0; s < nst; ++s) {
+          const uint32_t gs = gstage + s;
+          const int slot = gs % PF_NS;
+          if (gs >= PF_NS) tc::mbar_wait(&empty[slot], (gs / PF_NS - 1) & 1u);
+          const int p0 = s * (RK / 4);
+          const int np = (planes - p0) < RK / 4 ? (planes - p0) : RK / 4;
+          const uint32_t ab = static_cast<uint32_t>(np) * pa_b;
+          uint8_t* st = a_ring + slot * a_slot_bytes;
+          tc::mbar_arrive_expect_tx(&full[slot], 2u * ab);
+          tc::bulk_g2s(st, ah + static_cast<size_t>(p0) * PLA, ab, &full[slot]);
+          tc::bulk_g2s(st + (RK / 4) * pa_b, al + static_cast<size_t>(p0) * PLA, ab, &full[slot]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 0) {
+      if (t == 0) tc::mbar_wait(&bfull, 0u);
+      const uint64_t da0 = tc::make_desc(tc::smem_u32(a_ring), pa_b, 128);
+      const uint64_t db0 = tc::make_desc(tc::smem_u32(b_smem), pb_b, 128);
+      const uint32_t a_hiw = static_cast<uint32_t>(da0 >> 32), b_hiw = static_cast<uint32_t>(db0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(da0), b_lo0 = static_cast<uint32_t>(db0);
+      const uint32_t a_kstep = (2u * pa_b) >> 4, b_kstep = (2u * pb_b) >> 4;
+      const uint32_t a_half = ((RK / 4) * pa_b) >> 4, b_half = b_half_bytes >> 4;
+      const uint32_t idesc = tc::make_idesc_tf32(RM, 4 * UT);
+      for (int s = 0; s < nst; ++s) {
+        const uint32_t gs = gstage + s;
+        const int slot = gs % PF_NS;
+        const int p0 = s * (RK / 4);
+        const int ks = ((planes - p0) < RK / 4 ? (planes - p0) : RK / 4) >> 1;
+        tc::mbar_wait(&full[slot], (gs / PF_NS) & 1u);
+        tc::tc_fence_after();
+        const uint32_t a0 = a_lo0 + static_cast<uint32_t>(slot) * (a_slot_bytes >> 4);
+        const uint32_t b0 = b_lo0 + static_cast<uint32_t>(p0) * (pb_b >> 4);     // resident weights: plane p0 of the slice
+        if (tc::elect_one()) {
+          for (int j = 0; j < ks; ++j) {
+            const uint64_t ahd = (static_cast<uint64_t>(a_hiw) << 32) | (a0 + j * a_kstep);
+            const uint64_t ald = (static_cast<uint64_t>(a_hiw) << 32) | (a0 + j * a_kstep + a_half);
+            const uint64_t bhd = (static_cast<uint64_t>(b_hiw) << 32) | (b0 + j * b_kstep);
+            const uint64_t bld = (static_cast<uint64_t>(b_hiw) << 32) | (b0 + j * b_kstep + b_half);
+            const uint32_t acc0 = (s > 0 || j > 0) ? 1u : 0u;
+            tc::mma_tf32(tmem_base, ald, bhd, idesc, acc0);
+            tc::mma_tf32(tmem_base, ahd, bld, idesc, 1u);
+            tc::mma_tf32(tmem_base, ahd, bhd, idesc, 1u);
+          }
+          tc::commit(&empty[slot]);
+          if (s == nst - 1) tc::commit(&bdone);
+        }
+        __syncwarp();
+      }
+    }
+    gstage += static_cast<uint32_t>(nst);
+    // ---- epilogue of step t (all eight warps) ----
+    float4 gxv[4][2], cv[2];
+    bool dn = false;
+    if (ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const size_t o = plane_off(a.r0 + static_cast<long long>(t) * a.rows + row, q * planes + pl0, a.gx_cols4);
+        gxv[q][0] = *reinterpret_cast<const float4*>(a.gxp + o);
+        gxv[q][1] = *reinterpret_cast<const float4*>(a.gxp + o + PLC);
+      }
+      cv[0] = *reinterpret_cast<const float4*>(a.cp + so);
+      cv[1] = *reinterpret_cast<const float4*>(a.cp + so + PLC);
+      if (a.done != nullptr) dn = a.done[static_cast<size_t>(t) * pa.done_step + (a.inds ? a.inds[row] : row)] != 0;
+    }
+    tc::mbar_wait(&bdone, static_cast<uint32_t>(t) & 1u);
+    tc::tc_fence_after();
+    float acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      tmem_ld8(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(q * UT + 8 * ub), acc[q]);
+    if (ok) {
+      float c2[8], h2[8], iv[8], fv[8], gv[8], ov[8], tv[8];
+      const float gx0[4][8] = {
+          {gxv[0][0].x, gxv[0][0].y, gxv[0][0].z, gxv[0][0].w, gxv[0][1].x, gxv[0][1].y, gxv[0][1].z, gxv[0][1].w},
+          {gxv[1][0].x, gxv[1][0].y, gxv[1][0].z, gxv[1][0].w, gxv[1][1].x, gxv[1][1].y, gxv[1][1].z, gxv[1][1].w},
+          {gxv[2][0].x, gxv[2][0].y, gxv[2][0].z, gxv[2][0].w, gxv[2][1].x, gxv[2][1].y, gxv[2][1].z, gxv[2][1].w},
+          {gxv[3][0].x, gxv[3][0].y, gxv[3][0].z, gxv[3][0].w, gxv[3][1].x, gxv[3][1].y, gxv[3][1].z, gxv[3][1].w}};
+      const float c0[8] = {cv[0].x, cv[0].y, cv[0].z, cv[0].w, cv[1].x, cv[1].y, cv[1].z, cv[1].w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        iv[k] = sigmoid_f(acc[0][k] + gx0[0][k]);
+        fv[k] = sigmoid_f(acc[1][k] + gx0[1][k]);
+        gv[k] = tanhf(acc[2][k] + gx0[2][k]);
+        ov[k] = sigmoid_f(acc[3][k] + gx0[3][k]);
+        c2[k] = __fadd_rn(__fmul_rn(fv[k], c0[k]), __fmul_rn(iv[k], gv[k]));
+        tv[k] = tanhf(c2[k]);
+        h2[k] = __fmul_rn(ov[k], tv[k]);
+      }
+      const size_t co = static_cast<size_t>(t) * pa.cache_step + so;
+      auto stp = [&](float* base, size_t off, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(base + off) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(base + off + PLC) = make_float4(v[4], v[5], v[6], v[7]);
+      };
+      if (a.gi != nullptr) {
+        stp(a.gi, co, iv); stp(a.gf, co, fv); stp(a.gg, co, gv); stp(a.go, co, ov); stp(a.tcc, co, tv); stp(a.cin, co, c0);
+      }
+      if (a.hn_rm != nullptr) {
+        float* d = a.hn_rm + static_cast<size_t>(t) * pa.hn_step + static_cast<size_t>(row) * H + u0;
+        *reinterpret_cast<float4*>(d) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(h2[4], h2[5], h2[6], h2[7]);
+      }
+      if (dn) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c2[k] = 0.0f; h2[k] = 0.0f; }
+      }
+      stp(a.cp, so, c2);
+      {
+        float* d = a.h_next_rm + static_cast<size_t>(t) * pa.cat_step + static_cast<size_t>(row) * a.ld_hn + u0;
+        *reinterpret_cast<float4*>(d) = make_float4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(h2[4], h2[5], h2[6], h2[7]);
+      }
+      float4 hi, lo;
+      tc::split4_fast(make_float4(h2[0], h2[1], h2[2], h2[3]), hi, lo);
+      *reinterpret_cast<float4*>(a.hn_hi - 0 + nxt - cur + ho) = hi;       // (placeholder, replaced below)
+      (void)hi; (void)lo;
+    }
+    __syncthreads();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}

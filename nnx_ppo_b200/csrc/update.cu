@@ -167,15 +167,14 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
 // peer-memory exchange (include/b200ppo.h): comm buffer layout and device helpers
 // ------------------------------------------------------------------------------------------
 constexpr int MAXR = B200PPO_MAX_RANKS;
-constexpr size_t COMM_FLAG_ADV = 0;                       // uint32[MAXR], written by the peers
-constexpr size_t COMM_ADV = 128;                          // double[2 parity][MAXR][2]
-constexpr size_t COMM_FLAG_BLK = 1024;                    // uint32[MAXR][nblk]: per source rank, per 256-parameter block
+// Every exchanged 32-bit word travels as ONE 8-byte store {payload, epoch} (the "LL" idea of NCCL's low-latency
+// protocol): 8-byte stores are single-copy atomic, so the receiver needs no flag, no fence and no second round
+// trip - it polls the word in its OWN memory until the epoch half matches.  Cost: twice the bytes (800 KB per
+// rank and update at cfg 2: nothing for NVLink) for one one-way NVLink latency per exchange.  Epochs are
+// monotonic and start at 1, buffers alternate on the epoch's parity, so a stale word can never match.
+constexpr size_t COMM_ADV = 0;                            // uint2[2 parity][MAXR][4]: the two fp64 sums as four halves
+constexpr size_t COMM_GRAD = 2 * MAXR * 4 * sizeof(uint2);   // uint2[2 parity][world][Ppad]: every rank PUSHES its gradient here
 inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n_params)); }
-inline int comm_nblk(int64_t n_params) { return static_cast<int>((cdiv(n_params, 256) + 63) & ~63); }
-// float[2 parity][world][Ppad]: every rank PUSHES its gradient here
-__host__ __device__ inline size_t comm_grad_off(int nblk) {
-  return COMM_FLAG_BLK + static_cast<size_t>(B200PPO_MAX_RANKS) * static_cast<size_t>(nblk) * sizeof(uint32_t);
-}
 
 struct PeerComm {
   const uint64_t* table;   // device: comm base of every rank (nullptr: exchange disabled)
@@ -184,40 +183,27 @@ struct PeerComm {
 __device__ __forceinline__ uint8_t* comm_base(const PeerComm& c, int r) {
   return reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(c.table[r]));
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void ll_store(uint2* p, uint32_t payload, uint32_t epoch) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ll_load(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
-// spin until every rank's flag (written into OUR buffer by that rank) has reached `epoch`; the
-// acquire orders the data reads that follow (all data is pushed into our own buffer: no remote loads)
-__device__ __forceinline__ void comm_wait_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
-  const uint32_t* fl = reinterpret_cast<const uint32_t*>(comm_base(c, c.rank) + flag_off);
-  for (int r = 0; r < c.world; ++r) {
-    // bounded: a peer that died must not hang this GPU forever (about a minute of polling, then trap,
-    // which surfaces as a launch failure on the host)
-    unsigned long long spins = 0;
-    while (static_cast<int32_t>(ld_acquire_sys(fl + r) - epoch) < 0) {
-      if (++spins > (1ull << 27)) {
-        printf("b200ppo: rank %d waited too long for rank %d (flag offset %llu, epoch %u)\n", c.rank, r,
-               static_cast<unsigned long long>(flag_off), epoch);
-        __trap();
-      }
+// poll one word of OUR buffer until the sender's store of `epoch` has landed
+__device__ __forceinline__ uint32_t ll_wait(const uint2* p, uint32_t epoch, int rank, int from) {
+  unsigned long long spins = 0;
+  for (;;) {
+    const uint2 v = ll_load(p);
+    if (v.y == epoch) return v.x;
+    // bounded: a peer that died must not hang this GPU forever (about a minute of polling, then trap, which
+    // surfaces as a launch failure on the host)
+    if (++spins > (1ull << 27)) {
+      printf("b200ppo: rank %d waited too long for rank %d (epoch %u)\n", rank, from, epoch);
+      __trap();
     }
   }
-}
-// tell every rank (ourselves included) that our data of `epoch` is in place.  ONE system-scope fence
-// orders this thread's pushes (and, through the kernel boundary, those of earlier kernels) before
-// all the flag stores; the flags themselves are relaxed stores issued back to back.  (A
-// st.release.sys per peer waits for an NVLink round trip each: 8 ranks = 8 serialised round trips
-// per signal, measured as the scaling loss from 4 to 8 GPUs.)
-__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void comm_signal_all(const PeerComm& c, size_t flag_off, uint32_t epoch) {
-  __threadfence_system();
-  for (int r = 0; r < c.world; ++r)
-    st_relaxed_sys(reinterpret_cast<uint32_t*>(comm_base(c, r) + flag_off) + c.rank, epoch);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -554,13 +540,14 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
       dbl[1] = t2;
       if (a.comm.table != nullptr) {             // ... or every peer gets them through its comm buffer
         const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
+        const unsigned long long b1 = static_cast<unsigned long long>(__double_as_longlong(t1));
+        const unsigned long long b2 = static_cast<unsigned long long>(__double_as_longlong(t2));
+        const uint32_t w[4] = {static_cast<uint32_t>(b1), static_cast<uint32_t>(b1 >> 32), static_cast<uint32_t>(b2),
+                               static_cast<uint32_t>(b2 >> 32)};
         for (int r = 0; r < a.comm.world; ++r) {
-          double* slot = reinterpret_cast<double*>(comm_base(a.comm, r) + COMM_ADV) +
-                         ((epoch & 1u) * MAXR + a.comm.rank) * 2;
-          slot[0] = t1;
-          slot[1] = t2;
+          uint2* slot = reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_ADV) + ((epoch & 1u) * MAXR + a.comm.rank) * 4;
+          for (int i = 0; i < 4; ++i) ll_store(slot + i, w[i], epoch);
         }
-        comm_signal_all(a.comm, COMM_FLAG_ADV, epoch);
       }
     }
   }
@@ -596,12 +583,15 @@ __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean,
   double s1 = dbl[0], s2 = dbl[1];
   if (a.comm.table != nullptr) {
     const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
-    comm_wait_all(a.comm, COMM_FLAG_ADV, epoch);
-    const double* slot = reinterpret_cast<const double*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) +
-                         (epoch & 1u) * MAXR * 2;
+    const uint2* slot = reinterpret_cast<const uint2*>(comm_base(a.comm, a.comm.rank) + COMM_ADV) + (epoch & 1u) * MAXR * 4;
     s1 = 0.0;
     s2 = 0.0;
-    for (int r = 0; r < a.comm.world; ++r) { s1 += __ldcg(slot + 2 * r); s2 += __ldcg(slot + 2 * r + 1); }
+    for (int r = 0; r < a.comm.world; ++r) {               // rank order: identical sums on every rank
+      uint32_t w[4];
+      for (int i = 0; i < 4; ++i) w[i] = ll_wait(slot + r * 4 + i, epoch, a.comm.rank, r);
+      s1 += __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w[1]) << 32) | w[0]));
+      s2 += __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(w[3]) << 32) | w[2]));
+    }
   }
   const double m = s1 / a.n_global;
   double var = s2 / a.n_global - m * m;
@@ -1036,12 +1026,10 @@ struct AdamArgs {
   int update_index;
   float lr, b1, b2, eps, wd, clip;
   const float* hpd;                 // device hyper-parameter block (nullable): overrides the six values above
-  // peer exchange (table != nullptr): push this block's 256 reduced gradients into slot [parity][rank] of
-  // EVERY rank's buffer, raise this block's flag everywhere, wait for every rank's flag of THIS block only
-  // (a block needs nothing but its own 256 parameters from each peer), sum the slots in rank order
+  // peer exchange (table != nullptr): every thread pushes its reduced gradient element, epoch attached, into
+  // slot [parity][rank] of EVERY rank's buffer and sums the slots of its own buffer in rank order
   PeerComm comm;
   size_t comm_ppad;
-  int comm_nblk;
   int do_adam;                      // 0: reduce / exchange / norm only
   // nullable: squared global norm of the (summed) gradient -> *norm_out (block partials, ticket, fixed order)
   double* norm_part; double* norm_out; unsigned int* norm_ticket;
@@ -1069,40 +1057,17 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
       g = a.grad[i];
     }
   }
-  if (a.comm.table != nullptr) {
+  if (a.comm.table != nullptr && in) {
+    // push this element (with the epoch in the same 8-byte store) into slot [parity][rank] of EVERY rank's buffer,
+    // then collect the slots of our own buffer in rank order: no flag, no fence, no block-wide barrier
     const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
-    const size_t goff = comm_grad_off(a.comm_nblk);
-    const size_t slot = ((epoch & 1u) * a.comm.world + a.comm.rank) * a.comm_ppad;
-    if (in)
-      for (int r = 0; r < a.comm.world; ++r)        // stores over NVLink are fire-and-forget
-        (reinterpret_cast<float*>(comm_base(a.comm, r) + goff) + slot)[i] = g;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      // the barrier ordered the block's pushes before this thread; ONE system-scope fence, then relaxed
-      // flag stores back to back (a st.release.sys per peer is one NVLink round trip each)
-      __threadfence_system();
-      for (int r = 0; r < a.comm.world; ++r)
-        st_relaxed_sys(reinterpret_cast<uint32_t*>(comm_base(a.comm, r) + COMM_FLAG_BLK) +
-                           static_cast<size_t>(a.comm.rank) * a.comm_nblk + blockIdx.x, epoch);
-      const uint32_t* fl = reinterpret_cast<const uint32_t*>(comm_base(a.comm, a.comm.rank) + COMM_FLAG_BLK) + blockIdx.x;
-      for (int r = 0; r < a.comm.world; ++r) {
-        unsigned long long spins = 0;
-        while (static_cast<int32_t>(ld_acquire_sys(fl + static_cast<size_t>(r) * a.comm_nblk) - epoch) < 0) {
-          if (++spins > (1ull << 27)) {
-            printf("b200ppo: rank %d block %d waited too long for the gradient of rank %d (epoch %u)\n", a.comm.rank,
-                   static_cast<int>(blockIdx.x), r, epoch);
-            __trap();
-          }
-        }
-      }
-    }
-    __syncthreads();
-    if (in) {
-      g = 0.0f;
-      const float* pg = reinterpret_cast<const float*>(comm_base(a.comm, a.comm.rank) + goff) +
-                        (epoch & 1u) * a.comm.world * a.comm_ppad;
-      for (int r = 0; r < a.comm.world; ++r) g += __ldcg(pg + r * a.comm_ppad + i);   // rank order: identical on every rank
-    }
+    const size_t slot = ((epoch & 1u) * a.comm.world + a.comm.rank) * a.comm_ppad + static_cast<size_t>(i);
+    for (int r = 0; r < a.comm.world; ++r)
+      ll_store(reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_GRAD) + slot, __float_as_uint(g), epoch);
+    const uint2* pg = reinterpret_cast<const uint2*>(comm_base(a.comm, a.comm.rank) + COMM_GRAD) +
+                      (epoch & 1u) * a.comm.world * a.comm_ppad + static_cast<size_t>(i);
+    g = 0.0f;
+    for (int r = 0; r < a.comm.world; ++r) g += __uint_as_float(ll_wait(pg + r * a.comm_ppad, epoch, a.comm.rank, r));
   }
   if (in && a.grad_out != nullptr) a.grad_out[i] = g;
   if (a.norm_part != nullptr) {
@@ -1419,7 +1384,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.wd = hp->weight_decay; a.clip = hp->grad_clip; a.hpd = b->hparams_dev;
     // the exchange belongs to the ADAM stage: a caller that runs RED alone gets the local gradient
     a.comm = do_adam ? pc : PeerComm{nullptr, 1, 0};
-    a.comm_ppad = comm_ppad(plan->n_params); a.comm_nblk = comm_nblk(plan->n_params);
+    a.comm_ppad = comm_ppad(plan->n_params);
     a.norm_part = nullptr; a.norm_out = dbl + 2; a.norm_ticket = tickets + 2;
     a.mask = b->param_mask;
     a.n_seg = 0; a.ws = ws;
@@ -1459,8 +1424,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size) {
   if (check_plan_u(plan) || world_size < 1 || world_size > MAXR) return -1;
-  return static_cast<int64_t>(comm_grad_off(comm_nblk(plan->n_params)) +
-                              2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(float));
+  return static_cast<int64_t>(COMM_GRAD + 2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(uint2));
 }
 
 extern "C" int b200ppo_comm_alloc(int64_t bytes, void** out) {

@@ -345,7 +345,8 @@ int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const
  * Dense(act) -> LSTM -> Dense actor.  Only h_{t-1} Wh is sequential: the input projection, the post
  * Dense and every weight gradient are batched GEMMs over all T * rows samples; the T step launches
  * compute 128-row x 16-unit tiles with the gate math, the reset-on-done select and the activation cache
- * in the GEMM epilogue.  Needs hidden % 16 == 0 and pre_dim % 4 == 0 (b200ppo_lstm_seq_supported;
+ * in the GEMM epilogue; when all tiles fit on the device at once the forward recurrence is ONE persistent
+ * launch (weights resident in shared memory, the carry handed between CTAs through arrival counters).  Needs hidden % 16 == 0 and pre_dim % 4 == 0 (b200ppo_lstm_seq_supported;
  * otherwise use the step kernels above).  ws: b200ppo_lstm_seq_workspace_floats() floats, 256-byte aligned, shared by a
  * forward call (keep_cache = 1) and the backward call that follows it.
  *   x     dev [T*rows][obs_dim] inputs in step-major order; normalised on load when norm_mean / norm_std
@@ -358,8 +359,12 @@ int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const
  * backward: d_y dev [T*rows][out_dim]; grad dev [n_params]: the recurrent actor's weight and bias
  * gradients are WRITTEN (fixed-order sums: bit-reproducible), other entries untouched.               */
 int b200ppo_lstm_seq_supported(const b200ppo_lstm_plan* plan);
+/* 1 (also B200PPO_LSTM_PERSIST=1): the forward recurrence of a replay is one persistent launch when its tiles
+ * fit on the device at once; 0 (default: measured no faster inside the captured iteration): one launch per
+ * step.  Returns the previous setting (-1: unset). */
+int b200ppo_lstm_set_persistent(int on);
 int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows);
-int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t backward);
+int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows, int32_t backward);
 int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
                              const float* norm_mean, const float* norm_std, const float* x,
                              const uint8_t* done, const int32_t* inds, int32_t B, float* c, float* h,

@@ -112,8 +112,9 @@ SYMBOLS = {
     "b200ppo_lstm_wgrad_scratch_floats": (_i64, [C.POINTER(LstmPlan), _i32]),
     "b200ppo_lstm_weight_grads": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200ppo_lstm_seq_supported": (C.c_int, [C.POINTER(LstmPlan)]),
+    "b200ppo_lstm_set_persistent": (C.c_int, [C.c_int]),
     "b200ppo_lstm_seq_workspace_floats": (_i64, [C.POINTER(LstmPlan), _i32, _i32]),
-    "b200ppo_lstm_seq_num_launches": (C.c_int, [C.POINTER(LstmPlan), _i32, _i32]),
+    "b200ppo_lstm_seq_num_launches": (C.c_int, [C.POINTER(LstmPlan), _i32, _i32, _i32]),
     "b200ppo_lstm_seq_forward": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp,
                                            _i32, _i32, _vp, _vp, _i32]),
     "b200ppo_lstm_seq_backward": (C.c_int, [_vp, C.POINTER(LstmPlan), _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),

@@ -91,7 +91,7 @@ def _policy(eng, net, obs, t, s):
         _lib.check(lib.b200ppo_lstm_seq_forward(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                                 h.data_ptr(), 1, B, eng.r_ws.data_ptr(), eng.r_y.data_ptr(), 0),
                    "lstm_seq_forward(rollout)")
-        n = int(lib.b200ppo_lstm_seq_num_launches(lp, 1, 0))
+        n = int(lib.b200ppo_lstm_seq_num_launches(lp, 1, B, 0))
     else:
         _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                              h.data_ptr(), eng.r_y.data_ptr(), 0), "lstm_step_fwd(rollout)")
@@ -156,7 +156,7 @@ def _enqueue_iteration(eng, net, env, env_state):
             _lib.check(lib.b200ppo_lstm_seq_forward(s, lp, arena, 0, 0, eng.r_xhat_ptr, eng.done.data_ptr(), ip, B,
                                                     eng.r_c.data_ptr(), eng.r_h.data_ptr(), T, mb, eng.r_ws.data_ptr(),
                                                     eng.r_y_ptr, 1), "lstm_seq_forward(replay)")
-            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, 0))
+            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, mb, 0))
         else:
             for t in range(T):
                 _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, eng.obs[t].data_ptr(), ip,
@@ -170,7 +170,7 @@ def _enqueue_iteration(eng, net, env, env_state):
         if eng.r_seq:                                                                 # BPTT + weight gradients
             _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
                                                      T, mb, eng.r_ws.data_ptr(), eng.r_grad_ptr), "lstm_seq_backward")
-            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, 1))
+            n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, mb, 1))
         else:
             eng.r_dc.zero_()
             eng.r_dh.zero_()

@@ -24,6 +24,9 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 using namespace b200ppo;
 
 namespace {
@@ -607,6 +610,7 @@ struct SeqLayout {
   size_t dap;                             // A planes of da: [2 halves][tiles][4 gates][H / 4][PLA]
   size_t dhr;                             // split-K partials [4][tiles][H / 4][PLC]
   size_t whf, whb;                        // weight planes
+  size_t flags;                           // int32 [tiles][T + 1] arrival counters of the persistent forward kernel
   size_t part, bpart, total;
   int tiles, NBT, nbt;
   size_t hp_half, hp_buf, st_tile, cache_step, dap_half;
@@ -657,6 +661,7 @@ SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   L.dhr = take(4 * tiles * L.st_tile);
   L.whf = take((H / UT) * 2 * planes * plb(4 * UT));
   L.whb = take(static_cast<size_t>(L.nbt) * 4 * 2 * planes * plb(L.NBT));
+  L.flags = take(tiles * (static_cast<size_t>(T) + 1));
   const int Rr = static_cast<int>(R);
   L.S_cat = split_for(cdiv(P + H, RM) * cdiv(4 * H, 256), Rr);
   L.S_w1 = split_for(cdiv(p.obs_dim, RM), Rr);
@@ -672,6 +677,21 @@ SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   L.bpart = take(64 * nb);
   L.total = o;
   return L;
+}
+
+constexpr int PERSIST_SMEM_MAX = 220 * 1024;   // dynamic shared memory of the persistent kernel (227 KB minus static, with margin)
+int g_seq_persist = -1;
+// one persistent launch for the forward recurrence: T > 1 and every CTA resident at once (one per SM).
+// B200PPO_LSTM_PERSIST=1 / b200ppo_lstm_set_persistent(1) selects it; default: one launch per step.
+bool seq_persistent(const b200ppo_lstm_plan& p, int T, int rows) {
+  if (g_seq_persist < 0) {
+    const char* e = std::getenv("B200PPO_LSTM_PERSIST");
+    // Off unless asked for: measured on B200 (configs[2], profiles/r2_recurrent_notes.md) the persistent launch
+    // is parity-identical but not faster inside the captured iteration (46.4 vs 45.3 ms): a step is bound by the
+    // carry hand-off + 264 KB operand stream + gate epilogue, not by the kernel boundary.
+    g_seq_persist = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_seq_persist != 0 && T > 1 && cdiv(rows, RM) * (p.hidden / UT) <= b200ppo_num_sms();
 }
 
 int check_plan_tc(const b200ppo_lstm_plan* p) {
@@ -703,6 +723,8 @@ int set_attrs_tc() {
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(lstm_step_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SP_NS * sp_slot_bytes(4 * UT)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_seq_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM_MAX);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(lstm_step_bwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SP_NS * sp_slot_bytes(64)));
@@ -774,6 +796,12 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
 
 }  // namespace
 
+extern "C" int b200ppo_lstm_set_persistent(int on) {
+  const int prev = g_seq_persist < 0 ? -1 : g_seq_persist;
+  if (on == 0 || on == 1) g_seq_persist = on;
+  return prev;
+}
+
 extern "C" int b200ppo_lstm_seq_supported(const b200ppo_lstm_plan* plan) { return check_plan_tc(plan) == 0 ? 1 : 0; }
 
 extern "C" int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows) {
@@ -781,9 +809,11 @@ extern "C" int64_t b200ppo_lstm_seq_workspace_floats(const b200ppo_lstm_plan* pl
   return static_cast<int64_t>(seq_layout(*plan, T, rows).total);
 }
 
-extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t backward) {
-  if (check_plan_tc(plan) || T <= 0) return -1;
-  if (!backward) return 1 /* weight planes */ + 2 /* carry in */ + 2 /* pre, proj */ + T + 1 /* post */ + 2 /* carry out */;
+extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int32_t T, int32_t rows, int32_t backward) {
+  if (check_plan_tc(plan) || T <= 0 || rows <= 0) return -1;
+  const size_t p_smem = 2 * static_cast<size_t>(plan->hidden / 4) * tc::plane_bytes(4 * UT) + PF_NS * 2u * (RK / 4) * tc::plane_bytes(RM);
+  const int steps = (seq_persistent(*plan, T, rows) && p_smem <= PERSIST_SMEM_MAX) ? 1 : T;
+  if (!backward) return 1 /* weight planes */ + 2 /* carry in */ + 2 /* pre, proj */ + steps + 1 /* post */ + 2 /* carry out */;
   return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */;
 }
 
@@ -843,8 +873,8 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     rc = launch_gemm(s, g, 4 * H, 1);
     if (rc) return rc;
   }
-  // the recurrence
-  for (int t = 0; t < T; ++t) {
+  // the recurrence: one persistent launch when every CTA fits on the device at once, else one launch per step
+  auto step_args = [&](int t) {
     StepFwd2Args a;
     const size_t cur = static_cast<size_t>(t & 1) * L.hp_buf, nxt = static_cast<size_t>((t + 1) & 1) * L.hp_buf;
     a.hp_hi = ws + L.hp + cur; a.hp_lo = ws + L.hp + cur + L.hp_half; a.hp_tile = static_cast<long long>(planes) * PLA;
@@ -864,8 +894,29 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     a.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
     a.inds = inds;
     a.rows = rows; a.H = H;
-    lstm_step_fwd2_kernel<<<dim3(L.tiles, H / UT), RT, SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
+    return a;
+  };
+  const size_t p_smem = 2 * static_cast<size_t>(planes) * tc::plane_bytes(4 * UT) + PF_NS * 2u * (RK / 4) * tc::plane_bytes(RM);
+  if (seq_persistent(*plan, T, rows) && p_smem <= PERSIST_SMEM_MAX) {
+    if (cudaMemsetAsync(ws + L.flags, 0, sizeof(int) * L.tiles * (static_cast<size_t>(T) + 1), s) != cudaSuccess)
+      return static_cast<int>(cudaGetLastError());
+    SeqFwdPArgs pa;
+    pa.s = step_args(0);
+    pa.T = T;
+    pa.hp_buf = static_cast<long long>(L.hp_buf);
+    pa.cat_step = static_cast<long long>(rows) * LC; pa.hn_step = static_cast<long long>(rows) * H;
+    pa.cache_step = static_cast<long long>(L.cache_step); pa.done_step = B;
+    pa.hp_base_hi = ws + L.hp; pa.hp_base_lo = ws + L.hp + L.hp_half;
+    pa.flags = reinterpret_cast<int*>(ws + L.flags);
+    pa.n_ut = H / UT;
+    lstm_seq_fwd_persistent_kernel<<<dim3(L.tiles, H / UT), RT, p_smem, s>>>(pa);
     B200PPO_LAUNCH_CHECK();
+  } else {
+    for (int t = 0; t < T; ++t) {
+      const StepFwd2Args a = step_args(t);
+      lstm_step_fwd2_kernel<<<dim3(L.tiles, H / UT), RT, SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
+      B200PPO_LAUNCH_CHECK();
+    }
   }
   // y = h' W2 + b2
   {

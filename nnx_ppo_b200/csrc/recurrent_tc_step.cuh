@@ -468,6 +468,7 @@ struct SeqFwdPArgs {
   int T;
   long long hp_buf;            // floats between the two carry-plane buffers
   long long cat_step, hn_step, cache_step, done_step;
+  float* hp_base_hi; float* hp_base_lo;   // carry planes, buffer 0 (step t reads buffer t & 1, writes the other)
   int* flags;                  // [tiles][T + 1] zero-initialised arrival counters
   int n_ut;                    // CTAs per row tile (H / 16)
 };
@@ -532,8 +533,8 @@ __global__ void __launch_bounds__(RT, 1) lstm_seq_fwd_persistent_kernel(const Se
           }
           fence_proxy_async_all();
         }
-        const float* ah = a.hp_hi + cur + static_cast<size_t>(tile) * a.hp_tile;
-        const float* al = a.hp_lo + cur + static_cast<size_t>(tile) * a.hp_tile;
+        const float* ah = pa.hp_base_hi + cur + static_cast<size_t>(tile) * a.hp_tile;
+        const float* al = pa.hp_base_lo + cur + static_cast<size_t>(tile) * a.hp_tile;
         for (int s = 0; s < nst; ++s) {
           const uint32_t gs = gstage + s;
           const int slot = gs % PF_NS;
@@ -645,12 +646,23 @@ __global__ void __launch_bounds__(RT, 1) lstm_seq_fwd_persistent_kernel(const Se
         *reinterpret_cast<float4*>(d) = make_float4(h2[0], h2[1], h2[2], h2[3]);
         *reinterpret_cast<float4*>(d + 4) = make_float4(h2[4], h2[5], h2[6], h2[7]);
       }
+      // the carry as the next step's A operand
       float4 hi, lo;
       tc::split4_fast(make_float4(h2[0], h2[1], h2[2], h2[3]), hi, lo);
-      *reinterpret_cast<float4*>(a.hn_hi - 0 + nxt - cur + ho) = hi;       // (placeholder, replaced below)
-      (void)hi; (void)lo;
+      *reinterpret_cast<float4*>(pa.hp_base_hi + nxt + ho) = hi;
+      *reinterpret_cast<float4*>(pa.hp_base_lo + nxt + ho) = lo;
+      tc::split4_fast(make_float4(h2[4], h2[5], h2[6], h2[7]), hi, lo);
+      *reinterpret_cast<float4*>(pa.hp_base_hi + nxt + ho + PLA) = hi;
+      *reinterpret_cast<float4*>(pa.hp_base_lo + nxt + ho + PLA) = lo;
     }
+    // hand the carry on: our writes are ordered before the arrival (generic -> async proxy, CTA barrier, device fence)
+    fence_proxy_async_all();
+    tc::tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(flags + t + 1, 1);
+    }
   }
   tc::tc_fence_before();
   __syncthreads();

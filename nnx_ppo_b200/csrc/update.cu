@@ -71,6 +71,18 @@ struct Layout {
 
 inline size_t align64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
 
+double g_dw_wt_thin = 1.0, g_dw_wt_wide = 1.2;
+bool g_dw_wt_read = false;
+void read_dw_weights() {
+  if (g_dw_wt_read) return;
+  g_dw_wt_read = true;
+  const char* e = std::getenv("B200PPO_DW_WTS");
+  if (e) {
+    double a = 0.0, b = 0.0;
+    if (std::sscanf(e, "%lf,%lf", &a, &b) == 2 && a > 0.0 && b > 0.0) { g_dw_wt_thin = a; g_dw_wt_wide = b; }
+  }
+}
+
 int dw_tiles(const b200ppo_chain& c) {
   int n = 0;
   for (int l = 0; l < c.n_layers; ++l) n += cdiv(c.dims[l], DW_T) * cdiv(c.dims[l + 1], DW_T);
@@ -79,6 +91,7 @@ int dw_tiles(const b200ppo_chain& c) {
 
 Layout make_layout(const b200ppo_plan& p, int T, int mb) {
   Layout L;
+  read_dw_weights();
   L.R = T * mb;
   L.Rv = (T + 1) * mb;
   size_t o = 0;
@@ -136,7 +149,9 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
       const b200ppo_chain& ch = c == 0 ? p.actor : p.critic;
       for (int l = 0; l < ch.n_layers; ++l)
         for (int m = 0; m < cdiv(ch.dims[l], 128) && ni < 32; ++m) {
-          wts[ni] = ch.dims[l + 1] > 128 ? 1.2 : 1.0;
+          // relative cost of one 16-row stage of the item: wide operands are tensor bound, thin ones (the value
+          // head: N padded to 16) move a fraction of the bytes.  B200PPO_DW_WTS="thin,wide" overrides (tuning aid).
+          wts[ni] = ch.dims[l + 1] > 128 ? g_dw_wt_wide : (ch.dims[l + 1] <= 16 ? g_dw_wt_thin : 1.0);
           wsum += wts[ni++];
         }
     }

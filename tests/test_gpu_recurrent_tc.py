@@ -72,8 +72,12 @@ def test_weight_gradient_tile_gemm_matches_float64(cuda_device, lib, rows, Kdim,
                                  dict(O=16, A=4, B=37, T=20, P=32, H=32, act="relu", mb=list(range(37))),
                                  dict(O=10, A=3, B=300, T=9, P=12, H=16, act="tanh", mb=list(range(299, 10, -2))),
                                  dict(O=64, A=8, B=600, T=32, P=64, H=256, act="swish", mb=list(range(0, 600)))])
-def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg):
+@pytest.mark.parametrize("persist", [1, 0])
+def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
+    """persist = 1: the forward recurrence as one persistent launch (weights resident in shared memory, the carry
+    handed between the CTAs of a row tile through arrival counters); 0: one launch per step."""
     import torch
+    lib.b200ppo_lstm_set_persistent(persist)
     dev = cuda_device
     O, A, B, T, H, P = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["H"], cfg["P"]
     net = orec.make_recurrent_actor_critic(O, A, [P], H, [], [6], seed=3, activation=cfg["act"])
@@ -134,4 +138,6 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg):
     assert np.abs(outs[0][:n_rec] - ref).max() < 3e-4 * scale, (np.abs(outs[0][:n_rec] - ref).max(), scale)
     assert np.array_equal(outs[0], outs[1])                      # fixed-order sums: bit-reproducible
     assert np.all(outs[0][n_rec:] == 7.0)                        # the critic's slots are not touched
-    assert lib.b200ppo_lstm_seq_num_launches(plan, T, 0) == T + 8 and lib.b200ppo_lstm_seq_num_launches(plan, T, 1) == 2 * T + 10
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 0) == (1 if persist else T) + 8
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 1) == 2 * T + 10
+    lib.b200ppo_lstm_set_persistent(0)

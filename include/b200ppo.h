@@ -136,7 +136,8 @@ typedef struct b200ppo_update_bufs {
   const uint64_t* comm;
   /* optional dev uint8[n_params]: 0 marks a structural zero (the off-diagonal blocks when per-key
    * encoders — containers.py Concat — are laid out as one block-diagonal Dense layer); such entries
-   * are excluded from the gradient norm and never updated.  NULL: every entry is a parameter. */
+   * are excluded from the gradient norm and never updated; 2 marks the second copy of a tied
+   * parameter (param_tie below): updated, not counted in the norm.  NULL: every entry is a parameter. */
   const uint8_t* param_mask;
   /* optional dev float[B200PPO_HP_FLOATS]: when non-NULL the kernels read the numeric hyper-parameters
    * (gamma, lambda, clip range, critic weight, learning rate, Adam b1 / b2 / eps, weight-decay and
@@ -147,6 +148,12 @@ typedef struct b200ppo_update_bufs {
    * 1), advanced by b200ppo_iter_finalize.  NULL: the Adam count rng_state[3] is the base (it goes
    * backwards when a training state is rolled back, which would make stale flags look current). */
   const uint32_t* comm_epoch;
+  /* optional dev int32[n_params]: tied parameters (a trunk shared by the actor and the critic chain is stored
+   * once per chain).  param_tie[i] = index of the other copy of parameter i, or -1.  The RED stage adds the
+   * two copies' gradients (d loss / d w = actor path + critic path, containers.py Sequential feeding one
+   * feature tensor to both PPOAdapter ports), so both copies take the same optimizer step and stay
+   * bit-identical; mark the second copy 2 in param_mask to keep it out of the gradient norm.  NULL: no ties. */
+  const int32_t* param_tie;
 } b200ppo_update_bufs;
 
 /* -------- library -------------------------------------------------------------------------- */

@@ -49,7 +49,7 @@ class UpdateBufs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "obs", "raw_action", "loglik_old", "reward", "done", "truncated", "next_obs_last", "inds",
         "norm_mean", "norm_std", "params", "adam_mu", "adam_nu", "rng_state", "metrics_out", "ws", "comm",
-        "param_mask", "hparams_dev", "comm_epoch")]
+        "param_mask", "hparams_dev", "comm_epoch", "param_tie")]
 
 
 class LstmPlan(C.Structure):

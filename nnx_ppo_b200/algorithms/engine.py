@@ -182,6 +182,8 @@ class PPOEngine:
             b.param_mask = pm.data_ptr() if pm is not None else 0
             b.hparams_dev = self.hp_dev.data_ptr()
             b.comm_epoch = self.comm_epoch.data_ptr()
+            pt = getattr(net, "param_tie", None)
+            b.param_tie = pt.data_ptr() if pt is not None else 0
             self.bufs.append(b)
         self._hp_host = np.zeros(_lib.HP_FLOATS, np.float32)
         self.set_hparams()

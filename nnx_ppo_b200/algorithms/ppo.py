@@ -191,7 +191,7 @@ def _extra_metrics(m: dict, net, eng, logging_level, percentiles) -> None:
         if hasattr(net, "logical_index_dev"):
             w = net.arena[net.logical_index_dev()]
         else:
-            w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask != 0]
+            w = net.arena if getattr(net, "param_mask", None) is None else net.arena[net.param_mask == 1]
         _log_metric(m, "weights", w, percentiles)
 
 

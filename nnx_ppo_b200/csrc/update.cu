@@ -1048,7 +1048,9 @@ struct AdamArgs {
   int do_adam;                      // 0: reduce / exchange / norm only
   // nullable: squared global norm of the (summed) gradient -> *norm_out (block partials, ticket, fixed order)
   double* norm_part; double* norm_out; unsigned int* norm_ticket;
-  const uint8_t* mask;  // nullable: 0 = structural zero (off-diagonal block of per-key encoders), never updated
+  const uint8_t* mask;  // nullable: 0 = structural zero (off-diagonal block of per-key encoders), never updated;
+                        // 2 = second copy of a tied (shared-trunk) parameter: updated, not counted in the norm
+  const int32_t* tie;   // nullable: index of the tied partner of parameter i, or -1 (used with S > 0 only)
   // tensor-core path: the updated weight is also re-split into the hi / lo operand planes of the next
   // update (what upd_prep_w_kernel does from scratch), so that update can skip its prep launch
   int n_seg;                                   // 0: no refresh
@@ -1068,6 +1070,12 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   if (in) {
     if (a.S > 0) {
       for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
+      const int32_t j = a.tie ? a.tie[i] : -1;
+      if (j >= 0) {          // shared trunk: d(loss)/d(w) = the actor path's + the critic path's (a + b == b + a:
+        float g2 = 0.0f;     // both copies get the same bits)
+        for (int sp = 0; sp < a.S; ++sp) g2 += a.gpart[static_cast<size_t>(sp) * a.P + j];
+        g = __fadd_rn(g, g2);
+      }
     } else {
       g = a.grad[i];
     }
@@ -1086,7 +1094,7 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   }
   if (in && a.grad_out != nullptr) a.grad_out[i] = g;
   if (a.norm_part != nullptr) {
-    double sq = (in && !(a.mask && !a.mask[i])) ? static_cast<double>(g) * g : 0.0;
+    double sq = (in && !(a.mask && a.mask[i] != 1)) ? static_cast<double>(g) * g : 0.0;
     sq = warp_sum_d(sq);
     if ((threadIdx.x & 31) == 0) nred[threadIdx.x >> 5] = sq;
     __syncthreads();
@@ -1401,7 +1409,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.comm = do_adam ? pc : PeerComm{nullptr, 1, 0};
     a.comm_ppad = comm_ppad(plan->n_params);
     a.norm_part = nullptr; a.norm_out = dbl + 2; a.norm_ticket = tickets + 2;
-    a.mask = b->param_mask;
+    a.mask = b->param_mask; a.tie = b->param_tie;
     a.n_seg = 0; a.ws = ws;
     if (use_tc) {
       for (int c = 0; c < 2; ++c) {

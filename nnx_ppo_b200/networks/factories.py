@@ -112,3 +112,32 @@ def make_dict_actor_critic(obs_sizes: dict, action_size: int, encoder_hidden: di
     if normalize_obs:
         return Sequential([Normalizer(sum(obs_sizes.values())), adapter])
     return adapter
+
+
+def make_shared_trunk_actor_critic(obs_size: int, action_size: int, trunk_sizes: list[int],
+                                   actor_head_sizes: list[int], critic_head_sizes: list[int], rngs: prng.Rngs,
+                                   activation: Union[Callable, str] = feedforward.relu, normalize_obs: bool = True,
+                                   entropy_weight: float = 1e-2, min_std: float = 1e-1,
+                                   std_scale: float = 1.0) -> StatefulModule:
+    """The shared-trunk network of the reference's composition tutorial (docs/tutorials/02_composition.rst,
+    "shared body"): ``Sequential([Normalizer?, trunk MLP (activation after every layer), PPOAdapter(action =
+    Sequential([actor head MLP, sampler]), value = critic head MLP)])`` - both ports read the trunk's features.
+    Key-draw order: trunk, actor head, critic head, sampler."""
+    if isinstance(activation, str):
+        activation = {"swish": feedforward.swish, "tanh": feedforward.tanh, "relu": feedforward.relu}[activation]
+
+    def kernel_init(key, shape):
+        return prng.variance_scaling_uniform(key, shape[0], shape[1], 1.0)
+
+    trunk = make_mlp([obs_size] + list(trunk_sizes), rngs, activation, activation_last_layer=True, kernel_init=kernel_init)
+    width = trunk_sizes[-1]
+    actor_head = make_mlp_layers([width] + list(actor_head_sizes) + [action_size * 2], rngs, activation,
+                                 activation_last_layer=False, kernel_init=kernel_init)
+    critic_head = make_mlp([width] + list(critic_head_sizes) + [1], rngs, activation, activation_last_layer=False,
+                           kernel_init=kernel_init)
+    sampler = NormalTanhSampler(rngs, entropy_weight=entropy_weight, min_std=min_std, std_scale=std_scale)
+    adapter = PPOAdapter(action=Sequential([*actor_head, sampler]), value=critic_head)
+    layers = [trunk, adapter]
+    if normalize_obs:
+        layers.insert(0, Normalizer(obs_size))
+    return Sequential(layers)

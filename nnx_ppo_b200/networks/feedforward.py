@@ -42,6 +42,7 @@ class Param:
     def __init__(self, value: np.ndarray):
         self._host = np.ascontiguousarray(value, np.float32)
         self._dev = None
+        self._after_set = None          # compiled shared-trunk parameters: re-sync the tied second copy
 
     @property
     def shape(self):
@@ -61,6 +62,8 @@ class Param:
         if self._dev is not None:
             import torch
             self._dev.copy_(torch.from_numpy(value))
+            if self._after_set is not None:
+                self._after_set()
         self._host = value.copy()
 
     def __getitem__(self, idx):

@@ -27,6 +27,28 @@ def _align4(n: int) -> int:
     return (n + 3) & ~3
 
 
+def _flatten_trunk(modules) -> list:
+    """The layer modules of a shared trunk in order (nested Sequentials opened; a Concat may lead)."""
+    out = []
+    for m in modules:
+        if isinstance(m, Sequential):
+            out += _flatten_trunk(m.layers)
+        elif isinstance(m, (Dense, Concat)):
+            out.append(m)
+        else:
+            raise NotImplementedError(f"unsupported module {type(m).__name__} in a shared trunk (Dense stacks only)")
+    return out
+
+
+def _module_tree(m, leaf):
+    """`leaf` arranged like the state / rollout_extras pytree of module `m` (containers.py:18-39)."""
+    if isinstance(m, Sequential):
+        return [_module_tree(c, leaf) for c in m.layers]
+    if isinstance(m, Concat):
+        return {k: _module_tree(c, leaf) for k, c in m.components.items()}
+    return leaf
+
+
 class _VLayer:
     """One layer of a lowered chain: a plain Dense (one block) or the block-diagonal union of the
     same-depth Dense layers of a Concat's per-key encoders (blocks = [(row0, col0, Dense)])."""
@@ -86,18 +108,23 @@ class CompiledNet:
         # leading observation adapters (networks/utils.py: Flattener / Filter) are host plumbing
         # applied to the observation before the kernels see it; the plan starts after them
         self.obs_adapters = []
+        # shared trunk (docs/tutorials/02_composition.rst "shared body"): Dense stacks between the Normalizer and the
+        # PPOAdapter feed BOTH ports.  Lowered as the head of both chains: the trunk's parameters exist twice in
+        # the arena (actor copy, critic copy), tied - the update kernels add the two copies' gradients and give
+        # both the same optimizer step, so they stay bit-identical.
+        self.trunk_modules: list = []
         if isinstance(network, Sequential):
             layers = list(network.layers)
             while len(layers) > 1 and isinstance(layers[0], (Flattener, Filter)):
                 self.obs_adapters.append(layers.pop(0))
-            if len(layers) == 2 and isinstance(layers[0], Normalizer) and isinstance(layers[1], PPOAdapter):
-                normalizer, adapter = layers
-            elif len(layers) == 1 and isinstance(layers[0], PPOAdapter):
-                adapter = layers[0]
-            else:
+            if layers and isinstance(layers[0], Normalizer):
+                normalizer = layers.pop(0)
+            if not layers or not isinstance(layers[-1], PPOAdapter):
                 raise NotImplementedError(
                     "unsupported network topology: expected Sequential([Flattener / Filter..., Normalizer?, "
-                    "PPOAdapter]) or PPOAdapter (the MLP plan of make_mlp_actor_critic)")
+                    "shared Dense trunk..., PPOAdapter]) or PPOAdapter (the MLP plans)")
+            adapter = layers[-1]
+            self.trunk_modules = layers[:-1]
         if not isinstance(adapter, PPOAdapter):
             raise NotImplementedError("unsupported network topology: no PPOAdapter found")
         action = adapter.action
@@ -105,8 +132,15 @@ class CompiledNet:
             raise NotImplementedError("action port must be Sequential([Dense..., NormalTanhSampler])")
         self.sampler: NormalTanhSampler = action.layers[-1]
         value = adapter.value
-        actor_layers, self.obs_keys, self.obs_sizes = _lower_chain(action.layers[:-1])
-        critic_layers, ck, cs = _lower_chain(list(value.layers) if isinstance(value, Sequential) else [value])
+        trunk_flat = _flatten_trunk(self.trunk_modules)
+        self.n_trunk_layers = 0
+        actor_layers, self.obs_keys, self.obs_sizes = _lower_chain(trunk_flat + list(action.layers[:-1]))
+        critic_layers, ck, cs = _lower_chain(trunk_flat + (list(value.layers) if isinstance(value, Sequential) else [value]))
+        if trunk_flat:
+            self.n_trunk_layers = len(_lower_chain(trunk_flat)[0])
+            for vl in actor_layers[:self.n_trunk_layers]:
+                if vl.activation_name == "none":
+                    raise NotImplementedError("a shared trunk must apply its activation after every layer")
         if ck is not None and self.obs_keys is not None and (ck != self.obs_keys or cs != self.obs_sizes):
             raise NotImplementedError("actor and critic must split the observation dict the same way")
         if self.obs_keys is None:
@@ -163,7 +197,9 @@ class CompiledNet:
         # per-key encoders of a Concat, whose layers are stored block-diagonally)
         host = np.zeros(off, np.float32)
         mask = np.ones(off, np.uint8)
+        tie = np.full(off, -1, np.int32)
         masked = False
+        nt = self.n_trunk_layers
         for chain, layers in ((plan.actor, actor_layers), (plan.critic, critic_layers)):
             for i, vl in enumerate(layers):
                 K, N = vl.in_features, vl.out_features
@@ -178,16 +214,25 @@ class CompiledNet:
                 mask[chain.w_off[i]:chain.w_off[i] + K * N] = Md.ravel()
                 host[chain.b_off[i]:chain.b_off[i] + N] = bd
                 masked = masked or len(vl.blocks) > 1
+        for i in range(nt):                           # tie the two copies of every trunk layer
+            K, N = actor_layers[i].in_features, actor_layers[i].out_features
+            for oa, oc, n in ((plan.actor.w_off[i], plan.critic.w_off[i], K * N), (plan.actor.b_off[i], plan.critic.b_off[i], N)):
+                tie[oa:oa + n] = np.arange(oc, oc + n, dtype=np.int32)
+                tie[oc:oc + n] = np.arange(oa, oa + n, dtype=np.int32)
+                mask[oc:oc + n] = np.where(mask[oc:oc + n] != 0, 2, 0)      # 2: duplicate copy (updated, not counted in the norm)
+            masked = True
         self.arena = torch.from_numpy(host).to(device)
         self.param_mask = torch.from_numpy(mask).to(device) if masked else None
+        self.param_tie = torch.from_numpy(tie).to(device) if nt else None
+        self._tie_pairs = None
+        if nt:
+            dup = np.nonzero(mask == 2)[0]
+            self._tie_pairs = (torch.from_numpy(dup.astype(np.int64)).to(device),
+                               torch.from_numpy(tie[dup].astype(np.int64)).to(device))
         self._logical_params = []
         index = []
-        for chain, layers in ((plan.actor, actor_layers), (plan.critic, critic_layers)):
-            # logical (oracle) order: per key, the encoder's layers; then the shared trunk layers
-            nkeys = max(len(vl.blocks) for vl in layers)
-            enc_depth = sum(1 for vl in layers if len(vl.blocks) > 1)
-            order = [(j, kb) for kb in range(nkeys) for j in range(enc_depth)] if nkeys > 1 else []
-            order += [(j, 0) for j in range(enc_depth if nkeys > 1 else 0, len(layers))]
+        for ci, (chain, layers) in enumerate(((plan.critic, critic_layers), (plan.actor, actor_layers))):
+            # (critic first so that a shared trunk's Params end up as views of the ACTOR copy)
             for i, vl in enumerate(layers):
                 K, N = vl.in_features, vl.out_features
                 Wv = self.arena[chain.w_off[i]:chain.w_off[i] + K * N].view(K, N)
@@ -195,7 +240,18 @@ class CompiledNet:
                 for r0, c0, d in vl.blocks:
                     d.linear.kernel._dev = Wv[r0:r0 + d.in_features, c0:c0 + d.out_features]
                     d.linear.bias._dev = bv[c0:c0 + d.out_features]
+                    if i < nt:
+                        d.linear.kernel._after_set = d.linear.bias._after_set = self.sync_tied
+        for ci, (chain, layers) in enumerate(((plan.actor, actor_layers), (plan.critic, critic_layers))):
+            # logical (oracle) order: per key, the encoder's layers; then the shared trunk layers; the critic's
+            # copy of a shared trunk is not a parameter of its own
+            nkeys = max(len(vl.blocks) for vl in layers)
+            enc_depth = sum(1 for vl in layers if len(vl.blocks) > 1)
+            order = [(j, kb) for kb in range(nkeys) for j in range(enc_depth)] if nkeys > 1 else []
+            order += [(j, 0) for j in range(enc_depth if nkeys > 1 else 0, len(layers))]
             for j, kb in order:
+                if ci == 1 and j < nt:
+                    continue
                 r0, c0, d = layers[j].blocks[kb]
                 N = layers[j].out_features
                 self._logical_params += [d.linear.kernel, d.linear.bias]
@@ -231,15 +287,16 @@ class CompiledNet:
         """Per-layer list of the enclosing Sequential: `leaf` for every adapter, then the Normalizer's
         entry (`obs_flat` for extras, `()` for state), then the PPOAdapter's part."""
         n = len(self.obs_adapters)
+        trunk = [_module_tree(m, leaf) for m in self.trunk_modules]
         if self.normalizer is not None:
-            return [leaf] * n + [obs_flat, adapter_part]
-        if n:
-            return [leaf] * n + [adapter_part]
+            return [leaf] * n + [obs_flat] + trunk + [adapter_part]
+        if n or trunk:
+            return [leaf] * n + trunk + [adapter_part]
         return adapter_part
 
     def adapter_extras(self, rollout_extras):
         """The PPOAdapter's part of a rollout_extras pytree produced by ``wrap``."""
-        if self.normalizer is not None or self.obs_adapters:
+        if self.normalizer is not None or self.obs_adapters or self.trunk_modules:
             return rollout_extras[-1]
         return rollout_extras
 
@@ -249,7 +306,7 @@ class CompiledNet:
         by position (containers.py:36), the PPOAdapter by port name (adapter.py:112)."""
         path = []
         if self.network is not self.adapter:
-            path.append(len(self.obs_adapters) + (1 if self.normalizer is not None else 0))
+            path.append(len(self.obs_adapters) + (1 if self.normalizer is not None else 0) + len(self.trunk_modules))
         path += ["action", len(self.adapter.action.layers) - 1]
         return path
 
@@ -284,6 +341,14 @@ class CompiledNet:
         host = self.arena.detach().cpu().numpy().copy()
         host[self._logical_index] = np.asarray(flat, np.float32)
         self.arena.copy_(torch.from_numpy(host))
+        self.sync_tied()
+
+    def sync_tied(self) -> None:
+        """Copy the actor copy of a shared trunk over the critic copy (after parameters were written from
+        outside: checkpoint load, ``Param.set``); training keeps the two bit-identical by itself."""
+        if getattr(self, "_tie_pairs", None) is not None:
+            dup, src = self._tie_pairs
+            self.arena[dup] = self.arena[src]
 
     # ---- sampler stream bookkeeping (host mirror of counters[2]) ----
     @property

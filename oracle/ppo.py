@@ -235,6 +235,8 @@ def ppo_loss_and_grads(net: ActorCritic, ro: Rollout, inds: np.ndarray, rng_coun
         for dW, db in zip(dWs, dbs):
             parts += [dW.ravel(), db.ravel()]
     grads = np.concatenate(parts).astype(F)
+    if hasattr(net, "fold_grads"):            # shared trunk (oracle/sharednet.py): one parameter, two paths
+        grads = net.fold_grads(grads)
     return total, metrics, grads
 
 

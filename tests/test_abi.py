@@ -38,7 +38,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.Chain) == 4 + 4 + 9 * 4 + 4 + 8 * 8 + 8 * 8
     assert ctypes.sizeof(_lib.Plan) == 16 + 16 + 8 + 2 * ctypes.sizeof(_lib.Chain)
     assert ctypes.sizeof(_lib.HParams) == 52
-    assert ctypes.sizeof(_lib.UpdateBufs) == 20 * 8
+    assert ctypes.sizeof(_lib.UpdateBufs) == 21 * 8
     assert ctypes.sizeof(_lib.SynthEnv) == 32
 
 

@@ -176,6 +176,14 @@ def test_normalizer_default_std_is_ten(dev):
 # ------------------------------------------------------------------------------------------
 # K1 policy step (sample / replay / deterministic)
 # ------------------------------------------------------------------------------------------
+def _trunk_pair(obs_dim, act_dim, trunk, ah, ch, seed, act="relu"):
+    from nnx_ppo_b200.networks.factories import make_shared_trunk_actor_critic
+    from oracle import sharednet
+    nets = make_shared_trunk_actor_critic(obs_dim, act_dim, trunk, ah, ch, Rngs(seed), activation=act)
+    onet = sharednet.make_shared_trunk_actor_critic(obs_dim, act_dim, trunk, ah, ch, seed=seed, activation=act)
+    return nets, onet
+
+
 def _pair(obs_dim, act_dim, ah, ch, seed, act="relu", **kw):
     nets = make_mlp_actor_critic(obs_dim, act_dim, ah, ch, Rngs(seed), activation=act, **kw)
     onet = onets.make_mlp_actor_critic(obs_dim, act_dim, ah, ch, seed=seed, activation=act, **kw)
@@ -203,7 +211,7 @@ def test_policy_step_matches_oracle(dev, cfg):
     assert np.allclose(po.loglikelihoods.cpu().numpy(), ref["loglik"], rtol=1e-4, atol=1e-4)
     assert np.allclose(po.value_estimates.cpu().numpy(), ref["value"], **tol)
     assert np.allclose(out.regularization_loss.cpu().numpy(), ref["reg"], rtol=1e-4, atol=1e-5)
-    assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+    assert nets.layers[-1].action.layers[-1].rng.count == onet.rng_count
     # replay (adapter_test.py:61-75): same weights + stored extras -> same actions and log-probs
     out2 = nets(state, torch.from_numpy(obs).to(dev), out.rollout_extras)
     assert torch.equal(out2.output.actions, po.actions)
@@ -272,7 +280,7 @@ def test_fused_rollout_matches_oracle(dev, cfg):
     assert np.allclose(tr.rewards.cpu().numpy(), oro.reward, **tol)
     assert np.allclose(tr.next_obs.cpu().numpy(), oro.next_obs_last, **tol)
     assert np.allclose(env2.obs.cpu().numpy(), oenv2.obs, **tol)
-    assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+    assert nets.layers[-1].action.layers[-1].rng.count == onet.rng_count
 
 
 # ------------------------------------------------------------------------------------------
@@ -307,6 +315,8 @@ def _single_update(dev, cfg, loose):
         nets = make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], Rngs(5), activation=cfg["act"])
         onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], seed=5,
                                               activation=cfg["act"])
+    elif "trunk" in cfg:            # shared trunk feeding both PPOAdapter ports (tutorial 02_composition)
+        nets, onet = _trunk_pair(O, A, cfg["trunk"], cfg["ah"], cfg["ch"], 5, cfg["act"])
     else:
         nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
     env = SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
@@ -446,6 +456,8 @@ def _iterations(dev, cfg):
         from oracle import dictnet
         nets = make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], Rngs(0))
         onet = dictnet.make_dict_actor_critic(cfg["obs_sizes"], A, cfg["enc"], cfg["ah"], cfg["ch"], seed=0)
+    elif "trunk" in cfg:
+        nets, onet = _trunk_pair(O, A, cfg["trunk"], cfg["ah"], cfg["ch"], 0)
     else:
         nets, onet = _pair(O, A, cfg["ah"], cfg["ch"], 0)
     ekw = dict(max_len=cfg.get("max_len", 48), term_thresh16=cfg.get("thresh", 700))
@@ -467,7 +479,7 @@ def _iterations(dev, cfg):
         assert np.array_equal(u32(ts.env_states.term_state), ots.env_state.term_state)
         assert tuple(ts.rng_key) == tuple(int(x) for x in ots.rng_key)
         assert float(ts.steps_taken) == float(ots.steps_taken) == (it + 1) * T * B
-        assert nets.layers[1].action.layers[-1].rng.count == onet.rng_count
+        assert nets.layers[-1].action.layers[-1].rng.count == onet.rng_count
         cnt = u32(net.counters)
         assert cnt[2] == onet.rng_count and cnt[3] == (it + 1) * E * M == ots.opt.count
         assert float(net.normalizer.counter.numpy()[0]) == (it + 1) * T * B            # ppo_test.py:344-349
@@ -483,6 +495,45 @@ def _iterations(dev, cfg):
         assert np.allclose(net.normalizer.M2.numpy(), onet.M2, rtol=2e-3)
         assert np.allclose(ts.env_states.obs.cpu().numpy(), ots.env_state.obs, rtol=1e-3, atol=1e-3)
     assert eng.graph is not None or cfg["iters"] < 2    # iterations >= 2 ran from the captured CUDA graph
+
+
+# ------------------------------------------------------------------------------------------
+# shared trunk: Sequential([Normalizer, trunk, PPOAdapter(action=head+sampler, value=head)])
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [
+    dict(O=40, A=6, trunk=[64, 48], ah=[32], ch=[64, 16], B=128, T=16, M=2, act="relu", clip=None, wd=None),
+    dict(O=17, A=2, trunk=[96], ah=[], ch=[24], B=70, T=7, M=2, act="tanh", clip=0.5, wd=1e-3)])
+@pytest.mark.parametrize("gemm", [0, 1])
+def test_shared_trunk_single_update_matches_oracle(dev, cfg, gemm):
+    """The trunk's gradient is the SUM of the actor path's and the critic path's (the tied copies of the plan):
+    same per-stage checks as test_single_update_matches_oracle, oracle/sharednet.py as the reference."""
+    _lib.load().b200ppo_set_gemm_mode(gemm)
+    try:
+        _single_update(dev, cfg, 1.0)
+    finally:
+        _lib.load().b200ppo_set_gemm_mode(1)
+
+
+def test_shared_trunk_iterations_match_oracle(dev):
+    cfg = dict(O=40, A=6, trunk=[64, 48], ah=[32], ch=[64, 16], B=256, T=16, E=2, M=4, iters=3)
+    _iterations(dev, cfg)
+    # the two copies of the trunk (actor chain's, critic chain's) stayed bit-identical through 24 updates, in
+    # the parameters and in both Adam moments; the user-visible Params are views of the live arena
+    from nnx_ppo_b200.networks.plan import compile_network as cn
+    # (the engine / compiled plan of the last _iterations call is reachable through its network only; rebuild)
+    nets, _ = _trunk_pair(40, 6, [64, 48], [32], [64, 16], 0)
+    env = SyntheticEnv(40, 6, max_len=48, term_thresh16=700)
+    ts = ppo.new_training_state(env, nets, 256, 17, gradient_clipping=0.3)
+    net = cn(nets)
+    for _ in range(3):
+        ts, m = ppo.ppo_step(env, ts, 256, 16, 0.95, 0.99, 0.2, True, False, 2, 4)
+    dup, src = net._tie_pairs
+    assert dup.numel() == 40 * 64 + 64 + 64 * 48 + 48
+    for arr in (net.arena, ts.optimizer.mu, ts.optimizer.nu):
+        assert torch.equal(arr[dup], arr[src])
+    trunk0 = nets.layers[1].layers[0]
+    assert torch.equal(trunk0.linear.kernel.value.reshape(-1), net.arena[net.plan.actor.w_off[0]:net.plan.actor.w_off[0] + 40 * 64])
+    assert not np.array_equal(trunk0.linear.kernel.numpy(), _trunk_pair(40, 6, [64, 48], [32], [64, 16], 0)[0].layers[1].layers[0].linear.kernel.numpy())
 
 
 def test_adam_refreshes_split_weight_planes(dev, monkeypatch):

@@ -382,7 +382,10 @@ def _single_update(dev, cfg, loose):
         assert np.linalg.norm(got_g - grads) < 0.2 * np.linalg.norm(grads)
         return
     dy = _dbg(eng, 3, R * 2 * A).reshape(R, 2 * A)
-    assert np.abs(dy - m["d_y"]).max() < 1e-4 * loose * max(np.abs(m["d_y"]).max(), 1e-6) + 1e-9
+    # a probability ratio within rounding of 1 +- clip_range may fall on the other side of the clip (its
+    # sample's gradient is then zero on one side only): allow one such row per 4096 samples
+    bad = (np.abs(dy - m["d_y"]) >= 1e-4 * loose * max(np.abs(m["d_y"]).max(), 1e-6) + 1e-9).any(axis=1)
+    assert bad.sum() <= R // 4096, (int(bad.sum()), R)
     dv = _dbg(eng, 4, R)
     assert np.abs(dv - m["d_v"]).max() < 1e-4 * loose * np.abs(m["d_v"]).max() + 1e-10
     got_g = net.params_logical(eng.grad)

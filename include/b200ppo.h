@@ -319,6 +319,11 @@ typedef struct b200ppo_lstm_plan {
   int64_t wcat_off, bl_off;                     /* LSTM       [pre_dim + hidden, 4 hidden], [4 hidden] */
   int64_t w2_off, b2_off;                       /* post Dense [hidden, out_dim], [out_dim]         */
   int64_t n_params;
+  /* trainable_initial_state (recurrent.py:85-87, 135-141, 154-157): arena offsets of the learned carry a
+   * reset hands out, [hidden] each - init_c_off for carry slot 0 (the reference's `initial_h` Param, which
+   * flax's cell reads as c), init_h_off for slot 1; both 0 (a zero-initialised struct): reset to zeros.
+   * Sequence API only (the b200ppo_lstm_step_* kernels reject a plan that has them). */
+  int64_t init_c_off, init_h_off;
 } b200ppo_lstm_plan;
 /* floats of the per-step activation cache the backward step needs, for `rows` rows */
 int64_t b200ppo_lstm_cache_floats(const b200ppo_lstm_plan* plan, int32_t rows);

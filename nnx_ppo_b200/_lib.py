@@ -56,7 +56,8 @@ class LstmPlan(C.Structure):
     _fields_ = [("obs_dim", C.c_int32), ("pre_dim", C.c_int32), ("hidden", C.c_int32), ("out_dim", C.c_int32),
                 ("act", C.c_int32), ("normalize", C.c_int32),
                 ("w1_off", C.c_int64), ("b1_off", C.c_int64), ("wcat_off", C.c_int64), ("bl_off", C.c_int64),
-                ("w2_off", C.c_int64), ("b2_off", C.c_int64), ("n_params", C.c_int64)]
+                ("w2_off", C.c_int64), ("b2_off", C.c_int64), ("n_params", C.c_int64),
+                ("init_c_off", C.c_int64), ("init_h_off", C.c_int64)]
 
 
 class SynthEnv(C.Structure):

@@ -49,6 +49,8 @@ def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     H, Y, P = lp.hidden, lp.out_dim, lp.pre_dim
     f32 = dict(dtype=torch.float32, device=dev)
     eng.r_seq = bool(lib.b200ppo_lstm_seq_supported(lp)) and os.environ.get("B200PPO_LSTM", "tc") != "ffma"
+    if net.init_views is not None and not eng.r_seq:
+        raise NotImplementedError("trainable_initial_state is implemented by the sequence kernels only (B200PPO_LSTM=ffma is set)")
     eng.r_c, eng.r_h = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
     eng.r_y = torch.zeros(n_envs, Y, **f32)
     eng.r_carry = (torch.zeros(n_envs, H, **f32), torch.zeros(n_envs, H, **f32))      # live carry of every env
@@ -134,9 +136,13 @@ def _enqueue_iteration(eng, net, env, env_state):
         eng.trunc[t].copy_(tr.bool().to(torch.uint8))
         if t == T - 1:
             eng.next_obs_last.copy_(nxt.obs)
-        keep = (~done).to(torch.float32)[:, None]                        # reset_state -> zeros (rollout.py:33-40)
-        c.mul_(keep)
-        h.mul_(keep)
+        if net.init_views is None:                                       # reset_state -> zeros (rollout.py:33-40)
+            keep = (~done).to(torch.float32)[:, None]
+            c.mul_(keep)
+            h.mul_(keep)
+        else:                                                            # ... or the learned initial carry
+            torch.where(done[:, None], net.init_views[0], c, out=c)
+            torch.where(done[:, None], net.init_views[1], h, out=h)
         env_state = tree_where(done, env.reset(keys_all[t].contiguous()), nxt)
     # ---------------- E x M minibatch updates (ppo.py:284-328)
     _lib.check(lib.b200ppo_permutation(s, eng.iter_keys.data_ptr() + 8, B, eng.E, eng.inds.data_ptr(),

@@ -153,9 +153,7 @@ def _unroll_generic(env, env_state, networks, network_state, T: int, reset_key):
         nxt = env.step(env_state, po.actions)
         done = nxt.done.bool()
         if net.recurrent:                                                 # rollout.py:33-40: reset the carry on done
-            c, h = net.get_carry(out.next_state)
-            keep = (~done).to(torch.float32)[:, None]
-            network_state = net.set_carry(out.next_state, (c * keep, h * keep))
+            network_state = net.set_carry(out.next_state, net.reset_carry(net.get_carry(out.next_state), done))
         tr = nxt.info.get("truncated", torch.zeros_like(done)) if isinstance(nxt.info, dict) else torch.zeros_like(done)
         rec["obs"].append(net.flat_obs(env_state.obs))               # what the kernels saw (adapters applied)
         extras = net.adapter_extras(out.rollout_extras)

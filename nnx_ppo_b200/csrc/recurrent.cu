@@ -419,6 +419,7 @@ int check_lstm_plan(const b200ppo_lstm_plan* p) {
   if (!p || p->obs_dim <= 0 || p->pre_dim <= 0 || p->hidden <= 0 || p->out_dim <= 0 || p->n_params <= 0)
     return B200PPO_EINVAL;
   if (p->act < 0 || p->act > 3) return B200PPO_EINVAL;
+  if (p->init_c_off > 0 || p->init_h_off > 0) return B200PPO_ELIMIT;     // learned initial carry: sequence API only
   const int64_t offs[6] = {p->w1_off, p->b1_off, p->wcat_off, p->bl_off, p->w2_off, p->b2_off};
   const int64_t lens[6] = {static_cast<int64_t>(p->obs_dim) * p->pre_dim, p->pre_dim,
                            static_cast<int64_t>(p->pre_dim + p->hidden) * 4 * p->hidden, 4ll * p->hidden,

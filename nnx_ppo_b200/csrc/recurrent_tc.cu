@@ -611,6 +611,7 @@ struct SeqLayout {
   size_t dhr;                             // split-K partials [4][tiles][H / 4][PLC]
   size_t whf, whb;                        // weight planes
   size_t flags;                           // int32 [tiles][T + 1] arrival counters of the persistent forward kernel
+  size_t mdc, mdh, ipart;                 // learned initial carry: masked per-step gradient planes, per-step sums
   size_t part, bpart, total;
   int tiles, NBT, nbt;
   size_t hp_half, hp_buf, st_tile, cache_step, dap_half;
@@ -662,6 +663,10 @@ SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   L.whf = take((H / UT) * 2 * planes * plb(4 * UT));
   L.whb = take(static_cast<size_t>(L.nbt) * 4 * 2 * planes * plb(L.NBT));
   L.flags = take(tiles * (static_cast<size_t>(T) + 1));
+  const size_t tr = p.init_c_off > 0 ? 1 : 0;
+  L.mdc = take(tr * T * L.cache_step);
+  L.mdh = take(tr * T * L.cache_step);
+  L.ipart = take(tr * T * 2 * H);
   const int Rr = static_cast<int>(R);
   L.S_cat = split_for(cdiv(P + H, RM) * cdiv(4 * H, 256), Rr);
   L.S_w1 = split_for(cdiv(p.obs_dim, RM), Rr);
@@ -701,6 +706,12 @@ int check_plan_tc(const b200ppo_lstm_plan* p) {
   // (b200ppo_lstm_step_fwd / _bwd) have no such limits
   if (p->hidden % UT || p->pre_dim % 4) return B200PPO_ELIMIT;
   if (p->pre_dim > 4096 || p->out_dim > 4096 || p->obs_dim > 65536) return B200PPO_ELIMIT;
+  // learned initial carry: both or neither, inside the arena, 16-byte aligned
+  if ((p->init_c_off > 0) != (p->init_h_off > 0)) return B200PPO_EINVAL;
+  if (p->init_c_off > 0) {
+    if ((p->init_c_off & 3) || (p->init_h_off & 3)) return B200PPO_EALIGN;
+    if (p->init_c_off + p->hidden > p->n_params || p->init_h_off + p->hidden > p->n_params) return B200PPO_EINVAL;
+  }
   return 0;
 }
 
@@ -814,7 +825,8 @@ extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int3
   const size_t p_smem = 2 * static_cast<size_t>(plan->hidden / 4) * tc::plane_bytes(4 * UT) + PF_NS * 2u * (RK / 4) * tc::plane_bytes(RM);
   const int steps = (seq_persistent(*plan, T, rows) && p_smem <= PERSIST_SMEM_MAX) ? 1 : T;
   if (!backward) return 1 /* weight planes */ + 2 /* carry in */ + 2 /* pre, proj */ + steps + 1 /* post */ + 2 /* carry out */;
-  return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */;
+  return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */ +
+         (plan->init_c_off > 0 ? 2 : 0) /* initial-carry gradient */;
 }
 
 extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* plan, const float* params,
@@ -893,6 +905,8 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     }
     a.done = done != nullptr ? done + static_cast<size_t>(t) * B : nullptr;
     a.inds = inds;
+    a.init_c = plan->init_c_off > 0 ? params + plan->init_c_off : nullptr;
+    a.init_h = plan->init_h_off > 0 ? params + plan->init_h_off : nullptr;
     a.rows = rows; a.H = H;
     return a;
   };
@@ -978,6 +992,8 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
     e.inds = inds;
     e.da_rm = da + static_cast<size_t>(t) * rows * 4 * H;
     e.dap_hi = ws + L.dap; e.dap_lo = ws + L.dap + L.dap_half; e.dap_tile = dap_tile; e.dap_slice = dap_slice;
+    e.mdc = plan->init_c_off > 0 ? ws + L.mdc + so : nullptr;
+    e.mdh = plan->init_c_off > 0 ? ws + L.mdh + so : nullptr;
     e.rows = rows; e.H = H;
     lstm_step_bwd2_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(e);
     B200PPO_LAUNCH_CHECK();
@@ -991,6 +1007,16 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
       lstm_step_bwd_gemm_kernel<<<dim3(L.tiles, L.nbt, 4), RT, SP_NS * sp_slot_bytes(L.NBT), s>>>(g);
       B200PPO_LAUNCH_CHECK();
     }
+  }
+  if (plan->init_c_off > 0) {     // gradient of the learned initial carry (recurrent.py:85-87 Params)
+    InitGradArgs ig;
+    ig.mdc = ws + L.mdc; ig.mdh = ws + L.mdh; ig.step_stride = static_cast<long long>(L.cache_step);
+    ig.st_tile = static_cast<long long>(L.st_tile); ig.tiles = L.tiles; ig.rows = rows; ig.H = H; ig.T = T;
+    ig.part = ws + L.ipart; ig.g_c = grad + plan->init_c_off; ig.g_h = grad + plan->init_h_off;
+    lstm_init_grad_part_kernel<<<dim3(planes, T), RM, 0, s>>>(ig);
+    B200PPO_LAUNCH_CHECK();
+    lstm_init_grad_sum_kernel<<<cdiv(2 * H, 256), 256, 0, s>>>(ig);
+    B200PPO_LAUNCH_CHECK();
   }
   // du = da Wi^T;  dz1 = du * act'(z1)
   {

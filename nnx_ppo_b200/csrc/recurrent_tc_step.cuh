@@ -234,6 +234,7 @@ struct StepFwd2Args {
   float* hn_rm;                                                  // row-major pre-reset h' [rows][H]
   float* gi; float* gf; float* gg; float* go; float* tcc; float* cin;   // activation cache planes [tile][H / 4][PLC] (all or none)
   const uint8_t* done; const int32_t* inds;
+  const float* init_c; const float* init_h;                      // learned reset carry [H] each (nullable: zeros)
   int rows, H;
 };
 
@@ -310,9 +311,12 @@ __global__ void __launch_bounds__(RT, 1) lstm_step_fwd2_kernel(const StepFwd2Arg
       *reinterpret_cast<float4*>(d) = make_float4(h2[0], h2[1], h2[2], h2[3]);
       *reinterpret_cast<float4*>(d + 4) = make_float4(h2[4], h2[5], h2[6], h2[7]);
     }
-    if (dn) {
+    if (dn) {                       // reset_state: zeros, or the learned initial carry (recurrent.py:154-157)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { c2[k] = 0.0f; h2[k] = 0.0f; }
+      for (int k = 0; k < 8; ++k) {
+        c2[k] = a.init_c != nullptr ? a.init_c[u0 + k] : 0.0f;
+        h2[k] = a.init_h != nullptr ? a.init_h[u0 + k] : 0.0f;
+      }
     }
     stp(a.cp, c2);
     {
@@ -347,6 +351,10 @@ struct StepBwd2Args {
   const uint8_t* done; const int32_t* inds;
   float* da_rm;                                // [rows][4H]
   float* dap_hi; float* dap_lo; long long dap_tile; long long dap_slice;   // A planes [tile][slice q][H / 4][PLA]
+  // learned initial carry (nullable): where this step's `done` is set, the gradient that would have flowed into the
+  // carry handed on belongs to the initial-carry parameters instead - kept per step as planes [tile][H / 4][PLC]
+  // (zeros elsewhere) and summed in fixed order by lstm_init_grad_kernel
+  float* mdc; float* mdh;
   int rows, H;
 };
 
@@ -372,12 +380,16 @@ __global__ void __launch_bounds__(256) lstm_step_bwd2_kernel(const StepBwd2Args 
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
       dh[0] += keep * s.x; dh[1] += keep * s.y; dh[2] += keep * s.z; dh[3] += keep * s.w;
+      if (a.mdh != nullptr) *reinterpret_cast<float4*>(a.mdh + so) = dn ? s : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (a.mdh != nullptr) {
+      *reinterpret_cast<float4*>(a.mdh + so) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     auto ld = [&](const float* q) { return *reinterpret_cast<const float4*>(q + so); };
     const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dcp);
     const float iv[4] = {i4.x, i4.y, i4.z, i4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
     const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
     const float dcv[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
+    if (a.mdc != nullptr) *reinterpret_cast<float4*>(a.mdc + so) = dn ? dcn : make_float4(0.f, 0.f, 0.f, 0.f);
     float ri[4], rf[4], rg[4], ro[4], dco[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -451,6 +463,57 @@ __global__ void __launch_bounds__(RT, 1) lstm_step_bwd_gemm_kernel(const StepBwd
             make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   }
   step_fini(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// gradient of the learned initial carry: column sums of the masked per-step planes, two fixed-order stages
+//   stage 1: block (plane p, step t) sums its 4 units over every row of the step -> part[t][which][4p .. 4p+3]
+//   stage 2: thread j sums part[.][which][j] over the steps
+// ------------------------------------------------------------------------------------------
+struct InitGradArgs {
+  const float* mdc; const float* mdh; long long step_stride;   // [T][tiles][H / 4][PLC]
+  long long st_tile; int tiles, rows, H, T;
+  float* part;                                                // [T][2][H]
+  float* g_c; float* g_h;                                     // [H] each (stage 2)
+};
+
+__global__ void __launch_bounds__(RM) lstm_init_grad_part_kernel(const InitGradArgs a) {
+  __shared__ float4 red[2][RM / 32];
+  const int p = blockIdx.x, t = blockIdx.y, r = threadIdx.x;
+  float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), sh = sc;
+  for (int tile = 0; tile < a.tiles; ++tile) {
+    if (tile * RM + r < a.rows) {
+      const size_t o = static_cast<size_t>(t) * a.step_stride + static_cast<size_t>(tile) * a.st_tile + static_cast<size_t>(p) * PLC + r * 4;
+      const float4 vc = *reinterpret_cast<const float4*>(a.mdc + o), vh = *reinterpret_cast<const float4*>(a.mdh + o);
+      sc.x += vc.x; sc.y += vc.y; sc.z += vc.z; sc.w += vc.w;
+      sh.x += vh.x; sh.y += vh.y; sh.z += vh.z; sh.w += vh.w;
+    }
+  }
+  auto wsum = [](float4 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+      v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+    }
+    return v;
+  };
+  sc = wsum(sc); sh = wsum(sh);
+  if ((r & 31) == 0) { red[0][r >> 5] = sc; red[1][r >> 5] = sh; }
+  __syncthreads();
+  if (r < 2) {
+    float4 v = red[r][0];
+    for (int w = 1; w < RM / 32; ++w) { v.x += red[r][w].x; v.y += red[r][w].y; v.z += red[r][w].z; v.w += red[r][w].w; }
+    *reinterpret_cast<float4*>(a.part + (static_cast<size_t>(t) * 2 + r) * a.H + 4 * p) = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) lstm_init_grad_sum_kernel(const InitGradArgs a) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * a.H) return;
+  const int which = j / a.H, u = j - which * a.H;
+  float v = 0.0f;
+  for (int t = 0; t < a.T; ++t) v += a.part[(static_cast<size_t>(t) * 2 + which) * a.H + u];
+  (which == 0 ? a.g_c : a.g_h)[u] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -638,7 +701,10 @@ __global__ void __launch_bounds__(RT, 1) lstm_seq_fwd_persistent_kernel(const Se
       }
       if (dn) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { c2[k] = 0.0f; h2[k] = 0.0f; }
+        for (int k = 0; k < 8; ++k) {
+          c2[k] = a.init_c != nullptr ? a.init_c[u0 + k] : 0.0f;
+          h2[k] = a.init_h != nullptr ? a.init_h[u0 + k] : 0.0f;
+        }
       }
       stp(a.cp, so, c2);
       {

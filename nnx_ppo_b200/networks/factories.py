@@ -60,7 +60,8 @@ def make_recurrent_actor_critic(obs_size: int, action_size: int, pre_size: int, 
                                 critic_hidden_sizes: list[int], rngs: prng.Rngs,
                                 activation: Union[Callable, str] = feedforward.relu,
                                 normalize_obs: bool = True, entropy_weight: float = 1e-2,
-                                min_std: float = 1e-1, std_scale: float = 1.0) -> StatefulModule:
+                                min_std: float = 1e-1, std_scale: float = 1.0,
+                                trainable_initial_state: bool = False) -> StatefulModule:
     """Actor Dense(act) -> LSTM -> Dense with an MLP critic, the network of the reference's
     recurrent_test.py:245-258 wrapped like make_mlp_actor_critic (Normalizer + PPOAdapter)."""
     from .recurrent import LSTM
@@ -71,7 +72,7 @@ def make_recurrent_actor_critic(obs_size: int, action_size: int, pre_size: int, 
         return prng.variance_scaling_uniform(key, shape[0], shape[1], 1.0)
 
     actor = [feedforward.Dense(obs_size, pre_size, rngs, activation=activation, kernel_init=kernel_init),
-             LSTM(pre_size, lstm_hidden, rngs),
+             LSTM(pre_size, lstm_hidden, rngs, trainable_initial_state=trainable_initial_state),
              feedforward.Dense(lstm_hidden, action_size * 2, rngs, activation=None, kernel_init=kernel_init)]
     critic = make_mlp([obs_size] + list(critic_hidden_sizes) + [1], rngs, activation,
                       activation_last_layer=False, kernel_init=kernel_init)

@@ -459,7 +459,7 @@ def _call_recurrent(net, state: Any, obs, rollout_extras: Any):
         net.normalizer.prepare(s)
     net.sync_counters_to_device()
     mean_p, std_p = net.norm_ptrs()
-    _lib.check(lib.b200ppo_lstm_step_fwd(s, net.lplan, _lib.ptr(net.arena), mean_p, std_p, _lib.ptr(obs), 0, 0, B,
+    _lib.check(lib.b200ppo_lstm_step_fwd(s, net.lplan_step, _lib.ptr(net.arena), mean_p, std_p, _lib.ptr(obs), 0, 0, B,
                                          _lib.ptr(c), _lib.ptr(h), _lib.ptr(y), 0), "lstm_step_fwd")
     _lib.check(lib.b200ppo_sampler_step(s, _lib.ptr(y), B, A, mode, net.plan.min_std, net.plan.std_scale,
                                         net.plan.entropy_weight, _lib.ptr(net.counters), 0, _lib.ptr(raw_in),

@@ -72,6 +72,10 @@ class RecurrentCompiledNet(CompiledNet):
         lp.bl_off = off; off += 4 * H
         lp.w2_off = off; off += H * Y
         lp.b2_off = off; off += Y
+        if lstm.trainable_initial_state:                 # learned reset carry, [H] each, 16-byte aligned
+            off = _align4(off)
+            lp.init_c_off = off; off += H                # carry slot 0 <- `initial_h` (see networks/recurrent.py)
+            lp.init_h_off = off; off += H
         self.n_recurrent = off
         off = _align4(off)
 
@@ -100,11 +104,20 @@ class RecurrentCompiledNet(CompiledNet):
         plan.n_params = off
         lp.n_params = off
         self.plan, self.lplan, self.n_params = plan, lp, off
+        # a single step applies no reset: the per-step kernels get the plan without the learned carry
+        self.lplan_step = _lib.LstmPlan.from_buffer_copy(lp)
+        self.lplan_step.init_c_off = self.lplan_step.init_h_off = 0
 
         host = np.zeros(off, np.float32)
         params = [(lp.w1_off, pre.linear.kernel), (lp.b1_off, pre.linear.bias),
                   (lp.wcat_off, lstm.kernel_i), (lp.wcat_off + P * 4 * H, lstm.kernel_h), (lp.bl_off, lstm.bias),
                   (lp.w2_off, post.linear.kernel), (lp.b2_off, post.linear.bias)]
+        self.init_views = None
+        if lstm.trainable_initial_state:
+            if not _lib.load().b200ppo_lstm_seq_supported(lp):
+                raise NotImplementedError("trainable_initial_state needs the sequence kernels: hidden % 16 == 0 and "
+                                          "pre Dense width % 4 == 0")
+            params[5:5] = [(lp.init_c_off, lstm.initial_h), (lp.init_h_off, lstm.initial_c)]   # oracle order: after bl
         for i, l in enumerate(critic_layers):
             params += [(int(c.w_off[i]), l.linear.kernel), (int(c.b_off[i]), l.linear.bias)]
         self._params = params
@@ -114,6 +127,8 @@ class RecurrentCompiledNet(CompiledNet):
         self.arena = torch.from_numpy(host).to(device)
         for o, p in params:
             p._dev = self.arena[o:o + int(np.prod(p.shape))].view(*p.shape)
+        if lstm.trainable_initial_state:
+            self.init_views = (lstm.initial_h._dev, lstm.initial_c._dev)
         if normalizer is not None:
             normalizer._bind(device)
         rng = self.sampler.rng
@@ -127,6 +142,16 @@ class RecurrentCompiledNet(CompiledNet):
                                               for o, p in params])
         self.param_mask = None
         self.obs_keys = self.obs_sizes = None
+
+    def reset_carry(self, carry, done):
+        """rollout.py:33-40: envs that finished get ``reset_state`` - zeros, or the learned initial carry."""
+        import torch
+        c, h = carry
+        d = done.bool()[:, None]
+        if self.init_views is None:
+            keep = (~d).to(torch.float32)
+            return (c * keep, h * keep)
+        return (torch.where(d, self.init_views[0], c), torch.where(d, self.init_views[1], h))
 
     # ---- carry inside the reference-shaped network_states pytree ----
     def get_carry(self, network_states):

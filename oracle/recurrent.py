@@ -5,8 +5,10 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Status: parity unpinned — 
 imported here (no jax / flax), so this follows the reference source and flax's published LSTM cell:
 
 * ``nnx_ppo/networks/recurrent.py:89-161``: the carry tuple goes straight to the flax cell, the
-  layer output is the new hidden state, ``reset_state`` returns zeros (``trainable_initial_state``
-  is not restated), regularisation loss is zero.
+  layer output is the new hidden state, ``reset_state`` returns zeros - or, with
+  ``trainable_initial_state`` (:85-87, 135-141, 154-157), the learned ``initial_h`` / ``initial_c``
+  broadcast into carry slot 0 / slot 1 (slot 0 is what the flax cell reads as c); regularisation
+  loss is zero.
 * flax ``nnx.OptimizedLSTMCell`` (flax/nnx/nn/recurrent.py): four input kernels without bias and
   four hidden kernels with bias, gate order (i, f, g, o):
       i = sigmoid(x Wii + h Whi + bi)   f = sigmoid(x Wif + h Whf + bf)
@@ -74,6 +76,9 @@ class RecurrentActorCritic:
     mean: Optional[np.ndarray] = None
     M2: Optional[np.ndarray] = None
     counter: F = F(0.0)
+    # trainable_initial_state: learned carry (slot 0 = c, slot 1 = h of this restatement), [H] each
+    init_c: Optional[np.ndarray] = None
+    init_h: Optional[np.ndarray] = None
 
     norm_std = ActorCritic.norm_std
     normalize_obs = ActorCritic.normalize_obs
@@ -82,7 +87,16 @@ class RecurrentActorCritic:
 
     def initialize_state(self, B: int):
         H = self.lstm.hidden
+        if self.init_c is not None:
+            return np.broadcast_to(self.init_c, (B, H)).astype(F).copy(), np.broadcast_to(self.init_h, (B, H)).astype(F).copy()
         return np.zeros((B, H), F), np.zeros((B, H), F)          # (c, h)
+
+    def reset_carry(self, carry, done):
+        """rollout.py:33-40 / ppo.py:419-425: finished envs get ``reset_state``."""
+        d = done[:, None]
+        r0 = F(0) if self.init_c is None else self.init_c[None, :]
+        r1 = F(0) if self.init_h is None else self.init_h[None, :]
+        return np.where(d, r0, carry[0]).astype(F), np.where(d, r1, carry[1]).astype(F)
 
     def param_list(self):
         out = []
@@ -90,6 +104,8 @@ class RecurrentActorCritic:
             for W, b in zip(ch.W, ch.b):
                 out += [W, b]
         out += [self.lstm.Wi, self.lstm.Wh, self.lstm.b]
+        if self.init_c is not None:
+            out += [self.init_c, self.init_h]
         for ch in (self.post, self.critic):
             for W, b in zip(ch.W, ch.b):
                 out += [W, b]
@@ -107,7 +123,8 @@ class RecurrentActorCritic:
 
 
 def make_recurrent_actor_critic(obs_size, action_size, pre_sizes, lstm_hidden, post_sizes, critic_hidden_sizes,
-                                seed=0, activation="relu", normalize_obs=True) -> RecurrentActorCritic:
+                                seed=0, activation="relu", normalize_obs=True,
+                                trainable_initial_state=False) -> RecurrentActorCritic:
     """Key-draw order: pre Dense layers, LSTM (Wi, Wh), post Dense layers, critic layers, then the
     sampler's stream key — every Linear consumes two counts of the Rngs stream like the MLP factory."""
     rngs = prng.Rngs(seed)
@@ -135,6 +152,8 @@ def make_recurrent_actor_critic(obs_size, action_size, pre_sizes, lstm_hidden, p
     net.normalize = normalize_obs
     if normalize_obs:
         net.mean, net.M2 = np.zeros(obs_size, F), np.zeros(obs_size, F)
+    if trainable_initial_state:                                   # recurrent.py:85-87: zeros, no key drawn
+        net.init_c, net.init_h = np.zeros(H, F), np.zeros(H, F)
     return net
 
 
@@ -198,7 +217,7 @@ def unroll_env(env, env_state, net: RecurrentActorCritic, carry, T: int, reset_k
             ro.next_obs_last[:] = nxt.obs
         rs = env.reset_fast(keys[t])
         d = nxt.done
-        carry = (np.where(d[:, None], F(0), carry[0]).astype(F), np.where(d[:, None], F(0), carry[1]).astype(F))
+        carry = net.reset_carry(carry, d)
         s = EnvState(np.where(d[:, None], rs.obs, nxt.obs),
                      np.where(d, rs.step_counter, nxt.step_counter).astype(np.int32),
                      np.where(d, rs.term_state, nxt.term_state).astype(np.uint32),
@@ -225,8 +244,11 @@ def ppo_loss_and_grads(net: RecurrentActorCritic, ro: Rollout, start_carry, inds
         c, h, y, cache = actor_step(net, c, h, xs[t])
         ys.append(y)
         caches.append(cache)
-        keep = (~done[t])[:, None]
-        c, h = (c * keep).astype(F), (h * keep).astype(F)                      # reset_state -> zeros
+        if net.init_c is None:
+            keep = (~done[t])[:, None]
+            c, h = (c * keep).astype(F), (h * keep).astype(F)                  # reset_state -> zeros
+        else:
+            c, h = net.reset_carry((c, h), done[t])                            # ... or the learned carry
     y = np.concatenate(ys, axis=0)
     xf = xs.reshape(N, -1)
     v, zs_c = net.critic.forward(xf, keep=True)
@@ -245,6 +267,7 @@ def ppo_loss_and_grads(net: RecurrentActorCritic, ro: Rollout, start_carry, inds
     gWi, gWh, gb = np.zeros_like(net.lstm.Wi), np.zeros_like(net.lstm.Wh), np.zeros_like(net.lstm.b)
     dc_next = np.zeros((mb, H), F)
     dh_next = np.zeros((mb, H), F)
+    g_init_c, g_init_h = np.zeros(H, F), np.zeros(H, F)
     for t in reversed(range(T)):
         u, zs_pre, (i, f, g, o, tc), zs_post = caches[t]
         h_t = (o * tc).astype(F)
@@ -259,6 +282,9 @@ def ppo_loss_and_grads(net: RecurrentActorCritic, ro: Rollout, start_carry, inds
             if l > 0:
                 d = (d * act_grad(zs_post[l - 1], net.post.act)).astype(F)
         keep = (~done[t])[:, None]
+        if net.init_c is not None:                   # where done[t], step t+1 started from the learned carry
+            g_init_c += (dc_next * ~keep).sum(axis=0, dtype=F)
+            g_init_h += (dh_next * ~keep).sum(axis=0, dtype=F)
         dh = (d + dh_next * keep).astype(F)          # the carry handed to step t+1 was zeroed where done[t]
         dc = (dh * o * (F(1) - tc * tc) + dc_next * keep).astype(F)
         da = np.concatenate([dc * g * i * (F(1) - i), dc * c_in[t] * f * (F(1) - f), dc * i * (F(1) - g * g),
@@ -281,6 +307,8 @@ def ppo_loss_and_grads(net: RecurrentActorCritic, ro: Rollout, start_carry, inds
     for W, b in zip(g_pre_W, g_pre_b):
         parts += [W.ravel(), b.ravel()]
     parts += [gWi.ravel(), gWh.ravel(), gb.ravel()]
+    if net.init_c is not None:
+        parts += [g_init_c, g_init_h]
     for W, b in zip(g_post_W, g_post_b):
         parts += [W.ravel(), b.ravel()]
     for W, b in zip(dWc, dbc):

@@ -19,6 +19,11 @@ pytestmark = pytest.mark.gpu
 F = np.float32
 
 
+def torch_equal_rows(mat, vec):
+    import torch
+    return bool(torch.equal(mat, vec.to(mat.device)[None, :].expand_as(mat)))
+
+
 def _plan(net):
     """flat layout = RecurrentActorCritic.param_list(): W1, b1, Wi, Wh, bl, W2, b2, critic..."""
     p = _lib.LstmPlan()
@@ -30,6 +35,10 @@ def _plan(net):
     p.b1_off = o; o += P
     p.wcat_off = o; o += (P + H) * 4 * H
     p.bl_off = o; o += 4 * H
+    if net.init_c is not None:                 # trainable_initial_state: after the LSTM bias in param_list()
+        assert o % 4 == 0
+        p.init_c_off = o; o += H
+        p.init_h_off = o; o += H
     p.w2_off = o; o += H * Y
     p.b2_off = o; o += Y
     p.n_params = net.flat_params().size
@@ -129,7 +138,8 @@ def test_recurrent_replay_and_bptt_match_oracle(cuda_device, cfg):
     assert np.all(outs[0][n_rec:] == 7.0)
 
 
-def test_recurrent_ppo_step_matches_oracle(cuda_device):
+@pytest.mark.parametrize("trainable", [False, True])
+def test_recurrent_ppo_step_matches_oracle(cuda_device, trainable):
     """Public API (`ppo.ppo_step`) with an LSTM actor against oracle/recurrent.py over iterations:
     bit-exact masks / minibatch indices / counters, float32-tolerance losses and parameters
     (reference: recurrent_test.py:285-330 only checks finiteness and that parameters change)."""
@@ -139,8 +149,14 @@ def test_recurrent_ppo_step_matches_oracle(cuda_device):
     from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
     from nnx_ppo_b200.networks.plan import compile_network
     O, A, B, T, E, M, P, H = 16, 4, 64, 12, 2, 2, 32, 32
-    nets = make_recurrent_actor_critic(O, A, P, H, [48], Rngs(1))
-    onet = orec.make_recurrent_actor_critic(O, A, [P], H, [], [48], seed=1)
+    nets = make_recurrent_actor_critic(O, A, P, H, [48], Rngs(1), trainable_initial_state=trainable)
+    onet = orec.make_recurrent_actor_critic(O, A, [P], H, [], [48], seed=1, trainable_initial_state=trainable)
+    if trainable:       # trainable_initial_state (recurrent.py:85-87): start from a non-zero learned carry on both sides
+        gi = np.random.default_rng(8)
+        v0, v1 = (0.3 * gi.standard_normal(H)).astype(F), (0.3 * gi.standard_normal(H)).astype(F)
+        lstm = nets.layers[1].action.layers[1]
+        lstm.initial_h.set(v0); lstm.initial_c.set(v1)
+        onet.init_c[:], onet.init_h[:] = v0, v1
     env = SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
     oe = oenv.SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
     ts = ppo.new_training_state(env, nets, B, 17)
@@ -171,6 +187,14 @@ def test_recurrent_ppo_step_matches_oracle(cuda_device):
         assert np.allclose(c.cpu().numpy(), ots.carry[0], atol=2e-4) and np.allclose(h.cpu().numpy(), ots.carry[1], atol=2e-4)
         assert np.allclose(net.normalizer.mean.numpy(), onet.mean, rtol=1e-4, atol=1e-4)
     assert eng.r_seq and eng.r_graph is not None and eng.kernel_launches_per_iter > 0    # tensor-core sequence kernels, one graph
+    if trainable:
+        lstm = nets.layers[1].action.layers[1]
+        assert np.abs(lstm.initial_h.numpy() - v0).max() > 1e-5 and np.abs(lstm.initial_c.numpy() - v1).max() > 1e-5   # learned
+        assert np.allclose(lstm.initial_h.numpy(), onet.init_c, atol=4e-4) and np.allclose(lstm.initial_c.numpy(), onet.init_h, atol=4e-4)
+        # initialize_state / reset_state hand out the learned vectors broadcast over the batch (recurrent_test.py:113-150)
+        st = nets.initialize_state(5)
+        c0, h0 = net.get_carry(st)
+        assert c0.shape == (5, H) and torch_equal_rows(c0, lstm.initial_h.value) and torch_equal_rows(h0, lstm.initial_c.value)
 
 
 def test_recurrent_ffma_fallback_matches_tensor_core_path(cuda_device, monkeypatch):

@@ -71,7 +71,10 @@ def test_weight_gradient_tile_gemm_matches_float64(cuda_device, lib, rows, Kdim,
 @pytest.mark.parametrize("cfg", [dict(O=64, A=8, B=40, T=16, P=64, H=256, act="relu", mb=list(range(0, 40, 2))),
                                  dict(O=16, A=4, B=37, T=20, P=32, H=32, act="relu", mb=list(range(37))),
                                  dict(O=10, A=3, B=300, T=9, P=12, H=16, act="tanh", mb=list(range(299, 10, -2))),
-                                 dict(O=64, A=8, B=600, T=32, P=64, H=256, act="swish", mb=list(range(0, 600)))])
+                                 dict(O=64, A=8, B=600, T=32, P=64, H=256, act="swish", mb=list(range(0, 600))),
+                                 # trainable_initial_state: resets hand out the learned carry, which gets a gradient
+                                 dict(O=16, A=4, B=300, T=20, P=32, H=32, act="tanh", mb=list(range(0, 300, 2)), init=True),
+                                 dict(O=64, A=8, B=140, T=12, P=64, H=128, act="relu", mb=list(range(139, -1, -1)), init=True)])
 @pytest.mark.parametrize("persist", [1, 0])
 def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
     """persist = 1: the forward recurrence as one persistent launch (weights resident in shared memory, the carry
@@ -80,7 +83,12 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
     lib.b200ppo_lstm_set_persistent(persist)
     dev = cuda_device
     O, A, B, T, H, P = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["H"], cfg["P"]
-    net = orec.make_recurrent_actor_critic(O, A, [P], H, [], [6], seed=3, activation=cfg["act"])
+    init = cfg.get("init", False)
+    net = orec.make_recurrent_actor_critic(O, A, [P], H, [], [6], seed=3, activation=cfg["act"], trainable_initial_state=init)
+    if init:                        # (the reference starts the learned carry at zero)
+        gi = np.random.default_rng(4)
+        net.init_c[:] = 0.5 * gi.standard_normal(H)
+        net.init_h[:] = 0.5 * gi.standard_normal(H)
     e = oenv.SyntheticEnv(O, A, max_len=6, term_thresh16=9000)
     es = e.reset(prng.split(prng.key(5), B))
     es, carry, ro, start = orec.unroll_env(e, es, net, net.initialize_state(B), T, prng.key(11))
@@ -105,9 +113,10 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
     for k in range(T):
         cc, hh, yk, _ = orec.actor_step(net, cc, hh, xs.reshape(T, mb, -1)[k])
         ys.append(yk)
-        keep = (~ro.done[k, inds])[:, None]
-        cc, hh = cc * keep, hh * keep
+        cc, hh = net.reset_carry((cc, hh), ro.done[k, inds])
     y_ref = np.stack(ys)
+    r_c = net.init_c if init else np.zeros(H, F)
+    r_h = net.init_h if init else np.zeros(H, F)
     for raw in (False, True):      # replay form (normalised inputs) and rollout form (raw observations, normalised on load)
         c, h = t(start[0][inds]), t(start[1][inds])
         y = torch.zeros(T, mb, Y, device=dev)
@@ -120,7 +129,7 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
         assert np.abs(y.cpu().numpy() - y_ref).max() < 3e-5 * max(1.0, np.abs(y_ref).max())
         assert np.abs(c.cpu().numpy() - cc).max() < 3e-5 and np.abs(h.cpu().numpy() - hh).max() < 3e-5
         d_last = ro.done[-1, inds]
-        assert np.all(c.cpu().numpy()[d_last] == 0) and np.all(h.cpu().numpy()[d_last] == 0)     # reset: exact zeros
+        assert np.all(c.cpu().numpy()[d_last] == r_c) and np.all(h.cpu().numpy()[d_last] == r_h)     # reset: exact values
     # BPTT with the oracle's d loss / d y (the forward with keep_cache = 1 ran first in the loop above? no: last was raw)
     c, h = t(start[0][inds]), t(start[1][inds])
     _lib.check(lib.b200ppo_lstm_seq_forward(s, plan, params.data_ptr(), 0, 0, x.data_ptr(), done.data_ptr(), ind_d.data_ptr(),
@@ -139,5 +148,9 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
     assert np.array_equal(outs[0], outs[1])                      # fixed-order sums: bit-reproducible
     assert np.all(outs[0][n_rec:] == 7.0)                        # the critic's slots are not touched
     assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 0) == (1 if persist else T) + 8
-    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 1) == 2 * T + 10
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 1) == 2 * T + 10 + (2 if init else 0)
+    if init:                                                     # the learned carry's gradient is not negligible here
+        o = plan.init_c_off
+        assert np.abs(ref[o:o + 2 * H]).max() > 1e-3 * scale
+        assert np.abs(outs[0][o:o + 2 * H] - ref[o:o + 2 * H]).max() < 3e-4 * np.abs(ref[o:o + 2 * H]).max()
     lib.b200ppo_lstm_set_persistent(0)

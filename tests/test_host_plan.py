@@ -200,3 +200,31 @@ def test_arena_layout_recurrent_plan_matches_oracle_order():
     net = RecurrentCompiledNet(nets, torch.device("cpu"))
     assert net.recurrent and net.obs_adapters == []
     assert np.array_equal(net.params_logical(), onet.flat_params())
+
+
+def test_recurrent_plan_with_trainable_initial_state():
+    """recurrent.py:85-87: two [H] Params, zeros; carry slot 0 <- initial_h, slot 1 <- initial_c; the arena
+    holds them after the LSTM bias in the oracle's order; initialize_state / reset_state broadcast them."""
+    from nnx_ppo_b200.networks.rplan import RecurrentCompiledNet
+    from oracle import recurrent as orec
+    nets = factories.make_recurrent_actor_critic(16, 4, 32, 32, [48], prng.Rngs(1), trainable_initial_state=True)
+    onet = orec.make_recurrent_actor_critic(16, 4, [32], 32, [], [48], seed=1, trainable_initial_state=True)
+    lstm = nets.layers[1].action.layers[1]
+    assert lstm.trainable_initial_state and lstm.initial_h.shape == (32,) and not lstm.initial_h.numpy().any()
+    lstm.initial_h.set(np.arange(32, dtype=np.float32))
+    lstm.initial_c.set(-np.arange(32, dtype=np.float32))
+    onet.init_c[:], onet.init_h[:] = np.arange(32), -np.arange(32)
+    net = RecurrentCompiledNet(nets, torch.device("cpu"))
+    lp = net.lplan
+    assert lp.init_c_off > 0 and lp.init_c_off % 4 == 0 and lp.init_h_off == lp.init_c_off + 32
+    assert net.lplan_step.init_c_off == 0 and net.lplan_step.w2_off == lp.w2_off
+    assert np.array_equal(net.params_logical(), onet.flat_params())
+    st = nets.initialize_state(3)
+    c, h = net.get_carry(st)
+    assert torch.equal(c, torch.arange(32.0).expand(3, 32)) and torch.equal(h, -torch.arange(32.0).expand(3, 32))
+    rc, rh = net.reset_carry((torch.ones(3, 32), torch.ones(3, 32)), torch.tensor([True, False, True]))
+    assert torch.equal(rc[0], torch.arange(32.0)) and torch.equal(rc[1], torch.ones(32)) and torch.equal(rh[2], -torch.arange(32.0))
+    # the per-step FFMA kernels do not implement it: a plan that needs them is rejected up front
+    bad = factories.make_recurrent_actor_critic(16, 4, 30, 24, [48], prng.Rngs(1), trainable_initial_state=True)
+    with pytest.raises(NotImplementedError):
+        RecurrentCompiledNet(bad, torch.device("cpu"))

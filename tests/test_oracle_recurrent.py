@@ -14,8 +14,13 @@ from oracle.nets import loglikelihood, sampler_std
 F = np.float32
 
 
-def _setup(seed=3, O=10, A=3, B=12, T=9, H=8):
-    net = orec.make_recurrent_actor_critic(O, A, [7], H, [], [6], seed=seed, activation="tanh")
+def _setup(seed=3, O=10, A=3, B=12, T=9, H=8, trainable=False):
+    net = orec.make_recurrent_actor_critic(O, A, [7], H, [], [6], seed=seed, activation="tanh",
+                                           trainable_initial_state=trainable)
+    if trainable:                   # the reference starts them at zero; non-zero values make the checks meaningful
+        g = np.random.default_rng(9)
+        net.init_c[:] = 0.5 * g.standard_normal(H)
+        net.init_h[:] = 0.5 * g.standard_normal(H)
     e = oenv.SyntheticEnv(O, A, max_len=6, term_thresh16=9000)      # frequent resets inside T steps
     k = prng.key(5)
     es = e.reset(prng.split(k, B))
@@ -66,8 +71,10 @@ def _torch_loss(net, ro, start, inds, base, flat64):
     npre, npost = net.pre.n_layers, net.post.n_layers
     pre = ps[:2 * npre]
     Wi, Wh, b = ps[2 * npre:2 * npre + 3]
-    post = ps[2 * npre + 3:2 * npre + 3 + 2 * npost]
-    crit = ps[2 * npre + 3 + 2 * npost:]
+    ni = 2 if net.init_c is not None else 0
+    init = ps[2 * npre + 3:2 * npre + 3 + ni]
+    post = ps[2 * npre + 3 + ni:2 * npre + 3 + ni + 2 * npost]
+    crit = ps[2 * npre + 3 + ni + 2 * npost:]
     act = torch.tanh
     H = net.lstm.hidden
     x_all = t64(net.normalize_obs(ro.obs[:, inds].reshape(T * mb, -1))).reshape(T, mb, -1)
@@ -89,7 +96,10 @@ def _torch_loss(net, ro, start, inds, base, flat64):
                 y = act(y)
         ys.append(y)
         keep = (~done[t]).double()[:, None]
-        c, h = c * keep, h * keep
+        if ni:
+            c, h = c * keep + (1 - keep) * init[0][None, :], h * keep + (1 - keep) * init[1][None, :]
+        else:
+            c, h = c * keep, h * keep
     y = torch.cat(ys, 0)
 
     def critic(x):
@@ -131,6 +141,35 @@ def _torch_loss(net, ro, start, inds, base, flat64):
     crit_l = 0.5 * ((v - target) ** 2).mean()
     reg = (-net.entropy_weight * ent).mean()
     return actor + crit_l + reg
+
+
+def test_trainable_initial_state_resets_and_gradient():
+    """recurrent.py:85-87, 135-141, 154-157 (recurrent_test.py:95-150: the state is the learned vector broadcast
+    over the batch, at initialisation and after a reset) and the gradient those parameters get through the
+    resets inside the replayed window, against float64 autograd."""
+    net, e, es, carry, ro, start = _setup(trainable=True)
+    assert np.all(start[0] == net.init_c[None, :]) and np.all(start[1] == net.init_h[None, :])
+    d_last = ro.done[-1]
+    assert d_last.any() and np.all(carry[0][d_last] == net.init_c) and np.all(carry[1][d_last] == net.init_h)
+    inds = np.array([0, 3, 4, 7, 9, 11])
+    assert ro.done[:-1, inds].any()
+    base = net.rng_count
+    total, m, g = orec.ppo_loss_and_grads(net, ro, start, inds, base)
+    flat = torch.tensor(net.flat_params().astype(np.float64), requires_grad=True)
+    loss = _torch_loss(net, ro, start, inds, base, flat)
+    loss.backward()
+    gt = flat.grad.numpy()
+    assert abs(float(loss) - float(total)) < 2e-5 * max(1.0, abs(float(loss)))
+    scale = np.abs(gt).max()
+    assert np.abs(g - gt).max() < 2e-4 * scale, (np.abs(g - gt).max(), scale)
+    H = net.lstm.hidden
+    o = sum(p.size for p in net.param_list()[:2 * net.pre.n_layers + 3])
+    assert np.abs(gt[o:o + 2 * H]).max() > 1e-3 * scale               # the learned carry does get gradient
+    # the start carry is data (types.py:50-56 network_states), not a function of the parameters
+    net2, *_ = _setup(trainable=True)
+    ro.done[:] = False
+    _t, _m, g3 = orec.ppo_loss_and_grads(net, ro, start, inds, base)
+    assert np.all(g3[o:o + 2 * H] == 0)
 
 
 def test_bptt_gradient_matches_autograd():

@@ -608,7 +608,8 @@ struct SeqLayout {
   size_t cp, dcp;                         // state planes [tiles][H / 4][PLC]
   size_t cache[6];                        // gi gf gg go tc cin: [T][tiles][H / 4][PLC]
   size_t dap;                             // A planes of da: [2 halves][tiles][4 gates][H / 4][PLA]
-  size_t dhr;                             // split-K partials [4][tiles][H / 4][PLC]
+  size_t dhr;                             // split-K partials [4 * KS][tiles][H / 4][PLC]
+  int KS;                                 // k parts per gate block in the backward split-K GEMM
   size_t whf, whb;                        // weight planes
   size_t flags;                           // int32 [tiles][T + 1] arrival counters of the persistent forward kernel
   size_t mdc, mdh, ipart;                 // learned initial carry: masked per-step gradient planes, per-step sums
@@ -659,7 +660,9 @@ SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   for (int i = 0; i < 6; ++i) L.cache[i] = take(static_cast<size_t>(T) * L.cache_step);
   L.dap_half = tiles * 4 * planes * PLA;
   L.dap = take(2 * L.dap_half);
-  L.dhr = take(4 * tiles * L.st_tile);
+  // a minibatch of few row tiles leaves SMs idle: cut each gate block's K in two as well (needs 32-k slabs)
+  L.KS = (H % 64 == 0 && tiles * L.nbt * 8 <= 2 * 148) ? 2 : 1;
+  L.dhr = take(4 * L.KS * tiles * L.st_tile);
   L.whf = take((H / UT) * 2 * planes * plb(4 * UT));
   L.whb = take(static_cast<size_t>(L.nbt) * 4 * 2 * planes * plb(L.NBT));
   L.flags = take(tiles * (static_cast<size_t>(T) + 1));
@@ -699,6 +702,16 @@ bool seq_persistent(const b200ppo_lstm_plan& p, int T, int rows) {
   return g_seq_persist != 0 && T > 1 && cdiv(rows, RM) * (p.hidden / UT) <= b200ppo_num_sms();
 }
 
+// B200PPO_LSTM_PAIR=0 disables the cluster-pair forward step (A/B measurements)
+bool seq_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = std::getenv("B200PPO_LSTM_PAIR");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode != 0;
+}
+
 int check_plan_tc(const b200ppo_lstm_plan* p) {
   if (!p || p->obs_dim <= 0 || p->pre_dim <= 0 || p->hidden <= 0 || p->out_dim <= 0 || p->n_params <= 0) return B200PPO_EINVAL;
   if (p->act < 0 || p->act > 3) return B200PPO_EINVAL;
@@ -734,6 +747,9 @@ int set_attrs_tc() {
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(lstm_step_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(SP_NS * sp_slot_bytes(4 * UT)));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(lstm_step_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(FWD3_XB_BYTES + SP_NS * sp_slot_bytes(4 * UT)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(lstm_seq_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PERSIST_SMEM_MAX);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -926,9 +942,14 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     lstm_seq_fwd_persistent_kernel<<<dim3(L.tiles, H / UT), RT, p_smem, s>>>(pa);
     B200PPO_LAUNCH_CHECK();
   } else {
+    // few CTAs (small minibatch): a cluster pair per tile, each CTA half of K (see lstm_step_fwd3_kernel)
+    const bool pair = seq_pair_mode() && H % 32 == 0 && 2 * L.tiles * (H / UT) <= b200ppo_num_sms();
     for (int t = 0; t < T; ++t) {
       const StepFwd2Args a = step_args(t);
-      lstm_step_fwd2_kernel<<<dim3(L.tiles, H / UT), RT, SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
+      if (pair)
+        lstm_step_fwd3_kernel<<<dim3(L.tiles, H / UT, 2), RT, FWD3_XB_BYTES + SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
+      else
+        lstm_step_fwd2_kernel<<<dim3(L.tiles, H / UT), RT, SP_NS * sp_slot_bytes(4 * UT), s>>>(a);
       B200PPO_LAUNCH_CHECK();
     }
   }
@@ -983,7 +1004,7 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
     const size_t so = static_cast<size_t>(t) * L.cache_step;
     StepBwd2Args e;
     e.dhp = ws + L.dhpp; e.r0 = static_cast<long long>(t) * rows; e.dhp_cols4 = planes;
-    e.dhr = t == T - 1 ? nullptr : ws + L.dhr; e.dhr_slice = dhr_slice; e.n_slices = 4;
+    e.dhr = t == T - 1 ? nullptr : ws + L.dhr; e.dhr_slice = dhr_slice; e.n_slices = 4 * L.KS;
     e.dcp = ws + L.dcp;
     e.gi = ws + L.cache[0] + so; e.gf = ws + L.cache[1] + so; e.gg = ws + L.cache[2] + so;
     e.go = ws + L.cache[3] + so; e.tcc = ws + L.cache[4] + so; e.cin = ws + L.cache[5] + so;
@@ -1003,8 +1024,8 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
       g.dap_hi = e.dap_hi; g.dap_lo = e.dap_lo; g.dap_tile = dap_tile; g.dap_slice = dap_slice;
       g.whb = ws + L.whb; g.whb_slice = 2LL * planes * plb(L.NBT); g.whb_tile = 4 * g.whb_slice;
       g.dhr = ws + L.dhr; g.dhr_slice = dhr_slice; g.st_tile = static_cast<long long>(L.st_tile);
-      g.rows = rows; g.H = H; g.NBT = L.NBT;
-      lstm_step_bwd_gemm_kernel<<<dim3(L.tiles, L.nbt, 4), RT, SP_NS * sp_slot_bytes(L.NBT), s>>>(g);
+      g.rows = rows; g.H = H; g.NBT = L.NBT; g.KS = L.KS;
+      lstm_step_bwd_gemm_kernel<<<dim3(L.tiles, L.nbt, 4 * L.KS), RT, SP_NS * sp_slot_bytes(L.NBT), s>>>(g);
       B200PPO_LAUNCH_CHECK();
     }
   }

@@ -338,10 +338,142 @@ __global__ void __launch_bounds__(RT, 1) lstm_step_fwd2_kernel(const StepFwd2Arg
 }
 
 // ------------------------------------------------------------------------------------------
+// forward step for SMALL grids (a 512-row minibatch is 4 row tiles x 16 unit tiles = 64 CTAs on 148 SMs, and a
+// step is a latency chain: stream 300 KB of operands at ~64 B/clk, 96 dependent MMAs, the gate epilogue).  A
+// cluster of two CTAs shares one (row tile, unit tile): each streams and multiplies one HALF of K, the partial
+// accumulators are exchanged through distributed shared memory, and each CTA runs the gate math for 8 of the
+// 16 units - 4 units per thread instead of 8.  Sum order: k-low half + k-high half (fixed: deterministic).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_map(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+constexpr uint32_t FWD3_XB_BYTES = 2u * 2u * 4u * RM * 16u;      // [source CTA][unit quad][gate][row] float4
+
+__global__ void __cluster_dims__(1, 1, 2) __launch_bounds__(RT, 1) lstm_step_fwd3_kernel(const StepFwd2Args a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ StepBars bars;
+  __shared__ uint32_t tmem_slot;
+  uint32_t tmem_cols;
+  const uint32_t tmem_base = step_init(&bars, &tmem_slot, 4 * UT, tmem_cols);
+  cluster_arrive();                                   // "my shared memory exists"; waited for before the exchange
+  const int tile = blockIdx.x, ut = blockIdx.y;
+  const uint32_t z = cluster_ctarank();               // which half of K, and which 8 units this CTA finalises
+  const int H = a.H, planes = H >> 2, pp = planes >> 1;
+  uint8_t* ring = smem + FWD3_XB_BYTES;
+  BulkOperands g;
+  g.a_hi = a.hp_hi + static_cast<size_t>(tile) * a.hp_tile + static_cast<size_t>(z) * pp * PLA;
+  g.a_lo = a.hp_lo + static_cast<size_t>(tile) * a.hp_tile + static_cast<size_t>(z) * pp * PLA;
+  g.b_hi = a.whf + static_cast<size_t>(ut) * a.whf_tile + static_cast<size_t>(z) * pp * plb(4 * UT);
+  g.b_lo = g.b_hi + static_cast<size_t>(planes) * plb(4 * UT);
+  g.K = H >> 1; g.N = 4 * UT;
+  bulk_pipeline(g, ring, &bars, tmem_base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = warp & 3, ub = warp >> 2;
+  const int r = sub * 32 + lane;
+  const int row = tile * RM + r;
+  const int u0 = ut * UT + 8 * static_cast<int>(z) + 4 * ub;      // this thread finalises units u0 .. u0 + 3 of its row
+  const int pl0 = u0 >> 2;
+  const bool ok = row < a.rows;
+  float4 gxv[4], cv = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool dn = false;
+  const size_t so = static_cast<size_t>(tile) * a.cp_tile + static_cast<size_t>(pl0) * PLC + r * 4;
+  if (ok) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      gxv[q] = *reinterpret_cast<const float4*>(a.gxp + plane_off(a.r0 + row, q * planes + pl0, a.gx_cols4));
+    cv = *reinterpret_cast<const float4*>(a.cp + so);
+    if (a.done != nullptr) dn = a.done[a.inds ? a.inds[row] : row] != 0;
+  }
+  tc::mbar_wait(&bars.done, 0u);
+  tc::tc_fence_after();
+  float acc[4][8];                                    // partial sums: gate q, local units 8 ub .. 8 ub + 7
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    tmem_ld8(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(q * UT + 8 * ub), acc[q]);
+  // exchange: units 8 ub .. belong to CTA `ub` of the pair; there, quad h (units 8 ub + 4 h ..) goes to the thread
+  // with the same row in warp group h
+  cluster_wait();
+  {
+    const uint32_t xb = tc::smem_u32(smem);
+    const uint32_t dst_cta = static_cast<uint32_t>(ub);
+    const uint32_t base = dst_cta == z ? xb : cluster_map(xb, dst_cta);
+#pragma unroll
+    for (int hq = 0; hq < 2; ++hq)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t off = (((z * 2u + hq) * 4u + q) * RM + r) * 16u;
+        const float4 v = make_float4(acc[q][4 * hq], acc[q][4 * hq + 1], acc[q][4 * hq + 2], acc[q][4 * hq + 3]);
+        if (dst_cta == z) *reinterpret_cast<float4*>(smem + off) = v;
+        else st_cluster_f4(base + off, v);
+      }
+  }
+  cluster_arrive();
+  cluster_wait();
+  if (ok) {
+    float pre[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 p0 = *reinterpret_cast<const float4*>(smem + (((0u * 2u + ub) * 4u + q) * RM + r) * 16u);
+      const float4 p1 = *reinterpret_cast<const float4*>(smem + (((1u * 2u + ub) * 4u + q) * RM + r) * 16u);
+      pre[q][0] = __fadd_rn(__fadd_rn(p0.x, p1.x), gxv[q].x); pre[q][1] = __fadd_rn(__fadd_rn(p0.y, p1.y), gxv[q].y);
+      pre[q][2] = __fadd_rn(__fadd_rn(p0.z, p1.z), gxv[q].z); pre[q][3] = __fadd_rn(__fadd_rn(p0.w, p1.w), gxv[q].w);
+    }
+    const float c0[4] = {cv.x, cv.y, cv.z, cv.w};
+    float c2[4], h2[4], iv[4], fv[4], gv[4], ov[4], tv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      iv[k] = sigmoid_f(pre[0][k]);
+      fv[k] = sigmoid_f(pre[1][k]);
+      gv[k] = tanhf(pre[2][k]);
+      ov[k] = sigmoid_f(pre[3][k]);
+      c2[k] = __fadd_rn(__fmul_rn(fv[k], c0[k]), __fmul_rn(iv[k], gv[k]));
+      tv[k] = tanhf(c2[k]);
+      h2[k] = __fmul_rn(ov[k], tv[k]);
+    }
+    auto f4 = [](const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); };
+    if (a.gi != nullptr) {
+      *reinterpret_cast<float4*>(a.gi + so) = f4(iv); *reinterpret_cast<float4*>(a.gf + so) = f4(fv);
+      *reinterpret_cast<float4*>(a.gg + so) = f4(gv); *reinterpret_cast<float4*>(a.go + so) = f4(ov);
+      *reinterpret_cast<float4*>(a.tcc + so) = f4(tv); *reinterpret_cast<float4*>(a.cin + so) = cv;
+    }
+    if (a.hn_rm != nullptr) *reinterpret_cast<float4*>(a.hn_rm + static_cast<size_t>(row) * H + u0) = f4(h2);
+    if (dn) {                       // reset_state: zeros, or the learned initial carry
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        c2[k] = a.init_c != nullptr ? a.init_c[u0 + k] : 0.0f;
+        h2[k] = a.init_h != nullptr ? a.init_h[u0 + k] : 0.0f;
+      }
+    }
+    *reinterpret_cast<float4*>(a.cp + so) = f4(c2);
+    *reinterpret_cast<float4*>(a.h_next_rm + static_cast<size_t>(row) * a.ld_hn + u0) = f4(h2);
+    const size_t ho = static_cast<size_t>(tile) * a.hp_tile + static_cast<size_t>(pl0) * PLA + r * 4;
+    float4 hi, lo;
+    tc::split4_fast(f4(h2), hi, lo);
+    *reinterpret_cast<float4*>(a.hn_hi + ho) = hi;
+    *reinterpret_cast<float4*>(a.hn_lo + ho) = lo;
+  }
+  step_fini(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
 // backward step, element-wise part (oracle/recurrent.py ppo_loss_and_grads, BPTT loop), lane = row:
 //   dh = (dY W2^T)_t + keep * sum_q dh_rec[q];  dc = dh o (1 - tc^2) + keep * dc_next;  da = gate gradients
 // writes da row-major (batched GEMMs) and as the A operand planes of the split-K GEMM that follows
 // ------------------------------------------------------------------------------------------
+constexpr int BWD_MAX_SLICES = 8;            // 4 gate blocks x at most 2 k halves
 struct StepBwd2Args {
   const float* dhp; long long r0; int dhp_cols4;   // dY W2^T as planes over the R row space; first row of the step
   const float* dhr; long long dhr_slice; int n_slices;   // split-K partial planes [slice][tile][H / 4][PLC] (nullable: last step)
@@ -372,20 +504,24 @@ __global__ void __launch_bounds__(256) lstm_step_bwd2_kernel(const StepBwd2Args 
     const bool dn = a.done != nullptr && a.done[a.inds ? a.inds[row] : row] != 0;
     const float keep = dn ? 0.0f : 1.0f;
     const float4 dp = *reinterpret_cast<const float4*>(a.dhp + plane_off(a.r0 + row, p, a.dhp_cols4));
+    auto ld = [&](const float* q) { return *reinterpret_cast<const float4*>(q + so); };
+    const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dcp);
     float dh[4] = {dp.x, dp.y, dp.z, dp.w};
     if (a.dhr != nullptr) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < a.n_slices; ++q) {                   // fixed order: deterministic
-        const float4 v = *reinterpret_cast<const float4*>(a.dhr + q * a.dhr_slice + so);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      float4 pv[BWD_MAX_SLICES];                               // all partials in flight at once (one round trip)
+#pragma unroll
+      for (int q = 0; q < BWD_MAX_SLICES; ++q)
+        pv[q] = q < a.n_slices ? *reinterpret_cast<const float4*>(a.dhr + q * a.dhr_slice + so) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < BWD_MAX_SLICES; ++q) {               // fixed order: deterministic
+        s.x += pv[q].x; s.y += pv[q].y; s.z += pv[q].z; s.w += pv[q].w;
       }
       dh[0] += keep * s.x; dh[1] += keep * s.y; dh[2] += keep * s.z; dh[3] += keep * s.w;
       if (a.mdh != nullptr) *reinterpret_cast<float4*>(a.mdh + so) = dn ? s : make_float4(0.f, 0.f, 0.f, 0.f);
     } else if (a.mdh != nullptr) {
       *reinterpret_cast<float4*>(a.mdh + so) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    auto ld = [&](const float* q) { return *reinterpret_cast<const float4*>(q + so); };
-    const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dcp);
     const float iv[4] = {i4.x, i4.y, i4.z, i4.w}, fv[4] = {f4.x, f4.y, f4.z, f4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
     const float ov[4] = {o4.x, o4.y, o4.z, o4.w}, tv[4] = {t4.x, t4.y, t4.z, t4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
     const float dcv[4] = {dcn.x, dcn.y, dcn.z, dcn.w};
@@ -428,7 +564,7 @@ struct StepBwdGemmArgs {
   const float* dap_hi; const float* dap_lo; long long dap_tile; long long dap_slice;
   const float* whb; long long whb_tile; long long whb_slice;     // [n tile][q][half][H / 4][plb(NBT)]
   float* dhr; long long dhr_slice; long long st_tile;            // partial planes [slice][tile][H / 4][PLC]
-  int rows, H, NBT;
+  int rows, H, NBT, KS;
 };
 
 __global__ void __launch_bounds__(RT, 1) lstm_step_bwd_gemm_kernel(const StepBwdGemmArgs a) {
@@ -437,21 +573,23 @@ __global__ void __launch_bounds__(RT, 1) lstm_step_bwd_gemm_kernel(const StepBwd
   __shared__ uint32_t tmem_slot;
   uint32_t tmem_cols;
   const uint32_t tmem_base = step_init(&bars, &tmem_slot, a.NBT, tmem_cols);
-  const int tile = blockIdx.x, nt = blockIdx.y, q = blockIdx.z;
-  const int planes = a.H >> 2;
+  // blockIdx.z = gate block q x k part kp: the K = H columns of a gate block are cut into a.KS parts, so that a
+  // small minibatch still spreads over the device (each part streams 1 / KS of both operands)
+  const int tile = blockIdx.x, nt = blockIdx.y, q = blockIdx.z / a.KS, kp = blockIdx.z % a.KS;
+  const int planes = a.H >> 2, pp = planes / a.KS;
   BulkOperands g;
-  g.a_hi = a.dap_hi + static_cast<size_t>(tile) * a.dap_tile + static_cast<size_t>(q) * a.dap_slice;
-  g.a_lo = a.dap_lo + static_cast<size_t>(tile) * a.dap_tile + static_cast<size_t>(q) * a.dap_slice;
-  g.b_hi = a.whb + static_cast<size_t>(nt) * a.whb_tile + static_cast<size_t>(q) * a.whb_slice;
+  g.a_hi = a.dap_hi + static_cast<size_t>(tile) * a.dap_tile + static_cast<size_t>(q) * a.dap_slice + static_cast<size_t>(kp) * pp * PLA;
+  g.a_lo = a.dap_lo + static_cast<size_t>(tile) * a.dap_tile + static_cast<size_t>(q) * a.dap_slice + static_cast<size_t>(kp) * pp * PLA;
+  g.b_hi = a.whb + static_cast<size_t>(nt) * a.whb_tile + static_cast<size_t>(q) * a.whb_slice + static_cast<size_t>(kp) * pp * plb(a.NBT);
   g.b_lo = g.b_hi + static_cast<size_t>(planes) * plb(a.NBT);
-  g.K = a.H; g.N = a.NBT;
+  g.K = a.H / a.KS; g.N = a.NBT;
   bulk_pipeline(g, smem, &bars, tmem_base);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = warp & 3, cg = warp >> 2;
   const int r = sub * 32 + lane;
   tc::mbar_wait(&bars.done, 0u);
   tc::tc_fence_after();
-  float* out = a.dhr + static_cast<size_t>(q) * a.dhr_slice + static_cast<size_t>(tile) * a.st_tile;
+  float* out = a.dhr + static_cast<size_t>(blockIdx.z) * a.dhr_slice + static_cast<size_t>(tile) * a.st_tile;
   for (int c = cg * 16; c < a.NBT; c += 32) {
     float v[16];
     tc::tmem_ld16(tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + static_cast<uint32_t>(c), v);

@@ -552,10 +552,16 @@ __global__ void __launch_bounds__(RTI, 1) rg_tn_kernel(const TnArgs t) {
       for (int i = 0; i < 16; ++i) v[i] = 0.0f;
     }
     if (m < t.Kdim) {
+      float* dst = po + static_cast<size_t>(m) * t.ldp + n0 + c;
+      if ((t.ldp & 3) == 0 && n0 + c + 16 <= t.n_real && (reinterpret_cast<uintptr_t>(po) & 15) == 0) {
+        // 64 contiguous bytes per lane: whole sectors (scalar stores at a row stride wrote 8x the bytes)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = n0 + c + i;
-        if (n < t.n_real) po[static_cast<size_t>(m) * t.ldp + n] = v[i];
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + c + i < t.n_real) dst[i] = v[i];
       }
     }
   }
@@ -583,7 +589,15 @@ __global__ void __launch_bounds__(256) rg_reduce_kernel(const float* __restrict_
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   float s = 0.0f;
-  for (int sp = 0; sp < S; ++sp) s += part[sp * stride + i];
+  int sp = 0;
+  for (; sp + 8 <= S; sp += 8) {                       // eight loads in flight, summed in index order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = part[(sp + j) * stride + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; sp < S; ++sp) s += part[sp * stride + i];
   out[i] = s;
 }
 
@@ -622,7 +636,9 @@ struct SeqLayout {
 inline size_t al64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
 
 int split_for(int tiles, int rows) {
-  int S = (2 * 148) / (tiles > 0 ? tiles : 1);
+  // one wave of CTAs: twice as many splits of half the rows cost the same tensor time but double the partial-sum
+  // traffic (S x Kdim x N floats written and read back) and the per-CTA set-up
+  int S = 148 / (tiles > 0 ? tiles : 1);
   const int smax = (rows + 4 * TK - 1) / (4 * TK);
   if (S > smax) S = smax;
   if (S > 64) S = 64;

@@ -434,7 +434,7 @@ def run_own(args):
                                         if eng.p2p else "NCCL all-reduce x2 per update")),
                        "rollout_critic": "off: the fused rollout does not evaluate the critic (training replays it, ppo.py:425-446; "
                                          "value estimates are computed on request for logging)",
-                       "pdl": bool(lib.b200ppo_set_pdl(-1)),
+                       "pdl": int(lib.b200ppo_set_pdl(-1)),
                        "cuda_graph": getattr(eng, "graph", None) is not None, "done_rate": float(eng.done.float().mean()),
                        "truncation_rate": float(eng.trunc.float().mean())},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(),

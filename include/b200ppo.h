@@ -406,11 +406,11 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
-/* Programmatic dependent launch between the kernels of b200ppo_update (each kernel's prologue overlaps *
- * its predecessor's tail; griddepcontrol.wait before the first dependent access): 1 = on, 0 = plain   *
- * stream order (default: inside a captured graph the programmatic edges measured slower on B200);   *
- * also B200PPO_PDL=0|1.  Returns the previous setting; any other value only *
- * queries.  Takes effect for launches (and graph captures) made afterwards.                         */
+/* Programmatic dependent launch between the kernels of b200ppo_update (a kernel's prologue overlaps its
+ * predecessor's tail; griddepcontrol.wait before the first dependent access).  0 = plain stream order
+ * (default), 1 = every launch, 2 = only the small latency-bound kernels (GAE, loss, Adam), 3 = those and the
+ * kernel that follows one; also B200PPO_PDL=0..3 (measurements: profiles/r2_notes.md).  Returns the previous
+ * setting; any other value only queries.  Takes effect for launches (and graph captures) made afterwards. */
 int b200ppo_set_pdl(int on);
 /* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *
  * kernel -> out_host; returns -(1000 + count).                                                   */

@@ -30,10 +30,13 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();   // misc.cu (reads B200PPO_PDL once)
+int pdl_mode();       // 0 off, 1 every launch, 2 only the small kernels (GAE / loss / Adam), 3 those + the kernel after one
 
+// launch class: 0 = large kernel following a large kernel, 1 = small latency-bound kernel, 2 = large kernel
+// following a small one
 template <class... KArgs, class... Args>
-inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
-                            Args... args) {
+inline cudaError_t launch_kc(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                             Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -43,8 +46,15 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int m = pdl_mode();
+  cfg.numAttrs = (m == 1 || (m == 2 && cls == 1) || (m == 3 && cls >= 1)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args... args) {
+  return launch_kc(0, kernel, grid, block, smem, s, args...);
 }
 
 // ------------------------------------------------------------------------------------------

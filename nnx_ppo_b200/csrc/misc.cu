@@ -14,14 +14,19 @@ bool b200ppo::pdl_enabled() {
     const char* e = std::getenv("B200PPO_PDL");
     // Off by default: measured on B200 inside the captured iteration graph (profiles/r2_notes.md) the
     // programmatic edges made the iteration SLOWER (6.23 ms vs 5.64 ms per configs[1] iteration).
-    g_pdl = (e && e[0] == '1') ? 1 : 0;
+    g_pdl = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0;
   }
   return g_pdl != 0;
 }
 
+int b200ppo::pdl_mode() {
+  pdl_enabled();
+  return g_pdl;
+}
+
 extern "C" int b200ppo_set_pdl(int on) {
   const int prev = b200ppo::pdl_enabled() ? 1 : 0;
-  if (on == 0 || on == 1) g_pdl = on;
+  if (on >= 0 && on <= 3) g_pdl = on;
   return prev;
 }
 

@@ -1060,6 +1060,7 @@ struct AdamArgs {
 
 // optax.adam / adamw (scale_by_adam -> [add_decayed_weights] -> scale(-lr)), optionally preceded by
 // clip_by_global_norm — ppo.py:555-569.
+template <bool TIED>       // TIED: shared-trunk plans (a.tie != nullptr); the plain instantiation carries no extra code
 __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   __shared__ double nred[8];
   pdl_launch_dependents();
@@ -1070,8 +1071,8 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
   if (in) {
     if (a.S > 0) {
       for (int sp = 0; sp < a.S; ++sp) g += a.gpart[static_cast<size_t>(sp) * a.P + i];
-      const int32_t j = a.tie ? a.tie[i] : -1;
-      if (j >= 0) {          // shared trunk: d(loss)/d(w) = the actor path's + the critic path's (a + b == b + a:
+      const int32_t j = TIED ? a.tie[i] : -1;
+      if (TIED && j >= 0) {  // shared trunk: d(loss)/d(w) = the actor path's + the critic path's (a + b == b + a:
         float g2 = 0.0f;     // both copies get the same bits)
         for (int sp = 0; sp < a.S; ++sp) g2 += a.gpart[static_cast<size_t>(sp) * a.P + j];
         g = __fadd_rn(g, g2);
@@ -1332,6 +1333,11 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     const cudaError_t le__ = launch_k(__VA_ARGS__);                   \
     if (le__ != cudaSuccess) return static_cast<int>(le__);           \
   } while (0)
+#define B200PPO_LAUNCH_C(cls, ...)                                    \
+  do {                                                                \
+    const cudaError_t le__ = launch_kc(cls, __VA_ARGS__);             \
+    if (le__ != cudaSuccess) return static_cast<int>(le__);           \
+  } while (0)
 
   if (stages & B200PPO_STAGE_FWD) {
     FwdArgs a;
@@ -1344,7 +1350,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
         pa.plan = *plan; pa.L = L; pa.params = b->params; pa.ws = ws;
         B200PPO_LAUNCH(upd_prep_w_kernel, dim3(16, 2 * MAXL, 2), dim3(256), 0, s, pa);
       }
-      B200PPO_LAUNCH(upd_fwd_tc_kernel, dim3(cdiv(L.Rv, tile_f)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_f);
+      B200PPO_LAUNCH_C(2, upd_fwd_tc_kernel, dim3(cdiv(L.Rv, tile_f)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_f);
     } else {
       B200PPO_LAUNCH(upd_fwd_kernel, dim3(cdiv(L.Rv, TM)), dim3(NTH), GEMM_SMEM, s, a);
     }
@@ -1356,7 +1362,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.hpd = b->hparams_dev;
     a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
     a.rng_state = b->rng_state; a.comm_epoch = b->comm_epoch; a.update_index = update_index;
-    B200PPO_LAUNCH(upd_gae_kernel, dim3(cdiv(mb, GAE_THREADS)), dim3(GAE_THREADS), 0, s, a);
+    B200PPO_LAUNCH_C(1, upd_gae_kernel, dim3(cdiv(mb, GAE_THREADS)), dim3(GAE_THREADS), 0, s, a);
   }
   if (stages & B200PPO_STAGE_LOSS) {
     LossArgs a;
@@ -1372,8 +1378,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.update_index = update_index;
     const int A = plan->act_dim;
     const bool par = A <= 32 && (A & (A - 1)) == 0 && cdiv(static_cast<int64_t>(L.R) * A, 256) <= MAX_LOSS_BLOCKS;
-    if (par) B200PPO_LAUNCH(upd_loss_par_kernel, dim3(cdiv(static_cast<int64_t>(L.R) * A, 256)), dim3(256), 0, s, a);
-    else B200PPO_LAUNCH(upd_loss_kernel, dim3(cdiv(L.R, 128)), dim3(128), 0, s, a);
+    if (par) B200PPO_LAUNCH_C(1, upd_loss_par_kernel, dim3(cdiv(static_cast<int64_t>(L.R) * A, 256)), dim3(256), 0, s, a);
+    else B200PPO_LAUNCH_C(1, upd_loss_kernel, dim3(cdiv(L.R, 128)), dim3(128), 0, s, a);
   }
   if (stages & (B200PPO_STAGE_BWD | B200PPO_STAGE_BWD_DX | B200PPO_STAGE_BWD_DW)) {
     const bool do_dx = (stages & B200PPO_STAGE_BWD) || (stages & B200PPO_STAGE_BWD_DX);
@@ -1381,7 +1387,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     BwdArgs a;
     a.plan = *plan; a.L = L; a.params = b->params; a.ws = ws;
     if (use_tc) {
-      if (do_dx) B200PPO_LAUNCH(upd_bwd_dx_tc_kernel, dim3(cdiv(L.R, tile_b)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_b);
+      if (do_dx) B200PPO_LAUNCH_C(2, upd_bwd_dx_tc_kernel, dim3(cdiv(L.R, tile_b)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_b);
       if (do_dw) {
         if (L.tc_dw_bulk) B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0);
         else B200PPO_LAUNCH(upd_bwd_dw_tc_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), TC_SMEM, s, a, tc_split, 0);
@@ -1424,21 +1430,23 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
       }
     }
     const dim3 grid(cdiv(plan->n_params, 256)), block(256);
+    void (*adam_k)(const AdamArgs) = a.tie != nullptr ? upd_adam_kernel<true> : upd_adam_kernel<false>;
     if (!do_adam) {                         // RED alone
       a.do_adam = 0;
-      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+      B200PPO_LAUNCH_C(1, adam_k, grid, block, 0, s, a);
     } else if (!clip) {                     // (reduce +) (exchange +) Adam in one launch
       a.do_adam = 1;
-      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+      B200PPO_LAUNCH_C(1, adam_k, grid, block, 0, s, a);
     } else {                                // pass 1: (reduce +) (exchange +) squared norm; pass 2: clipped Adam
       AdamArgs p1 = a;
       p1.do_adam = 0; p1.norm_part = dbl + DBL_GN_PART;
-      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, p1);
+      B200PPO_LAUNCH_C(1, adam_k, grid, block, 0, s, p1);
       a.S = 0; a.comm = PeerComm{nullptr, 1, 0}; a.grad_out = nullptr; a.do_adam = 1;
-      B200PPO_LAUNCH(upd_adam_kernel, grid, block, 0, s, a);
+      B200PPO_LAUNCH_C(1, adam_k, grid, block, 0, s, a);
     }
   }
 #undef B200PPO_LAUNCH
+#undef B200PPO_LAUNCH_C
   return 0;
 }
 

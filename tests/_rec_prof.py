@@ -44,3 +44,33 @@ for r in range(reps):
     torch.cuda.synchronize()
     print(f"rep {r}: forward {ev[0].elapsed_time(ev[1]) * 1e3:.0f} us, backward {ev[1].elapsed_time(ev[2]) * 1e3:.0f} us", flush=True)
 assert bool(torch.isfinite(grad).all()) and bool(torch.isfinite(y).all())
+
+# the same calls inside a captured CUDA graph (how the engine runs them): per-call time without host launch gaps
+def _graph_time(fn, n=10):
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fn(_lib.current_stream())
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(n):
+                fn(_lib.current_stream())
+    gr.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); gr.replay(); gr.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (2 * n)
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "graph":
+    fwd = lambda s_: _lib.check(lib.b200ppo_lstm_seq_forward(s_, p, params.data_ptr(), 0, 0, x.data_ptr(), done.data_ptr(), inds.data_ptr(), B,
+                                                             c.data_ptr(), h.data_ptr(), T, mb, ws.data_ptr(), y.data_ptr(), 1))
+    bwd = lambda s_: _lib.check(lib.b200ppo_lstm_seq_backward(s_, p, params.data_ptr(), x.data_ptr(), dy.data_ptr(), done.data_ptr(),
+                                                              inds.data_ptr(), B, T, mb, ws.data_ptr(), grad.data_ptr()))
+    print(f"in-graph: seq_forward {_graph_time(fwd):.0f} us, seq_backward {_graph_time(bwd):.0f} us", flush=True)
+    for TT in (1, 2, 4, 8, 16):
+        f2 = lambda s_: _lib.check(lib.b200ppo_lstm_seq_forward(s_, p, params.data_ptr(), 0, 0, x.data_ptr(), done.data_ptr(), inds.data_ptr(), B,
+                                                                c.data_ptr(), h.data_ptr(), TT, mb, ws.data_ptr(), y.data_ptr(), 1))
+        b2 = lambda s_: _lib.check(lib.b200ppo_lstm_seq_backward(s_, p, params.data_ptr(), x.data_ptr(), dy.data_ptr(), done.data_ptr(),
+                                                                 inds.data_ptr(), B, TT, mb, ws.data_ptr(), grad.data_ptr()))
+        print(f"in-graph T={TT}: seq_forward {_graph_time(f2):.0f} us, seq_backward {_graph_time(b2):.0f} us", flush=True)

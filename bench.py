@@ -430,7 +430,10 @@ def run_own(args):
             "config": {"workload": cfg["workload"], "global_envs": cfg["n_envs"] * world, "parallelism": f"dp{world} (env-sharded)",
                        "l2": "no flush: every update streams a > 100 MB working set (around / above the 126 MB L2) that the iteration itself rewrites",
                        "collectives": ("none" if world == 1 else
-                                       ("peer memory: stores into every rank's comm buffer + per-block epoch flags inside the GAE / loss / Adam kernels"
+                                       ("peer memory over NVLink inside the loss / Adam kernels: 8-byte {payload, epoch} words, "
+                                         + ("gradient as reduce-scatter + all-gather (owner rank per 256-parameter block)"
+                                            if world >= int(os.environ.get("B200PPO_P2P_2HOP", "8")) else
+                                            "every rank pushes its gradient to every peer")
                                         if eng.p2p else "NCCL all-reduce x2 per update")),
                        "rollout_critic": "off: the fused rollout does not evaluate the critic (training replays it, ppo.py:425-446; "
                                          "value estimates are computed on request for logging)",

@@ -190,6 +190,24 @@ constexpr int MAXR = B200PPO_MAX_RANKS;
 constexpr size_t COMM_ADV = 0;                            // uint2[2 parity][MAXR][4]: the two fp64 sums as four halves
 constexpr size_t COMM_GRAD = 2 * MAXR * 4 * sizeof(uint2);   // uint2[2 parity][world][Ppad]: every rank PUSHES its gradient here
 inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n_params)); }
+// Two-hop gradient exchange (reduce-scatter + all-gather inside the one Adam launch) for larger worlds: every
+// rank pushing its whole gradient to every peer moves (world - 1) x P words per rank and direction (5.6 MB at
+// world 8, cfg 2: measured 16 us per update, bandwidth bound for 8-byte packets); with an owner rank per
+// 256-parameter block it is 2 x (world - 1) / world x P words (1.4 MB) for one more NVLink latency.  Layout
+// inside COMM_GRAD: scatter uint2[2 parity][world src][chunk], then gather uint2[2 parity][Ppad].
+inline size_t comm_chunk(int64_t n_params, int world) {
+  const size_t c = (static_cast<size_t>(n_params) + world - 1) / world;
+  return (c + 255) & ~static_cast<size_t>(255);
+}
+int g_twohop_min = -1;
+inline bool comm_two_hop(int world) {
+  if (g_twohop_min < 0) {
+    const char* e = std::getenv("B200PPO_P2P_2HOP");      // smallest world size that uses the two-hop exchange
+    g_twohop_min = e ? std::atoi(e) : 8;
+    if (g_twohop_min < 2) g_twohop_min = 2;
+  }
+  return world >= g_twohop_min;
+}
 
 struct PeerComm {
   const uint64_t* table;   // device: comm base of every rank (nullptr: exchange disabled)
@@ -1045,6 +1063,7 @@ struct AdamArgs {
   // slot [parity][rank] of EVERY rank's buffer and sums the slots of its own buffer in rank order
   PeerComm comm;
   size_t comm_ppad;
+  size_t comm_chunk;                // > 0: two-hop exchange, parameters [r * chunk, (r + 1) * chunk) are reduced by rank r
   int do_adam;                      // 0: reduce / exchange / norm only
   // nullable: squared global norm of the (summed) gradient -> *norm_out (block partials, ticket, fixed order)
   double* norm_part; double* norm_out; unsigned int* norm_ticket;
@@ -1085,13 +1104,33 @@ __global__ void __launch_bounds__(256) upd_adam_kernel(const AdamArgs a) {
     // push this element (with the epoch in the same 8-byte store) into slot [parity][rank] of EVERY rank's buffer,
     // then collect the slots of our own buffer in rank order: no flag, no fence, no block-wide barrier
     const uint32_t epoch = comm_epoch_of(a.comm_epoch, a.rng_state, a.update_index);
-    const size_t slot = ((epoch & 1u) * a.comm.world + a.comm.rank) * a.comm_ppad + static_cast<size_t>(i);
-    for (int r = 0; r < a.comm.world; ++r)
-      ll_store(reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_GRAD) + slot, __float_as_uint(g), epoch);
-    const uint2* pg = reinterpret_cast<const uint2*>(comm_base(a.comm, a.comm.rank) + COMM_GRAD) +
-                      (epoch & 1u) * a.comm.world * a.comm_ppad + static_cast<size_t>(i);
-    g = 0.0f;
-    for (int r = 0; r < a.comm.world; ++r) g += __uint_as_float(ll_wait(pg + r * a.comm_ppad, epoch, a.comm.rank, r));
+    const int W = a.comm.world, me = a.comm.rank;
+    if (a.comm_chunk == 0) {
+      const size_t slot = ((epoch & 1u) * W + me) * a.comm_ppad + static_cast<size_t>(i);
+      for (int r = 0; r < W; ++r)
+        ll_store(reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_GRAD) + slot, __float_as_uint(g), epoch);
+      const uint2* pg = reinterpret_cast<const uint2*>(comm_base(a.comm, me) + COMM_GRAD) +
+                        (epoch & 1u) * W * a.comm_ppad + static_cast<size_t>(i);
+      g = 0.0f;
+      for (int r = 0; r < W; ++r) g += __uint_as_float(ll_wait(pg + r * a.comm_ppad, epoch, me, r));
+    } else {
+      // hop 1: this element to its owner rank (block-uniform: chunks are multiples of the block size); the owner
+      // sums the world's words in rank order and (hop 2) hands the total to every rank - all ranks get the same bits
+      const size_t chunk = a.comm_chunk;
+      const int owner = static_cast<int>(static_cast<size_t>(i) / chunk);
+      const size_t il = static_cast<size_t>(i) - owner * chunk;
+      ll_store(reinterpret_cast<uint2*>(comm_base(a.comm, owner) + COMM_GRAD) + ((epoch & 1u) * W + me) * chunk + il,
+               __float_as_uint(g), epoch);
+      const size_t goff = 2u * static_cast<size_t>(W) * chunk + (epoch & 1u) * a.comm_ppad + static_cast<size_t>(i);
+      if (owner == me) {
+        const uint2* ps = reinterpret_cast<const uint2*>(comm_base(a.comm, me) + COMM_GRAD) + (epoch & 1u) * W * chunk + il;
+        float t = 0.0f;
+        for (int r = 0; r < W; ++r) t += __uint_as_float(ll_wait(ps + r * chunk, epoch, me, r));
+        for (int r = 0; r < W; ++r)
+          ll_store(reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_GRAD) + goff, __float_as_uint(t), epoch);
+      }
+      g = __uint_as_float(ll_wait(reinterpret_cast<const uint2*>(comm_base(a.comm, me) + COMM_GRAD) + goff, epoch, me, owner));
+    }
   }
   if (in && a.grad_out != nullptr) a.grad_out[i] = g;
   if (a.norm_part != nullptr) {
@@ -1414,6 +1453,7 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     // the exchange belongs to the ADAM stage: a caller that runs RED alone gets the local gradient
     a.comm = do_adam ? pc : PeerComm{nullptr, 1, 0};
     a.comm_ppad = comm_ppad(plan->n_params);
+    a.comm_chunk = (a.comm.table != nullptr && comm_two_hop(a.comm.world)) ? comm_chunk(plan->n_params, a.comm.world) : 0;
     a.norm_part = nullptr; a.norm_out = dbl + 2; a.norm_ticket = tickets + 2;
     a.mask = b->param_mask; a.tie = b->param_tie;
     a.n_seg = 0; a.ws = ws;
@@ -1455,7 +1495,11 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
 // ------------------------------------------------------------------------------------------
 extern "C" int64_t b200ppo_comm_bytes(const b200ppo_plan* plan, int32_t world_size) {
   if (check_plan_u(plan) || world_size < 1 || world_size > MAXR) return -1;
-  return static_cast<int64_t>(COMM_GRAD + 2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params) * sizeof(uint2));
+  // one-hop layout: 2 x world x Ppad words; two-hop layout: 2 x world x chunk + 2 x Ppad words (never larger for
+  // world >= 3; sized for both so that the mode is a run-time choice)
+  const size_t one = 2 * static_cast<size_t>(world_size) * comm_ppad(plan->n_params);
+  const size_t two = 2 * static_cast<size_t>(world_size) * comm_chunk(plan->n_params, world_size) + 2 * comm_ppad(plan->n_params);
+  return static_cast<int64_t>(COMM_GRAD + (one > two ? one : two) * sizeof(uint2));
 }
 
 extern "C" int b200ppo_comm_alloc(int64_t bytes, void** out) {

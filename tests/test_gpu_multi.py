@@ -23,9 +23,10 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, p2p, out_dir, clip=None):
+def _worker(rank, world, port, p2p, out_dir, clip=None, twohop=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank), B200PPO_P2P="1" if p2p else "0")
+                      LOCAL_RANK=str(rank), B200PPO_P2P="1" if p2p else "0",
+                      B200PPO_P2P_2HOP="2" if twohop else "99")      # smallest world that uses the two-hop exchange
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -55,16 +56,19 @@ def _worker(rank, world, port, p2p, out_dir, clip=None):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("clip", [None, 0.05])
-def test_peer_exchange_matches_nccl(tmp_path, clip):
+@pytest.mark.parametrize("clip,twohop", [(None, False), (0.05, False), (None, True), (0.05, True)])
+def test_peer_exchange_matches_nccl(tmp_path, clip, twohop):
+    """twohop: the reduce-scatter + all-gather form of the gradient exchange (default from 8 ranks up), forced at
+    world size 2 - owner-rank sums are rank ordered, so the result must still be NCCL's a + b bit for bit."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     res = {}
-    for p2p, port in ((True, 29611 + (2 if clip else 0)), (False, 29612 + (2 if clip else 0))):
+    base = 29611 + (2 if clip else 0) + (4 if twohop else 0)
+    for p2p, port in ((True, base), (False, base + 1)):
         ctx = mp.get_context("spawn")
-        procs = [ctx.Process(target=_worker, args=(r, 2, port, p2p, str(tmp_path), clip)) for r in range(2)]
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, p2p, str(tmp_path), clip, twohop)) for r in range(2)]
         for p in procs:
             p.start()
         for p in procs:

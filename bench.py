@@ -432,7 +432,7 @@ def run_own(args):
                        "collectives": ("none" if world == 1 else
                                        ("peer memory over NVLink inside the loss / Adam kernels: 8-byte {payload, epoch} words, "
                                          + ("gradient as reduce-scatter + all-gather (owner rank per 256-parameter block)"
-                                            if world >= int(os.environ.get("B200PPO_P2P_2HOP", "8")) else
+                                            if world >= int(os.environ.get("B200PPO_P2P_2HOP", "4")) else
                                             "every rank pushes its gradient to every peer")
                                         if eng.p2p else "NCCL all-reduce x2 per update")),
                        "rollout_critic": "off: the fused rollout does not evaluate the critic (training replays it, ppo.py:425-446; "

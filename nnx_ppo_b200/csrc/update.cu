@@ -193,7 +193,8 @@ inline size_t comm_ppad(int64_t n_params) { return align64(static_cast<size_t>(n
 // Two-hop gradient exchange (reduce-scatter + all-gather inside the one Adam launch) for larger worlds: every
 // rank pushing its whole gradient to every peer moves (world - 1) x P words per rank and direction (5.6 MB at
 // world 8, cfg 2: measured 16 us per update, bandwidth bound for 8-byte packets); with an owner rank per
-// 256-parameter block it is 2 x (world - 1) / world x P words (1.4 MB) for one more NVLink latency.  Layout
+// 256-parameter block it is 2 x (world - 1) / world x P words (1.4 MB) for one more NVLink latency: measured
+// 6.27 -> 6.12 ms per iteration at world 8, 5.98 -> 5.96 at world 4 (default: from 4 ranks up).  Layout
 // inside COMM_GRAD: scatter uint2[2 parity][world src][chunk], then gather uint2[2 parity][Ppad].
 inline size_t comm_chunk(int64_t n_params, int world) {
   const size_t c = (static_cast<size_t>(n_params) + world - 1) / world;
@@ -203,7 +204,7 @@ int g_twohop_min = -1;
 inline bool comm_two_hop(int world) {
   if (g_twohop_min < 0) {
     const char* e = std::getenv("B200PPO_P2P_2HOP");      // smallest world size that uses the two-hop exchange
-    g_twohop_min = e ? std::atoi(e) : 8;
+    g_twohop_min = e ? std::atoi(e) : 4;
     if (g_twohop_min < 2) g_twohop_min = 2;
   }
   return world >= g_twohop_min;

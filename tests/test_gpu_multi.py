@@ -58,7 +58,7 @@ def _worker(rank, world, port, p2p, out_dir, clip=None, twohop=False):
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("clip,twohop", [(None, False), (0.05, False), (None, True), (0.05, True)])
 def test_peer_exchange_matches_nccl(tmp_path, clip, twohop):
-    """twohop: the reduce-scatter + all-gather form of the gradient exchange (default from 8 ranks up), forced at
+    """twohop: the reduce-scatter + all-gather form of the gradient exchange (default from 4 ranks up), forced at
     world size 2 - owner-rank sums are rank ordered, so the result must still be NCCL's a + b bit for bit."""
     import torch
     if torch.cuda.device_count() < 2:

@@ -225,6 +225,9 @@ int b200ppo_synth_init_keys(void* stream, uint32_t k0, uint32_t k1, int32_t B, u
  * that a captured graph follows the per-iteration keys (rollout.py:57-59: split(reset_key, (T, B))).      */
 int b200ppo_split_keys_dev(void* stream, const uint32_t* key /*dev*/, int64_t first, int32_t count,
                            uint32_t* keys_out /*dev [count][2]*/);
+/* keys_out[i] = element `index` of jax.random.split(keys[i]) for each of `rows` row keys (dev uint32[rows][2]):
+ * the key flow of a vmapped `env.reset(key)` that splits its key first (wrappers, rollout.py:39). */
+int b200ppo_split_rows(void* stream, const uint32_t* keys, int32_t rows, uint32_t index, uint32_t* keys_out);
 int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
                           const float* params /*dev*/, const float* norm_mean, const float* norm_std,
                           const uint32_t* rng_state /*dev*/, const uint32_t* iter_keys /*dev*/,

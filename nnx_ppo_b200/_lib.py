@@ -87,6 +87,7 @@ SYMBOLS = {
     "b200ppo_synth_reset": (C.c_int, [_vp, _EP, _vp, _i32, _vp, _vp, _vp]),
     "b200ppo_synth_init_keys": (C.c_int, [_vp, _u32, _u32, _i32, _vp]),
     "b200ppo_split_keys_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "b200ppo_split_rows": (C.c_int, [_vp, _vp, _i32, _u32, _vp]),
     "b200ppo_rollout_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_eval_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _i32, _i32, _i32,

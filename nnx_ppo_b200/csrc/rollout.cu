@@ -241,6 +241,16 @@ __global__ void split_keys_dev_kernel(const uint32_t* __restrict__ key, int64_t 
   }
 }
 
+// element `index` of jax.random.split(key_i) for every row key (vmapped env.reset key flows, wrappers)
+__global__ void split_rows_kernel(const uint32_t* __restrict__ keys, int rows, uint32_t index, uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    const Key o = split_at(Key{keys[2 * i], keys[2 * i + 1]}, index);
+    out[2 * i] = o.a;
+    out[2 * i + 1] = o.b;
+  }
+}
+
 __global__ void synth_reset_kernel(const uint32_t* __restrict__ keys, int B, int O, int max_len,
                                    float* __restrict__ obs, int32_t* __restrict__ counter,
                                    uint32_t* __restrict__ term) {
@@ -684,6 +694,14 @@ extern "C" int b200ppo_split_keys_dev(void* stream, const uint32_t* key, int64_t
   if (count < 0 || first < 0 || !key || (count > 0 && !keys_out)) return B200PPO_EINVAL;
   if (count == 0) return 0;
   split_keys_dev_kernel<<<cdiv(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(key, first, count, keys_out);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_split_rows(void* stream, const uint32_t* keys, int32_t rows, uint32_t index, uint32_t* keys_out) {
+  if (rows < 0 || (rows > 0 && (!keys || !keys_out))) return B200PPO_EINVAL;
+  if (rows == 0) return 0;
+  split_rows_kernel<<<cdiv(rows, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, rows, index, keys_out);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }

@@ -57,11 +57,12 @@ class EpisodeWrapper:
 
 
 def _split0(keys):
-    """Element 0 of jax.random.split(key) for every row of an int32 [B, 2] key tensor (host
-    round trip: reset-time only)."""
-    import numpy as np
+    """Element 0 of jax.random.split(key) for every row of an int32 [B, 2] key tensor, on the device
+    (`b200ppo_split_rows`): the generic rollout calls `env.reset` for all envs on every step like the
+    reference (rollout.py:39), so this must not touch the host."""
     import torch
-    from .. import prng
-    k = keys.cpu().numpy().view(np.uint32)
-    out = np.array([prng.split((int(a), int(b)))[0] for a, b in k], np.uint32)
-    return torch.from_numpy(out.view(np.int32).copy()).to(keys.device)
+    lib = _lib.load()
+    keys = keys.contiguous()
+    out = torch.empty_like(keys)
+    _lib.check(lib.b200ppo_split_rows(_lib.current_stream(), _lib.ptr(keys), keys.shape[0], 0, _lib.ptr(out)), "split_rows")
+    return out

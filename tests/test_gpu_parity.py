@@ -234,6 +234,48 @@ def _oracle_state(oe, onet, B, seed):
     return oppo.new_training_state(oe, onet, B, seed)
 
 
+def test_split_rows_and_episode_wrapper_key_flow(dev):
+    """`b200ppo_split_rows`: element j of jax.random.split(key_i) per row key, bit exact; EpisodeWrapper.reset
+    (episode_wrapper.py:25) hands split(key)[0] to the wrapped env and draws the start counter from split(key)[1]
+    - entirely on the device (the generic rollout resets all envs every step, rollout.py:39)."""
+    import dataclasses as dc
+    from nnx_ppo_b200.wrappers import EpisodeWrapper
+    lib = _lib.load()
+    keys = oprng.split(oprng.key(21), 777)
+    kd = torch.from_numpy(keys.view(np.int32).copy()).to(dev)
+    for j in (0, 1):
+        out = torch.empty_like(kd)
+        _lib.check(lib.b200ppo_split_rows(_lib.current_stream(), kd.data_ptr(), 777, j, out.data_ptr()))
+        ref = np.stack([oprng.split(k)[j] for k in keys])
+        assert np.array_equal(u32(out), ref)
+    assert lib.b200ppo_split_rows(_lib.current_stream(), 0, 0, 0, 0) == 0
+
+    @dc.dataclass
+    class St:
+        obs: torch.Tensor
+        reward: torch.Tensor
+        done: torch.Tensor
+        info: dict
+
+    class Inner:
+        observation_size, action_size = 2, 1
+        def reset(self, k):
+            self.seen = k.clone()
+            z = torch.zeros(k.shape[0], device=k.device)
+            return St(torch.zeros(k.shape[0], 2, device=k.device), z, z, {})
+        def step(self, st, a):
+            return dc.replace(st, reward=st.reward + 1)
+
+    inner = Inner()
+    env = EpisodeWrapper(inner, max_len=40)
+    st = env.reset(kd)
+    assert np.array_equal(u32(inner.seen), np.stack([oprng.split(k)[0] for k in keys]))
+    oe = oenv.SyntheticEnv(2, 1, max_len=40)
+    assert np.array_equal(st.info["step_counter"].cpu().numpy(), oe.reset_fast(keys).step_counter)
+    st2 = env.step(st, torch.zeros(777, 1, device=dev))
+    assert torch.equal(st2.info["step_counter"], st.info["step_counter"] + 1)
+
+
 def test_env_reset_matches_oracle(dev):
     env = SyntheticEnv(64, 8, max_len=64)
     oe = oenv.SyntheticEnv(64, 8, max_len=64)

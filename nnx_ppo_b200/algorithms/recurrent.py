@@ -10,7 +10,9 @@ sequence over engine-owned buffers and is captured into ONE CUDA graph on its se
 jits ``ppo_step``); per-iteration inputs (PRNG keys, hyper-parameters) reach the kernels through the
 engine's device block, so the graph is never re-captured.  Networks whose sizes the tensor-core kernels do
 not take (hidden % 16, pre_dim % 4) use the per-step FFMA kernels of csrc/recurrent.cu instead, launched
-from the host.  Single GPU.
+from the host.  Data parallel like the MLP path (envs sharded over ranks): the advantage-moment and gradient
+exchanges run inside the GAE / loss / Adam kernels over peer memory (the Adam stage exchanges whatever gradient
+it is handed, so the recurrent actor's gradient travels with the critic's); the peer path is required.
 """
 from __future__ import annotations
 
@@ -27,9 +29,11 @@ from .types import LoggingLevel
 
 def _engine(net, opt, env, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
     from .engine import cached_engine
-    shape_key = (n_envs, T, E, M, bool(norm_adv), opt.gradient_clipping is not None, opt.wd_value >= 0.0)
+    from . import ppo as _ppo
+    world, group = _ppo._dist_info()
+    shape_key = (n_envs, T, E, M, bool(norm_adv), opt.gradient_clipping is not None, opt.wd_value >= 0.0, world)
     eng = cached_engine(net, "recurrent", env, opt, shape_key,
-                        lambda: _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw))
+                        lambda: _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw, world, group))
     eng.set_hparams(lam, gamma, clip, cw)
     return eng
 
@@ -38,13 +42,16 @@ def _ptr(v) -> int:
     return int(C.cast(v, C.c_void_p).value)
 
 
-def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw):
+def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw, world=1, group=None):
     from .engine import PPOEngine
     import torch
     eng = PPOEngine.__new__(PPOEngine)
     fake_env = type("E", (), {"fused_rollout": True})()
     PPOEngine.__init__(eng, net, fake_env, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw,
-                       world_size=1, group=None, use_graph=False)
+                       world_size=world, group=group, use_graph=False)
+    if world > 1 and not eng.p2p:
+        raise NotImplementedError("data-parallel recurrent training needs the peer-memory exchange (B200PPO_P2P=0 is "
+                                  "set, or the GPUs have no peer access)")
     lib, lp, mb, dev = eng.lib, net.lplan, eng.mb, net.device
     H, Y, P = lp.hidden, lp.out_dim, lp.pre_dim
     f32 = dict(dtype=torch.float32, device=dev)
@@ -194,12 +201,22 @@ def _enqueue_iteration(eng, net, env, env_state):
             n += T + 9
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_ADAM), "update/adam")
         n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_ADAM))
+    if eng.world > 1:
+        from .. import parallel
+        # every column is pre-divided by the GLOBAL sample count except the gradient norm [3], identical on every rank
+        if eng.hp.grad_clip > 0.0 and parallel.dist_info()[1] != 0:
+            eng.metrics[:, 3].zero_()
+        eng._allreduce(eng.metrics)
     # ---------------- Normalizer statistics, counters (ppo.py:329-346)
     if net.normalizer is not None:
         nz = net.normalizer
         _lib.check(lib.b200ppo_norm_batch_stats(s, eng.obs.data_ptr(), T * B, nz.size, eng.batch_stats.data_ptr(),
                                                 eng.norm_scratch.data_ptr()), "norm_batch_stats")
-        _lib.check(lib.b200ppo_norm_merge(s, eng.batch_stats.data_ptr(), 1, float(T * B), nz.size,
+        src = eng.batch_stats
+        if eng.world > 1:                                  # per-rank moments merged in rank order, as the MLP engine does
+            parallel.all_gather_into(eng.batch_stats_all.view(-1), eng.batch_stats, eng.group)
+            src = eng.batch_stats_all
+        _lib.check(lib.b200ppo_norm_merge(s, src.data_ptr(), eng.world, float(T * B), nz.size,
                                           nz.mean._dev.data_ptr(), nz.M2._dev.data_ptr(),
                                           nz.counter._dev.data_ptr()), "norm_merge")
         n += 3
@@ -248,8 +265,6 @@ def ppo_step_recurrent(env, training_state, n_envs, rollout_length, gae_lambda, 
     import torch
     from . import ppo as _ppo
     net = compile_network(training_state.networks)
-    if _ppo._dist_info()[0] != 1:
-        raise NotImplementedError("the recurrent path is single-GPU for now")
     opt = training_state.optimizer
     T, B = rollout_length, n_envs
     eng = _engine(net, opt, env, B, T, n_epochs, n_minibatches, gae_lambda, discounting_factor, clip_range,

@@ -90,3 +90,60 @@ def test_peer_exchange_matches_nccl(tmp_path, clip, twohop):
             np.testing.assert_array_equal(gn, res[(1, p2p)]["gn_logged"])
             assert gn.min() > clip                      # the threshold really clips in this test
         np.testing.assert_allclose(res[(0, True)]["gn_logged"], res[(0, False)]["gn_logged"], rtol=1e-6)
+
+
+def _recurrent_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), B200PPO_P2P="1")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import ppo
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_recurrent_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    O, A, B, T, E, M, P, H = 16, 4, 256, 12, 2, 2, 32, 64
+    nets = make_recurrent_actor_critic(O, A, P, H, [48], Rngs(1), trainable_initial_state=True)
+    env = SyntheticEnv(O, A, max_len=10, term_thresh16=3000)
+    ts = ppo.new_training_state(env, nets, B, 17)
+    net = compile_network(nets)
+    p0 = net.arena.cpu().numpy().copy()
+    ms = []
+    for _ in range(3):                       # eager, graph capture + replay, replay
+        ts, m = ppo.ppo_step(env, ts, B, T, 0.95, 0.99, 0.2, True, False, E, M)
+        ms.append([m[k] for k in ("losses/actor/mean", "losses/critic/mean", "losses/regularization/mean")])
+    eng = next(iter(net.engines.values()))
+    assert eng.p2p and eng.world == world and eng.r_graph is not None
+    torch.cuda.synchronize()
+    c, h = net.get_carry(ts.network_states)
+    np.savez(os.path.join(out_dir, f"rec{rank}.npz"), params=net.arena.cpu().numpy(), p0=p0, m=np.array(ms, np.float64),
+             obs=ts.env_states.obs.cpu().numpy(), mean=net.normalizer.mean.numpy(), h=h.cpu().numpy())
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+@pytest.mark.timeout(600)
+def test_recurrent_data_parallel_replicas_stay_in_sync(tmp_path):
+    """Recurrent (LSTM, trainable initial carry) actor on 2 ranks: every rank steps its own envs, the advantage
+    moments and the gradient (recurrent actor + critic) are exchanged inside the kernels, so parameters,
+    normaliser statistics and the (global) loss metrics are identical on both ranks while the env shards differ."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_recurrent_worker, args=(r, 2, 29641, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    a, b = np.load(tmp_path / "rec0.npz"), np.load(tmp_path / "rec1.npz")
+    np.testing.assert_array_equal(a["params"], b["params"])
+    np.testing.assert_array_equal(a["mean"], b["mean"])
+    np.testing.assert_allclose(a["m"], b["m"], rtol=1e-6)
+    assert np.all(np.isfinite(a["params"])) and np.abs(a["params"] - a["p0"]).max() > 1e-5
+    assert not np.array_equal(a["obs"], b["obs"]) and not np.array_equal(a["h"], b["h"])       # different env shards

@@ -371,6 +371,8 @@ int b200ppo_lstm_weight_grads(void* stream, const b200ppo_lstm_plan* plan, const
  *         done[t*B + (inds ? inds[j] : j)] is set
  *   c, h  dev [rows][hidden]: in = carry entering step 0, out = carry after step T-1 (reset applied)
  *   y     dev [T*rows][out_dim] actor outputs
+ *   keep_cache  bit 0: keep the activation cache in ws for the backward call; bit 1: the split weight planes in
+ *         ws are current (same params as the previous call on this ws: the rollout's T calls) - skip their launch
  * backward: d_y dev [T*rows][out_dim]; grad dev [n_params]: the recurrent actor's weight and bias
  * gradients are WRITTEN (fixed-order sums: bit-reproducible), other entries untouched.               */
 int b200ppo_lstm_seq_supported(const b200ppo_lstm_plan* plan);

@@ -73,6 +73,7 @@ def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw, wor
         n_roll = int(lib.b200ppo_lstm_seq_workspace_floats(lp, 1, n_envs))
         n_upd = int(lib.b200ppo_lstm_seq_workspace_floats(lp, T, mb))
         eng.r_ws = torch.zeros(max(n_roll, n_upd) + 64, **f32)
+        eng.r_grad2 = torch.zeros(int(net.n_params), **f32)       # the recurrent actor's gradient (see _enqueue_iteration)
     else:
         eng.r_cache = torch.zeros(T, int(lib.b200ppo_lstm_cache_floats(lp, mb)), **f32)
         eng.r_dc, eng.r_dh = torch.zeros(mb, H, **f32), torch.zeros(mb, H, **f32)
@@ -97,10 +98,11 @@ def _policy(eng, net, obs, t, s):
     mean_p, std_p = net.norm_ptrs()
     arena = net.arena.data_ptr()
     if eng.r_seq:
+        # the parameters do not change during the rollout: the split weight planes of step 0 serve all T steps
         _lib.check(lib.b200ppo_lstm_seq_forward(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
-                                                h.data_ptr(), 1, B, eng.r_ws.data_ptr(), eng.r_y.data_ptr(), 0),
+                                                h.data_ptr(), 1, B, eng.r_ws.data_ptr(), eng.r_y.data_ptr(), 0 if t == 0 else 2),
                    "lstm_seq_forward(rollout)")
-        n = int(lib.b200ppo_lstm_seq_num_launches(lp, 1, B, 0))
+        n = int(lib.b200ppo_lstm_seq_num_launches(lp, 1, B, 0)) - (0 if t == 0 else 1)
     else:
         _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                              h.data_ptr(), eng.r_y.data_ptr(), 0), "lstm_step_fwd(rollout)")
@@ -178,13 +180,23 @@ def _enqueue_iteration(eng, net, env, env_state):
                            "lstm_step_fwd(replay)")
             n += T
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_GAE | ST.STAGE_LOSS), "update/loss")
-        _lib.check(lib.b200ppo_update(*args, ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
         n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_GAE | ST.STAGE_LOSS | ST.STAGE_BWD | ST.STAGE_RED))
         if eng.r_seq:                                                                 # BPTT + weight gradients
+            # The critic's backward (dX, dW, reduction: full-device GEMM kernels) and the recurrent actor's BPTT (64
+            # dependent latency-bound step launches that leave the SMs mostly idle) only share their inputs: they
+            # run as two branches (side stream; parallel branches of the captured graph).  The reduction writes the
+            # whole flat gradient, so BPTT writes the actor's entries to its own buffer, copied in after the join.
+            cur = torch.cuda.current_stream()
+            eng._side.wait_stream(cur)
+            with torch.cuda.stream(eng._side):
+                _lib.check(lib.b200ppo_update(_lib.current_stream(), *args[1:], ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
             _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
-                                                     T, mb, eng.r_ws.data_ptr(), eng.r_grad_ptr), "lstm_seq_backward")
+                                                     T, mb, eng.r_ws.data_ptr(), eng.r_grad2.data_ptr()), "lstm_seq_backward")
+            cur.wait_stream(eng._side)
+            eng.grad[:net.n_recurrent].copy_(eng.r_grad2[:net.n_recurrent])
             n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, mb, 1))
         else:
+            _lib.check(lib.b200ppo_update(*args, ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
             eng.r_dc.zero_()
             eng.r_dh.zero_()
             for t in reversed(range(T)):

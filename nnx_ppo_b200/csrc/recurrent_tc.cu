@@ -601,6 +601,34 @@ __global__ void __launch_bounds__(256) rg_reduce_kernel(const float* __restrict_
   out[i] = s;
 }
 
+// several fixed-order partial reductions in one launch (the three weight-gradient GEMMs of a sequence backward
+// and their bias sums): block b belongs to the segment whose block range contains it
+struct ReduceSegs {
+  int n_seg;
+  int blk0[7];                                  // first block of segment i; blk0[n_seg] = total
+  const float* part[6]; long long n[6]; int S[6]; long long stride[6]; float* out[6];
+};
+__global__ void __launch_bounds__(256) rg_reduce_multi_kernel(const ReduceSegs g) {
+  int q = 0;
+  while (q + 1 < g.n_seg && static_cast<int>(blockIdx.x) >= g.blk0[q + 1]) ++q;
+  const long long i = (static_cast<long long>(blockIdx.x) - g.blk0[q]) * blockDim.x + threadIdx.x;
+  if (i >= g.n[q]) return;
+  const float* part = g.part[q];
+  const long long stride = g.stride[q];
+  const int S = g.S[q];
+  float s = 0.0f;
+  int sp = 0;
+  for (; sp + 8 <= S; sp += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = part[(sp + j) * stride + i];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+  }
+  for (; sp < S; ++sp) s += part[sp * stride + i];
+  g.out[q][i] = s;
+}
+
 // carry in / out of the sequence workspace: dst[r][0..H) = src[r][0..H) with row strides
 __global__ void __launch_bounds__(256) rg_copy_rows_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst,
                                                            int ldd, int rows, int H) {
@@ -627,7 +655,7 @@ struct SeqLayout {
   size_t whf, whb;                        // weight planes
   size_t flags;                           // int32 [tiles][T + 1] arrival counters of the persistent forward kernel
   size_t mdc, mdh, ipart;                 // learned initial carry: masked per-step gradient planes, per-step sums
-  size_t part, bpart, total;
+  size_t part, bpart, part1, bpart1, part2, bpart2, total;   // partial sums of the three weight-gradient GEMMs
   int tiles, NBT, nbt;
   size_t hp_half, hp_buf, st_tile, cache_step, dap_half;
   int S_cat, S_w1, S_w2;
@@ -690,15 +718,12 @@ SeqLayout seq_layout(const b200ppo_lstm_plan& p, int T, int rows) {
   L.S_cat = split_for(cdiv(P + H, RM) * cdiv(4 * H, 256), Rr);
   L.S_w1 = split_for(cdiv(p.obs_dim, RM), Rr);
   L.S_w2 = split_for(cdiv(H, RM), Rr);
-  size_t pmax = static_cast<size_t>(L.S_cat) * (P + H) * 4 * H;
-  const size_t p1 = static_cast<size_t>(L.S_w1) * p.obs_dim * P, p2 = static_cast<size_t>(L.S_w2) * H * Y;
-  pmax = p1 > pmax ? p1 : pmax;
-  pmax = p2 > pmax ? p2 : pmax;
-  L.part = take(pmax);
-  size_t nb = 4 * H;
-  nb = P > nb ? P : nb;
-  nb = Y > nb ? Y : nb;
-  L.bpart = take(64 * nb);
+  L.part = take(static_cast<size_t>(L.S_cat) * (P + H) * 4 * H);
+  L.bpart = take(64 * 4 * H);
+  L.part1 = take(static_cast<size_t>(L.S_w1) * p.obs_dim * P);
+  L.bpart1 = take(64 * P);
+  L.part2 = take(static_cast<size_t>(L.S_w2) * H * Y);
+  L.bpart2 = take(64 * Y);
   L.total = o;
   return L;
 }
@@ -813,8 +838,9 @@ int launch_gemm(cudaStream_t s, GemmArgs g, int n_real, int slices, int n_tile =
 }
 
 // weight gradient out[Kdim][n_real] (+ bias gradient) = A^T D over `rows` rows, S row splits, fixed-order reduction
+// (segs == nullptr: reduced right away; else the reductions are appended to *segs for one rg_reduce_multi_kernel)
 int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int act_a, const float* D, int ldd, int n_real,
-              int rows, int S, float* part, float* bpart, float* gw, float* gb) {
+              int rows, int S, float* part, float* bpart, float* gw, float* gb, ReduceSegs* segs = nullptr) {
   TnArgs t;
   t.A = A; t.lda = lda; t.a_col0 = a_col0; t.Kdim = Kdim; t.act_a = act_a;
   t.D = D; t.ldd = ldd; t.n_real = n_real; t.N = mma_n(n_real); t.n_log2 = ilog2(t.N); t.tile_stride = t.N;
@@ -828,6 +854,16 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
   rg_tn_kernel<<<grid, RTI, smem, s>>>(t);
   B200PPO_LAUNCH_CHECK();
   const long long n = static_cast<long long>(Kdim) * n_real;
+  if (segs != nullptr) {
+    auto add = [&](const float* p, long long cnt, float* out) {
+      const int q = segs->n_seg++;
+      segs->part[q] = p; segs->n[q] = cnt; segs->S[q] = S; segs->stride[q] = cnt; segs->out[q] = out;
+      segs->blk0[q + 1] = segs->blk0[q] + static_cast<int>(cdiv(cnt, 256));
+    };
+    add(part, n, gw);
+    if (gb != nullptr) add(bpart, n_real, gb);
+    return 0;
+  }
   rg_reduce_kernel<<<cdiv(n, 256), 256, 0, s>>>(part, n, S, n, gw);
   B200PPO_LAUNCH_CHECK();
   if (gb != nullptr) {
@@ -856,8 +892,8 @@ extern "C" int b200ppo_lstm_seq_num_launches(const b200ppo_lstm_plan* plan, int3
   if (check_plan_tc(plan) || T <= 0 || rows <= 0) return -1;
   const size_t p_smem = 2 * static_cast<size_t>(plan->hidden / 4) * tc::plane_bytes(4 * UT) + PF_NS * 2u * (RK / 4) * tc::plane_bytes(RM);
   const int steps = (seq_persistent(*plan, T, rows) && p_smem <= PERSIST_SMEM_MAX) ? 1 : T;
-  if (!backward) return 1 /* weight planes */ + 2 /* carry in */ + 2 /* pre, proj */ + steps + 1 /* post */ + 2 /* carry out */;
-  return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 * 3 /* TN + 2 reductions each */ +
+  if (!backward) return 1 /* weight planes */ + 1 /* carry in */ + 2 /* pre, proj */ + steps + 1 /* post */ + 1 /* carry out */;
+  return 1 /* dh_post */ + T /* element-wise */ + (T - 1) /* split-K dh_rec */ + 1 /* du */ + 3 /* TN */ + 1 /* reductions */ +
          (plan->init_c_off > 0 ? 2 : 0) /* initial-carry gradient */;
 }
 
@@ -879,23 +915,24 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
   float* z1 = ws + L.z1;
   float* cat = ws + L.cat;
   const float* Wh = params + plan->wcat_off + static_cast<size_t>(P) * 4 * H;
-  // Wh -> operand planes (forward and transposed forms)
-  {
+  // Wh -> operand planes (forward and transposed forms); keep_cache bit 1: the planes in ws are current (the
+  // rollout calls this T times between two parameter updates)
+  if (!(keep_cache & 2)) {
     PrepWhArgs a;
     a.Wh = Wh; a.H = H; a.NBT = L.NBT; a.whf = ws + L.whf; a.whb = ws + L.whb;
     const long long n = static_cast<long long>(H / UT) * planes * 64 + static_cast<long long>(L.nbt) * 4 * planes * L.NBT;
     lstm_prep_wh_kernel<<<cdiv(n, 256), 256, 0, s>>>(a);
     B200PPO_LAUNCH_CHECK();
   }
+  keep_cache &= 1;
   // carry in: h -> A planes of step 0 (and row-major cat[0][:, P:] for the weight gradients), c -> state planes
   {
     CarryInArgs a;
     a.c = c; a.h = h; a.rows = rows; a.H = H;
     a.hp_hi = ws + L.hp; a.hp_lo = ws + L.hp + L.hp_half; a.hp_tile = static_cast<long long>(planes) * PLA;
     a.cp = ws + L.cp; a.cp_tile = static_cast<long long>(L.st_tile);
+    a.cat_h = cat + P; a.ld_cat = LC;
     lstm_carry_in_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(a);
-    B200PPO_LAUNCH_CHECK();
-    rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(h, H, cat + P, LC, rows, H);
     B200PPO_LAUNCH_CHECK();
   }
   // z1 = x W1 + b1;  u = act(z1) -> cat[:, :P]
@@ -979,11 +1016,8 @@ extern "C" int b200ppo_lstm_seq_forward(void* stream, const b200ppo_lstm_plan* p
     if (rc) return rc;
   }
   // carry out (reset already applied by the last step)
-  rg_copy_rows_kernel<<<cdiv(static_cast<int64_t>(rows) * H, 256), 256, 0, s>>>(cat + static_cast<size_t>(T) * rows * LC + P, LC, h,
-                                                                             H, rows, H);
-  B200PPO_LAUNCH_CHECK();
-  lstm_carry_out_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(ws + L.cp, static_cast<long long>(L.st_tile),
-                                                                                            c, rows, H);
+  lstm_carry_out_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(
+      ws + L.cp, static_cast<long long>(L.st_tile), c, cat + static_cast<size_t>(T) * rows * LC + P, LC, h, rows, H);
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
@@ -1012,8 +1046,6 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
     rc = launch_gemm(s, g, H, 1);
     if (rc) return rc;
   }
-  if (cudaMemsetAsync(ws + L.dcp, 0, sizeof(float) * L.tiles * L.st_tile, s) != cudaSuccess)
-    return static_cast<int>(cudaGetLastError());
   const long long dap_slice = static_cast<long long>(planes) * PLA, dap_tile = 4 * dap_slice;
   const long long dhr_slice = static_cast<long long>(L.tiles) * L.st_tile;
   for (int t = T - 1; t >= 0; --t) {
@@ -1031,6 +1063,7 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
     e.dap_hi = ws + L.dap; e.dap_lo = ws + L.dap + L.dap_half; e.dap_tile = dap_tile; e.dap_slice = dap_slice;
     e.mdc = plan->init_c_off > 0 ? ws + L.mdc + so : nullptr;
     e.mdh = plan->init_c_off > 0 ? ws + L.mdh + so : nullptr;
+    e.dc_zero = t == T - 1 ? 1 : 0;
     e.rows = rows; e.H = H;
     lstm_step_bwd2_kernel<<<cdiv(static_cast<int64_t>(L.tiles) * planes * RM, 256), 256, 0, s>>>(e);
     B200PPO_LAUNCH_CHECK();
@@ -1065,15 +1098,21 @@ extern "C" int b200ppo_lstm_seq_backward(void* stream, const b200ppo_lstm_plan* 
     rc = launch_gemm(s, g, P, 1);
     if (rc) return rc;
   }
-  // weight gradients (x: the NORMALISED observations the forward pass saw)
+  // weight gradients (x: the NORMALISED observations the forward pass saw); one reduction launch for all of them
+  ReduceSegs segs;
+  segs.n_seg = 0; segs.blk0[0] = 0;
   rc = launch_tn(s, cat, LC, 0, LC, B200PPO_ACT_NONE, da, 4 * H, 4 * H, R, L.S_cat, ws + L.part, ws + L.bpart,
-                 grad + plan->wcat_off, grad + plan->bl_off);
+                 grad + plan->wcat_off, grad + plan->bl_off, &segs);
   if (rc) return rc;
-  rc = launch_tn(s, x, O, 0, O, B200PPO_ACT_NONE, ws + L.dz1, P, P, R, L.S_w1, ws + L.part, ws + L.bpart,
-                 grad + plan->w1_off, grad + plan->b1_off);
+  rc = launch_tn(s, x, O, 0, O, B200PPO_ACT_NONE, ws + L.dz1, P, P, R, L.S_w1, ws + L.part1, ws + L.bpart1,
+                 grad + plan->w1_off, grad + plan->b1_off, &segs);
   if (rc) return rc;
-  return launch_tn(s, ws + L.hn, H, 0, H, B200PPO_ACT_NONE, d_y, Y, Y, R, L.S_w2, ws + L.part, ws + L.bpart,
-                   grad + plan->w2_off, grad + plan->b2_off);
+  rc = launch_tn(s, ws + L.hn, H, 0, H, B200PPO_ACT_NONE, d_y, Y, Y, R, L.S_w2, ws + L.part2, ws + L.bpart2,
+                 grad + plan->w2_off, grad + plan->b2_off, &segs);
+  if (rc) return rc;
+  rg_reduce_multi_kernel<<<segs.blk0[segs.n_seg], 256, 0, s>>>(segs);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
 }
 
 // test hook: C[M][N] = A[M][K] B (b_nt = 0: B is [K][N]; 1: B is [N][K]) through the generic tile kernel

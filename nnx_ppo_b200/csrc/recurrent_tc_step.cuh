@@ -179,6 +179,7 @@ struct CarryInArgs {
   const float* c; const float* h; int rows, H;
   float* hp_hi; float* hp_lo; long long hp_tile;       // [tile][H / 4][PLA]
   float* cp; long long cp_tile;                        // [tile][H / 4][PLC]
+  float* cat_h; int ld_cat;                            // row-major copy of h for the weight gradients (cat[0][:, P:])
 };
 
 __global__ void __launch_bounds__(256) lstm_carry_in_kernel(const CarryInArgs a) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) lstm_carry_in_kernel(const CarryInArgs a)
   if (row < a.rows) {
     hv = *reinterpret_cast<const float4*>(a.h + static_cast<size_t>(row) * a.H + 4 * p);
     cv = *reinterpret_cast<const float4*>(a.c + static_cast<size_t>(row) * a.H + 4 * p);
+    *reinterpret_cast<float4*>(a.cat_h + static_cast<size_t>(row) * a.ld_cat + 4 * p) = hv;
   }
   float4 hi, lo;
   tc::split4_fast(hv, hi, lo);
@@ -202,8 +204,9 @@ __global__ void __launch_bounds__(256) lstm_carry_in_kernel(const CarryInArgs a)
   *reinterpret_cast<float4*>(a.cp + static_cast<size_t>(tile) * a.cp_tile + static_cast<size_t>(p) * PLC + r * 4) = cv;
 }
 
-// state planes of c -> row-major (carry out)
+// carry out: state planes of c -> row-major; h from the row-major slot the last step wrote (cat[T][:, P:])
 __global__ void __launch_bounds__(256) lstm_carry_out_kernel(const float* __restrict__ cp, long long cp_tile, float* __restrict__ c,
+                                                            const float* __restrict__ cat_h, int ld_cat, float* __restrict__ h,
                                                             int rows, int H) {
   const int planes = H >> 2;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -214,6 +217,8 @@ __global__ void __launch_bounds__(256) lstm_carry_out_kernel(const float* __rest
   if (row >= rows) return;
   *reinterpret_cast<float4*>(c + static_cast<size_t>(row) * H + 4 * p) =
       *reinterpret_cast<const float4*>(cp + static_cast<size_t>(tile) * cp_tile + static_cast<size_t>(p) * PLC + r * 4);
+  *reinterpret_cast<float4*>(h + static_cast<size_t>(row) * H + 4 * p) =
+      *reinterpret_cast<const float4*>(cat_h + static_cast<size_t>(row) * ld_cat + 4 * p);
 }
 
 // element (row, col) of a matrix stored as planes over its whole row space: [row / 128][cols / 4][128][4]
@@ -487,6 +492,7 @@ struct StepBwd2Args {
   // carry handed on belongs to the initial-carry parameters instead - kept per step as planes [tile][H / 4][PLC]
   // (zeros elsewhere) and summed in fixed order by lstm_init_grad_kernel
   float* mdc; float* mdh;
+  int dc_zero;                                 // last step of the sequence: the incoming dc is zero (dcp not read)
   int rows, H;
 };
 
@@ -505,7 +511,8 @@ __global__ void __launch_bounds__(256) lstm_step_bwd2_kernel(const StepBwd2Args 
     const float keep = dn ? 0.0f : 1.0f;
     const float4 dp = *reinterpret_cast<const float4*>(a.dhp + plane_off(a.r0 + row, p, a.dhp_cols4));
     auto ld = [&](const float* q) { return *reinterpret_cast<const float4*>(q + so); };
-    const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin), dcn = ld(a.dcp);
+    const float4 i4 = ld(a.gi), f4 = ld(a.gf), g4 = ld(a.gg), o4 = ld(a.go), t4 = ld(a.tcc), c4 = ld(a.cin);
+    const float4 dcn = a.dc_zero ? make_float4(0.f, 0.f, 0.f, 0.f) : ld(a.dcp);
     float dh[4] = {dp.x, dp.y, dp.z, dp.w};
     if (a.dhr != nullptr) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -147,8 +147,8 @@ def test_sequence_replay_and_bptt_match_oracle(cuda_device, lib, cfg, persist):
     assert np.abs(outs[0][:n_rec] - ref).max() < 3e-4 * scale, (np.abs(outs[0][:n_rec] - ref).max(), scale)
     assert np.array_equal(outs[0], outs[1])                      # fixed-order sums: bit-reproducible
     assert np.all(outs[0][n_rec:] == 7.0)                        # the critic's slots are not touched
-    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 0) == (1 if persist else T) + 8
-    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 1) == 2 * T + 10 + (2 if init else 0)
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 0) == (1 if persist else T) + 6
+    assert lib.b200ppo_lstm_seq_num_launches(plan, T, mb, 1) == 2 * T + 5 + (2 if init else 0)
     if init:                                                     # the learned carry's gradient is not negligible here
         o = plan.init_c_off
         assert np.abs(ref[o:o + 2 * H]).max() > 1e-3 * scale

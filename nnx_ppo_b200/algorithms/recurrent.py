@@ -83,6 +83,9 @@ def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw, wor
         eng.r_da = torch.zeros(T, mb, 4 * H, **f32)
         eng.r_dz = torch.zeros(T, mb, P, **f32)
         eng.r_scratch = torch.zeros(int(lib.b200ppo_lstm_wgrad_scratch_floats(lp, T * mb)), **f32)
+    # measured on B200 (same box, configs[2]): 43.1 / 41.3 ms per iteration with the overlap, 40.9 / 40.9 without - the
+    # full-device GEMM kernels of the critic's backward delay the latency-critical step chain more than they hide
+    eng.r_overlap = os.environ.get("B200PPO_REC_OVERLAP", "0") == "1"
     eng.r_env = None            # engine-owned env state (the object a captured graph points at)
     eng.r_graph = None
     eng.r_graphable = False
@@ -182,18 +185,22 @@ def _enqueue_iteration(eng, net, env, env_state):
         _lib.check(lib.b200ppo_update(*args, ST.STAGE_GAE | ST.STAGE_LOSS), "update/loss")
         n += int(lib.b200ppo_update_num_launches(plan, eng.hp, T, mb, ST.STAGE_GAE | ST.STAGE_LOSS | ST.STAGE_BWD | ST.STAGE_RED))
         if eng.r_seq:                                                                 # BPTT + weight gradients
-            # The critic's backward (dX, dW, reduction: full-device GEMM kernels) and the recurrent actor's BPTT (64
-            # dependent latency-bound step launches that leave the SMs mostly idle) only share their inputs: they
-            # run as two branches (side stream; parallel branches of the captured graph).  The reduction writes the
-            # whole flat gradient, so BPTT writes the actor's entries to its own buffer, copied in after the join.
-            cur = torch.cuda.current_stream()
-            eng._side.wait_stream(cur)
-            with torch.cuda.stream(eng._side):
-                _lib.check(lib.b200ppo_update(_lib.current_stream(), *args[1:], ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
-            _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
-                                                     T, mb, eng.r_ws.data_ptr(), eng.r_grad2.data_ptr()), "lstm_seq_backward")
-            cur.wait_stream(eng._side)
-            eng.grad[:net.n_recurrent].copy_(eng.r_grad2[:net.n_recurrent])
+            # B200PPO_REC_OVERLAP=1 (off by default, see _build_engine): the critic's backward and the recurrent actor's
+            # BPTT only share their inputs and can run as two branches of the captured graph.  The reduction writes
+            # the whole flat gradient, so BPTT then writes the actor's entries to its own buffer, copied in after the join.
+            if eng.r_overlap:
+                cur = torch.cuda.current_stream()
+                eng._side.wait_stream(cur)
+                with torch.cuda.stream(eng._side):
+                    _lib.check(lib.b200ppo_update(_lib.current_stream(), *args[1:], ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
+                _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
+                                                         T, mb, eng.r_ws.data_ptr(), eng.r_grad2.data_ptr()), "lstm_seq_backward")
+                cur.wait_stream(eng._side)
+                eng.grad[:net.n_recurrent].copy_(eng.r_grad2[:net.n_recurrent])
+            else:
+                _lib.check(lib.b200ppo_update(*args, ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")
+                _lib.check(lib.b200ppo_lstm_seq_backward(s, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
+                                                         T, mb, eng.r_ws.data_ptr(), eng.r_grad_ptr), "lstm_seq_backward")
             n += int(lib.b200ppo_lstm_seq_num_launches(lp, T, mb, 1))
         else:
             _lib.check(lib.b200ppo_update(*args, ST.STAGE_BWD | ST.STAGE_RED), "update/bwd")

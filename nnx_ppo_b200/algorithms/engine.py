@@ -94,7 +94,22 @@ def _side_stream(dev):
     return st
 
 
+class PendingMetrics:
+    """Per-update metric rows of one iteration on their way to the host (pinned slot + event)."""
+
+    def __init__(self, slot, event):
+        self._slot, self._event, self._value = slot, event, None
+
+    def wait(self) -> np.ndarray:
+        if self._value is None:
+            self._event.synchronize()
+            self._value = self._slot.numpy().copy()
+            self._slot = self._event = None
+        return self._value
+
+
 class PPOEngine:
+    N_MH = 4          # slots of the metrics ring
     N_SLOTS = 8
 
     def __init__(self, net: CompiledNet, env, opt: AdamOptimizer, n_envs: int, rollout_length: int,
@@ -137,7 +152,14 @@ class PPOEngine:
         self.ws = torch.zeros(ws_bytes // 4, **f32)
         self.n_updates = self.E * self.M
         self.metrics = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, **f32)
-        self.metrics_host = torch.zeros(self.n_updates, _lib.METRICS_STRIDE, dtype=torch.float32).pin_memory()
+        # device -> host ring of the per-update metric rows: step(fetch_metrics="lazy") queues the copy and returns a
+        # handle, so the host can enqueue the next iteration before it reads this one's losses (the reference's
+        # jitted ppo_step is dispatched asynchronously in the same way)
+        self._mh_ring = [torch.zeros(self.n_updates, _lib.METRICS_STRIDE, dtype=torch.float32).pin_memory()
+                         for _ in range(self.N_MH)]
+        self._mh_pending = [None] * self.N_MH
+        self._mh_i = 0
+        self.metrics_host = self._mh_ring[0]
         # per-iteration host -> device block: int32[4] keys | float32[HP_FLOATS] hyper-parameters.  A ring
         # of pinned slots with one event each: a slot is rewritten only after the copy that read it has
         # executed, so the host may run many iterations ahead of the GPU (fetch_metrics=False).
@@ -536,7 +558,19 @@ class PPOEngine:
         self.opt.step += self.n_updates
         self.net.adam_step = self.opt.step
         if fetch_metrics:
+            i = self._mh_i
+            self._mh_i = (i + 1) % self.N_MH
+            old = self._mh_pending[i]
+            if old is not None:
+                old.wait()                        # an unread result is about to lose its slot: keep its values
+            self.metrics_host = self._mh_ring[i]
             self.metrics_host.copy_(self.metrics, non_blocking=True)
+            if fetch_metrics == "lazy":
+                ev = torch.cuda.Event()
+                ev.record()
+                h = self._mh_pending[i] = PendingMetrics(self.metrics_host, ev)
+                return h
+            self._mh_pending[i] = None
             torch.cuda.current_stream().synchronize()
             return self.metrics_host.numpy().copy()
         return None

@@ -9,6 +9,8 @@ import time
 from collections.abc import Callable
 from typing import Any, Optional
 
+import os
+
 import numpy as np
 
 from .. import _lib, parallel, prng
@@ -102,14 +104,106 @@ def ppo_step(env: RLEnv, training_state: TrainingState, n_envs: int, rollout_len
     if LoggingLevel.GRAD_NORM in logging_level:
         eng.enable_grad_norm()
     reset_key, new_key = prng.split(training_state.rng_key)              # ppo.py:271
-    per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
     total_steps = np.float32(training_state.steps_taken + np.float32(rollout_length * n_envs))
-    metrics = _iteration_metrics(per_update, eng, logging_level, logging_percentiles)
-    metrics["total_steps"] = total_steps                                 # ppo.py:333
+    if not (logging_level & _EAGER_LEVELS) and _LAZY_METRICS:
+        # only the per-update loss rows are logged: return without waiting for the device.  The dict
+        # materialises (event wait + mean / std over the updates) when it is first read - the reference's
+        # jitted ppo_step returns asynchronously dispatched arrays in the same way.
+        pending = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics="lazy")
+
+        def build():
+            m = _iteration_metrics(pending.wait(), eng, logging_level, logging_percentiles)
+            m["total_steps"] = total_steps                               # ppo.py:333
+            return m
+        metrics = LazyMetrics(build)
+    else:
+        per_update = eng.step(training_state.env_states, reset_key, new_key, fetch_metrics=True)
+        metrics = _iteration_metrics(per_update, eng, logging_level, logging_percentiles)
+        metrics["total_steps"] = total_steps                             # ppo.py:333
     # the engine advances ITS env-state tensors in place: hand those back, so that the caller's next
     # TrainingState points at the live state whatever object came in (ppo.py:341-346)
     new_state = training_state.replace(env_states=eng.env_state, rng_key=new_key, steps_taken=total_steps)
     return new_state, metrics
+
+
+# levels whose metrics read the rollout buffers / parameters (which the next iteration overwrites): computed eagerly
+_EAGER_LEVELS = (LoggingLevel.CRITIC_EXTRA | LoggingLevel.ACTOR_EXTRA | LoggingLevel.TRAIN_ROLLOUT_STATS
+                 | LoggingLevel.TRAINING_ENV_METRICS | LoggingLevel.WEIGHTS)
+_LAZY_METRICS = os.environ.get("B200PPO_LAZY_METRICS", "1") != "0"
+
+
+class LazyMetrics(dict):
+    """The metrics dict of one iteration, filled in on first access (any read forces it)."""
+
+    def __init__(self, build):
+        super().__init__()
+        self._build = build
+
+    def _force(self):
+        b = self._build
+        if b is not None:
+            self._build = None
+            dict.update(self, b())
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self._force(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self._force())
+
+    def __len__(self):
+        return dict.__len__(self._force())
+
+    def __contains__(self, k):
+        return dict.__contains__(self._force(), k)
+
+    def __repr__(self):
+        return dict.__repr__(self._force())
+
+    def __eq__(self, other):
+        return dict.__eq__(self._force(), other)
+
+    __hash__ = None
+
+    def __setitem__(self, k, v):
+        dict.__setitem__(self._force(), k, v)
+
+    def __delitem__(self, k):
+        dict.__delitem__(self._force(), k)
+
+    def get(self, k, default=None):
+        return dict.get(self._force(), k, default)
+
+    def keys(self):
+        return dict.keys(self._force())
+
+    def values(self):
+        return dict.values(self._force())
+
+    def items(self):
+        return dict.items(self._force())
+
+    def copy(self):
+        return dict(self._force())
+
+    def update(self, *a, **kw):
+        dict.update(self._force(), *a, **kw)
+
+    def pop(self, *a):
+        return dict.pop(self._force(), *a)
+
+    def setdefault(self, k, default=None):
+        return dict.setdefault(self._force(), k, default)
+
+    def __or__(self, other):
+        return dict(self._force()) | other
+
+    def __ror__(self, other):
+        return other | dict(self._force())
+
+    def __reduce__(self):
+        return (dict, (dict(self._force()),))
 
 
 def _iteration_metrics(per_update: np.ndarray, eng, logging_level, percentiles) -> dict[str, Any]:
@@ -375,8 +469,9 @@ def train_ppo(env: RLEnv, networks: StatefulModule, config: Optional[TrainConfig
             config.ppo.combine_advantages, config.ppo.n_epochs, config.ppo.n_minibatches,
             config.ppo.critic_loss_weight, config.ppo.logging_level, config.ppo.logging_percentiles)
         n_iterations += 1
-        steps = int(training_state.steps_taken)          # ppo_step already synchronised on the metrics
+        steps = int(training_state.steps_taken)
         if measure_throughput:
+            len(metrics)                                 # wait for the iteration (ppo_step may return before it ends)
             metrics["throughput/train_sps"] = (config.ppo.n_envs * config.ppo.rollout_length
                                                / (time.perf_counter() - t0))
         if config.eval.enabled and _should_run(steps, last_eval_step, config.eval.every_steps):

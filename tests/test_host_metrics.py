@@ -150,3 +150,30 @@ def test_train_ppo_cadence_matches_reference_rules(monkeypatch):
     cfg2 = TrainConfig(ppo=PPOConfig(n_envs=10, rollout_length=10), eval=EvalConfig(enabled=False))
     res = ppo.train_ppo(None, nets, cfg2, total_steps=250, seed=9, log_fn=lambda m, s: logs.append(s), initial_state=ts)
     assert res.total_steps == 300 and res.total_iterations == 3 and evals == [] and logs == [100, 200, 300]
+
+
+def test_lazy_metrics_dict_materialises_on_any_read():
+    """ppo_step returns a dict that is filled in on first access (the device work is still running when it
+    returns): every read path of a plain dict must force it exactly once."""
+    import json
+    import pickle
+    from nnx_ppo_b200.algorithms.ppo import LazyMetrics
+    calls = []
+
+    def build():
+        calls.append(1)
+        return {"losses/actor/mean": np.float32(1.5), "total_steps": np.float32(64.0)}
+
+    for read in (lambda m: m["total_steps"], lambda m: list(m), lambda m: len(m), lambda m: "total_steps" in m,
+                 lambda m: dict(m), lambda m: {**m}, lambda m: m.items(), lambda m: m.get("x"), lambda m: repr(m),
+                 lambda m: json.dumps({k: float(v) for k, v in m.items()}), lambda m: pickle.dumps(m),
+                 lambda m: m.update({"a": 1}), lambda m: m.__setitem__("b", 2), lambda m: m == {}, lambda m: m | {"c": 3}):
+        calls.clear()
+        m = LazyMetrics(build)
+        assert not calls
+        read(m)
+        assert calls == [1]
+        assert float(m["losses/actor/mean"]) == 1.5 and calls == [1]
+    m = LazyMetrics(build)
+    assert dict(m) == {"losses/actor/mean": np.float32(1.5), "total_steps": np.float32(64.0)}
+    assert type(pickle.loads(pickle.dumps(m))) is dict

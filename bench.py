@@ -371,8 +371,6 @@ def run_own(args):
     hyper = (cfg["n_envs"], cfg["T"], 0.95, 0.99, 0.2, True, False, cfg["E"], cfg["M"])
     net = compile_network(nets)
     recurrent = bool(net.recurrent)
-    if recurrent and world > 1:
-        raise SystemExit("bench.py: the recurrent configuration is single-GPU")
 
     def barrier():
         if world > 1:
@@ -508,6 +506,8 @@ def run_own(args):
                             "stage_tflops_algorithmic": {k: flops[k] * U / (stage_ms[k] * 1e-3) / 1e12 for k in flops}}
         if sync_us is not None:
             line["roofline"]["sync_us_per_update"] = sync_us
+    if not args.quick and recurrent:
+        line["roofline"] = recurrent_roofline(eng, net, cfg, lib, _lib, torch, tf_peak, which, ms / args.steps)
     if world == 1 and not args.quick and rank == 0:
         # CPU baseline: the oracle on a bounded sample of the same workload
         Bs = min(args.ref_envs, cfg["n_envs"])
@@ -533,6 +533,58 @@ def run_own(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def recurrent_roofline(eng, net, cfg, lib, _lib, torch, tf_peak, which, ms_iter):
+    """configs[2]: the dominant piece is the recurrent actor's replay (b200ppo_lstm_seq_forward) and its reverse
+    pass (b200ppo_lstm_seq_backward): launch sequences, timed inside a captured CUDA graph on the engine's own
+    buffers (the state of the last update), algorithmic flops of the Dense -> LSTM -> Dense actor over T x rows."""
+    lp, T, mb, B = net.lplan, eng.T, eng.mb, eng.B
+    O, P, H, Y = lp.obs_dim, lp.pre_dim, lp.hidden, lp.out_dim
+    arena, ip = net.arena.data_ptr(), eng.inds.data_ptr()
+
+    def fwd(s_):
+        _lib.check(lib.b200ppo_lstm_seq_forward(s_, lp, arena, 0, 0, eng.r_xhat_ptr, eng.done.data_ptr(), ip, B,
+                                                eng.r_c.data_ptr(), eng.r_h.data_ptr(), T, mb, eng.r_ws.data_ptr(), eng.r_y_ptr, 1))
+
+    def bwd(s_):
+        _lib.check(lib.b200ppo_lstm_seq_backward(s_, lp, arena, eng.r_xhat_ptr, eng.r_dy_ptr, eng.done.data_ptr(), ip, B,
+                                                 T, mb, eng.r_ws.data_ptr(), eng.r_grad_ptr))
+
+    def graph_us(fn, n=8):
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            fn(_lib.current_stream())
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=st):
+                for _ in range(n):
+                    fn(_lib.current_stream())
+        gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gr.replay(); gr.replay(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (2 * n)
+
+    if not getattr(eng, "r_seq", False):
+        return None
+    us_f, us_b = graph_us(fwd), graph_us(bwd)
+    R = T * mb
+    f_fwd = 2.0 * R * (O * P + (P + H) * 4 * H + H * Y)
+    f_bwd = 2.0 * f_fwd - 2.0 * R * O * P            # dX and dW of every layer; no input gradient for the first
+    ach = (f_fwd + f_bwd) / ((us_f + us_b) * 1e-6) / 1e12
+    U = eng.n_updates
+    return {"bound": "tensor", "kernel": "b200ppo_lstm_seq_forward + b200ppo_lstm_seq_backward (per-step tcgen05 kernels + batched tile GEMMs)",
+            "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+            "peak_source": f"{which} bf16 tensor (sustained)",
+            "compute_path": "tcgen05.mma kind::tf32, error-compensated 3xTF32; achieved counts ALGORITHMIC flops",
+            "ceiling_3xtf32_tflops": tf_peak / 6.0, "frac_of_3xtf32_ceiling": ach / (tf_peak / 6.0),
+            "flop_per_launch": f_fwd + f_bwd, "launch_ms": (us_f + us_b) * 1e-3,
+            "seq_forward_us": us_f, "seq_backward_us": us_b,
+            "share_of_iteration": U * (us_f + us_b) * 1e-3 / ms_iter,
+            "note": "latency bound: 2 x T dependent step launches per update on 4 row tiles (profiles/r2_recurrent_notes.md)"}
 
 
 def main():

@@ -277,6 +277,10 @@ int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const b200ppo_syn
  * call on this workspace was an update whose ADAM stage ran (it refreshes the split operand planes
  * together with the parameters) and nothing else has touched `params` since. */
 #define B200PPO_STAGE_NO_PREP 256
+/* modifier of STAGE_LOSS: the distillation head (distillation.py:160-232) instead of the PPO surrogate - mean
+ * negative log-likelihood of bufs->raw_action (the teacher's mean, raw space) under the current policy + the
+ * entropy regulariser; no GAE stage needed, d loss / d value = 0; metrics [0] = NLL, [1] = 0, [2] = regulariser */
+#define B200PPO_STAGE_NLL 512
 
 int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb);
 int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200ppo_hparams* hp,

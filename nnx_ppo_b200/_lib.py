@@ -18,6 +18,7 @@ STAGE_FWD, STAGE_GAE, STAGE_LOSS, STAGE_BWD, STAGE_RED, STAGE_ADAM = 1, 2, 4, 8,
 STAGE_ALL = 63
 STAGE_BWD_DX, STAGE_BWD_DW = 64, 128
 STAGE_NO_PREP = 256
+STAGE_NLL = 512
 METRICS_STRIDE = 12   # B200PPO_METRICS_STRIDE
 # layout of the device hyper-parameter block (B200PPO_HP_*)
 HP_GAMMA, HP_LAMBDA, HP_CLIP_RANGE, HP_CRITIC_WEIGHT, HP_LEARNING_RATE = 0, 1, 2, 3, 4

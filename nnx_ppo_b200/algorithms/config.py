@@ -11,7 +11,7 @@ from typing import Any, Optional
 
 import numpy as np
 
-from .types import LoggingLevel, TrainingState
+from .types import DistillationState, LoggingLevel, TrainingState
 
 
 @dataclass
@@ -66,6 +66,31 @@ class TrainConfig:
 
 
 @dataclass
+class DistillationConfig:
+    """config.py:72-84 of the reference."""
+    n_envs: int = 256
+    rollout_length: int = 20
+    total_steps: int = 512_000
+    learning_rate: float = 1e-4
+    n_epochs: int = 4
+    n_minibatches: int = 4
+    gradient_clipping: Optional[float] = None
+    weight_decay: Optional[float] = None
+    logging_level: LoggingLevel = LoggingLevel.LOSSES
+    logging_percentiles: Optional[tuple[int, ...]] = None
+
+
+@dataclass
+class DistillationTrainConfig:
+    """config.py:88-95 of the reference."""
+    distillation: DistillationConfig = field(default_factory=DistillationConfig)
+    eval: EvalConfig = field(default_factory=EvalConfig)
+    video: VideoConfig = field(default_factory=VideoConfig)
+    seed: int = 17
+    checkpoint_every_steps: int = 500_000
+
+
+@dataclass
 class VideoData:
     frames: np.ndarray                      # (T, H, W, C) uint8
     step: int
@@ -76,6 +101,15 @@ class VideoData:
 @dataclass
 class TrainResult:
     training_state: TrainingState
+    final_metrics: dict[str, Any]
+    eval_history: list[dict[str, Any]]
+    total_steps: int
+    total_iterations: int
+
+
+@dataclass
+class DistillationTrainResult:
+    training_state: DistillationState
     final_metrics: dict[str, Any]
     eval_history: list[dict[str, Any]]
     total_steps: int

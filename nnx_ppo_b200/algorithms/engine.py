@@ -210,7 +210,11 @@ class PPOEngine:
         self._hp_host = np.zeros(_lib.HP_FLOATS, np.float32)
         self.set_hparams()
         self._upload_block((0, 0), (0, 0))
-        self.rng_per_iter = 2 * T + self.n_updates * 2 * (T + 1)
+        # sampler counts one update's replay consumes (ppo.py:425-436: T replayed steps + the bootstrap call, two
+        # draws each) and the loss head; the distillation engine overrides both (no bootstrap call, NLL head)
+        self.rng_per_update = 2 * (T + 1)
+        self.nll = False
+        self.rng_per_iter = 2 * T + self.n_updates * self.rng_per_update
         # data-parallel exchange of the per-update advantage sums and gradients: peer memory
         # (flags + P2P loads inside the GAE / loss / Adam kernels) unless disabled or unsupported
         self.fuse_prep = os.environ.get("B200PPO_FUSE_PREP", "1") != "0"
@@ -470,25 +474,29 @@ class PPOEngine:
             self._side.wait_stream(cur)                      # the rollout's observations are complete
             with torch.cuda.stream(self._side):
                 n += self._enqueue_batch_stats()
+        # PPO: every stage; distillation: no GAE, the NLL head (include/b200ppo.h B200PPO_STAGE_NLL)
+        gae_bit = 0 if self.nll else _lib.STAGE_GAE
+        loss_bits = _lib.STAGE_LOSS | (_lib.STAGE_NLL if self.nll else 0)
+        stage_all = _lib.STAGE_FWD | gae_bit | loss_bits | _lib.STAGE_BWD | _lib.STAGE_RED | _lib.STAGE_ADAM
         for u in range(self.n_updates):
-            off = rng_offset0 + u * 2 * (T + 1)
+            off = rng_offset0 + u * self.rng_per_update
             args = (s, net.plan, self.hp, self.bufs[u], T, B, self.mb, off, u)
             # the Adam kernel of update u-1 refreshed the split weight planes: only the first update
             # of an iteration (parameters may have been touched from outside) runs the prep launch
             noprep = _lib.STAGE_NO_PREP if (u > 0 and self.fuse_prep) else 0
-            per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, _lib.STAGE_ALL | noprep))
+            per_update = int(lib.b200ppo_update_num_launches(net.plan, self.hp, T, self.mb, stage_all | noprep))
             if (self.world == 1 or self.p2p) and self.adv_log is not None:
-                head = _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS
+                head = _lib.STAGE_FWD | gae_bit | loss_bits
                 _lib.check(lib.b200ppo_update(*args, head | noprep), "update/loss")
                 self.adv_log[u].copy_(self._adv_view)
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL & ~head), "update/bwd")
+                _lib.check(lib.b200ppo_update(*args, stage_all & ~head), "update/bwd")
             elif self.world == 1 or self.p2p:
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_ALL | noprep), "update")
+                _lib.check(lib.b200ppo_update(*args, stage_all | noprep), "update")
             else:
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | _lib.STAGE_GAE | noprep), "update/fwd")
-                if self.hp.normalize_advantages:
+                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_FWD | gae_bit | noprep), "update/fwd")
+                if self.hp.normalize_advantages and not self.nll:
                     self._allreduce(self.adv_sums)
-                _lib.check(lib.b200ppo_update(*args, _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")
+                _lib.check(lib.b200ppo_update(*args, loss_bits | _lib.STAGE_BWD | _lib.STAGE_RED), "update/bwd")
                 if self.adv_log is not None:
                     self.adv_log[u].copy_(self._adv_view)
                 self._allreduce(self.grad)

@@ -54,6 +54,37 @@ class Transition:
     rollout_extras: Any = None
 
 
+@dataclasses.dataclass(frozen=True)
+class DistillationTransition:
+    """Reference: algorithms/types.py:85-106.  The teacher's rollout_extras at the sampler position (its action
+    mean in raw space, the teacher running in eval mode) is the distillation target."""
+    obs: Any
+    student_output: Any
+    rewards: Any
+    done: Any
+    truncated: Any
+    next_obs: Any
+    metrics: dict
+    student_rollout_extras: Any = None
+    teacher_rollout_extras: Any = None
+
+
+@dataclasses.dataclass(frozen=True)
+class DistillationState:
+    """Reference: algorithms/types.py:111-125.  The teacher is an argument of the step (like the env), only its
+    per-env carry is tracked here."""
+    student: Any
+    student_states: Any
+    teacher_states: Any
+    env_states: Any
+    optimizer: Any
+    rng_key: Any
+    steps_taken: Any
+
+    def replace(self, **kw):
+        return dataclasses.replace(self, **kw)
+
+
 class LoggingLevel(enum.Flag):
     LOSSES = enum.auto()
     CRITIC_EXTRA = enum.auto()

@@ -606,13 +606,17 @@ struct LossArgs {
   PeerComm comm;
   const uint32_t* comm_epoch;
   int update_index;
+  // 1: distillation head (distillation.py:160-232): the loss is the mean negative log-likelihood of the target
+  // raw action in `raw_action` (the teacher's mean) under the current policy plus the entropy regulariser; no
+  // advantages, no value loss (metrics: [0] = NLL, [1] = 0)
+  int nll;
 };
 
 // global advantage moments: the local sums, or (peer exchange) all ranks' sums in rank order
 __device__ __forceinline__ void loss_adv_stats(const LossArgs& a, float& a_mean, float& a_den) {
   a_mean = 0.0f;
   a_den = 1.0f;
-  if (!a.normalize_adv) return;
+  if (!a.normalize_adv || a.nll) return;
   const double* dbl = reinterpret_cast<const double*>(a.ws + a.L.dbl);
   double s1 = dbl[0], s2 = dbl[1];
   if (a.comm.table != nullptr) {
@@ -649,6 +653,11 @@ __device__ __forceinline__ void loss_write_metrics(const LossArgs& a, const doub
   a.metrics_out[4] = static_cast<float>(s[3] / ng);
   a.metrics_out[5] = static_cast<float>(s[4] / ng);
   a.metrics_out[6] = static_cast<float>(s[5] / ng);
+  if (a.nll) {
+    a.metrics_out[7] = a.metrics_out[8] = a.metrics_out[9] = 0.0f;
+    a.metrics_out[10] = static_cast<float>(static_cast<double>(a.L.R) / ng);
+    return;
+  }
   const double s1 = __ldcg(dbl), s2 = __ldcg(dbl + 1), n_loc = static_cast<double>(a.L.R);
   const double m = a_mean, den = a_den;
   a.metrics_out[7] = static_cast<float>((s1 - n_loc * m) / den / ng);
@@ -695,26 +704,32 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
       const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
       ent += 0.5f + B200PPO_HALF_LOG_2PI + ls + log_det_jac(zp);
     }
-    const float adv = a.ws[a.L.adv + r];
-    const float v = a.ws[a.v_off + r];
-    const float target = __fadd_rn(v, adv);                    // ppo.py:456-458
-    const float diff = __fsub_rn(v, target);
-    const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
-    const float ratio = expf(ll - a.loglik_old[grow]);
-    const float lo = 1.0f - clip, hi = 1.0f + clip;
-    const float c1 = __fmul_rn(ratio, an);
-    const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
-    l_actor = -static_cast<double>(fminf(c1, c2));
-    l_critic = 0.5 * static_cast<double>(diff) * diff;
+    float g_ll, diff = 0.0f;
     l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
-    l_clip = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
-    l_t1 = target;
-    l_t2 = static_cast<double>(target) * target;
-    // JAX tie rules: minimum and clip split the cotangent 0.5 / 0.5 on exact ties
-    const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
-    const float w2 = 1.0f - w1;
-    const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
-    const float g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    if (a.nll) {                                               // distillation: d(-mean ll) / d ll = -1 / N
+      l_actor = -static_cast<double>(ll);
+      g_ll = -inv_n;
+    } else {
+      const float adv = a.ws[a.L.adv + r];
+      const float v = a.ws[a.v_off + r];
+      const float target = __fadd_rn(v, adv);                    // ppo.py:456-458
+      diff = __fsub_rn(v, target);
+      const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
+      const float ratio = expf(ll - a.loglik_old[grow]);
+      const float lo = 1.0f - clip, hi = 1.0f + clip;
+      const float c1 = __fmul_rn(ratio, an);
+      const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
+      l_actor = -static_cast<double>(fminf(c1, c2));
+      l_critic = 0.5 * static_cast<double>(diff) * diff;
+      l_clip = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
+      l_t1 = target;
+      l_t2 = static_cast<double>(target) * target;
+      // JAX tie rules: minimum and clip split the cotangent 0.5 / 0.5 on exact ties
+      const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
+      const float w2 = 1.0f - w1;
+      const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
+      g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    }
     const float we = a.plan.entropy_weight * inv_n;
     for (int d = 0; d < A; ++d) {
       const float mu = y[d], rho = y[A + d], z = z_in[d];
@@ -803,19 +818,25 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   const float critic_w = a.hpd ? a.hpd[B200PPO_HP_CRITIC_WEIGHT] : a.critic_w;
   double l_actor = 0.0, l_critic = 0.0, l_reg = 0.0, l_clip = 0.0, l_t1 = 0.0, l_t2 = 0.0;
   if (valid) {
-    const float adv = a.ws[a.L.adv + r];
-    const float v = a.ws[a.v_off + r];
-    const float target = __fadd_rn(v, adv);
-    const float diff = __fsub_rn(v, target);
-    const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
-    const float ratio = expf(ll - a.loglik_old[grow]);
-    const float lo = 1.0f - clip, hi = 1.0f + clip;
-    const float c1 = __fmul_rn(ratio, an);
-    const float c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
-    const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
-    const float w2 = 1.0f - w1;
-    const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
-    const float g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    float g_ll, diff = 0.0f, c1 = 0.0f, c2 = 0.0f, ratio = 1.0f, target = 0.0f;
+    if (a.nll) {                                               // distillation: d(-mean ll) / d ll = -1 / N
+      g_ll = -inv_n;
+      c1 = c2 = ll;                                            // l_actor = -min(c1, c2) = -ll below
+    } else {
+      const float adv = a.ws[a.L.adv + r];
+      const float v = a.ws[a.v_off + r];
+      target = __fadd_rn(v, adv);
+      diff = __fsub_rn(v, target);
+      const float an = a.normalize_adv ? (adv - a_mean) / a_den : adv;
+      ratio = expf(ll - a.loglik_old[grow]);
+      const float lo = 1.0f - clip, hi = 1.0f + clip;
+      c1 = __fmul_rn(ratio, an);
+      c2 = __fmul_rn(fminf(fmaxf(ratio, lo), hi), an);
+      const float w1 = c1 < c2 ? 1.0f : (c1 == c2 ? 0.5f : 0.0f);
+      const float w2 = 1.0f - w1;
+      const float dclip = (ratio > lo && ratio < hi) ? 1.0f : ((ratio == lo || ratio == hi) ? 0.5f : 0.0f);
+      g_ll = -(w1 * an + w2 * an * dclip) * inv_n * ratio;
+    }
     const float we = a.plan.entropy_weight * inv_n;
     const float dm = z - mu;
     const float is = 1.0f / sigma;
@@ -829,7 +850,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
       l_actor = -static_cast<double>(fminf(c1, c2));
       l_critic = 0.5 * static_cast<double>(diff) * diff;
       l_reg = -static_cast<double>(a.plan.entropy_weight) * ent;
-      l_clip = fabsf(ratio - 1.0f) > clip ? 1.0 : 0.0;
+      l_clip = (!a.nll && fabsf(ratio - 1.0f) > clip) ? 1.0 : 0.0;
       l_t1 = target;
       l_t2 = static_cast<double>(target) * target;
     }
@@ -1413,7 +1434,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.clip = hp->clip_range; a.critic_w = hp->critic_loss_weight; a.normalize_adv = hp->normalize_advantages;
     a.hpd = b->hparams_dev;
     a.n_global = static_cast<double>(L.R) * hp->world_size;
-    a.comm = hp->normalize_advantages ? pc : PeerComm{nullptr, 1, 0};
+    a.nll = (stages & B200PPO_STAGE_NLL) ? 1 : 0;
+    a.comm = (hp->normalize_advantages && !a.nll) ? pc : PeerComm{nullptr, 1, 0};
     a.comm_epoch = b->comm_epoch;
     a.update_index = update_index;
     const int A = plan->act_dim;

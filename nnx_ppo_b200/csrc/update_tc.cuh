@@ -524,8 +524,17 @@ __device__ __forceinline__ void tc_chain_setup(TcCtx& cx, const b200ppo_chain& c
     tc::mbar_wait(cx.bar_done, (cx.done_uses - 1u) & 1u);
   cx.b_half = bh;
   const uint32_t ring_end = cx.b_base + TC_NS * 2u * bh;
-  cx.chain_ok = ring_end + TC_EBUF_BYTES <= TC_SMEM;
-  cx.ebuf_off = cx.chain_ok ? ring_end : 0u;
+  // The transpose buffer sits at the TOP of the allocation whatever the ring size: the weight streamer of the
+  // next chain runs while the producers are still in the previous chain's last epilogue, so a buffer placed
+  // at ring_end was overwritten by the next chain's (larger) weight stages (actor wider than the critic: wrong
+  // actor outputs whenever the epilogue was slow enough to lose the race, i.e. tanh / swish).  A new ring
+  // reaches the old buffer only when the new chain has no room for one; then the streamer waits for the
+  // producers to leave the old epilogue.
+  const bool ok = ring_end + TC_EBUF_BYTES <= TC_SMEM;
+  if (cx.done_uses > 0u && cx.chain_ok && !ok && (threadIdx.x >> 5) != TC_NPROD / 32)
+    asm volatile("bar.sync 2, %0;" ::"n"(TC_NPROD + 32) : "memory");
+  cx.chain_ok = ok;
+  cx.ebuf_off = ok ? TC_SMEM - TC_EBUF_BYTES : 0u;
 }
 
 __device__ __forceinline__ void tc_chain_forward(TcCtx& cx, const b200ppo_chain& ch, const TcLayer* tl,

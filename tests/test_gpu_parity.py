@@ -338,7 +338,10 @@ def _dbg(eng, which, n):
     dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, M=2, act="relu", clip=None, wd=None),
     dict(O=5, A=1, ah=[64] * 4, ch=[256] * 2, B=96, T=30, M=2, act="tanh", clip=0.5, wd=None),
     dict(O=24, A=5, ah=[48, 40], ch=[72], B=70, T=7, M=2, act="swish", clip=None, wd=1e-3),
-    dict(O=300, A=3, ah=[32], ch=[20, 20], B=40, T=5, M=1, act="relu", clip=None, wd=None)])
+    dict(O=300, A=3, ah=[32], ch=[20, 20], B=40, T=5, M=1, act="relu", clip=None, wd=None),
+    # actor wider than the critic + a slow (tanh) epilogue: the next chain's weight stages used to land on the
+    # previous chain's epilogue buffer (update_tc.cuh tc_chain_setup)
+    dict(O=24, A=3, ah=[48], ch=[32], B=96, T=9, M=2, act="tanh", clip=None, wd=None)])
 @pytest.mark.parametrize("gemm", [0, 1, 2])
 def test_single_update_matches_oracle(dev, cfg, gemm):
     """gemm = 0: fp32 FFMA kernels, 1: tcgen05 3xTF32 (default), 2: tcgen05 plain TF32 (loose)."""

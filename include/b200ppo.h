@@ -415,6 +415,9 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
+/* Dense engine of the fused rollout (b200ppo_rollout_synth): 1 = warp-level tensor-core tiles (mma.sync m16n8k8, *
+ * error-compensated 3xTF32; default), 0 = fp32 FFMA tiles; also B200PPO_ROLLOUT=ffma|mma.  Returns the previous mode. */
+int b200ppo_set_rollout_mode(int mode);
 /* Programmatic dependent launch between the kernels of b200ppo_update (a kernel's prologue overlaps its
  * predecessor's tail; griddepcontrol.wait before the first dependent access).  0 = plain stream order
  * (default), 1 = every launch, 2 = only the small latency-bound kernels (GAE, loss, Adam), 3 = those and the

@@ -11,6 +11,9 @@
 // each thread computes a 2-env x 4-column register tile per layer, and layers with fewer tiles than
 // threads split their k range over the idle threads (dense_tile).  The evaluation rollout
 // (rollout.py:97-148) is the same loop without the transition record and with sticky done flags.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 using namespace b200ppo;
@@ -431,6 +434,258 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_kernel(const RolloutArgs 
 }
 
 // ------------------------------------------------------------------------------------------
+// The same rollout with the Dense layers on the tensor cores: warp-level mma.sync m16n8k8 (TF32 operands, fp32
+// accumulate), error-compensated with the 3-product split (x = hi + lo: lo*hi + hi*lo + hi*hi), so the result
+// keeps fp32-level accuracy.  A tile of TE = 16 envs is exactly one m16 row tile; a layer's 8-column n-tiles
+// go round-robin over the 8 warps.  Why not tcgen05 here: a CTA-wide tcgen05 tile is 128 envs, i.e. 32 CTAs
+// for 4096 envs, and every layer would pay the commit -> mbarrier -> TMEM-load hand-off (~2.5 K cycles in the
+// update kernels) on a chain of 6 dependent layers per step; the warp-level MMA has a ~30-cycle dependent
+// latency and keeps 256 CTAs (2 per SM) busy.  What the tensor path buys over the FFMA tiles above is operand
+// traffic: the FFMA version needs 6 LDS.128 per 32 FMAs (the LSU pipe, not the FMA pipe, was its bound), here
+// a k-step of 1024 MACs takes 4 LDS.32 + 1 LDS.64.
+// Weights are staged once per CTA in FRAGMENT order: for n-tile j and k-step s the 32 lanes' (b0, b1) pairs
+// are 256 contiguous bytes (lane = 4 g + t holds W[8s + t][8j + g], W[8s + t + 4][8j + g]); rows / columns
+// beyond the layer's K / N are zero, so ragged widths need no predicates in the loop.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// floats of one layer's fragment-ordered weights
+__host__ __device__ inline int frag_floats(int K, int N) { return ((K + 7) & ~7) * ((N + 7) & ~7); }
+
+// stage W [K][N] (row-major, global) into fragment order
+__device__ __forceinline__ void stage_frags(const float* __restrict__ W, int K, int N, float2* __restrict__ dst) {
+  const int KS = (K + 7) >> 3, NJ = (N + 7) >> 3;
+  for (int idx = threadIdx.x; idx < NJ * KS * 32; idx += NT) {
+    const int lane = idx & 31, q = idx >> 5, s = q % KS, j = q / KS;
+    const int k = 8 * s + (lane & 3), n = 8 * j + (lane >> 2);
+    float2 v = make_float2(0.0f, 0.0f);
+    if (n < N) {
+      if (k < K) v.x = W[static_cast<size_t>(k) * N + n];
+      if (k + 4 < K) v.y = W[static_cast<size_t>(k + 4) * N + n];
+    }
+    dst[idx] = v;
+  }
+}
+
+// out[e][n] = act(sum_k in[e][k] W[k][n] + bias[n]) for the 16 rows of the tile; `in` columns >= K are finite
+// (zero-initialised padding), `out` columns up to the padded width are written (padding -> act(0) = 0).
+// Two accumulator sets (even / odd k-steps) of three products each: six independent MMA chains per warp.
+__device__ __forceinline__ void mma_layer(const float* __restrict__ in, int ld, int K, const float2* __restrict__ wf,
+                                          const float* __restrict__ bias /*padded, smem; nullptr: none*/, int N,
+                                          float* __restrict__ out, int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int KS = (K + 7) >> 3, NJ = (N + 7) >> 3;
+  const float* r0 = in + g * ld + t;
+  const float* r1 = in + (g + 8) * ld + t;
+  for (int j = warp; j < NJ; j += NT / 32) {
+    float acc[2][3][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[p][q][i] = 0.0f;
+    const float2* wj = wf + static_cast<size_t>(j) * KS * 32 + lane;
+#pragma unroll 2
+    for (int s = 0; s < KS; ++s) {
+      const float x[4] = {r0[8 * s], r1[8 * s], r0[8 * s + 4], r1[8 * s + 4]};
+      const float2 w = wj[s * 32];
+      // split by truncation: the MMA ignores the low 13 mantissa bits of a tf32 operand, so hi is the masked
+      // value (2 instructions per element: LOP3 + FADD; cvt.rna.tf32 is 4 + the FADD) and lo = x - hi is exact
+      // in fp32, itself truncated by the MMA: |error| <= 2^-20 |x|
+      uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        ah[i] = __float_as_uint(x[i]) & 0xFFFFE000u;
+        al[i] = __float_as_uint(x[i] - __uint_as_float(ah[i]));
+      }
+      bh[0] = __float_as_uint(w.x) & 0xFFFFE000u; bl[0] = __float_as_uint(w.x - __uint_as_float(bh[0]));
+      bh[1] = __float_as_uint(w.y) & 0xFFFFE000u; bl[1] = __float_as_uint(w.y - __uint_as_float(bh[1]));
+      const int p = s & 1;
+      mma_tf32_16x8x8(acc[p][0], al, bh);
+      mma_tf32_16x8x8(acc[p][1], ah, bl);
+      mma_tf32_16x8x8(acc[p][2], ah, bh);
+    }
+    const int col = 8 * j + 2 * t;
+    float z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)     // small terms first
+      z[i] = ((acc[0][0][i] + acc[1][0][i]) + (acc[0][1][i] + acc[1][1][i])) + (acc[0][2][i] + acc[1][2][i]);
+    if (bias != nullptr) {
+      const float b0 = bias[col], b1 = bias[col + 1];
+      z[0] += b0; z[1] += b1; z[2] += b0; z[3] += b1;
+    }
+    *reinterpret_cast<float2*>(out + g * ld + col) = make_float2(act_fwd(z[0], act), act_fwd(z[1], act));
+    *reinterpret_cast<float2*>(out + (g + 8) * ld + col) = make_float2(act_fwd(z[2], act), act_fwd(z[3], act));
+  }
+}
+
+static_assert(TE == 16, "the tensor-core rollout maps a CTA's env tile onto one m16 MMA row tile");
+
+__global__ void __launch_bounds__(NT, 2) rollout_synth_mma_kernel(const RolloutArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.O, A = a.A, ld = a.ld;
+  const int env0 = blockIdx.x * TE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const b200ppo_chain& ch = a.plan.actor;
+  const int L = ch.n_layers;
+  float* sp = smem;
+  float* bufA = sp; sp += TE * ld;
+  float* bufB = sp; sp += TE * ld;
+  float* bufX = sp; sp += TE * ld;      // env-step input tile, resident across steps: [obs | action] per env row
+  float* raw_s = sp; sp += TE * A;
+  float* llt_s = sp; sp += TE * A;
+  float* mean_s = sp; sp += O;
+  float* std_s = sp; sp += O;
+  int32_t* cnt_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  uint32_t* term_s = reinterpret_cast<uint32_t*>(sp); sp += TE;
+  uint32_t* kb_s = reinterpret_cast<uint32_t*>(sp); sp += 2 * TE;
+  int32_t* done_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  sp = smem + ((sp - smem + 3) & ~3);
+  __shared__ int woff_s[B200PPO_MAX_LAYERS + 1], boff_s[B200PPO_MAX_LAYERS];
+  // fragment-ordered weights and padded biases of every actor layer, then the env's [Wo; Wa]
+  float* wbase = sp;
+  {
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+      if (threadIdx.x == 0) woff_s[l] = off;
+      off += frag_floats(ch.dims[l], ch.dims[l + 1]);
+    }
+    if (threadIdx.x == 0) woff_s[L] = off;
+    off += frag_floats(O + A, O);
+    for (int l = 0; l < L; ++l) {
+      if (threadIdx.x == 0) boff_s[l] = off;
+      off += (ch.dims[l + 1] + 7) & ~7;
+    }
+  }
+  for (int i = threadIdx.x; i < 3 * TE * ld; i += NT) smem[i] = 0.0f;      // padding columns stay zero
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    stage_frags(a.params + ch.w_off[l], ch.dims[l], ch.dims[l + 1], reinterpret_cast<float2*>(wbase + woff_s[l]));
+    const int N = ch.dims[l + 1], Np = (N + 7) & ~7;
+    for (int i = threadIdx.x; i < Np; i += NT) wbase[boff_s[l] + i] = i < N ? a.params[ch.b_off[l] + i] : 0.0f;
+  }
+  stage_frags(a.Wenv, O + A, O, reinterpret_cast<float2*>(wbase + woff_s[L]));
+  for (int i = threadIdx.x; i < O; i += NT) {
+    mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
+    std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
+  }
+  for (int e = warp; e < TE; e += NT / 32)
+    for (int o = lane; o < O; o += 32)
+      bufX[e * ld + o] = (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f;
+  if (threadIdx.x < TE) {
+    const bool ok = env0 + threadIdx.x < a.B;
+    cnt_s[threadIdx.x] = ok ? a.env_counter[env0 + threadIdx.x] : 0;
+    term_s[threadIdx.x] = ok ? a.env_term[env0 + threadIdx.x] : 0u;
+  }
+  const Key stream_key{a.rng_state[0], a.rng_state[1]};
+  const uint32_t count0 = a.rng_state[2];
+  const Key reset_key{a.iter_keys[0], a.iter_keys[1]};
+  __syncthreads();
+
+  for (int t = 0; t < a.T; ++t) {
+    // (1) record the raw observation, normalise into bufA  (rollout.py:23; normalizer.py:78-80)
+    const size_t row0 = static_cast<size_t>(t) * a.B + env0;
+    for (int e = warp; e < TE; e += NT / 32)
+      for (int o = lane; o < O; o += 32) {
+        const float x = bufX[e * ld + o];
+        if (env0 + e < a.B) a.obs[(row0 + e) * O + o] = x;
+        bufA[e * ld + o] = a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x;
+      }
+    __syncthreads();
+    // (2) actor MLP: activations ping-pong between bufA and bufB
+    float* cur = bufA;
+    float* nxt = bufB;
+    for (int l = 0; l < L; ++l) {
+      mma_layer(cur, ld, ch.dims[l], reinterpret_cast<const float2*>(wbase + woff_s[l]), wbase + boff_s[l],
+                ch.dims[l + 1], nxt, l + 1 < L ? ch.act : B200PPO_ACT_NONE);
+      __syncthreads();
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    float* y = cur;
+    // (3) sampler (count = count0 + 2t; the entropy draw does not influence the rollout): action -> env input tile
+    const Key k_sample = fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
+    for (int i = threadIdx.x; i < TE * A; i += NT) {
+      const int e = i / A, d = i - e * A;
+      const uint32_t j = static_cast<uint32_t>(env0 + e) * static_cast<uint32_t>(A) + d;
+      const SamplerOut s = sampler_elem(y[e * ld + d], y[e * ld + A + d], a.plan.min_std,
+                                        a.plan.std_scale, a.plan.entropy_weight, 0, 0.0f, k_sample,
+                                        k_sample, j, false);
+      raw_s[i] = s.raw;
+      bufX[e * ld + O + d] = s.action;
+      llt_s[i] = s.llterm;
+      if (env0 + e < a.B) {
+        a.raw_action[row0 * A + i] = s.raw;
+        a.action[row0 * A + i] = s.action;
+      }
+    }
+    __syncthreads();
+    // (4) episode bookkeeping (integer-exact) and reset scalars, beside the env-step GEMM
+    if (threadIdx.x < TE) {
+      const int e = threadIdx.x;
+      const int ge = env0 + e;
+      float ll = 0.0f;
+      for (int d = 0; d < A; ++d) ll += llt_s[e * A + d];
+      const int32_t c = cnt_s[e] + 1;
+      const uint32_t ts = term_s[e] * 1664525u + 1013904223u;
+      const bool terminated = (ts >> 16) < static_cast<uint32_t>(a.term_thresh16);
+      const bool truncated = c >= a.max_len;
+      const bool dn = terminated || truncated;
+      if (ge < a.B) {
+        a.loglik[row0 + e] = ll;
+        a.done[row0 + e] = dn ? 1 : 0;
+        a.trunc[row0 + e] = truncated ? 1 : 0;
+      }
+      done_s[e] = dn ? 1 : 0;
+      if (dn) {
+        const Key k = split_at(reset_key, static_cast<uint32_t>(t) * static_cast<uint32_t>(a.B) +
+                                              static_cast<uint32_t>(ge));
+        const ResetScalars r = synth_reset_scalars(k, a.max_len);
+        cnt_s[e] = r.counter;
+        term_s[e] = r.term;
+        kb_s[2 * e] = r.k_base.a;
+        kb_s[2 * e + 1] = r.k_base.b;
+      } else {
+        cnt_s[e] = c;
+        term_s[e] = ts;
+      }
+    }
+    // (5) env step: obs' = tanh([obs, action] @ [Wo; Wa]) into the tile the actor no longer needs
+    float* yo = nxt;
+    mma_layer(bufX, ld, O + A, reinterpret_cast<const float2*>(wbase + woff_s[L]), nullptr, O, yo, B200PPO_ACT_TANH);
+    __syncthreads();
+    // (6) reward = -mean(obs'^2); next_obs[-1] is the pre-reset observation; tree_where(done, reset, next)
+    for (int e = warp; e < TE; e += NT / 32) {
+      const bool dn = done_s[e] != 0;
+      const Key kb{kb_s[2 * e], kb_s[2 * e + 1]};
+      float sq = 0.0f;
+      for (int o = lane; o < O; o += 32) {
+        const float v = yo[e * ld + o];
+        sq = fmaf(v, v, sq);
+        if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0 + e) * O + o] = v;
+        bufX[e * ld + o] = dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v;
+      }
+      sq = warp_sum(sq);
+      if (lane == 0 && env0 + e < a.B) a.reward[row0 + e] = -(sq / static_cast<float>(O));
+    }
+    __syncthreads();
+  }
+  for (int e = warp; e < TE; e += NT / 32)
+    for (int o = lane; o < O; o += 32)
+      if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0 + e) * O + o] = bufX[e * ld + o];
+  if (threadIdx.x < TE && env0 + threadIdx.x < a.B) {
+    a.env_counter[env0 + threadIdx.x] = cnt_s[threadIdx.x];
+    a.env_term[env0 + threadIdx.x] = term_s[threadIdx.x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // persistent fused evaluation rollout (rollout.py:97-148): no transition record, no env reset;
 // done is sticky, the reward is accumulated while the env was alive BEFORE the step, lifespan
 // counts the steps that did not end in done.  Once every env of the tile is done nothing
@@ -661,6 +916,16 @@ int max_dim(const b200ppo_chain& c) {
   return m;
 }
 
+// Dense engine of the fused rollout: 1 = mma.sync 3xTF32 tiles (default), 0 = fp32 FFMA tiles.  B200PPO_ROLLOUT=ffma|mma
+int g_rollout_mode = -1;
+int rollout_mode() {
+  if (g_rollout_mode < 0) {
+    const char* e = std::getenv("B200PPO_ROLLOUT");
+    g_rollout_mode = (e && !std::strcmp(e, "ffma")) ? 0 : 1;
+  }
+  return g_rollout_mode;
+}
+
 int check_plan(const b200ppo_plan* p) {
   if (!p) return B200PPO_EINVAL;
   if (p->obs_dim <= 0 || p->act_dim <= 0) return B200PPO_EINVAL;
@@ -744,6 +1009,21 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   a.done = done; a.trunc = truncated; a.next_obs_last = next_obs_last;
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
+  if (rollout_mode() == 1) {
+    // tensor-core tiles (mma.sync 3xTF32): fragment-ordered weights of every layer resident in shared memory
+    a.ld = ((md + 7) & ~7) + 4;          // = 4 (mod 8): the A-fragment loads (lane = 4 g + t -> g * ld + t) hit 32 distinct banks
+    int64_t fl = 3ll * TE * a.ld + 2ll * TE * A + 2ll * O + 5ll * TE + 8;
+    for (int l = 0; l < plan->actor.n_layers; ++l)
+      fl += frag_floats(plan->actor.dims[l], plan->actor.dims[l + 1]) + ((plan->actor.dims[l + 1] + 7) & ~7);
+    fl += frag_floats(O + A, O);
+    if (4 * fl <= SMEM_LIMIT - 2048) {     // the kernel also has ~1 KB of static shared memory
+      cudaError_t e = cudaFuncSetAttribute(rollout_synth_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(4 * fl));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      rollout_synth_mma_kernel<<<cdiv(B, TE), NT, 4 * fl, static_cast<cudaStream_t>(stream)>>>(a);
+      B200PPO_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   a.ld = tile_ld(md);
   fill_split(plan->actor, a.ld, a.split);
   a.split[B200PPO_MAX_LAYERS] = static_cast<int8_t>(ksplit_log2(O + A, O, a.ld));
@@ -784,6 +1064,12 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   if (rc) return rc;
   B200PPO_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int b200ppo_set_rollout_mode(int mode) {
+  const int prev = rollout_mode();
+  if (mode == 0 || mode == 1) g_rollout_mode = mode;
+  return prev;
 }
 
 extern "C" int b200ppo_eval_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,

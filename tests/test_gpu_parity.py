@@ -293,10 +293,21 @@ def test_env_reset_matches_oracle(dev):
 @pytest.mark.parametrize("cfg", [dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=200, T=40, max_len=24, thr=1500),
                                   dict(O=5, A=1, ah=[32, 32], ch=[32], B=64, T=30, max_len=16, thr=3000),
                                   dict(O=12, A=3, ah=[48], ch=[16, 16], B=31, T=9, max_len=8, thr=0),
+                                  dict(O=21, A=5, ah=[100, 37, 64], ch=[16], B=50, T=12, max_len=8, thr=1500, act="tanh"),
                                   # tiles too wide for the k-split scratch tile: the unsplit path
                                   dict(O=900, A=4, ah=[32], ch=[16], B=20, T=5, max_len=8, thr=1500)])
-def test_fused_rollout_matches_oracle(dev, cfg):
-    nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 11)
+@pytest.mark.parametrize("engine", [1, 0])
+def test_fused_rollout_matches_oracle(dev, cfg, engine):
+    """engine = 1: warp-level tensor-core tiles (mma.sync, 3xTF32; default), 0: fp32 FFMA tiles."""
+    prev = _lib.load().b200ppo_set_rollout_mode(engine)
+    try:
+        _fused_rollout(dev, cfg)
+    finally:
+        _lib.load().b200ppo_set_rollout_mode(prev)
+
+
+def _fused_rollout(dev, cfg):
+    nets, onet = _pair(cfg["O"], cfg["A"], cfg["ah"], cfg["ch"], 11, cfg.get("act", "relu"))
     env = SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
     oe = oenv.SyntheticEnv(cfg["O"], cfg["A"], cfg["max_len"], cfg["thr"])
     ts = ppo.new_training_state(env, nets, cfg["B"], 17)

@@ -415,9 +415,23 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
-/* Dense engine of the fused rollout (b200ppo_rollout_synth): 1 = warp-level tensor-core tiles (mma.sync m16n8k8, *
- * error-compensated 3xTF32; default), 0 = fp32 FFMA tiles; also B200PPO_ROLLOUT=ffma|mma.  Returns the previous mode. */
+/* Dense engine of the rollout (b200ppo_rollout_synth / _ws): 1 = tensor cores (default: the fused kernel on warp-level *
+ * mma.sync m16n8k8 tiles, error-compensated 3xTF32, while the weights fit an SM's shared memory; the batched per-step  *
+ * tcgen05 GEMM path of b200ppo_rollout_synth_ws beyond that), 0 = fused kernel on fp32 FFMA tiles, 2 = batched path     *
+ * whenever a workspace is passed; also B200PPO_ROLLOUT=ffma|mma|wide.  Returns the previous mode.                       */
 int b200ppo_set_rollout_mode(int mode);
+/* b200ppo_rollout_synth with a caller-owned scratch buffer (b200ppo_rollout_synth_workspace_bytes(plan, B) bytes; 0 =  *
+ * this plan keeps its weights resident in the fused kernel and needs none).  With a workspace, networks / envs whose    *
+ * weights do not fit shared memory (e.g. 768-wide dict-observation encoders) run every Dense layer of a step as one      *
+ * tcgen05 tile GEMM over all B envs instead of re-streaming the weights per 16-env tile; same results contract.          */
+int64_t b200ppo_rollout_synth_workspace_bytes(const b200ppo_plan* plan, int32_t B);
+int b200ppo_rollout_synth_num_launches(const b200ppo_plan* plan, int32_t T, int32_t B, int32_t with_ws);
+int b200ppo_rollout_synth_ws(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                             const float* params, const float* norm_mean, const float* norm_std,
+                             const uint32_t* rng_state, const uint32_t* iter_keys, int32_t T, int32_t B,
+                             float* env_obs, int32_t* env_counter, uint32_t* env_term, float* obs,
+                             float* raw_action, float* action, float* loglik, float* reward, uint8_t* done,
+                             uint8_t* truncated, float* next_obs_last, void* ws, int64_t ws_bytes);
 /* Programmatic dependent launch between the kernels of b200ppo_update (a kernel's prologue overlaps its
  * predecessor's tail; griddepcontrol.wait before the first dependent access).  0 = plain stream order
  * (default), 1 = every launch, 2 = only the small latency-bound kernels (GAE, loss, Adam), 3 = those and the

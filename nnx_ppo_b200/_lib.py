@@ -91,6 +91,10 @@ SYMBOLS = {
     "b200ppo_split_rows": (C.c_int, [_vp, _vp, _i32, _u32, _vp]),
     "b200ppo_rollout_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200ppo_rollout_synth_ws": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "b200ppo_rollout_synth_workspace_bytes": (_i64, [_PP, _i32]),
+    "b200ppo_rollout_synth_num_launches": (C.c_int, [_PP, _i32, _i32, _i32]),
     "b200ppo_eval_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                                      _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_update_workspace_bytes": (_i64, [_PP, _i32, _i32]),

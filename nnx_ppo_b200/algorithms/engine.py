@@ -384,12 +384,15 @@ class PPOEngine:
             net.normalizer.prepare(s); n += 1
         mean_p, std_p = net.norm_ptrs()
         es = self.env.c_struct(self.dev)
-        _lib.check(lib.b200ppo_rollout_synth(
+        ws_p, ws_n = net.rollout_workspace(B)
+        _lib.check(lib.b200ppo_rollout_synth_ws(
             s, net.plan, es, net.arena.data_ptr(), mean_p, std_p, net.counters.data_ptr(),
             self.iter_keys.data_ptr(), T, B, env_state.obs.data_ptr(), env_state.step_counter.data_ptr(),
             env_state.term_state.data_ptr(), self.obs.data_ptr(), self.raw_action.data_ptr(),
             self.action.data_ptr(), self.loglik.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
-            self.trunc.data_ptr(), self.next_obs_last.data_ptr()), "rollout_synth"); n += 1
+            self.trunc.data_ptr(), self.next_obs_last.data_ptr(), ws_p, ws_n), "rollout_synth")
+        # one fused launch, or the batched per-step sequence for networks too wide for shared memory
+        n += int(lib.b200ppo_rollout_synth_num_launches(net.plan, T, B, 1 if ws_n else 0))
         return n
 
     def enable_values(self, net_metrics: bool = False) -> None:

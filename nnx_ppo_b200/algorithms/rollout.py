@@ -83,11 +83,12 @@ def unroll_env(env, env_state, networks, network_state, unroll_length: int, rng_
         new_env = type(env_state)(env_state.obs.clone(), env_state.step_counter.clone(),
                                   env_state.term_state.clone(), env_state.reward, env_state.done,
                                   dict(env_state.info), dict(env_state.metrics))
-        _lib.check(lib.b200ppo_rollout_synth(
+        ws_p, ws_n = net.rollout_workspace(B)
+        _lib.check(lib.b200ppo_rollout_synth_ws(
             s, net.plan, env.c_struct(dev), net.arena.data_ptr(), mean_p, std_p, net.counters.data_ptr(),
             keys.data_ptr(), T, B, new_env.obs.data_ptr(), new_env.step_counter.data_ptr(),
             new_env.term_state.data_ptr(), obs.data_ptr(), raw.data_ptr(), act.data_ptr(), ll.data_ptr(),
-            rew.data_ptr(), done.data_ptr(), trunc.data_ptr(), nol.data_ptr()), "rollout_synth")
+            rew.data_ptr(), done.data_ptr(), trunc.data_ptr(), nol.data_ptr(), ws_p, ws_n), "rollout_synth")
         net.advance_rng(2 * T)
         net.sync_counters_to_device()
         # value estimates of the rollout (metrics only, ppo.py never trains on them): K1 in

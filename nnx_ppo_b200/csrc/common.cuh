@@ -200,6 +200,75 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+struct SamplerOut {
+  float raw, action, llterm, regterm;
+};
+
+// NormalTanhSampler for one (row, action-dim) element — sampling_layers.py:88-147.
+__device__ __forceinline__ SamplerOut sampler_elem(float mu, float rho, float min_std, float std_scale,
+                                                   float entropy_weight, int mode, float raw_in,
+                                                   Key k_sample, Key k_ent, uint32_t j, bool want_reg) {
+  SamplerOut o;
+  const float sigma = (softplus_f(rho) + min_std) * std_scale;
+  float z;
+  if (mode & 1) {
+    z = raw_in;                                   // LOSS_REPLAY: stored raw action
+  } else if (mode & 2) {
+    z = mu;                                       // deterministic
+  } else {
+    const float eps = bits_to_normal(random_bits_at(k_sample, j));
+    z = __fadd_rn(mu, __fmul_rn(sigma, eps));
+  }
+  o.raw = z;
+  o.action = tanhf(z);
+  const float q = (z - mu) / sigma;
+  o.llterm = -0.5f * q * q - (B200PPO_HALF_LOG_2PI + logf(sigma)) - log_det_jac(z);
+  o.regterm = 0.0f;
+  if (want_reg) {
+    const float eps2 = bits_to_normal(random_bits_at(k_ent, j));
+    const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
+    o.regterm = -entropy_weight * (0.5f + B200PPO_HALF_LOG_2PI + logf(sigma) + log_det_jac(zp));
+  }
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// reset of the synthetic env for one env (see oracle/env.py for the definition)
+// ------------------------------------------------------------------------------------------
+struct ResetScalars {
+  Key k_base;
+  int32_t counter;
+  uint32_t term;
+};
+__device__ __forceinline__ ResetScalars synth_reset_scalars(Key key, int max_len) {
+  ResetScalars r;
+  r.k_base = split_at(key, 0u);
+  const Key k_cnt = split_at(key, 1u);
+  r.counter = randint_scalar(k_cnt, static_cast<uint32_t>(max_len / 2));
+  r.term = k_cnt.a ^ k_cnt.b;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched ("wide") rollout: the per-step launch sequence for networks / envs whose weights do not fit an SM's
+// shared memory (csrc/recurrent_tc.cu, rollout_wide).  Shared between the two translation units.
+// ------------------------------------------------------------------------------------------
+struct RolloutWideArgs {
+  const b200ppo_plan* plan;
+  const float* Wenv;          // [(O + A)][O]
+  int max_len, term_thresh16;
+  const float* params; const float* mean; const float* std;
+  const uint32_t* rng_state; const uint32_t* iter_keys;
+  int T, B;
+  float* env_obs; int32_t* env_counter; uint32_t* env_term;
+  float* obs; float* raw_action; float* action; float* loglik; float* reward;
+  uint8_t* done; uint8_t* trunc; float* next_obs_last;
+  float* ws;
+};
+int64_t rollout_wide_ws_floats(const b200ppo_plan* plan, int B);
+int rollout_wide_num_launches(const b200ppo_plan* plan, int T);
+int rollout_wide(cudaStream_t s, const RolloutWideArgs& a);
+
 static inline int cdiv(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 }  // namespace b200ppo

@@ -873,7 +873,199 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched ("wide") rollout on the synthetic env: rollout.single_transition / unroll_env (rollout.py:11-73) as a
+// per-step launch sequence for networks whose weights do not fit an SM's shared memory (BASELINE configs[3]:
+// 768-wide block-diagonal encoder layers and a 789 x 768 env matrix).  The fused kernel (csrc/rollout.cu) keeps a
+// 16-env tile per CTA and re-streams every weight from L2 per tile and step (2.7 GB per step at 8192 envs:
+// 1.26 ms per step); here every Dense layer of a step is ONE tcgen05 tile GEMM over all B envs (128-env row
+// tiles: the weights are read 64 times per step instead of 512), the element-wise parts are three small kernels:
+//   init (once)   X[:, :O] <- env obs; obs[0] <- env obs
+//   per step      L layer GEMMs (normalise / activation on load, bias in the epilogue)
+//                 sampler: y -> raw action, action (record + the env input tile X[:, O:]), log-likelihood
+//                 env GEMM: obs' = tanh([obs | action] [Wo; Wa])
+//                 bookkeeping: counters, done / truncation, reward, next_obs[-1], reset select -> X, obs[t + 1]
+// Same arithmetic per element as the fused kernels (sampler_elem / synth_reset_scalars in common.cuh), integer
+// bookkeeping bit-identical.
+// ------------------------------------------------------------------------------------------
+struct WideLayout {
+  int ldx, ldz, ldo;
+  size_t x, za, zb, zenv, ynext, total;
+};
+WideLayout wide_layout(const b200ppo_plan& p, int B) {
+  WideLayout L;
+  const int O = p.obs_dim, A = p.act_dim;
+  int mx = 0;
+  for (int l = 0; l < p.actor.n_layers; ++l) mx = p.actor.dims[l + 1] > mx ? p.actor.dims[l + 1] : mx;
+  L.ldx = (O + A + 3) & ~3;
+  L.ldz = (mx + 3) & ~3;
+  L.ldo = (O + 3) & ~3;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
+  L.x = take(static_cast<size_t>(B) * L.ldx);
+  L.za = take(static_cast<size_t>(B) * L.ldz);
+  L.zb = take(static_cast<size_t>(B) * L.ldz);
+  L.zenv = take(static_cast<size_t>(B) * L.ldo);
+  L.ynext = take(static_cast<size_t>(B) * L.ldo);
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(256) wide_init_kernel(const float* __restrict__ env_obs, int B, int O, float* __restrict__ X,
+                                                        int ldx, float* __restrict__ obs0) {
+  const size_t n = static_cast<size_t>(B) * O;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t e = i / O, o = i - e * O;
+    const float v = env_obs[i];
+    X[e * ldx + o] = v;
+    obs0[i] = v;
+  }
+}
+
+// one thread per (env, action dim): count = count0 + 2 t (the entropy draw does not influence the rollout)
+__global__ void __launch_bounds__(256) wide_sampler_kernel(const float* __restrict__ y, int ldy, int B, int A, float min_std,
+                                                           float std_scale, const uint32_t* __restrict__ rng_state, uint32_t t,
+                                                           float* __restrict__ raw, float* __restrict__ action,
+                                                           float* __restrict__ X, int ldx, int O, float* __restrict__ llterm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * A) return;
+  const int e = i / A, d = i - e * A;
+  const Key stream_key{rng_state[0], rng_state[1]};
+  const Key k_sample = fold_in(stream_key, rng_state[2] + 2u * t);
+  const SamplerOut s = sampler_elem(y[static_cast<size_t>(e) * ldy + d], y[static_cast<size_t>(e) * ldy + A + d], min_std, std_scale,
+                                    0.0f, 0, 0.0f, k_sample, k_sample, static_cast<uint32_t>(i), false);
+  raw[i] = s.raw;
+  action[i] = s.action;
+  X[static_cast<size_t>(e) * ldx + O + d] = s.action;
+  llterm[i] = s.llterm;
+}
+
+struct WideBookArgs {
+  int B, O, A, T, t, max_len, term_thresh16, ldx, ldo;
+  const uint32_t* iter_keys;
+  const float* ynext; const float* llterm;
+  float* X; float* obs_next;            // obs[t + 1] (nullptr at the last step)
+  float* loglik; float* reward; uint8_t* done; uint8_t* trunc;     // row t of the record
+  float* next_obs_last; float* env_obs;                            // written at the last step only
+  int32_t* env_counter; uint32_t* env_term;                        // advanced in place every step
+};
+// one warp per env (rollout.cu steps (4) and (6))
+__global__ void __launch_bounds__(256) wide_book_kernel(const WideBookArgs a) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= a.B) return;
+  int dn = 0;
+  uint32_t kba = 0u, kbb = 0u;
+  if (lane == 0) {
+    float ll = 0.0f;
+    for (int d = 0; d < a.A; ++d) ll += a.llterm[static_cast<size_t>(e) * a.A + d];
+    const int32_t c = a.env_counter[e] + 1;
+    const uint32_t ts = a.env_term[e] * 1664525u + 1013904223u;
+    const bool terminated = (ts >> 16) < static_cast<uint32_t>(a.term_thresh16);
+    const bool truncated = c >= a.max_len;
+    dn = (terminated || truncated) ? 1 : 0;
+    a.loglik[e] = ll;
+    a.done[e] = dn ? 1 : 0;
+    a.trunc[e] = truncated ? 1 : 0;
+    if (dn) {
+      const Key reset_key{a.iter_keys[0], a.iter_keys[1]};
+      const Key k = split_at(reset_key, static_cast<uint32_t>(a.t) * static_cast<uint32_t>(a.B) + static_cast<uint32_t>(e));
+      const ResetScalars r = synth_reset_scalars(k, a.max_len);
+      a.env_counter[e] = r.counter;
+      a.env_term[e] = r.term;
+      kba = r.k_base.a; kbb = r.k_base.b;
+    } else {
+      a.env_counter[e] = c;
+      a.env_term[e] = ts;
+    }
+  }
+  dn = __shfl_sync(0xffffffffu, dn, 0);
+  kba = __shfl_sync(0xffffffffu, kba, 0);
+  kbb = __shfl_sync(0xffffffffu, kbb, 0);
+  const Key kb{kba, kbb};
+  const bool last = a.t == a.T - 1;
+  float sq = 0.0f;
+  for (int o = lane; o < a.O; o += 32) {
+    const float v = a.ynext[static_cast<size_t>(e) * a.ldo + o];
+    sq = fmaf(v, v, sq);
+    if (last) a.next_obs_last[static_cast<size_t>(e) * a.O + o] = v;
+    const float nv = dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v;
+    a.X[static_cast<size_t>(e) * a.ldx + o] = nv;
+    if (a.obs_next != nullptr) a.obs_next[static_cast<size_t>(e) * a.O + o] = nv;
+    if (last) a.env_obs[static_cast<size_t>(e) * a.O + o] = nv;
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) a.reward[e] = -(sq / static_cast<float>(a.O));
+}
+
 }  // namespace
+
+namespace b200ppo {
+int64_t rollout_wide_ws_floats(const b200ppo_plan* plan, int B) {
+  return static_cast<int64_t>(wide_layout(*plan, B).total + static_cast<size_t>(B) * plan->act_dim + 64);
+}
+int rollout_wide_num_launches(const b200ppo_plan* plan, int T) { return 1 + T * (plan->actor.n_layers + 3); }
+
+int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
+  int rc = set_attrs_tc();
+  if (rc) return rc;
+  const b200ppo_plan& p = *a.plan;
+  const int O = p.obs_dim, A = p.act_dim, B = a.B, T = a.T, L = p.actor.n_layers;
+  const WideLayout W = wide_layout(p, B);
+  float* X = a.ws + W.x;
+  float* zbuf[2] = {a.ws + W.za, a.ws + W.zb};
+  float* zenv = a.ws + W.zenv;
+  float* ynext = a.ws + W.ynext;
+  float* llterm = a.ws + W.total;
+  const int row_tiles = cdiv(B, RM);
+  auto n_tile_for = [&](int N) { return row_tiles * cdiv(N, 256) >= b200ppo_num_sms() ? 256 : 128; };
+  wide_init_kernel<<<cdiv(static_cast<int64_t>(B) * O, 256 * 8), 256, 0, s>>>(a.env_obs, B, O, X, W.ldx, a.obs);
+  B200PPO_LAUNCH_CHECK();
+  for (int t = 0; t < T; ++t) {
+    const size_t row0 = static_cast<size_t>(t) * B;
+    const float* in = X;
+    int ldin = W.ldx;
+    for (int l = 0; l < L; ++l) {
+      const int K = p.actor.dims[l], N = p.actor.dims[l + 1];
+      GemmArgs g = gemm_defaults();
+      g.A = in; g.lda = ldin; g.M = B; g.K = K;
+      if (l == 0) {
+        if (p.normalize) { g.a_mean = a.mean; g.a_std = a.std; }
+      } else {
+        g.act_a = p.actor.act;
+      }
+      g.B = a.params + p.actor.w_off[l]; g.ldb = N;
+      g.bias = a.params + p.actor.b_off[l];
+      g.C = zbuf[l & 1]; g.ldc = W.ldz;
+      rc = launch_gemm(s, g, N, 1, n_tile_for(N));
+      if (rc) return rc;
+      in = zbuf[l & 1];
+      ldin = W.ldz;
+    }
+    wide_sampler_kernel<<<cdiv(static_cast<int64_t>(B) * A, 256), 256, 0, s>>>(
+        in, ldin, B, A, p.min_std, p.std_scale, a.rng_state, static_cast<uint32_t>(t), a.raw_action + row0 * A,
+        a.action + row0 * A, X, W.ldx, O, llterm);
+    B200PPO_LAUNCH_CHECK();
+    {
+      GemmArgs g = gemm_defaults();
+      g.A = X; g.lda = W.ldx; g.M = B; g.K = O + A;
+      g.B = a.Wenv; g.ldb = O;
+      g.C = zenv; g.ldc = W.ldo;
+      g.C2 = ynext; g.ldc2 = W.ldo; g.act_c2 = B200PPO_ACT_TANH;
+      rc = launch_gemm(s, g, O, 1, n_tile_for(O));
+      if (rc) return rc;
+    }
+    WideBookArgs b;
+    b.B = B; b.O = O; b.A = A; b.T = T; b.t = t; b.max_len = a.max_len; b.term_thresh16 = a.term_thresh16;
+    b.ldx = W.ldx; b.ldo = W.ldo; b.iter_keys = a.iter_keys; b.ynext = ynext; b.llterm = llterm; b.X = X;
+    b.obs_next = t + 1 < T ? a.obs + (row0 + B) * O : nullptr;
+    b.loglik = a.loglik + row0; b.reward = a.reward + row0; b.done = a.done + row0; b.trunc = a.trunc + row0;
+    b.next_obs_last = a.next_obs_last; b.env_obs = a.env_obs; b.env_counter = a.env_counter; b.env_term = a.env_term;
+    wide_book_kernel<<<cdiv(B, 8), 256, 0, s>>>(b);
+    B200PPO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+}  // namespace b200ppo
 
 extern "C" int b200ppo_lstm_set_persistent(int on) {
   const int prev = g_seq_persist < 0 ? -1 : g_seq_persist;

@@ -176,55 +176,6 @@ __device__ __forceinline__ float* run_chain(const b200ppo_chain& ch, const float
   return cur;
 }
 
-struct SamplerOut {
-  float raw, action, llterm, regterm;
-};
-
-// NormalTanhSampler for one (row, action-dim) element — sampling_layers.py:88-147.
-__device__ __forceinline__ SamplerOut sampler_elem(float mu, float rho, float min_std, float std_scale,
-                                                   float entropy_weight, int mode, float raw_in,
-                                                   Key k_sample, Key k_ent, uint32_t j, bool want_reg) {
-  SamplerOut o;
-  const float sigma = (softplus_f(rho) + min_std) * std_scale;
-  float z;
-  if (mode & 1) {
-    z = raw_in;                                   // LOSS_REPLAY: stored raw action
-  } else if (mode & 2) {
-    z = mu;                                       // deterministic
-  } else {
-    const float eps = bits_to_normal(random_bits_at(k_sample, j));
-    z = __fadd_rn(mu, __fmul_rn(sigma, eps));
-  }
-  o.raw = z;
-  o.action = tanhf(z);
-  const float q = (z - mu) / sigma;
-  o.llterm = -0.5f * q * q - (B200PPO_HALF_LOG_2PI + logf(sigma)) - log_det_jac(z);
-  o.regterm = 0.0f;
-  if (want_reg) {
-    const float eps2 = bits_to_normal(random_bits_at(k_ent, j));
-    const float zp = __fadd_rn(mu, __fmul_rn(sigma, eps2));
-    o.regterm = -entropy_weight * (0.5f + B200PPO_HALF_LOG_2PI + logf(sigma) + log_det_jac(zp));
-  }
-  return o;
-}
-
-// ------------------------------------------------------------------------------------------
-// reset of the synthetic env for one env (see oracle/env.py for the definition)
-// ------------------------------------------------------------------------------------------
-struct ResetScalars {
-  Key k_base;
-  int32_t counter;
-  uint32_t term;
-};
-__device__ __forceinline__ ResetScalars synth_reset_scalars(Key key, int max_len) {
-  ResetScalars r;
-  r.k_base = split_at(key, 0u);
-  const Key k_cnt = split_at(key, 1u);
-  r.counter = randint_scalar(k_cnt, static_cast<uint32_t>(max_len / 2));
-  r.term = k_cnt.a ^ k_cnt.b;
-  return r;
-}
-
 __global__ void synth_init_keys_kernel(Key k, int B, uint32_t* __restrict__ keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
@@ -916,12 +867,13 @@ int max_dim(const b200ppo_chain& c) {
   return m;
 }
 
-// Dense engine of the fused rollout: 1 = mma.sync 3xTF32 tiles (default), 0 = fp32 FFMA tiles.  B200PPO_ROLLOUT=ffma|mma
+// Dense engine of the rollout: 1 = tensor cores (default; include/b200ppo.h b200ppo_set_rollout_mode), 0 = fp32 FFMA tiles,
+// 2 = the batched per-step path whenever a workspace is passed.  B200PPO_ROLLOUT=ffma|mma|wide
 int g_rollout_mode = -1;
 int rollout_mode() {
   if (g_rollout_mode < 0) {
     const char* e = std::getenv("B200PPO_ROLLOUT");
-    g_rollout_mode = (e && !std::strcmp(e, "ffma")) ? 0 : 1;
+    g_rollout_mode = (e && !std::strcmp(e, "ffma")) ? 0 : ((e && !std::strcmp(e, "wide")) ? 2 : 1);
   }
   return g_rollout_mode;
 }
@@ -981,13 +933,28 @@ extern "C" int b200ppo_synth_reset(void* stream, const b200ppo_synth_env* env, c
   return 0;
 }
 
-extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+namespace {
+// weights of the whole actor chain + the env matrix resident in one SM's shared memory?  (fused kernels: yes ->
+// every weight is read once per CTA; no -> every CTA re-streams them from L2 on every step)
+bool fused_weights_resident(const b200ppo_plan* plan) {
+  const int O = plan->obs_dim, A = plan->act_dim;
+  int64_t w = static_cast<int64_t>(O + A) * O;
+  for (int l = 0; l < plan->actor.n_layers; ++l) w += static_cast<int64_t>(plan->actor.dims[l]) * plan->actor.dims[l + 1];
+  return 4 * w <= SMEM_LIMIT - 48 * 1024;
+}
+// batched (per-step tcgen05 GEMM) path: forced (mode 2) or chosen when the fused kernels would stream weights
+bool wide_preferred(const b200ppo_plan* plan, int B) {
+  if (rollout_mode() == 2) return true;
+  return rollout_mode() == 1 && !fused_weights_resident(plan) && B >= 1024;
+}
+
+int rollout_synth_impl(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
                                      const float* params, const float* norm_mean, const float* norm_std,
                                      const uint32_t* rng_state, const uint32_t* iter_keys, int32_t T,
                                      int32_t B, float* env_obs, int32_t* env_counter, uint32_t* env_term,
                                      float* obs, float* raw_action, float* action, float* loglik,
                                      float* reward, uint8_t* done, uint8_t* truncated,
-                                     float* next_obs_last) {
+                                     float* next_obs_last, void* ws, int64_t ws_bytes) {
   int rc = check_plan(plan);
   if (rc) return rc;
   if (!env || !params || !rng_state || !iter_keys || !env_obs || !env_counter || !env_term || !obs ||
@@ -1007,9 +974,18 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   a.env_obs = env_obs; a.env_counter = env_counter; a.env_term = env_term;
   a.obs = obs; a.raw_action = raw_action; a.action = action; a.loglik = loglik; a.reward = reward;
   a.done = done; a.trunc = truncated; a.next_obs_last = next_obs_last;
+  if (ws != nullptr && wide_preferred(plan, B) && ws_bytes >= 4 * rollout_wide_ws_floats(plan, B)) {
+    RolloutWideArgs w;
+    w.plan = plan; w.Wenv = env->Wo; w.max_len = env->max_len; w.term_thresh16 = env->term_thresh16;
+    w.params = params; w.mean = norm_mean; w.std = norm_std; w.rng_state = rng_state; w.iter_keys = iter_keys;
+    w.T = T; w.B = B; w.env_obs = env_obs; w.env_counter = env_counter; w.env_term = env_term;
+    w.obs = obs; w.raw_action = raw_action; w.action = action; w.loglik = loglik; w.reward = reward;
+    w.done = done; w.trunc = truncated; w.next_obs_last = next_obs_last; w.ws = static_cast<float*>(ws);
+    return rollout_wide(static_cast<cudaStream_t>(stream), w);
+  }
   int md = max_dim(plan->actor);
   if (O + A > md) md = O + A;
-  if (rollout_mode() == 1) {
+  if (rollout_mode() >= 1) {
     // tensor-core tiles (mma.sync 3xTF32): fragment-ordered weights of every layer resident in shared memory
     a.ld = ((md + 7) & ~7) + 4;          // = 4 (mod 8): the A-fragment loads (lane = 4 g + t -> g * ld + t) hit 32 distinct banks
     int64_t fl = 3ll * TE * a.ld + 2ll * TE * A + 2ll * O + 5ll * TE + 8;
@@ -1065,10 +1041,45 @@ extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, con
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
+}  // namespace
+
+extern "C" int b200ppo_rollout_synth(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                                     const float* params, const float* norm_mean, const float* norm_std,
+                                     const uint32_t* rng_state, const uint32_t* iter_keys, int32_t T,
+                                     int32_t B, float* env_obs, int32_t* env_counter, uint32_t* env_term,
+                                     float* obs, float* raw_action, float* action, float* loglik,
+                                     float* reward, uint8_t* done, uint8_t* truncated,
+                                     float* next_obs_last) {
+  return rollout_synth_impl(stream, plan, env, params, norm_mean, norm_std, rng_state, iter_keys, T, B, env_obs,
+                            env_counter, env_term, obs, raw_action, action, loglik, reward, done, truncated,
+                            next_obs_last, nullptr, 0);
+}
+
+extern "C" int64_t b200ppo_rollout_synth_workspace_bytes(const b200ppo_plan* plan, int32_t B) {
+  if (check_plan(plan) || B <= 0) return -1;
+  return wide_preferred(plan, B) ? 4 * rollout_wide_ws_floats(plan, B) : 0;
+}
+
+extern "C" int b200ppo_rollout_synth_num_launches(const b200ppo_plan* plan, int32_t T, int32_t B, int32_t with_ws) {
+  if (check_plan(plan) || B <= 0 || T <= 0) return -1;
+  return (with_ws && wide_preferred(plan, B)) ? rollout_wide_num_launches(plan, T) : 1;
+}
+
+extern "C" int b200ppo_rollout_synth_ws(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,
+                                        const float* params, const float* norm_mean, const float* norm_std,
+                                        const uint32_t* rng_state, const uint32_t* iter_keys, int32_t T,
+                                        int32_t B, float* env_obs, int32_t* env_counter, uint32_t* env_term,
+                                        float* obs, float* raw_action, float* action, float* loglik,
+                                        float* reward, uint8_t* done, uint8_t* truncated,
+                                        float* next_obs_last, void* ws, int64_t ws_bytes) {
+  return rollout_synth_impl(stream, plan, env, params, norm_mean, norm_std, rng_state, iter_keys, T, B, env_obs,
+                            env_counter, env_term, obs, raw_action, action, loglik, reward, done, truncated,
+                            next_obs_last, ws, ws_bytes);
+}
 
 extern "C" int b200ppo_set_rollout_mode(int mode) {
   const int prev = rollout_mode();
-  if (mode == 0 || mode == 1) g_rollout_mode = mode;
+  if (mode >= 0 && mode <= 2) g_rollout_mode = mode;
   return prev;
 }
 

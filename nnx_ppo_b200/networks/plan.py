@@ -369,6 +369,21 @@ class CompiledNet:
             return 0, 0
         return _lib.ptr(self.normalizer.mean._dev), _lib.ptr(self.normalizer._std)
 
+    def rollout_workspace(self, B: int):
+        """(pointer, bytes) of the scratch buffer `b200ppo_rollout_synth_ws` wants for B envs: (0, 0) while the
+        fused kernel keeps this network's weights resident in shared memory; otherwise a cached device buffer for
+        the batched per-step path (include/b200ppo.h)."""
+        import torch
+        n = int(_lib.load().b200ppo_rollout_synth_workspace_bytes(self.plan, B))
+        if n <= 0:
+            return 0, 0
+        cache = self.__dict__.setdefault("_rollout_ws", {})
+        ws = cache.get(B)
+        if ws is None or ws.numel() * 4 < n:
+            cache.clear()                                  # one live size: the buffers are ~100 MB at configs[3]
+            ws = cache[B] = torch.zeros((n + 3) // 4, dtype=torch.float32, device=self.device)
+        return ws.data_ptr(), n
+
 
 def compile_network(network: StatefulModule, device=None) -> CompiledNet:
     import torch

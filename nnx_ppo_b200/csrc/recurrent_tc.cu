@@ -890,7 +890,7 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
 // ------------------------------------------------------------------------------------------
 struct WideLayout {
   int ldx, ldz, ldo;
-  size_t x, za, zb, zenv, ynext, total;
+  size_t x, xn, za, zb, zenv, ynext, total;
 };
 WideLayout wide_layout(const b200ppo_plan& p, int B) {
   WideLayout L;
@@ -903,6 +903,7 @@ WideLayout wide_layout(const b200ppo_plan& p, int B) {
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
   L.x = take(static_cast<size_t>(B) * L.ldx);
+  L.xn = take(static_cast<size_t>(B) * L.ldo);       // normalised observations: the first layer's A operand
   L.za = take(static_cast<size_t>(B) * L.ldz);
   L.zb = take(static_cast<size_t>(B) * L.ldz);
   L.zenv = take(static_cast<size_t>(B) * L.ldo);
@@ -912,13 +913,15 @@ WideLayout wide_layout(const b200ppo_plan& p, int B) {
 }
 
 __global__ void __launch_bounds__(256) wide_init_kernel(const float* __restrict__ env_obs, int B, int O, float* __restrict__ X,
-                                                        int ldx, float* __restrict__ obs0) {
+                                                        int ldx, float* __restrict__ obs0, float* __restrict__ Xn, int ldo,
+                                                        const float* __restrict__ mean, const float* __restrict__ stdv) {
   const size_t n = static_cast<size_t>(B) * O;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t e = i / O, o = i - e * O;
     const float v = env_obs[i];
     X[e * ldx + o] = v;
     obs0[i] = v;
+    Xn[e * ldo + o] = mean != nullptr ? __fdiv_rn(v - mean[o], stdv[o]) : v;
   }
 }
 
@@ -945,6 +948,7 @@ struct WideBookArgs {
   const uint32_t* iter_keys;
   const float* ynext; const float* llterm;
   float* X; float* obs_next;            // obs[t + 1] (nullptr at the last step)
+  float* Xn; const float* mean; const float* stdv;   // normalised next observation (normalizer.py:78-80; mean == nullptr: none)
   float* loglik; float* reward; uint8_t* done; uint8_t* trunc;     // row t of the record
   float* next_obs_last; float* env_obs;                            // written at the last step only
   int32_t* env_counter; uint32_t* env_term;                        // advanced in place every step
@@ -984,14 +988,28 @@ __global__ void __launch_bounds__(256) wide_book_kernel(const WideBookArgs a) {
   const Key kb{kba, kbb};
   const bool last = a.t == a.T - 1;
   float sq = 0.0f;
-  for (int o = lane; o < a.O; o += 32) {
-    const float v = a.ynext[static_cast<size_t>(e) * a.ldo + o];
-    sq = fmaf(v, v, sq);
+  auto put = [&](int o, float v) {
     if (last) a.next_obs_last[static_cast<size_t>(e) * a.O + o] = v;
     const float nv = dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v;
     a.X[static_cast<size_t>(e) * a.ldx + o] = nv;
+    a.Xn[static_cast<size_t>(e) * a.ldo + o] = a.mean != nullptr ? __fdiv_rn(nv - a.mean[o], a.stdv[o]) : nv;
     if (a.obs_next != nullptr) a.obs_next[static_cast<size_t>(e) * a.O + o] = nv;
     if (last) a.env_obs[static_cast<size_t>(e) * a.O + o] = nv;
+  };
+  if ((a.O & 3) == 0) {
+    // four columns per lane and trip (lane l owns columns 128 i + 4 l .. + 3): a fixed summation order of its own,
+    // the reward differs from the fused kernels' in the last bits only
+    for (int o = 4 * lane; o < a.O; o += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(a.ynext + static_cast<size_t>(e) * a.ldo + o);
+      sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
+      put(o, v.x); put(o + 1, v.y); put(o + 2, v.z); put(o + 3, v.w);
+    }
+  } else {
+    for (int o = lane; o < a.O; o += 32) {
+      const float v = a.ynext[static_cast<size_t>(e) * a.ldo + o];
+      sq = fmaf(v, v, sq);
+      put(o, v);
+    }
   }
   sq = warp_sum(sq);
   if (lane == 0) a.reward[e] = -(sq / static_cast<float>(a.O));
@@ -1012,27 +1030,26 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
   const int O = p.obs_dim, A = p.act_dim, B = a.B, T = a.T, L = p.actor.n_layers;
   const WideLayout W = wide_layout(p, B);
   float* X = a.ws + W.x;
+  float* Xn = a.ws + W.xn;
+  const float* nmean = p.normalize ? a.mean : nullptr;
+  const float* nstd = p.normalize ? a.std : nullptr;
   float* zbuf[2] = {a.ws + W.za, a.ws + W.zb};
   float* zenv = a.ws + W.zenv;
   float* ynext = a.ws + W.ynext;
   float* llterm = a.ws + W.total;
   const int row_tiles = cdiv(B, RM);
   auto n_tile_for = [&](int N) { return row_tiles * cdiv(N, 256) >= b200ppo_num_sms() ? 256 : 128; };
-  wide_init_kernel<<<cdiv(static_cast<int64_t>(B) * O, 256 * 8), 256, 0, s>>>(a.env_obs, B, O, X, W.ldx, a.obs);
+  wide_init_kernel<<<cdiv(static_cast<int64_t>(B) * O, 256 * 8), 256, 0, s>>>(a.env_obs, B, O, X, W.ldx, a.obs, Xn, W.ldo, nmean, nstd);
   B200PPO_LAUNCH_CHECK();
   for (int t = 0; t < T; ++t) {
     const size_t row0 = static_cast<size_t>(t) * B;
-    const float* in = X;
-    int ldin = W.ldx;
+    const float* in = Xn;
+    int ldin = W.ldo;
     for (int l = 0; l < L; ++l) {
       const int K = p.actor.dims[l], N = p.actor.dims[l + 1];
       GemmArgs g = gemm_defaults();
       g.A = in; g.lda = ldin; g.M = B; g.K = K;
-      if (l == 0) {
-        if (p.normalize) { g.a_mean = a.mean; g.a_std = a.std; }
-      } else {
-        g.act_a = p.actor.act;
-      }
+      if (l > 0) g.act_a = p.actor.act;
       g.B = a.params + p.actor.w_off[l]; g.ldb = N;
       g.bias = a.params + p.actor.b_off[l];
       g.C = zbuf[l & 1]; g.ldc = W.ldz;
@@ -1056,7 +1073,7 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
     }
     WideBookArgs b;
     b.B = B; b.O = O; b.A = A; b.T = T; b.t = t; b.max_len = a.max_len; b.term_thresh16 = a.term_thresh16;
-    b.ldx = W.ldx; b.ldo = W.ldo; b.iter_keys = a.iter_keys; b.ynext = ynext; b.llterm = llterm; b.X = X;
+    b.ldx = W.ldx; b.ldo = W.ldo; b.iter_keys = a.iter_keys; b.ynext = ynext; b.llterm = llterm; b.X = X; b.Xn = Xn; b.mean = nmean; b.stdv = nstd;
     b.obs_next = t + 1 < T ? a.obs + (row0 + B) * O : nullptr;
     b.loglik = a.loglik + row0; b.reward = a.reward + row0; b.done = a.done + row0; b.trunc = a.trunc + row0;
     b.next_obs_last = a.next_obs_last; b.env_obs = a.env_obs; b.env_counter = a.env_counter; b.env_term = a.env_term;

@@ -63,6 +63,9 @@ struct GemmArgs {
   //             col(n) = b_col0 + (n >> b_unit_log2) * b_gate_stride + (n & (2^b_unit_log2 - 1))   (gate-interleaved tiles)
   //   b_nt = 1: row-major [N][ldb];  Bop(n, k) = B[(b_col0 + n) * ldb + b_k0 + k]  (reduction index contiguous)
   const float* B; int ldb; int b_nt; int b_col0; int b_unit_log2; int b_gate_stride; int b_k0;
+  // optional (rg_gemm_kernel<0>): B pre-split by rg_prep_b_kernel into the shared-memory stage layout, per column
+  // tile and 32-k stage one contiguous block [hi planes | lo planes] -> ONE cp.async.bulk per stage, no thread work
+  const float* Bplanes;
   int N; int n_log2;                           // MMA N of one tile: a power of two in [16, 256]
   int n_real;                                  // valid columns over all tiles (columns >= n_real are padding)
   int tile_stride;                             // columns per blockIdx.y tile (added to b_col0 / the C column)
@@ -81,6 +84,7 @@ struct StageRegs {
   float4 a[4];
   float4 b[RN_MAX / 32];
 };
+
 
 __host__ __device__ inline uint32_t stage_bytes_nn(int n) {
   return 2u * (RK / 4) * tc::plane_bytes(RM) + 2u * (RK / 4) * tc::plane_bytes(n);
@@ -261,6 +265,17 @@ __device__ __forceinline__ void issue_slab(const Pipe& p, uint8_t* st, uint32_t 
   }
 }
 
+// B operand of stage s from the pre-split planes: one bulk copy, completion counted on the stage's full barrier
+// (the issuing thread's expect_tx arrival is the extra arrival pipe_init is told about)
+__device__ __forceinline__ void gemm_bulk_b(const GemmArgs& g, const Pipe& p, int buf, int s, int nst, uint32_t pa,
+                                            uint32_t pb, uint32_t sbytes) {
+  const uint32_t bytes = 2u * (RK / 4) * pb;
+  uint8_t* dst = p.smem + buf * sbytes + 2u * (RK / 4) * pa;
+  const float* src = g.Bplanes + (static_cast<size_t>(blockIdx.y) * nst + s) * (bytes / 4);
+  tc::mbar_arrive_expect_tx(&p.bar_full[buf], bytes);
+  tc::bulk_g2s(dst, src, bytes, &p.bar_full[buf]);
+}
+
 // accumulate into TMEM columns [0, N).  Warps 0-7 stage (two statically named register sets ping-pong so that the
 // loads of stage s + 1 are in flight while stage s is split and stored; a rotating `cur = next` copy would make
 // every stage wait for a memory round trip: profiles/r1_tc_notes.md, finding 2) and hand each buffer to the issuer
@@ -287,6 +302,7 @@ __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, 
   for (int s = 0; s < nst; s += 2) {
     gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 1, nst, x1);
     if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
+    if (NB == 0 && threadIdx.x == 0) gemm_bulk_b(g, p, 0, s, nst, pa, pb, sbytes);
     gemm_store_stage<NB>(g, p.smem, x0);
     tc::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
     __syncwarp();
@@ -294,6 +310,7 @@ __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, 
     if (s + 1 < nst) {
       gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 2, nst, x0);
       if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
+      if (NB == 0 && threadIdx.x == 0) gemm_bulk_b(g, p, 1, s + 1, nst, pa, pb, sbytes);
       gemm_store_stage<NB>(g, p.smem + sbytes, x1);
       tc::fence_proxy_async();
       __syncwarp();
@@ -313,7 +330,7 @@ __global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
   __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   Pipe p;
-  pipe_init(p, smem, bars, &tmem_slot, g.N, RT / 32);
+  pipe_init(p, smem, bars, &tmem_slot, g.N, RT / 32 + (NB == 0 ? 1 : 0));
   const int row0 = blockIdx.x * RM;
   const int tile = blockIdx.y, slice = blockIdx.z;
   const int col0 = g.b_col0 + tile * g.tile_stride;
@@ -780,6 +797,8 @@ int set_attrs_tc() {
   if (g_attr_tc) return 0;
   const int big = 2 * static_cast<int>(stage_bytes_nn(256));
   cudaError_t e;
+  e = cudaFuncSetAttribute(rg_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(rg_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(rg_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -807,7 +826,7 @@ int set_attrs_tc() {
 GemmArgs gemm_defaults() {
   GemmArgs g;
   g.A = nullptr; g.lda = 0; g.a_k0 = 0; g.M = 0; g.K = 0; g.act_a = B200PPO_ACT_NONE; g.a_mean = nullptr; g.a_std = nullptr;
-  g.B = nullptr; g.ldb = 0; g.b_nt = 0; g.b_col0 = 0; g.b_unit_log2 = 30; g.b_gate_stride = 0; g.b_k0 = 0;
+  g.B = nullptr; g.ldb = 0; g.b_nt = 0; g.b_col0 = 0; g.b_unit_log2 = 30; g.b_gate_stride = 0; g.b_k0 = 0; g.Bplanes = nullptr;
   g.N = 16; g.n_log2 = 4; g.n_real = 0; g.tile_stride = 0;
   g.C = nullptr; g.ldc = 0; g.c_planes = 0; g.c_cols4 = 0; g.bias = nullptr; g.C2 = nullptr; g.ldc2 = 0; g.act_c2 = B200PPO_ACT_NONE;
   g.Zmul = nullptr; g.ldz = 0; g.act_z = B200PPO_ACT_NONE;
@@ -830,7 +849,8 @@ int launch_gemm(cudaStream_t s, GemmArgs g, int n_real, int slices, int n_tile =
   const int tiles = cdiv(n_real, g.N);
   const dim3 grid(cdiv(g.M, RM), tiles, slices);
   const size_t smem = 2 * static_cast<size_t>(stage_bytes_nn(g.N));
-  if (g.N <= 32) rg_gemm_kernel<1><<<grid, RTI, smem, s>>>(g);
+  if (g.Bplanes != nullptr) rg_gemm_kernel<0><<<grid, RTI, smem, s>>>(g);
+  else if (g.N <= 32) rg_gemm_kernel<1><<<grid, RTI, smem, s>>>(g);
   else if (g.N <= 64) rg_gemm_kernel<2><<<grid, RTI, smem, s>>>(g);
   else rg_gemm_kernel<8><<<grid, RTI, smem, s>>>(g);
   B200PPO_LAUNCH_CHECK();
@@ -888,8 +908,41 @@ int launch_tn(cudaStream_t s, const float* A, int lda, int a_col0, int Kdim, int
 // Same arithmetic per element as the fused kernels (sampler_elem / synth_reset_scalars in common.cuh), integer
 // bookkeeping bit-identical.
 // ------------------------------------------------------------------------------------------
+// floats of the pre-split B planes of a [K][n_real] weight matrix cut into column tiles of mma_n(min(n_real, n_tile))
+inline int planes_ntile(int n_real, int n_tile) { return mma_n(n_real < n_tile ? n_real : n_tile); }
+inline size_t planes_floats(int K, int n_real, int n_tile) {
+  const int N = planes_ntile(n_real, n_tile);
+  return static_cast<size_t>(cdiv(n_real, N)) * cdiv(K, RK) * 2 * (RK / 4) * (N + 1) * 4;
+}
+// W [K][ldb] row-major -> per (column tile, 32-k stage) the stage's B area exactly as gemm_store_stage lays it out:
+// hi planes q = 0..7 ([N + 1] float4 each, entry n = the 4 consecutive k of column n), then the lo planes
+__global__ void __launch_bounds__(256) rg_prep_b_kernel(const float* __restrict__ W, int ldb, int K, int n_real, int N,
+                                                        int nst, int tiles, float4* __restrict__ out) {
+  const int prow = N + 1;
+  const size_t total = static_cast<size_t>(tiles) * nst * (RK / 4) * prow;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx % prow);
+    size_t r = idx / prow;
+    const int q = static_cast<int>(r % (RK / 4)); r /= (RK / 4);
+    const int s = static_cast<int>(r % nst), tile = static_cast<int>(r / nst);
+    const int k = s * RK + 4 * q, col = tile * N + n;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < N && col < n_real)
+      for (int j = 0; j < 4; ++j)
+        if (k + j < K) x[j] = W[static_cast<size_t>(k + j) * ldb + col];
+    float4 hi, lo;
+    tc::split4_fast(make_float4(x[0], x[1], x[2], x[3]), hi, lo);
+    const size_t base = (static_cast<size_t>(tile) * nst + s) * 2 * (RK / 4) * prow;
+    out[base + static_cast<size_t>(q) * prow + n] = hi;
+    out[base + static_cast<size_t>(RK / 4 + q) * prow + n] = lo;
+  }
+}
+
 struct WideLayout {
   int ldx, ldz, ldo;
+  int n_tile[B200PPO_MAX_LAYERS + 1];                 // column-tile width request of every layer GEMM; [L] = the env GEMM
+  size_t planes[B200PPO_MAX_LAYERS + 1];              // pre-split weight planes (rg_prep_b_kernel)
   size_t x, xn, za, zb, zenv, ynext, total;
 };
 WideLayout wide_layout(const b200ppo_plan& p, int B) {
@@ -908,6 +961,14 @@ WideLayout wide_layout(const b200ppo_plan& p, int B) {
   L.zb = take(static_cast<size_t>(B) * L.ldz);
   L.zenv = take(static_cast<size_t>(B) * L.ldo);
   L.ynext = take(static_cast<size_t>(B) * L.ldo);
+  const int row_tiles = cdiv(B, RM);
+  auto n_tile_for = [&](int N) { return row_tiles * cdiv(N, 256) >= b200ppo_num_sms() ? 256 : 128; };
+  for (int l = 0; l < p.actor.n_layers; ++l) {
+    L.n_tile[l] = n_tile_for(p.actor.dims[l + 1]);
+    L.planes[l] = take(planes_floats(p.actor.dims[l], p.actor.dims[l + 1], L.n_tile[l]));
+  }
+  L.n_tile[p.actor.n_layers] = n_tile_for(O);
+  L.planes[p.actor.n_layers] = take(planes_floats(O + A, O, L.n_tile[p.actor.n_layers]));
   L.total = o;
   return L;
 }
@@ -1021,7 +1082,9 @@ namespace b200ppo {
 int64_t rollout_wide_ws_floats(const b200ppo_plan* plan, int B) {
   return static_cast<int64_t>(wide_layout(*plan, B).total + static_cast<size_t>(B) * plan->act_dim + 64);
 }
-int rollout_wide_num_launches(const b200ppo_plan* plan, int T) { return 1 + T * (plan->actor.n_layers + 3); }
+int rollout_wide_num_launches(const b200ppo_plan* plan, int T) {
+  return plan->actor.n_layers + 2 + T * (plan->actor.n_layers + 3);     // weight planes + init, then the per-step sequence
+}
 
 int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
   int rc = set_attrs_tc();
@@ -1037,8 +1100,22 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
   float* zenv = a.ws + W.zenv;
   float* ynext = a.ws + W.ynext;
   float* llterm = a.ws + W.total;
-  const int row_tiles = cdiv(B, RM);
-  auto n_tile_for = [&](int N) { return row_tiles * cdiv(N, 256) >= b200ppo_num_sms() ? 256 : 128; };
+  // the weights are constant over the rollout: split them once into the GEMMs' shared-memory stage layout
+  auto prep = [&](const float* Wm, int K, int N, int li) -> int {
+    const int Nt = planes_ntile(N, W.n_tile[li]);
+    const int tiles = cdiv(N, Nt), nst = cdiv(K, RK);
+    const size_t total = static_cast<size_t>(tiles) * nst * (RK / 4) * (Nt + 1);
+    rg_prep_b_kernel<<<cdiv(static_cast<int64_t>(total), 256), 256, 0, s>>>(Wm, N, K, N, Nt, nst, tiles,
+                                                                          reinterpret_cast<float4*>(a.ws + W.planes[li]));
+    B200PPO_LAUNCH_CHECK();
+    return 0;
+  };
+  for (int l = 0; l < L; ++l) {
+    rc = prep(a.params + p.actor.w_off[l], p.actor.dims[l], p.actor.dims[l + 1], l);
+    if (rc) return rc;
+  }
+  rc = prep(a.Wenv, O + A, O, L);
+  if (rc) return rc;
   wide_init_kernel<<<cdiv(static_cast<int64_t>(B) * O, 256 * 8), 256, 0, s>>>(a.env_obs, B, O, X, W.ldx, a.obs, Xn, W.ldo, nmean, nstd);
   B200PPO_LAUNCH_CHECK();
   for (int t = 0; t < T; ++t) {
@@ -1051,9 +1128,10 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
       g.A = in; g.lda = ldin; g.M = B; g.K = K;
       if (l > 0) g.act_a = p.actor.act;
       g.B = a.params + p.actor.w_off[l]; g.ldb = N;
+      g.Bplanes = a.ws + W.planes[l];
       g.bias = a.params + p.actor.b_off[l];
       g.C = zbuf[l & 1]; g.ldc = W.ldz;
-      rc = launch_gemm(s, g, N, 1, n_tile_for(N));
+      rc = launch_gemm(s, g, N, 1, W.n_tile[l]);
       if (rc) return rc;
       in = zbuf[l & 1];
       ldin = W.ldz;
@@ -1066,9 +1144,10 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
       GemmArgs g = gemm_defaults();
       g.A = X; g.lda = W.ldx; g.M = B; g.K = O + A;
       g.B = a.Wenv; g.ldb = O;
+      g.Bplanes = a.ws + W.planes[L];
       g.C = zenv; g.ldc = W.ldo;
       g.C2 = ynext; g.ldc2 = W.ldo; g.act_c2 = B200PPO_ACT_TANH;
-      rc = launch_gemm(s, g, O, 1, n_tile_for(O));
+      rc = launch_gemm(s, g, O, 1, W.n_tile[L]);
       if (rc) return rc;
     }
     WideBookArgs b;

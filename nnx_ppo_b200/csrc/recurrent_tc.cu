@@ -962,7 +962,10 @@ WideLayout wide_layout(const b200ppo_plan& p, int B) {
   L.zenv = take(static_cast<size_t>(B) * L.ldo);
   L.ynext = take(static_cast<size_t>(B) * L.ldo);
   const int row_tiles = cdiv(B, RM);
-  auto n_tile_for = [&](int N) { return row_tiles * cdiv(N, 256) >= b200ppo_num_sms() ? 256 : 128; };
+  // 256-column tiles on layers with enough row tiles to fill the device, 128 otherwise (B200PPO_WIDE_NTILE=128: always
+  // 128; measured equal at configs[3]: 42.0 vs 42.3 ms per iteration)
+  static const int want256 = [] { const char* e = std::getenv("B200PPO_WIDE_NTILE"); return e && std::atoi(e) == 128 ? 0 : 1; }();
+  auto n_tile_for = [&](int N) { return (want256 && row_tiles * cdiv(N, 256) >= b200ppo_num_sms()) ? 256 : 128; };
   for (int l = 0; l < p.actor.n_layers; ++l) {
     L.n_tile[l] = n_tile_for(p.actor.dims[l + 1]);
     L.planes[l] = take(planes_floats(p.actor.dims[l], p.actor.dims[l + 1], L.n_tile[l]));
@@ -1058,12 +1061,32 @@ __global__ void __launch_bounds__(256) wide_book_kernel(const WideBookArgs a) {
     if (last) a.env_obs[static_cast<size_t>(e) * a.O + o] = nv;
   };
   if ((a.O & 3) == 0) {
-    // four columns per lane and trip (lane l owns columns 128 i + 4 l .. + 3): a fixed summation order of its own,
-    // the reward differs from the fused kernels' in the last bits only
+    // four columns per lane and trip (lane l owns columns 128 i + 4 l .. + 3), 16-byte loads and stores: a fixed
+    // summation order of its own, the reward differs from the fused kernels' in the last bits only
+    const bool norm = a.mean != nullptr;
     for (int o = 4 * lane; o < a.O; o += 128) {
       const float4 v = *reinterpret_cast<const float4*>(a.ynext + static_cast<size_t>(e) * a.ldo + o);
       sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
-      put(o, v.x); put(o + 1, v.y); put(o + 2, v.z); put(o + 3, v.w);
+      float4 nv = v;
+      if (dn) {
+        nv.x = bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o)));
+        nv.y = bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o + 1)));
+        nv.z = bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o + 2)));
+        nv.w = bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o + 3)));
+      }
+      float4 xn = nv;
+      if (norm) {
+        const float4 m = *reinterpret_cast<const float4*>(a.mean + o), sd = *reinterpret_cast<const float4*>(a.stdv + o);
+        xn.x = __fdiv_rn(nv.x - m.x, sd.x); xn.y = __fdiv_rn(nv.y - m.y, sd.y);
+        xn.z = __fdiv_rn(nv.z - m.z, sd.z); xn.w = __fdiv_rn(nv.w - m.w, sd.w);
+      }
+      *reinterpret_cast<float4*>(a.X + static_cast<size_t>(e) * a.ldx + o) = nv;
+      *reinterpret_cast<float4*>(a.Xn + static_cast<size_t>(e) * a.ldo + o) = xn;
+      if (a.obs_next != nullptr) *reinterpret_cast<float4*>(a.obs_next + static_cast<size_t>(e) * a.O + o) = nv;
+      if (last) {
+        *reinterpret_cast<float4*>(a.next_obs_last + static_cast<size_t>(e) * a.O + o) = v;
+        *reinterpret_cast<float4*>(a.env_obs + static_cast<size_t>(e) * a.O + o) = nv;
+      }
     }
   } else {
     for (int o = lane; o < a.O; o += 32) {

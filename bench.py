@@ -51,6 +51,19 @@ SEED, NET_SEED = 17, 0
 METRIC = "PPO samples/sec (rollout policy + GAE + update)"
 
 
+def _rollout_engine(lib, eng, cfg, recurrent) -> str:
+    """Which rollout path ran (include/b200ppo.h, b200ppo_set_rollout_mode)."""
+    if recurrent:
+        return "per-step launches: tcgen05 sequence kernels with T = 1 + sampler + env (algorithms/recurrent.py)"
+    mode = int(lib.b200ppo_set_rollout_mode(-1))
+    n = int(lib.b200ppo_rollout_synth_num_launches(eng.net.plan, cfg["T"], cfg["n_envs"], 1))
+    if n > 1:
+        return (f"batched: {n} launches per rollout, one tcgen05 3xTF32 tile GEMM per layer and step over all envs, "
+                "weights pre-split once per rollout (the network does not fit shared memory)")
+    return ("fused persistent kernel, one launch: " +
+            ("warp-level mma.sync m16n8k8 3xTF32 tiles, weights resident in shared memory" if mode >= 1 else "fp32 FFMA tiles"))
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -443,6 +456,7 @@ def run_own(args):
                                         if eng.p2p else "NCCL all-reduce x2 per update")),
                        "rollout_critic": "off: the fused rollout does not evaluate the critic (training replays it, ppo.py:425-446; "
                                          "value estimates are computed on request for logging)",
+                       "rollout_engine": _rollout_engine(lib, eng, cfg, recurrent),
                        "pdl": int(lib.b200ppo_set_pdl(-1)),
                        "cuda_graph": getattr(eng, "graph", None) is not None, "done_rate": float(eng.done.float().mean()),
                        "truncation_rate": float(eng.trunc.float().mean())},

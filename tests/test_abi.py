@@ -201,6 +201,32 @@ def test_host_side_sizing_entry_points_for_the_bench_configuration(lib):
     assert int(lib.b200ppo_comm_bytes(net.plan, 8)) > 8 * 2 * 4 * net.n_params   # two parities x 8 rank slots
 
 
+def test_rollout_engine_selection_is_host_logic(lib):
+    """`b200ppo_rollout_synth_workspace_bytes` / `_num_launches`: networks whose weights fit an SM's shared memory keep
+    the fused one-launch rollout (no workspace); BASELINE configs[3] (768-wide dict-observation encoders, 789 x 768
+    env matrix) takes the batched per-step path once a workspace is offered.  Host-only (no launch)."""
+    import torch
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    mlp = CompiledNet(factories.make_mlp_actor_critic(64, 8, [64] * 4, [256] * 2, prng.Rngs(0)), torch.device("cpu"))
+    assert int(lib.b200ppo_rollout_synth_workspace_bytes(mlp.plan, 4096)) == 0
+    assert int(lib.b200ppo_rollout_synth_num_launches(mlp.plan, 32, 4096, 1)) == 1
+    wide = CompiledNet(factories.make_dict_actor_critic({"proprio": 256, "target": 512}, 21, {"proprio": [128, 64], "target": [128, 64]},
+                                                        [256, 256], [256, 256], prng.Rngs(0)), torch.device("cpu"))
+    L = wide.plan.actor.n_layers
+    assert L == 5
+    ws = int(lib.b200ppo_rollout_synth_workspace_bytes(wide.plan, 8192))
+    assert 80e6 < ws < 200e6 and ws % 4 == 0
+    assert int(lib.b200ppo_rollout_synth_num_launches(wide.plan, 32, 8192, 1)) == (L + 1) + 1 + 32 * (L + 3)
+    assert int(lib.b200ppo_rollout_synth_num_launches(wide.plan, 32, 8192, 0)) == 1        # no workspace: fused kernel
+    assert int(lib.b200ppo_rollout_synth_workspace_bytes(wide.plan, 256)) == 0             # few envs: tiles would idle
+    assert int(lib.b200ppo_rollout_synth_workspace_bytes(None, 8192)) == -1
+    prev = lib.b200ppo_set_rollout_mode(0)                                                  # FFMA tiles: always fused
+    try:
+        assert int(lib.b200ppo_rollout_synth_workspace_bytes(wide.plan, 8192)) == 0
+    finally:
+        lib.b200ppo_set_rollout_mode(prev)
+
+
 def test_host_key_arithmetic_equals_the_oracle_restatement():
     """nnx_ppo_b200/prng.py (host key flow of the product) against oracle/prng.py (NumPy restatement) on
     random keys: split, fold_in, uniform and the variance-scaling initializer draw."""

@@ -89,3 +89,40 @@ def test_distillation_step_bookkeeping_and_teacher_frozen():
         first = float(mm["losses/distillation_nll"]) if first is None else first
         last = float(mm["losses/distillation_nll"])
     assert last < first - 0.05
+
+
+def test_distillation_api_mirrors_the_reference():
+    """Names, positional order and defaults of the drop-in surface (nnx_ppo/algorithms/distillation.py:63,235,363,422;
+    config.py:72-95,120-127; types.py:85-125) - the product module is importable without a GPU."""
+    import dataclasses
+    import inspect
+    from nnx_ppo_b200.algorithms import config as cfg, distillation as d, types as t
+
+    def params(f):
+        return [(p.name, p.default if p.default is not inspect.Parameter.empty else None, p.kind.name)
+                for p in inspect.signature(f).parameters.values()]
+
+    assert [p[0] for p in params(d.distillation_step)] == [
+        "env", "teacher", "distillation_state", "n_envs", "rollout_length", "n_epochs", "n_minibatches",
+        "logging_level", "logging_percentiles"]
+    assert [p[0] for p in params(d.new_distillation_state)] == [
+        "env", "teacher", "student", "n_envs", "seed", "learning_rate", "gradient_clipping", "weight_decay"]
+    assert dict((p[0], p[1]) for p in params(d.new_distillation_state))["learning_rate"] == 1e-4
+    td = params(d.train_distillation)
+    assert [p[0] for p in td] == ["env", "teacher", "student", "config", "total_steps", "seed", "log_fn", "video_fn",
+                                  "checkpoint_fn", "eval_env", "initial_state"]
+    assert all(p[2] == "KEYWORD_ONLY" for p in td[4:])
+    dc = cfg.DistillationConfig()
+    assert [f.name for f in dataclasses.fields(dc)] == [
+        "n_envs", "rollout_length", "total_steps", "learning_rate", "n_epochs", "n_minibatches", "gradient_clipping",
+        "weight_decay", "logging_level", "logging_percentiles"]
+    assert (dc.n_envs, dc.rollout_length, dc.total_steps, dc.n_epochs, dc.n_minibatches) == (256, 20, 512_000, 4, 4)
+    tc = d.default_distillation_config()
+    assert isinstance(tc, cfg.DistillationTrainConfig) and tc.seed == 17 and tc.checkpoint_every_steps == 500_000
+    assert [f.name for f in dataclasses.fields(cfg.DistillationTrainResult)] == [
+        "training_state", "final_metrics", "eval_history", "total_steps", "total_iterations"]
+    assert [f.name for f in dataclasses.fields(t.DistillationState)] == [
+        "student", "student_states", "teacher_states", "env_states", "optimizer", "rng_key", "steps_taken"]
+    assert [f.name for f in dataclasses.fields(t.DistillationTransition)] == [
+        "obs", "student_output", "rewards", "done", "truncated", "next_obs", "metrics", "student_rollout_extras",
+        "teacher_rollout_extras"]

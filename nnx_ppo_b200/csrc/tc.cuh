@@ -74,6 +74,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// 2-D tiled TMA load global -> shared (UTMALDG): the box described by the tensor map at element coordinates
+// (c0 = fastest dimension, c1), dense in shared memory (no swizzle); completes box-bytes on the mbarrier
+// (out-of-bounds elements are filled and counted).  dst 128-byte aligned.
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- proxies / tcgen05 fences ----
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

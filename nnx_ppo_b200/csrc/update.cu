@@ -13,6 +13,8 @@
 //   ADAM fused optax update
 // All GEMMs share one register-tiled fp32 FFMA routine (TM=128 rows resident in shared memory,
 // 8x4 accumulators per thread, B operand streamed in double-buffered 16-deep chunks).
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -128,7 +130,9 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
     for (int l = 0; l < ch.n_layers; ++l) {
       const int K = ch.dims[l], N = ch.dims[l + 1];
       if (N > 256) L.tc_ok = 0;
-      if (K > 256) L.tc_dw_bulk = 0;                         // dW v2 stages full rows of H (<= 256 wide)
+      // dW v2 stages full rows of H (<= 256 wide); a wider OBSERVATION layer (l == 0, H = xhat) is fetched as 2-D
+      // TMA boxes instead (16-byte row pitch needed); anything else keeps the gather kernel
+      if (K > 256 && !(l == 0 && (K & 3) == 0)) L.tc_dw_bulk = 0;
       tl[l].kpad = (K + 31) & ~31;
       tl[l].npad = (N + 15) & ~15;
       tl[l].nred_pad = (N + 31) & ~31;
@@ -1341,6 +1345,32 @@ int set_attrs() {
   return 0;
 }
 
+// Tensor map over xhat [rows][O] (fp32, row pitch O * 4 bytes) with a 128-column x 16-row box for the dW kernel's
+// wide observation layer.  cuTensorMapEncodeTiled is a host-only driver function: resolved through the runtime
+// (no link dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_xhat_map(CUtensorMap* tm, const float* xhat, int O, int rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if (q != cudaDriverEntryPointSuccess || p == nullptr) return B200PPO_ELIMIT;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(O), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(O) * 4u};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(TCM), static_cast<cuuint32_t>(TCK)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(xhat), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : B200PPO_EINVAL;
+}
+
 // GEMM engine: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (default, fp32-level accuracy),
 // 2 = tcgen05 1xTF32 (JAX-GPU default matmul precision; NOT fp32 parity).  B200PPO_GEMM=ffma|tf32x3|tf32
 int g_gemm_mode = -1;
@@ -1543,7 +1573,15 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     if (use_tc) {
       if (do_dx) B200PPO_LAUNCH_C(2, upd_bwd_dx_tc_kernel, dim3(cdiv(L.R, tile_b)), dim3(TCT), TC_SMEM, s, a, tc_split, 3, tile_b);
       if (do_dw) {
-        if (L.tc_dw_bulk) B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0);
+        if (L.tc_dw_bulk) {
+          CUtensorMap tm;
+          std::memset(&tm, 0, sizeof(tm));
+          if (plan->obs_dim > 256) {
+            const int trc = encode_xhat_map(&tm, ws + L.xhat, plan->obs_dim, L.R);
+            if (trc) return trc;
+          }
+          B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0, tm);
+        }
         else B200PPO_LAUNCH(upd_bwd_dw_tc_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), TC_SMEM, s, a, tc_split, 0);
       }
     } else {

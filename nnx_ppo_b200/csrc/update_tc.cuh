@@ -1122,7 +1122,11 @@ constexpr uint32_t DW2_RAW_B = TCK * TC_MAXN * 4u;           // 16 rows x <= 256
 constexpr uint32_t DW2_RAW_BYTES = DW2_RAW_A + DW2_RAW_B;
 constexpr uint32_t DW2_SMEM = DW2_NS * TC_STAGE_BYTES + DW2_NR * DW2_RAW_BYTES;
 
-__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split, const int item_base) {
+// Observation layers wider than DW2_MAXK (layer 0 of a chain: H = xhat [rows][obs_dim]; dict-observation plans,
+// BASELINE configs[3]) cannot stage full rows: their CTA's 16-row x 128-column block is fetched by ONE 2-D tiled TMA
+// load (`tm_xhat`: tensor map over xhat, box 128 x 16, zero fill beyond obs_dim / the rows) and lands densely.
+__global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split, const int item_base,
+                                                                const __grid_constant__ CUtensorMap tm_xhat) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
   __shared__ uint64_t rbar[2 * DW2_NR];                      // [0..NR) raw full, [NR..2NR) raw empty
@@ -1192,9 +1196,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     // A: thread -> (m = tid & 127, plane q = tid >> 7): rows 4q..4q+3 of column m
     const int am = tid & (TCM - 1), aq = tid >> 7;
     const bool av = am < kw;
-    const uint32_t a_src = static_cast<uint32_t>(((4 * aq) * K + m0 + (av ? am : 0)) * 4);
+    const bool wide = K > DW2_MAXK;                       // raw block = this CTA's 128 columns only (TMA box), else full rows
+    const uint32_t a_src = wide ? static_cast<uint32_t>(((4 * aq) * TCM + (av ? am : 0)) * 4)
+                                : static_cast<uint32_t>(((4 * aq) * K + m0 + (av ? am : 0)) * 4);
     const uint32_t a_dst = aq * pa + am * 16;
-    const uint32_t a_rs = static_cast<uint32_t>(K) * 4u;
+    const uint32_t a_rs = wide ? static_cast<uint32_t>(TCM) * 4u : static_cast<uint32_t>(K) * 4u;
     // B: chunk ids tid and tid + 512 -> (plane p = id / npad, column = id % npad)
     const int c0 = tid, c1 = tid + TC_NPROD;
     const bool bs0 = c0 < 4 * npad, bs1 = c1 < 4 * npad;
@@ -1314,7 +1320,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     // raw-block streamer: 16 full rows of H and of D per stage, one bulk copy each (many small
     // copies are slow: ~100 cycles apiece through the copy engine, measured with 512-byte segments)
     if ((tid & 31) == 0) {
-      const uint32_t bytes_a = static_cast<uint32_t>(TCK) * K * 4u, bytes_b = static_cast<uint32_t>(TCK) * N * 4u;
+      const bool wide = K > DW2_MAXK;
+      const uint32_t bytes_a = static_cast<uint32_t>(TCK) * (wide ? TCM : K) * 4u, bytes_b = static_cast<uint32_t>(TCK) * N * 4u;
       int rslot = 0;
       uint32_t epar = 1u;
       bool first = true;
@@ -1323,7 +1330,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
         const size_t rs = static_cast<size_t>(r_begin) + static_cast<size_t>(s) * TCK;
         if (!first) wait(&raw_empty[rslot], epar);
         tc::mbar_arrive_expect_tx(&raw_full[rslot], bytes_a + bytes_b);
-        tc::bulk_g2s(rw, H + rs * K, bytes_a, &raw_full[rslot]);
+        if (wide) tc::tma_load_2d(rw, &tm_xhat, m0, static_cast<int>(rs), &raw_full[rslot]);
+        else tc::bulk_g2s(rw, H + rs * K, bytes_a, &raw_full[rslot]);
         tc::bulk_g2s(rw + DW2_RAW_A, D + rs * N, bytes_b, &raw_full[rslot]);
         if (++rslot == DW2_NR) { rslot = 0; epar ^= 1u; first = false; }
       }

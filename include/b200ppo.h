@@ -424,6 +424,19 @@ int b200ppo_set_rollout_mode(int mode);
  * this plan keeps its weights resident in the fused kernel and needs none).  With a workspace, networks / envs whose    *
  * weights do not fit shared memory (e.g. 768-wide dict-observation encoders) run every Dense layer of a step as one      *
  * tcgen05 tile GEMM over all B envs instead of re-streaming the weights per 16-env tile; same results contract.          */
+/* The synthetic env's side of ONE rollout step for a policy evaluated elsewhere (the recurrent actor's            *
+ * b200ppo_lstm_seq_forward): `_begin` once per rollout (splits the env matrix into operand planes, copies the env   *
+ * observation into the step's input tile and into obs[0]); `_step` for t = 0 .. T-1: NormalTanhSampler on the actor *
+ * outputs y [B][ldy] (sample count rng_state[2] + 2 t, rollout.py:18 / sampling_layers.py:88-113), env step, reward, *
+ * done / truncation, reset select (rollout.py:19-45), record row t and obs[t + 1]; env state advanced in place.       */
+int64_t b200ppo_synth_env_step_workspace_bytes(int32_t O, int32_t A, int32_t B);
+int b200ppo_synth_env_begin(void* stream, const b200ppo_synth_env* env, int32_t B, const float* env_obs /*dev [B][O]*/,
+                            float* obs0 /*dev [B][O]*/, void* ws, int64_t ws_bytes);
+int b200ppo_synth_env_step(void* stream, const b200ppo_synth_env* env, const float* y, int32_t ldy, float min_std,
+                           float std_scale, const uint32_t* rng_state, const uint32_t* iter_keys, int32_t t, int32_t T,
+                           int32_t B, float* env_obs, int32_t* env_counter, uint32_t* env_term, float* obs,
+                           float* raw_action, float* action, float* loglik, float* reward, uint8_t* done,
+                           uint8_t* truncated, float* next_obs_last, void* ws, int64_t ws_bytes);
 int64_t b200ppo_rollout_synth_workspace_bytes(const b200ppo_plan* plan, int32_t B);
 int b200ppo_rollout_synth_num_launches(const b200ppo_plan* plan, int32_t T, int32_t B, int32_t with_ws);
 int b200ppo_rollout_synth_ws(void* stream, const b200ppo_plan* plan, const b200ppo_synth_env* env,

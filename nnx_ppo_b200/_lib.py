@@ -94,6 +94,10 @@ SYMBOLS = {
     "b200ppo_rollout_synth_ws": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "b200ppo_rollout_synth_workspace_bytes": (_i64, [_PP, _i32]),
+    "b200ppo_synth_env_step_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "b200ppo_synth_env_begin": (C.c_int, [_vp, _EP, _i32, _vp, _vp, _vp, _i64]),
+    "b200ppo_synth_env_step": (C.c_int, [_vp, _EP, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _i32, _i32, _i32,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "b200ppo_rollout_synth_num_launches": (C.c_int, [_PP, _i32, _i32, _i32]),
     "b200ppo_eval_synth": (C.c_int, [_vp, _PP, _EP, _vp, _vp, _vp, _vp, _i32, _i32, _i32,
                                      _vp, _vp, _vp, _vp, _vp]),

@@ -93,7 +93,7 @@ def _build_engine(net, opt, n_envs, T, E, M, lam, gamma, clip, norm_adv, cw, wor
     return eng
 
 
-def _policy(eng, net, obs, t, s):
+def _policy(eng, net, obs, t, s, sample=True):
     """One network call of the rollout on all envs: recurrent actor + sampler (rollout.py:18)."""
     lib, lp, plan = eng.lib, net.lplan, net.plan
     B, A = eng.B, plan.act_dim
@@ -110,6 +110,8 @@ def _policy(eng, net, obs, t, s):
         _lib.check(lib.b200ppo_lstm_step_fwd(s, lp, arena, mean_p, std_p, obs.data_ptr(), 0, 0, B, c.data_ptr(),
                                              h.data_ptr(), eng.r_y.data_ptr(), 0), "lstm_step_fwd(rollout)")
         n = 1
+    if not sample:
+        return n                      # the fused env step samples from eng.r_y itself (same key, same element index)
     _lib.check(lib.b200ppo_sampler_step(s, eng.r_y.data_ptr(), B, A, 0, plan.min_std, plan.std_scale,
                                         plan.entropy_weight, net.counters.data_ptr(), 2 * t, 0,
                                         eng.raw_action[t].data_ptr(), eng.action[t].data_ptr(),
@@ -136,7 +138,38 @@ def _enqueue_iteration(eng, net, env, env_state):
     _lib.check(lib.b200ppo_split_keys_dev(s, eng.iter_keys.data_ptr(), 0, T * B, eng.r_keys.data_ptr()), "split_keys"); n += 1
     keys_all = eng.r_keys.view(T, B, 2)
     # ---------------- rollout (rollout.py:48-73)
-    for t in range(T):
+    # Device envs with fused step kernels (the synthetic env): sampler, env step, reward / done / truncation, reset
+    # select and the transition record are three launches per step (include/b200ppo.h, b200ppo_synth_env_step)
+    # instead of ~20 torch ops incl. an env.reset of every env; same arithmetic, same keys (B200PPO_REC_FUSED_ENV=0
+    # keeps the generic protocol below, which any RLEnv takes).
+    fused_env = (eng.r_seq and getattr(env, "fused_rollout", False) and hasattr(env, "c_struct")
+                 and os.environ.get("B200PPO_REC_FUSED_ENV", "1") != "0")
+    if fused_env:
+        es = env.c_struct(eng.dev)
+        O, A = plan.obs_dim, plan.act_dim
+        nb = int(lib.b200ppo_synth_env_step_workspace_bytes(O, A, B))
+        if getattr(eng, "r_envws", None) is None or eng.r_envws.numel() * 4 < nb:
+            eng.r_envws = torch.zeros((nb + 3) // 4, dtype=torch.float32, device=eng.dev)
+        wsp = eng.r_envws.data_ptr()
+        _lib.check(lib.b200ppo_synth_env_begin(s, es, B, env_state.obs.data_ptr(), eng.obs.data_ptr(), wsp, nb),
+                   "synth_env_begin"); n += 2
+        for t in range(T):
+            n += _policy(eng, net, eng.obs[t], t, s, sample=False)
+            _lib.check(lib.b200ppo_synth_env_step(
+                s, es, eng.r_y.data_ptr(), Y, plan.min_std, plan.std_scale, net.counters.data_ptr(),
+                eng.iter_keys.data_ptr(), t, T, B, env_state.obs.data_ptr(), env_state.step_counter.data_ptr(),
+                env_state.term_state.data_ptr(), eng.obs.data_ptr(), eng.raw_action.data_ptr(), eng.action.data_ptr(),
+                eng.loglik.data_ptr(), eng.reward.data_ptr(), eng.done.data_ptr(), eng.trunc.data_ptr(),
+                eng.next_obs_last.data_ptr(), wsp, nb), "synth_env_step"); n += 3
+            done = eng.done[t].bool()
+            if net.init_views is None:                                   # reset_state -> zeros (rollout.py:33-40)
+                keep = (~done).to(torch.float32)[:, None]
+                c.mul_(keep)
+                h.mul_(keep)
+            else:
+                torch.where(done[:, None], net.init_views[0], c, out=c)
+                torch.where(done[:, None], net.init_views[1], h, out=h)
+    for t in range(0 if fused_env else T):                               # generic RLEnv protocol
         obs = env_state.obs.contiguous()
         n += _policy(eng, net, obs, t, s)
         nxt = env.step(env_state, eng.action[t])

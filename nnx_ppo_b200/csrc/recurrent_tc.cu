@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(256) wide_init_kernel(const float* __restrict_
     const float v = env_obs[i];
     X[e * ldx + o] = v;
     obs0[i] = v;
-    Xn[e * ldo + o] = mean != nullptr ? __fdiv_rn(v - mean[o], stdv[o]) : v;
+    if (Xn != nullptr) Xn[e * ldo + o] = mean != nullptr ? __fdiv_rn(v - mean[o], stdv[o]) : v;
   }
 }
 
@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(256) wide_book_kernel(const WideBookArgs a) {
     if (last) a.next_obs_last[static_cast<size_t>(e) * a.O + o] = v;
     const float nv = dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v;
     a.X[static_cast<size_t>(e) * a.ldx + o] = nv;
-    a.Xn[static_cast<size_t>(e) * a.ldo + o] = a.mean != nullptr ? __fdiv_rn(nv - a.mean[o], a.stdv[o]) : nv;
+    if (a.Xn != nullptr) a.Xn[static_cast<size_t>(e) * a.ldo + o] = a.mean != nullptr ? __fdiv_rn(nv - a.mean[o], a.stdv[o]) : nv;
     if (a.obs_next != nullptr) a.obs_next[static_cast<size_t>(e) * a.O + o] = nv;
     if (last) a.env_obs[static_cast<size_t>(e) * a.O + o] = nv;
   };
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256) wide_book_kernel(const WideBookArgs a) {
         xn.z = __fdiv_rn(nv.z - m.z, sd.z); xn.w = __fdiv_rn(nv.w - m.w, sd.w);
       }
       *reinterpret_cast<float4*>(a.X + static_cast<size_t>(e) * a.ldx + o) = nv;
-      *reinterpret_cast<float4*>(a.Xn + static_cast<size_t>(e) * a.ldo + o) = xn;
+      if (a.Xn != nullptr) *reinterpret_cast<float4*>(a.Xn + static_cast<size_t>(e) * a.ldo + o) = xn;
       if (a.obs_next != nullptr) *reinterpret_cast<float4*>(a.obs_next + static_cast<size_t>(e) * a.O + o) = nv;
       if (last) {
         *reinterpret_cast<float4*>(a.next_obs_last + static_cast<size_t>(e) * a.O + o) = v;
@@ -1185,6 +1185,107 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
   return 0;
 }
 }  // namespace b200ppo
+
+// ------------------------------------------------------------------------------------------
+// The synthetic env's side of one rollout step for policies evaluated elsewhere (the recurrent actor): sampler on the
+// actor outputs, env GEMM, bookkeeping - the last three launches of the batched rollout above, same kernels.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct EnvStepLayout {
+  int ldx, ldo, n_tile;
+  size_t x, zenv, ynext, llterm, planes, total;
+};
+EnvStepLayout env_step_layout(int O, int A, int B) {
+  EnvStepLayout L;
+  L.ldx = (O + A + 3) & ~3;
+  L.ldo = (O + 3) & ~3;
+  L.n_tile = cdiv(B, RM) * cdiv(O, 256) >= b200ppo_num_sms() ? 256 : 128;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
+  L.x = take(static_cast<size_t>(B) * L.ldx);
+  L.zenv = take(static_cast<size_t>(B) * L.ldo);
+  L.ynext = take(static_cast<size_t>(B) * L.ldo);
+  L.llterm = take(static_cast<size_t>(B) * A);
+  L.planes = take(planes_floats(O + A, O, L.n_tile));
+  L.total = o;
+  return L;
+}
+int check_env_step(const b200ppo_synth_env* env, int B, const void* ws, int64_t ws_bytes) {
+  if (!env || !env->Wo || !env->Wa || env->obs_dim <= 0 || env->act_dim <= 0 || B <= 0 || !ws) return B200PPO_EINVAL;
+  if (env->Wa != env->Wo + static_cast<size_t>(env->obs_dim) * env->obs_dim) return B200PPO_EINVAL;
+  if (ws_bytes < static_cast<int64_t>(4 * env_step_layout(env->obs_dim, env->act_dim, B).total)) return B200PPO_EINVAL;
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t b200ppo_synth_env_step_workspace_bytes(int32_t O, int32_t A, int32_t B) {
+  if (O <= 0 || A <= 0 || B <= 0) return -1;
+  return static_cast<int64_t>(4 * env_step_layout(O, A, B).total);
+}
+
+extern "C" int b200ppo_synth_env_begin(void* stream, const b200ppo_synth_env* env, int32_t B, const float* env_obs,
+                                       float* obs0, void* ws, int64_t ws_bytes) {
+  int rc = check_env_step(env, B, ws, ws_bytes);
+  if (rc) return rc;
+  if (!env_obs || !obs0) return B200PPO_EINVAL;
+  rc = set_attrs_tc();
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int O = env->obs_dim, A = env->act_dim;
+  const EnvStepLayout L = env_step_layout(O, A, B);
+  float* w = static_cast<float*>(ws);
+  const int Nt = planes_ntile(O, L.n_tile);
+  const int tiles = cdiv(O, Nt), nst = cdiv(O + A, RK);
+  const size_t total = static_cast<size_t>(tiles) * nst * (RK / 4) * (Nt + 1);
+  rg_prep_b_kernel<<<cdiv(static_cast<int64_t>(total), 256), 256, 0, s>>>(env->Wo, O, O + A, O, Nt, nst, tiles,
+                                                                        reinterpret_cast<float4*>(w + L.planes));
+  B200PPO_LAUNCH_CHECK();
+  wide_init_kernel<<<cdiv(static_cast<int64_t>(B) * O, 256 * 8), 256, 0, s>>>(env_obs, B, O, w + L.x, L.ldx, obs0, nullptr, 0,
+                                                                             nullptr, nullptr);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200ppo_synth_env_step(void* stream, const b200ppo_synth_env* env, const float* y, int32_t ldy,
+                                      float min_std, float std_scale, const uint32_t* rng_state,
+                                      const uint32_t* iter_keys, int32_t t, int32_t T, int32_t B, float* env_obs,
+                                      int32_t* env_counter, uint32_t* env_term, float* obs, float* raw_action,
+                                      float* action, float* loglik, float* reward, uint8_t* done, uint8_t* truncated,
+                                      float* next_obs_last, void* ws, int64_t ws_bytes) {
+  int rc = check_env_step(env, B, ws, ws_bytes);
+  if (rc) return rc;
+  if (!y || !rng_state || !iter_keys || !env_obs || !env_counter || !env_term || !obs || !raw_action || !action ||
+      !loglik || !reward || !done || !truncated || !next_obs_last || t < 0 || t >= T || ldy < 2 * env->act_dim)
+    return B200PPO_EINVAL;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int O = env->obs_dim, A = env->act_dim;
+  const EnvStepLayout L = env_step_layout(O, A, B);
+  float* w = static_cast<float*>(ws);
+  float* X = w + L.x;
+  const size_t row0 = static_cast<size_t>(t) * B;
+  wide_sampler_kernel<<<cdiv(static_cast<int64_t>(B) * A, 256), 256, 0, s>>>(
+      y, ldy, B, A, min_std, std_scale, rng_state, static_cast<uint32_t>(t), raw_action + row0 * A, action + row0 * A, X,
+      L.ldx, O, w + L.llterm);
+  B200PPO_LAUNCH_CHECK();
+  GemmArgs g = gemm_defaults();
+  g.A = X; g.lda = L.ldx; g.M = B; g.K = O + A;
+  g.B = env->Wo; g.ldb = O;
+  g.Bplanes = w + L.planes;
+  g.C = w + L.zenv; g.ldc = L.ldo;
+  g.C2 = w + L.ynext; g.ldc2 = L.ldo; g.act_c2 = B200PPO_ACT_TANH;
+  rc = launch_gemm(s, g, O, 1, L.n_tile);
+  if (rc) return rc;
+  WideBookArgs b;
+  b.B = B; b.O = O; b.A = A; b.T = T; b.t = t; b.max_len = env->max_len; b.term_thresh16 = env->term_thresh16;
+  b.ldx = L.ldx; b.ldo = L.ldo; b.iter_keys = iter_keys; b.ynext = w + L.ynext; b.llterm = w + L.llterm; b.X = X;
+  b.Xn = nullptr; b.mean = nullptr; b.stdv = nullptr;
+  b.obs_next = t + 1 < T ? obs + (row0 + B) * O : nullptr;
+  b.loglik = loglik + row0; b.reward = reward + row0; b.done = done + row0; b.trunc = truncated + row0;
+  b.next_obs_last = next_obs_last; b.env_obs = env_obs; b.env_counter = env_counter; b.env_term = env_term;
+  wide_book_kernel<<<cdiv(B, 8), 256, 0, s>>>(b);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int b200ppo_lstm_set_persistent(int on) {
   const int prev = g_seq_persist < 0 ? -1 : g_seq_persist;

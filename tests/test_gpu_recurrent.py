@@ -138,11 +138,15 @@ def test_recurrent_replay_and_bptt_match_oracle(cuda_device, cfg):
     assert np.all(outs[0][n_rec:] == 7.0)
 
 
+@pytest.mark.parametrize("fused_env", ["1", "0"])
 @pytest.mark.parametrize("trainable", [False, True])
-def test_recurrent_ppo_step_matches_oracle(cuda_device, trainable):
+def test_recurrent_ppo_step_matches_oracle(cuda_device, trainable, fused_env, monkeypatch):
     """Public API (`ppo.ppo_step`) with an LSTM actor against oracle/recurrent.py over iterations:
     bit-exact masks / minibatch indices / counters, float32-tolerance losses and parameters
-    (reference: recurrent_test.py:285-330 only checks finiteness and that parameters change)."""
+    (reference: recurrent_test.py:285-330 only checks finiteness and that parameters change).
+    fused_env: the synthetic env's step as three kernels (b200ppo_synth_env_step) or through the generic RLEnv
+    protocol (env.step / env.reset / tree_where in torch ops)."""
+    monkeypatch.setenv("B200PPO_REC_FUSED_ENV", fused_env)
     from nnx_ppo_b200 import Rngs
     from nnx_ppo_b200.algorithms import ppo
     from nnx_ppo_b200.envs import SyntheticEnv

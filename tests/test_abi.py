@@ -275,6 +275,23 @@ def test_rollout_and_policy_launchers_reject_before_launching(lib):
     env.Wa -= 4
     assert lib.b200ppo_eval_synth(None, net.plan, env, p, p, p, p, 1, 10, 32, p, p, p, p, p) == EINVAL   # mode: 0 or 2
     assert lib.b200ppo_eval_synth(None, net.plan, env, p, p, p, p, 2, 0, 32, p, p, p, p, p) == EINVAL    # L
+    # the env half of a rollout step for policies evaluated elsewhere: same host-side checks
+    nb = int(lib.b200ppo_synth_env_step_workspace_bytes(12, 3, 32))
+    assert nb > 0 and nb % 4 == 0 and int(lib.b200ppo_synth_env_step_workspace_bytes(0, 3, 32)) == -1
+    assert lib.b200ppo_synth_env_begin(None, env, 32, p, p, p, nb - 4) == EINVAL         # workspace too small
+    assert lib.b200ppo_synth_env_begin(None, env, 32, None, p, p, nb) == EINVAL          # env observations
+    assert lib.b200ppo_synth_env_begin(None, env, 0, p, p, p, nb) == EINVAL              # B
+    step_ok = [None, env, p, 6, 0.1, 1.0, p, p, 0, 8, 32] + [p] * 11 + [p, nb]
+    def env_step(**kw):
+        a = list(step_ok)
+        for i, v in kw.items():
+            a[int(i[1:])] = v
+        return lib.b200ppo_synth_env_step(*a)
+    assert env_step(a2=None) == EINVAL                     # actor outputs
+    assert env_step(a3=5) == EINVAL                        # ldy < 2 * act_dim
+    assert env_step(a8=8) == EINVAL and env_step(a8=-1) == EINVAL      # t outside [0, T)
+    assert env_step(a23=nb - 4) == EINVAL                  # workspace too small
+    assert env_step(a22=None) == EINVAL                    # no workspace
     # tiles that cannot fit in shared memory even without the k-split scratch tile
     wide = CompiledNet(factories.make_mlp_actor_critic(6000, 3, [16], [16], prng.Rngs(0)), torch.device("cpu"))
     wenv = _lib.SynthEnv()

@@ -207,17 +207,18 @@ __device__ __forceinline__ uint32_t pow2_cols(int n) {
   return c;
 }
 
-// bars: [0..1] empty, [2..3] full (`full_count` arrivals each), [4] done
-__device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot, int ncols, int full_count) {
+// bars: [0..ns) empty, [ns..2 ns) full (`full_count` arrivals each), [2 ns] done; ns = ring depth (2, or 3 for the bulk-fed GEMM)
+__device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot, int ncols, int full_count,
+                                          int ns = 2) {
   const int warp = threadIdx.x >> 5;
   p.tmem_cols = pow2_cols(ncols);
   if (warp == 0) tc::tmem_alloc(tmem_slot, p.tmem_cols);
   if (threadIdx.x == 32) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
-    tc::mbar_init(&bars[2], full_count);
-    tc::mbar_init(&bars[3], full_count);
-    tc::mbar_init(&bars[4], 1);
+    for (int i = 0; i < ns; ++i) {
+      tc::mbar_init(&bars[i], 1);
+      tc::mbar_init(&bars[ns + i], full_count);
+    }
+    tc::mbar_init(&bars[2 * ns], 1);
     tc::mbar_init_fence();
   }
   tc::tc_fence_before();
@@ -225,8 +226,8 @@ __device__ __forceinline__ void pipe_init(Pipe& p, uint8_t* smem, uint64_t* bars
   tc::tc_fence_after();
   p.smem = smem;
   p.bar_empty = bars;
-  p.bar_full = bars + 2;
-  p.bar_done = bars + 4;
+  p.bar_full = bars + ns;
+  p.bar_done = bars + 2 * ns;
   p.tmem_base = *tmem_slot;
 }
 
@@ -265,6 +266,10 @@ __device__ __forceinline__ void issue_slab(const Pipe& p, uint8_t* st, uint32_t 
   }
 }
 
+// operand ring depth: 3 slots for the bulk-fed kernel when three stages fit shared memory (column tiles <= 128), else 2
+template <int NB>
+__host__ __device__ inline int gemm_ring_depth(int N) { return (NB == 0 && N <= 128) ? 3 : 2; }
+
 // B operand of stage s from the pre-split planes: one bulk copy, completion counted on the stage's full barrier
 // (the issuing thread's expect_tx arrival is the extra arrival pipe_init is told about)
 __device__ __forceinline__ void gemm_bulk_b(const GemmArgs& g, const Pipe& p, int buf, int s, int nst, uint32_t pa,
@@ -288,21 +293,93 @@ __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, 
   const int nst = (g.K + RK - 1) / RK;
   if (threadIdx.x >= RT) {                                   // issuer warp
     const uint32_t idesc = tc::make_idesc_tf32(RM, g.N);
+    const int ns = gemm_ring_depth<NB>(g.N);
     for (int s = 0; s < nst; ++s) {
-      const int buf = s & 1;
-      tc::mbar_wait(&p.bar_full[buf], static_cast<uint32_t>(s >> 1) & 1u);
+      const int buf = s % ns;
+      tc::mbar_wait(&p.bar_full[buf], static_cast<uint32_t>(s / ns) & 1u);
       issue_slab<RK / 8>(p, p.smem + buf * sbytes, pa, pb, idesc, s == 0, s == nst - 1, buf);
     }
     return;
   }
   const bool lane0 = (threadIdx.x & 31) == 0;
+  if (NB == 0) {
+    // bulk-fed B operand: the copy of stage s can only be issued once its ring slot is free, and its latency
+    // (~1 K cycles for 33 KB) is exposed with two slots (the slot of stage s frees when the MMAs of stage s - 2 retire,
+    // one MMA time before stage s is needed).  Three slots (tiles of <= 128 columns: 3 x 66 KB) give it two MMA times.
+    const int ns = gemm_ring_depth<NB>(g.N);
+    // lean A path: the generic loaders spend ~280 dependent instructions per warp and stage on addresses, bounds and the
+    // activation switch (ncu: 8.7 cycles per issued instruction with 9 warps per SM = 2.4 K cycles per stage, the whole
+    // stage time).  Per-thread row pointers and shared-memory offsets are hoisted; a stage that lies fully inside K takes
+    // four predicated 16-byte loads.
+    const int tid = threadIdx.x;
+    const bool a_al = ((g.lda | kbase_a) & 3) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+    const float* ap[4];
+    bool av[4];
+    uint32_t so[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = tid + j * RT;
+      const int q = idx & 7, r = idx >> 3;
+      av[j] = row0 + r < g.M;
+      ap[j] = g.A + static_cast<size_t>(av[j] ? row0 + r : 0) * g.lda + kbase_a + 4 * q;
+      so[j] = q * pa + r * 16;
+    }
+    const int act_a = g.act_a;
+    auto ld = [&](int s, float4 (&x)[4]) {
+      const int k0 = s * RK;
+      if (s < nst && a_al && k0 + RK <= g.K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = av[j] ? __ldg(reinterpret_cast<const float4*>(ap[j] + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + 4 * ((tid + j * RT) & 7);
+          x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (s < nst && av[j] && k < g.K) x[j] = ld4_guard(ap[j] + k0, k, g.K, a_al);
+        }
+      }
+    };
+    auto put = [&](int s, const float4 (&x)[4]) {
+      const int buf = s % ns;
+      if (s >= ns) tc::mbar_wait(&p.bar_empty[buf], static_cast<uint32_t>(s / ns - 1) & 1u);
+      if (tid == 0) gemm_bulk_b(g, p, buf, s, nst, pa, pb, sbytes);
+      uint8_t* a_hi = p.smem + buf * sbytes;
+      uint8_t* a_lo = a_hi + (RK / 4) * pa;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 v = x[j];
+        if (act_a == B200PPO_ACT_RELU) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        } else if (act_a != B200PPO_ACT_NONE) {
+          v.x = act_fwd(v.x, act_a); v.y = act_fwd(v.y, act_a); v.z = act_fwd(v.z, act_a); v.w = act_fwd(v.w, act_a);
+        }
+        float4 hi, lo;
+        tc::split4_fast(v, hi, lo);
+        *reinterpret_cast<float4*>(a_hi + so[j]) = hi;
+        *reinterpret_cast<float4*>(a_lo + so[j]) = lo;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane0) tc::mbar_arrive(&p.bar_full[buf]);
+    };
+    float4 y0[4], y1[4];
+    ld(0, y0);
+    for (int s = 0; s < nst; s += 2) {
+      ld(s + 1, y1);
+      put(s, y0);
+      if (s + 1 < nst) {
+        ld(s + 2, y0);
+        put(s + 1, y1);
+      }
+    }
+    return;
+  }
   uint32_t phase0 = 0u, phase1 = 0u;
   StageRegs x0, x1;
   gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, 0, nst, x0);
   for (int s = 0; s < nst; s += 2) {
     gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 1, nst, x1);
     if (s >= 2) { tc::mbar_wait(&p.bar_empty[0], phase0); phase0 ^= 1u; }
-    if (NB == 0 && threadIdx.x == 0) gemm_bulk_b(g, p, 0, s, nst, pa, pb, sbytes);
     gemm_store_stage<NB>(g, p.smem, x0);
     tc::fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core
     __syncwarp();
@@ -310,7 +387,6 @@ __device__ __forceinline__ void gemm_mainloop(const GemmArgs& g, const Pipe& p, 
     if (s + 1 < nst) {
       gemm_load_stage<NB>(g, row0, kbase_a, kbase_b, col0, s + 2, nst, x0);
       if (s >= 2) { tc::mbar_wait(&p.bar_empty[1], phase1); phase1 ^= 1u; }
-      if (NB == 0 && threadIdx.x == 0) gemm_bulk_b(g, p, 1, s + 1, nst, pa, pb, sbytes);
       gemm_store_stage<NB>(g, p.smem + sbytes, x1);
       tc::fence_proxy_async();
       __syncwarp();
@@ -327,10 +403,10 @@ __device__ __forceinline__ void wait_acc(const Pipe& p) {
 template <int NB>
 __global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[7];
   __shared__ uint32_t tmem_slot;
   Pipe p;
-  pipe_init(p, smem, bars, &tmem_slot, g.N, RT / 32 + (NB == 0 ? 1 : 0));
+  pipe_init(p, smem, bars, &tmem_slot, g.N, RT / 32 + (NB == 0 ? 1 : 0), gemm_ring_depth<NB>(g.N));
   const int row0 = blockIdx.x * RM;
   const int tile = blockIdx.y, slice = blockIdx.z;
   const int col0 = g.b_col0 + tile * g.tile_stride;
@@ -342,6 +418,7 @@ __global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
   const int row = row0 + sub * 32 + lane;
   float* Cb = g.C + static_cast<long long>(slice) * g.c_slice_stride;
   const bool vec_c = (g.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cb) & 15) == 0;
+  const bool vec_c2 = g.C2 != nullptr && (g.ldc2 & 3) == 0 && (reinterpret_cast<uintptr_t>(g.C2) & 15) == 0;
   if (threadIdx.x < RT) wait_acc(p);
   for (int c = cg * 16; c < g.N && threadIdx.x < RT; c += 32) {
     float v[16];
@@ -366,7 +443,9 @@ __global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
         const int n = n0 + 4 * i;
         if (n >= g.n_real) break;
         const float4 val = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        if (g.c_planes) {
+        if (g.C == nullptr) {
+          // only the activated copy is wanted (the env step's tanh): no pre-activation store
+        } else if (g.c_planes) {
           *reinterpret_cast<float4*>(Cb + (static_cast<size_t>(row >> 7) * g.c_cols4 + (n >> 2)) * (RM * 4) + (row & (RM - 1)) * 4) = val;
         } else if (vec_c && n + 3 < g.n_real) {
           *reinterpret_cast<float4*>(Cb + static_cast<size_t>(row) * g.ldc + n) = val;
@@ -377,8 +456,13 @@ __global__ void __launch_bounds__(RTI, 1) rg_gemm_kernel(const GemmArgs g) {
         }
         if (g.C2 != nullptr) {
           const float vv[4] = {val.x, val.y, val.z, val.w};
-          for (int j = 0; j < 4; ++j)
-            if (n + j < g.n_real) g.C2[static_cast<size_t>(row) * g.ldc2 + n + j] = act_fwd(vv[j], g.act_c2);
+          if (vec_c2 && n + 3 < g.n_real) {
+            *reinterpret_cast<float4*>(g.C2 + static_cast<size_t>(row) * g.ldc2 + n) =
+                make_float4(act_fwd(vv[0], g.act_c2), act_fwd(vv[1], g.act_c2), act_fwd(vv[2], g.act_c2), act_fwd(vv[3], g.act_c2));
+          } else {
+            for (int j = 0; j < 4; ++j)
+              if (n + j < g.n_real) g.C2[static_cast<size_t>(row) * g.ldc2 + n + j] = act_fwd(vv[j], g.act_c2);
+          }
         }
       }
     }
@@ -797,7 +881,8 @@ int set_attrs_tc() {
   if (g_attr_tc) return 0;
   const int big = 2 * static_cast<int>(stage_bytes_nn(256));
   cudaError_t e;
-  e = cudaFuncSetAttribute(rg_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  e = cudaFuncSetAttribute(rg_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           big > 3 * static_cast<int>(stage_bytes_nn(128)) ? big : 3 * static_cast<int>(stage_bytes_nn(128)));
   if (e != cudaSuccess) return static_cast<int>(e);
   e = cudaFuncSetAttribute(rg_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return static_cast<int>(e);
@@ -849,7 +934,8 @@ int launch_gemm(cudaStream_t s, GemmArgs g, int n_real, int slices, int n_tile =
   const int tiles = cdiv(n_real, g.N);
   const dim3 grid(cdiv(g.M, RM), tiles, slices);
   const size_t smem = 2 * static_cast<size_t>(stage_bytes_nn(g.N));
-  if (g.Bplanes != nullptr) rg_gemm_kernel<0><<<grid, RTI, smem, s>>>(g);
+  if (g.Bplanes != nullptr && g.a_mean != nullptr) return B200PPO_EINVAL;     // the bulk-fed kernel's A path does not normalise
+  if (g.Bplanes != nullptr) rg_gemm_kernel<0><<<grid, RTI, gemm_ring_depth<0>(g.N) * static_cast<size_t>(stage_bytes_nn(g.N)), s>>>(g);
   else if (g.N <= 32) rg_gemm_kernel<1><<<grid, RTI, smem, s>>>(g);
   else if (g.N <= 64) rg_gemm_kernel<2><<<grid, RTI, smem, s>>>(g);
   else rg_gemm_kernel<8><<<grid, RTI, smem, s>>>(g);
@@ -962,9 +1048,9 @@ WideLayout wide_layout(const b200ppo_plan& p, int B) {
   L.zenv = take(static_cast<size_t>(B) * L.ldo);
   L.ynext = take(static_cast<size_t>(B) * L.ldo);
   const int row_tiles = cdiv(B, RM);
-  // 256-column tiles on layers with enough row tiles to fill the device, 128 otherwise (B200PPO_WIDE_NTILE=128: always
-  // 128; measured equal at configs[3]: 42.0 vs 42.3 ms per iteration)
-  static const int want256 = [] { const char* e = std::getenv("B200PPO_WIDE_NTILE"); return e && std::atoi(e) == 128 ? 0 : 1; }();
+  // 128-column tiles: three operand stages fit shared memory (B200PPO_WIDE_NTILE=256: 256-column tiles with a two-slot
+  // ring on layers with enough row tiles to fill the device)
+  static const int want256 = [] { const char* e = std::getenv("B200PPO_WIDE_NTILE"); return e && std::atoi(e) == 256 ? 1 : 0; }();
   auto n_tile_for = [&](int N) { return (want256 && row_tiles * cdiv(N, 256) >= b200ppo_num_sms()) ? 256 : 128; };
   for (int l = 0; l < p.actor.n_layers; ++l) {
     L.n_tile[l] = n_tile_for(p.actor.dims[l + 1]);
@@ -1168,7 +1254,7 @@ int rollout_wide(cudaStream_t s, const RolloutWideArgs& a) {
       g.A = X; g.lda = W.ldx; g.M = B; g.K = O + A;
       g.B = a.Wenv; g.ldb = O;
       g.Bplanes = a.ws + W.planes[L];
-      g.C = zenv; g.ldc = W.ldo;
+      g.C = nullptr; g.ldc = W.ldo;
       g.C2 = ynext; g.ldc2 = W.ldo; g.act_c2 = B200PPO_ACT_TANH;
       rc = launch_gemm(s, g, O, 1, W.n_tile[L]);
       if (rc) return rc;
@@ -1199,7 +1285,7 @@ EnvStepLayout env_step_layout(int O, int A, int B) {
   EnvStepLayout L;
   L.ldx = (O + A + 3) & ~3;
   L.ldo = (O + 3) & ~3;
-  L.n_tile = cdiv(B, RM) * cdiv(O, 256) >= b200ppo_num_sms() ? 256 : 128;
+  L.n_tile = 128;                       // three-slot operand ring (see gemm_ring_depth)
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o = al64(o + n); return r; };
   L.x = take(static_cast<size_t>(B) * L.ldx);
@@ -1271,7 +1357,7 @@ extern "C" int b200ppo_synth_env_step(void* stream, const b200ppo_synth_env* env
   g.A = X; g.lda = L.ldx; g.M = B; g.K = O + A;
   g.B = env->Wo; g.ldb = O;
   g.Bplanes = w + L.planes;
-  g.C = w + L.zenv; g.ldc = L.ldo;
+  g.C = nullptr; g.ldc = L.ldo;
   g.C2 = w + L.ynext; g.ldc2 = L.ldo; g.act_c2 = B200PPO_ACT_TANH;
   rc = launch_gemm(s, g, O, 1, L.n_tile);
   if (rc) return rc;

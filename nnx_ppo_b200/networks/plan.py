@@ -377,10 +377,11 @@ class CompiledNet:
         n = int(_lib.load().b200ppo_rollout_synth_workspace_bytes(self.plan, B))
         if n <= 0:
             return 0, 0
+        # one buffer per env count, never freed while the network lives: a captured iteration graph keeps the pointer
+        # it was recorded with (~100 MB at configs[3]; only plans wider than shared memory get here)
         cache = self.__dict__.setdefault("_rollout_ws", {})
         ws = cache.get(B)
         if ws is None or ws.numel() * 4 < n:
-            cache.clear()                                  # one live size: the buffers are ~100 MB at configs[3]
             ws = cache[B] = torch.zeros((n + 3) // 4, dtype=torch.float32, device=self.device)
         return ws.data_ptr(), n
 

@@ -215,7 +215,7 @@ def test_rollout_engine_selection_is_host_logic(lib):
     L = wide.plan.actor.n_layers
     assert L == 5
     ws = int(lib.b200ppo_rollout_synth_workspace_bytes(wide.plan, 8192))
-    assert 80e6 < ws < 200e6 and ws % 4 == 0
+    assert 80e6 < ws < 300e6 and ws % 4 == 0
     assert int(lib.b200ppo_rollout_synth_num_launches(wide.plan, 32, 8192, 1)) == (L + 1) + 1 + 32 * (L + 3)
     assert int(lib.b200ppo_rollout_synth_num_launches(wide.plan, 32, 8192, 0)) == 1        # no workspace: fused kernel
     assert int(lib.b200ppo_rollout_synth_workspace_bytes(wide.plan, 256)) == 0             # few envs: tiles would idle

@@ -7,10 +7,14 @@
 //
 // Design: every env is an independent unit, so one CTA owns a tile of TE envs for ALL T steps
 // (no grid-wide synchronisation, one launch per rollout).  Actor + env weights are staged once
-// in shared memory and re-used for T steps; activations ping-pong between two smem tiles;
-// each thread computes a 2-env x 4-column register tile per layer, and layers with fewer tiles than
-// threads split their k range over the idle threads (dense_tile).  The evaluation rollout
-// (rollout.py:97-148) is the same loop without the transition record and with sticky done flags.
+// in shared memory and re-used for T steps; activations ping-pong between two smem tiles.
+// Two Dense engines: rollout_synth_mma_kernel (default) runs a layer as warp-level tensor-core tiles
+// (mma.sync m16n8k8, 3xTF32, weights in fragment order); rollout_synth_kernel / eval_synth_kernel /
+// policy_step_kernel compute a 2-env x 4-column FFMA register tile per thread, and layers with fewer
+// tiles than threads split their k range over the idle threads (dense_tile).  Networks whose weights do
+// not fit shared memory go to the batched per-step path (rollout_wide, csrc/recurrent_tc.cu) when the
+// caller passes a workspace (b200ppo_rollout_synth_ws).  The evaluation rollout (rollout.py:97-148) is
+// the same loop without the transition record and with sticky done flags.
 #include <cstdlib>
 #include <cstring>
 

@@ -945,9 +945,11 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     }
   }
   double lq[NLQ] = {l_actor, l_critic, l_reg, l_clip, l_t1, l_t2};
+  // only the first lane of every AP-lane row group holds a term: butterfly over those lanes only (offsets AP, 2 AP, ..:
+  // 2 steps instead of 5 for A = 8; 12 shuffles + 6 fp64 adds per step saved for every warp)
 #pragma unroll
   for (int q = 0; q < NLQ; ++q) {
-    lq[q] = warp_sum_d(lq[q]);
+    for (int o = AP; o < 32; o <<= 1) lq[q] += __shfl_xor_sync(0xffffffffu, lq[q], o);
     if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = lq[q];
   }
   __syncthreads();

@@ -1,5 +1,5 @@
 """Policy distillation — same public API as nnx_ppo/algorithms/distillation.py (``train_distillation`` :422,
-``distillation_step`` :235, ``new_distillation_state`` :363, ``default_distillation_config`` :63) on the
+``distillation_loss`` :160, ``distillation_step`` :235, ``new_distillation_state`` :363, ``default_distillation_config`` :63) on the
 kernels of the PPO path.
 
 One iteration is the PPO launch sequence with two changes (include/b200ppo.h, B200PPO_STAGE_NLL):
@@ -112,6 +112,55 @@ def _distillation_metrics(per_update: np.ndarray, eng, logging_level, percentile
     lvl = logging_level & (LoggingLevel.TRAIN_ROLLOUT_STATS | LoggingLevel.TRAINING_ENV_METRICS)   # :334-349
     _extra_metrics(m, eng.net, eng, lvl, percentiles)
     return m
+
+
+def distillation_loss(student: StatefulModule, student_state: Any, rollout_data, logging_level: LoggingLevel, *,
+                      return_grads: bool = False):
+    """distillation.py:160-232 as a callable: ``(total_loss, loss_metrics)`` of one minibatch ``DistillationTransition``
+    ([T, mb, ...] leaves, the teacher's rollout_extras holding its raw-space mean at the sampler position) under the
+    student's CURRENT parameters - stages FWD | LOSS (NLL head) of the update kernels on the rows in their given order.
+    Like the reference call it advances the student's sampler stream by 2 * T counts.  The reference differentiates
+    this function with ``nnx.grad``; here the analytic backward is part of the same kernels: ``return_grads=True`` also
+    runs BWD | RED and returns the flat gradient (``CompiledNet.params_logical`` order) as a third element."""
+    import torch
+    net = compile_network(student)
+    if net.recurrent:
+        raise NotImplementedError("distillation runs on the MLP plans")
+    lib = _lib.load()
+    T, mb = rollout_data.rewards.shape
+
+    def build():
+        eng = PPOEngine.__new__(PPOEngine)
+        fake_env = type("E", (), {"fused_rollout": True})()
+        PPOEngine.__init__(eng, net, fake_env, AdamOptimizer(net), mb, T, 1, 1, 0.0, 0.0, 0.0, False, 0.0, world_size=1,
+                           group=None, use_graph=False)
+        eng.inds.copy_(torch.arange(mb, dtype=torch.int32, device=net.device).reshape(1, mb))
+        return eng
+
+    eng = cached_engine(net, "distill_loss", None, None, (T, mb), build)
+    eng._upload_block((0, 0), (0, 0))
+    eng.obs.copy_(net.flat_obs(rollout_data.obs).reshape(T, mb, -1))
+    eng.raw_action.copy_(net.adapter_extras(rollout_data.teacher_rollout_extras)["action"][-1].reshape(T, mb, -1))
+    eng.done.copy_(rollout_data.done.to(torch.uint8))
+    s = _lib.current_stream()
+    if net.normalizer is not None:
+        net.normalizer.prepare(s)
+    net.sync_counters_to_device()
+    stages = _lib.STAGE_FWD | _lib.STAGE_LOSS | _lib.STAGE_NLL
+    if return_grads:
+        stages |= _lib.STAGE_BWD | _lib.STAGE_RED
+    _lib.check(lib.b200ppo_update(s, net.plan, eng.hp, eng.bufs[0], T, mb, mb, 0, 0, stages), "distillation_loss")
+    net.advance_rng(2 * T)
+    net.sync_counters_to_device()
+    row = eng.metrics[0].cpu().numpy()
+    total = np.float32(row[0] + row[2])                                      # :222
+    loss_metrics: dict[str, Any] = {}
+    if LoggingLevel.LOSSES in logging_level:                                # :225-228
+        loss_metrics["losses/distillation_nll"] = np.float32(row[0])
+        loss_metrics["losses/regularization"] = np.float32(row[2])
+    if return_grads:
+        return total, loss_metrics, net.params_logical(eng.grad)
+    return total, loss_metrics
 
 
 def distillation_step(env: RLEnv, teacher: StatefulModule, distillation_state: DistillationState, n_envs: int,

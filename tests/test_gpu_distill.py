@@ -121,3 +121,32 @@ def test_train_distillation_api(dev):
     # (the NLL is not monotone over iterations here: the student's Normalizer statistics and its state distribution
     # move under it; the fixed-batch decrease is asserted on the oracle in tests/test_oracle_distill.py)
     assert all(np.isfinite(m["losses/distillation_nll/mean"]) for _, m in logs[1:])
+
+
+def test_distillation_loss_callable_matches_oracle(dev):
+    """`distillation_loss(student, student_state, rollout_data, logging_level)` (distillation.py:160-232) on one
+    minibatch DistillationTransition against oracle/distill.py: loss terms, analytic gradient, sampler counts."""
+    from nnx_ppo_b200.algorithms.types import DistillationTransition
+    O, A, T, mb = 24, 3, 7, 40
+    student, teacher, ostudent, oteacher = _nets(O, A, [48, 32], [40], "tanh")
+    g = np.random.default_rng(5)
+    obs = g.standard_normal((T, mb, O)).astype(np.float32)
+    hist = (0.3 + 2.0 * g.standard_normal((3, 50, O))).astype(np.float32)
+    student.layers[0].update_statistics(torch.from_numpy(hist).to(dev)); ostudent.update_statistics(hist)
+    mu_t = odistill.teacher_means(oteacher, obs)
+    net = compile_network(student)
+    extras = net.wrap(torch.from_numpy(obs).to(dev), {"action": [None] * len(net.actor_layers) + [torch.from_numpy(mu_t).to(dev)],
+                                                      "value": [None] * len(net.critic_layers)}, None)
+    z = torch.zeros(T, mb, device=dev)
+    data = DistillationTransition(obs=torch.from_numpy(obs).to(dev), student_output=None, rewards=z, done=z.bool(),
+                                  truncated=z.bool(), next_obs=None, metrics={}, student_rollout_extras=None,
+                                  teacher_rollout_extras=extras)
+    c0 = ostudent.rng_count
+    total, lm, grads = distillation.distillation_loss(student, student.initialize_state(mb), data, LoggingLevel.LOSSES,
+                                                      return_grads=True)
+    ototal, om, ograds = odistill.distillation_loss_and_grads(ostudent, obs, mu_t, np.arange(mb, dtype=np.int32), c0)
+    assert abs(float(total) - float(ototal)) < 2e-5 * max(1.0, abs(float(ototal)))
+    assert abs(float(lm["losses/distillation_nll"]) - float(om["losses/distillation_nll"])) < 2e-5 * max(1.0, abs(float(ototal)))
+    assert abs(float(lm["losses/regularization"]) - float(om["losses/regularization"])) < 2e-5
+    assert np.abs(grads - ograds).max() < 3e-4 * np.abs(ograds).max()
+    assert net.rng_count == c0 + 2 * T

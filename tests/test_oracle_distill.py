@@ -105,6 +105,7 @@ def test_distillation_api_mirrors_the_reference():
     assert [p[0] for p in params(d.distillation_step)] == [
         "env", "teacher", "distillation_state", "n_envs", "rollout_length", "n_epochs", "n_minibatches",
         "logging_level", "logging_percentiles"]
+    assert [p[0] for p in params(d.distillation_loss)][:4] == ["student", "student_state", "rollout_data", "logging_level"]
     assert [p[0] for p in params(d.new_distillation_state)] == [
         "env", "teacher", "student", "n_envs", "seed", "learning_rate", "gradient_clipping", "weight_decay"]
     assert dict((p[0], p[1]) for p in params(d.new_distillation_state))["learning_rate"] == 1e-4

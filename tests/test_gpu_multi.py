@@ -9,7 +9,7 @@ the norm is identical on every rank and must not be multiplied by the world size
 summed over ranks.
 
 The driver's round-end GPU box has one GPU (this file is skipped there); the log of a 2-GPU run of this
-file is kept under profiles/ (r2_gputest_2gpu.log).
+file is kept under profiles/ (r2_gputest_2gpu.log, r2b_gputest_2gpu.log).
 """
 import os
 import sys
@@ -147,3 +147,63 @@ def test_recurrent_data_parallel_replicas_stay_in_sync(tmp_path):
     np.testing.assert_allclose(a["m"], b["m"], rtol=1e-6)
     assert np.all(np.isfinite(a["params"])) and np.abs(a["params"] - a["p0"]).max() > 1e-5
     assert not np.array_equal(a["obs"], b["obs"]) and not np.array_equal(a["h"], b["h"])       # different env shards
+
+
+def _distill_worker(rank, world, port, p2p, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), B200PPO_P2P="1" if p2p else "0")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    from nnx_ppo_b200 import Rngs
+    from nnx_ppo_b200.algorithms import distillation
+    from nnx_ppo_b200.envs import SyntheticEnv
+    from nnx_ppo_b200.networks.factories import make_mlp_actor_critic
+    from nnx_ppo_b200.networks.plan import compile_network
+    O, A, B, T, E, M = 24, 4, 256, 8, 2, 4
+    env = SyntheticEnv(O, A, 16, 2048)
+    student = make_mlp_actor_critic(O, A, [64, 64], [32], Rngs(1))
+    teacher = make_mlp_actor_critic(O, A, [48], [16], Rngs(2))
+    teacher.eval()
+    ds = distillation.new_distillation_state(env, teacher, student, B, 17, learning_rate=3e-4)
+    net = compile_network(student)
+    ms = []
+    for _ in range(3):                       # eager, graph capture + replay, replay
+        ds, m = distillation.distillation_step(env, teacher, ds, B, T, E, M)
+        ms.append([float(m["losses/distillation_nll/mean"]), float(m["losses/regularization/mean"])])
+    eng = next(iter(net.engines.values()))
+    assert eng.p2p == bool(p2p) and eng.world == world and eng.nll
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, f"d{rank}_{int(p2p)}.npz"), params=net.arena.cpu().numpy(), m=np.array(ms, np.float64),
+             obs=ds.env_states.obs.cpu().numpy())
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+@pytest.mark.timeout(600)
+def test_distillation_data_parallel(tmp_path):
+    """Policy distillation on 2 ranks (NLL loss head: no advantage-moment exchange, the gradient exchange of the PPO
+    path): replicas stay in sync, the peer-memory path equals the NCCL path bit for bit, the env shards differ."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    res = {}
+    for p2p, port in ((True, 29671), (False, 29672)):
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=_distill_worker, args=(r, 2, port, p2p, str(tmp_path))) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(240)
+            assert p.exitcode == 0
+        for r in range(2):
+            res[(r, p2p)] = np.load(tmp_path / f"d{r}_{int(p2p)}.npz")
+    for p2p in (True, False):
+        np.testing.assert_array_equal(res[(0, p2p)]["params"], res[(1, p2p)]["params"])
+        np.testing.assert_allclose(res[(0, p2p)]["m"], res[(1, p2p)]["m"], rtol=1e-6)
+        assert not np.array_equal(res[(0, p2p)]["obs"], res[(1, p2p)]["obs"])
+    np.testing.assert_array_equal(res[(0, True)]["params"], res[(0, False)]["params"])
+    assert np.all(np.isfinite(res[(0, True)]["params"]))

@@ -641,6 +641,270 @@ __global__ void __launch_bounds__(NT, 2) rollout_synth_mma_kernel(const RolloutA
 }
 
 // ------------------------------------------------------------------------------------------
+// Second version of the tensor-core rollout: ONE 512-thread CTA per SM holding two independent 8-warp env groups
+// (16 envs each, own activation tiles, own named barrier) that share one copy of the fragment-ordered weights.  The room
+// this frees (no second copy of the 88 KB of weights) holds every activation tile PRE-SPLIT (a hi tile and a lo tile,
+// written once by the producing epilogue), so a k-step's A fragments are two `ldmatrix.x4` instead of four LDS.32 plus
+// eight split instructions that all eight warps of a group repeated: 13 instead of 23 issued instructions per k-step
+// (profiles/r2b_notes.md).  The two groups hide each other's barrier and latency bubbles the way the two CTAs per SM of
+// the first version did.
+// ------------------------------------------------------------------------------------------
+constexpr int NT2 = 512;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+// value of a pre-split tile element / store of one (hi = the tf32-truncated value, lo = the exact remainder: hi + lo == v)
+__device__ __forceinline__ float tile_get(const float* t, int tlo, int i) { return t[i] + t[i + tlo]; }
+__device__ __forceinline__ void tile_put(float* t, int tlo, int i, float v) {
+  const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  t[i] = hi;
+  t[i + tlo] = v - hi;
+}
+
+__device__ __forceinline__ void mma_layer2(const float* __restrict__ in, int tlo, int ld, int K, const float2* __restrict__ wf,
+                                           const float* __restrict__ bias, int N, float* __restrict__ out, int act, int lwarp,
+                                           int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int KS = (K + 7) >> 3, NJ = (N + 7) >> 3;
+  // ldmatrix row addresses of the m16 x k8 fp32 fragment: matrices 0..3 = (rows 0-7 | 8-15) x (k 0-3 | 4-7)
+  const int frow = (lane & 7) + ((lane >> 3) & 1) * 8, fcol = (lane >> 4) * 4;
+  const uint32_t a_hi = static_cast<uint32_t>(__cvta_generic_to_shared(in + frow * ld + fcol));
+  const uint32_t a_lo = a_hi + static_cast<uint32_t>(tlo) * 4u;
+  for (int j = lwarp; j < NJ; j += 8) {
+    float acc[2][3][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[p][q][i] = 0.0f;
+    const float2* wj = wf + static_cast<size_t>(j) * KS * 32 + lane;
+#pragma unroll 2
+    for (int s = 0; s < KS; ++s) {
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      ldmatrix_x4(ah, a_hi + 32u * s);
+      ldmatrix_x4(al, a_lo + 32u * s);
+      const float2 w = wj[s * 32];
+      bh[0] = __float_as_uint(w.x) & 0xFFFFE000u; bl[0] = __float_as_uint(w.x - __uint_as_float(bh[0]));
+      bh[1] = __float_as_uint(w.y) & 0xFFFFE000u; bl[1] = __float_as_uint(w.y - __uint_as_float(bh[1]));
+      const int p = s & 1;
+      mma_tf32_16x8x8(acc[p][0], al, bh);
+      mma_tf32_16x8x8(acc[p][1], ah, bl);
+      mma_tf32_16x8x8(acc[p][2], ah, bh);
+    }
+    const int col = 8 * j + 2 * t;
+    float z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)     // small terms first
+      z[i] = ((acc[0][0][i] + acc[1][0][i]) + (acc[0][1][i] + acc[1][1][i])) + (acc[0][2][i] + acc[1][2][i]);
+    if (bias != nullptr) {
+      const float b0 = bias[col], b1 = bias[col + 1];
+      z[0] += b0; z[1] += b1; z[2] += b0; z[3] += b1;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = act_fwd(z[i], act);
+    float h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __uint_as_float(__float_as_uint(z[i]) & 0xFFFFE000u);
+    float* o0 = out + g * ld + col;
+    float* o1 = out + (g + 8) * ld + col;
+    *reinterpret_cast<float2*>(o0) = make_float2(h[0], h[1]);
+    *reinterpret_cast<float2*>(o1) = make_float2(h[2], h[3]);
+    *reinterpret_cast<float2*>(o0 + tlo) = make_float2(z[0] - h[0], z[1] - h[1]);
+    *reinterpret_cast<float2*>(o1 + tlo) = make_float2(z[2] - h[2], z[3] - h[3]);
+  }
+}
+
+__global__ void __launch_bounds__(NT2, 1) rollout_synth_mma2_kernel(const RolloutArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int O = a.O, A = a.A, ld = a.ld;
+  const int gi = threadIdx.x >> 8, lt = threadIdx.x & 255;        // env group, thread within the group
+  const int env0 = (blockIdx.x * 2 + gi) * TE;
+  const int warp = lt >> 5, lane = lt & 31;
+  const b200ppo_chain& ch = a.plan.actor;
+  const int L = ch.n_layers;
+  const int tlo = TE * ld;                                          // lo tile follows its hi tile
+  const int per_group = 6 * TE * ld + 2 * TE * A + 5 * TE;
+  float* sp = smem + gi * ((per_group + 3) & ~3);
+  float* bufA = sp; sp += 2 * TE * ld;
+  float* bufB = sp; sp += 2 * TE * ld;
+  float* bufX = sp; sp += 2 * TE * ld;  // env-step input tile, resident across steps: [obs | action] per env row
+  float* raw_s = sp; sp += TE * A;
+  float* llt_s = sp; sp += TE * A;
+  int32_t* cnt_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  uint32_t* term_s = reinterpret_cast<uint32_t*>(sp); sp += TE;
+  uint32_t* kb_s = reinterpret_cast<uint32_t*>(sp); sp += 2 * TE;
+  int32_t* done_s = reinterpret_cast<int32_t*>(sp); sp += TE;
+  float* shared0 = smem + 2 * ((per_group + 3) & ~3);
+  float* mean_s = shared0;
+  float* std_s = mean_s + O;
+  float* wbase = shared0 + ((2 * O + 3) & ~3);
+  __shared__ int woff_s[B200PPO_MAX_LAYERS + 1], boff_s[B200PPO_MAX_LAYERS];
+  {
+    int off = 0;
+    for (int l = 0; l < L; ++l) {
+      if (threadIdx.x == 0) woff_s[l] = off;
+      off += frag_floats(ch.dims[l], ch.dims[l + 1]);
+    }
+    if (threadIdx.x == 0) woff_s[L] = off;
+    off += frag_floats(O + A, O);
+    for (int l = 0; l < L; ++l) {
+      if (threadIdx.x == 0) boff_s[l] = off;
+      off += (ch.dims[l + 1] + 7) & ~7;
+    }
+  }
+  for (int i = lt; i < 6 * TE * ld; i += 256) bufA[i] = 0.0f;        // all six tiles of the group; padding stays zero
+  __syncthreads();
+  for (int l = 0; l < L; ++l) {
+    const int K = ch.dims[l], N = ch.dims[l + 1], Np = (N + 7) & ~7;
+    const int KS = (K + 7) >> 3, NJ = (N + 7) >> 3;
+    float2* dst = reinterpret_cast<float2*>(wbase + woff_s[l]);
+    const float* W = a.params + ch.w_off[l];
+    for (int idx = threadIdx.x; idx < NJ * KS * 32; idx += NT2) {
+      const int ln = idx & 31, q = idx >> 5, s = q % KS, j = q / KS;
+      const int k = 8 * s + (ln & 3), n = 8 * j + (ln >> 2);
+      float2 v = make_float2(0.0f, 0.0f);
+      if (n < N) {
+        if (k < K) v.x = W[static_cast<size_t>(k) * N + n];
+        if (k + 4 < K) v.y = W[static_cast<size_t>(k + 4) * N + n];
+      }
+      dst[idx] = v;
+    }
+    for (int i = threadIdx.x; i < Np; i += NT2) wbase[boff_s[l] + i] = i < N ? a.params[ch.b_off[l] + i] : 0.0f;
+  }
+  {
+    const int K = O + A, N = O, KS = (K + 7) >> 3, NJ = (N + 7) >> 3;
+    float2* dst = reinterpret_cast<float2*>(wbase + woff_s[L]);
+    for (int idx = threadIdx.x; idx < NJ * KS * 32; idx += NT2) {
+      const int ln = idx & 31, q = idx >> 5, s = q % KS, j = q / KS;
+      const int k = 8 * s + (ln & 3), n = 8 * j + (ln >> 2);
+      float2 v = make_float2(0.0f, 0.0f);
+      if (n < N) {
+        if (k < K) v.x = a.Wenv[static_cast<size_t>(k) * N + n];
+        if (k + 4 < K) v.y = a.Wenv[static_cast<size_t>(k + 4) * N + n];
+      }
+      dst[idx] = v;
+    }
+  }
+  for (int i = threadIdx.x; i < O; i += NT2) {
+    mean_s[i] = a.plan.normalize ? a.mean[i] : 0.0f;
+    std_s[i] = a.plan.normalize ? a.std[i] : 1.0f;
+  }
+  for (int e = warp; e < TE; e += 8)
+    for (int o = lane; o < O; o += 32)
+      tile_put(bufX, tlo, e * ld + o, (env0 + e < a.B) ? a.env_obs[static_cast<size_t>(env0 + e) * O + o] : 0.0f);
+  if (lt < TE) {
+    const bool ok = env0 + lt < a.B;
+    cnt_s[lt] = ok ? a.env_counter[env0 + lt] : 0;
+    term_s[lt] = ok ? a.env_term[env0 + lt] : 0u;
+  }
+  const Key stream_key{a.rng_state[0], a.rng_state[1]};
+  const uint32_t count0 = a.rng_state[2];
+  const Key reset_key{a.iter_keys[0], a.iter_keys[1]};
+  __syncthreads();
+  // from here on the two groups never meet again: barrier 1 + gi, 256 threads
+#define GROUP_SYNC() asm volatile("bar.sync %0, 256;" ::"r"(1 + gi) : "memory")
+
+  for (int t = 0; t < a.T; ++t) {
+    // (1) record the raw observation, normalise into bufA  (rollout.py:23; normalizer.py:78-80)
+    const size_t row0 = static_cast<size_t>(t) * a.B + env0;
+    for (int e = warp; e < TE; e += 8)
+      for (int o = lane; o < O; o += 32) {
+        const float x = tile_get(bufX, tlo, e * ld + o);
+        if (env0 + e < a.B) a.obs[(row0 + e) * O + o] = x;
+        tile_put(bufA, tlo, e * ld + o, a.plan.normalize ? __fdiv_rn(x - mean_s[o], std_s[o]) : x);
+      }
+    GROUP_SYNC();
+    // (2) actor MLP: activations ping-pong between bufA and bufB
+    float* cur = bufA;
+    float* nxt = bufB;
+    for (int l = 0; l < L; ++l) {
+      mma_layer2(cur, tlo, ld, ch.dims[l], reinterpret_cast<const float2*>(wbase + woff_s[l]), wbase + boff_s[l],
+                 ch.dims[l + 1], nxt, l + 1 < L ? ch.act : B200PPO_ACT_NONE, warp, lane);
+      GROUP_SYNC();
+      float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    const float* y = cur;
+    // (3) sampler (count = count0 + 2t; the entropy draw does not influence the rollout): action -> env input tile
+    const Key k_sample = fold_in(stream_key, count0 + 2u * static_cast<uint32_t>(t));
+    for (int i = lt; i < TE * A; i += 256) {
+      const int e = i / A, d = i - e * A;
+      const uint32_t j = static_cast<uint32_t>(env0 + e) * static_cast<uint32_t>(A) + d;
+      const SamplerOut s = sampler_elem(tile_get(y, tlo, e * ld + d), tile_get(y, tlo, e * ld + A + d), a.plan.min_std,
+                                        a.plan.std_scale, a.plan.entropy_weight, 0, 0.0f, k_sample, k_sample, j, false);
+      raw_s[i] = s.raw;
+      tile_put(bufX, tlo, e * ld + O + d, s.action);
+      llt_s[i] = s.llterm;
+      if (env0 + e < a.B) {
+        a.raw_action[row0 * A + i] = s.raw;
+        a.action[row0 * A + i] = s.action;
+      }
+    }
+    GROUP_SYNC();
+    // (4) episode bookkeeping (integer-exact) and reset scalars, beside the env-step GEMM
+    if (lt < TE) {
+      const int e = lt;
+      const int ge = env0 + e;
+      float ll = 0.0f;
+      for (int d = 0; d < A; ++d) ll += llt_s[e * A + d];
+      const int32_t c = cnt_s[e] + 1;
+      const uint32_t ts = term_s[e] * 1664525u + 1013904223u;
+      const bool terminated = (ts >> 16) < static_cast<uint32_t>(a.term_thresh16);
+      const bool truncated = c >= a.max_len;
+      const bool dn = terminated || truncated;
+      if (ge < a.B) {
+        a.loglik[row0 + e] = ll;
+        a.done[row0 + e] = dn ? 1 : 0;
+        a.trunc[row0 + e] = truncated ? 1 : 0;
+      }
+      done_s[e] = dn ? 1 : 0;
+      if (dn) {
+        const Key k = split_at(reset_key, static_cast<uint32_t>(t) * static_cast<uint32_t>(a.B) + static_cast<uint32_t>(ge));
+        const ResetScalars r = synth_reset_scalars(k, a.max_len);
+        cnt_s[e] = r.counter;
+        term_s[e] = r.term;
+        kb_s[2 * e] = r.k_base.a;
+        kb_s[2 * e + 1] = r.k_base.b;
+      } else {
+        cnt_s[e] = c;
+        term_s[e] = ts;
+      }
+    }
+    // (5) env step: obs' = tanh([obs, action] @ [Wo; Wa]) into the tile the actor no longer needs
+    float* yo = nxt;
+    mma_layer2(bufX, tlo, ld, O + A, reinterpret_cast<const float2*>(wbase + woff_s[L]), nullptr, O, yo, B200PPO_ACT_TANH, warp,
+               lane);
+    GROUP_SYNC();
+    // (6) reward = -mean(obs'^2); next_obs[-1] is the pre-reset observation; tree_where(done, reset, next)
+    for (int e = warp; e < TE; e += 8) {
+      const bool dn = done_s[e] != 0;
+      const Key kb{kb_s[2 * e], kb_s[2 * e + 1]};
+      float sq = 0.0f;
+      for (int o = lane; o < O; o += 32) {
+        const float v = tile_get(yo, tlo, e * ld + o);
+        sq = fmaf(v, v, sq);
+        if (t == a.T - 1 && env0 + e < a.B) a.next_obs_last[static_cast<size_t>(env0 + e) * O + o] = v;
+        tile_put(bufX, tlo, e * ld + o, dn ? bits_to_normal(random_bits_at(kb, static_cast<uint32_t>(o))) : v);
+      }
+      sq = warp_sum(sq);
+      if (lane == 0 && env0 + e < a.B) a.reward[row0 + e] = -(sq / static_cast<float>(O));
+    }
+    GROUP_SYNC();
+  }
+#undef GROUP_SYNC
+  for (int e = warp; e < TE; e += 8)
+    for (int o = lane; o < O; o += 32)
+      if (env0 + e < a.B) a.env_obs[static_cast<size_t>(env0 + e) * O + o] = tile_get(bufX, tlo, e * ld + o);
+  if (lt < TE && env0 + lt < a.B) {
+    a.env_counter[env0 + lt] = cnt_s[lt];
+    a.env_term[env0 + lt] = term_s[lt];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // persistent fused evaluation rollout (rollout.py:97-148): no transition record, no env reset;
 // done is sticky, the reward is accumulated while the env was alive BEFORE the step, lifespan
 // counts the steps that did not end in done.  Once every env of the tile is done nothing
@@ -882,6 +1146,12 @@ int rollout_mode() {
   return g_rollout_mode;
 }
 
+// B200PPO_ROLLOUT_MMA=1 selects the first tensor-core rollout kernel (two 16-env CTAs per SM, split on load)
+int rollout_mma_version() {
+  static const int v = [] { const char* e = std::getenv("B200PPO_ROLLOUT_MMA"); return e && std::atoi(e) == 1 ? 1 : 2; }();
+  return v;
+}
+
 int check_plan(const b200ppo_plan* p) {
   if (!p) return B200PPO_EINVAL;
   if (p->obs_dim <= 0 || p->act_dim <= 0) return B200PPO_EINVAL;
@@ -996,6 +1266,21 @@ int rollout_synth_impl(void* stream, const b200ppo_plan* plan, const b200ppo_syn
     for (int l = 0; l < plan->actor.n_layers; ++l)
       fl += frag_floats(plan->actor.dims[l], plan->actor.dims[l + 1]) + ((plan->actor.dims[l + 1] + 7) & ~7);
     fl += frag_floats(O + A, O);
+    // second version first: one CTA per SM with two env groups sharing the weights, activation tiles pre-split
+    {
+      const int64_t per_group = (6ll * TE * a.ld + 2ll * TE * A + 5ll * TE + 3) & ~3ll;
+      int64_t f2 = 2 * per_group + ((2ll * O + 3) & ~3ll);
+      for (int l = 0; l < plan->actor.n_layers; ++l)
+        f2 += frag_floats(plan->actor.dims[l], plan->actor.dims[l + 1]) + ((plan->actor.dims[l + 1] + 7) & ~7);
+      f2 += frag_floats(O + A, O);
+      if (4 * f2 <= SMEM_LIMIT - 2048 && rollout_mma_version() == 2) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_synth_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(4 * f2));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        rollout_synth_mma2_kernel<<<cdiv(B, 2 * TE), NT2, 4 * f2, static_cast<cudaStream_t>(stream)>>>(a);
+        B200PPO_LAUNCH_CHECK();
+        return 0;
+      }
+    }
     if (4 * fl <= SMEM_LIMIT - 2048) {     // the kernel also has ~1 KB of static shared memory
       cudaError_t e = cudaFuncSetAttribute(rollout_synth_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(4 * fl));
       if (e != cudaSuccess) return static_cast<int>(e);

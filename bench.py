@@ -304,41 +304,73 @@ def build_workload(name, cfg):
     return env, nets
 
 
-def time_stages(eng, ts_env_state, lib, _lib, torch, local_only=False):
-    """Per-stage CUDA-event timing of the E*M updates of one iteration (eager launches on the current
-    stream).  `local_only`: the same launches without the peer exchange (world-size-1 arithmetic on this
-    rank's shard), so that the difference is what the cross-GPU synchronisation costs."""
+def time_stages(eng, ts_env_state, lib, _lib, torch, local_only=False, graphs=True):
+    """Per-stage CUDA-event timing of the E*M updates of one iteration.  `graphs` (single GPU): the E*M launches of a
+    stage are captured into one CUDA graph and a replay is timed, so the figure is the stage's time on the device,
+    kernel boundaries included, without the host's launch gaps (eager, a Python -> ctypes launch every ~15 us leaves the
+    GPU idle between the events: the in-kernel globaltimer stamps of profiles/r2c_cta_times.log put the forward kernel
+    at 39 us where eager events read 50-56).  With the peer exchange (N > 1) the launches run eagerly, once: every
+    exchange epoch can be used only once.  `local_only`: the same launches without the peer exchange (world-size-1
+    arithmetic on this rank's shard), so that the difference is what the cross-GPU synchronisation costs."""
     net = eng.net
     T, B, mb = eng.T, eng.B, eng.mb
+    # "gae_loss": both stages in one call, as the iteration runs them (one fused launch, csrc/update.cu
+    # upd_gae_loss_kernel); "gae" / "loss" alone are the two stand-alone kernels (idempotent recomputations)
     stages = [("fwd", _lib.STAGE_FWD), ("gae", _lib.STAGE_GAE), ("loss", _lib.STAGE_LOSS),
+              ("gae_loss", _lib.STAGE_GAE | _lib.STAGE_LOSS),
               ("bwd_dx", _lib.STAGE_BWD_DX), ("bwd_dw", _lib.STAGE_BWD_DW), ("red_adam", _lib.STAGE_RED | _lib.STAGE_ADAM)]
     tot = {k: 0.0 for k, _ in stages}
-    s = _lib.current_stream()
     saved = None
     if local_only:
         saved = (eng.hp.world_size, [b.comm for b in eng.bufs])
         eng.hp.world_size = 1
         for b in eng.bufs:
             b.comm = 0
-    evs = []
-    for u in range(eng.n_updates):
+
+    def launch(u, mask):
         off = 2 * T + u * 2 * (T + 1)
-        row = []
+        _lib.check(lib.b200ppo_update(_lib.current_stream(), net.plan, eng.hp, eng.bufs[u], T, B, mb, off, u, mask))
+
+    if graphs and eng.hp.world_size == 1:
         for name, mask in stages:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _lib.check(lib.b200ppo_update(s, net.plan, eng.hp, eng.bufs[u], T, B, mb, off, u, mask))
-            e1.record()
-            row.append((name, e0, e1))
-        evs.append(row)
-    torch.cuda.synchronize()
+            for u in range(eng.n_updates):            # eager once: every buffer a later stage reads exists
+                launch(u, mask)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for u in range(eng.n_updates):
+                    launch(u, mask)
+            g.replay()
+            torch.cuda.synchronize()
+            reps = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                reps.append(e0.elapsed_time(e1))
+            tot[name] = sorted(reps)[1]
+            del g
+    else:
+        evs = []
+        for u in range(eng.n_updates):
+            row = []
+            for name, mask in stages:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                launch(u, mask)
+                e1.record()
+                row.append((name, e0, e1))
+            evs.append(row)
+        torch.cuda.synchronize()
+        for row in evs:
+            for name, e0, e1 in row:
+                tot[name] += e0.elapsed_time(e1)
     if saved is not None:
         eng.hp.world_size = saved[0]
         for b, c in zip(eng.bufs, saved[1]):
             b.comm = c
-    for row in evs:
-        for name, e0, e1 in row:
-            tot[name] += e0.elapsed_time(e1)
     if ts_env_state is not None and not local_only:
         # the rollout launch alone, on a scratch copy of the env state (sampler counts are not advanced, so
         # the training state is untouched); median of 5
@@ -516,7 +548,9 @@ def run_own(args):
                             "ffma_peak_tflops": ffma_tf, "frac_of_ffma_peak": ach / ffma_tf,
                             "flop_per_launch": flops[dom], "launch_ms": stage_ms[dom] / U,
                             "stage_ms_per_iteration": stage_ms,
-                            "small_kernel_share": (stage_ms["gae"] + stage_ms["loss"] + stage_ms["red_adam"]) / (ms / args.steps),
+                            "stage_timing": ("one CUDA-graph replay of the E*M launches of each stage (device time, no host launch gaps)"
+                                             if world == 1 else "eager launches, one event pair per launch (includes host launch gaps)"),
+                            "small_kernel_share": (stage_ms["gae_loss"] + stage_ms["red_adam"]) / (ms / args.steps),
                             "stage_tflops_algorithmic": {k: flops[k] * U / (stage_ms[k] * 1e-3) / 1e12 for k in flops}}
         if sync_us is not None:
             line["roofline"]["sync_us_per_update"] = sync_us

@@ -454,6 +454,10 @@ int b200ppo_set_pdl(int on);
 /* Profiling aid (synchronous): clock64 phase stamps of CTA 0 of the last tensor-core update       *
  * kernel -> out_host; returns -(1000 + count).                                                   */
 int b200ppo_debug_timestamps(long long* out_host, int32_t max_n);
+/* Profiling aid (synchronous): globaltimer (ns) of every CTA of the last tensor-core update kernel, *
+ * three per CTA (entry, TMEM / barrier set-up done, exit) -> out_host[3 * max_ctas]; returns the   *
+ * number of CTA slots copied (<= 1024).                                                           */
+int b200ppo_debug_cta_times(unsigned long long* out_host, int32_t max_ctas);
 int b200ppo_debug_select(int flags);     /* bit 0: the dW kernel keeps dX's stamps; bits 8..: blockIdx.x of the stamped CTA */
 /* Number of kernels b200ppo_update launches for the given stage mask (for launch accounting).   */
 int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
@@ -476,6 +480,12 @@ int b200ppo_iter_finalize(void* stream, uint32_t* rng_state /*dev*/, uint32_t rn
 int b200ppo_tc_gemm_test(void* stream, const float* A /*dev*/, const float* B /*dev*/, float* C /*dev*/,
                          int32_t M, int32_t N, int32_t K, int32_t split);
 
+/* Bring-up / parity harness of the MN-major tensor-core operand path (the dW kernel's): C[K][N] = H^T D  *
+ * for row-major H [rows][K], D [rows][N] (device pointers), operands fetched by swizzled TMA boxes, no    *
+ * software transposition.  K <= 128, N <= 256, K % 4 == N % 4 == 0; split != 0: error-compensated 3xTF32. */
+int b200ppo_tc_mn_test(void* stream, const float* H /*dev*/, const float* D /*dev*/, float* C /*dev*/, int32_t rows,
+                       int32_t K, int32_t N, int32_t split, float* dbg /*dev, nullable: (4 + ceil(N/32)) * 512 floats, the
+                       operand tiles of the last 16-row stage as they landed in shared memory*/);
 /* Microbenchmark (profiling aid): cycles for `iters` dependent tcgen05.mma (M=128, N, K=8), for  *
  * `iters` serialized bulk copies of `bytes`, and for the MMAs over `nacc` accumulators.           */
 int b200ppo_tc_microbench(void* stream, const float* src /*dev*/, long long* out /*dev [4]*/, int32_t N,

@@ -103,6 +103,7 @@ SYMBOLS = {
                                      _vp, _vp, _vp, _vp, _vp]),
     "b200ppo_update_workspace_bytes": (_i64, [_PP, _i32, _i32]),
     "b200ppo_update": (C.c_int, [_vp, _PP, _HP, _BP, _i32, _i32, _i32, _u32, _i32, _i32]),
+    "b200ppo_debug_cta_times": (C.c_int, [_vp, _i32]),
     "b200ppo_debug_select": (C.c_int, [C.c_int]),
     "b200ppo_debug_timestamps": (C.c_int, [_vp, _i32]),
     "b200ppo_set_gemm_mode": (C.c_int, [C.c_int]),
@@ -136,6 +137,7 @@ SYMBOLS = {
     "b200ppo_iter_finalize": (C.c_int, [_vp, _vp, _u32, _u32, _vp]),
     "b200ppo_set_pdl": (C.c_int, [C.c_int]),
     "b200ppo_tc_gemm_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32]),
+    "b200ppo_tc_mn_test": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "b200ppo_tc_microbench": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32]),
     "b200ppo_ffma_peak": (C.c_int, [_vp, _i32, _vp, _i32, _i32]),
 }

@@ -83,6 +83,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
                : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- proxies / tcgen05 fences ----
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -123,6 +129,31 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 // instruction descriptor: D = F32, A = B = TF32, both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---- MN-major tf32 operands: 128-byte swizzle with 32-byte atoms (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B,
+// the only shared-memory layout the hardware takes for an MN-major 32-bit operand; every other layout type reads as
+// zeros) ----
+// A row-major global tile [k][mn] loaded by TMA with a {32 mn, 16 k} box and CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B lands
+// as 16 rows of 128 bytes (row = k, 32 consecutive mn elements), the four 32-byte chunks of a row XOR-permuted by
+// (k & 3): the canonical operand ((8 x 16 B, mn atoms), (4 k, k groups)) : ((16 B, LBO), (128 B, SBO)).  One K = 8 MMA
+// reads two 4-row groups SBO = 512 bytes apart; 32-wide mn atoms are LBO apart.  No transposition in software: the
+// reduction index of dW = H^T D is the row index of both operands.
+constexpr uint32_t MN_ATOM_BYTES = 2048;   // one {32 mn, 16 k} box: two K = 8 steps of 1024 bytes
+constexpr uint32_t MN_SBO_BYTES = 512;     // 4 k rows
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;                        // descriptor version (Blackwell)
+  d |= 1ull << 61;                        // layout type SWIZZLE_128B_BASE32B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both MN-major (bits 15, 16), dense
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 

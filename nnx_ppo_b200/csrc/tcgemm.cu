@@ -224,3 +224,120 @@ extern "C" int b200ppo_tc_gemm_test(void* stream, const float* A, const float* B
   B200PPO_LAUNCH_CHECK();
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Bring-up / parity harness of the MN-major operand path (tc.cuh: make_desc_mn_sw128): C[K][N] = H^T D for
+// row-major H [rows][K <= 128], D [rows][N <= 256], both fetched by swizzled TMA boxes and consumed by the MMA
+// without a software transposition; the hi half of the 3xTF32 split is the raw fp32 tile (the tensor core reads
+// the upper 19 bits), the lo half x - trunc(x) is computed element-wise at the same offsets.
+// ------------------------------------------------------------------------------------------
+#include "tmap.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(128, 1)
+tc_mn_test_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmD,
+                  float* __restrict__ C, int rows, int K, int N, int split, int tmem_cols, float* __restrict__ dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int n32 = (N + 31) / 32, npad = n32 * 32;
+  const uint32_t a_bytes = 4u * tc::MN_ATOM_BYTES, b_bytes = static_cast<uint32_t>(n32) * tc::MN_ATOM_BYTES;
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = a_hi + a_bytes;
+  uint8_t* b_hi = a_lo + a_bytes;
+  uint8_t* b_lo = b_hi + b_bytes;
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, tmem_cols);
+  if (tid == 32) { tc::mbar_init(&bar_full, 1); tc::mbar_init(&bar_done, 1); tc::mbar_init_fence(); }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nst = (rows + 15) / 16;
+  const uint32_t idesc = tc::make_idesc_tf32_mn(128, npad);
+  for (int s = 0; s < nst; ++s) {
+    if (tid == 0) {
+      tc::mbar_arrive_expect_tx(&bar_full, a_bytes + b_bytes);
+      for (int i = 0; i < 4; ++i) tc::tma_load_2d(a_hi + i * tc::MN_ATOM_BYTES, &tmH, 32 * i, 16 * s, &bar_full);
+      for (int j = 0; j < n32; ++j) tc::tma_load_2d(b_hi + j * tc::MN_ATOM_BYTES, &tmD, 32 * j, 16 * s, &bar_full);
+    }
+    tc::mbar_wait(&bar_full, static_cast<uint32_t>(s) & 1u);
+    if (dbg != nullptr && s == nst - 1) {                  // the raw operand tiles of the last stage, as they landed
+      for (uint32_t i = tid; i < a_bytes / 4; i += 128) dbg[i] = reinterpret_cast<const float*>(a_hi)[i];
+      for (uint32_t i = tid; i < b_bytes / 4; i += 128) dbg[a_bytes / 4 + i] = reinterpret_cast<const float*>(b_hi)[i];
+    }
+    if (split) {
+      const int nchunk = static_cast<int>((a_bytes + b_bytes) / 16);     // A and B hi tiles are adjacent only when
+      for (int c = tid; c < nchunk; c += 128) {                          // a_lo is skipped: index them separately
+        const bool isa = c < static_cast<int>(a_bytes / 16);
+        const uint32_t off = isa ? c * 16u : (c * 16u - a_bytes);
+        const uint4 x = *reinterpret_cast<const uint4*>((isa ? a_hi : b_hi) + off);
+        float4 lo;
+        lo.x = __uint_as_float(x.x) - __uint_as_float(x.x & 0xFFFFE000u);
+        lo.y = __uint_as_float(x.y) - __uint_as_float(x.y & 0xFFFFE000u);
+        lo.z = __uint_as_float(x.z) - __uint_as_float(x.z & 0xFFFFE000u);
+        lo.w = __uint_as_float(x.w) - __uint_as_float(x.w & 0xFFFFE000u);
+        *reinterpret_cast<float4*>((isa ? a_lo : b_lo) + off) = lo;
+      }
+      tc::fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      for (int j = 0; j < 2; ++j) {
+        const uint64_t ah = tc::make_desc_mn_sw128(tc::smem_u32(a_hi) + j * 1024u, tc::MN_ATOM_BYTES, tc::MN_SBO_BYTES);
+        const uint64_t bh = tc::make_desc_mn_sw128(tc::smem_u32(b_hi) + j * 1024u, tc::MN_ATOM_BYTES, tc::MN_SBO_BYTES);
+        const uint32_t acc0 = (s > 0 || j > 0) ? 1u : 0u;
+        if (split) {
+          const uint64_t al = tc::make_desc_mn_sw128(tc::smem_u32(a_lo) + j * 1024u, tc::MN_ATOM_BYTES, tc::MN_SBO_BYTES);
+          const uint64_t bl = tc::make_desc_mn_sw128(tc::smem_u32(b_lo) + j * 1024u, tc::MN_ATOM_BYTES, tc::MN_SBO_BYTES);
+          tc::mma_tf32(tmem_base, al, bh, idesc, acc0);
+          tc::mma_tf32(tmem_base, ah, bl, idesc, 1u);
+          tc::mma_tf32(tmem_base, ah, bh, idesc, 1u);
+        } else {
+          tc::mma_tf32(tmem_base, ah, bh, idesc, acc0);
+        }
+      }
+      tc::commit(&bar_done);
+      tc::mbar_wait(&bar_done, static_cast<uint32_t>(s) & 1u);
+    }
+    __syncthreads();
+  }
+  tc::tc_fence_after();
+  const int m = warp * 32 + lane;
+  for (int c = 0; c < npad; c += 16) {
+    float v[16];
+    tc::tmem_ld16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(c), v);
+    if (m < K)
+      for (int i = 0; i < 16; ++i)
+        if (c + i < N) C[static_cast<size_t>(m) * N + c + i] = v[i];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace
+
+// Test hook: C[K][N] = H[rows][K]^T D[rows][N] through the MN-major swizzled operand path.  K <= 128, N <= 256,
+// K % 4 == 0, N % 4 == 0 (TMA row pitch); synchronous tensor-map encoding, asynchronous launch.
+extern "C" int b200ppo_tc_mn_test(void* stream, const float* H, const float* D, float* C, int32_t rows, int32_t K,
+                                  int32_t N, int32_t split, float* dbg) {
+  if (!H || !D || !C || rows <= 0 || K <= 0 || K > 128 || (K & 3) || N <= 0 || N > 256 || (N & 3)) return B200PPO_EINVAL;
+  CUtensorMap tmH, tmD;
+  int rc = encode_tiled_2d(&tmH, H, K, rows, 32, 16, true);
+  if (rc) return rc;
+  rc = encode_tiled_2d(&tmD, D, N, rows, 32, 16, true);
+  if (rc) return rc;
+  const int n32 = (N + 31) / 32;
+  int cols = 32;
+  while (cols < n32 * 32) cols <<= 1;
+  const size_t smem = 1024 + 2 * (4 + static_cast<size_t>(n32)) * tc::MN_ATOM_BYTES;
+  cudaError_t e = cudaFuncSetAttribute(tc_mn_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  tc_mn_test_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tmH, tmD, C, rows, K, N, split, cols, dbg);
+  B200PPO_LAUNCH_CHECK();
+  return 0;
+}

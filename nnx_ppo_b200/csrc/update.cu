@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "tc.cuh"
+#include "tmap.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -73,7 +74,15 @@ struct Layout {
 
 inline size_t align64(size_t x) { return (x + 63) & ~static_cast<size_t>(63); }
 
-double g_dw_wt_thin = 1.0, g_dw_wt_wide = 1.2;
+// Relative cost of one 16-row stage of a dW item (the row splits are handed out so that the most expensive CTA is as
+// cheap as possible).  An item on the MN-major operand path is bound by shared-memory traffic and, at 256 gradient
+// columns, by the tensor pipe: measured per stage (profiles/r2c_notes.md) 0.95 / 1.0 / 2.05 at 16 / 64 / 256 columns
+// (1.85 when the CTA owns only 64 columns of H), 128 columns interpolated.  An item on the transposing path (a width
+// that is not a multiple of 4: the value head, a 42-column policy head) costs `thin` (<= 128 columns) or `wide`.
+// B200PPO_DW_WTS="thin,wide".
+double g_dw_wt_thin = 1.5, g_dw_wt_wide = 1.8;
+bool dw_mn_enabled();
+int dw_mn_maxn();
 bool g_dw_wt_read = false;
 void read_dw_weights() {
   if (g_dw_wt_read) return;
@@ -155,22 +164,45 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
         for (int m = 0; m < cdiv(ch.dims[l], 128) && ni < 32; ++m) {
           // relative cost of one 16-row stage of the item: wide operands are tensor bound, thin ones (the value
           // head: N padded to 16) move a fraction of the bytes.  B200PPO_DW_WTS="thin,wide" overrides (tuning aid).
-          wts[ni] = ch.dims[l + 1] > 128 ? g_dw_wt_wide : (ch.dims[l + 1] <= 16 ? g_dw_wt_thin : 1.0);
+          const bool mn = dw_mn_enabled() && !(ch.dims[l] & 3) && !(ch.dims[l + 1] & 3) && ch.dims[l + 1] <= dw_mn_maxn();
+          const int n32 = (ch.dims[l + 1] + 31) / 32;
+          const int kw_m = ch.dims[l] - m * 128 < 128 ? ch.dims[l] - m * 128 : 128;
+          const double w_mn = n32 <= 1 ? 0.95 : (n32 == 2 ? 1.0 : (n32 <= 4 ? 1.33 : (kw_m <= 64 ? 1.85 : 2.05)));
+          wts[ni] = mn ? w_mn : (ch.dims[l + 1] > 128 ? g_dw_wt_wide : g_dw_wt_thin);
           wsum += wts[ni++];
         }
     }
     if (L.tc_tiles > 32) L.tc_ok = 0;
     L.tc_S = 1;
+    // greedy minimax: every item starts with one split; the item whose CTAs are the most expensive (cost per stage
+    // x rows per split, rows in multiples of 32) gets the next one until the SMs are used up (one CTA per SM)
+    (void)wsum;
+    int Ssum = 0;
     for (int i = 0; i < ni; ++i) {
-      int Si = static_cast<int>(sms * wts[i] / wsum);
-      if (Si < 1) Si = 1;
-      if (Si > 64) Si = 64;
-      int rps_i = cdiv(cdiv(L.R, Si), 32) * 32;
-      if (rps_i < 32) rps_i = 32;
-      L.tc_item_rps[i] = rps_i;
-      L.tc_item_S[i] = cdiv(L.R, rps_i);
-      if (L.tc_item_S[i] > L.tc_S) L.tc_S = L.tc_item_S[i];
+      L.tc_item_S[i] = 1;
+      L.tc_item_rps[i] = cdiv(L.R, 32) * 32;
+      ++Ssum;
     }
+    while (Ssum < sms) {
+      int worst = -1;
+      double wc = -1.0;
+      for (int i = 0; i < ni; ++i) {
+        const double c = wts[i] * L.tc_item_rps[i];
+        if (c > wc && L.tc_item_S[i] < 64 && L.tc_item_rps[i] > 32) { wc = c; worst = i; }
+      }
+      if (worst < 0) break;
+      // the next split count that actually shortens the item's rows per split
+      int Sn = L.tc_item_S[worst] + 1, rps_n = L.tc_item_rps[worst];
+      while (Sn <= 64 && (rps_n = cdiv(cdiv(L.R, Sn), 32) * 32) >= L.tc_item_rps[worst]) ++Sn;
+      if (Sn > 64) break;
+      const int S_real = cdiv(L.R, rps_n);
+      if (Ssum - L.tc_item_S[worst] + S_real > sms) break;
+      Ssum += S_real - L.tc_item_S[worst];
+      L.tc_item_S[worst] = S_real;
+      L.tc_item_rps[worst] = rps_n;
+    }
+    for (int i = 0; i < ni; ++i)
+      if (L.tc_item_S[i] > L.tc_S) L.tc_S = L.tc_item_S[i];
     for (int i = ni; i < 32; ++i) { L.tc_item_S[i] = 0; L.tc_item_rps[i] = 32; }
     L.tc_rows_per_split = L.tc_item_rps[0];
   }
@@ -504,8 +536,22 @@ __device__ __forceinline__ uint32_t comm_epoch_of(const uint32_t* comm_epoch, co
 
 // Block sums of (adv, adv^2) -> per-block partials -> the last block to finish adds them in block order and
 // publishes the minibatch sums (and pushes them to the peers): shared tail of the two GAE kernels.
+// `bid` / `nblk`: this block's index among the GAE blocks (the fused GAE + loss kernel runs them as the first blocks
+// of a larger grid); `ready` (nullable): flag the last block releases once the advantages and their sums are
+// complete, for the loss blocks of the same launch.
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int TICKET_GAE_READY = 4;
+
 template <int NW>
-__device__ __forceinline__ void gae_finish(const GaeArgs& a, double s1, double s2, double (*red)[NW], bool* is_last) {
+__device__ __forceinline__ void gae_finish(const GaeArgs& a, double s1, double s2, double (*red)[NW], bool* is_last,
+                                           unsigned int bid, unsigned int nblk, unsigned int* ready) {
   __syncthreads();
   s1 = warp_sum_d(s1);
   s2 = warp_sum_d(s2);
@@ -518,11 +564,11 @@ __device__ __forceinline__ void gae_finish(const GaeArgs& a, double s1, double s
     double b1 = 0.0, b2 = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) { b1 += red[0][w]; b2 += red[1][w]; }
-    part[2 * blockIdx.x] = b1;
-    part[2 * blockIdx.x + 1] = b2;
+    part[2 * bid] = b1;
+    part[2 * bid + 1] = b2;
     __threadfence();
     const unsigned int tk = atomicAdd(&ticket[0], 1u);
-    *is_last = tk == gridDim.x - 1;
+    *is_last = tk == nblk - 1;
     if (*is_last) {
       ticket[0] = 0u;
       __threadfence();
@@ -532,7 +578,7 @@ __device__ __forceinline__ void gae_finish(const GaeArgs& a, double s1, double s
   if (!*is_last || threadIdx.x >= 32) return;
   // fixed order whatever block finishes last: lane l adds blocks l, l + 32, ... then a butterfly over the lanes
   double t1 = 0.0, t2 = 0.0;
-  for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) {
+  for (unsigned int b = threadIdx.x; b < nblk; b += 32) {
     t1 += __ldcg(&part[2 * b]);
     t2 += __ldcg(&part[2 * b + 1]);
   }
@@ -551,6 +597,10 @@ __device__ __forceinline__ void gae_finish(const GaeArgs& a, double s1, double s
         uint2* slot = reinterpret_cast<uint2*>(comm_base(a.comm, r) + COMM_ADV) + ((epoch & 1u) * MAXR + a.comm.rank) * 4;
         for (int i = 0; i < 4; ++i) ll_store(slot + i, w[i], epoch);
       }
+    }
+    if (ready != nullptr) {                    // every block's advantages were fenced before its ticket
+      __threadfence();
+      st_release_u32(ready, 1u);
     }
   }
 }
@@ -605,7 +655,7 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
       }
     }
   }
-  gae_finish<4>(a, s1, s2, red, &is_last);
+  gae_finish<4>(a, s1, s2, red, &is_last, blockIdx.x, gridDim.x, nullptr);
 }
 
 // The same recurrence with the time steps of an env spread over the block: every (t, env) element computes its
@@ -617,15 +667,14 @@ __global__ void __launch_bounds__(GAE_THREADS) upd_gae_kernel(const GaeArgs a) {
 constexpr int GAE_PAR_THREADS = 256;
 constexpr int GAE_PAR_EPB = 8;            // envs per block: 64 blocks for a 512-env minibatch
 
-__global__ void __launch_bounds__(GAE_PAR_THREADS) upd_gae_par_kernel(const GaeArgs a) {
-  extern __shared__ float gsm[];          // [2][T][EPB]: residual (overwritten by the advantage) | coefficient
+__device__ __forceinline__ void gae_par_body(const GaeArgs& a, float* gsm, const unsigned int bid,
+                                             const unsigned int nblk, unsigned int* ready) {
+  // gsm: [2][T][EPB]: residual (overwritten by the advantage) | coefficient
   __shared__ double red[2][GAE_PAR_THREADS / 32];
   __shared__ bool is_last;
   __shared__ int env_s[GAE_PAR_EPB];
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int E = GAE_PAR_EPB;
-  const int j0 = blockIdx.x * E;
+  const int j0 = static_cast<int>(bid) * E;
   const float* v = a.ws + a.v_off;
   float* adv = a.ws + a.L.adv;
   const float gamma = a.hpd ? a.hpd[B200PPO_HP_GAMMA] : a.gamma;
@@ -669,7 +718,14 @@ __global__ void __launch_bounds__(GAE_PAR_THREADS) upd_gae_par_kernel(const GaeA
       s2 += static_cast<double>(x) * x;
     }
   }
-  gae_finish<GAE_PAR_THREADS / 32>(a, s1, s2, red, &is_last);
+  gae_finish<GAE_PAR_THREADS / 32>(a, s1, s2, red, &is_last, bid, nblk, ready);
+}
+
+__global__ void __launch_bounds__(GAE_PAR_THREADS) upd_gae_par_kernel(const GaeArgs a) {
+  extern __shared__ float gsm[];
+  pdl_launch_dependents();
+  pdl_wait();
+  gae_par_body(a, gsm, blockIdx.x, gridDim.x, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -858,17 +914,18 @@ __global__ void __launch_bounds__(128) upd_loss_kernel(const LossArgs a) {
 // threefry / erfinv / transcendental chains of the A dims run in parallel and the two row sums
 // (log-lik, entropy) are butterfly reductions over the A adjacent lanes.  ncu: the thread-per-row
 // version ran 4 warps per SM on long dependent chains (27 us per launch).
-__global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
+// `bid` / `nblk`: this block's index among the loss blocks; `ready` (nullable): the fused launch's GAE blocks release
+// it when the advantages and their sums are complete (the last loss block clears it again).
+__device__ __forceinline__ void loss_par_body(const LossArgs& a, const unsigned int bid, const unsigned int nblk,
+                                              unsigned int* ready) {
   __shared__ double red[NLQ][8];
   __shared__ float stats_s[2];
-  pdl_launch_dependents();
-  pdl_wait();
   const int A = a.plan.act_dim;
   // AP = A rounded up to a power of two lanes per row (lanes d >= A idle: Humanoid-scale A = 21 runs on 32 lanes
   // instead of falling back to the thread-per-row kernel: 70 -> 54 us per launch at configs[3])
   const int ap_log2 = A > 1 ? 32 - __clz(A - 1) : 0;
   const int AP = 1 << ap_log2;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gid = static_cast<int>(bid) * blockDim.x + threadIdx.x;
   const int r = gid >> ap_log2, d = gid & (AP - 1);
   const double ng = a.n_global;
   const float inv_n = static_cast<float>(1.0 / ng);
@@ -900,7 +957,13 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
   // global advantage moments (fp64 once per block).  Taken AFTER the sampler math: with the peer
   // exchange this is where a rank waits for the other ranks' GAE sums, and the NVLink latency
   // hides behind the threefry / erfinv / transcendental work above.
-  if (threadIdx.x == 0) loss_adv_stats(a, stats_s[0], stats_s[1]);
+  if (threadIdx.x == 0) {
+    // fused launch: the GAE blocks of this grid (lowest block indices: dispatched first, they wait for nobody) are
+    // still at work while the sampler math above runs; everything below needs their advantages
+    if (ready != nullptr)
+      while (ld_acquire_u32(ready) == 0u) __nanosleep(20);
+    loss_adv_stats(a, stats_s[0], stats_s[1]);
+  }
   __syncthreads();
   const float a_mean = stats_s[0], a_den = stats_s[1];
   const float clip = a.hpd ? a.hpd[B200PPO_HP_CLIP_RANGE] : a.clip;
@@ -912,7 +975,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
       g_ll = -inv_n;
       c1 = c2 = ll;                                            // l_actor = -min(c1, c2) = -ll below
     } else {
-      const float adv = a.ws[a.L.adv + r];
+      const float adv = __ldcg(a.ws + a.L.adv + r);            // written by other SMs, maybe during this launch
       const float v = a.ws[a.v_off + r];
       target = __fadd_rn(v, adv);
       diff = __fsub_rn(v, target);
@@ -960,12 +1023,15 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     for (int q = 0; q < NLQ; ++q) {
       double sacc = 0.0;
       for (int w = 0; w < 8; ++w) sacc += red[q][w];
-      part[NLQ * blockIdx.x + q] = sacc;
+      part[NLQ * bid + q] = sacc;
     }
     __threadfence();
     const unsigned int tk = atomicAdd(&ticket[1], 1u);
-    is_last_s = tk == gridDim.x - 1;
-    if (is_last_s) ticket[1] = 0u;
+    is_last_s = tk == nblk - 1;
+    if (is_last_s) {
+      ticket[1] = 0u;
+      if (ready != nullptr) *ready = 0u;      // every loss block passed its wait before it took a ticket
+    }
   }
   __syncthreads();
   if (is_last_s) {
@@ -973,7 +1039,7 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
     // together, then a fixed-order tree): deterministic, and not a serial latency chain
     __threadfence();
     double acc[NLQ] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+    for (unsigned int b = threadIdx.x; b < nblk; b += blockDim.x)
       for (int q = 0; q < NLQ; ++q) acc[q] += __ldcg(&part[NLQ * b + q]);
     for (int q = 0; q < NLQ; ++q) acc[q] = warp_sum_d(acc[q]);
     __syncthreads();
@@ -990,6 +1056,25 @@ __global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
       loss_write_metrics(a, tot, a_mean, a_den);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) upd_loss_par_kernel(const LossArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  loss_par_body(a, blockIdx.x, gridDim.x, nullptr);
+}
+
+// GAE and loss of one update in ONE launch: blocks [0, n_gae) run the time-parallel GAE, the others the loss.  The
+// loss blocks' sampler math (threefry, erfinv, the transcendental chains: most of their time) needs no advantage, so
+// it overlaps the GAE blocks' two dependent memory round trips; one launch boundary less per update.
+static_assert(GAE_PAR_THREADS == 256, "the fused kernel runs both bodies on 256-thread blocks");
+__global__ void __launch_bounds__(256) upd_gae_loss_kernel(const GaeArgs g, const LossArgs a, const unsigned int n_gae) {
+  extern __shared__ float gsm[];
+  pdl_launch_dependents();
+  pdl_wait();
+  unsigned int* ready = reinterpret_cast<unsigned int*>(a.ws + a.L.tickets) + TICKET_GAE_READY;
+  if (blockIdx.x < n_gae) gae_par_body(g, gsm, blockIdx.x, n_gae, ready);
+  else loss_par_body(a, blockIdx.x - n_gae, gridDim.x - n_gae, ready);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1350,27 +1435,8 @@ int set_attrs() {
 // Tensor map over xhat [rows][O] (fp32, row pitch O * 4 bytes) with a 128-column x 16-row box for the dW kernel's
 // wide observation layer.  cuTensorMapEncodeTiled is a host-only driver function: resolved through the runtime
 // (no link dependency on libcuda).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 int encode_xhat_map(CUtensorMap* tm, const float* xhat, int O, int rows) {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    if (q != cudaDriverEntryPointSuccess || p == nullptr) return B200PPO_ELIMIT;
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(O), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t gstr[1] = {static_cast<cuuint64_t>(O) * 4u};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(TCM), static_cast<cuuint32_t>(TCK)};
-  const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(xhat), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : B200PPO_EINVAL;
+  return encode_tiled_2d(tm, xhat, O, rows, TCM, TCK, false);
 }
 
 // GEMM engine: 0 = fp32 FFMA (CUDA cores), 1 = tcgen05 3xTF32 (default, fp32-level accuracy),
@@ -1384,6 +1450,57 @@ int gemm_mode() {
     if (e && !std::strcmp(e, "tf32")) g_gemm_mode = 2;
   }
   return g_gemm_mode;
+}
+
+// deepest raw ring of the dW kernel (2 .. DW2_NR_MAX; B200PPO_DW_NR=2 is the fixed two-slot ring of the first version)
+int g_dw_nr = -1;
+int dw_nr_max() {
+  if (g_dw_nr < 0) {
+    const char* e = std::getenv("B200PPO_DW_NR");
+    int v = e ? std::atoi(e) : DW2_NR_MAX;
+    g_dw_nr = v < 2 ? 2 : (v > DW2_NR_MAX ? DW2_NR_MAX : v);
+  }
+  return g_dw_nr;
+}
+
+// dW operand path: MN-major TMA boxes (default) or the transposing v2 path for every layer (B200PPO_DW_MN=0)
+int g_dw_mn = -1;
+bool dw_mn_enabled() {
+  if (g_dw_mn < 0) {
+    const char* e = std::getenv("B200PPO_DW_MN");
+    g_dw_mn = (e && !std::strcmp(e, "0")) ? 0 : 1;
+  }
+  return g_dw_mn != 0;
+}
+
+int g_dw_mn_maxn = -1;
+int dw_mn_maxn() {
+  if (g_dw_mn_maxn < 0) {
+    const char* e = std::getenv("B200PPO_DW_MN_MAXN");
+    g_dw_mn_maxn = e ? std::atoi(e) : 256;
+  }
+  return g_dw_mn_maxn;
+}
+
+// GAE + loss of an update in one launch (default) or two (B200PPO_FUSE_GAE_LOSS=0)
+int g_fuse_gl = -1;
+bool fuse_gae_loss() {
+  if (g_fuse_gl < 0) {
+    const char* e = std::getenv("B200PPO_FUSE_GAE_LOSS");
+    g_fuse_gl = (e && !std::strcmp(e, "0")) ? 0 : 1;
+  }
+  return g_fuse_gl != 0;
+}
+
+// the fused launch needs both stages in one call, both in their block-parallel form (no NLL head: it has no GAE)
+bool gae_loss_fusable(const b200ppo_plan& plan, const Layout& L, int T, int mb, int stages) {
+  if (!fuse_gae_loss() || !(stages & B200PPO_STAGE_GAE) || !(stages & B200PPO_STAGE_LOSS) || (stages & B200PPO_STAGE_NLL))
+    return false;
+  int AP = 1;
+  while (AP < plan.act_dim) AP <<= 1;
+  const size_t gae_smem = 2 * static_cast<size_t>(T) * GAE_PAR_EPB * sizeof(float);
+  return cdiv(mb, GAE_PAR_EPB) <= MAX_PART_BLOCKS && gae_smem <= 8 * 1024 && plan.act_dim <= 32 &&
+         cdiv(static_cast<int64_t>(L.R) * AP, 256) <= MAX_LOSS_BLOCKS;
 }
 
 }  // namespace
@@ -1407,6 +1524,15 @@ extern "C" int b200ppo_debug_timestamps(long long* out_host, int32_t max_n) {
   return -1000 - n;   // encodes the count: n = -(rc + 1000)
 }
 
+extern "C" int b200ppo_debug_cta_times(unsigned long long* out_host, int32_t max_ctas) {
+  if (!out_host || max_ctas <= 0) return B200PPO_EINVAL;
+  const int n = max_ctas < TC_MAX_CTA_T ? max_ctas : TC_MAX_CTA_T;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaMemcpyFromSymbol(out_host, g_cta_gt, sizeof(unsigned long long) * 3 * n);
+  return e == cudaSuccess ? n : -static_cast<int>(e);
+}
+
 extern "C" int b200ppo_debug_select(int skip_dw) {
   cudaError_t e = cudaMemcpyToSymbol(g_tc_stamp_skip_dw, &skip_dw, sizeof(int));
   return e == cudaSuccess ? 0 : static_cast<int>(e);
@@ -1426,7 +1552,7 @@ extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200p
   int n = 0;
   if (stages & B200PPO_STAGE_FWD) n += (use_tc && !(stages & B200PPO_STAGE_NO_PREP)) ? 2 : 1;
   if (stages & B200PPO_STAGE_GAE) n += 1;
-  if (stages & B200PPO_STAGE_LOSS) n += 1;
+  if (stages & B200PPO_STAGE_LOSS) n += gae_loss_fusable(*plan, L, T, mb, stages) ? 0 : 1;
   if (stages & B200PPO_STAGE_BWD) n += 2;
   else n += ((stages & B200PPO_STAGE_BWD_DX) ? 1 : 0) + ((stages & B200PPO_STAGE_BWD_DW) ? 1 : 0);
   const bool red = (stages & B200PPO_STAGE_RED) != 0, adam = (stages & B200PPO_STAGE_ADAM) != 0;
@@ -1533,6 +1659,10 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
       B200PPO_LAUNCH(upd_fwd_kernel, dim3(cdiv(L.Rv, TM)), dim3(NTH), GEMM_SMEM, s, a);
     }
   }
+  // GAE + loss in one launch (see upd_gae_loss_kernel) when a call runs both stages and both have their
+  // block-parallel form; B200PPO_FUSE_GAE_LOSS=0 keeps the two launches (A/B switch)
+  GaeArgs ga_fused;
+  bool fuse_gl = false;
   if (stages & B200PPO_STAGE_GAE) {
     GaeArgs a;
     a.L = L; a.reward = b->reward; a.done = b->done; a.trunc = b->truncated; a.inds = b->inds;
@@ -1542,7 +1672,11 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     a.rng_state = b->rng_state; a.comm_epoch = b->comm_epoch; a.update_index = update_index;
     // time-parallel version unless its partial-sum blocks or its shared-memory arrays would not fit
     const size_t gae_smem = 2 * static_cast<size_t>(T) * GAE_PAR_EPB * sizeof(float);
-    if (cdiv(mb, GAE_PAR_EPB) <= MAX_PART_BLOCKS && gae_smem <= 40 * 1024)
+    fuse_gl = gae_loss_fusable(*plan, L, T, mb, stages);
+    ga_fused = a;
+    if (fuse_gl) {
+      // launched below, together with the loss
+    } else if (cdiv(mb, GAE_PAR_EPB) <= MAX_PART_BLOCKS && gae_smem <= 40 * 1024)
       B200PPO_LAUNCH_C(1, upd_gae_par_kernel, dim3(cdiv(mb, GAE_PAR_EPB)), dim3(GAE_PAR_THREADS), gae_smem, s, a);
     else
       B200PPO_LAUNCH_C(1, upd_gae_kernel, dim3(cdiv(mb, GAE_THREADS)), dim3(GAE_THREADS), 0, s, a);
@@ -1564,7 +1698,12 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
     int AP = 1;
     while (AP < A) AP <<= 1;
     const bool par = A <= 32 && cdiv(static_cast<int64_t>(L.R) * AP, 256) <= MAX_LOSS_BLOCKS;
-    if (par) B200PPO_LAUNCH_C(1, upd_loss_par_kernel, dim3(cdiv(static_cast<int64_t>(L.R) * AP, 256)), dim3(256), 0, s, a);
+    if (fuse_gl) {
+      const unsigned int n_gae = cdiv(mb, GAE_PAR_EPB);
+      const size_t gae_smem = 2 * static_cast<size_t>(T) * GAE_PAR_EPB * sizeof(float);
+      B200PPO_LAUNCH_C(1, upd_gae_loss_kernel, dim3(n_gae + cdiv(static_cast<int64_t>(L.R) * AP, 256)), dim3(256), gae_smem, s,
+                       ga_fused, a, n_gae);
+    } else if (par) B200PPO_LAUNCH_C(1, upd_loss_par_kernel, dim3(cdiv(static_cast<int64_t>(L.R) * AP, 256)), dim3(256), 0, s, a);
     else B200PPO_LAUNCH_C(1, upd_loss_kernel, dim3(cdiv(L.R, 128)), dim3(128), 0, s, a);
   }
   if (stages & (B200PPO_STAGE_BWD | B200PPO_STAGE_BWD_DX | B200PPO_STAGE_BWD_DW)) {
@@ -1582,7 +1721,28 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
             const int trc = encode_xhat_map(&tm, ws + L.xhat, plan->obs_dim, L.R);
             if (trc) return trc;
           }
-          B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0, tm);
+          // v3 operand path (MN-major TMA boxes) for every layer whose two widths give 16-byte row pitches
+          static DwMaps maps;                   // host scratch (calls are serialised by the caller's stream use)
+          uint32_t mn_mask = 0u;
+          if (dw_mn_enabled()) {
+            for (int c = 0; c < 2; ++c) {
+              const b200ppo_chain& ch = c == 0 ? plan->actor : plan->critic;
+              const size_t* zo = c == 0 ? L.za : L.zc;
+              const size_t* dof = c == 0 ? L.da : L.dc;
+              for (int l = 0; l < ch.n_layers; ++l) {
+                const int K = ch.dims[l], N = ch.dims[l + 1];
+                const float* H = l == 0 ? ws + L.xhat : ws + zo[l - 1];
+                const float* D = ws + dof[l];
+                if ((K & 3) || (N & 3) || (reinterpret_cast<uintptr_t>(H) & 15) || (reinterpret_cast<uintptr_t>(D) & 15)) continue;
+                if (N > dw_mn_maxn()) continue;
+                if (encode_mn_atoms_3d(&maps.h[c * MAXL + l], H, K, L.R, TCK, 4)) continue;
+                if (encode_mn_atoms_3d(&maps.d[c * MAXL + l], D, N, L.R, TCK, (N + 31) / 32)) continue;
+                mn_mask |= 1u << (c * MAXL + l);
+              }
+            }
+          }
+          B200PPO_LAUNCH(upd_bwd_dw_tc2_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), DW2_SMEM, s, a, tc_split, 0, tm, dw_nr_max(),
+                         maps, mn_mask);
         }
         else B200PPO_LAUNCH(upd_bwd_dw_tc_kernel, dim3(L.tc_tiles, L.tc_S), dim3(TCT), TC_SMEM, s, a, tc_split, 0);
       }

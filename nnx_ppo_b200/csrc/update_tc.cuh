@@ -53,6 +53,19 @@ __device__ __forceinline__ void tc_stamp(int& n) {
 #define TC_PROBE_FLUSH(base, n) do { } while (0)
 #endif
 
+// wall-clock (globaltimer, ns) of every CTA of the most recent tensor-core update kernel: entry, set-up done
+// (TMEM / barriers), exit — read back with b200ppo_debug_cta_times; three stores per CTA
+constexpr int TC_MAX_CTA_T = 1024;
+__device__ unsigned long long g_cta_gt[3 * TC_MAX_CTA_T];
+__device__ __forceinline__ void tc_cta_time(int which) {
+  const unsigned int cta = blockIdx.x + blockIdx.y * gridDim.x;
+  if (threadIdx.x == 0 && cta < TC_MAX_CTA_T) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_gt[3 * cta + which] = t;
+  }
+}
+
 struct TcCtx {
   uint8_t* smem;
   uint64_t* bar_empty;   // [NS] stage free (tcgen05.commit of the MMAs that read it)
@@ -74,6 +87,7 @@ struct TcCtx {
 __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* bars, uint32_t* tmem_slot,
                                             uint32_t tmem_cols = TC_MAXN) {
   const int warp = threadIdx.x >> 5;
+  tc_cta_time(0);
   if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
   if (threadIdx.x == 32) {
 #pragma unroll
@@ -104,6 +118,7 @@ __device__ __forceinline__ void tc_ctx_init(TcCtx& cx, uint8_t* smem, uint64_t* 
   cx.chain_ok = false;
   cx.nstamp = (static_cast<int>(blockIdx.x) == (g_tc_stamp_skip_dw >> 8) && blockIdx.y == 0) ? 0 : -100000;
   tc_stamp(cx.nstamp);
+  tc_cta_time(1);
 }
 
 __device__ __forceinline__ void tc_ctx_fini(TcCtx& cx) {
@@ -112,6 +127,7 @@ __device__ __forceinline__ void tc_ctx_fini(TcCtx& cx) {
   tc::tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(cx.tmem_base, cx.tmem_cols);
+  tc_cta_time(2);
 }
 
 struct TcStage {
@@ -1115,7 +1131,8 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc_kernel(const BwdArgs a, 
 // host keeps v1.
 // ------------------------------------------------------------------------------------------
 constexpr int DW2_NS = 3;                                    // UMMA stage ring
-constexpr int DW2_NR = 2;                                    // raw ring
+constexpr int DW2_NR = 2;                                    // raw ring: slots of the widest item (sizes the area)
+constexpr int DW2_NR_MAX = 8;                                // narrower items cut the same area into more, smaller slots
 constexpr int DW2_MAXK = 256;                                // widest H the raw ring holds (full rows)
 constexpr uint32_t DW2_RAW_A = TCK * DW2_MAXK * 4u;          // 16 full rows of H
 constexpr uint32_t DW2_RAW_B = TCK * TC_MAXN * 4u;           // 16 rows x <= 256 columns
@@ -1125,11 +1142,36 @@ constexpr uint32_t DW2_SMEM = DW2_NS * TC_STAGE_BYTES + DW2_NR * DW2_RAW_BYTES;
 // Observation layers wider than DW2_MAXK (layer 0 of a chain: H = xhat [rows][obs_dim]; dict-observation plans,
 // BASELINE configs[3]) cannot stage full rows: their CTA's 16-row x 128-column block is fetched by ONE 2-D tiled TMA
 // load (`tm_xhat`: tensor map over xhat, box 128 x 16, zero fill beyond obs_dim / the rows) and lands densely.
+// dW v3 (MN-major operands, tc.cuh): both operands of dW = H^T D already have the reduction index (the row) as their
+// slow dimension in global memory, which IS the MN-major operand layout — a {32 columns, 16 rows} TMA box with the
+// 32-byte-atom 128-byte swizzle lands as a ready UMMA operand, no transposition.  The hi half of the 3xTF32 split is
+// the tile as it landed (the tensor core reads the upper 19 bits of an fp32 word: hi = trunc(x)); the producer warps
+// only apply the activation in place and write lo = x - trunc(x) at the same offsets of a second tile: ~15 instead of
+// ~100 instructions per thread and 16-row stage (clock64 probes of v2, profiles/r2c_notes.md: the transposing warps
+// were busy 630 of the 1 140 cycles of a stage and the issuer waited for them 57 % of the time).  Layers whose widths
+// are not multiples of 4 (TMA row pitch; the value head's [rows][1] gradient) keep the v2 path below, in the same
+// launch.  One tensor map per layer and operand, indexed actor layers first.
+struct DwMaps {
+  CUtensorMap h[2 * MAXL];
+  CUtensorMap d[2 * MAXL];
+};
+constexpr int DW3_NS = 4;                                     // stage ring (A hi | A lo | B hi | B lo, TMA-fed): slots of the widest item
+constexpr int DW3_NG = 4;                                     // producer groups (4 warps each): group g owns stages s = g (mod 4)
+constexpr int DW3_NS_MAX = 8;                                 // narrower items cut the same area into more slots (latency-bound stream)
+constexpr uint32_t DW3_A_BYTES = 4u * tc::MN_ATOM_BYTES;      // 128 columns of H x 16 rows
+__host__ __device__ constexpr uint32_t dw3_stage_bytes(int n32) {
+  return 2u * DW3_A_BYTES + 2u * static_cast<uint32_t>(n32) * tc::MN_ATOM_BYTES;
+}
+static_assert(DW3_NS * dw3_stage_bytes(8) + 1024u <= DW2_SMEM, "v3 ring must fit the launch's shared memory");
+
 __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a, const int split, const int item_base,
-                                                                const __grid_constant__ CUtensorMap tm_xhat) {
+                                                                const __grid_constant__ CUtensorMap tm_xhat,
+                                                                const int nr_max, const __grid_constant__ DwMaps maps,
+                                                                const uint32_t mn_mask) {
   extern __shared__ __align__(128) uint8_t tsmem[];
   __shared__ uint64_t bars[TC_NBARS];
-  __shared__ uint64_t rbar[2 * DW2_NR];                      // [0..NR) raw full, [NR..2NR) raw empty
+  __shared__ uint64_t rbar[2 * DW2_NR_MAX];                  // [0..NRMAX) raw full, [NRMAX..2 NRMAX) raw empty
+  __shared__ uint64_t bar3[3 * DW3_NS_MAX];                  // v3 ring: TMA landed | lo halves written | MMAs retired
   __shared__ uint32_t tmem_slot;
   __shared__ float bred[2][TC_NPROD];
   pdl_launch_dependents();
@@ -1137,24 +1179,31 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   const b200ppo_chain* ch = &a.plan.actor;
   const size_t* zoff = a.L.za;
   const size_t* doff = a.L.da;
-  int layer = -1, mt = 0;
+  int layer = -1, mt = 0, glayer = 0;                       // glayer: index into `maps` / bit of `mn_mask`
   for (int c = 0; c < 2 && layer < 0; ++c) {
     ch = c == 0 ? &a.plan.actor : &a.plan.critic;
     zoff = c == 0 ? a.L.za : a.L.zc;
     doff = c == 0 ? a.L.da : a.L.dc;
     for (int l = 0; l < ch->n_layers; ++l) {
       const int nm = (ch->dims[l] + TCM - 1) / TCM;
-      if (item < nm) { layer = l; mt = item; break; }
+      if (item < nm) { layer = l; mt = item; glayer = c * MAXL + l; break; }
       item -= nm;
     }
   }
   if (layer < 0) return;                                   // uniform per CTA
+  const bool use_mn = (mn_mask >> glayer) & 1u;
   if (static_cast<int>(blockIdx.y) >= a.L.tc_item_S[blockIdx.x + item_base]) return;   // this item has fewer row splits
   if (threadIdx.x == 64) {
 #pragma unroll
-    for (int i = 0; i < DW2_NR; ++i) {
+    for (int i = 0; i < DW2_NR_MAX; ++i) {
       tc::mbar_init(&rbar[i], 1);
-      tc::mbar_init(&rbar[DW2_NR + i], TC_NPROD / 32);
+      tc::mbar_init(&rbar[DW2_NR_MAX + i], TC_NPROD / 32);
+    }
+#pragma unroll
+    for (int i = 0; i < DW3_NS_MAX; ++i) {
+      tc::mbar_init(&bar3[i], 1);
+      tc::mbar_init(&bar3[DW3_NS_MAX + i], TC_NPROD / 32 / DW3_NG);
+      tc::mbar_init(&bar3[2 * DW3_NS_MAX + i], 1);
     }
     tc::mbar_init_fence();
   }
@@ -1185,14 +1234,151 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
   const int nst = r_end > r_begin ? (r_end - r_begin + TCK - 1) / TCK : 0;
   uint8_t* raw = tsmem + DW2_NS * TC_STAGE_BYTES;
   uint64_t* raw_full = rbar;
-  uint64_t* raw_empty = rbar + DW2_NR;
+  uint64_t* raw_empty = rbar + DW2_NR_MAX;
+  // Raw ring of this item: a stage is 16 rows of H (full rows, or the CTA's 128 columns through the tensor map) and
+  // of D.  The streamer is latency bound (a slot is refilled only after the transposing warps have read it, and the
+  // refill comes from DRAM), so the depth of the ring is what sets the stage rate: narrow items (64 + 64 columns: 8 KB
+  // per stage) get 8 slots out of the area that holds 2 stages of the widest item (256 + 256 columns).
+  const uint32_t raw_a_bytes = static_cast<uint32_t>(TCK) * static_cast<uint32_t>(K > DW2_MAXK ? TCM : K) * 4u;
+  const uint32_t raw_b_off = (raw_a_bytes + 127u) & ~127u;
+  const uint32_t raw_slot = (raw_b_off + static_cast<uint32_t>(TCK) * static_cast<uint32_t>(N) * 4u + 127u) & ~127u;
+  int NR = static_cast<int>((DW2_NR * DW2_RAW_BYTES) / raw_slot);
+  NR = NR > nr_max ? nr_max : NR;
   float bsum0 = 0.0f, bsum1 = 0.0f;
   const bool spin = (g_tc_stamp_skip_dw & 2) != 0;
   auto wait = [&](uint64_t* bar, uint32_t par) {
     if (spin) tc::mbar_wait_spin(bar, par);
     else tc::mbar_wait(bar, par);
   };
-  if (warp < TC_NPROD / 32) {
+  float bs[8][4];                                            // v3: column sums of this thread's D chunks (bias gradient)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bs[i][0] = bs[i][1] = bs[i][2] = bs[i][3] = 0.0f;
+  if (use_mn) {
+    // ---------------- v3: TMA-fed MN-major operands ----------------
+    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tsmem) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int n32 = (N + 31) >> 5;                           // 32-column atoms of D (zero-filled beyond N)
+    const int na = (kw + 31) >> 5;                           // atoms of H this CTA owns (<= 4)
+    const uint32_t b_bytes = static_cast<uint32_t>(n32) * tc::MN_ATOM_BYTES;
+    const uint32_t stage_b = dw3_stage_bytes(n32);
+    uint64_t* full_raw = bar3;                               // TMA landed (tx count)
+    uint64_t* full_lo = bar3 + DW3_NS_MAX;                   // one arrive per producer warp
+    uint64_t* empty3 = bar3 + 2 * DW3_NS_MAX;                // tcgen05.commit of the MMAs that read the slot
+    int NS3 = static_cast<int>((DW2_SMEM - 1024u) / stage_b);
+    NS3 = NS3 > DW3_NS_MAX ? DW3_NS_MAX : NS3;
+    if (warp < TC_NPROD / 32) {
+      // A producer warp's work on a stage is one dependent chain (wait -> LDS -> STS -> proxy fence -> arrive, ~500
+      // cycles whatever the width), so the 16 warps form DW3_NG groups that take the stages round-robin: four stages
+      // are in the producers' hands at any time.  Thread lt of a group owns, in EVERY 2 KB atom of the stage, the
+      // 16-byte chunk at offset lt * 16 (row lt >> 3): its column sums (bias gradient) stay in registers.
+      const int grp = warp >> 2, lt = tid & 127;
+      const bool do_bias = mt == 0;
+      const uint32_t coff = static_cast<uint32_t>(lt) * 16u;
+      for (int s = grp; s < nst; s += DW3_NG) {
+        const int slot = s % NS3;
+        const uint32_t par = static_cast<uint32_t>(s / NS3) & 1u;
+        uint8_t* st = ring + slot * stage_b;
+        uint8_t* a_hi = st;
+        uint8_t* a_lo = st + DW3_A_BYTES;
+        uint8_t* b_hi = st + 2u * DW3_A_BYTES;
+        uint8_t* b_lo = b_hi + b_bytes;
+        wait(&full_raw[slot], par);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < na) {
+            const uint32_t off = static_cast<uint32_t>(i) * tc::MN_ATOM_BYTES + coff;
+            float4 x = *reinterpret_cast<const float4*>(a_hi + off);
+            if (act_in != B200PPO_ACT_NONE) {
+              x = act4(x, act_in);
+              *reinterpret_cast<float4*>(a_hi + off) = x;
+            }
+            if (split) {
+              float4 lo;
+              lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+              lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+              lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+              lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(a_lo + off) = lo;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < n32) {
+            const uint32_t off = static_cast<uint32_t>(j) * tc::MN_ATOM_BYTES + coff;
+            const float4 x = *reinterpret_cast<const float4*>(b_hi + off);
+            if (do_bias) { bs[j][0] += x.x; bs[j][1] += x.y; bs[j][2] += x.z; bs[j][3] += x.w; }
+            if (split) {
+              float4 lo;
+              lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+              lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+              lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+              lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(b_lo + off) = lo;
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if ((tid & 31) == 0) tc::mbar_arrive(&full_lo[slot]);
+      }
+    } else if (warp == TC_NPROD / 32) {
+      // issuer: descriptors of slot 0 once; a slot / k-step / half is an add on the 16-byte start-address field
+      const uint32_t idesc = tc::make_idesc_tf32_mn(TCM, n32 * 32);
+      const uint64_t d0 = tc::make_desc_mn_sw128(tc::smem_u32(ring), tc::MN_ATOM_BYTES, tc::MN_SBO_BYTES);
+      const uint32_t hiw = static_cast<uint32_t>(d0 >> 32), low0 = static_cast<uint32_t>(d0);
+      const uint32_t dcol = cx.tmem_base;
+      int slot = 0;
+      uint32_t par = 0u;
+      for (int s = 0; s < nst; ++s) {
+        wait(&full_lo[slot], par);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t a0 = low0 + ((static_cast<uint32_t>(slot) * stage_b) >> 4);
+          const uint32_t b0 = a0 + ((2u * DW3_A_BYTES) >> 4);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t ah = tc_desc(hiw, a0 + j * (1024u >> 4));
+            const uint64_t bh = tc_desc(hiw, b0 + j * (1024u >> 4));
+            const uint32_t acc0 = (s > 0 || j > 0) ? 1u : 0u;
+            if (split) {
+              const uint64_t al = tc_desc(hiw, a0 + j * (1024u >> 4) + (DW3_A_BYTES >> 4));
+              const uint64_t bl = tc_desc(hiw, b0 + j * (1024u >> 4) + (b_bytes >> 4));
+              tc::mma_tf32(dcol, al, bh, idesc, acc0);
+              tc::mma_tf32(dcol, ah, bl, idesc, 1u);
+              tc::mma_tf32(dcol, ah, bh, idesc, 1u);
+            } else {
+              tc::mma_tf32(dcol, ah, bh, idesc, acc0);
+            }
+          }
+          tc::commit(&empty3[slot]);
+          if (s == nst - 1) tc::commit(cx.bar_done);
+        }
+        __syncwarp();
+        if (++slot == NS3) { slot = 0; par ^= 1u; }
+      }
+    } else {
+      // TMA streamer: two instructions per 16-row stage (3-D maps, tmap.cuh): the CTA's 4 atoms of H and every atom
+      // of D land in the slot's hi tiles
+      if ((tid & 31) == 0) {
+        const CUtensorMap* mh = &maps.h[glayer];
+        const CUtensorMap* md = &maps.d[glayer];
+        const uint32_t bytes = static_cast<uint32_t>(4 + n32) * tc::MN_ATOM_BYTES;   // whole boxes, zero fill included
+        int slot = 0;
+        uint32_t epar = 1u;
+        bool first = true;
+        for (int s = 0; s < nst; ++s) {
+          uint8_t* st = ring + slot * stage_b;
+          const int rs = r_begin + s * TCK;
+          if (!first) wait(&empty3[slot], epar);
+          tc::mbar_arrive_expect_tx(&full_raw[slot], bytes);
+          tc::tma_load_3d(st, mh, 0, rs, m0 >> 5, &full_raw[slot]);                       // 4 atoms of H (zeros beyond K)
+          tc::tma_load_3d(st + 2u * DW3_A_BYTES, md, 0, rs, 0, &full_raw[slot]);          // every atom of D
+          if (++slot == NS3) { slot = 0; epar ^= 1u; first = false; }
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp < TC_NPROD / 32) {
     // A: thread -> (m = tid & 127, plane q = tid >> 7): rows 4q..4q+3 of column m
     const int am = tid & (TCM - 1), aq = tid >> 7;
     const bool av = am < kw;
@@ -1208,10 +1394,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     const int p1 = c1 / npad, col1 = c1 - p1 * npad;
     const bool bv0 = bs0 && col0 < N, bv1 = bs1 && col1 < N;
     const uint32_t b_rs = static_cast<uint32_t>(N) * 4u;
-    const uint32_t b_src0 = DW2_RAW_A + static_cast<uint32_t>(((4 * p0) * N + (bv0 ? col0 : 0)) * 4);
-    const uint32_t b_src1 = DW2_RAW_A + static_cast<uint32_t>(((4 * p1) * N + (bv1 ? col1 : 0)) * 4);
+    const uint32_t b_src0 = raw_b_off + static_cast<uint32_t>(((4 * p0) * N + (bv0 ? col0 : 0)) * 4);
+    const uint32_t b_src1 = raw_b_off + static_cast<uint32_t>(((4 * p1) * N + (bv1 ? col1 : 0)) * 4);
     const uint32_t b_dst0 = p0 * pb + col0 * 16, b_dst1 = p1 * pb + col1 * 16;
-    static_assert(DW2_NR == 2, "raw slot / parity below are derived from the stage number");
+    int lslot = 0;                                          // raw slot / parity of the next `ld` (called in stage order)
+    uint32_t lpar = 0u;
     int uslot = 0;
     uint32_t upar = 1u;                                     // parity to wait on `empty` (first lap skipped)
     bool ufirst = true;
@@ -1219,10 +1406,11 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
     TC_PROBE_DECL
     // shared -> registers for stage s, then hand the raw slot straight back to the streamer
     auto ld = [&](int s, Raw& x) {
-      const int rslot = s & 1;
-      const uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
+      const int rslot = lslot;
+      const uint8_t* rw = raw + rslot * raw_slot;
       TC_PROBE_START();
-      wait(&raw_full[rslot], static_cast<uint32_t>(s >> 1) & 1u);
+      wait(&raw_full[rslot], lpar);
+      if (++lslot == NR) { lslot = 0; lpar ^= 1u; }
       TC_PROBE_LAP(0);
       x.a = x.b0 = x.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (av) {
@@ -1326,14 +1514,14 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
       uint32_t epar = 1u;
       bool first = true;
       for (int s = 0; s < nst; ++s) {
-        uint8_t* rw = raw + rslot * DW2_RAW_BYTES;
+        uint8_t* rw = raw + rslot * raw_slot;
         const size_t rs = static_cast<size_t>(r_begin) + static_cast<size_t>(s) * TCK;
         if (!first) wait(&raw_empty[rslot], epar);
         tc::mbar_arrive_expect_tx(&raw_full[rslot], bytes_a + bytes_b);
         if (wide) tc::tma_load_2d(rw, &tm_xhat, m0, static_cast<int>(rs), &raw_full[rslot]);
         else tc::bulk_g2s(rw, H + rs * K, bytes_a, &raw_full[rslot]);
-        tc::bulk_g2s(rw + DW2_RAW_A, D + rs * N, bytes_b, &raw_full[rslot]);
-        if (++rslot == DW2_NR) { rslot = 0; epar ^= 1u; first = false; }
+        tc::bulk_g2s(rw + raw_b_off, D + rs * N, bytes_b, &raw_full[rslot]);
+        if (++rslot == NR) { rslot = 0; epar ^= 1u; first = false; }
       }
     }
     __syncwarp();
@@ -1367,7 +1555,30 @@ __global__ void __launch_bounds__(TCT, 1) upd_bwd_dw_tc2_kernel(const BwdArgs a,
         });
   }
   cx.done_uses++;
-  if (mt == 0) {                                           // bias gradient: fixed-order column sums
+  if (mt == 0 && use_mn) {
+    // v3 bias gradient: thread lt of producer group g holds, for every D atom, the sums of row k = lt >> 3 (over the
+    // group's stages) of the 4 columns at the un-swizzled position of its chunk; the 4 x 16 partial sums of a column
+    // meet in shared memory (the ring is idle now) and are added in (group, row) order
+    __syncthreads();
+    const int n32 = (N + 31) >> 5, ncol = n32 * 32;
+    float* scr = reinterpret_cast<float*>(tsmem);
+    if (tid < TC_NPROD) {
+      const int grp = warp >> 2, lt = tid & 127;
+      const int k = lt >> 3, colin = ((((lt >> 1) & 3) ^ (k & 3)) << 3) + ((lt & 1) << 2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n32)
+          *reinterpret_cast<float4*>(scr + (grp * TCK + k) * ncol + j * 32 + colin) = make_float4(bs[j][0], bs[j][1], bs[j][2], bs[j][3]);
+    }
+    __syncthreads();
+    if (tid < N) {
+      float acc = 0.0f;
+      for (int q = 0; q < DW3_NG * TCK; ++q) acc += scr[q * ncol + tid];
+      gpart[ch->b_off[layer] + tid] = acc;
+      for (int s2 = sp + Si; s2 < S_all; s2 += Si)
+        gpart[static_cast<size_t>(s2 - sp) * a.plan.n_params + ch->b_off[layer] + tid] = 0.0f;
+    }
+  } else if (mt == 0) {                                    // bias gradient: fixed-order column sums
     if (tid < TC_NPROD) { bred[0][tid] = bsum0; bred[1][tid] = bsum1; }
     __syncthreads();
     if (tid < N && tid < TC_MAXN) {

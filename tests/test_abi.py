@@ -185,11 +185,14 @@ def test_host_side_sizing_entry_points_for_the_bench_configuration(lib):
     hp.weight_decay, hp.grad_clip, hp.normalize_advantages, hp.world_size = -1.0, -1.0, 1, 1
     first = int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL))
     later = int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP))
-    assert (first, later) == (7, 6)            # prep + fwd, gae, loss, dX, dW, reduce+adam
+    assert (first, later) == (6, 5)            # prep + fwd, gae+loss (one fused launch), dX, dW, reduce+adam
+    split = int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_GAE)) + \
+        int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_LOSS))
+    assert split == 2                          # the stages called one by one stay two kernels
     # one iteration: 32 updates + norm prepare, rollout, permutation, 2 stats passes, merge, finalize
-    assert first + 31 * later + 7 == 200       # bench.py's gpu_launches at configs[1]
+    assert first + 31 * later + 7 == 168       # bench.py's gpu_launches at configs[1]
     hp.grad_clip = 0.5                         # clip_by_global_norm: reduce (+ exchange) + norm, then the clipped Adam
-    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP)) == 7
+    assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ALL | _lib.STAGE_NO_PREP)) == 6
     assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_RED)) == 1
     assert int(lib.b200ppo_update_num_launches(net.plan, hp, T, mb, _lib.STAGE_ADAM)) == 2
     base = 1 << 20

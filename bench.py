@@ -319,6 +319,10 @@ def time_stages(eng, ts_env_state, lib, _lib, torch, local_only=False, graphs=Tr
     stages = [("fwd", _lib.STAGE_FWD), ("gae", _lib.STAGE_GAE), ("loss", _lib.STAGE_LOSS),
               ("gae_loss", _lib.STAGE_GAE | _lib.STAGE_LOSS),
               ("bwd_dx", _lib.STAGE_BWD_DX), ("bwd_dw", _lib.STAGE_BWD_DW), ("red_adam", _lib.STAGE_RED | _lib.STAGE_ADAM)]
+    if eng.hp.world_size > 1 or local_only:
+        # with the peer exchange every timed stage that waits for the other ranks also measures their launch skew:
+        # keep the two exchange points of the real iteration (loss, Adam), not a third one
+        stages = [st for st in stages if st[0] not in ("gae", "loss")]
     tot = {k: 0.0 for k, _ in stages}
     saved = None
     if local_only:

@@ -415,6 +415,12 @@ int b200ppo_sampler_step(void* stream, const float* y, int32_t B, int32_t A, int
  * compensated, fp32-level accuracy), 2 = tcgen05 plain TF32 (not fp32 parity).  Also selectable  *
  * with the environment variable B200PPO_GEMM=ffma|tf32x3|tf32.  Returns the previous mode.       */
 int b200ppo_set_gemm_mode(int mode);
+/* Kernel-structure switches of the update (A/B measurements, cross-checks; environment: B200PPO_FUSE_GAE_LOSS,  *
+ * B200PPO_DW_MN): fuse_gae_loss_on = 1: GAE and loss of a call that runs both stages are ONE launch (default),     *
+ * 0: two; dw_mn_on = 1: the weight-gradient kernel takes its operands as MN-major swizzled TMA boxes wherever the  *
+ * layer's widths are multiples of 4 (default), 0: it transposes them in shared memory.  -1 keeps a setting.      *
+ * Returns the previous settings (bit 0 | bit 1).  The row-split table of a plan depends on dw_mn_on.              */
+int b200ppo_set_update_paths(int fuse_gae_loss_on, int dw_mn_on);
 /* Dense engine of the rollout (b200ppo_rollout_synth / _ws): 1 = tensor cores (default: the fused kernel on warp-level *
  * mma.sync m16n8k8 tiles, error-compensated 3xTF32, while the weights fit an SM's shared memory; the batched per-step  *
  * tcgen05 GEMM path of b200ppo_rollout_synth_ws beyond that), 0 = fused kernel on fp32 FFMA tiles, 2 = batched path     *

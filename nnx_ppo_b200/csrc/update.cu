@@ -1538,6 +1538,15 @@ extern "C" int b200ppo_debug_select(int skip_dw) {
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
+// bit 0: GAE + loss in one launch, bit 1: dW on the MN-major operand path; argument -1 keeps a setting.  Returns
+// the previous settings packed the same way.
+extern "C" int b200ppo_set_update_paths(int fuse_gae_loss_on, int dw_mn_on) {
+  const int prev = (fuse_gae_loss() ? 1 : 0) | (dw_mn_enabled() ? 2 : 0);
+  if (fuse_gae_loss_on >= 0) g_fuse_gl = fuse_gae_loss_on ? 1 : 0;
+  if (dw_mn_on >= 0) g_dw_mn = dw_mn_on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int b200ppo_set_gemm_mode(int mode) {
   const int prev = gemm_mode();
   if (mode >= 0 && mode <= 2) g_gemm_mode = mode;

@@ -463,6 +463,52 @@ def _single_update(dev, cfg, loose):
         assert abs(eng.metrics[0, 3].item() - np.sqrt((got_g.astype(np.float64) ** 2).sum())) < 1e-4 * max(1, gs)
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(O=64, A=8, ah=[64] * 4, ch=[256] * 2, B=256, T=32, M=2, act="relu"),
+    dict(O=24, A=5, ah=[48, 40], ch=[72], B=70, T=7, M=2, act="swish"),
+    dict(O=300, A=3, ah=[32], ch=[20, 20], B=40, T=5, M=1, act="tanh")])
+def test_update_kernel_structure_switches_agree(dev, cfg):
+    """The two structural choices of the update (b200ppo_set_update_paths) against their plain versions on one
+    rollout: GAE + loss as ONE launch must be bit-identical to the two launches (same blocks, same partial-sum
+    order); the weight-gradient kernel on MN-major TMA operands (hi = truncated tile) must agree with the
+    transposing kernel (hi = rounded) to fp32-GEMM accuracy."""
+    O, A, B, T, M = cfg["O"], cfg["A"], cfg["B"], cfg["T"], cfg["M"]
+    nets, _ = _pair(O, A, cfg["ah"], cfg["ch"], 5, cfg["act"])
+    env = SyntheticEnv(O, A, max_len=12, term_thresh16=2500)
+    ts = ppo.new_training_state(env, nets, B, 3, learning_rate=1e-3)
+    net = compile_network(nets)
+    lib = _lib.load()
+    mb, R = B // M, T * (B // M)
+    out = {}
+    prev = lib.b200ppo_set_update_paths(-1, -1)
+    try:
+        for name, (fuse, mn) in (("new", (1, 1)), ("plain", (0, 0))):
+            lib.b200ppo_set_update_paths(fuse, mn)
+            eng = PPOEngine(net, env, ts.optimizer, B, T, 1, M, 0.95, 0.99, 0.2, True, 1.0, use_graph=False)
+            reset_key, new_key = hprng.split(ts.rng_key)
+            eng.iter_keys.copy_(torch.from_numpy(np.array([*reset_key, *new_key], np.uint32).view(np.int32).copy()))
+            net.sync_counters_to_device()
+            state = type(ts.env_states)(ts.env_states.obs.clone(), ts.env_states.step_counter.clone(),
+                                        ts.env_states.term_state.clone())
+            eng._enqueue_rollout(state)
+            _lib.check(lib.b200ppo_permutation(_lib.current_stream(), eng.iter_keys.data_ptr() + 8, B, 1,
+                                               eng.inds.data_ptr(), eng.perm_scratch.data_ptr()))
+            _lib.check(lib.b200ppo_update(_lib.current_stream(), net.plan, eng.hp, eng.bufs[0], T, B, mb, 2 * T, 0,
+                                          _lib.STAGE_FWD | _lib.STAGE_GAE | _lib.STAGE_LOSS | _lib.STAGE_BWD | _lib.STAGE_RED))
+            torch.cuda.synchronize()
+            out[name] = dict(adv=_dbg(eng, 0, R).copy(), dy=_dbg(eng, 3, R * 2 * A).copy(), dv=_dbg(eng, 4, R).copy(),
+                             met=eng.metrics[0].cpu().numpy().copy(), sums=eng.adv_sums.cpu().numpy().copy(),
+                             grad=net.params_logical(eng.grad).copy())
+    finally:
+        lib.b200ppo_set_update_paths(prev & 1, (prev >> 1) & 1)
+    a, b = out["new"], out["plain"]
+    for k in ("adv", "dy", "dv", "sums"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["met"][:3], b["met"][:3]) and np.array_equal(a["met"][4:11], b["met"][4:11])
+    gs = np.abs(b["grad"]).max()
+    assert np.isfinite(a["grad"]).all() and np.abs(a["grad"] - b["grad"]).max() < 2e-5 * gs, (np.abs(a["grad"] - b["grad"]).max(), gs)
+
+
 # ------------------------------------------------------------------------------------------
 # full iterations through the public API (eager first iteration, captured graph afterwards)
 # ------------------------------------------------------------------------------------------

@@ -43,3 +43,31 @@ def test_tc_microbench_runs(cuda_device):
     torch.cuda.synchronize()
     o = out.cpu().tolist()
     assert all(v > 0 for v in o) and o[0] / 256 < 1000
+
+
+@pytest.mark.parametrize("rows,K,N", [(16, 128, 32), (37, 64, 16), (160, 64, 64), (1024, 64, 4), (1261, 128, 256)])
+def test_tc_mn_major_operand_path(cuda_device, rows, K, N):
+    """The dW kernel's operand path (csrc/tc.cuh make_desc_mn_sw128): C = H^T D with both operands fetched as
+    swizzled {32 column, 16 row} TMA boxes and consumed MN-major, no software transposition.  Small integers are
+    exact in tf32, so the plain-TF32 product must be exact (any layout / swizzle / descriptor mistake is an integer
+    off); the 3xTF32 product (hi = the tile as it landed, lo = x - trunc(x)) stays at fp32-GEMM accuracy."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(rows + K + N)
+    H = torch.randint(-4, 5, (rows, K), generator=g).float().to(cuda_device)
+    D = torch.randint(-4, 5, (rows, N), generator=g).float().to(cuda_device)
+    C = torch.full((K, N), float("nan"), device=cuda_device)
+    _lib.check(lib.b200ppo_tc_mn_test(_lib.current_stream(), H.data_ptr(), D.data_ptr(), C.data_ptr(), rows, K, N, 0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(C.double(), H.double().T @ D.double())
+    H = torch.randn(rows, K, generator=g).to(cuda_device)
+    D = torch.randn(rows, N, generator=g).to(cuda_device)
+    ref = H.double().T @ D.double()
+    err = {}
+    for split in (1, 0):
+        C = torch.full((K, N), float("nan"), device=cuda_device)
+        _lib.check(lib.b200ppo_tc_mn_test(_lib.current_stream(), H.data_ptr(), D.data_ptr(), C.data_ptr(), rows, K, N, split, None))
+        torch.cuda.synchronize()
+        err[split] = (C.double() - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    print(f"rows={rows} K={K} N={N} max|err| 3xTF32 {err[1]:.3e} TF32 {err[0]:.3e} scale {scale:.1f}")
+    assert err[1] < 2e-5 * scale and err[1] < err[0] / 20 and err[0] < 3e-3 * scale

@@ -106,6 +106,38 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.p = None
+        self.nvml = None
+        # NVML from a thread every ~2 ms: a 20-step timed region is ~0.1 s, less than nvidia-smi needs to start
+        try:
+            import threading
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            try:
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._h, self._nv = h, pynvml
+            self._sm, self._bits, self._stop = [], 0, threading.Event()
+            self._mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self._sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+                        self._bits |= int(get(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.nvml = threading.Thread(target=loop, daemon=True)
+            self.nvml.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
@@ -114,6 +146,13 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.nvml.join(timeout=2)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = sorted(n for b, n in names.items() if self._bits & b)
+            return {"sm_mhz": statistics.median(self._sm) if self._sm else None, "sm_max_mhz": self._mx,
+                    "samples": len(self._sm), "reasons": reasons, "source": "nvml, sampled every ~2 ms inside the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -427,8 +466,25 @@ def run_own(args):
         torch.cuda.synchronize()
 
     # warm-up through the public API (iteration 0 eager, iteration 1 captures the CUDA graph)
-    for _ in range(max(args.warmup, 3)):
+    # at least W (>= 3) steps, then as many more as ~0.3 s of device work takes, so that the clocks have ramped (three
+    # 5 ms steps after the idle time of import / build are not enough: the first timed steps then run below the final
+    # clock).  The count is rank 0's, so that every rank runs the same number of (collective) iterations.
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         ts, metrics = ppo.ppo_step(env, ts, *hyper)
+    float(metrics["losses/actor/mean"])
+    barrier()
+    t_w = time.perf_counter()
+    ts, metrics = ppo.ppo_step(env, ts, *hyper)
+    float(metrics["losses/actor/mean"])
+    barrier()
+    extra = torch.tensor([min(200, int(0.3 / max(time.perf_counter() - t_w, 1e-4)))], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.broadcast(extra, src=0)
+    for _ in range(int(extra.item())):
+        ts, metrics = ppo.ppo_step(env, ts, *hyper)
+    float(metrics["losses/actor/mean"])
+    n_warm += 1 + int(extra.item())
     eng = next(reversed(net.engines.values()))
     samples_per_step = cfg["n_envs"] * cfg["T"] * world
 
@@ -479,7 +535,7 @@ def run_own(args):
 
     hbm, tf_peak, which = _peaks()
     line = {"metric": METRIC, "value": value, "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": n_warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": cfg["workload"], "global_envs": cfg["n_envs"] * world, "parallelism": f"dp{world} (env-sharded)",

@@ -465,6 +465,11 @@ int b200ppo_debug_timestamps(long long* out_host, int32_t max_n);
  * number of CTA slots copied (<= 1024).                                                           */
 int b200ppo_debug_cta_times(unsigned long long* out_host, int32_t max_ctas);
 int b200ppo_debug_select(int flags);     /* bit 0: the dW kernel keeps dX's stamps; bits 8..: blockIdx.x of the stamped CTA */
+/* Host-only: the weight-gradient kernel's work table for (plan, T, mb): M-tile item i (actor layers first, one    *
+ * item per 128 input columns of a layer) runs as out_splits[i] CTAs of out_rows_per_split[i] rows each (the sum of   *
+ * the splits never exceeds the SM count: one CTA per SM).  Returns the number of items written (<= max_items).     */
+int b200ppo_update_dw_splits(const b200ppo_plan* plan, int32_t T, int32_t mb, int32_t* out_splits,
+                             int32_t* out_rows_per_split, int32_t max_items);
 /* Number of kernels b200ppo_update launches for the given stage mask (for launch accounting).   */
 int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200ppo_hparams* hp, int32_t T,
                                 int32_t mb, int32_t stages);

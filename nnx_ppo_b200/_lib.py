@@ -108,6 +108,7 @@ SYMBOLS = {
     "b200ppo_debug_timestamps": (C.c_int, [_vp, _i32]),
     "b200ppo_set_gemm_mode": (C.c_int, [C.c_int]),
     "b200ppo_set_update_paths": (C.c_int, [C.c_int, C.c_int]),
+    "b200ppo_update_dw_splits": (C.c_int, [_PP, _i32, _i32, _vp, _vp, _i32]),
     "b200ppo_set_rollout_mode": (C.c_int, [C.c_int]),
     "b200ppo_update_num_launches": (C.c_int, [_PP, _HP, _i32, _i32, _i32]),
     "b200ppo_update_adv_sums_ptr": (_vp, [_PP, _i32, _i32, _vp]),

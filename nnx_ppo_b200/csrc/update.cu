@@ -1572,6 +1572,21 @@ extern "C" int b200ppo_update_num_launches(const b200ppo_plan* plan, const b200p
   return n;
 }
 
+// Host-only: the weight-gradient kernel's work table for (plan, T, mb): out_splits[i] row splits of rows_per_split[i]
+// rows for M-tile item i (actor layers first, one item per 128 input columns of a layer).  Returns the item count.
+extern "C" int b200ppo_update_dw_splits(const b200ppo_plan* plan, int32_t T, int32_t mb, int32_t* out_splits,
+                                        int32_t* out_rows_per_split, int32_t max_items) {
+  if (check_plan_u(plan) || T <= 0 || mb <= 0 || !out_splits || !out_rows_per_split || max_items <= 0) return B200PPO_EINVAL;
+  const Layout L = make_layout(*plan, T, mb);
+  int n = L.tc_tiles < 32 ? L.tc_tiles : 32;
+  if (n > max_items) n = max_items;
+  for (int i = 0; i < n; ++i) {
+    out_splits[i] = L.tc_item_S[i];
+    out_rows_per_split[i] = L.tc_item_rps[i];
+  }
+  return n;
+}
+
 extern "C" int64_t b200ppo_update_workspace_bytes(const b200ppo_plan* plan, int32_t T, int32_t mb) {
   if (check_plan_u(plan) || T <= 0 || mb <= 0) return B200PPO_EINVAL;
   return static_cast<int64_t>(make_layout(*plan, T, mb).total_floats) * 4;
@@ -1731,7 +1746,8 @@ extern "C" int b200ppo_update(void* stream, const b200ppo_plan* plan, const b200
             if (trc) return trc;
           }
           // v3 operand path (MN-major TMA boxes) for every layer whose two widths give 16-byte row pitches
-          static DwMaps maps;                   // host scratch (calls are serialised by the caller's stream use)
+          DwMaps maps;                          // passed by value: captured with the launch
+          std::memset(&maps, 0, sizeof(maps));
           uint32_t mn_mask = 0u;
           if (dw_mn_enabled()) {
             for (int c = 0; c < 2; ++c) {

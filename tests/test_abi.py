@@ -344,3 +344,38 @@ def test_update_launcher_rejects_before_launching(lib):
     hp.world_size = _lib.MAX_RANKS + 1 if hasattr(_lib, "MAX_RANKS") else 17
     hp.grad_clip = -1.0
     assert call() == EINVAL
+
+
+def test_dw_row_split_table_is_a_one_wave_cover(lib):
+    """Host-only: the weight-gradient kernel's work table (greedy minimax over the measured per-stage costs, csrc/update.cu
+    make_layout) for the four BASELINE plans: every item covers all rows in splits of a multiple of 32 rows, the splits
+    fit one wave (<= one CTA per SM), nearly all SMs are used, and the costlier 256-column items get shorter row ranges
+    than the 64-column ones."""
+    import ctypes
+    import torch
+    import bench
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    sms = int(lib.b200ppo_num_sms())
+    for name in ("mlp", "cartpole_shapes", "dict"):
+        cfg = bench.CONFIGS[name]
+        _, nets = bench.build_workload(name, cfg)
+        net = CompiledNet(nets, torch.device("cpu"))
+        T, mb = cfg["T"], cfg["n_envs"] // cfg["M"]
+        R = T * mb
+        S = (ctypes.c_int32 * 32)()
+        rps = (ctypes.c_int32 * 32)()
+        n = int(lib.b200ppo_update_dw_splits(net.plan, T, mb, S, rps, 32))
+        dims = []
+        for ch in (net.plan.actor, net.plan.critic):
+            for l in range(ch.n_layers):
+                dims += [(ch.dims[l], ch.dims[l + 1])] * ((ch.dims[l] + 127) // 128)
+        assert n == len(dims) and n >= 2
+        tot = 0
+        for i in range(n):
+            assert S[i] >= 1 and rps[i] % 32 == 0 and S[i] * rps[i] >= R > (S[i] - 1) * rps[i], (name, i, S[i], rps[i])
+            tot += S[i]
+        assert sms - n <= tot <= sms, (name, tot, sms)
+        wide = [rps[i] for i in range(n) if dims[i][1] > 128 and dims[i][0] % 4 == 0]
+        narrow = [rps[i] for i in range(n) if dims[i][1] == 64 and dims[i][0] % 4 == 0]
+        if wide and narrow:
+            assert max(wide) < min(narrow), (name, wide, narrow)

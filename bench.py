@@ -614,6 +614,9 @@ def run_own(args):
                             "stage_tflops_algorithmic": {k: flops[k] * U / (stage_ms[k] * 1e-3) / 1e12 for k in flops}}
         if sync_us is not None:
             line["roofline"]["sync_us_per_update"] = sync_us
+            line["roofline"]["sync_note"] = ("difference of eagerly launched stages with and without the peer exchange: an upper bound that "
+                                             "includes the ranks' host launch skew (the in-graph cost is the N-GPU minus the 1-GPU iteration "
+                                             "time over the 32 updates)")
     if not args.quick and recurrent:
         line["roofline"] = recurrent_roofline(eng, net, cfg, lib, _lib, torch, tf_peak, which, ms / args.steps)
     if world == 1 and not args.quick and rank == 0:

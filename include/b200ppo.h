@@ -424,7 +424,10 @@ int b200ppo_set_update_paths(int fuse_gae_loss_on, int dw_mn_on);
 /* Dense engine of the rollout (b200ppo_rollout_synth / _ws): 1 = tensor cores (default: the fused kernel on warp-level *
  * mma.sync m16n8k8 tiles, error-compensated 3xTF32, while the weights fit an SM's shared memory; the batched per-step  *
  * tcgen05 GEMM path of b200ppo_rollout_synth_ws beyond that), 0 = fused kernel on fp32 FFMA tiles, 2 = batched path     *
- * whenever a workspace is passed; also B200PPO_ROLLOUT=ffma|mma|wide.  Returns the previous mode.                       */
+ * whenever a workspace is passed; also B200PPO_ROLLOUT=ffma|mma|wide.  Mode 1 picks between the two tensor-core        *
+ * kernels by the number of 16-env tiles (more tiles than SMs: one CTA per SM with two env groups sharing the weights;  *
+ * else one tile per CTA); 3 / 4 = mode 1 with the one-tile / two-group kernel forced (tests, A/B; B200PPO_ROLLOUT_MMA=1|2). *
+ * Returns the previous mode (0..2).                                                                                    */
 int b200ppo_set_rollout_mode(int mode);
 /* b200ppo_rollout_synth with a caller-owned scratch buffer (b200ppo_rollout_synth_workspace_bytes(plan, B) bytes; 0 =  *
  * this plan keeps its weights resident in the fused kernel and needs none).  With a workspace, networks / envs whose    *

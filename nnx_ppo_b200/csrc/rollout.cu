@@ -1146,10 +1146,16 @@ int rollout_mode() {
   return g_rollout_mode;
 }
 
-// B200PPO_ROLLOUT_MMA=1 selects the first tensor-core rollout kernel (two 16-env CTAs per SM, split on load)
-int rollout_mma_version() {
-  static const int v = [] { const char* e = std::getenv("B200PPO_ROLLOUT_MMA"); return e && std::atoi(e) == 1 ? 1 : 2; }();
-  return v;
+// Which tensor-core rollout kernel: 2 = one CTA per SM with two 16-env groups sharing the weights, 1 = one 16-env tile
+// per CTA (two CTAs per SM).  B200PPO_ROLLOUT_MMA=1|2 forces one; by default the second version runs when there are
+// more 16-env tiles than SMs (configs[1]: 256 tiles, 0.393 -> 0.362 ms) and the first when every tile can have an SM
+// of its own (configs[0] shapes, 64 tiles: 0.245 vs 0.278 ms).
+int g_rollout_mma_force = 0;        // b200ppo_set_rollout_mode(3 | 4)
+int rollout_mma_version(int n_envs) {
+  static const int v = [] { const char* e = std::getenv("B200PPO_ROLLOUT_MMA"); return e ? std::atoi(e) : 0; }();
+  if (g_rollout_mma_force) return g_rollout_mma_force;
+  if (v == 1 || v == 2) return v;
+  return cdiv(n_envs, TE) > b200ppo_num_sms() ? 2 : 1;
 }
 
 int check_plan(const b200ppo_plan* p) {
@@ -1273,7 +1279,7 @@ int rollout_synth_impl(void* stream, const b200ppo_plan* plan, const b200ppo_syn
       for (int l = 0; l < plan->actor.n_layers; ++l)
         f2 += frag_floats(plan->actor.dims[l], plan->actor.dims[l + 1]) + ((plan->actor.dims[l + 1] + 7) & ~7);
       f2 += frag_floats(O + A, O);
-      if (4 * f2 <= SMEM_LIMIT - 2048 && rollout_mma_version() == 2) {
+      if (4 * f2 <= SMEM_LIMIT - 2048 && rollout_mma_version(B) == 2) {
         cudaError_t e = cudaFuncSetAttribute(rollout_synth_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(4 * f2));
         if (e != cudaSuccess) return static_cast<int>(e);
         rollout_synth_mma2_kernel<<<cdiv(B, 2 * TE), NT2, 4 * f2, static_cast<cudaStream_t>(stream)>>>(a);
@@ -1368,7 +1374,8 @@ extern "C" int b200ppo_rollout_synth_ws(void* stream, const b200ppo_plan* plan, 
 
 extern "C" int b200ppo_set_rollout_mode(int mode) {
   const int prev = rollout_mode();
-  if (mode >= 0 && mode <= 2) g_rollout_mode = mode;
+  if (mode >= 0 && mode <= 2) { g_rollout_mode = mode; g_rollout_mma_force = 0; }
+  if (mode == 3 || mode == 4) { g_rollout_mode = 1; g_rollout_mma_force = mode - 2; }   // tensor cores, kernel version 1 / 2
   return prev;
 }
 

@@ -296,11 +296,12 @@ def test_env_reset_matches_oracle(dev):
                                   dict(O=21, A=5, ah=[100, 37, 64], ch=[16], B=50, T=12, max_len=8, thr=1500, act="tanh"),
                                   # tiles too wide for the k-split scratch tile: the unsplit path
                                   dict(O=900, A=4, ah=[32], ch=[16], B=20, T=5, max_len=8, thr=1500)])
-@pytest.mark.parametrize("engine", [1, 0, 2])
+@pytest.mark.parametrize("engine", [1, 0, 2, 3, 4])
 def test_fused_rollout_matches_oracle(dev, cfg, engine):
     """engine = 1: warp-level tensor-core tiles (mma.sync, 3xTF32; default), 0: fp32 FFMA tiles, 2: the batched
     per-step path (one tcgen05 tile GEMM per layer and step over all envs; the default beyond shared-memory-sized
-    networks, forced here for every shape)."""
+    networks, forced here for every shape), 3 / 4: the one-tile-per-CTA / two-groups-per-CTA tensor-core kernel forced
+    (mode 1 picks between them by the number of env tiles)."""
     prev = _lib.load().b200ppo_set_rollout_mode(engine)
     try:
         _fused_rollout(dev, cfg)

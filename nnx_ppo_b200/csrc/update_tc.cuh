@@ -6,7 +6,9 @@
 // x = hi + lo (both tf32): D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (3xTF32), measured at 2-4x the
 // error of a cuBLAS fp32 GEMM (tests/test_gpu_tensorcore.py).  Weights are split once per update
 // by upd_prep_w_kernel and reach shared memory with cp.async.bulk; activations / gradients are
-// split while they are staged.
+// split while they are staged.  The weight-gradient kernel (dW = H^T D, reduction over the rows of two
+// row-major matrices) instead takes both operands MN-major, straight from swizzled TMA boxes with the hi
+// half of the split = the tile as it landed (see upd_bwd_dw_tc2_kernel and tc.cuh).
 //
 // Warp-specialised pipeline over a 4-deep shared-memory ring of 16-k stages (no __syncthreads in
 // the main loop; all hand-offs are mbarriers):

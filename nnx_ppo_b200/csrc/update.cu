@@ -154,59 +154,63 @@ Layout make_layout(const b200ppo_plan& p, int T, int mb) {
       L.tc_tiles += cdiv(K, 128);
     }
   }
-  {
-    double wsum = 0.0;
+  // Row splits of the dW items.  `mn_on`: the operand path the cost table is for (b200ppo_set_update_paths); the table
+  // of the OTHER setting is computed too, only for its largest split count: the partial-gradient buffer is sized for
+  // both, so that flipping the switch on a live workspace can never overrun it.
+  auto dw_splits = [&](bool mn_on, int* item_S, int* item_rps) {
     double wts[32];
     int ni = 0;
     for (int c = 0; c < 2; ++c) {
       const b200ppo_chain& ch = c == 0 ? p.actor : p.critic;
       for (int l = 0; l < ch.n_layers; ++l)
         for (int m = 0; m < cdiv(ch.dims[l], 128) && ni < 32; ++m) {
-          // relative cost of one 16-row stage of the item: wide operands are tensor bound, thin ones (the value
-          // head: N padded to 16) move a fraction of the bytes.  B200PPO_DW_WTS="thin,wide" overrides (tuning aid).
-          const bool mn = dw_mn_enabled() && !(ch.dims[l] & 3) && !(ch.dims[l + 1] & 3) && ch.dims[l + 1] <= dw_mn_maxn();
+          // relative cost of one 16-row stage of the item (table above g_dw_wt_thin)
+          const bool mn = mn_on && !(ch.dims[l] & 3) && !(ch.dims[l + 1] & 3) && ch.dims[l + 1] <= dw_mn_maxn();
           const int n32 = (ch.dims[l + 1] + 31) / 32;
           const int kw_m = ch.dims[l] - m * 128 < 128 ? ch.dims[l] - m * 128 : 128;
           const double w_mn = n32 <= 1 ? 0.95 : (n32 == 2 ? 1.0 : (n32 <= 4 ? 1.33 : (kw_m <= 64 ? 1.85 : 2.05)));
-          wts[ni] = mn ? w_mn : (ch.dims[l + 1] > 128 ? g_dw_wt_wide : g_dw_wt_thin);
-          wsum += wts[ni++];
+          wts[ni++] = mn ? w_mn : (ch.dims[l + 1] > 128 ? g_dw_wt_wide : g_dw_wt_thin);
         }
     }
-    if (L.tc_tiles > 32) L.tc_ok = 0;
-    L.tc_S = 1;
     // greedy minimax: every item starts with one split; the item whose CTAs are the most expensive (cost per stage
     // x rows per split, rows in multiples of 32) gets the next one until the SMs are used up (one CTA per SM)
-    (void)wsum;
     int Ssum = 0;
     for (int i = 0; i < ni; ++i) {
-      L.tc_item_S[i] = 1;
-      L.tc_item_rps[i] = cdiv(L.R, 32) * 32;
+      item_S[i] = 1;
+      item_rps[i] = cdiv(L.R, 32) * 32;
       ++Ssum;
     }
     while (Ssum < sms) {
       int worst = -1;
       double wc = -1.0;
       for (int i = 0; i < ni; ++i) {
-        const double c = wts[i] * L.tc_item_rps[i];
-        if (c > wc && L.tc_item_S[i] < 64 && L.tc_item_rps[i] > 32) { wc = c; worst = i; }
+        const double c = wts[i] * item_rps[i];
+        if (c > wc && item_S[i] < 64 && item_rps[i] > 32) { wc = c; worst = i; }
       }
       if (worst < 0) break;
       // the next split count that actually shortens the item's rows per split
-      int Sn = L.tc_item_S[worst] + 1, rps_n = L.tc_item_rps[worst];
-      while (Sn <= 64 && (rps_n = cdiv(cdiv(L.R, Sn), 32) * 32) >= L.tc_item_rps[worst]) ++Sn;
+      int Sn = item_S[worst] + 1, rps_n = item_rps[worst];
+      while (Sn <= 64 && (rps_n = cdiv(cdiv(L.R, Sn), 32) * 32) >= item_rps[worst]) ++Sn;
       if (Sn > 64) break;
       const int S_real = cdiv(L.R, rps_n);
-      if (Ssum - L.tc_item_S[worst] + S_real > sms) break;
-      Ssum += S_real - L.tc_item_S[worst];
-      L.tc_item_S[worst] = S_real;
-      L.tc_item_rps[worst] = rps_n;
+      if (Ssum - item_S[worst] + S_real > sms) break;
+      Ssum += S_real - item_S[worst];
+      item_S[worst] = S_real;
+      item_rps[worst] = rps_n;
     }
+    int smx = 1;
     for (int i = 0; i < ni; ++i)
-      if (L.tc_item_S[i] > L.tc_S) L.tc_S = L.tc_item_S[i];
-    for (int i = ni; i < 32; ++i) { L.tc_item_S[i] = 0; L.tc_item_rps[i] = 32; }
-    L.tc_rows_per_split = L.tc_item_rps[0];
-  }
-  const int smax = L.tc_S > S ? L.tc_S : S;
+      if (item_S[i] > smx) smx = item_S[i];
+    for (int i = ni; i < 32; ++i) { item_S[i] = 0; item_rps[i] = 32; }
+    return smx;
+  };
+  if (L.tc_tiles > 32) L.tc_ok = 0;
+  L.tc_S = dw_splits(dw_mn_enabled(), L.tc_item_S, L.tc_item_rps);
+  L.tc_rows_per_split = L.tc_item_rps[0];
+  int other_S[32], other_rps[32];
+  const int tc_S_other = dw_splits(!dw_mn_enabled(), other_S, other_rps);
+  const int tc_S_cap = L.tc_S > tc_S_other ? L.tc_S : tc_S_other;
+  const int smax = tc_S_cap > S ? tc_S_cap : S;
   L.gpart = take(static_cast<size_t>(smax) * p.n_params);
   L.grad = take(p.n_params);
   take(16 * 256);                                           // slack: dW v2 copies whole 16-row blocks

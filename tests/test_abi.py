@@ -379,3 +379,26 @@ def test_dw_row_split_table_is_a_one_wave_cover(lib):
         narrow = [rps[i] for i in range(n) if dims[i][1] == 64 and dims[i][0] % 4 == 0]
         if wide and narrow:
             assert max(wide) < min(narrow), (name, wide, narrow)
+
+
+def test_workspace_size_does_not_depend_on_the_kernel_structure_switches(lib):
+    """b200ppo_set_update_paths changes the weight-gradient kernel's row-split table (host-only here); the partial-
+    gradient buffer is sized for both tables, so flipping the switch on a live workspace cannot overrun it."""
+    import torch
+    from nnx_ppo_b200.networks.plan import CompiledNet
+    nets = factories.make_mlp_actor_critic(64, 8, [64] * 4, [256] * 2, prng.Rngs(0))
+    net = CompiledNet(nets, torch.device("cpu"))
+    prev = lib.b200ppo_set_update_paths(-1, -1)
+    try:
+        sizes, tables = [], []
+        for mn in (1, 0):
+            lib.b200ppo_set_update_paths(-1, mn)
+            sizes.append(int(lib.b200ppo_update_workspace_bytes(net.plan, 32, 512)))
+            S = (ctypes.c_int32 * 32)()
+            rps = (ctypes.c_int32 * 32)()
+            n = int(lib.b200ppo_update_dw_splits(net.plan, 32, 512, S, rps, 32))
+            tables.append(list(S[:n]))
+        assert sizes[0] == sizes[1]
+        assert tables[0] != tables[1]          # the tables themselves do differ (different per-stage costs)
+    finally:
+        lib.b200ppo_set_update_paths(prev & 1, (prev >> 1) & 1)
